@@ -1,0 +1,191 @@
+// ref_shim.cpp -- thin extern "C" door onto the UNMODIFIED reference header.
+//
+// TEST / BASELINE INFRASTRUCTURE ONLY.  Compiled by oracle/Makefile from the
+// reference sources where they lie (CPPRCODER_H, default /root/reference/cpprcoder.h;
+// nothing is copied into this repository) into oracle/_ref/libcpprcoder_ref.so,
+// which is git-ignored and travels to the GPU box as a built artefact.  It is
+// used to (a) validate oracle/rc_oracle.c, (b) generate tests/golden/, and
+// (c) time the reference's own CPU coder for bench.py's cpu_baseline and
+// `--impl reference` legs.  The product library never links it.
+//
+// Per-block calls follow how the reference harness drives the coder:
+// run_rangecoder (test/main.cpp:254-301) and run_adaptive (test/main.cpp:305-363).
+#define CPPRCODER_IMPLEMENTATION
+#include CPPRCODER_H
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace
+{
+using namespace cpprcoder;
+
+// MemoryStream::writeByte never grows (cpprcoder.h:1047-1054), so the stream is
+// pre-sized to the caller's slot, as the harness pre-sizes it to the input size.
+long encode_one(int mode, const u8* src, u32 n, u8* dst, size_t cap, MemoryStream& scratch)
+{
+    scratch.resize(0);
+    if(mode == 0) {
+        RangeEncoder<> coder;
+        if(!coder.encode(scratch, n, src)) {
+            return -1;
+        }
+    } else {
+        AdaptiveRangeEncoder<> coder;
+        if(!coder.initialize(scratch, n)) {
+            return -1;
+        }
+        if(n == 0) {
+            // encode(0, ...) reaches finish() immediately (cpprcoder.h:714-717)
+        }
+        Result r = coder.encode(static_cast<s32>(n), src);
+        if(r.status_ != Status_Success) {
+            return -1;
+        }
+    }
+    const size_t got = static_cast<size_t>(scratch.size());
+    if(got > cap) {
+        return -1;
+    }
+    memcpy(dst, scratch.get(), got);
+    return static_cast<long>(got);
+}
+
+long decode_one(int mode, const u8* src, size_t n, u8* dst, size_t cap, MemoryStream& scratch)
+{
+    scratch.resize(0);
+    if(mode == 0) {
+        RangeEncoder<> coder;
+        if(!coder.decode(scratch, static_cast<u32>(n), src)) {
+            return -1;
+        }
+    } else {
+        AdaptiveRangeDecoder<> coder;
+        if(!coder.initialize(scratch)) {
+            return -1;
+        }
+        Result r = coder.decode(static_cast<s32>(n), src);
+        if(r.status_ != Status_Success) {
+            return -1;
+        }
+    }
+    const size_t got = static_cast<size_t>(scratch.size());
+    if(got > cap) {
+        return -1;
+    }
+    memcpy(dst, scratch.get(), got);
+    return static_cast<long>(got);
+}
+
+size_t slot_for(u32 n)
+{
+    size_t s = static_cast<size_t>(n) + n / 8 + 1024;
+    return (s + 127) & ~static_cast<size_t>(127);
+}
+} // namespace
+
+extern "C" {
+
+long ref_encode(int mode, const uint8_t* src, uint32_t n, uint8_t* dst, size_t cap)
+{
+    cpprcoder::MemoryStream scratch(static_cast<cpprcoder::s32>(cap));
+    static const uint8_t nothing = 0;
+    return encode_one(mode, src ? src : &nothing, n, dst, cap, scratch);
+}
+
+long ref_decode(int mode, const uint8_t* src, size_t n, uint8_t* dst, size_t cap)
+{
+    cpprcoder::MemoryStream scratch(static_cast<cpprcoder::s32>(cap ? cap : 16));
+    return decode_one(mode, src, n, dst, cap, scratch);
+}
+
+// Block-parallel std::thread drivers: workers pull block
+// indices from an atomic counter; each owns one pre-allocated MemoryStream so no
+// allocation happens inside the timed loop.
+int ref_encode_blocks(int mode, const uint8_t* src, uint64_t n, uint32_t block, uint8_t* slots, uint64_t slot_stride,
+                      uint32_t* sizes, int threads)
+{
+    if(block == 0) {
+        return -1;
+    }
+    const uint64_t nblocks = (n + block - 1) / block;
+    std::atomic<uint64_t> next(0);
+    std::atomic<int> failed(0);
+    auto body = [&]() {
+        cpprcoder::MemoryStream scratch(static_cast<cpprcoder::s32>(slot_for(block)));
+        for(;;) {
+            const uint64_t b = next.fetch_add(1);
+            if(b >= nblocks) {
+                break;
+            }
+            const uint64_t at = b * static_cast<uint64_t>(block);
+            const uint32_t len = static_cast<uint32_t>((n - at < block) ? (n - at) : block);
+            const long r = encode_one(mode, src + at, len, slots + b * slot_stride, slot_stride, scratch);
+            if(r < 0) {
+                failed = 1;
+            } else {
+                sizes[b] = static_cast<uint32_t>(r);
+            }
+        }
+    };
+    if(threads <= 1) {
+        body();
+    } else {
+        std::vector<std::thread> pool;
+        for(int i = 0; i < threads; ++i) {
+            pool.emplace_back(body);
+        }
+        for(auto& t : pool) {
+            t.join();
+        }
+    }
+    return failed ? -1 : 0;
+}
+
+int ref_decode_blocks(int mode, const uint8_t* stream, const uint64_t* offsets, uint64_t nblocks, uint32_t block,
+                      uint8_t* dst, uint64_t n, int threads)
+{
+    if(block == 0 || nblocks != (n + block - 1) / block) {
+        return -1;
+    }
+    std::atomic<uint64_t> next(0);
+    std::atomic<int> failed(0);
+    auto body = [&]() {
+        cpprcoder::MemoryStream scratch(static_cast<cpprcoder::s32>(block + 16));
+        for(;;) {
+            const uint64_t b = next.fetch_add(1);
+            if(b >= nblocks) {
+                break;
+            }
+            const uint64_t at = b * static_cast<uint64_t>(block);
+            const uint32_t len = static_cast<uint32_t>((n - at < block) ? (n - at) : block);
+            const long r = decode_one(mode, stream + offsets[b], static_cast<size_t>(offsets[b + 1] - offsets[b]),
+                                      dst + at, len, scratch);
+            if(r != static_cast<long>(len)) {
+                failed = 1;
+            }
+        }
+    };
+    if(threads <= 1) {
+        body();
+    } else {
+        std::vector<std::thread> pool;
+        for(int i = 0; i < threads; ++i) {
+            pool.emplace_back(body);
+        }
+        for(auto& t : pool) {
+            t.join();
+        }
+    }
+    return failed ? -1 : 0;
+}
+
+int ref_hardware_threads(void)
+{
+    const unsigned h = std::thread::hardware_concurrency();
+    return h ? static_cast<int>(h) : 1;
+}
+}
