@@ -1,0 +1,71 @@
+"""ctypes binding of libb2rc.so (include/b2rc.h).  There is no fallback: a missing
+library is an error, and every coding call needs a CUDA device."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+SO = PKG / "libb2rc.so"
+
+OK, E_ARG, E_DST_SMALL, E_CORRUPT, E_CUDA, E_EXPAND, E_NOMEM = 0, -1, -2, -3, -4, -5, -6
+MODE_STATIC, MODE_ADAPTIVE = 0, 1
+HEADER_BYTES = 32
+DEFAULT_BLOCK = 65536
+
+_P = C.c_void_p
+_U64 = C.c_uint64
+_U32 = C.c_uint32
+
+# name -> (restype, argtypes); mirrors include/b2rc.h one to one
+SIGNATURES = {
+    "b2rc_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "b2rc_ctx_destroy": (None, [_P]),
+    "b2rc_strerror": (C.c_char_p, [C.c_int]),
+    "b2rc_last_cuda_error": (C.c_char_p, [_P]),
+    "b2rc_bound": (_U64, [C.c_int, _U64, _U32]),
+    "b2rc_slot_bytes": (_U64, [_U32]),
+    "b2rc_nblocks": (_U64, [_U64, _U32]),
+    "b2rc_encode": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, C.POINTER(_U64)]),
+    "b2rc_decode": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64)]),
+    "b2rc_peek": (C.c_int, [_P, _U64, C.POINTER(C.c_int), C.POINTER(_U32), C.POINTER(_U64), C.POINTER(_U64)]),
+    "b2rc_encode_device": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
+    "b2rc_decode_device": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
+    "b2rc_k_histogram": (C.c_int, [_P, _P, _U64, _U32, _P, _P]),
+    "b2rc_k_encode_blocks": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _P, _U64, _P, _P, _P]),
+    "b2rc_k_scan": (C.c_int, [_P, _P, _U64, _P, _P]),
+    "b2rc_k_compact": (C.c_int, [_P, _P, _U64, _P, _P, _U64, _P, _U64, _P, _P]),
+    "b2rc_k_decode_blocks": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, _P, _U64, _P, _P]),
+    "b2rc_launch_count": (_U64, [_P]),
+    "b2rc_build_arch": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+class B2rcError(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str = ""):
+        self.code = code
+        msg = f"{what}: {strerror(code)} ({code})"
+        if detail:
+            msg += f" [{detail}]"
+        super().__init__(msg)
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not SO.exists():
+            raise RuntimeError(f"{SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback for the coder)")
+        lib = C.CDLL(str(SO))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def strerror(code: int) -> str:
+    return load().b2rc_strerror(code).decode()

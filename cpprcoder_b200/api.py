@@ -1,0 +1,166 @@
+"""Python face of the C ABI: torch owns device memory and streams, libb2rc.so does the work.
+
+Every function here ends in a kernel launch inside libb2rc.so; nothing is coded in
+Python or on the CPU.  Names follow include/b2rc.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B2rcError, MODE_ADAPTIVE, MODE_STATIC  # noqa: F401
+
+DEFAULT_BLOCK = _lib.DEFAULT_BLOCK
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def bound(mode: int, n: int, block: int = DEFAULT_BLOCK) -> int:
+    return int(_lib.load().b2rc_bound(mode, n, block))
+
+
+def slot_bytes(n: int) -> int:
+    return int(_lib.load().b2rc_slot_bytes(n))
+
+
+def nblocks(n: int, block: int) -> int:
+    return int(_lib.load().b2rc_nblocks(n, block))
+
+
+class Context:
+    """b2rc_ctx: one per host thread and device."""
+
+    def __init__(self, device: int | None = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("cpprcoder_b200 needs a CUDA device: there is no CPU coding path")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        rc = self.lib.b2rc_ctx_create(self.device, C.byref(h))
+        if rc != _lib.OK:
+            raise B2rcError(rc, "b2rc_ctx_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2rc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != _lib.OK:
+            raise B2rcError(rc, what, self.lib.b2rc_last_cuda_error(self.h).decode())
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.b2rc_launch_count(self.h))
+
+    # ---- whole container, device memory ------------------------------------
+    def encode_device(self, mode: int, src: torch.Tensor, dst: torch.Tensor | None = None,
+                      block: int = DEFAULT_BLOCK) -> tuple[torch.Tensor, int]:
+        """src: uint8 CUDA tensor.  Returns (dst, bytes used)."""
+        n = src.numel()
+        if dst is None:
+            dst = torch.empty(bound(mode, n, block), dtype=torch.uint8, device=src.device)
+        out_n = C.c_uint64(0)
+        rc = self.lib.b2rc_encode_device(self.h, mode, block, _ptr(src), n, _ptr(dst), dst.numel(), C.byref(out_n),
+                                         _stream())
+        self._check(rc, "b2rc_encode_device")
+        return dst, int(out_n.value)
+
+    def decode_device(self, src: torch.Tensor, n_src: int, dst: torch.Tensor) -> int:
+        out_n = C.c_uint64(0)
+        rc = self.lib.b2rc_decode_device(self.h, _ptr(src), n_src, _ptr(dst), dst.numel(), C.byref(out_n), _stream())
+        self._check(rc, "b2rc_decode_device")
+        return int(out_n.value)
+
+    # ---- whole container, host memory (the call the C++ drop-in classes make) ---
+    def encode(self, mode: int, src, block: int = DEFAULT_BLOCK, dst: np.ndarray | None = None) -> np.ndarray:
+        src = np.ascontiguousarray(np.frombuffer(src, dtype=np.uint8) if isinstance(src, (bytes, bytearray)) else src,
+                                   dtype=np.uint8)
+        if dst is None:
+            dst = np.empty(bound(mode, src.size, block), dtype=np.uint8)
+        out_n = C.c_uint64(0)
+        rc = self.lib.b2rc_encode(self.h, mode, block, src.ctypes.data_as(C.c_void_p), src.size,
+                                  dst.ctypes.data_as(C.c_void_p), dst.size, C.byref(out_n))
+        self._check(rc, "b2rc_encode")
+        return dst[:int(out_n.value)]
+
+    def decode(self, src, dst: np.ndarray | None = None) -> np.ndarray:
+        src = np.ascontiguousarray(np.frombuffer(src, dtype=np.uint8) if isinstance(src, (bytes, bytearray)) else src,
+                                   dtype=np.uint8)
+        mode, block, total, nb = self.peek(src)
+        if dst is None:
+            dst = np.empty(max(total, 1), dtype=np.uint8)
+        out_n = C.c_uint64(0)
+        rc = self.lib.b2rc_decode(self.h, src.ctypes.data_as(C.c_void_p), src.size, dst.ctypes.data_as(C.c_void_p),
+                                  dst.size, C.byref(out_n))
+        self._check(rc, "b2rc_decode")
+        return dst[:int(out_n.value)]
+
+    def peek(self, src: np.ndarray):
+        mode, block, total, nb = C.c_int(0), C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.b2rc_peek(src.ctypes.data_as(C.c_void_p), src.size, C.byref(mode), C.byref(block),
+                                C.byref(total), C.byref(nb))
+        self._check(rc, "b2rc_peek")
+        return mode.value, block.value, total.value, nb.value
+
+    # ---- per-kernel doors -----------------------------------------------------
+    def histogram(self, src: torch.Tensor, block: int, freq16: torch.Tensor | None = None) -> torch.Tensor:
+        nb = nblocks(src.numel(), block)
+        if freq16 is None:
+            freq16 = torch.empty((max(nb, 1), 256), dtype=torch.int16, device=src.device)
+        self._check(self.lib.b2rc_k_histogram(self.h, _ptr(src), src.numel(), block, _ptr(freq16), _stream()),
+                    "b2rc_k_histogram")
+        return freq16
+
+    def encode_blocks(self, mode: int, src: torch.Tensor, block: int = DEFAULT_BLOCK, freq16=None, slots=None,
+                      sizes=None, err=None):
+        """K1 (when needed) + K2.  Returns (slots, slot_stride, sizes, err)."""
+        n = src.numel()
+        nb = nblocks(n, block)
+        stride = slot_bytes(block)
+        dev = src.device
+        if slots is None:
+            slots = torch.empty(max(nb, 1) * stride, dtype=torch.uint8, device=dev)
+        if sizes is None:
+            sizes = torch.zeros(max(nb, 1), dtype=torch.int32, device=dev)
+        if err is None:
+            err = torch.zeros(4, dtype=torch.int32, device=dev)
+        if mode == MODE_STATIC and block <= 65536 and freq16 is None:
+            freq16 = self.histogram(src, block)
+        self._check(self.lib.b2rc_k_encode_blocks(self.h, mode, block, _ptr(src), n, _ptr(freq16), _ptr(slots), stride,
+                                                  _ptr(sizes), _ptr(err), _stream()), "b2rc_k_encode_blocks")
+        return slots, stride, sizes, err
+
+    def scan(self, sizes: torch.Tensor, nb: int, offsets: torch.Tensor | None = None) -> torch.Tensor:
+        if offsets is None:
+            offsets = torch.empty(nb + 1, dtype=torch.int64, device=sizes.device)
+        self._check(self.lib.b2rc_k_scan(self.h, _ptr(sizes), nb, _ptr(offsets), _stream()), "b2rc_k_scan")
+        return offsets
+
+    def compact(self, slots, stride, sizes, offsets, nb, payload: torch.Tensor, err: torch.Tensor):
+        self._check(self.lib.b2rc_k_compact(self.h, _ptr(slots), stride, _ptr(sizes), _ptr(offsets), nb, _ptr(payload),
+                                            payload.numel(), _ptr(err), _stream()), "b2rc_k_compact")
+
+    def decode_blocks(self, mode: int, payload: torch.Tensor, payload_len: int, offsets: torch.Tensor, nb: int,
+                      dst: torch.Tensor, n: int, block: int = DEFAULT_BLOCK, err: torch.Tensor | None = None):
+        if err is None:
+            err = torch.zeros(4, dtype=torch.int32, device=dst.device)
+        self._check(self.lib.b2rc_k_decode_blocks(self.h, mode, block, _ptr(payload), payload_len, _ptr(offsets), nb,
+                                                  _ptr(dst), n, _ptr(err), _stream()), "b2rc_k_decode_blocks")
+        return err

@@ -1,0 +1,656 @@
+// b2rc.cu -- the extern "C" layer of libb2rc.so (declared in include/b2rc.h).
+//
+// Host side of the drop-in boundary: argument checking, device scratch, kernel
+// launches, the B2RC container.  No torch types, no CPU coding path: every call
+// that codes bytes launches the sm_100a kernels in b2rc_kernels.cuh.
+#include "../../include/b2rc.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "b2rc_kernels.cuh"
+
+using namespace b2rc;
+
+struct b2rc_ctx {
+    int device;
+    cudaStream_t stream;
+    // device scratch, grown on demand
+    u8* slots;
+    size_t slots_cap;
+    u32* sizes;
+    size_t sizes_cap;
+    u16* freq16;
+    size_t freq_cap;
+    u8* stage_in;
+    size_t stage_in_cap;
+    u8* stage_out;
+    size_t stage_out_cap;
+    int* d_err;
+    u64* d_total;
+    struct Result {
+        int err;
+        int pad;
+        u64 total;
+        u8 header[B2RC_HEADER_BYTES];
+    } * h_res;  // pinned
+    u64 launches;
+    char last_err[256];
+};
+
+namespace
+{
+bool cuda_ok(b2rc_ctx* c, cudaError_t e, const char* what)
+{
+    if(e == cudaSuccess) {
+        return true;
+    }
+    if(c) {
+        snprintf(c->last_err, sizeof c->last_err, "%s: %s", what, cudaGetErrorString(e));
+    }
+    cudaGetLastError();
+    return false;
+}
+#define CK(call)                          \
+    do {                                  \
+        if(!cuda_ok(ctx, (call), #call)) { \
+            return B2RC_E_CUDA;           \
+        }                                 \
+    } while(0)
+
+template <class T>
+int grow(b2rc_ctx* ctx, T*& p, size_t& cap, size_t want_bytes)
+{
+    if(want_bytes <= cap) {
+        return B2RC_OK;
+    }
+    if(p) {
+        CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+    }
+    size_t bytes = want_bytes + want_bytes / 8 + 4096;
+    void* q = nullptr;
+    if(!cuda_ok(ctx, cudaMalloc(&q, bytes), "cudaMalloc")) {
+        bytes = want_bytes;
+        if(!cuda_ok(ctx, cudaMalloc(&q, bytes), "cudaMalloc")) {
+            return B2RC_E_NOMEM;
+        }
+    }
+    p = static_cast<T*>(q);
+    cap = bytes;
+    return B2RC_OK;
+}
+
+bool block_ok(u32 block)
+{
+    return block >= B2RC_MIN_BLOCK && block <= B2RC_MAX_BLOCK && (block % 64u) == 0;
+}
+bool aligned16(const void* p)
+{
+    return ((uintptr_t)p & 15u) == 0;
+}
+u64 index_bytes(u64 nblocks)
+{
+    return (u64)B2RC_HEADER_BYTES + 8ull * (nblocks + 1);
+}
+
+// dynamic shared memory of the coder kernels (one warp per CTA)
+constexpr u32 smem_enc_static(bool wide)
+{
+    return (wide ? 257u : 256u) * 128u + 2u * TILE_BYTES + RING_BYTES;
+}
+constexpr u32 smem_enc_adaptive(bool wide)
+{
+    return 512u * 32u * (wide ? 4u : 2u) + 2u * TILE_BYTES + RING_BYTES;
+}
+constexpr u32 smem_dec_static(bool wide)
+{
+    return (wide ? 257u : 256u) * 128u + TILE_BYTES + RING_BYTES;
+}
+constexpr u32 smem_dec_adaptive(bool wide)
+{
+    return 512u * 32u * (wide ? 4u : 2u) + TILE_BYTES + RING_BYTES;
+}
+
+int set_smem_limits(b2rc_ctx* ctx)
+{
+    CK(cudaFuncSetAttribute(k_enc_static<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_static(false)));
+    CK(cudaFuncSetAttribute(k_enc_static<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_static(true)));
+    CK(cudaFuncSetAttribute(k_enc_adaptive<u16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_adaptive(false)));
+    CK(cudaFuncSetAttribute(k_enc_adaptive<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_adaptive(true)));
+    CK(cudaFuncSetAttribute(k_dec_static<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static(false)));
+    CK(cudaFuncSetAttribute(k_dec_static<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static(true)));
+    CK(cudaFuncSetAttribute(k_dec_adaptive<u16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(false)));
+    CK(cudaFuncSetAttribute(k_dec_adaptive<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
+    return B2RC_OK;
+}
+
+int launch_check(b2rc_ctx* ctx, const char* what)
+{
+    ctx->launches += 1;
+    return cuda_ok(ctx, cudaGetLastError(), what) ? B2RC_OK : B2RC_E_CUDA;
+}
+
+int map_kernel_err(int bits)
+{
+    if(bits & ERR_CORRUPT) {
+        return B2RC_E_CORRUPT;
+    }
+    if(bits & ERR_SLOT_OVERFLOW) {
+        return B2RC_E_EXPAND;
+    }
+    if(bits & ERR_DST_SMALL) {
+        return B2RC_E_DST_SMALL;
+    }
+    return B2RC_OK;
+}
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(0), ok(false)
+    {
+        if(cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) {
+            ok = true;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if(ok) {
+            cudaSetDevice(prev);
+        }
+    }
+};
+}  // namespace
+
+extern "C" {
+
+const char* b2rc_build_arch(void)
+{
+    return "sm_100a";
+}
+
+const char* b2rc_strerror(int code)
+{
+    switch(code) {
+    case B2RC_OK: return "ok";
+    case B2RC_E_ARG: return "bad argument";
+    case B2RC_E_DST_SMALL: return "destination too small";
+    case B2RC_E_CORRUPT: return "corrupt container or payload";
+    case B2RC_E_CUDA: return "CUDA error or no device";
+    case B2RC_E_EXPAND: return "payload outgrew its staging slot";
+    case B2RC_E_NOMEM: return "out of device memory";
+    default: return "unknown";
+    }
+}
+
+uint64_t b2rc_slot_bytes(uint32_t n)
+{
+    const u64 s = (u64)n + n / 8 + 1024;
+    return (s + 127) & ~127ull;
+}
+
+uint64_t b2rc_nblocks(uint64_t n, uint32_t block_size)
+{
+    return block_size ? (n + block_size - 1) / block_size : 0;
+}
+
+uint64_t b2rc_bound(int mode, uint64_t n, uint32_t block_size)
+{
+    (void)mode;
+    if(!block_ok(block_size)) {
+        return 0;
+    }
+    const u64 nb = b2rc_nblocks(n, block_size);
+    if(nb == 0) {
+        return index_bytes(0);
+    }
+    const u64 last = n - (nb - 1) * block_size;
+    return index_bytes(nb) + (nb - 1) * b2rc_slot_bytes(block_size) + b2rc_slot_bytes((u32)last);
+}
+
+int b2rc_ctx_create(int device, b2rc_ctx** out)
+{
+    if(!out) {
+        return B2RC_E_ARG;
+    }
+    *out = nullptr;
+    int count = 0;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return B2RC_E_CUDA;  // no CPU fallback, by design
+    }
+    DeviceGuard g(device);
+    if(!g.ok) {
+        return B2RC_E_CUDA;
+    }
+    b2rc_ctx* ctx = new(std::nothrow) b2rc_ctx();
+    if(!ctx) {
+        return B2RC_E_NOMEM;
+    }
+    memset(ctx, 0, sizeof *ctx);
+    ctx->device = device;
+    int rc = B2RC_OK;
+    do {
+        if(!cuda_ok(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+            rc = B2RC_E_CUDA;
+            break;
+        }
+        if(!cuda_ok(ctx, cudaMalloc((void**)&ctx->d_err, 16), "cudaMalloc") ||
+           !cuda_ok(ctx, cudaMalloc((void**)&ctx->d_total, 16), "cudaMalloc") ||
+           !cuda_ok(ctx, cudaMallocHost((void**)&ctx->h_res, sizeof(b2rc_ctx::Result)), "cudaMallocHost")) {
+            rc = B2RC_E_CUDA;
+            break;
+        }
+        rc = set_smem_limits(ctx);
+    } while(0);
+    if(rc != B2RC_OK) {
+        fprintf(stderr, "b2rc_ctx_create: %s\n", ctx->last_err);
+        b2rc_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return B2RC_OK;
+}
+
+void b2rc_ctx_destroy(b2rc_ctx* ctx)
+{
+    if(!ctx) {
+        return;
+    }
+    DeviceGuard g(ctx->device);
+    if(ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(ctx->slots);
+    cudaFree(ctx->sizes);
+    cudaFree(ctx->freq16);
+    cudaFree(ctx->stage_in);
+    cudaFree(ctx->stage_out);
+    cudaFree(ctx->d_err);
+    cudaFree(ctx->d_total);
+    if(ctx->h_res) {
+        cudaFreeHost(ctx->h_res);
+    }
+    if(ctx->stream) {
+        cudaStreamDestroy(ctx->stream);
+    }
+    cudaGetLastError();
+    delete ctx;
+}
+
+const char* b2rc_last_cuda_error(const b2rc_ctx* ctx)
+{
+    return ctx ? ctx->last_err : "";
+}
+
+uint64_t b2rc_launch_count(const b2rc_ctx* ctx)
+{
+    return ctx ? ctx->launches : 0;
+}
+
+int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, uint64_t* total, uint64_t* nblocks)
+{
+    if(!src) {
+        return B2RC_E_ARG;
+    }
+    if(n < B2RC_HEADER_BYTES + 8) {
+        return B2RC_E_CORRUPT;
+    }
+    u32 h[8];
+    memcpy(h, src, sizeof h);
+    const u32 version = h[1] & 0xFFFFu, md = h[1] >> 16;
+    const u64 tot = (u64)h[4] | ((u64)h[5] << 32), nb = (u64)h[6] | ((u64)h[7] << 32);
+    if(h[0] != 0x43523242u || version != 1u || md > 1u || !block_ok(h[2]) || h[3] != 0u) {
+        return B2RC_E_CORRUPT;
+    }
+    if(nb != b2rc_nblocks(tot, h[2]) || nb > (n - B2RC_HEADER_BYTES) / 8 - 1) {
+        return B2RC_E_CORRUPT;
+    }
+    if(mode) {
+        *mode = (int)md;
+    }
+    if(block_size) {
+        *block_size = h[2];
+    }
+    if(total) {
+        *total = tot;
+    }
+    if(nblocks) {
+        *nblocks = nb;
+    }
+    return B2RC_OK;
+}
+
+// ------------------------------------------------------------ kernel doors --
+int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t block_size, uint16_t* d_freq16,
+                     void* cuda_stream)
+{
+    if(!ctx || !d_src || !d_freq16 || !block_ok(block_size) || block_size > 65536u || !aligned16(d_src) ||
+       !aligned16(d_freq16)) {
+        return B2RC_E_ARG;
+    }
+    const u64 nb = b2rc_nblocks(n, block_size);
+    if(nb == 0) {
+        return B2RC_OK;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    u64 grid = (nb + HIST_WARPS - 1) / HIST_WARPS;
+    if(grid > 148ull * 16) {
+        grid = 148ull * 16;
+    }
+    k_hist<<<(unsigned)grid, HIST_WARPS * 32, 0, st>>>(d_src, n, block_size, nb, d_freq16);
+    return launch_check(ctx, "k_hist");
+}
+
+int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
+                         const uint16_t* d_freq16, uint8_t* d_slots, uint64_t slot_stride, uint32_t* d_sizes,
+                         int* d_err, void* cuda_stream)
+{
+    if(!ctx || !d_src || !d_slots || !d_sizes || !d_err || (mode != B2RC_MODE_STATIC && mode != B2RC_MODE_ADAPTIVE) ||
+       !block_ok(block_size) || !aligned16(d_src) || !aligned16(d_slots) || (slot_stride & 15u) ||
+       slot_stride < b2rc_slot_bytes(block_size)) {
+        return B2RC_E_ARG;
+    }
+    const bool wide = block_size > 65536u;
+    if(mode == B2RC_MODE_STATIC && !wide && (!d_freq16 || !aligned16(d_freq16))) {
+        return B2RC_E_ARG;
+    }
+    const u64 nb = b2rc_nblocks(n, block_size);
+    if(nb == 0) {
+        return B2RC_OK;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    EncArgs a;
+    a.src = d_src;
+    a.n = n;
+    a.block = block_size;
+    a.nblocks = nb;
+    a.freq16 = d_freq16;
+    a.slots = d_slots;
+    a.slot_stride = slot_stride;
+    a.sizes = d_sizes;
+    a.err = d_err;
+    const unsigned grid = (unsigned)((nb + 31) / 32);
+    if(mode == B2RC_MODE_STATIC) {
+        if(wide) {
+            k_enc_static<true><<<grid, 32, smem_enc_static(true), st>>>(a);
+        } else {
+            k_enc_static<false><<<grid, 32, smem_enc_static(false), st>>>(a);
+        }
+    } else {
+        if(wide) {
+            k_enc_adaptive<u32><<<grid, 32, smem_enc_adaptive(true), st>>>(a);
+        } else {
+            k_enc_adaptive<u16><<<grid, 32, smem_enc_adaptive(false), st>>>(a);
+        }
+    }
+    return launch_check(ctx, "k_enc");
+}
+
+static int scan_launch(b2rc_ctx* ctx, const u32* d_sizes, u64 nb, u64* d_offsets, u64* d_total, u8* d_header, u32 mode,
+                       u32 block, u64 n, cudaStream_t st)
+{
+    k_scan<<<1, SCAN_THREADS, 0, st>>>(d_sizes, nb, d_offsets, d_total, d_header, mode, block, n);
+    return launch_check(ctx, "k_scan");
+}
+
+int b2rc_k_scan(b2rc_ctx* ctx, const uint32_t* d_sizes, uint64_t nblocks, uint64_t* d_offsets, void* cuda_stream)
+{
+    if(!ctx || !d_offsets || (nblocks && !d_sizes) || ((uintptr_t)d_offsets & 7u)) {
+        return B2RC_E_ARG;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    return scan_launch(ctx, d_sizes, nblocks, d_offsets, nullptr, nullptr, 0, 0, 0, st);
+}
+
+int b2rc_k_compact(b2rc_ctx* ctx, const uint8_t* d_slots, uint64_t slot_stride, const uint32_t* d_sizes,
+                   const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_payload, uint64_t payload_cap, int* d_err,
+                   void* cuda_stream)
+{
+    if(!ctx || !d_slots || !d_sizes || !d_offsets || !d_payload || !d_err || !aligned16(d_slots) || (slot_stride & 15u)) {
+        return B2RC_E_ARG;
+    }
+    if(nblocks == 0) {
+        return B2RC_OK;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    u64 grid = nblocks;
+    if(grid > 148ull * 8) {
+        grid = 148ull * 8;
+    }
+    k_compact<<<(unsigned)grid, COMPACT_THREADS, 0, st>>>(d_slots, slot_stride, d_sizes, d_offsets, nblocks, d_payload,
+                                                          payload_cap, d_err);
+    return launch_check(ctx, "k_compact");
+}
+
+int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload,
+                         uint64_t payload_len, const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n,
+                         int* d_err, void* cuda_stream)
+{
+    if(!ctx || !d_payload || !d_offsets || !d_dst || !d_err || (mode != B2RC_MODE_STATIC && mode != B2RC_MODE_ADAPTIVE) ||
+       !block_ok(block_size) || !aligned16(d_dst) || ((uintptr_t)d_offsets & 7u) ||
+       nblocks != b2rc_nblocks(n, block_size)) {
+        return B2RC_E_ARG;
+    }
+    if(nblocks == 0) {
+        return B2RC_OK;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DecArgs a;
+    a.payload = d_payload;
+    a.payload_len = payload_len;
+    a.offsets = d_offsets;
+    a.nblocks = nblocks;
+    a.block = block_size;
+    a.dst = d_dst;
+    a.n = n;
+    a.err = d_err;
+    const bool wide = block_size > 65536u;
+    const unsigned grid = (unsigned)((nblocks + 31) / 32);
+    if(mode == B2RC_MODE_STATIC) {
+        if(wide) {
+            k_dec_static<true><<<grid, 32, smem_dec_static(true), st>>>(a);
+        } else {
+            k_dec_static<false><<<grid, 32, smem_dec_static(false), st>>>(a);
+        }
+    } else {
+        if(wide) {
+            k_dec_adaptive<u32><<<grid, 32, smem_dec_adaptive(true), st>>>(a);
+        } else {
+            k_dec_adaptive<u16><<<grid, 32, smem_dec_adaptive(false), st>>>(a);
+        }
+    }
+    return launch_check(ctx, "k_dec");
+}
+
+// ------------------------------------------------------ container, device --
+int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
+                       uint8_t* d_dst, uint64_t dst_cap, uint64_t* out_n, void* cuda_stream)
+{
+    if(!ctx || !d_dst || (n && !d_src) || (mode != B2RC_MODE_STATIC && mode != B2RC_MODE_ADAPTIVE) ||
+       !block_ok(block_size) || !aligned16(d_src) || !aligned16(d_dst)) {
+        return B2RC_E_ARG;
+    }
+    const u64 nb = b2rc_nblocks(n, block_size);
+    const u64 idx = index_bytes(nb);
+    if(out_n) {
+        *out_n = b2rc_bound(mode, n, block_size);
+    }
+    if(dst_cap < idx) {
+        return B2RC_E_DST_SMALL;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const u64 stride = b2rc_slot_bytes(block_size);
+    int rc;
+    if((rc = grow(ctx, ctx->slots, ctx->slots_cap, (size_t)(nb * stride))) != B2RC_OK ||
+       (rc = grow(ctx, ctx->sizes, ctx->sizes_cap, (size_t)(nb * 4 + 16))) != B2RC_OK) {
+        return rc;
+    }
+    const bool need_hist = mode == B2RC_MODE_STATIC && block_size <= 65536u;
+    if(need_hist && (rc = grow(ctx, ctx->freq16, ctx->freq_cap, (size_t)(nb * 512 + 16))) != B2RC_OK) {
+        return rc;
+    }
+    CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
+    if(nb) {
+        if(need_hist && (rc = b2rc_k_histogram(ctx, d_src, n, block_size, ctx->freq16, st)) != B2RC_OK) {
+            return rc;
+        }
+        if((rc = b2rc_k_encode_blocks(ctx, mode, block_size, d_src, n, ctx->freq16, ctx->slots, stride, ctx->sizes,
+                                      ctx->d_err, st)) != B2RC_OK) {
+            return rc;
+        }
+    }
+    if((rc = scan_launch(ctx, ctx->sizes, nb, reinterpret_cast<u64*>(d_dst + B2RC_HEADER_BYTES), ctx->d_total, d_dst,
+                         (u32)mode, block_size, n, st)) != B2RC_OK) {
+        return rc;
+    }
+    if(nb && (rc = b2rc_k_compact(ctx, ctx->slots, stride, ctx->sizes,
+                                  reinterpret_cast<const u64*>(d_dst + B2RC_HEADER_BYTES), nb, d_dst + idx,
+                                  dst_cap - idx, ctx->d_err, st)) != B2RC_OK) {
+        return rc;
+    }
+    CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ctx->h_res->total, ctx->d_total, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if(out_n) {
+        *out_n = idx + ctx->h_res->total;
+    }
+    return map_kernel_err(ctx->h_res->err);
+}
+
+int b2rc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t dst_cap,
+                       uint64_t* out_n, void* cuda_stream)
+{
+    if(!ctx || !d_src || !aligned16(d_src) || !aligned16(d_dst)) {
+        return B2RC_E_ARG;
+    }
+    if(n < B2RC_HEADER_BYTES + 8) {
+        return B2RC_E_CORRUPT;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaMemcpyAsync(ctx->h_res->header, d_src, B2RC_HEADER_BYTES, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int mode;
+    u32 block;
+    u64 total, nb;
+    // the offsets live on the device; peek only needs the header and the container length
+    u8 probe[B2RC_HEADER_BYTES + 8];
+    memcpy(probe, ctx->h_res->header, B2RC_HEADER_BYTES);
+    memset(probe + B2RC_HEADER_BYTES, 0, 8);
+    int rc = b2rc_peek(probe, n, &mode, &block, &total, &nb);
+    if(rc != B2RC_OK) {
+        return rc;
+    }
+    if(out_n) {
+        *out_n = total;
+    }
+    if(dst_cap < total || (total && !d_dst)) {
+        return B2RC_E_DST_SMALL;
+    }
+    if(nb == 0) {
+        return B2RC_OK;
+    }
+    const u64 idx = index_bytes(nb);
+    CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
+    // payload_len bounds every offset the kernel reads (dec_setup)
+    if((rc = b2rc_k_decode_blocks(ctx, mode, block, d_src + idx, n - idx,
+                                  reinterpret_cast<const u64*>(d_src + B2RC_HEADER_BYTES), nb, d_dst, total, ctx->d_err,
+                                  st)) != B2RC_OK) {
+        return rc;
+    }
+    CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return map_kernel_err(ctx->h_res->err);
+}
+
+// -------------------------------------------------------- container, host --
+int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src, uint64_t n, uint8_t* dst,
+                uint64_t dst_cap, uint64_t* out_n)
+{
+    if(!ctx || !dst || (n && !src) || (mode != B2RC_MODE_STATIC && mode != B2RC_MODE_ADAPTIVE) || !block_ok(block_size)) {
+        return B2RC_E_ARG;
+    }
+    DeviceGuard g(ctx->device);
+    const u64 bound = b2rc_bound(mode, n, block_size);
+    int rc;
+    if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
+       (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(bound + 16))) != B2RC_OK) {
+        return rc;
+    }
+    if(n) {
+        CK(cudaMemcpyAsync(ctx->stage_in, src, n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    u64 made = 0;
+    rc = b2rc_encode_device(ctx, mode, block_size, ctx->stage_in, n, ctx->stage_out, bound, &made, ctx->stream);
+    if(out_n) {
+        *out_n = made;
+    }
+    if(rc != B2RC_OK) {
+        return rc;
+    }
+    if(made > dst_cap) {
+        return B2RC_E_DST_SMALL;
+    }
+    CK(cudaMemcpyAsync(dst, ctx->stage_out, made, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2RC_OK;
+}
+
+int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n)
+{
+    if(!ctx || !src) {
+        return B2RC_E_ARG;
+    }
+    int mode;
+    u32 block;
+    u64 total, nb;
+    int rc = b2rc_peek(src, n, &mode, &block, &total, &nb);
+    if(rc != B2RC_OK) {
+        return rc;
+    }
+    if(out_n) {
+        *out_n = total;
+    }
+    if(dst_cap < total || (total && !dst)) {
+        return B2RC_E_DST_SMALL;
+    }
+    // the index is in host memory here: check it before anything reaches the device
+    const u64 idx = index_bytes(nb);
+    u64 prev = 0;
+    for(u64 b = 0; b <= nb; ++b) {
+        u64 o;
+        memcpy(&o, src + B2RC_HEADER_BYTES + 8 * b, 8);
+        if(o < prev || o > n - idx || (b == 0 && o != 0)) {
+            return B2RC_E_CORRUPT;
+        }
+        prev = o;
+    }
+    DeviceGuard g(ctx->device);
+    if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
+       (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(total + 16))) != B2RC_OK) {
+        return rc;
+    }
+    CK(cudaMemcpyAsync(ctx->stage_in, src, n, cudaMemcpyHostToDevice, ctx->stream));
+    u64 made = 0;
+    rc = b2rc_decode_device(ctx, ctx->stage_in, n, ctx->stage_out, total, &made, ctx->stream);
+    if(rc != B2RC_OK) {
+        return rc;
+    }
+    if(total) {
+        CK(cudaMemcpyAsync(dst, ctx->stage_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2RC_OK;
+}
+}

@@ -1,0 +1,1014 @@
+// b2rc_kernels.cuh -- the sm_100a kernels of the block range coder.
+//
+//   K1  k_hist            per-block byte histogram + the reference's count scaling
+//   K2  k_enc_static      static encode      (RangeEncoder::encode,          cpprcoder.h:375-458)
+//       k_enc_adaptive    adaptive encode    (AdaptiveRangeEncoder,          cpprcoder.h:678-802)
+//   K3  k_dec_static      static decode      (RangeEncoder::decode,          cpprcoder.h:460-535)
+//       k_dec_adaptive    adaptive decode    (AdaptiveRangeDecoder,          cpprcoder.h:859-940)
+//   K4  k_scan, k_compact exclusive scan of payload sizes + compaction into one stream
+//
+// Mapping: one block per LANE, one warp per CTA, 32
+// consecutive blocks per warp.  The coder's per-symbol chain is serial per block,
+// so throughput comes from the number of chains in flight, not from splitting a
+// block over a warp.  Per-warp shared memory holds
+//   * the model table, interleaved by lane ([entry][lane]: bank == lane),
+//   * input tiles staged by cp.async (encode) / a refilled word ring (decode),
+//   * an output word ring (encode) / an output tile (decode),
+// and all global traffic is done cooperatively by the warp in 128-byte rows.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rc_lane.cuh"
+
+namespace b2rc
+{
+constexpr u32 FULL = 0xFFFFFFFFu;
+constexpr int TILE = 64;   // symbols per lane per staged tile
+constexpr int ROW = 80;    // bytes per lane row of a tile: 64 + 16, so that the 8 lanes of a
+                           // quarter warp hit 8 disjoint bank groups on 16-byte accesses
+constexpr int RING = 32;   // words per lane in the output (encode) / input (decode) ring
+constexpr int TILE_BYTES = 32 * ROW;
+constexpr int RING_BYTES = RING * 32 * 4;
+
+enum : int {
+    ERR_SLOT_OVERFLOW = 1,  // a payload outgrew its slot
+    ERR_CORRUPT = 2,        // decoder met an impossible header / state
+    ERR_DST_SMALL = 4,      // compaction ran out of destination
+};
+
+// --------------------------------------------------------------- small helpers --
+__device__ __forceinline__ u32 smem_addr(const void* p)
+{
+    return (u32)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async16(u32 dst, const void* src, u32 bytes)
+{
+    // 16-byte async copy global -> shared, zero-filling beyond `bytes` (LDGSTS)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ u32 lane_id()
+{
+    return threadIdx.x & 31u;
+}
+
+// Table view of one lane: entry i lives at base[i * 32] (base already offset by the lane).
+template <class W>
+struct LaneTab {
+    W* base;
+    __device__ __forceinline__ u32 ld(u32 i) const { return (u32)base[i * 32u]; }
+    __device__ __forceinline__ void st(u32 i, u32 v) { base[i * 32u] = (W)v; }
+};
+
+// Stage tile `tile_off .. tile_off+TILE` of 32 consecutive blocks into shared memory.
+// Row r of the tile is block b0+r; 4 lanes cover one 64-byte row, 8 rows per instruction.
+// Bytes past the end of the block / of the input are zero-filled by cp.async's src-size.
+__device__ __forceinline__ void stage_tile(u8* tile, const u8* src, u64 n, u64 b0, u32 block, u32 tile_off, u32 lane)
+{
+    constexpr int CH = TILE / 16;
+    constexpr int RPI = 32 / CH;
+#pragma unroll
+    for(int it = 0; it < 32 / RPI; ++it) {
+        const u32 row = it * RPI + lane / CH;
+        const u32 ch = lane % CH;
+        const u64 blk_lo = (b0 + row) * (u64)block;
+        u64 blk_hi = blk_lo + block;
+        if(blk_hi > n) {
+            blk_hi = n;
+        }
+        const u64 at = blk_lo + tile_off + ch * 16u;
+        u32 bytes = 0;
+        if(at < blk_hi) {
+            const u64 rem = blk_hi - at;
+            bytes = rem >= 16 ? 16u : (u32)rem;
+        }
+        cp_async16(smem_addr(tile + row * ROW + ch * 16u), bytes ? (const void*)(src + at) : (const void*)src, bytes);
+    }
+}
+
+// ------------------------------------------------------------ encoder output --
+// Words leave a lane through a per-lane ring in shared memory; the warp empties all
+// 32 rings together with 128-byte rows.  Word i of lane r sits in column (r + i) & 31
+// so that both the lane's own stores (bank varies with its own progress) and the
+// cooperative row reads (i = f .. f+31 of one lane) spread over the banks.
+struct RingSink {
+    u32* ring;
+    u32* out;  // coded stream start of this lane's block (slot + header), 4-byte aligned
+    u32 lane, wcount, flushed, cap_words;
+    int* err;
+
+    __device__ __forceinline__ u32 slot_of(u32 i) const { return (i % RING) * 32u + ((lane + i) & 31u); }
+
+    __device__ void drain()  // lane-local, only when a single lane overruns its ring (long 0xFF runs)
+    {
+        for(u32 i = flushed; i < wcount; ++i) {
+            if(i < cap_words) {
+                out[i] = ring[slot_of(i)];
+            }
+        }
+        flushed = wcount;
+    }
+    __device__ __forceinline__ void push(u32 w)
+    {
+        if(wcount - flushed >= (u32)RING) {
+            drain();
+        }
+        ring[slot_of(wcount)] = rc_bswap(w);
+        ++wcount;
+    }
+};
+
+__device__ __noinline__ void ring_flush(RingSink& s)
+{
+    __syncwarp();
+#pragma unroll 1
+    for(int r = 0; r < 32; ++r) {
+        const u32 f = __shfl_sync(FULL, s.flushed, r);
+        const u32 w = __shfl_sync(FULL, s.wcount, r);
+        if(f == w) {
+            continue;
+        }
+        u32* o = (u32*)__shfl_sync(FULL, (unsigned long long)s.out, r);
+        const u32 capw = __shfl_sync(FULL, s.cap_words, r);
+        for(u32 i = f + s.lane; i < w; i += 32u) {
+            if(i < capw) {
+                o[i] = s.ring[(i % RING) * 32u + (((u32)r + i) & 31u)];
+            }
+        }
+    }
+    if(s.wcount > s.cap_words) {
+        atomicOr(s.err, ERR_SLOT_OVERFLOW);
+    }
+    s.flushed = s.wcount;
+    __syncwarp();
+}
+
+struct EncArgs {
+    const u8* src;
+    u64 n;
+    u32 block;
+    u64 nblocks;
+    const u16* freq16;
+    u8* slots;
+    u64 slot_stride;
+    u32* sizes;
+    int* err;
+};
+
+// Tail of a block: the 4..7 bytes that do not fill a word, then the size.
+__device__ __forceinline__ void finish_block(RcEnc& st, RingSink& sink, bool has, u32 hdr, u8* slot, u32* size_out)
+{
+    u8 tail[8];
+    u32 ntail = 0;
+    if(has) {
+        ntail = rc_enc_finish(st, sink, tail);
+    }
+    ring_flush(sink);
+    if(has) {
+        const u32 at = hdr + 4u * sink.wcount;
+        if((u64)at + ntail <= (u64)hdr + 4ull * sink.cap_words) {
+            for(u32 k = 0; k < ntail; ++k) {
+                slot[at + k] = tail[k];
+            }
+        } else {
+            atomicOr(sink.err, ERR_SLOT_OVERFLOW);
+        }
+        *size_out = at + ntail;
+    }
+}
+
+// ======================================================================= K2s ==
+// Static encode.  WIDE = false: blocks <= 65536 bytes, table entry = cum << 16 | freq
+// (both fit 16 bits) built from K1's frequencies.
+// WIDE = true: larger blocks; the lane counts its own block with the reference's
+// order-dependent rule (cpprcoder.h:543-571) and keeps a 257-entry u32 cum table.
+template <bool WIDE>
+struct StaticTab {
+    u32* base;  // + lane
+    __device__ __forceinline__ void get(u32 sym, u32& cum, u32& freq) const
+    {
+        if(WIDE) {
+            cum = base[sym * 32u];
+            freq = base[(sym + 1u) * 32u] - cum;
+        } else {
+            const u32 e = base[sym * 32u];
+            cum = e >> 16;
+            freq = e & 0xFFFFu;
+        }
+    }
+};
+
+template <bool WIDE, bool POW2, bool RAGGED>
+__device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u8* tiles, const StaticTab<WIDE>& tab, RcEnc& st,
+                                                 RingSink& sink, u64 b0, u32 n_b, u32 n_max, u32 total, u32 magic,
+                                                 u32 shift, u32 lane)
+{
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+    // tile 0 was staged (and committed) by the caller
+#pragma unroll 1
+    for(u32 tix = 0; tix < ntiles; ++tix) {
+        if(tix + 1 < ntiles) {
+            stage_tile(tiles + ((tix + 1) & 1u) * TILE_BYTES, a.src, a.n, b0, a.block, (tix + 1) * TILE, lane);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const u8* row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+#pragma unroll
+        for(int q = 0; q < TILE / 16; ++q) {
+            const uint4 v = *reinterpret_cast<const uint4*>(row + q * 16);
+            const u32 w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for(int k = 0; k < 16; ++k) {
+                const u32 sym = (w4[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                if(!RAGGED || tix * TILE + q * 16 + k < n_b) {
+                    u32 cum, freq;
+                    tab.get(sym, cum, freq);
+                    const u32 t = POW2 ? (st.range >> shift) : rc_div(st.range, total, magic);
+                    rc_enc_step(st, cum, freq, t, sink);
+                }
+            }
+            if(__any_sync(FULL, sink.wcount - sink.flushed >= (u32)(RING - 13))) {
+                ring_flush(sink);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    constexpr u32 TAB_BYTES = (WIDE ? 257u : 256u) * 32u * 4u;
+    constexpr u32 TAB_PAD = (TAB_BYTES + 15u) & ~15u;
+    u32* table = reinterpret_cast<u32*>(smem);
+    u8* tiles = smem + TAB_PAD;
+    u32* ring = reinterpret_cast<u32*>(smem + TAB_PAD + 2 * TILE_BYTES);
+
+    const u32 lane = lane_id();
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    u8* slot = a.slots + b * a.slot_stride;
+    u32 total = 0;
+
+    if(!WIDE) {
+        // first input tile in flight while the tables are built
+        stage_tile(tiles, a.src, a.n, b0, a.block, 0, lane);
+        cp_async_commit();
+#pragma unroll 1
+        for(u32 r = 0; r < 32; ++r) {
+            if(b0 + r >= a.nblocks) {
+                break;
+            }
+            // lane j holds the frequencies of symbols 8j .. 8j+7 of block b0+r
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.freq16 + (b0 + r) * 256u) + lane);
+            const u32 f[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
+                              v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+            u32 sum = 0;
+#pragma unroll
+            for(int k = 0; k < 8; ++k) {
+                sum += f[k];
+            }
+            u32 incl = sum;
+#pragma unroll
+            for(int d = 1; d < 32; d <<= 1) {
+                const u32 up = __shfl_up_sync(FULL, incl, d);
+                if(lane >= (u32)d) {
+                    incl += up;
+                }
+            }
+            u32 run = incl - sum;  // calcCumulatives (cpprcoder.h:573-583)
+#pragma unroll
+            for(int k = 0; k < 8; ++k) {
+                table[(8u * lane + k) * 32u + r] = (run << 16) | f[k];
+                run += f[k];
+            }
+            const u32 tot = __shfl_sync(FULL, incl, 31);
+            if(lane == r) {
+                total = tot;
+            }
+            // payload header: u32 LE size, then write16 (cpprcoder.h:386-395, :604-619)
+            u8* slot_r = a.slots + (b0 + r) * a.slot_stride;
+            const u32 n_r = __shfl_sync(FULL, n_b, (int)r);
+            u32* hw = reinterpret_cast<u32*>(slot_r + 4u + 16u * lane);
+            hw[0] = v.x;
+            hw[1] = v.y;
+            hw[2] = v.z;
+            hw[3] = v.w;
+            if(lane == 0) {
+                *reinterpret_cast<u32*>(slot_r) = n_r;
+            }
+        }
+        __syncwarp();
+    } else {
+        // count(): the halving is order dependent, so each lane walks its own block once
+        u32* mine = table + lane;
+        for(u32 s = 0; s < 257; ++s) {
+            mine[s * 32u] = 0;
+        }
+        const u32 n_max0 = __reduce_max_sync(FULL, n_b);
+        const u32 ntiles = (n_max0 + TILE - 1) / TILE;
+        stage_tile(tiles, a.src, a.n, b0, a.block, 0, lane);
+        cp_async_commit();
+#pragma unroll 1
+        for(u32 tix = 0; tix < ntiles; ++tix) {
+            if(tix + 1 < ntiles) {
+                stage_tile(tiles + ((tix + 1) & 1u) * TILE_BYTES, a.src, a.n, b0, a.block, (tix + 1) * TILE, lane);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+            const u8* row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+            for(u32 k = 0; k < (u32)TILE; ++k) {
+                if(tix * TILE + k < n_b) {
+                    const u32 c = row[k];
+                    u32 f = mine[c * 32u];
+                    if(f >= 0xFFFFu) {
+                        for(u32 s = 0; s < 256; ++s) {
+                            const u32 x = mine[s * 32u];
+                            if(x) {
+                                mine[s * 32u] = (x >> 1) | 1u;
+                            }
+                        }
+                        f = mine[c * 32u];
+                    }
+                    mine[c * 32u] = f + 1u;
+                }
+            }
+            __syncwarp();
+        }
+        if(has) {
+            *reinterpret_cast<u32*>(slot) = n_b;
+            u32 run = 0;
+            for(u32 s = 0; s < 256; ++s) {
+                const u32 f = mine[s * 32u];
+                *reinterpret_cast<u16*>(slot + 4u + 2u * s) = (u16)f;
+                mine[s * 32u] = run;
+                run += f;
+            }
+            mine[256u * 32u] = run;
+            total = run;
+        }
+        __syncwarp();
+        stage_tile(tiles, a.src, a.n, b0, a.block, 0, lane);
+        cp_async_commit();
+    }
+
+    RcEnc st;
+    rc_enc_init(st, RC_STATIC_RANGE0);
+    RingSink sink;
+    sink.ring = ring;
+    sink.out = reinterpret_cast<u32*>(slot + RC_STATIC_HDR);
+    sink.lane = lane;
+    sink.wcount = 0;
+    sink.flushed = 0;
+    sink.cap_words = has ? (u32)((a.slot_stride - RC_STATIC_HDR) / 4u) : 0u;
+    sink.err = a.err;
+
+    const StaticTab<WIDE> tab{table + lane};
+    const u32 magic = rc_magic(total);
+    const bool is_pow2 = total != 0 && (total & (total - 1u)) == 0;
+    const u32 shift = is_pow2 ? 31u - rc_clz(total) : 0u;
+    const u32 n_max = __reduce_max_sync(FULL, n_b);
+    const bool all_pow2 = __all_sync(FULL, is_pow2 || !has);
+    const bool ragged = __any_sync(FULL, n_b != n_max);
+
+    if(all_pow2 && !ragged) {
+        enc_static_tiles<WIDE, true, false>(a, tiles, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
+    } else if(!ragged) {
+        enc_static_tiles<WIDE, false, false>(a, tiles, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
+    } else {
+        enc_static_tiles<WIDE, false, true>(a, tiles, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
+    }
+
+    // cpprcoder.h:439-451: when the block ends on low_ == 0xFFFFFFFF the reference bumps
+    // the held byte but still writes low_ as FF FF FF FF -- not the big-endian sum.
+    // Probability 2^-32 per block; redo such a block with the reference-shaped encoder.
+    bool exact = false;
+    if(has && st.low == 0xFFFFFFFFu) {
+        exact = true;
+        sink.wcount = sink.flushed;  // drop what the ring still holds
+        u32 at = RC_STATIC_HDR;
+        const u8* blk = a.src + b * (u64)a.block;
+        const u32 cap = (u32)a.slot_stride;
+        bool over = false;
+        rc_static_encode_exact(
+            n_b, total,
+            [&](u32 c) -> u32 {
+                if(c >= 256u) {
+                    return total;
+                }
+                u32 cum, freq;
+                tab.get(c, cum, freq);
+                return cum;
+            },
+            [&](u32 i) -> u32 { return blk[i]; },
+            [&](u8 byte) {
+                if(at < cap) {
+                    slot[at] = byte;
+                } else {
+                    over = true;
+                }
+                ++at;
+            });
+        if(over) {
+            atomicOr(a.err, ERR_SLOT_OVERFLOW);
+        }
+        a.sizes[b] = at;
+    }
+    finish_block(st, sink, has && !exact, RC_STATIC_HDR, slot, a.sizes + b);
+}
+
+// ======================================================================= K2a ==
+// Adaptive encode.  The model is the count tree of rc_model_encode, one per lane.
+// total_i = 256 + i is the same for every lane, so the 64 magics of a tile are
+// computed once per warp (two per lane) and handed round by shuffle.
+template <class W, bool RAGGED>
+__device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u8* tiles, LaneTab<W>& tab, RcEnc& st,
+                                                   RingSink& sink, u64 b0, u32 n_b, u32 n_max, u32 lane)
+{
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+#pragma unroll 1
+    for(u32 tix = 0; tix < ntiles; ++tix) {
+        if(tix + 1 < ntiles) {
+            stage_tile(tiles + ((tix + 1) & 1u) * TILE_BYTES, a.src, a.n, b0, a.block, (tix + 1) * TILE, lane);
+        }
+        cp_async_commit();
+        const u32 d0 = 256u + tix * TILE;
+        const u32 mg0 = rc_magic(d0 + lane);
+        const u32 mg1 = rc_magic(d0 + 32u + lane);
+        cp_async_wait<1>();
+        __syncwarp();
+        const u8* row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+#pragma unroll
+        for(int q = 0; q < TILE / 16; ++q) {
+            const uint4 v = *reinterpret_cast<const uint4*>(row + q * 16);
+            const u32 w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for(int k = 0; k < 16; ++k) {
+                const int j = q * 16 + k;
+                const u32 sym = (w4[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                const u32 magic = __shfl_sync(FULL, j < 32 ? mg0 : mg1, j & 31);
+                if(!RAGGED || tix * TILE + j < n_b) {
+                    u32 cum, freq;
+                    rc_model_encode(tab, sym, cum, freq);
+                    const u32 t = rc_div(st.range, d0 + j, magic);
+                    rc_enc_step(st, cum, freq, t, sink);
+                }
+            }
+            if(__any_sync(FULL, sink.wcount - sink.flushed >= (u32)(RING - 13))) {
+                ring_flush(sink);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <class W>
+__global__ void __launch_bounds__(32) k_enc_adaptive(EncArgs a)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    constexpr u32 TAB_BYTES = 512u * 32u * sizeof(W);
+    W* table = reinterpret_cast<W*>(smem);
+    u8* tiles = smem + TAB_BYTES;
+    u32* ring = reinterpret_cast<u32*>(smem + TAB_BYTES + 2 * TILE_BYTES);
+
+    const u32 lane = lane_id();
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    u8* slot = a.slots + b * a.slot_stride;
+
+    stage_tile(tiles, a.src, a.n, b0, a.block, 0, lane);
+    cp_async_commit();
+    {  // initialize(): all counts zero (the ones are implicit), cpprcoder.h:1094-1132
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for(u32 i = lane; i < TAB_BYTES / 16u; i += 32u) {
+            z[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    if(has) {
+        *reinterpret_cast<u32*>(slot) = n_b;  // cpprcoder.h:689-694
+    }
+    __syncwarp();
+
+    RcEnc st;
+    rc_enc_init(st, RC_ADAPT_RANGE0);
+    RingSink sink;
+    sink.ring = ring;
+    sink.out = reinterpret_cast<u32*>(slot + RC_ADAPT_HDR);
+    sink.lane = lane;
+    sink.wcount = 0;
+    sink.flushed = 0;
+    sink.cap_words = has ? (u32)((a.slot_stride - RC_ADAPT_HDR) / 4u) : 0u;
+    sink.err = a.err;
+    LaneTab<W> tab{table + lane};
+
+    const u32 n_max = __reduce_max_sync(FULL, n_b);
+    if(__any_sync(FULL, n_b != n_max)) {
+        enc_adaptive_tiles<W, true>(a, tiles, tab, st, sink, b0, n_b, n_max, lane);
+    } else {
+        enc_adaptive_tiles<W, false>(a, tiles, tab, st, sink, b0, n_b, n_max, lane);
+    }
+    finish_block(st, sink, has, RC_ADAPT_HDR, slot, a.sizes + b);
+}
+
+// ============================================================= decoder input ==
+// Each lane reads its own payload at its own pace.  The warp keeps a ring of
+// aligned stream words per lane topped up (128-byte rows, one lane's stream per
+// row); a lane pops one word whenever its bit window runs low.
+struct DecArgs {
+    const u8* payload;    // payload base
+    u64 payload_len;
+    const u64* offsets;   // nblocks + 1, relative to payload
+    u64 nblocks;
+    u32 block;
+    u8* dst;
+    u64 n;
+    int* err;
+};
+
+struct WordSrc {
+    const u32* ring;
+    const u8* wbase;  // aligned address of the word holding coded byte 0
+    const u8* end;    // one past the last readable stream byte
+    u32 lane, consumed, filled, limit;
+
+    __device__ __forceinline__ u32 operator()()
+    {
+        u32 w = 0;
+        if(consumed < filled) {
+            w = rc_bswap(ring[(consumed % RING) * 32u + ((lane + consumed) & 31u)]);
+        }
+        ++consumed;
+        return w;
+    }
+};
+
+__device__ __forceinline__ u32 load_stream_word(const u8* p, const u8* end)
+{
+    if(p + 4 <= end) {
+        return *reinterpret_cast<const u32*>(p);
+    }
+    u32 w = 0;
+    for(int k = 0; k < 4; ++k) {
+        if(p + k < end) {
+            w |= (u32)p[k] << (8 * k);
+        }
+    }
+    return w;
+}
+
+__device__ __noinline__ void ring_fill(WordSrc& s, u32* ring)
+{
+    __syncwarp();
+#pragma unroll 1
+    for(int r = 0; r < 32; ++r) {
+        const u32 c = __shfl_sync(FULL, s.consumed, r);
+        const u32 f = __shfl_sync(FULL, s.filled, r);
+        const u32 lim = __shfl_sync(FULL, s.limit, r);
+        u32 target = c + (u32)RING;
+        if(target > lim) {
+            target = lim;
+        }
+        if(f >= target) {
+            continue;
+        }
+        const u8* wb = (const u8*)__shfl_sync(FULL, (unsigned long long)s.wbase, r);
+        const u8* end = (const u8*)__shfl_sync(FULL, (unsigned long long)s.end, r);
+        for(u32 i = f + s.lane; i < target; i += 32u) {
+            ring[(i % RING) * 32u + (((u32)r + i) & 31u)] = load_stream_word(wb + 4ull * i, end);
+        }
+        if(s.lane == (u32)r) {
+            s.filled = target;
+        }
+    }
+    __syncwarp();
+}
+
+// Output tile -> global, 8 rows of 64 bytes per instruction.
+__device__ __forceinline__ void store_tile(const u8* tile, u8* dst, u64 n, u64 b0, u32 block, u32 tile_off, u32 lane)
+{
+    constexpr int CH = TILE / 16;
+    constexpr int RPI = 32 / CH;
+#pragma unroll
+    for(int it = 0; it < 32 / RPI; ++it) {
+        const u32 row = it * RPI + lane / CH;
+        const u32 ch = lane % CH;
+        const u64 blk_lo = (b0 + row) * (u64)block;
+        u64 blk_hi = blk_lo + block;
+        if(blk_hi > n) {
+            blk_hi = n;
+        }
+        const u64 at = blk_lo + tile_off + ch * 16u;
+        if(at >= blk_hi) {
+            continue;
+        }
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + row * ROW + ch * 16u);
+        if(at + 16 <= blk_hi) {
+            *reinterpret_cast<uint4*>(dst + at) = v;
+        } else {
+            const u32 w4[4] = {v.x, v.y, v.z, v.w};
+            for(u32 k = 0; at + k < blk_hi; ++k) {
+                dst[at + k] = (u8)(w4[k >> 2] >> (8 * (k & 3)));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u32 lane, u64 b, bool has, u32 n_b, u32* ring,
+                                          WordSrc& src, const u8*& pay, bool& ok)
+{
+    pay = a.payload;
+    u64 len = 0;
+    if(has) {
+        const u64 o0 = a.offsets[b], o1 = a.offsets[b + 1];
+        if(o0 <= o1 && o1 <= a.payload_len) {
+            pay = a.payload + o0;
+            len = o1 - o0;
+        }
+    }
+    ok = has && len >= (u64)hdr + 5u;
+    if(ok) {
+        const u32 want = (u32)pay[0] | ((u32)pay[1] << 8) | ((u32)pay[2] << 16) | ((u32)pay[3] << 24);
+        ok = want == n_b;  // the container, not the payload, says how long block b is
+    }
+    if(has && !ok) {
+        atomicOr(a.err, ERR_CORRUPT);
+    }
+    const u8* coded = pay + hdr;
+    src.ring = ring;
+    src.lane = lane;
+    src.consumed = 0;
+    src.filled = 0;
+    src.wbase = (const u8*)((uintptr_t)coded & ~(uintptr_t)3);
+    src.end = pay + len;
+    src.limit = ok ? (u32)((src.end - src.wbase + 3) / 4) : 0u;
+}
+
+// ======================================================================= K3s ==
+// Static decode.  Symbol search is two 16-way steps in the product domain
+// (cum * t <= low, no second divide): level 1 compares the 15
+// chunk boundaries cum[16j] held in registers, level 2 the 15 boundaries inside the
+// chunk from the lane's table.  Equivalent to RangeEncoder::find (cpprcoder.h:521-535).
+template <bool WIDE>
+__global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    constexpr u32 TAB_BYTES = (WIDE ? 257u : 256u) * 32u * 4u;
+    constexpr u32 TAB_PAD = (TAB_BYTES + 15u) & ~15u;
+    u32* table = reinterpret_cast<u32*>(smem);
+    u8* otile = smem + TAB_PAD;
+    u32* ring = reinterpret_cast<u32*>(smem + TAB_PAD + TILE_BYTES);
+
+    const u32 lane = lane_id();
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    WordSrc src;
+    const u8* pay;
+    bool ok;
+    dec_setup(a, RC_STATIC_HDR, lane, b, has, n_b, ring, src, pay, ok);
+
+    // read16 + calcCumulatives (cpprcoder.h:585-602, :573-583); payloads are unaligned
+    u32* mine = table + lane;
+    u32 total = 0;
+    u32 key[16];
+    {
+        u32 run = 0;
+        for(u32 s = 0; s < 256; ++s) {
+            u32 f = 0;
+            if(ok) {
+                f = (u32)pay[4u + 2u * s] | ((u32)pay[5u + 2u * s] << 8);
+            }
+            if(WIDE) {
+                mine[s * 32u] = run;
+            } else {
+                mine[s * 32u] = (run << 16) | f;
+            }
+            run += f;
+        }
+        if(WIDE) {
+            mine[256u * 32u] = run;
+        }
+        total = run;
+        if(ok && (total == 0 || (!WIDE && total > 65536u))) {
+            ok = false;
+            atomicOr(a.err, ERR_CORRUPT);
+        }
+#pragma unroll
+        for(int j = 0; j < 16; ++j) {
+            key[j] = WIDE ? mine[(16u * j) * 32u] : (mine[(16u * j) * 32u] >> 16);
+        }
+    }
+    if(!ok) {
+        n_b = 0;
+        src.limit = 0;
+        total = 1;
+    }
+    const u32 magic = rc_magic(total);
+    ring_fill(src, ring);
+    RcDec d;
+    rc_dec_init(d, RC_STATIC_RANGE0, (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u), src);
+
+    const u32 n_max = __reduce_max_sync(FULL, n_b);
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+#pragma unroll 1
+    for(u32 tix = 0; tix < ntiles; ++tix) {
+#pragma unroll 1
+        for(int q = 0; q < TILE / 16; ++q) {
+            u32 w4[4] = {0, 0, 0, 0};
+            if(__any_sync(FULL, src.filled < src.limit && src.filled - src.consumed < 13u)) {
+                ring_fill(src, ring);
+            }
+#pragma unroll
+            for(int k = 0; k < 16; ++k) {
+                if(tix * TILE + q * 16 + k < n_b) {
+                    const u32 t = rc_div(d.range, total, magic);
+                    u32 c1 = 0;
+#pragma unroll
+                    for(int j = 1; j < 16; ++j) {
+                        c1 += (key[j] * t <= d.low) ? 1u : 0u;
+                    }
+                    const u32* chunk = mine + (16u * c1) * 32u;
+                    u32 c2 = 0;
+#pragma unroll
+                    for(int j = 1; j < 16; ++j) {
+                        const u32 e = chunk[j * 32];
+                        c2 += ((WIDE ? e : (e >> 16)) * t <= d.low) ? 1u : 0u;
+                    }
+                    const u32 sym = 16u * c1 + c2;
+                    u32 cum, freq;
+                    if(WIDE) {
+                        cum = mine[sym * 32u];
+                        freq = mine[(sym + 1u) * 32u] - cum;
+                    } else {
+                        const u32 e = mine[sym * 32u];
+                        cum = e >> 16;
+                        freq = e & 0xFFFFu;
+                    }
+                    rc_dec_advance(d, cum, freq, t, src);
+                    w4[k >> 2] |= sym << (8 * (k & 3));
+                }
+            }
+            *reinterpret_cast<uint4*>(otile + lane * ROW + q * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+        __syncwarp();
+        store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
+        __syncwarp();
+    }
+    if(ok && d.range == 0) {
+        atomicOr(a.err, ERR_CORRUPT);
+    }
+}
+
+// ======================================================================= K3a ==
+template <class W>
+__global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    constexpr u32 TAB_BYTES = 512u * 32u * sizeof(W);
+    W* table = reinterpret_cast<W*>(smem);
+    u8* otile = smem + TAB_BYTES;
+    u32* ring = reinterpret_cast<u32*>(smem + TAB_BYTES + TILE_BYTES);
+
+    const u32 lane = lane_id();
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    WordSrc src;
+    const u8* pay;
+    bool ok;
+    dec_setup(a, RC_ADAPT_HDR, lane, b, has, n_b, ring, src, pay, ok);
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for(u32 i = lane; i < TAB_BYTES / 16u; i += 32u) {
+            z[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    if(!ok) {
+        n_b = 0;
+        src.limit = 0;
+    }
+    __syncwarp();
+    LaneTab<W> tab{table + lane};
+    ring_fill(src, ring);
+    RcDec d;
+    rc_dec_init(d, RC_ADAPT_RANGE0, (u32)((uintptr_t)(pay + RC_ADAPT_HDR) & 3u), src);
+
+    const u32 n_max = __reduce_max_sync(FULL, n_b);
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+#pragma unroll 1
+    for(u32 tix = 0; tix < ntiles; ++tix) {
+        const u32 d0 = 256u + tix * TILE;
+        const u32 mg0 = rc_magic(d0 + lane);
+        const u32 mg1 = rc_magic(d0 + 32u + lane);
+#pragma unroll
+        for(int q = 0; q < TILE / 16; ++q) {
+            u32 w4[4] = {0, 0, 0, 0};
+            if(__any_sync(FULL, src.filled < src.limit && src.filled - src.consumed < 13u)) {
+                ring_fill(src, ring);
+            }
+#pragma unroll
+            for(int k = 0; k < 16; ++k) {
+                const int j = q * 16 + k;
+                const u32 magic = __shfl_sync(FULL, j < 32 ? mg0 : mg1, j & 31);
+                if(tix * TILE + j < n_b) {
+                    const u32 t = rc_div(d.range, d0 + j, magic);
+                    u32 sym, cum, freq;
+                    rc_model_decode(tab, d.low, t, sym, cum, freq);
+                    rc_dec_advance(d, cum, freq, t, src);
+                    w4[k >> 2] |= sym << (8 * (k & 3));
+                }
+            }
+            *reinterpret_cast<uint4*>(otile + lane * ROW + q * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+        __syncwarp();
+        store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
+        __syncwarp();
+    }
+    if(ok && d.range == 0) {
+        atomicOr(a.err, ERR_CORRUPT);
+    }
+}
+
+// ======================================================================== K1 ==
+// Per-block histogram for blocks <= 65536 bytes: one warp per block, 16-byte loads,
+// warp-private shared-memory bins.  For such blocks RangeEncoder::count never halves
+// except when all 65536 bytes are equal, where it ends at 0x8000.
+constexpr int HIST_WARPS = 8;
+__global__ void __launch_bounds__(HIST_WARPS * 32) k_hist(const u8* src, u64 n, u32 block, u64 nblocks, u16* freq16)
+{
+    __shared__ u32 bins[HIST_WARPS][256];
+    const u32 lane = lane_id();
+    const u32 warp = threadIdx.x >> 5;
+    u32* h = bins[warp];
+    for(u64 b = (u64)blockIdx.x * HIST_WARPS + warp; b < nblocks; b += (u64)gridDim.x * HIST_WARPS) {
+#pragma unroll
+        for(int k = 0; k < 8; ++k) {
+            h[lane + 32 * k] = 0;
+        }
+        __syncwarp();
+        const u64 lo = b * (u64)block;
+        const u32 len = (u32)((n - lo < block) ? (n - lo) : block);
+        const u8* p = src + lo;
+        const u32 vec = len & ~15u;
+        for(u32 off = lane * 16u; off < vec; off += 512u) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + off));
+            const u32 w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for(int k = 0; k < 16; ++k) {
+                atomicAdd(&h[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu], 1u);
+            }
+        }
+        for(u32 off = vec + lane; off < len; off += 32u) {
+            atomicAdd(&h[p[off]], 1u);
+        }
+        __syncwarp();
+        u32 f[8];
+#pragma unroll
+        for(int k = 0; k < 8; ++k) {
+            f[k] = h[8u * lane + k];
+            if(f[k] >= 0x10000u) {
+                f[k] = 0x8000u;  // 65535 hits, then halve-all-and-increment: (0xFFFF >> 1 | 1) + 1
+            }
+        }
+        uint4 o;
+        o.x = f[0] | (f[1] << 16);
+        o.y = f[2] | (f[3] << 16);
+        o.z = f[4] | (f[5] << 16);
+        o.w = f[6] | (f[7] << 16);
+        reinterpret_cast<uint4*>(freq16 + b * 256u)[lane] = o;
+        __syncwarp();
+    }
+}
+
+// ======================================================================== K4 ==
+// Exclusive scan of the payload sizes (one CTA; the index is tiny next to the data)
+// and, fused into it, the 32-byte container header when `header` is not null.
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32* sizes, u64 nblocks, u64* offsets, u64* total_out,
+                                                       u8* header, u32 mode, u32 block, u64 n)
+{
+    __shared__ u64 part[SCAN_THREADS];
+    const u32 t = threadIdx.x;
+    const u64 per = (nblocks + SCAN_THREADS - 1) / SCAN_THREADS;
+    u64 lo = per * t, hi = lo + per;
+    if(lo > nblocks) {
+        lo = nblocks;
+    }
+    if(hi > nblocks) {
+        hi = nblocks;
+    }
+    u64 sum = 0;
+    for(u64 i = lo; i < hi; ++i) {
+        sum += sizes[i];
+    }
+    part[t] = sum;
+    __syncthreads();
+    for(u32 d = 1; d < SCAN_THREADS; d <<= 1) {
+        u64 add = 0;
+        if(t >= d) {
+            add = part[t - d];
+        }
+        __syncthreads();
+        part[t] += add;
+        __syncthreads();
+    }
+    u64 run = part[t] - sum;
+    for(u64 i = lo; i < hi; ++i) {
+        offsets[i] = run;
+        run += sizes[i];
+    }
+    if(t == SCAN_THREADS - 1) {
+        offsets[nblocks] = part[t];
+        if(total_out) {
+            *total_out = part[t];
+        }
+    }
+    if(header && t == 0) {
+        u32* h = reinterpret_cast<u32*>(header);
+        h[0] = 0x43523242u;  // 'B','2','R','C'
+        h[1] = 1u | (mode << 16);
+        h[2] = block;
+        h[3] = 0;
+        h[4] = (u32)n;
+        h[5] = (u32)(n >> 32);
+        h[6] = (u32)nblocks;
+        h[7] = (u32)(nblocks >> 32);
+    }
+}
+
+// Compaction: payload b (16-byte aligned slot) -> payload + offsets[b] (any alignment).
+// One CTA per block at a time; destination-aligned 4-byte words assembled from two
+// neighbouring source words with a funnel shift.
+constexpr int COMPACT_THREADS = 256;
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const u8* slots, u64 slot_stride, const u32* sizes,
+                                                             const u64* offsets, u64 nblocks, u8* payload,
+                                                             u64 payload_cap, int* err)
+{
+    for(u64 b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const u8* s = slots + b * slot_stride;
+        const u32 len = sizes[b];
+        const u64 off = offsets[b];
+        if(off + len > payload_cap) {
+            if(threadIdx.x == 0) {
+                atomicOr(err, ERR_DST_SMALL);
+            }
+            continue;
+        }
+        u8* d = payload + off;
+        u32 head = (u32)((4u - ((uintptr_t)d & 3u)) & 3u);
+        if(head > len) {
+            head = len;
+        }
+        if(threadIdx.x < head) {
+            d[threadIdx.x] = s[threadIdx.x];
+        }
+        const u32 nwords = (len - head) >> 2;
+        u32* dw = reinterpret_cast<u32*>(d + head);
+        const u32* sw = reinterpret_cast<const u32*>(s);
+        const u32 sh = head * 8u;  // source byte offset of dst word j is head + 4j
+        for(u32 j = threadIdx.x; j < nwords; j += COMPACT_THREADS) {
+            const u32 a0 = __ldg(sw + j);
+            const u32 a1 = sh ? __ldg(sw + j + 1) : 0u;
+            dw[j] = __funnelshift_r(a0, a1, sh);
+        }
+        const u32 done = head + 4u * nwords;
+        if(done + threadIdx.x < len) {
+            d[done + threadIdx.x] = s[done + threadIdx.x];
+        }
+    }
+}
+
+}  // namespace b2rc

@@ -1,0 +1,417 @@
+// rc_lane.cuh -- the per-block coder arithmetic, one block per GPU lane.
+//
+// Every kernel in this library maps ONE independent block to ONE lane: a warp
+// advances 32 blocks in lock step, tables live in shared memory interleaved by
+// lane ([entry][lane], bank == lane, conflict free) and nothing in the hot loop
+// needs a shuffle.  The only serial dependency of an order-0 range coder is
+//     range' = norm(freq * (range / total))
+// per block; mapping blocks to lanes keeps 32 of those chains in flight per warp
+// instead of one.
+//
+// This header holds the arithmetic of one lane and is written __host__ __device__
+// so tests/sim can drive exactly the same code on the CPU against the oracle.
+// It restates behaviour of the reference (cpprcoder.h, cited per function); no
+// reference code is reused: the encoder here is a carry-save formulation (a wide
+// shift register with deferred word emission) instead of the reference's
+// byte-at-a-time buffer_/count_ state machine.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RC_HD __host__ __device__ __forceinline__
+#define RC_COLD __host__ __device__ __noinline__
+#else
+#define RC_HD inline
+#define RC_COLD inline
+#endif
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t s32;
+typedef int64_t s64;
+
+#define RC_MIN_RANGE 0x01000000u      // cpprcoder.h:327, :631
+#define RC_STATIC_RANGE0 0xFFFFFFFFu  // cpprcoder.h:326
+#define RC_ADAPT_RANGE0 0xFFFFFF00u   // cpprcoder.h:630 (the decoder reaches it after its first normalize, :813,:929)
+#define RC_STATIC_HDR 516u            // cpprcoder.h:331
+#define RC_ADAPT_HDR 4u               // cpprcoder.h:689-694
+
+// ------------------------------------------------------------------ bit helpers --
+RC_HD u32 rc_funnel_l(u32 lo, u32 hi, u32 s)  // high word of (hi:lo) << s, s in [0,31]
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s ? ((hi << s) | (lo >> (32u - s))) : hi;
+#endif
+}
+RC_HD u32 rc_funnel_r(u32 lo, u32 hi, u32 s)  // low word of (hi:lo) >> s, s in [0,31]
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? ((lo >> s) | (hi << (32u - s))) : lo;
+#endif
+}
+RC_HD u32 rc_clz(u32 x)
+{
+#if defined(__CUDA_ARCH__)
+    return (u32)__clz((int)x);
+#else
+    return x ? (u32)__builtin_clz(x) : 32u;
+#endif
+}
+RC_HD u32 rc_umulhi(u32 a, u32 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (u32)(((u64)a * b) >> 32);
+#endif
+}
+RC_HD u32 rc_bswap(u32 x)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+}
+
+// ------------------------------------------------------------------- division --
+// t = range / total is the one divide per symbol (cpprcoder.h:401, :501, :703, :904).
+// magic = floor(2^32 / d) gives q or q-1 from one mulhi; one compare repairs it.
+// d == 1 uses magic 0xFFFFFFFF and is repaired by the same compare.
+RC_HD u32 rc_magic(u32 d)
+{
+    if(d <= 1) {
+        return 0xFFFFFFFFu;
+    }
+    u32 m = 0xFFFFFFFFu / d;
+    if((d & (d - 1)) == 0) {  // d divides 2^32
+        m += 1;
+    }
+    return m;
+}
+RC_HD u32 rc_div(u32 x, u32 d, u32 magic)
+{
+    u32 q = rc_umulhi(x, magic);
+    u32 r = x - q * d;
+    return q + (r >= d ? 1u : 0u);
+}
+
+// -------------------------------------------------------------------- encoder --
+// Carry-save restatement of RangeEncoder::encode (cpprcoder.h:400-457) and
+// AdaptiveRangeEncoder::encode/normalize/finish (cpprcoder.h:697-802).
+//
+// The coded bytes are one big-endian integer: sum over symbols of cum*t placed at
+// the byte position the renormalisation shifts define.  The lane keeps the tail of
+// that integer in a shift register  o(64) : low(32);  `ocnt` bits of o are valid.
+// Whenever 32 valid bits have left `low` they are cut off as one stream word.
+// A carry out of `low` ripples into o by plain addition; a carry out of o's valid
+// bits is parked just above them and is applied, when the next word is cut, to the
+// newest word that is not all ones (`pend`) -- all-ones words after it are only
+// counted (`nff`), which is the reference's buffer_/count_ idea at word size.
+struct RcEnc {
+    u32 low, range;
+    u32 o_lo, o_hi;
+    s32 ocnt;       // valid bits in o (multiple of 8, < 32 between steps)
+    u32 pend, nff;  // deferred word and the number of 0xFFFFFFFF words behind it
+    u32 has_pend;
+};
+
+RC_HD void rc_enc_init(RcEnc& e, u32 range0)
+{
+    e.low = 0;
+    e.range = range0;
+    e.o_lo = 0;
+    e.o_hi = 0;
+    e.ocnt = 8;  // the reference's initial buffer_ = 0 is the first stream byte (cpprcoder.h:385, :687)
+    e.pend = 0;
+    e.nff = 0;
+    e.has_pend = 0;
+}
+
+// Rare part of cutting a word: a parked carry, or all-ones words in play.  Kept out
+// of line so the 64-times-unrolled hot loops stay small.
+template <class Sink>
+RC_COLD void rc_enc_word_slow(RcEnc& e, u32 word, u32 ovf, Sink& s)
+{
+    if(ovf) {  // cpprcoder.h:405-415 / :767-781 at word granularity
+        e.pend += ovf;
+        if(e.nff) {
+            s.push(e.pend);
+            for(u32 i = 1; i < e.nff; ++i) {
+                s.push(0u);
+            }
+            e.pend = 0;
+            e.nff = 0;
+        }
+    }
+    if(word == 0xFFFFFFFFu && e.has_pend) {
+        e.nff += 1;  // cpprcoder.h:431 / :796
+        return;
+    }
+    if(e.has_pend) {  // cpprcoder.h:420-428 / :785-794
+        s.push(e.pend);
+        for(u32 i = 0; i < e.nff; ++i) {
+            s.push(0xFFFFFFFFu);
+        }
+    }
+    e.pend = word;
+    e.nff = 0;
+    e.has_pend = 1;
+}
+
+// One symbol: cum/freq from the model, t = range / total already divided.
+template <class Sink>
+RC_HD void rc_enc_step(RcEnc& e, u32 cum, u32 freq, u32 t, Sink& s)
+{
+    const u32 nl = e.low + cum * t;
+    const u32 c = (nl < e.low) ? 1u : 0u;
+    e.low = nl;
+    const u32 ol = e.o_lo + c;
+    e.o_hi += (ol < c) ? 1u : 0u;
+    e.o_lo = ol;
+    e.range = freq * t;
+    const u32 sh = rc_clz(e.range) & 24u;  // 8 bits per renormalisation round (cpprcoder.h:418, :783)
+    e.o_hi = rc_funnel_l(e.o_lo, e.o_hi, sh);
+    e.o_lo = rc_funnel_l(e.low, e.o_lo, sh);
+    e.low <<= sh;
+    e.range <<= sh;
+    e.ocnt += (s32)sh;
+    if(e.ocnt >= 32) {
+        const u32 k = (u32)e.ocnt - 32u;  // 0..23
+        const u32 word = rc_funnel_r(e.o_lo, e.o_hi, k);
+        const u32 ovf = e.o_hi >> k;
+        e.o_hi = 0;
+        e.o_lo &= (1u << k) - 1u;
+        e.ocnt = (s32)k;
+        if((ovf | e.nff) != 0u || word == 0xFFFFFFFFu || !e.has_pend) {
+            rc_enc_word_slow(e, word, ovf, s);
+        } else {
+            s.push(e.pend);
+            e.pend = word;
+        }
+    }
+}
+
+// End of block (cpprcoder.h:439-457 / :744-762).  Pushes the deferred words and
+// returns the bytes that do not fill a word: `tail[0..ntail)`, ntail in 4..7.
+// The caller must have dealt with the static coder's low_ == 0xFFFFFFFF quirk
+// (cpprcoder.h:440-443) BEFORE calling: that case is re-encoded by rc_static_encode_exact.
+template <class Sink>
+RC_HD u32 rc_enc_finish(RcEnc& e, Sink& s, u8 tail[8])
+{
+    const u64 o = ((u64)e.o_hi << 32) | e.o_lo;
+    const u32 ovf = (u32)(o >> e.ocnt);
+    if(ovf) {
+        e.pend += ovf;
+        if(e.nff) {
+            s.push(e.pend);
+            for(u32 i = 1; i < e.nff; ++i) {
+                s.push(0u);
+            }
+            e.pend = 0;
+            e.nff = 0;
+        }
+    }
+    if(e.has_pend) {
+        s.push(e.pend);
+        for(u32 i = 0; i < e.nff; ++i) {
+            s.push(0xFFFFFFFFu);
+        }
+    }
+    u32 n = 0;
+    for(s32 b = e.ocnt - 8; b >= 0; b -= 8) {
+        tail[n++] = (u8)(e.o_lo >> b);
+    }
+    tail[n++] = (u8)(e.low >> 24);
+    tail[n++] = (u8)(e.low >> 16);
+    tail[n++] = (u8)(e.low >> 8);
+    tail[n++] = (u8)(e.low);
+    return n;
+}
+
+// Reference-shaped byte-at-a-time static encoder for ONE block.  Used only for the
+// 2^-32 flush quirk (final low_ == 0xFFFFFFFF, cpprcoder.h:439-451), where the
+// reference's output is NOT the big-endian sum, and as a cross-check in tests.
+// cum[257] is the exclusive prefix of the block's frequencies.  `put(byte)` appends.
+template <class CumAt, class SymAt, class Put>
+RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, Put put)
+{
+    u32 range = RC_STATIC_RANGE0, low = 0, run = 0, held = 0;
+    const u32 magic = rc_magic(total);
+    for(u32 i = 0; i < n; ++i) {
+        const u32 c = sym_at(i);
+        const u32 t = rc_div(range, total, magic);
+        const u32 lo_c = cum_at(c);
+        const u32 next = low + lo_c * t;
+        range = (cum_at(c + 1) - lo_c) * t;
+        if(next < low) {
+            ++held;
+            for(; run != 0; --run) {
+                put((u8)held);
+                held = 0;
+            }
+        }
+        low = next;
+        while(range < RC_MIN_RANGE) {
+            if(low < 0xFF000000u) {
+                put((u8)held);
+                for(; run != 0; --run) {
+                    put((u8)0xFF);
+                }
+                held = low >> 24;
+            } else {
+                ++run;
+            }
+            low <<= 8;
+            range <<= 8;
+        }
+    }
+    u8 fill = 0xFF;
+    if(low == 0xFFFFFFFFu) {
+        ++held;
+        fill = 0;
+    }
+    put((u8)held);
+    for(; run != 0; --run) {
+        put(fill);
+    }
+    put((u8)(low >> 24));
+    put((u8)(low >> 16));
+    put((u8)(low >> 8));
+    put((u8)low);
+}
+
+// -------------------------------------------------------------------- decoder --
+// Restates the state handling of RangeEncoder::decode (cpprcoder.h:494-517) and
+// AdaptiveRangeDecoder::decode/normalize (cpprcoder.h:889-917, :926-940).
+// Input bytes wait in a 64-bit big-endian window (`wbits` valid bits, kept >= 32)
+// that is topped up one aligned stream word at a time.
+struct RcDec {
+    u32 low, range;
+    u32 w_hi, w_lo;
+    s32 wbits;
+};
+
+// `next()` returns the next 4 stream bytes as a big-endian word (zeros past the end).
+// `skip` = bytes of the first word that precede the coded stream (0..3).
+// Both coders start with low = coded bytes 1..4: the static decoder skips byte 0
+// outright (cpprcoder.h:494-498); the adaptive one loads bytes 0..3 and its first
+// normalize shifts byte 0 (always 0) out while pulling byte 4 (cpprcoder.h:889-892, :929-938).
+template <class Next>
+RC_HD void rc_dec_init(RcDec& d, u32 range0, u32 skip, Next& next)
+{
+    d.w_hi = next();
+    d.w_lo = next();
+    const u32 drop = (skip + 1u) * 8u;  // alignment bytes + the dummy first byte
+    if(drop == 32u) {
+        d.w_hi = d.w_lo;
+        d.w_lo = next();
+    } else {
+        d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, drop);
+        d.w_lo <<= drop;
+        const u32 w = next();  // window holds 64 - drop bits; append 32 more below them
+        d.w_lo |= w >> (32u - drop);
+        d.low = d.w_hi;
+        d.w_hi = d.w_lo;
+        d.w_lo = w << drop;
+        d.wbits = 64 - (s32)drop;
+        d.range = range0;
+        return;
+    }
+    d.low = d.w_hi;
+    d.w_hi = d.w_lo;
+    d.w_lo = 0;
+    d.wbits = 32;
+    d.range = range0;
+}
+
+// After the symbol is known: low -= cum*t, range = freq*t, renormalise, refill.
+template <class Next>
+RC_HD void rc_dec_advance(RcDec& d, u32 cum, u32 freq, u32 t, Next& next)
+{
+    d.low -= cum * t;
+    d.range = freq * t;
+    const u32 sh = rc_clz(d.range) & 24u;
+    d.range <<= sh;
+    d.low = rc_funnel_l(d.w_hi, d.low, sh);
+    d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);
+    d.w_lo <<= sh;
+    d.wbits -= (s32)sh;
+    if(d.wbits < 32) {  // 8, 16 or 24 valid bits left in w_hi; w_lo is empty
+        const u32 w = next();
+        d.w_hi |= w >> (u32)d.wbits;
+        d.w_lo = w << (32u - (u32)d.wbits);
+        d.wbits += 32;
+    }
+}
+
+// ------------------------------------------------------------- adaptive model --
+// AdaptiveFrequencyTable (cpprcoder.h:256-314, :1094-1261) for blocks short enough
+// that it never halves (total = 256 + i stays below 2^24, cpprcoder.h:1138): then
+//     freq_i(c) = 1 + #{j < i : b_j == c}        cum_i(c) = c + #{j < i : b_j < c}.
+// Only the counts are stored; the "+1 per symbol" of initialize() is implicit.
+//
+// Encoder side: a binary tree of left-subtree counts.  Node (256|b) >> (l+1) holds
+// how many symbols so far share b's bits above l and have bit l clear.  One walk
+// both answers #{b_j < b} (sum the nodes where b's bit is set) and records b
+// (increment the nodes where it is clear): 8 table touches instead of the
+// reference's up-to-15 adds plus up-to-16 prefix increments (cpprcoder.h:1156-1159,
+// :1179-1187).  Entries 256..511 are the per-symbol counts.
+template <class Tab>
+RC_HD void rc_model_encode(Tab& tab, u32 b, u32& cum, u32& freq)
+{
+    u32 below = 0;
+    const u32 leaf = 256u | b;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(s32 l = 7; l >= 0; --l) {
+        const u32 id = leaf >> (l + 1);
+        const u32 v = tab.ld(id);
+        if((b >> l) & 1u) {
+            below += v;
+        } else {
+            tab.st(id, v + 1u);
+        }
+    }
+    const u32 f = tab.ld(leaf);
+    tab.st(leaf, f + 1u);
+    cum = b + below;
+    freq = 1u + f;
+}
+
+// Decoder side, same tree: walk down from the root comparing in the product
+// domain -- smallest symbol whose upper bound exceeds low (the scalar branch of
+// AdaptiveFrequencyTable::find, cpprcoder.h:1221-1241, for target < total).
+// (base + left) * t <= low  <=>  base + left <= low / t, and never overflows
+// because (base + left) <= total and total * t <= range.
+template <class Tab>
+RC_HD void rc_model_decode(Tab& tab, u32 low, u32 t, u32& sym, u32& cum, u32& freq)
+{
+    u32 id = 1, base = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(s32 l = 7; l >= 0; --l) {
+        const u32 v = tab.ld(id);
+        const u32 left = v + (1u << l);  // counts + the implicit one per symbol
+        if((base + left) * t <= low) {
+            base += left;
+            id = 2 * id + 1;
+        } else {
+            tab.st(id, v + 1u);
+            id = 2 * id;
+        }
+    }
+    const u32 f = tab.ld(id);  // id is now 256 | symbol
+    tab.st(id, f + 1u);
+    sym = id & 255u;
+    cum = base;
+    freq = 1u + f;
+}

@@ -1,0 +1,129 @@
+/*
+ * b2rc.h -- C ABI of the B200-native block range coder (libb2rc.so).
+ *
+ * This is the drop-in boundary for the range-coder hot path of taqu/cpprcoder.
+ * The reference has no FFI: its boundary is the C++ class API of cpprcoder.h
+ *     RangeEncoder<T>::encode / ::decode                 (cpprcoder.h:336-337)
+ *     AdaptiveRangeEncoder<T>::initialize / ::encode     (cpprcoder.h:636-638)
+ *     AdaptiveRangeDecoder<T>::initialize / ::decode     (cpprcoder.h:819-820)
+ * cpprcoder_b200/include/cpprcoder_b200.h re-creates those classes on top of the
+ * functions below (INTEGRATION.md shows the binding).  Plain pointers and sizes
+ * only; no CUDA or torch types appear in the signatures (a CUDA stream is passed
+ * as void*).  There is NO CPU fallback: every entry point that does work needs a
+ * CUDA device and returns B2RC_E_CUDA without one.
+ *
+ * Framing ("B2RC" container, little endian; ours -- the reference codes one stream):
+ *     0   u32  magic 'B','2','R','C'
+ *     4   u16  version (1)          6  u16 mode (0 static, 1 adaptive)
+ *     8   u32  block_size          12  u32 flags (0)
+ *     16  u64  total_uncompressed  24  u64 nblocks
+ *     32  u64  offsets[nblocks+1]  relative to the payload base, offsets[0] = 0
+ *     32 + 8*(nblocks+1)           payloads, back to back
+ * Payload b is byte-for-byte what the reference encoder emits for block b alone:
+ * static  = u32 LE size, 256 x u16 LE frequencies, coded bytes  (cpprcoder.h:386-457)
+ * adaptive = u32 LE size, coded bytes                            (cpprcoder.h:689-762)
+ * The last block may be short; an empty input has zero blocks.
+ */
+#ifndef B2RC_H_
+#define B2RC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2RC_MODE_STATIC 0   /* RangeEncoder<T>          cpprcoder.h:321-619 */
+#define B2RC_MODE_ADAPTIVE 1 /* AdaptiveRangeEncoder/Decoder<T>  cpprcoder.h:626-940 */
+
+#define B2RC_DEFAULT_BLOCK 65536u
+#define B2RC_MIN_BLOCK 64u          /* block_size must be a multiple of 64 ... */
+#define B2RC_MAX_BLOCK (1u << 23)   /* ... and small enough that neither model rescales by size
+                                       (cpprcoder.h:561, :1138) */
+#define B2RC_HEADER_BYTES 32u
+
+/* Status codes.  0 = the reference's `true` / Status_Success (cpprcoder.h:112-117);
+ * negatives map to `false` / Status_Error in the C++ header. */
+#define B2RC_OK 0
+#define B2RC_E_ARG (-1)      /* null pointer, bad mode, bad block size, misaligned device pointer */
+#define B2RC_E_DST_SMALL (-2) /* dst capacity too small; *out_n holds the size needed (when known) */
+#define B2RC_E_CORRUPT (-3)  /* container or payload fails validation */
+#define B2RC_E_CUDA (-4)     /* CUDA runtime error, or no device */
+#define B2RC_E_EXPAND (-5)   /* a block's payload outgrew its staging slot (pathological input);
+                                the reference fails the same way when its MemoryStream is full
+                                (cpprcoder.h:409-411, :1047-1051) */
+#define B2RC_E_NOMEM (-6)
+
+typedef struct b2rc_ctx b2rc_ctx;
+
+/* One context per host thread and device.  Owns the device scratch (staging slots,
+ * per-block sizes, frequency tables) and a stream of its own for the host-pointer calls. */
+int b2rc_ctx_create(int device, b2rc_ctx** out);
+void b2rc_ctx_destroy(b2rc_ctx* ctx);
+const char* b2rc_strerror(int code);
+/* Last CUDA error text seen by this context ("" if none). */
+const char* b2rc_last_cuda_error(const b2rc_ctx* ctx);
+
+/* Sizes.  b2rc_bound: capacity that always suffices for b2rc_encode*(n bytes).
+ * b2rc_slot_bytes: staging slot (and per-block payload bound) for a block of n bytes. */
+uint64_t b2rc_bound(int mode, uint64_t n, uint32_t block_size);
+uint64_t b2rc_slot_bytes(uint32_t n);
+uint64_t b2rc_nblocks(uint64_t n, uint32_t block_size);
+
+/* ---- whole-container calls, HOST pointers (what the C++ drop-in classes call) ----
+ * replaces RangeEncoder<T>::encode (cpprcoder.h:375) and
+ * AdaptiveRangeEncoder<T>::initialize+encode (cpprcoder.h:678, :697). */
+int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src, uint64_t n, uint8_t* dst,
+                uint64_t dst_cap, uint64_t* out_n);
+/* replaces RangeEncoder<T>::decode (cpprcoder.h:460) and AdaptiveRangeDecoder<T>::decode
+ * (cpprcoder.h:872).  mode and block size come from the container header. */
+int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n);
+/* Parses a container header held in host memory. */
+int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, uint64_t* total, uint64_t* nblocks);
+
+/* ---- whole-container calls, DEVICE pointers (what bench.py times as `value`) ----
+ * d_src / d_dst must be 16-byte aligned.  `cuda_stream` is a cudaStream_t (NULL = the
+ * legacy default stream, as everywhere in CUDA).  The calls return after the stream has drained. */
+int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
+                       uint8_t* d_dst, uint64_t dst_cap, uint64_t* out_n, void* cuda_stream);
+int b2rc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t dst_cap,
+                       uint64_t* out_n, void* cuda_stream);
+
+/* ---- per-kernel entry points (parity tests, ncu, multi-GPU sharding) ----
+ * All pointers are device pointers; launches are asynchronous on `cuda_stream`
+ * unless stated.  `d_err` is one int the kernels OR error bits into (0 = clean).
+ *
+ * K1  b2rc_k_histogram: per-block symbol counts with the reference's scaling rule,
+ *     RangeEncoder::count (cpprcoder.h:543-571), for block_size <= 65536.
+ *     d_freq16[b*256 + s] = u16 frequency of symbol s in block b. */
+int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t block_size, uint16_t* d_freq16,
+                     void* cuda_stream);
+/* K2  b2rc_k_encode_blocks: block b's payload -> d_slots + b*slot_stride, its length ->
+ *     d_sizes[b].  Static mode with block_size <= 65536 needs d_freq16 from K1; larger
+ *     static blocks count inside the kernel (pass NULL).  slot_stride >= b2rc_slot_bytes(block_size),
+ *     multiple of 16. */
+int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
+                         const uint16_t* d_freq16, uint8_t* d_slots, uint64_t slot_stride, uint32_t* d_sizes,
+                         int* d_err, void* cuda_stream);
+/* K4  b2rc_k_scan: d_offsets[0..nblocks] = exclusive prefix of d_sizes (u64).
+ *     b2rc_k_compact: payload b -> d_payload + d_offsets[b] (payload_cap bytes available). */
+int b2rc_k_scan(b2rc_ctx* ctx, const uint32_t* d_sizes, uint64_t nblocks, uint64_t* d_offsets, void* cuda_stream);
+int b2rc_k_compact(b2rc_ctx* ctx, const uint8_t* d_slots, uint64_t slot_stride, const uint32_t* d_sizes,
+                   const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_payload, uint64_t payload_cap, int* d_err,
+                   void* cuda_stream);
+/* K3  b2rc_k_decode_blocks: payload b = d_payload[d_offsets[b] .. d_offsets[b+1]) -> block b of d_dst
+ *     (n bytes in all, 16-byte aligned).  Offsets beyond payload_len mark the block corrupt. */
+int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload,
+                         uint64_t payload_len, const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n,
+                         int* d_err, void* cuda_stream);
+
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+uint64_t b2rc_launch_count(const b2rc_ctx* ctx);
+/* "sm_100a" etc.: the architecture the kernels were compiled for. */
+const char* b2rc_build_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

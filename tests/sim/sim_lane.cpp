@@ -1,0 +1,197 @@
+// sim_lane.cpp -- drives cpprcoder_b200/csrc/rc_lane.cuh on the CPU, one block at
+// a time, so the lane arithmetic the kernels run (carry-save encoder, windowed
+// decoder, count-tree model, magic division) can be checked against the oracle
+// without a GPU.  TEST INFRASTRUCTURE: built and loaded by tests/test_sim_lane.py only.
+#include "../../cpprcoder_b200/csrc/rc_lane.cuh"
+
+#include <cstring>
+#include <vector>
+
+namespace
+{
+struct VecSink {
+    std::vector<u8>* out;
+    void push(u32 w)
+    {
+        out->push_back((u8)(w >> 24));
+        out->push_back((u8)(w >> 16));
+        out->push_back((u8)(w >> 8));
+        out->push_back((u8)w);
+    }
+};
+
+struct ArrTab {
+    u32 v[512];
+    u32 ld(u32 i) const { return v[i]; }
+    void st(u32 i, u32 x) { v[i] = x; }
+};
+
+// static count for blocks of at most 65536 bytes (the K1 rule)
+void count64k(const u8* src, u32 n, u32 freq[256])
+{
+    memset(freq, 0, 256 * sizeof(u32));
+    for(u32 i = 0; i < n; ++i) {
+        freq[src[i]]++;
+    }
+    for(int s = 0; s < 256; ++s) {
+        if(freq[s] >= 0x10000u) {
+            freq[s] = 0x8000u;
+        }
+    }
+}
+
+struct WordReader {
+    const u8* p;
+    size_t n, pos;  // pos = byte index of the next aligned word
+    u32 operator()()
+    {
+        u32 w = 0;
+        for(int k = 0; k < 4; ++k) {
+            const size_t at = pos + k;
+            w = (w << 8) | (at < n ? p[at] : 0u);
+        }
+        pos += 4;
+        return w;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+// mode 0 static (n <= 65536), 1 adaptive.  force_exact: use the reference-shaped path.
+long sim_encode(int mode, const u8* src, u32 n, u8* dst, size_t cap, int force_exact)
+{
+    std::vector<u8> out;
+    out.push_back((u8)n);
+    out.push_back((u8)(n >> 8));
+    out.push_back((u8)(n >> 16));
+    out.push_back((u8)(n >> 24));
+    VecSink sink{&out};
+    RcEnc e;
+    u8 tail[8];
+    if(mode == 0) {
+        u32 freq[256], cum[257];
+        count64k(src, n, freq);
+        u32 run = 0;
+        for(int s = 0; s < 256; ++s) {
+            out.push_back((u8)freq[s]);
+            out.push_back((u8)(freq[s] >> 8));
+            cum[s] = run;
+            run += freq[s];
+        }
+        cum[256] = run;
+        const u32 total = run;
+        const u32 magic = rc_magic(total);
+        const bool pow2 = total && (total & (total - 1)) == 0;
+        const u32 shT = pow2 ? 31u - rc_clz(total) : 0;
+        rc_enc_init(e, RC_STATIC_RANGE0);
+        if(!force_exact) {
+            for(u32 i = 0; i < n; ++i) {
+                const u32 c = src[i];
+                const u32 t = pow2 ? (e.range >> shT) : rc_div(e.range, total, magic);
+                rc_enc_step(e, cum[c], cum[c + 1] - cum[c], t, sink);
+            }
+        }
+        if(force_exact || e.low == 0xFFFFFFFFu) {
+            out.resize(RC_STATIC_HDR);
+            rc_static_encode_exact(
+                n, total, [&](u32 c) { return cum[c]; }, [&](u32 i) { return (u32)src[i]; },
+                [&](u8 b) { out.push_back(b); });
+        } else {
+            const u32 nt = rc_enc_finish(e, sink, tail);
+            out.insert(out.end(), tail, tail + nt);
+        }
+    } else {
+        ArrTab tab;
+        memset(tab.v, 0, sizeof tab.v);
+        rc_enc_init(e, RC_ADAPT_RANGE0);
+        for(u32 i = 0; i < n; ++i) {
+            u32 cum, freq;
+            rc_model_encode(tab, src[i], cum, freq);
+            const u32 d = 256u + i;
+            const u32 t = rc_div(e.range, d, rc_magic(d));
+            rc_enc_step(e, cum, freq, t, sink);
+        }
+        const u32 nt = rc_enc_finish(e, sink, tail);
+        out.insert(out.end(), tail, tail + nt);
+    }
+    if(out.size() > cap) {
+        return -1;
+    }
+    memcpy(dst, out.data(), out.size());
+    return (long)out.size();
+}
+
+// `lead` = how many bytes precede the payload inside an (aligned) stream, to exercise
+// the misaligned-start path of rc_dec_init.  src points at the aligned stream start.
+long sim_decode(int mode, const u8* stream, size_t stream_len, u32 lead, u8* dst, size_t cap)
+{
+    const u8* pay = stream + lead;
+    const u32 want = (u32)pay[0] | ((u32)pay[1] << 8) | ((u32)pay[2] << 16) | ((u32)pay[3] << 24);
+    if(want > cap) {
+        return -1;
+    }
+    if(want == 0) {
+        return 0;
+    }
+    const u32 hdr = mode == 0 ? RC_STATIC_HDR : RC_ADAPT_HDR;
+    const size_t coded = lead + hdr;  // byte index of coded byte 0 within the stream
+    WordReader rd{stream, stream_len, coded & ~(size_t)3};
+    RcDec d;
+    if(mode == 0) {
+        u32 cum[257];
+        u32 run = 0;
+        for(int s = 0; s < 256; ++s) {
+            cum[s] = run;
+            run += (u32)pay[4 + 2 * s] | ((u32)pay[5 + 2 * s] << 8);
+        }
+        cum[256] = run;
+        const u32 total = run;
+        if(total == 0) {
+            return -1;
+        }
+        const u32 magic = rc_magic(total);
+        rc_dec_init(d, RC_STATIC_RANGE0, (u32)(coded & 3), rd);
+        for(u32 i = 0; i < want; ++i) {
+            const u32 t = rc_div(d.range, total, magic);
+            // two-level 16-ary search in the product domain, as the kernel does it
+            u32 k = 0;
+            for(u32 j = 1; j < 16; ++j) {
+                k += (cum[16 * j] * t <= d.low) ? 1u : 0u;
+            }
+            u32 s = 0;
+            for(u32 j = 1; j < 16; ++j) {
+                s += (cum[16 * k + j] * t <= d.low) ? 1u : 0u;
+            }
+            const u32 sym = 16 * k + s;
+            dst[i] = (u8)sym;
+            rc_dec_advance(d, cum[sym], cum[sym + 1] - cum[sym], t, rd);
+        }
+    } else {
+        ArrTab tab;
+        memset(tab.v, 0, sizeof tab.v);
+        rc_dec_init(d, RC_ADAPT_RANGE0, (u32)(coded & 3), rd);
+        for(u32 i = 0; i < want; ++i) {
+            const u32 dd = 256u + i;
+            const u32 t = rc_div(d.range, dd, rc_magic(dd));
+            u32 sym, cum, freq;
+            rc_model_decode(tab, d.low, t, sym, cum, freq);
+            dst[i] = (u8)sym;
+            rc_dec_advance(d, cum, freq, t, rd);
+        }
+    }
+    return (long)want;
+}
+
+// exhaustive-ish check of the magic division; returns the number of mismatches
+u64 sim_check_div(u32 d, u32 x0, u32 step, u32 count)
+{
+    const u32 m = rc_magic(d);
+    u64 bad = 0;
+    u32 x = x0;
+    for(u32 i = 0; i < count; ++i, x += step) {
+        bad += (rc_div(x, d, m) != x / d) ? 1u : 0u;
+    }
+    return bad;
+}
+}

@@ -1,0 +1,35 @@
+import numpy as np
+import pytest
+
+from cpprcoder_b200 import container
+
+
+def test_round_trip_and_validation():
+    pays = [b"abc", b"", b"defgh"]
+    with pytest.raises(ValueError):
+        container.build(0, 64, 100, pays)  # 100 bytes at block 64 is 2 blocks, not 3
+    c = container.build(0, 64, 130, pays)
+    info = container.parse(c)
+    assert (info.mode, info.block, info.total, info.nblocks) == (0, 64, 130, 3)
+    assert [bytes(info.payload(c, b)) for b in range(3)] == pays
+    bad = c.copy()
+    bad[32 + 8] = 9  # offsets[1] > offsets[2]
+    with pytest.raises(ValueError):
+        container.parse(bad)
+    with pytest.raises(ValueError):
+        container.parse(c[:40])
+
+
+def test_shard_ranges_tile_the_blocks():
+    for nb in (0, 1, 7, 49, 16384):
+        for world in (1, 2, 3, 4, 8):
+            spans = [container.shard_range(nb, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == nb
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_merge_sizes():
+    off = container.merge_sizes([[3, 4], [], [5]])
+    assert off.tolist() == [0, 3, 7, 12]
+    assert container.merge_sizes([]).tolist() == [0]

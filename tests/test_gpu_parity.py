@@ -1,0 +1,213 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libb2rc.so), against the
+oracle on the same inputs -- bit exact, per block.  Run on the B200 with `-m gpu`."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from _cases import crafted, crafted_stream
+from _oracle import ADAPTIVE, CANTERBURY, STATIC, Oracle, canterbury, fnv1a64, offsets_of
+from cpprcoder_b200 import container, synth
+
+pytestmark = pytest.mark.gpu
+MODES = [(STATIC, "static"), (ADAPTIVE, "adaptive")]
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    import torch
+    from cpprcoder_b200 import api
+    built.build_native()
+    assert torch.cuda.is_available()
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def oracle(built):
+    return Oracle.get()
+
+
+def payloads_of(buf: np.ndarray):
+    info = container.parse(buf)
+    return info, [bytes(info.payload(buf, b)) for b in range(info.nblocks)]
+
+
+def assert_blocks_equal(got, want, what):
+    assert len(got) == len(want), what
+    for b, (g, w) in enumerate(zip(got, want)):
+        if g != w:
+            k = next((i for i in range(min(len(g), len(w))) if g[i] != w[i]), min(len(g), len(w)))
+            raise AssertionError(f"{what}: block {b} differs at byte {k} (sizes {len(g)} vs {len(w)})")
+
+
+# ------------------------------------------------------------------ config 1 + 2 --
+@pytest.mark.parametrize("name", CANTERBURY)
+def test_canterbury_every_block_is_the_reference_payload(ctx, oracle, golden, name):
+    data = np.frombuffer(canterbury(name), dtype=np.uint8)
+    ent = golden["canterbury"][name]
+    for mode, key in MODES:
+        enc = ctx.encode(mode, data, 65536)
+        info, pays = payloads_of(enc)
+        assert (info.mode, info.block, info.total) == (mode, 65536, data.size)
+        assert [len(p) for p in pays] == ent["blocks64k"][key]["sizes"]
+        assert [f"{fnv1a64(p):016x}" for p in pays] == ent["blocks64k"][key]["fnv"]  # golden = unmodified reference
+        assert_blocks_equal(pays, oracle.encode_blocks(mode, data, 65536), f"{name}/{key}")
+        assert ctx.decode(enc).tobytes() == data.tobytes()
+
+
+def test_alice29_single_block_equals_whole_file_reference_output(ctx, golden):
+    # config 1: one block >= the file => the payload IS the reference's whole-file stream (87380 B, ratio 0.574532)
+    data = np.frombuffer(canterbury("alice29.txt"), dtype=np.uint8)
+    for mode, key in MODES:
+        enc = ctx.encode(mode, data, 1 << 18)
+        _, pays = payloads_of(enc)
+        assert len(pays) == 1
+        want = golden["canterbury"]["alice29.txt"]["whole"][key]
+        assert len(pays[0]) == want["size"] and f"{fnv1a64(pays[0]):016x}" == want["fnv"]
+        assert ctx.decode(enc).tobytes() == data.tobytes()
+
+
+# ------------------------------------------------------------- crafted / ragged --
+@pytest.mark.parametrize("block,nblocks,ragged", [(65536, 70, 12345), (65536, 33, 0), (4096, 200, 1), (16384, 64, 16383),
+                                                  (64, 300, 7), (1024, 31, 0)])
+def test_crafted_streams_match_oracle(ctx, oracle, block, nblocks, ragged):
+    data = crafted_stream(nblocks, block, seed=block + nblocks, ragged=ragged)
+    for mode, key in MODES:
+        enc = ctx.encode(mode, data, block)
+        _, pays = payloads_of(enc)
+        assert_blocks_equal(pays, oracle.encode_blocks(mode, data, block, threads=4), f"crafted {block}/{key}")
+        assert ctx.decode(enc).tobytes() == data.tobytes()
+
+
+@pytest.mark.parametrize("block", [131072, 262144, 1048576])
+def test_blocks_above_64k_follow_the_order_dependent_count(ctx, oracle, block):
+    # kennedy-like data: 44 % zeros => RangeEncoder::count halves (cpprcoder.h:549-555) inside every block
+    data = synth.kennedy(3 * block + 4097)
+    _, events = oracle.static_count(data[:block])
+    assert events >= 1
+    parts = [data, np.concatenate([crafted(5, block, np.random.default_rng(3)), crafted(6, block // 2, np.random.default_rng(4))])]
+    for d in parts:
+        for mode, key in MODES:
+            enc = ctx.encode(mode, d, block)
+            _, pays = payloads_of(enc)
+            assert_blocks_equal(pays, oracle.encode_blocks(mode, d, block, threads=4), f"wide {block}/{key}")
+            assert ctx.decode(enc).tobytes() == d.tobytes()
+
+
+def test_edges(ctx, oracle):
+    for d in [b"", b"A", b"AB" * 32, b"A" * 65535, b"A" * 65536, b"A" * 65537, b"\xff" * 65536, bytes(range(256)) * 3]:
+        data = np.frombuffer(d, dtype=np.uint8)
+        for mode, key in MODES:
+            enc = ctx.encode(mode, data, 65536)
+            info, pays = payloads_of(enc)
+            assert info.nblocks == (len(d) + 65535) // 65536  # never an empty block
+            assert_blocks_equal(pays, oracle.encode_blocks(mode, data, 65536), f"edge {len(d)}/{key}")
+            assert ctx.decode(enc).tobytes() == d
+
+
+def test_synthetic_golden_vectors(ctx, golden):
+    for ent in golden["synthetic"]:
+        d = synth.GENERATORS[ent["gen"]](ent["n"])
+        mode = STATIC if ent["mode"] == "static" else ADAPTIVE
+        enc = ctx.encode(mode, d, ent["block"])
+        _, pays = payloads_of(enc)
+        assert [len(p) for p in pays] == ent["sizes"], (ent["gen"], ent["block"], ent["mode"])
+        assert f"{fnv1a64(b''.join(pays)):016x}" == ent["cat_fnv"]
+
+
+# ----------------------------------------------------------------- kernel doors --
+def test_kernel_doors_step_by_step(ctx, oracle):
+    import torch
+    block = 65536
+    data = crafted_stream(40, block, seed=99, ragged=777)
+    n = data.size
+    nb = (n + block - 1) // block
+    src = torch.from_numpy(data).cuda()
+    # K1 against RangeEncoder::count
+    f16 = ctx.histogram(src, block).cpu().numpy().view(np.uint16)
+    for b in range(nb):
+        want, _ = oracle.static_count(data[b * block:(b + 1) * block])
+        assert (f16[b].astype(np.uint32) == want).all(), f"histogram of block {b}"
+    for mode, key in MODES:
+        slots, stride, sizes, err = ctx.encode_blocks(mode, src, block)
+        offsets = ctx.scan(sizes, nb)
+        total = int(offsets[nb].item())
+        want = oracle.encode_blocks(mode, data, block, threads=4)
+        assert sizes[:nb].cpu().tolist() == [len(p) for p in want]
+        assert offsets.cpu().tolist() == offsets_of(want).tolist()
+        payload = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+        # unaligned destination: compaction must cope with any byte offset
+        ctx.compact(slots, stride, sizes, offsets, nb, payload[3:], err)
+        assert int(err[0].item()) == 0
+        assert payload[3:3 + total].cpu().numpy().tobytes() == b"".join(want)
+        dst = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        derr = ctx.decode_blocks(mode, payload[3:], total, offsets, nb, dst, n, block)
+        assert int(derr[0].item()) == 0
+        assert dst.cpu().numpy().tobytes() == data.tobytes()
+
+
+# ------------------------------------------------------ full size, by properties --
+@pytest.mark.parametrize("gen,mode", [("zipf", STATIC), ("mixed", ADAPTIVE)])
+def test_full_size_round_trip_and_sampled_blocks(ctx, oracle, gen, mode):
+    import torch
+    n = (1 << 28) + 4321  # 256 MiB + ragged tail, device resident
+    data = synth.GENERATORS[gen](n)
+    src = torch.from_numpy(data).cuda()
+    enc, used = ctx.encode_device(mode, src)
+    head = enc[:used].cpu().numpy()
+    info = container.parse(head)
+    assert info.total == n and info.nblocks == (n + 65535) // 65536
+    sizes = np.diff(info.offsets.astype(np.int64))
+    hdr = 521 if mode == STATIC else 9
+    assert sizes.min() >= hdr and sizes.max() <= 65536 + 65536 // 8 + 1024
+    for b in list(range(0, info.nblocks, 257)) + [info.nblocks - 1]:  # sampled blocks, byte exact
+        want = oracle.encode(mode, data[b * 65536:(b + 1) * 65536])
+        assert bytes(info.payload(head, b)) == want, f"block {b}"
+    dst = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert ctx.decode_device(enc, used, dst) == n
+    assert torch.equal(dst, src)
+
+
+# ----------------------------------------------------------------------- errors --
+def test_error_paths(ctx):
+    import torch
+    from cpprcoder_b200._lib import B2rcError, E_ARG, E_CORRUPT, E_DST_SMALL
+    data = synth.zipf(200000)
+    enc = ctx.encode(STATIC, data, 65536).copy()
+    with pytest.raises(B2rcError) as e:
+        ctx.decode(enc, dst=np.empty(1000, np.uint8))
+    assert e.value.code == E_DST_SMALL
+    bad = enc.copy()
+    bad[0] ^= 0xFF
+    with pytest.raises(B2rcError) as e:
+        ctx.decode(bad)
+    assert e.value.code == E_CORRUPT
+    bad = enc.copy()
+    bad[32 + 8:32 + 16] = 0xFF  # offsets[1] far outside the container
+    with pytest.raises(B2rcError) as e:
+        ctx.decode(bad)
+    assert e.value.code == E_CORRUPT
+    bad = enc.copy()
+    base = 32 + 8 * 5
+    bad[base] ^= 1  # block 0's own size field no longer matches the container
+    with pytest.raises(B2rcError) as e:
+        ctx.decode(bad)
+    assert e.value.code == E_CORRUPT
+    # truncated payload bytes decode to garbage but must neither hang nor fault
+    bad = enc.copy()
+    bad[-2000:] = 0
+    out = ctx.decode(bad)
+    assert out.size == data.size
+    with pytest.raises(B2rcError) as e:
+        ctx.encode(STATIC, data, 1000)  # block size not a multiple of 64
+    assert e.value.code == E_ARG
+    src = torch.from_numpy(data).cuda()
+    with pytest.raises(B2rcError) as e:
+        ctx.encode_device(STATIC, src[1:])  # misaligned device pointer
+    assert e.value.code == E_ARG
+    small = torch.empty(64, dtype=torch.uint8, device="cuda")
+    with pytest.raises(B2rcError) as e:
+        ctx.encode_device(STATIC, src, small)
+    assert e.value.code == E_DST_SMALL

@@ -1,0 +1,78 @@
+"""The lane arithmetic the kernels run (cpprcoder_b200/csrc/rc_lane.cuh), driven on the
+CPU by tests/sim/sim_lane.cpp and checked against the oracle.  This is a test of the
+device code's logic, not a CPU coding path: nothing in the product calls it."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from _cases import crafted
+from _oracle import ADAPTIVE, CANTERBURY, STATIC, Oracle, canterbury, slot_bytes
+
+
+@pytest.fixture(scope="module")
+def sim(built):
+    lib = C.CDLL(str(built.build_sim()))
+    lib.sim_encode.restype = C.c_long
+    lib.sim_encode.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_int]
+    lib.sim_decode.restype = C.c_long
+    lib.sim_decode.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t]
+    lib.sim_check_div.restype = C.c_uint64
+    lib.sim_check_div.argtypes = [C.c_uint32] * 4
+    return lib
+
+
+def _enc(sim, mode, d, exact=0):
+    d = np.ascontiguousarray(d, dtype=np.uint8)
+    cap = slot_bytes(d.size) + 2 * d.size
+    out = np.empty(cap, np.uint8)
+    r = sim.sim_encode(mode, d.ctypes.data_as(C.c_void_p), d.size, out.ctypes.data_as(C.c_void_p), cap, exact)
+    assert r >= 0
+    return out[:r].tobytes()
+
+
+def _dec(sim, mode, pay, n, lead):
+    st = np.frombuffer(bytes(lead) + pay + bytes(3), dtype=np.uint8).copy()
+    st[:lead] = 0xA5
+    out = np.empty(max(n, 1), np.uint8)
+    r = sim.sim_decode(mode, st.ctypes.data_as(C.c_void_p), len(st) - 3, lead, out.ctypes.data_as(C.c_void_p), n)
+    assert r == n
+    return out[:n].tobytes()
+
+
+def test_magic_division_is_exact(sim):
+    rng = np.random.default_rng(5)
+    bad = 0
+    for d in [1, 2, 3, 7, 255, 256, 257, 65535, 65536, 65537, 0x8000, 1000003, (1 << 24) - 1, 1 << 24]:
+        bad += sim.sim_check_div(d, 0, 4099, 1 << 18)
+        bad += sim.sim_check_div(d, 0xFFFC0000, 1, 0x3FFFF)
+    for _ in range(200):
+        bad += sim.sim_check_div(int(rng.integers(1, 1 << 24)), int(rng.integers(0, 1 << 32)),
+                                 int(rng.integers(1, 1 << 16)), 5000)
+    assert bad == 0
+
+
+def test_lane_coder_matches_oracle_on_crafted_blocks(sim):
+    o = Oracle.get()
+    rng = np.random.default_rng(7)
+    for it in range(210):
+        n = 65536 if it % 3 == 0 else int(rng.integers(1, 65537))
+        d = crafted(it % 7, n, rng)
+        for mode in (STATIC, ADAPTIVE):
+            a = o.encode(mode, d)
+            assert _enc(sim, mode, d) == a, (it, mode, n)
+            if mode == STATIC:  # the reference-shaped path used for the low_==0xFFFFFFFF flush quirk
+                assert _enc(sim, STATIC, d, 1) == a
+            assert _dec(sim, mode, a, n, it % 4) == d.tobytes()
+
+
+@pytest.mark.parametrize("name", ["alice29.txt", "kennedy.xls", "ptt5", "xargs.1"])
+def test_lane_coder_on_canterbury_blocks(sim, name):
+    o = Oracle.get()
+    data = canterbury(name)
+    for mode in (STATIC, ADAPTIVE):
+        pays = o.encode_blocks(mode, data, 65536)
+        for i, p in enumerate(pays):
+            blk = data[i * 65536:(i + 1) * 65536]
+            assert _enc(sim, mode, np.frombuffer(blk, np.uint8)) == p
+            assert _dec(sim, mode, p, len(blk), (i + 1) % 4) == blk
