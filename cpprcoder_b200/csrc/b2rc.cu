@@ -106,9 +106,9 @@ constexpr u32 smem_enc_adaptive(bool wide)
 {
     return 512u * 32u * (wide ? 4u : 2u) + 2u * TILE_BYTES + RING_BYTES;
 }
-constexpr u32 smem_dec_static(bool wide)
+constexpr u32 smem_dec_static()
 {
-    return (wide ? 257u : 256u) * 128u + TILE_BYTES + RING_BYTES;
+    return DEC_STATIC_TAB + TILE_BYTES + RING_BYTES;
 }
 constexpr u32 smem_dec_adaptive(bool wide)
 {
@@ -121,8 +121,7 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_enc_static<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_static(true)));
     CK(cudaFuncSetAttribute(k_enc_adaptive<u16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_adaptive(false)));
     CK(cudaFuncSetAttribute(k_enc_adaptive<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_adaptive(true)));
-    CK(cudaFuncSetAttribute(k_dec_static<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static(false)));
-    CK(cudaFuncSetAttribute(k_dec_static<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static(true)));
+    CK(cudaFuncSetAttribute(k_dec_static, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static()));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(false)));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     return B2RC_OK;
@@ -457,11 +456,7 @@ int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     const bool wide = block_size > 65536u;
     const unsigned grid = (unsigned)((nblocks + 31) / 32);
     if(mode == B2RC_MODE_STATIC) {
-        if(wide) {
-            k_dec_static<true><<<grid, 32, smem_dec_static(true), st>>>(a);
-        } else {
-            k_dec_static<false><<<grid, 32, smem_dec_static(false), st>>>(a);
-        }
+        k_dec_static<<<grid, 32, smem_dec_static(), st>>>(a);
     } else {
         if(wide) {
             k_dec_adaptive<u32><<<grid, 32, smem_dec_adaptive(true), st>>>(a);

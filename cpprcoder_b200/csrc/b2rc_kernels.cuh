@@ -9,12 +9,16 @@
 //
 // Mapping: one block per LANE, one warp per CTA, 32
 // consecutive blocks per warp.  The coder's per-symbol chain is serial per block,
-// so throughput comes from the number of chains in flight, not from splitting a
-// block over a warp.  Per-warp shared memory holds
+// so throughput comes from the number of chains in flight and from how few
+// instructions one step of a (lone) warp needs -- not from splitting a block over a
+// warp.  Per-warp shared memory holds
 //   * the model table, interleaved by lane ([entry][lane]: bank == lane),
 //   * input tiles staged by cp.async (encode) / a refilled word ring (decode),
 //   * an output word ring (encode) / an output tile (decode),
 // and all global traffic is done cooperatively by the warp in 128-byte rows.
+// Hot-loop shared-memory accesses use explicit ld/st.shared on 32-bit shared
+// addresses: generic pointers made the compiler rebuild the shared window base
+// (S2UR SR_CgaCtaId) on every step and turned ring stores into generic ST.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -23,12 +27,13 @@
 namespace b2rc
 {
 constexpr u32 FULL = 0xFFFFFFFFu;
-constexpr int TILE = 64;   // symbols per lane per staged tile
-constexpr int ROW = 80;    // bytes per lane row of a tile: 64 + 16, so that the 8 lanes of a
-                           // quarter warp hit 8 disjoint bank groups on 16-byte accesses
-constexpr int RING = 32;   // words per lane in the output (encode) / input (decode) ring
+constexpr int TILE = 64;        // symbols per lane per staged tile
+constexpr int ROW = 80;         // bytes per lane row of a tile (64 + 16 pad; rows stay 16-byte aligned)
+constexpr int RING = 32;        // words per lane in the output (encode) / input (decode) ring
+constexpr int RING_ROW = 33;    // words between two lanes' rings: word i of lane r sits in bank (r + i) & 31,
+                                // so a lane's own accesses and the warp's row-wise sweeps both spread over banks
 constexpr int TILE_BYTES = 32 * ROW;
-constexpr int RING_BYTES = RING * 32 * 4;
+constexpr int RING_BYTES = 32 * RING_ROW * 4;  // 4224, a multiple of 16
 
 enum : int {
     ERR_SLOT_OVERFLOW = 1,  // a payload outgrew its slot
@@ -59,19 +64,45 @@ __device__ __forceinline__ u32 lane_id()
 {
     return threadIdx.x & 31u;
 }
-
-// Table view of one lane: entry i lives at base[i * 32] (base already offset by the lane).
-template <class W>
-struct LaneTab {
-    W* base;
-    __device__ __forceinline__ u32 ld(u32 i) const { return (u32)base[i * 32u]; }
-    __device__ __forceinline__ void st(u32 i, u32 v) { base[i * 32u] = (W)v; }
-};
+// read-only data (static tables, staged input): plain asm, free to be hoisted
+__device__ __forceinline__ u32 lds32(u32 a)
+{
+    u32 v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ u32 lds16(u32 a)
+{
+    u32 v;
+    asm("{ .reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(v) : "r"(a));
+    return v;
+}
+// read-write data (adaptive model, rings): volatile keeps program order among them
+__device__ __forceinline__ u32 lds32v(u32 a)
+{
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ u32 lds16v(u32 a)
+{
+    u32 v;
+    asm volatile("{ .reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32v(u32 a, u32 v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v));
+}
+__device__ __forceinline__ void sts16v(u32 a, u32 v)
+{
+    asm volatile("{ .reg .u16 h; cvt.u16.u32 h, %1; st.shared.u16 [%0], h; }" ::"r"(a), "r"(v));
+}
 
 // Stage tile `tile_off .. tile_off+TILE` of 32 consecutive blocks into shared memory.
 // Row r of the tile is block b0+r; 4 lanes cover one 64-byte row, 8 rows per instruction.
 // Bytes past the end of the block / of the input are zero-filled by cp.async's src-size.
-__device__ __forceinline__ void stage_tile(u8* tile, const u8* src, u64 n, u64 b0, u32 block, u32 tile_off, u32 lane)
+__device__ __forceinline__ void stage_tile(u32 tile, const u8* src, u64 n, u64 b0, u32 block, u32 tile_off, u32 lane)
 {
     constexpr int CH = TILE / 16;
     constexpr int RPI = 32 / CH;
@@ -90,65 +121,91 @@ __device__ __forceinline__ void stage_tile(u8* tile, const u8* src, u64 n, u64 b
             const u64 rem = blk_hi - at;
             bytes = rem >= 16 ? 16u : (u32)rem;
         }
-        cp_async16(smem_addr(tile + row * ROW + ch * 16u), bytes ? (const void*)(src + at) : (const void*)src, bytes);
+        cp_async16(tile + row * ROW + ch * 16u, bytes ? (const void*)(src + at) : (const void*)src, bytes);
     }
 }
 
 // ------------------------------------------------------------ encoder output --
-// Words leave a lane through a per-lane ring in shared memory; the warp empties all
-// 32 rings together with 128-byte rows.  Word i of lane r sits in column (r + i) & 31
-// so that both the lane's own stores (bank varies with its own progress) and the
-// cooperative row reads (i = f .. f+31 of one lane) spread over the banks.
+// Words leave a lane through its ring in shared memory; the warp empties all 32
+// rings together, one lane's words per 128-byte row.  `wcount` starts at -1: the
+// encoder's first push is its placeholder word (rc_lane.cuh, Sink contract) and
+// lands in a ring slot that is never flushed.
+struct CheckedRingSink;
 struct RingSink {
-    u32* ring;
+    typedef CheckedRingSink Checked;
+    u32 ring;  // shared address of this lane's ring row
     u32* out;  // coded stream start of this lane's block (slot + header), 4-byte aligned
-    u32 lane, wcount, flushed, cap_words;
+    s32 wcount, flushed;
+    u32 cap_words;
     int* err;
 
-    __device__ __forceinline__ u32 slot_of(u32 i) const { return (i % RING) * 32u + ((lane + i) & 31u); }
-
-    __device__ void drain()  // lane-local, only when a single lane overruns its ring (long 0xFF runs)
+    __device__ __forceinline__ void push(u32 w)  // hot path: room is guaranteed by the flush policy
     {
-        for(u32 i = flushed; i < wcount; ++i) {
-            if(i < cap_words) {
-                out[i] = ring[slot_of(i)];
-            }
-        }
-        flushed = wcount;
-    }
-    __device__ __forceinline__ void push(u32 w)
-    {
-        if(wcount - flushed >= (u32)RING) {
-            drain();
-        }
-        ring[slot_of(wcount)] = rc_bswap(w);
+        sts32v(ring + (((u32)wcount & (RING - 1)) << 2), rc_bswap(w));
         ++wcount;
     }
 };
 
-__device__ __noinline__ void ring_flush(RingSink& s)
+// Lane-local emptying of one ring: only when a single lane outruns the warp (long 0xFF runs).
+__device__ __noinline__ s32 ring_drain(u32 ring, u32* out, s32 flushed, s32 wcount, u32 cap_words)
+{
+    for(s32 i = flushed < 0 ? 0 : flushed; i < wcount; ++i) {
+        if((u32)i < cap_words) {
+            out[i] = lds32v(ring + (((u32)i & (RING - 1)) << 2));
+        }
+    }
+    return wcount;
+}
+
+struct CheckedRingSink {
+    RingSink s;
+    __device__ explicit CheckedRingSink(const RingSink& r) : s(r) {}
+    __device__ void push(u32 w)
+    {
+        if(s.wcount - s.flushed >= RING) {
+            s.flushed = ring_drain(s.ring, s.out, s.flushed, s.wcount, s.cap_words);
+        }
+        s.push(w);
+    }
+    __device__ void settle(RingSink& r)
+    {
+        // leave room for the unchecked pushes that may still follow before the next flush check
+        if(s.wcount - s.flushed > RING - 8) {
+            s.flushed = ring_drain(s.ring, s.out, s.flushed, s.wcount, s.cap_words);
+        }
+        r.wcount = s.wcount;
+        r.flushed = s.flushed;
+    }
+};
+
+// Cooperative flush of all 32 rings.  By value: the caller's sink stays in registers.
+__device__ __noinline__ s32 ring_flush_all(RingSink s, u32 ring_base, u32 lane)
 {
     __syncwarp();
 #pragma unroll 1
     for(int r = 0; r < 32; ++r) {
-        const u32 f = __shfl_sync(FULL, s.flushed, r);
-        const u32 w = __shfl_sync(FULL, s.wcount, r);
-        if(f == w) {
+        s32 f = __shfl_sync(FULL, s.flushed, r);
+        const s32 w = __shfl_sync(FULL, s.wcount, r);
+        if(f < 0) {
+            f = 0;
+        }
+        if(f >= w) {
             continue;
         }
         u32* o = (u32*)__shfl_sync(FULL, (unsigned long long)s.out, r);
         const u32 capw = __shfl_sync(FULL, s.cap_words, r);
-        for(u32 i = f + s.lane; i < w; i += 32u) {
-            if(i < capw) {
-                o[i] = s.ring[(i % RING) * 32u + (((u32)r + i) & 31u)];
+        const u32 row = ring_base + (u32)r * (RING_ROW * 4u);
+        for(s32 i = f + (s32)lane; i < w; i += 32) {
+            if((u32)i < capw) {
+                o[i] = lds32v(row + (((u32)i & (RING - 1)) << 2));
             }
         }
     }
-    if(s.wcount > s.cap_words) {
+    if(s.wcount > 0 && (u32)s.wcount > s.cap_words) {
         atomicOr(s.err, ERR_SLOT_OVERFLOW);
     }
-    s.flushed = s.wcount;
     __syncwarp();
+    return s.wcount;
 }
 
 struct EncArgs {
@@ -164,16 +221,20 @@ struct EncArgs {
 };
 
 // Tail of a block: the 4..7 bytes that do not fill a word, then the size.
-__device__ __forceinline__ void finish_block(RcEnc& st, RingSink& sink, bool has, u32 hdr, u8* slot, u32* size_out)
+__device__ __forceinline__ void finish_block(RcEnc& st, RingSink& sink, u32 ring_base, u32 lane, bool has, u32 hdr,
+                                             u8* slot, u32* size_out)
 {
     u8 tail[8];
     u32 ntail = 0;
     if(has) {
-        ntail = rc_enc_finish(st, sink, tail);
+        CheckedRingSink cs(sink);
+        ntail = rc_enc_finish(st, cs, tail);
+        sink.wcount = cs.s.wcount;
+        sink.flushed = cs.s.flushed;
     }
-    ring_flush(sink);
+    sink.flushed = ring_flush_all(sink, ring_base, lane);
     if(has) {
-        const u32 at = hdr + 4u * sink.wcount;
+        const u32 at = hdr + 4u * (u32)sink.wcount;
         if((u64)at + ntail <= (u64)hdr + 4ull * sink.cap_words) {
             for(u32 k = 0; k < ntail; ++k) {
                 slot[at + k] = tail[k];
@@ -186,30 +247,35 @@ __device__ __forceinline__ void finish_block(RcEnc& st, RingSink& sink, bool has
 }
 
 // ======================================================================= K2s ==
-// Static encode.  WIDE = false: blocks <= 65536 bytes, table entry = cum << 16 | freq
-// (both fit 16 bits) built from K1's frequencies.
-// WIDE = true: larger blocks; the lane counts its own block with the reference's
-// order-dependent rule (cpprcoder.h:543-571) and keeps a 257-entry u32 cum table.
+// Static encode.  WIDE = false: blocks <= 65536 bytes; cum and freq of a coded symbol
+// both fit 16 bits and live in two u16 arrays built from K1's
+// frequencies.  WIDE = true: larger blocks; the lane counts its own block with the
+// reference's order-dependent rule (cpprcoder.h:543-571) and keeps a 257-entry u32
+// cum table (freq = difference of neighbours).
+constexpr u32 ENC_STATIC_TAB_NARROW = 2u * 256u * 32u * 2u;  // cum16[256][32] then freq16[256][32]
+constexpr u32 ENC_STATIC_TAB_WIDE = 257u * 32u * 4u;
+
 template <bool WIDE>
 struct StaticTab {
-    u32* base;  // + lane
+    u32 base;  // shared address, already offset by the lane
     __device__ __forceinline__ void get(u32 sym, u32& cum, u32& freq) const
     {
         if(WIDE) {
-            cum = base[sym * 32u];
-            freq = base[(sym + 1u) * 32u] - cum;
+            const u32 a = base + sym * 128u;
+            cum = lds32(a);
+            freq = lds32(a + 128u) - cum;
         } else {
-            const u32 e = base[sym * 32u];
-            cum = e >> 16;
-            freq = e & 0xFFFFu;
+            const u32 a = base + sym * 64u;
+            cum = lds16(a);
+            freq = lds16(a + 256u * 64u);
         }
     }
 };
 
 template <bool WIDE, bool POW2, bool RAGGED>
-__device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u8* tiles, const StaticTab<WIDE>& tab, RcEnc& st,
-                                                 RingSink& sink, u64 b0, u32 n_b, u32 n_max, u32 total, u32 magic,
-                                                 u32 shift, u32 lane)
+__device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, u32 ring_base, const StaticTab<WIDE>& tab,
+                                                 RcEnc& st, RingSink& sink, u64 b0, u32 n_b, u32 n_max, u32 total,
+                                                 u32 magic, u32 shift, u32 lane)
 {
     const u32 ntiles = (n_max + TILE - 1) / TILE;
     // tile 0 was staged (and committed) by the caller
@@ -221,23 +287,37 @@ __device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u8* tiles, co
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
-        const u8* row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+        const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+        // Four symbols per trip.  The trip stays small on purpose: with one warp per SM
+        // nothing hides an instruction fetch.  Table entries of the NEXT four symbols are
+        // requested before the current four are coded, so their latency is off the chain.
+        u32 word = lds32(row);
+        u32 cum[4], freq[4];
 #pragma unroll
-        for(int q = 0; q < TILE / 16; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4*>(row + q * 16);
-            const u32 w4[4] = {v.x, v.y, v.z, v.w};
+        for(int k = 0; k < 4; ++k) {
+            tab.get((word >> (8 * k)) & 0xFFu, cum[k], freq[k]);
+        }
+#pragma unroll 1
+        for(int wi = 0; wi < TILE / 4; ++wi) {
+            const u32 wnext = lds32(row + 4u * (u32)((wi + 1) & (TILE / 4 - 1)));
+            u32 ncum[4], nfreq[4];
 #pragma unroll
-            for(int k = 0; k < 16; ++k) {
-                const u32 sym = (w4[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-                if(!RAGGED || tix * TILE + q * 16 + k < n_b) {
-                    u32 cum, freq;
-                    tab.get(sym, cum, freq);
-                    const u32 t = POW2 ? (st.range >> shift) : rc_div(st.range, total, magic);
-                    rc_enc_step(st, cum, freq, t, sink);
-                }
+            for(int k = 0; k < 4; ++k) {
+                tab.get((wnext >> (8 * k)) & 0xFFu, ncum[k], nfreq[k]);
             }
-            if(__any_sync(FULL, sink.wcount - sink.flushed >= (u32)(RING - 13))) {
-                ring_flush(sink);
+#pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                const bool active = !RAGGED || tix * TILE + wi * 4 + k < n_b;
+                const u32 t = POW2 ? (st.range >> shift) : rc_div(st.range, total, magic);
+                rc_enc_step(st, cum[k], freq[k], t, sink, active);
+            }
+            if(__any_sync(FULL, sink.wcount - sink.flushed >= RING - 4)) {
+                sink.flushed = ring_flush_all(sink, ring_base, lane);
+            }
+#pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                cum[k] = ncum[k];
+                freq[k] = nfreq[k];
             }
         }
         __syncwarp();
@@ -248,11 +328,10 @@ template <bool WIDE>
 __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
-    constexpr u32 TAB_BYTES = (WIDE ? 257u : 256u) * 32u * 4u;
-    constexpr u32 TAB_PAD = (TAB_BYTES + 15u) & ~15u;
-    u32* table = reinterpret_cast<u32*>(smem);
-    u8* tiles = smem + TAB_PAD;
-    u32* ring = reinterpret_cast<u32*>(smem + TAB_PAD + 2 * TILE_BYTES);
+    constexpr u32 TAB_BYTES = WIDE ? ENC_STATIC_TAB_WIDE : ENC_STATIC_TAB_NARROW;
+    const u32 sbase = smem_addr(smem);
+    const u32 tiles = sbase + TAB_BYTES;
+    const u32 ring_base = tiles + 2 * TILE_BYTES;
 
     const u32 lane = lane_id();
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -270,6 +349,8 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
         // first input tile in flight while the tables are built
         stage_tile(tiles, a.src, a.n, b0, a.block, 0, lane);
         cp_async_commit();
+        u16* cum16 = reinterpret_cast<u16*>(smem);
+        u16* frq16 = cum16 + 256 * 32;
 #pragma unroll 1
         for(u32 r = 0; r < 32; ++r) {
             if(b0 + r >= a.nblocks) {
@@ -295,7 +376,10 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
             u32 run = incl - sum;  // calcCumulatives (cpprcoder.h:573-583)
 #pragma unroll
             for(int k = 0; k < 8; ++k) {
-                table[(8u * lane + k) * 32u + r] = (run << 16) | f[k];
+                // a symbol that occurs has cum <= total - freq <= 65535; for one that does not,
+                // the truncated value is never read
+                cum16[(8u * lane + k) * 32u + r] = (u16)run;
+                frq16[(8u * lane + k) * 32u + r] = (u16)f[k];
                 run += f[k];
             }
             const u32 tot = __shfl_sync(FULL, incl, 31);
@@ -317,7 +401,7 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
         __syncwarp();
     } else {
         // count(): the halving is order dependent, so each lane walks its own block once
-        u32* mine = table + lane;
+        u32* mine = reinterpret_cast<u32*>(smem) + lane;
         for(u32 s = 0; s < 257; ++s) {
             mine[s * 32u] = 0;
         }
@@ -333,7 +417,8 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
             cp_async_commit();
             cp_async_wait<1>();
             __syncwarp();
-            const u8* row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+            const u8* row = smem + TAB_BYTES + (tix & 1u) * TILE_BYTES + lane * ROW;
+#pragma unroll 1
             for(u32 k = 0; k < (u32)TILE; ++k) {
                 if(tix * TILE + k < n_b) {
                     const u32 c = row[k];
@@ -372,15 +457,14 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
     RcEnc st;
     rc_enc_init(st, RC_STATIC_RANGE0);
     RingSink sink;
-    sink.ring = ring;
+    sink.ring = ring_base + lane * (RING_ROW * 4u);
     sink.out = reinterpret_cast<u32*>(slot + RC_STATIC_HDR);
-    sink.lane = lane;
-    sink.wcount = 0;
+    sink.wcount = -1;
     sink.flushed = 0;
     sink.cap_words = has ? (u32)((a.slot_stride - RC_STATIC_HDR) / 4u) : 0u;
     sink.err = a.err;
 
-    const StaticTab<WIDE> tab{table + lane};
+    const StaticTab<WIDE> tab{sbase + lane * (WIDE ? 4u : 2u)};
     const u32 magic = rc_magic(total);
     const bool is_pow2 = total != 0 && (total & (total - 1u)) == 0;
     const u32 shift = is_pow2 ? 31u - rc_clz(total) : 0u;
@@ -389,11 +473,11 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
     const bool ragged = __any_sync(FULL, n_b != n_max);
 
     if(all_pow2 && !ragged) {
-        enc_static_tiles<WIDE, true, false>(a, tiles, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
+        enc_static_tiles<WIDE, true, false>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
     } else if(!ragged) {
-        enc_static_tiles<WIDE, false, false>(a, tiles, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
+        enc_static_tiles<WIDE, false, false>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
     } else {
-        enc_static_tiles<WIDE, false, true>(a, tiles, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
+        enc_static_tiles<WIDE, false, true>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
     }
 
     // cpprcoder.h:439-451: when the block ends on low_ == 0xFFFFFFFF the reference bumps
@@ -402,7 +486,8 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
     bool exact = false;
     if(has && st.low == 0xFFFFFFFFu) {
         exact = true;
-        sink.wcount = sink.flushed;  // drop what the ring still holds
+        sink.wcount = sink.flushed < 0 ? 0 : sink.flushed;  // drop what the ring still holds
+        sink.flushed = sink.wcount;
         u32 at = RC_STATIC_HDR;
         const u8* blk = a.src + b * (u64)a.block;
         const u32 cap = (u32)a.slot_stride;
@@ -413,9 +498,17 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
                 if(c >= 256u) {
                     return total;
                 }
+                // walk the frequencies: the 16-bit cum array is only exact for symbols that occur
                 u32 cum, freq;
-                tab.get(c, cum, freq);
-                return cum;
+                if(WIDE) {
+                    tab.get(c, cum, freq);
+                    return cum;
+                }
+                u32 run = 0;
+                for(u32 s = 0; s < c; ++s) {
+                    run += lds16(tab.base + s * 64u + 256u * 64u);
+                }
+                return run;
             },
             [&](u32 i) -> u32 { return blk[i]; },
             [&](u8 byte) {
@@ -431,16 +524,34 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
         }
         a.sizes[b] = at;
     }
-    finish_block(st, sink, has && !exact, RC_STATIC_HDR, slot, a.sizes + b);
+    finish_block(st, sink, ring_base, lane, has && !exact, RC_STATIC_HDR, slot, a.sizes + b);
 }
 
 // ======================================================================= K2a ==
-// Adaptive encode.  The model is the count tree of rc_model_encode, one per lane.
-// total_i = 256 + i is the same for every lane, so the 64 magics of a tile are
-// computed once per warp (two per lane) and handed round by shuffle.
+// Adaptive encode.  The model is the count tree of rc_model_encode, one per lane
+// ([node][lane], u16 for blocks <= 65536 bytes, u32 above).  total_i = 256 + i is the
+// same for every lane, so the 64 magics of a tile are computed once per warp (two per
+// lane) and handed round by shuffle.
+template <class W>
+struct LaneTab {
+    u32 base;  // shared address, already offset by the lane
+    __device__ __forceinline__ u32 ld(u32 i) const
+    {
+        return sizeof(W) == 2 ? lds16v(base + i * 64u) : lds32v(base + i * 128u);
+    }
+    __device__ __forceinline__ void st(u32 i, u32 v) const
+    {
+        if(sizeof(W) == 2) {
+            sts16v(base + i * 64u, v);
+        } else {
+            sts32v(base + i * 128u, v);
+        }
+    }
+};
+
 template <class W, bool RAGGED>
-__device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u8* tiles, LaneTab<W>& tab, RcEnc& st,
-                                                   RingSink& sink, u64 b0, u32 n_b, u32 n_max, u32 lane)
+__device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, u32 ring_base, LaneTab<W>& tab,
+                                                   RcEnc& st, RingSink& sink, u64 b0, u32 n_b, u32 n_max, u32 lane)
 {
     const u32 ntiles = (n_max + TILE - 1) / TILE;
 #pragma unroll 1
@@ -454,25 +565,26 @@ __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u8* tiles, 
         const u32 mg1 = rc_magic(d0 + 32u + lane);
         cp_async_wait<1>();
         __syncwarp();
-        const u8* row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+        const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+#pragma unroll 1
+        for(int wi = 0; wi < TILE / 4; ++wi) {
+            const u32 word = lds32(row + 4u * (u32)wi);
+            const u32 mg = wi < 8 ? mg0 : mg1;
 #pragma unroll
-        for(int q = 0; q < TILE / 16; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4*>(row + q * 16);
-            const u32 w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for(int k = 0; k < 16; ++k) {
-                const int j = q * 16 + k;
-                const u32 sym = (w4[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-                const u32 magic = __shfl_sync(FULL, j < 32 ? mg0 : mg1, j & 31);
-                if(!RAGGED || tix * TILE + j < n_b) {
-                    u32 cum, freq;
+            for(int k = 0; k < 4; ++k) {
+                const int j = wi * 4 + k;
+                const u32 sym = (word >> (8 * k)) & 0xFFu;
+                const u32 magic = __shfl_sync(FULL, mg, j & 31);
+                const bool active = !RAGGED || tix * TILE + j < n_b;
+                u32 cum = 0, freq = 1;
+                if(active) {
                     rc_model_encode(tab, sym, cum, freq);
-                    const u32 t = rc_div(st.range, d0 + j, magic);
-                    rc_enc_step(st, cum, freq, t, sink);
                 }
+                const u32 t = rc_div(st.range, d0 + j, magic);
+                rc_enc_step(st, cum, freq, t, sink, active);
             }
-            if(__any_sync(FULL, sink.wcount - sink.flushed >= (u32)(RING - 13))) {
-                ring_flush(sink);
+            if(__any_sync(FULL, sink.wcount - sink.flushed >= RING - 4)) {
+                sink.flushed = ring_flush_all(sink, ring_base, lane);
             }
         }
         __syncwarp();
@@ -484,9 +596,9 @@ __global__ void __launch_bounds__(32) k_enc_adaptive(EncArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
     constexpr u32 TAB_BYTES = 512u * 32u * sizeof(W);
-    W* table = reinterpret_cast<W*>(smem);
-    u8* tiles = smem + TAB_BYTES;
-    u32* ring = reinterpret_cast<u32*>(smem + TAB_BYTES + 2 * TILE_BYTES);
+    const u32 sbase = smem_addr(smem);
+    const u32 tiles = sbase + TAB_BYTES;
+    const u32 ring_base = tiles + 2 * TILE_BYTES;
 
     const u32 lane = lane_id();
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -515,22 +627,21 @@ __global__ void __launch_bounds__(32) k_enc_adaptive(EncArgs a)
     RcEnc st;
     rc_enc_init(st, RC_ADAPT_RANGE0);
     RingSink sink;
-    sink.ring = ring;
+    sink.ring = ring_base + lane * (RING_ROW * 4u);
     sink.out = reinterpret_cast<u32*>(slot + RC_ADAPT_HDR);
-    sink.lane = lane;
-    sink.wcount = 0;
+    sink.wcount = -1;
     sink.flushed = 0;
     sink.cap_words = has ? (u32)((a.slot_stride - RC_ADAPT_HDR) / 4u) : 0u;
     sink.err = a.err;
-    LaneTab<W> tab{table + lane};
+    LaneTab<W> tab{sbase + lane * (u32)sizeof(W)};
 
     const u32 n_max = __reduce_max_sync(FULL, n_b);
     if(__any_sync(FULL, n_b != n_max)) {
-        enc_adaptive_tiles<W, true>(a, tiles, tab, st, sink, b0, n_b, n_max, lane);
+        enc_adaptive_tiles<W, true>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, lane);
     } else {
-        enc_adaptive_tiles<W, false>(a, tiles, tab, st, sink, b0, n_b, n_max, lane);
+        enc_adaptive_tiles<W, false>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, lane);
     }
-    finish_block(st, sink, has, RC_ADAPT_HDR, slot, a.sizes + b);
+    finish_block(st, sink, ring_base, lane, has, RC_ADAPT_HDR, slot, a.sizes + b);
 }
 
 // ============================================================= decoder input ==
@@ -549,16 +660,16 @@ struct DecArgs {
 };
 
 struct WordSrc {
-    const u32* ring;
+    u32 ring;         // shared address of this lane's ring row
     const u8* wbase;  // aligned address of the word holding coded byte 0
     const u8* end;    // one past the last readable stream byte
-    u32 lane, consumed, filled, limit;
+    u32 consumed, filled, limit;
 
     __device__ __forceinline__ u32 operator()()
     {
         u32 w = 0;
         if(consumed < filled) {
-            w = rc_bswap(ring[(consumed % RING) * 32u + ((lane + consumed) & 31u)]);
+            w = rc_bswap(lds32v(ring + ((consumed & (RING - 1)) << 2)));
         }
         ++consumed;
         return w;
@@ -579,8 +690,9 @@ __device__ __forceinline__ u32 load_stream_word(const u8* p, const u8* end)
     return w;
 }
 
-__device__ __noinline__ void ring_fill(WordSrc& s, u32* ring)
+__device__ __noinline__ u32 ring_fill_all(WordSrc s, u32 ring_base, u32 lane)
 {
+    u32 mine = s.filled;
     __syncwarp();
 #pragma unroll 1
     for(int r = 0; r < 32; ++r) {
@@ -596,14 +708,16 @@ __device__ __noinline__ void ring_fill(WordSrc& s, u32* ring)
         }
         const u8* wb = (const u8*)__shfl_sync(FULL, (unsigned long long)s.wbase, r);
         const u8* end = (const u8*)__shfl_sync(FULL, (unsigned long long)s.end, r);
-        for(u32 i = f + s.lane; i < target; i += 32u) {
-            ring[(i % RING) * 32u + (((u32)r + i) & 31u)] = load_stream_word(wb + 4ull * i, end);
+        const u32 row = ring_base + (u32)r * (RING_ROW * 4u);
+        for(u32 i = f + lane; i < target; i += 32u) {
+            sts32v(row + ((i & (RING - 1)) << 2), load_stream_word(wb + 4ull * i, end));
         }
-        if(s.lane == (u32)r) {
-            s.filled = target;
+        if(lane == (u32)r) {
+            mine = target;
         }
     }
     __syncwarp();
+    return mine;
 }
 
 // Output tile -> global, 8 rows of 64 bytes per instruction.
@@ -636,7 +750,7 @@ __device__ __forceinline__ void store_tile(const u8* tile, u8* dst, u64 n, u64 b
     }
 }
 
-__device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u32 lane, u64 b, bool has, u32 n_b, u32* ring,
+__device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u32 lane, u64 b, bool has, u32 n_b, u32 ring_base,
                                           WordSrc& src, const u8*& pay, bool& ok)
 {
     pay = a.payload;
@@ -657,8 +771,7 @@ __device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u32 lane, u
         atomicOr(a.err, ERR_CORRUPT);
     }
     const u8* coded = pay + hdr;
-    src.ring = ring;
-    src.lane = lane;
+    src.ring = ring_base + lane * (RING_ROW * 4u);
     src.consumed = 0;
     src.filled = 0;
     src.wbase = (const u8*)((uintptr_t)coded & ~(uintptr_t)3);
@@ -671,15 +784,17 @@ __device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u32 lane, u
 // (cum * t <= low, no second divide): level 1 compares the 15
 // chunk boundaries cum[16j] held in registers, level 2 the 15 boundaries inside the
 // chunk from the lane's table.  Equivalent to RangeEncoder::find (cpprcoder.h:521-535).
-template <bool WIDE>
+// The table is the plain 257-entry u32 cum array: trailing symbols that never occur
+// have cum == total, which can be 65536 and does not fit a packed 16-bit field.
+constexpr u32 DEC_STATIC_TAB = 257u * 32u * 4u;  // 32896, a multiple of 16
 __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
-    constexpr u32 TAB_BYTES = (WIDE ? 257u : 256u) * 32u * 4u;
-    constexpr u32 TAB_PAD = (TAB_BYTES + 15u) & ~15u;
+    const u32 sbase = smem_addr(smem);
     u32* table = reinterpret_cast<u32*>(smem);
-    u8* otile = smem + TAB_PAD;
-    u32* ring = reinterpret_cast<u32*>(smem + TAB_PAD + TILE_BYTES);
+    u8* otile = smem + DEC_STATIC_TAB;
+    const u32 otile_a = sbase + DEC_STATIC_TAB;
+    const u32 ring_base = otile_a + TILE_BYTES;
 
     const u32 lane = lane_id();
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -693,37 +808,33 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     WordSrc src;
     const u8* pay;
     bool ok;
-    dec_setup(a, RC_STATIC_HDR, lane, b, has, n_b, ring, src, pay, ok);
+    dec_setup(a, RC_STATIC_HDR, lane, b, has, n_b, ring_base, src, pay, ok);
 
     // read16 + calcCumulatives (cpprcoder.h:585-602, :573-583); payloads are unaligned
     u32* mine = table + lane;
+    const u32 mine_a = sbase + lane * 4u;
     u32 total = 0;
     u32 key[16];
     {
         u32 run = 0;
+#pragma unroll 1
         for(u32 s = 0; s < 256; ++s) {
             u32 f = 0;
             if(ok) {
                 f = (u32)pay[4u + 2u * s] | ((u32)pay[5u + 2u * s] << 8);
             }
-            if(WIDE) {
-                mine[s * 32u] = run;
-            } else {
-                mine[s * 32u] = (run << 16) | f;
-            }
+            mine[s * 32u] = run;
             run += f;
         }
-        if(WIDE) {
-            mine[256u * 32u] = run;
-        }
+        mine[256u * 32u] = run;
         total = run;
-        if(ok && (total == 0 || (!WIDE && total > 65536u))) {
+        if(ok && total == 0) {
             ok = false;
             atomicOr(a.err, ERR_CORRUPT);
         }
 #pragma unroll
         for(int j = 0; j < 16; ++j) {
-            key[j] = WIDE ? mine[(16u * j) * 32u] : (mine[(16u * j) * 32u] >> 16);
+            key[j] = mine[(16u * j) * 32u];
         }
     }
     if(!ok) {
@@ -732,7 +843,7 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
         total = 1;
     }
     const u32 magic = rc_magic(total);
-    ring_fill(src, ring);
+    src.filled = ring_fill_all(src, ring_base, lane);
     RcDec d;
     rc_dec_init(d, RC_STATIC_RANGE0, (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u), src);
 
@@ -741,42 +852,39 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
 #pragma unroll 1
     for(u32 tix = 0; tix < ntiles; ++tix) {
 #pragma unroll 1
-        for(int q = 0; q < TILE / 16; ++q) {
-            u32 w4[4] = {0, 0, 0, 0};
-            if(__any_sync(FULL, src.filled < src.limit && src.filled - src.consumed < 13u)) {
-                ring_fill(src, ring);
+        for(int wi = 0; wi < TILE / 4; ++wi) {
+            if((wi & 3) == 0 && __any_sync(FULL, src.filled < src.limit && src.filled - src.consumed < 13u)) {
+                src.filled = ring_fill_all(src, ring_base, lane);
             }
+            u32 word = 0;
 #pragma unroll
-            for(int k = 0; k < 16; ++k) {
-                if(tix * TILE + q * 16 + k < n_b) {
+            for(int k = 0; k < 4; ++k) {
+                if(tix * TILE + wi * 4 + k < n_b) {
                     const u32 t = rc_div(d.range, total, magic);
                     u32 c1 = 0;
 #pragma unroll
                     for(int j = 1; j < 16; ++j) {
                         c1 += (key[j] * t <= d.low) ? 1u : 0u;
                     }
-                    const u32* chunk = mine + (16u * c1) * 32u;
+                    const u32 chunk = mine_a + c1 * (16u * 128u);
+                    u32 e[16];
+#pragma unroll
+                    for(int j = 1; j < 16; ++j) {
+                        e[j] = lds32(chunk + j * 128u);
+                    }
                     u32 c2 = 0;
 #pragma unroll
                     for(int j = 1; j < 16; ++j) {
-                        const u32 e = chunk[j * 32];
-                        c2 += ((WIDE ? e : (e >> 16)) * t <= d.low) ? 1u : 0u;
+                        c2 += (e[j] * t <= d.low) ? 1u : 0u;
                     }
                     const u32 sym = 16u * c1 + c2;
-                    u32 cum, freq;
-                    if(WIDE) {
-                        cum = mine[sym * 32u];
-                        freq = mine[(sym + 1u) * 32u] - cum;
-                    } else {
-                        const u32 e = mine[sym * 32u];
-                        cum = e >> 16;
-                        freq = e & 0xFFFFu;
-                    }
+                    const u32 cum = lds32(chunk + c2 * 128u);
+                    const u32 freq = lds32(chunk + c2 * 128u + 128u) - cum;
                     rc_dec_advance(d, cum, freq, t, src);
-                    w4[k >> 2] |= sym << (8 * (k & 3));
+                    word |= sym << (8 * k);
                 }
             }
-            *reinterpret_cast<uint4*>(otile + lane * ROW + q * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            sts32v(otile_a + lane * ROW + wi * 4, word);
         }
         __syncwarp();
         store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
@@ -793,9 +901,10 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
     constexpr u32 TAB_BYTES = 512u * 32u * sizeof(W);
-    W* table = reinterpret_cast<W*>(smem);
+    const u32 sbase = smem_addr(smem);
     u8* otile = smem + TAB_BYTES;
-    u32* ring = reinterpret_cast<u32*>(smem + TAB_BYTES + TILE_BYTES);
+    const u32 otile_a = sbase + TAB_BYTES;
+    const u32 ring_base = otile_a + TILE_BYTES;
 
     const u32 lane = lane_id();
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -809,7 +918,7 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
     WordSrc src;
     const u8* pay;
     bool ok;
-    dec_setup(a, RC_ADAPT_HDR, lane, b, has, n_b, ring, src, pay, ok);
+    dec_setup(a, RC_ADAPT_HDR, lane, b, has, n_b, ring_base, src, pay, ok);
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
         for(u32 i = lane; i < TAB_BYTES / 16u; i += 32u) {
@@ -821,8 +930,8 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
         src.limit = 0;
     }
     __syncwarp();
-    LaneTab<W> tab{table + lane};
-    ring_fill(src, ring);
+    LaneTab<W> tab{sbase + lane * (u32)sizeof(W)};
+    src.filled = ring_fill_all(src, ring_base, lane);
     RcDec d;
     rc_dec_init(d, RC_ADAPT_RANGE0, (u32)((uintptr_t)(pay + RC_ADAPT_HDR) & 3u), src);
 
@@ -833,25 +942,26 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
         const u32 d0 = 256u + tix * TILE;
         const u32 mg0 = rc_magic(d0 + lane);
         const u32 mg1 = rc_magic(d0 + 32u + lane);
-#pragma unroll
-        for(int q = 0; q < TILE / 16; ++q) {
-            u32 w4[4] = {0, 0, 0, 0};
-            if(__any_sync(FULL, src.filled < src.limit && src.filled - src.consumed < 13u)) {
-                ring_fill(src, ring);
+#pragma unroll 1
+        for(int wi = 0; wi < TILE / 4; ++wi) {
+            if((wi & 3) == 0 && __any_sync(FULL, src.filled < src.limit && src.filled - src.consumed < 13u)) {
+                src.filled = ring_fill_all(src, ring_base, lane);
             }
+            const u32 mg = wi < 8 ? mg0 : mg1;
+            u32 word = 0;
 #pragma unroll
-            for(int k = 0; k < 16; ++k) {
-                const int j = q * 16 + k;
-                const u32 magic = __shfl_sync(FULL, j < 32 ? mg0 : mg1, j & 31);
+            for(int k = 0; k < 4; ++k) {
+                const int j = wi * 4 + k;
+                const u32 magic = __shfl_sync(FULL, mg, j & 31);
                 if(tix * TILE + j < n_b) {
                     const u32 t = rc_div(d.range, d0 + j, magic);
                     u32 sym, cum, freq;
                     rc_model_decode(tab, d.low, t, sym, cum, freq);
                     rc_dec_advance(d, cum, freq, t, src);
-                    w4[k >> 2] |= sym << (8 * (k & 3));
+                    word |= sym << (8 * k);
                 }
             }
-            *reinterpret_cast<uint4*>(otile + lane * ROW + q * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            sts32v(otile_a + lane * ROW + wi * 4, word);
         }
         __syncwarp();
         store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);

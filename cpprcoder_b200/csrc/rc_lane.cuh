@@ -119,9 +119,14 @@ struct RcEnc {
     u32 o_lo, o_hi;
     s32 ocnt;       // valid bits in o (multiple of 8, < 32 between steps)
     u32 pend, nff;  // deferred word and the number of 0xFFFFFFFF words behind it
-    u32 has_pend;
 };
 
+// Sink contract: push(word) appends one big-endian stream word.  The FIRST word an
+// encoder pushes is a placeholder (the initial `pend`) and must be discarded by the
+// sink -- that spares the hot path a "has a deferred word yet?" test.  push() on the
+// hot path may assume room for one word per symbol; Sink::Checked is the variant the
+// rare path uses for runs of any length, and Checked::settle(sink) writes its
+// bookkeeping back.
 RC_HD void rc_enc_init(RcEnc& e, u32 range0)
 {
     e.low = 0;
@@ -131,15 +136,32 @@ RC_HD void rc_enc_init(RcEnc& e, u32 range0)
     e.ocnt = 8;  // the reference's initial buffer_ = 0 is the first stream byte (cpprcoder.h:385, :687)
     e.pend = 0;
     e.nff = 0;
-    e.has_pend = 0;
 }
 
-// Rare part of cutting a word: a parked carry, or all-ones words in play.  Kept out
-// of line so the 64-times-unrolled hot loops stay small.
+// (o_hi : o_lo : low) += term
+RC_HD void rc_add96(u32& low, u32& o_lo, u32& o_hi, u32 term)
+{
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.u32 %2, %2, 0;"
+        : "+r"(low), "+r"(o_lo), "+r"(o_hi)
+        : "r"(term));
+#else
+    const u32 nl = low + term;
+    const u32 c = (nl < low) ? 1u : 0u;
+    low = nl;
+    const u32 ol = o_lo + c;
+    o_hi += (ol < c) ? 1u : 0u;
+    o_lo = ol;
+#endif
+}
+
+// Rare part of cutting a word: all-ones words in play (cpprcoder.h:405-435 / :767-800 at
+// word granularity).  Kept out of line; callers pass copies so that the lane state proper
+// never has its address taken and stays in registers.
 template <class Sink>
 RC_COLD void rc_enc_word_slow(RcEnc& e, u32 word, u32 ovf, Sink& s)
 {
-    if(ovf) {  // cpprcoder.h:405-415 / :767-781 at word granularity
+    if(ovf) {  // a carry reaches the deferred word: the 0xFF run behind it rolls over to zeros
         e.pend += ovf;
         if(e.nff) {
             s.push(e.pend);
@@ -150,51 +172,62 @@ RC_COLD void rc_enc_word_slow(RcEnc& e, u32 word, u32 ovf, Sink& s)
             e.nff = 0;
         }
     }
-    if(word == 0xFFFFFFFFu && e.has_pend) {
+    if(word == 0xFFFFFFFFu) {
         e.nff += 1;  // cpprcoder.h:431 / :796
         return;
     }
-    if(e.has_pend) {  // cpprcoder.h:420-428 / :785-794
-        s.push(e.pend);
-        for(u32 i = 0; i < e.nff; ++i) {
-            s.push(0xFFFFFFFFu);
-        }
+    s.push(e.pend);  // cpprcoder.h:420-428 / :785-794
+    for(u32 i = 0; i < e.nff; ++i) {
+        s.push(0xFFFFFFFFu);
     }
     e.pend = word;
     e.nff = 0;
-    e.has_pend = 1;
 }
 
+#if defined(__CUDA_ARCH__)
+#define RC_WARP_ANY(p) __any_sync(0xFFFFFFFFu, (p))
+#else
+#define RC_WARP_ANY(p) (p)
+#endif
+
 // One symbol: cum/freq from the model, t = range / total already divided.
+// CONVERGED: every lane of the warp must call this together (it votes).
 template <class Sink>
-RC_HD void rc_enc_step(RcEnc& e, u32 cum, u32 freq, u32 t, Sink& s)
+RC_HD void rc_enc_step(RcEnc& e, u32 cum, u32 freq, u32 t, Sink& s, bool active = true)
 {
-    const u32 nl = e.low + cum * t;
-    const u32 c = (nl < e.low) ? 1u : 0u;
-    e.low = nl;
-    const u32 ol = e.o_lo + c;
-    e.o_hi += (ol < c) ? 1u : 0u;
-    e.o_lo = ol;
-    e.range = freq * t;
-    const u32 sh = rc_clz(e.range) & 24u;  // 8 bits per renormalisation round (cpprcoder.h:418, :783)
-    e.o_hi = rc_funnel_l(e.o_lo, e.o_hi, sh);
-    e.o_lo = rc_funnel_l(e.low, e.o_lo, sh);
-    e.low <<= sh;
-    e.range <<= sh;
-    e.ocnt += (s32)sh;
-    if(e.ocnt >= 32) {
-        const u32 k = (u32)e.ocnt - 32u;  // 0..23
-        const u32 word = rc_funnel_r(e.o_lo, e.o_hi, k);
-        const u32 ovf = e.o_hi >> k;
+    if(active) {
+        rc_add96(e.low, e.o_lo, e.o_hi, cum * t);
+        e.range = freq * t;
+        const u32 sh = rc_clz(e.range) & 24u;  // 8 bits per renormalisation round (cpprcoder.h:418, :783)
+        e.o_hi = rc_funnel_l(e.o_lo, e.o_hi, sh);
+        e.o_lo = rc_funnel_l(e.low, e.o_lo, sh);
+        e.low <<= sh;
+        e.range <<= sh;
+        e.ocnt += (s32)sh;
+    }
+    const bool cut = active && e.ocnt >= 32;
+    const u32 k = (u32)(e.ocnt - 32) & 31u;  // 0..23 when cutting
+    const u32 word = rc_funnel_r(e.o_lo, e.o_hi, k);
+    const u32 ovf = e.o_hi >> k;  // carry parked above the valid bits: belongs to the deferred word
+    const bool slow = cut && (e.nff != 0u || word == 0xFFFFFFFFu);
+    if(RC_WARP_ANY(slow)) {
+        if(slow) {
+            RcEnc te = e;
+            typename Sink::Checked ts(s);  // may push a long run: this one checks for room
+            rc_enc_word_slow(te, word, ovf, ts);
+            e.pend = te.pend;
+            e.nff = te.nff;
+            ts.settle(s);
+        }
+    }
+    if(cut) {
+        if(!slow) {
+            s.push(e.pend + ovf);
+            e.pend = word;
+        }
         e.o_hi = 0;
         e.o_lo &= (1u << k) - 1u;
         e.ocnt = (s32)k;
-        if((ovf | e.nff) != 0u || word == 0xFFFFFFFFu || !e.has_pend) {
-            rc_enc_word_slow(e, word, ovf, s);
-        } else {
-            s.push(e.pend);
-            e.pend = word;
-        }
     }
 }
 
@@ -218,11 +251,9 @@ RC_HD u32 rc_enc_finish(RcEnc& e, Sink& s, u8 tail[8])
             e.nff = 0;
         }
     }
-    if(e.has_pend) {
-        s.push(e.pend);
-        for(u32 i = 0; i < e.nff; ++i) {
-            s.push(0xFFFFFFFFu);
-        }
+    s.push(e.pend);
+    for(u32 i = 0; i < e.nff; ++i) {
+        s.push(0xFFFFFFFFu);
     }
     u32 n = 0;
     for(s32 b = e.ocnt - 8; b >= 0; b -= 8) {

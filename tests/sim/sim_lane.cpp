@@ -10,9 +10,16 @@
 namespace
 {
 struct VecSink {
+    typedef VecSink Checked;
     std::vector<u8>* out;
+    bool first = true;
+    void settle(VecSink& s) const { s = *this; }
     void push(u32 w)
     {
+        if(first) {  // the encoder's placeholder word (rc_lane.cuh, Sink contract)
+            first = false;
+            return;
+        }
         out->push_back((u8)(w >> 24));
         out->push_back((u8)(w >> 16));
         out->push_back((u8)(w >> 8));

@@ -86,7 +86,7 @@ def test_blocks_above_64k_follow_the_order_dependent_count(ctx, oracle, block):
     # kennedy-like data: 44 % zeros => RangeEncoder::count halves (cpprcoder.h:549-555) inside every block
     data = synth.kennedy(3 * block + 4097)
     _, events = oracle.static_count(data[:block])
-    assert events >= 1
+    assert events >= 1 or block < 262144  # 44 % of 128 KiB is still below 0xFFFF
     parts = [data, np.concatenate([crafted(5, block, np.random.default_rng(3)), crafted(6, block // 2, np.random.default_rng(4))])]
     for d in parts:
         for mode, key in MODES:
