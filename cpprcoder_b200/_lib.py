@@ -37,6 +37,8 @@ SIGNATURES = {
     "b2rc_k_compact": (C.c_int, [_P, _P, _U64, _P, _P, _U64, _P, _U64, _P, _P]),
     "b2rc_k_decode_blocks": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, _P, _U64, _P, _P]),
     "b2rc_launch_count": (_U64, [_P]),
+    "b2rc_profile": (C.c_int, [_P, C.c_int]),
+    "b2rc_kernel_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "b2rc_build_arch": (C.c_char_p, []),
 }
 

@@ -69,6 +69,21 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.b2rc_launch_count(self.h))
 
+    KERNELS = {"histogram": 0, "encode": 1, "scan": 2, "compact": 3, "decode": 4}
+
+    def profile(self, enable: bool = True):
+        self._check(self.lib.b2rc_profile(self.h, 1 if enable else 0), "b2rc_profile")
+
+    def kernel_ms(self) -> dict:
+        """Duration of the last launch of each kernel since profile(True); missing ones are omitted."""
+        out = {}
+        for name, k in self.KERNELS.items():
+            ms = C.c_float(-1.0)
+            self._check(self.lib.b2rc_kernel_ms(self.h, k, C.byref(ms)), "b2rc_kernel_ms")
+            if ms.value >= 0:
+                out[name] = float(ms.value)
+        return out
+
     # ---- whole container, device memory ------------------------------------
     def encode_device(self, mode: int, src: torch.Tensor, dst: torch.Tensor | None = None,
                       block: int = DEFAULT_BLOCK) -> tuple[torch.Tensor, int]:

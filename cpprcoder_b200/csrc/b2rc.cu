@@ -38,6 +38,10 @@ struct b2rc_ctx {
     } * h_res;  // pinned
     u64 launches;
     char last_err[256];
+    // optional per-kernel timing (b2rc_profile): CUDA events on the launching stream
+    int profiling;
+    cudaEvent_t ev[B2RC_K_COUNT][2];
+    int ev_used[B2RC_K_COUNT];
 };
 
 namespace
@@ -132,6 +136,26 @@ int launch_check(b2rc_ctx* ctx, const char* what)
     ctx->launches += 1;
     return cuda_ok(ctx, cudaGetLastError(), what) ? B2RC_OK : B2RC_E_CUDA;
 }
+
+// Brackets one kernel launch with events when profiling is on.
+struct KernelTimer {
+    b2rc_ctx* ctx;
+    int which;
+    cudaStream_t st;
+    KernelTimer(b2rc_ctx* c, int w, cudaStream_t s) : ctx(c), which(w), st(s)
+    {
+        if(ctx->profiling) {
+            cudaEventRecord(ctx->ev[which][0], st);
+        }
+    }
+    ~KernelTimer()
+    {
+        if(ctx->profiling) {
+            cudaEventRecord(ctx->ev[which][1], st);
+            ctx->ev_used[which] = 1;
+        }
+    }
+};
 
 int map_kernel_err(int bits)
 {
@@ -244,7 +268,16 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
             rc = B2RC_E_CUDA;
             break;
         }
-        rc = set_smem_limits(ctx);
+        for(int k = 0; k < B2RC_K_COUNT && rc == B2RC_OK; ++k) {
+            for(int e = 0; e < 2; ++e) {
+                if(!cuda_ok(ctx, cudaEventCreate(&ctx->ev[k][e]), "cudaEventCreate")) {
+                    rc = B2RC_E_CUDA;
+                }
+            }
+        }
+        if(rc == B2RC_OK) {
+            rc = set_smem_limits(ctx);
+        }
     } while(0);
     if(rc != B2RC_OK) {
         fprintf(stderr, "b2rc_ctx_create: %s\n", ctx->last_err);
@@ -274,6 +307,13 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     if(ctx->h_res) {
         cudaFreeHost(ctx->h_res);
     }
+    for(int k = 0; k < B2RC_K_COUNT; ++k) {
+        for(int e = 0; e < 2; ++e) {
+            if(ctx->ev[k][e]) {
+                cudaEventDestroy(ctx->ev[k][e]);
+            }
+        }
+    }
     if(ctx->stream) {
         cudaStreamDestroy(ctx->stream);
     }
@@ -289,6 +329,31 @@ const char* b2rc_last_cuda_error(const b2rc_ctx* ctx)
 uint64_t b2rc_launch_count(const b2rc_ctx* ctx)
 {
     return ctx ? ctx->launches : 0;
+}
+
+int b2rc_profile(b2rc_ctx* ctx, int enable)
+{
+    if(!ctx) {
+        return B2RC_E_ARG;
+    }
+    ctx->profiling = enable ? 1 : 0;
+    memset(ctx->ev_used, 0, sizeof ctx->ev_used);
+    return B2RC_OK;
+}
+
+int b2rc_kernel_ms(b2rc_ctx* ctx, int which, float* ms)
+{
+    if(!ctx || !ms || which < 0 || which >= B2RC_K_COUNT) {
+        return B2RC_E_ARG;
+    }
+    *ms = -1.0f;
+    if(!ctx->ev_used[which]) {
+        return B2RC_OK;
+    }
+    DeviceGuard g(ctx->device);
+    CK(cudaEventSynchronize(ctx->ev[which][1]));
+    CK(cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+    return B2RC_OK;
 }
 
 int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, uint64_t* total, uint64_t* nblocks)
@@ -342,6 +407,7 @@ int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t b
     if(grid > 148ull * 16) {
         grid = 148ull * 16;
     }
+    KernelTimer kt(ctx, B2RC_K_HISTOGRAM, st);
     k_hist<<<(unsigned)grid, HIST_WARPS * 32, 0, st>>>(d_src, n, block_size, nb, d_freq16);
     return launch_check(ctx, "k_hist");
 }
@@ -376,6 +442,7 @@ int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     a.sizes = d_sizes;
     a.err = d_err;
     const unsigned grid = (unsigned)((nb + 31) / 32);
+    KernelTimer kt(ctx, B2RC_K_ENCODE, st);
     if(mode == B2RC_MODE_STATIC) {
         if(wide) {
             k_enc_static<true><<<grid, 32, smem_enc_static(true), st>>>(a);
@@ -395,6 +462,7 @@ int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
 static int scan_launch(b2rc_ctx* ctx, const u32* d_sizes, u64 nb, u64* d_offsets, u64* d_total, u8* d_header, u32 mode,
                        u32 block, u64 n, cudaStream_t st)
 {
+    KernelTimer kt(ctx, B2RC_K_SCAN, st);
     k_scan<<<1, SCAN_THREADS, 0, st>>>(d_sizes, nb, d_offsets, d_total, d_header, mode, block, n);
     return launch_check(ctx, "k_scan");
 }
@@ -425,6 +493,7 @@ int b2rc_k_compact(b2rc_ctx* ctx, const uint8_t* d_slots, uint64_t slot_stride, 
     if(grid > 148ull * 8) {
         grid = 148ull * 8;
     }
+    KernelTimer kt(ctx, B2RC_K_COMPACT, st);
     k_compact<<<(unsigned)grid, COMPACT_THREADS, 0, st>>>(d_slots, slot_stride, d_sizes, d_offsets, nblocks, d_payload,
                                                           payload_cap, d_err);
     return launch_check(ctx, "k_compact");
@@ -455,6 +524,7 @@ int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     a.err = d_err;
     const bool wide = block_size > 65536u;
     const unsigned grid = (unsigned)((nblocks + 31) / 32);
+    KernelTimer kt(ctx, B2RC_K_DECODE, st);
     if(mode == B2RC_MODE_STATIC) {
         k_dec_static<<<grid, 32, smem_dec_static(), st>>>(a);
     } else {

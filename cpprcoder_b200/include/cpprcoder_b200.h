@@ -1,0 +1,483 @@
+// cpprcoder_b200.h -- drop-in C++ host header for the range-coder path of taqu/cpprcoder.
+//
+// Same namespace, class names, entry points, argument meaning and error behaviour as
+// the reference's cpprcoder.h for this path, so that its callers -- run_rangecoder /
+// run_adaptive (test/main.cpp:254-363), test_rangecoder / test_adaptive (:1170-1237) --
+// compile unchanged against this header:
+//
+//   cpprcoder::RangeEncoder<T>::encode(T&, u32, const u8*) / ::decode     cpprcoder.h:336-337
+//   cpprcoder::AdaptiveRangeEncoder<T>::initialize / ::encode(s32,..) / ::encode(u8)   :636-638
+//   cpprcoder::AdaptiveRangeDecoder<T>::initialize / ::decode             :819-820
+//   cpprcoder::MemoryStream, IStream<T>, Status, Result, u8..u64          :83-247
+//
+// What differs, by design: the bytes written to the stream are a B2RC container
+// (include/b2rc.h) of independent 64 KiB blocks, each block's payload being exactly
+// the reference's output for that block; the work is done by CUDA kernels through the
+// C ABI of libb2rc.so.  There is no CPU coding path: without a CUDA device encode /
+// decode return false / Status_Error.
+//
+// This is new code written against the reference's interface; no reference source is
+// reused.  Stream concept kept: encoders need `s32 write(s32, const u8*)`, decoders
+// are given the whole output through write() as well (a superset of the reference,
+// whose writeByte() fails where capacity < output, cpprcoder.h:1047-1054).
+#ifndef INC_CPPRCODER_B200_H_
+#define INC_CPPRCODER_B200_H_
+
+#include <cassert>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/b2rc.h"
+
+#ifndef CPPRCODER_ASSERT
+#    define CPPRCODER_ASSERT(exp) assert(exp)
+#endif
+#ifndef CPPRCODER_NULL
+#    define CPPRCODER_NULL nullptr
+#endif
+
+namespace cpprcoder
+{
+#ifndef CPPRCODER_TYPES
+#    define CPPRCODER_TYPES
+typedef int8_t s8;
+typedef int16_t s16;
+typedef int32_t s32;
+typedef int64_t s64;
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef float f32;
+typedef double f64;
+typedef char Char;
+using ::size_t;
+using ::uintptr_t;
+#endif
+
+enum Status  // cpprcoder.h:112-117
+{
+    Status_Success = 0,
+    Status_Pending = 1,
+    Status_Error = -1,
+};
+
+struct Result  // cpprcoder.h:119-123
+{
+    Status status_;
+    u32 requestSize_;
+};
+
+// CRTP byte stream, cpprcoder.h:130-166
+template<class T>
+class IStream
+{
+public:
+    s32 read(s32 size, u8* bytes) { return static_cast<T*>(this)->read(size, bytes); }
+    bool readByte(u8& byte) { return static_cast<T*>(this)->readByte(byte); }
+    s32 write(s32 size, const u8* bytes) { return static_cast<T*>(this)->write(size, bytes); }
+    bool writeByte(u8 byte) { return static_cast<T*>(this)->writeByte(byte); }
+
+protected:
+    IStream() {}
+    ~IStream() {}
+
+private:
+    IStream(const IStream&) = delete;
+    IStream& operator=(const IStream&) = delete;
+};
+
+// Growable memory buffer with the reference's conventions (cpprcoder.h:185-247, :964-1077):
+// capacity rounded up to 16, write() grows (x2 below 16 KiB, +16 KiB above), writeByte()
+// never grows, reserve() discards, size() is both cursors.
+class MemoryStream : public IStream<MemoryStream>
+{
+public:
+    MemoryStream() : capacity_(0), size_(0), buffer_(CPPRCODER_NULL) {}
+    explicit MemoryStream(s32 capacity) : capacity_(capacity), size_(0)
+    {
+        capacity_ = (capacity_ <= 0) ? 16 : static_cast<s32>((static_cast<u32>(capacity_) + 15U) & ~15U);
+        buffer_ = static_cast<u8*>(::malloc(static_cast<size_t>(capacity_)));
+    }
+    ~MemoryStream() { ::free(buffer_); }
+
+    s32 capacity() const { return capacity_; }
+    s32 size() const { return size_; }
+    const u8* get() const { return buffer_; }
+    const u8& operator[](s32 index) const
+    {
+        CPPRCODER_ASSERT(0 <= index && index < size_);
+        return buffer_[index];
+    }
+    u8& operator[](s32 index)
+    {
+        CPPRCODER_ASSERT(0 <= index && index < size_);
+        return buffer_[index];
+    }
+
+    void reserve(s32 capacity)
+    {
+        capacity = static_cast<s32>((static_cast<u32>(capacity) + 15U) & ~15U);
+        if(capacity < capacity_) {
+            return;
+        }
+        ::free(buffer_);
+        capacity_ = capacity;
+        buffer_ = static_cast<u8*>(::malloc(static_cast<size_t>(capacity_)));
+    }
+    void resize(s32 size)
+    {
+        CPPRCODER_ASSERT(0 <= size);
+        if(capacity_ < size) {
+            reserve(size);
+        }
+        size_ = size;
+    }
+    s32 read(s32 size, u8* bytes)
+    {
+        const s32 end = size_ + size;
+        if(capacity_ < end) {
+            return -1;
+        }
+        ::memcpy(bytes, buffer_ + size_, static_cast<size_t>(size));
+        size_ = end;
+        return size;
+    }
+    bool readByte(u8& byte)
+    {
+        if(capacity_ < size_ + 1) {
+            return false;
+        }
+        byte = buffer_[size_++];
+        return true;
+    }
+    s32 write(s32 size, const u8* bytes)
+    {
+        CPPRCODER_ASSERT(0 <= size);
+        const s32 end = size_ + size;
+        if(capacity_ < end && !expand(end)) {
+            return -1;
+        }
+        ::memcpy(buffer_ + size_, bytes, static_cast<size_t>(size));
+        size_ = end;
+        return size;
+    }
+    bool writeByte(u8 byte)
+    {
+        if(capacity_ <= size_) {
+            return false;
+        }
+        buffer_[size_++] = byte;
+        return true;
+    }
+
+private:
+    MemoryStream(const MemoryStream&) = delete;
+    MemoryStream& operator=(const MemoryStream&) = delete;
+    static const s32 EXPAND_LIMIT_SIZE = 4096 * 4;
+
+    bool expand(s32 size)
+    {
+        s32 prev = capacity_, capacity = 0;
+        do {
+            if(prev <= 0) {
+                prev = capacity = 1024;
+            } else if(prev < EXPAND_LIMIT_SIZE) {
+                prev = capacity = prev << 1;
+            } else {
+                prev = capacity = prev + EXPAND_LIMIT_SIZE;
+            }
+        } while(capacity < size);
+        capacity = static_cast<s32>((static_cast<u32>(capacity) + 15U) & ~15U);
+        u8* grown = static_cast<u8*>(::malloc(static_cast<size_t>(capacity)));
+        if(CPPRCODER_NULL == grown) {
+            return false;
+        }
+        if(buffer_) {
+            ::memcpy(grown, buffer_, static_cast<size_t>(size_));
+        }
+        ::free(buffer_);
+        capacity_ = capacity;
+        buffer_ = grown;
+        return true;
+    }
+
+    s32 capacity_;
+    s32 size_;
+    u8* buffer_;
+};
+
+namespace detail
+{
+// One b2rc context per host thread, created on first use (device 0 unless
+// CPPRCODER_B200_DEVICE is set).  Null when there is no CUDA device.
+inline b2rc_ctx* context()
+{
+    struct Holder {
+        b2rc_ctx* ctx;
+        Holder() : ctx(CPPRCODER_NULL)
+        {
+            const char* dev = ::getenv("CPPRCODER_B200_DEVICE");
+            b2rc_ctx_create(dev ? ::atoi(dev) : 0, &ctx);
+        }
+        ~Holder() { b2rc_ctx_destroy(ctx); }
+    };
+    static thread_local Holder holder;
+    return holder.ctx;
+}
+
+// the stream API is s32-sized (cpprcoder.h:143); hand large outputs over in slices
+template<class T>
+bool write_all(T& stream, const u8* bytes, u64 size)
+{
+    while(0 < size) {
+        const s32 piece = static_cast<s32>(size < 0x40000000ULL ? size : 0x40000000ULL);
+        if(stream.write(piece, bytes) <= 0) {
+            return false;
+        }
+        bytes += piece;
+        size -= static_cast<u64>(piece);
+    }
+    return true;
+}
+
+template<class T>
+bool encode_to(T& stream, int mode, u32 blockSize, u64 size, const u8* bytes)
+{
+    b2rc_ctx* ctx = context();
+    if(CPPRCODER_NULL == ctx) {
+        return false;
+    }
+    std::vector<u8> out(static_cast<size_t>(b2rc_bound(mode, size, blockSize)));
+    u64 made = 0;
+    static const u8 nothing = 0;
+    if(B2RC_OK != b2rc_encode(ctx, mode, blockSize, bytes ? bytes : &nothing, size, out.data(), out.size(), &made)) {
+        return false;
+    }
+    return write_all(stream, out.data(), made);
+}
+
+template<class T>
+int decode_to(T& stream, u64 size, const u8* bytes)
+{
+    b2rc_ctx* ctx = context();
+    if(CPPRCODER_NULL == ctx) {
+        return B2RC_E_CUDA;
+    }
+    u64 total = 0;
+    int rc = b2rc_peek(bytes, size, CPPRCODER_NULL, CPPRCODER_NULL, &total, CPPRCODER_NULL);
+    if(B2RC_OK != rc) {
+        return rc;
+    }
+    std::vector<u8> out(static_cast<size_t>(total ? total : 1));
+    u64 made = 0;
+    rc = b2rc_decode(ctx, bytes, size, out.data(), out.size(), &made);
+    if(B2RC_OK != rc) {
+        return rc;
+    }
+    return write_all(stream, out.data(), made) ? B2RC_OK : B2RC_E_DST_SMALL;
+}
+} // namespace detail
+
+//----------------------------------------------
+//--- RangeEncoder            (cpprcoder.h:321-619)
+//----------------------------------------------
+template<class T = MemoryStream>
+class RangeEncoder
+{
+public:
+    static const u32 MAX_SIZE = 0x7FFFFFFFU;  // cpprcoder.h:329
+    static const u32 FREQUENCY_SIZE = 256;
+
+    RangeEncoder() : blockSize_(B2RC_DEFAULT_BLOCK) {}
+    ~RangeEncoder() {}
+
+    /// Block size of the container written by encode (multiple of 64, 64 .. 2^23).
+    void setBlockSize(u32 blockSize) { blockSize_ = blockSize; }
+    u32 blockSize() const { return blockSize_; }
+
+    /// cpprcoder.h:375: false when the stream cannot take the output (or no CUDA device).
+    bool encode(T& stream, u32 size, const u8* bytes)
+    {
+        CPPRCODER_ASSERT(size <= MAX_SIZE);
+        CPPRCODER_ASSERT(CPPRCODER_NULL != bytes || 0 == size);
+        return detail::encode_to(stream, B2RC_MODE_STATIC, blockSize_, size, bytes);
+    }
+    /// 64-bit entry for streams above 2 GiB (the C ABI is 64-bit throughout).  A separate name keeps
+    /// `encode(stream, int, ptr)` calls of existing code unambiguous.
+    bool encode64(T& stream, u64 size, const u8* bytes)
+    {
+        return detail::encode_to(stream, B2RC_MODE_STATIC, blockSize_, size, bytes);
+    }
+    /// cpprcoder.h:460: false on short or corrupt input.
+    bool decode(T& stream, u32 size, const u8* bytes)
+    {
+        CPPRCODER_ASSERT(CPPRCODER_NULL != bytes);
+        if(size < 1) {
+            return false;  // cpprcoder.h:468-470
+        }
+        return B2RC_OK == detail::decode_to(stream, size, bytes);
+    }
+    bool decode64(T& stream, u64 size, const u8* bytes) { return B2RC_OK == detail::decode_to(stream, size, bytes); }
+
+private:
+    RangeEncoder(const RangeEncoder&) = delete;
+    RangeEncoder& operator=(const RangeEncoder&) = delete;
+    u32 blockSize_;
+};
+
+//----------------------------------------------
+//--- AdaptiveRangeEncoder    (cpprcoder.h:626-802)
+//----------------------------------------------
+// Streaming contract kept: initialize(stream, total) then encode(size, bytes) any number
+// of times; each call returns {Status_Pending, bytes still expected} until the last byte
+// arrives, which returns {Status_Success, 0} (cpprcoder.h:714-719).  The pieces are
+// gathered on the host and coded on the GPU when the stream is complete.
+template<class T = MemoryStream>
+class AdaptiveRangeEncoder
+{
+public:
+    AdaptiveRangeEncoder() : stream_(CPPRCODER_NULL), umcompressedSize_(0), inSize_(0), blockSize_(B2RC_DEFAULT_BLOCK) {}
+    ~AdaptiveRangeEncoder() {}
+
+    void setBlockSize(u32 blockSize) { blockSize_ = blockSize; }
+
+    bool initialize(T& stream, u32 umcompressedSize)  // cpprcoder.h:678
+    {
+        stream_ = &stream;
+        umcompressedSize_ = umcompressedSize;
+        inSize_ = 0;
+        pending_.clear();
+        if(0 == umcompressedSize_) {  // the reference writes its 4-byte size here; we write the empty container at once
+            return detail::encode_to(*stream_, B2RC_MODE_ADAPTIVE, blockSize_, 0, CPPRCODER_NULL);
+        }
+        return true;
+    }
+
+    Result encode(s32 size, const u8* bytes)  // cpprcoder.h:697
+    {
+        CPPRCODER_ASSERT(CPPRCODER_NULL != stream_);
+        CPPRCODER_ASSERT((static_cast<u64>(inSize_) + static_cast<u64>(size)) <= umcompressedSize_);
+        if(CPPRCODER_NULL == stream_ || size < 0) {
+            return {Status_Error, 0};
+        }
+        if(0 == inSize_ && static_cast<u32>(size) == umcompressedSize_) {  // the common whole-buffer call: no copy
+            inSize_ = umcompressedSize_;
+            return finish(bytes);
+        }
+        pending_.insert(pending_.end(), bytes, bytes + size);
+        inSize_ += static_cast<u32>(size);
+        if(umcompressedSize_ <= inSize_) {
+            return finish(pending_.data());
+        }
+        return {Status_Pending, umcompressedSize_ - inSize_};
+    }
+
+    Result encode(u8 byte) { return encode(1, &byte); }  // cpprcoder.h:722
+
+private:
+    AdaptiveRangeEncoder(const AdaptiveRangeEncoder&) = delete;
+    AdaptiveRangeEncoder& operator=(const AdaptiveRangeEncoder&) = delete;
+
+    Result finish(const u8* bytes)
+    {
+        const bool ok = detail::encode_to(*stream_, B2RC_MODE_ADAPTIVE, blockSize_, umcompressedSize_, bytes);
+        pending_.clear();
+        if(ok) {
+            return {Status_Success, 0};
+        }
+        return {Status_Pending, 0};  // the reference reports a full stream as Pending (cpprcoder.h:708-711)
+    }
+
+    T* stream_;
+    u32 umcompressedSize_;
+    u32 inSize_;
+    u32 blockSize_;
+    std::vector<u8> pending_;
+};
+
+//----------------------------------------------
+//--- AdaptiveRangeDecoder    (cpprcoder.h:809-940)
+//----------------------------------------------
+// decode(size, bytes) may be fed the container in pieces: it answers
+// {Status_Pending, bytes still missing} until the whole container has arrived
+// (the reference resumes the same way when its input starves, cpprcoder.h:901-903).
+template<class T = MemoryStream>
+class AdaptiveRangeDecoder
+{
+public:
+    AdaptiveRangeDecoder() : stream_(CPPRCODER_NULL) {}
+    ~AdaptiveRangeDecoder() {}
+
+    bool initialize(T& stream)  // cpprcoder.h:859
+    {
+        stream_ = &stream;
+        pending_.clear();
+        return true;
+    }
+
+    Result decode(s32 size, const u8* bytes)  // cpprcoder.h:872
+    {
+        if(CPPRCODER_NULL == stream_ || size < 0) {
+            return {Status_Error, 0};
+        }
+        const u8* all = bytes;
+        u64 have = static_cast<u64>(size);
+        if(!pending_.empty()) {
+            pending_.insert(pending_.end(), bytes, bytes + size);
+            all = pending_.data();
+            have = pending_.size();
+        }
+        const u64 need = containerBytes(all, have);
+        if(0 == need) {
+            return {Status_Error, 0};
+        }
+        if(have < need) {
+            if(pending_.empty()) {
+                pending_.assign(bytes, bytes + size);
+            }
+            const u64 missing = need - have;
+            return {Status_Pending, static_cast<u32>(missing < 0xFFFFFFFFULL ? missing : 0xFFFFFFFFULL)};
+        }
+        const int rc = detail::decode_to(*stream_, need, all);
+        pending_.clear();
+        if(B2RC_OK == rc) {
+            return {Status_Success, 0};
+        }
+        return {B2RC_E_DST_SMALL == rc ? Status_Pending : Status_Error, 0};
+    }
+
+private:
+    AdaptiveRangeDecoder(const AdaptiveRangeDecoder&) = delete;
+    AdaptiveRangeDecoder& operator=(const AdaptiveRangeDecoder&) = delete;
+
+    // Total container length once enough of it is known; the smallest prefix that tells
+    // more when it is not; 0 for garbage.
+    static u64 containerBytes(const u8* bytes, u64 have)
+    {
+        if(have < B2RC_HEADER_BYTES) {
+            return B2RC_HEADER_BYTES + 8;
+        }
+        u32 h[8];
+        ::memcpy(h, bytes, sizeof h);
+        if(h[0] != 0x43523242U || (h[1] & 0xFFFFU) != 1U) {
+            return 0;
+        }
+        const u64 nblocks = static_cast<u64>(h[6]) | (static_cast<u64>(h[7]) << 32);
+        const u64 index = B2RC_HEADER_BYTES + 8ULL * (nblocks + 1);
+        if(have < index) {
+            return index;
+        }
+        u64 last;
+        ::memcpy(&last, bytes + index - 8, 8);
+        return index + last;
+    }
+
+    T* stream_;
+    std::vector<u8> pending_;
+};
+
+} // namespace cpprcoder
+#endif // INC_CPPRCODER_B200_H_

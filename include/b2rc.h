@@ -120,6 +120,17 @@ int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
 
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t b2rc_launch_count(const b2rc_ctx* ctx);
+/* Per-kernel device timing.  b2rc_profile(ctx, 1) makes every launch record CUDA events on
+ * its stream; b2rc_kernel_ms returns the duration of the LAST launch of kernel `which`
+ * (-1 if none since profiling was switched on).  Measurement only; off by default. */
+#define B2RC_K_HISTOGRAM 0
+#define B2RC_K_ENCODE 1
+#define B2RC_K_SCAN 2
+#define B2RC_K_COMPACT 3
+#define B2RC_K_DECODE 4
+#define B2RC_K_COUNT 5
+int b2rc_profile(b2rc_ctx* ctx, int enable);
+int b2rc_kernel_ms(b2rc_ctx* ctx, int which, float* ms);
 /* "sm_100a" etc.: the architecture the kernels were compiled for. */
 const char* b2rc_build_arch(void);
 

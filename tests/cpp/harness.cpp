@@ -1,0 +1,197 @@
+// harness.cpp -- drives the drop-in header the way the reference's own harness drives
+// cpprcoder.h: per file, encode -> decode -> byte-compare, one markdown row
+// |file|ratio|enc MiB/s|dec MiB/s| (the format of test/main.cpp:104-107).  The call
+// sequences follow run_rangecoder / run_adaptive / test_rangecoder (test/main.cpp:254-363,
+// :1170-1197); unlike the reference's harness, a mismatch or a failed call is an error exit.
+//
+//   harness <file>...            static + adaptive round trip of every file
+//   harness --selftest           the 127-nibble static test and the chunked adaptive API
+#include "../../cpprcoder_b200/include/cpprcoder_b200.h"
+
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+#include <random>
+#include <string>
+#include <vector>
+
+namespace
+{
+double now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void print(const char* filepath, double ratio, double deflateSpeed, double inflateSpeed)
+{
+    printf("|%s|%f|%f|%f|\n", filepath, ratio, deflateSpeed, inflateSpeed);
+}
+
+bool same(const cpprcoder::MemoryStream& got, const std::vector<cpprcoder::u8>& want)
+{
+    if(got.size() != static_cast<cpprcoder::s32>(want.size())) {
+        printf("size %d != %zu\n", got.size(), want.size());
+        return false;
+    }
+    for(size_t i = 0; i < want.size(); ++i) {
+        if(got[static_cast<cpprcoder::s32>(i)] != want[i]) {
+            printf("[%zu] %d != %d\n", i, got[static_cast<cpprcoder::s32>(i)], want[i]);
+            return false;
+        }
+    }
+    return true;
+}
+
+bool run_rangecoder(const char* filepath, const std::vector<cpprcoder::u8>& src)
+{
+    const cpprcoder::u32 size = static_cast<cpprcoder::u32>(src.size());
+    cpprcoder::MemoryStream encstream(size);
+    cpprcoder::MemoryStream decstream(size);
+    cpprcoder::RangeEncoder<> encoder;
+    double t = now();
+    if(!encoder.encode(encstream, size, src.data())) {
+        printf("%s: static encode failed\n", filepath);
+        return false;
+    }
+    const double deflateTime = now() - t;
+    t = now();
+    if(!encoder.decode(decstream, static_cast<cpprcoder::u32>(encstream.size()), encstream.get())) {
+        printf("%s: static decode failed\n", filepath);
+        return false;
+    }
+    const double inflateTime = now() - t;
+    print(filepath, (double)size / encstream.size(), size / deflateTime / (1024.0 * 1024.0),
+          size / inflateTime / (1024.0 * 1024.0));
+    return same(decstream, src);
+}
+
+bool run_adaptive(const char* filepath, const std::vector<cpprcoder::u8>& src)
+{
+    const cpprcoder::u32 size = static_cast<cpprcoder::u32>(src.size());
+    cpprcoder::MemoryStream encstream(size);
+    cpprcoder::MemoryStream decstream(size);
+    double t = now();
+    cpprcoder::AdaptiveRangeEncoder<> encoder;
+    if(!encoder.initialize(encstream, size)) {
+        return false;
+    }
+    cpprcoder::Result result0 = encoder.encode(static_cast<cpprcoder::s32>(size), src.data());
+    if(cpprcoder::Status_Success != result0.status_) {
+        printf("%s: adaptive encode status %d\n", filepath, result0.status_);
+        return false;
+    }
+    const double deflateTime = now() - t;
+    t = now();
+    cpprcoder::AdaptiveRangeDecoder<> decoder;
+    if(!decoder.initialize(decstream)) {
+        return false;
+    }
+    cpprcoder::Result result1 = decoder.decode(encstream.size(), &encstream[0]);
+    if(cpprcoder::Status_Success != result1.status_) {
+        printf("%s: adaptive decode status %d\n", filepath, result1.status_);
+        return false;
+    }
+    const double inflateTime = now() - t;
+    print(filepath, (double)size / encstream.size(), size / deflateTime / (1024.0 * 1024.0),
+          size / inflateTime / (1024.0 * 1024.0));
+    return same(decstream, src);
+}
+
+bool test_rangecoder()
+{
+    std::mt19937 mt(12345);
+    static const int Size = 127;
+    std::vector<cpprcoder::u8> src(Size);
+    for(int i = 0; i < Size; ++i) {
+        src[i] = static_cast<cpprcoder::u8>(mt() & 0x0FU);
+    }
+    cpprcoder::RangeEncoder<> encoder;
+    cpprcoder::MemoryStream encstream(Size);
+    if(!encoder.encode(encstream, Size, src.data())) {
+        return false;
+    }
+    cpprcoder::MemoryStream decstream(Size);
+    if(!encoder.decode(decstream, static_cast<cpprcoder::u32>(encstream.size()), encstream.get())) {
+        return false;
+    }
+    return same(decstream, src);
+}
+
+// the streaming contract: pieces in, Pending with the remaining count, Success on the last
+bool test_adaptive_chunked()
+{
+    std::mt19937 mt(777);
+    static const int Size = 300000;
+    std::vector<cpprcoder::u8> src(Size);
+    for(int i = 0; i < Size; ++i) {
+        src[i] = static_cast<cpprcoder::u8>((mt() & 0xFFU) < 200 ? 'a' + (mt() % 7) : mt() & 0xFFU);
+    }
+    cpprcoder::AdaptiveRangeEncoder<> encoder;
+    cpprcoder::MemoryStream encstream(16);
+    if(!encoder.initialize(encstream, Size)) {
+        return false;
+    }
+    int fed = 0;
+    while(fed < Size) {
+        const int piece = (Size - fed) < 70001 ? (Size - fed) : 70001;
+        cpprcoder::Result r = encoder.encode(piece, src.data() + fed);
+        fed += piece;
+        if(fed < Size) {
+            if(r.status_ != cpprcoder::Status_Pending || r.requestSize_ != static_cast<cpprcoder::u32>(Size - fed)) {
+                printf("chunked encode: expected Pending/%d, got %d/%u\n", Size - fed, r.status_, r.requestSize_);
+                return false;
+            }
+        } else if(r.status_ != cpprcoder::Status_Success) {
+            return false;
+        }
+    }
+    // one whole-buffer encode must give the same bytes
+    cpprcoder::AdaptiveRangeEncoder<> once;
+    cpprcoder::MemoryStream encstream2(16);
+    once.initialize(encstream2, Size);
+    if(once.encode(Size, src.data()).status_ != cpprcoder::Status_Success || encstream2.size() != encstream.size() ||
+       0 != memcmp(encstream2.get(), encstream.get(), static_cast<size_t>(encstream.size()))) {
+        printf("chunked and whole-buffer encodes differ\n");
+        return false;
+    }
+    cpprcoder::AdaptiveRangeDecoder<> decoder;
+    cpprcoder::MemoryStream decstream(16);
+    decoder.initialize(decstream);
+    int given = 0;
+    const int total = encstream.size();
+    cpprcoder::Result r = {cpprcoder::Status_Pending, 0};
+    while(given < total) {
+        const int piece = (total - given) < 50000 ? (total - given) : 50000;
+        r = decoder.decode(piece, encstream.get() + given);
+        given += piece;
+        if(given < total && r.status_ != cpprcoder::Status_Pending) {
+            printf("chunked decode: expected Pending, got %d\n", r.status_);
+            return false;
+        }
+    }
+    return r.status_ == cpprcoder::Status_Success && same(decstream, src);
+}
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    if(argc >= 2 && std::string(argv[1]) == "--selftest") {
+        const bool a = test_rangecoder();
+        const bool b = test_adaptive_chunked();
+        printf("test_rangecoder %s\ntest_adaptive_chunked %s\n", a ? "ok" : "FAILED", b ? "ok" : "FAILED");
+        return (a && b) ? 0 : 1;
+    }
+    int bad = 0;
+    for(int i = 1; i < argc; ++i) {
+        std::ifstream file(argv[i], std::ios::binary);
+        if(!file.is_open()) {
+            printf("cannot open %s\n", argv[i]);
+            ++bad;
+            continue;
+        }
+        std::vector<cpprcoder::u8> src((std::istreambuf_iterator<char>(file)), std::istreambuf_iterator<char>());
+        bad += run_rangecoder(argv[i], src) ? 0 : 1;
+        bad += run_adaptive(argv[i], src) ? 0 : 1;
+    }
+    return bad ? 1 : 0;
+}

@@ -1,0 +1,74 @@
+"""world_size-2 (and 3) runs of the sharding / index-exchange logic over gloo on CPU tensors.
+The coder itself is CUDA-only; here the ORACLE stands in for it (test infrastructure) so the
+collective, the shard arithmetic and the stitched container can be checked without a GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from _oracle import ADAPTIVE, STATIC, Oracle
+from cpprcoder_b200 import container
+from cpprcoder_b200 import dist as rcdist
+from cpprcoder_b200 import synth
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_total, block, mode, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        data = synth.kennedy(n_total)
+        lo, hi, blk_lo, blk_hi = rcdist.shard_of(n_total, block, rank, world)
+        pays = Oracle.get().encode_blocks(mode, data[lo:hi], block) if hi > lo else []
+        assert len(pays) == blk_hi - blk_lo
+        sizes = torch.tensor([len(p) for p in pays], dtype=torch.int32)
+        all_sizes = rcdist.allgather_sizes(sizes, n_total, block)
+        offsets = rcdist.global_offsets(all_sizes)
+        # every rank must now hold the same, complete index
+        gathered = [None] * world
+        dist.all_gather_object(gathered, offsets.tolist())
+        assert all(g == gathered[0] for g in gathered)
+        assert int(offsets[blk_hi] - offsets[blk_lo]) == sum(len(p) for p in pays)
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(b"".join(pays), parts, dst=0)
+        if rank == 0:
+            nb = container.nblocks_of(n_total, block)
+            buf = np.frombuffer(container.pack_header(mode, block, n_total, nb)
+                                + offsets.numpy().astype(np.uint64).tobytes() + b"".join(parts), dtype=np.uint8)
+            np.save(os.path.join(out_dir, "stitched.npy"), buf)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total,block,mode", [(2, 5 * 4096 + 123, 4096, STATIC), (2, 300, 4096, ADAPTIVE),
+                                                      (3, 10 * 1024, 1024, ADAPTIVE)])
+def test_sharded_index_exchange_and_stitching(tmp_path, built, world, n_total, block, mode):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_total, block, mode, str(tmp_path)), nprocs=world, join=True)
+    buf = np.load(tmp_path / "stitched.npy")
+    info = container.parse(buf)
+    data = synth.kennedy(n_total)
+    o = Oracle.get()
+    # the stitched container is exactly what a single rank would have produced
+    whole = o.encode_blocks(mode, data, block)
+    assert [bytes(info.payload(buf, b)) for b in range(info.nblocks)] == whole
+    back = o.decode_blocks(mode, buf[info.payload_base:], info.offsets, block, n_total)
+    assert back.tobytes() == data.tobytes()
+
+
+def test_shard_of_covers_the_stream():
+    for n_total, block in [(0, 4096), (1, 4096), (4096 * 7 + 5, 4096), (1 << 20, 65536)]:
+        for world in (1, 2, 4, 8):
+            spans = [rcdist.shard_of(n_total, block, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n_total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))

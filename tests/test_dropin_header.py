@@ -1,0 +1,55 @@
+"""The C++ drop-in header (cpprcoder_b200/include/cpprcoder_b200.h) driven the way the
+reference's harness drives cpprcoder.h (tests/cpp/harness.cpp)."""
+import subprocess
+import tarfile
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "cpprcoder_b200"
+
+
+@pytest.fixture(scope="module")
+def harness(built, tmp_path_factory):
+    built.build_native()
+    out = tmp_path_factory.mktemp("harness") / "harness"
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", str(ROOT / "tests" / "cpp" / "harness.cpp"), "-o", str(out),
+           f"-L{PKG}", "-lb2rc", f"-Wl,-rpath,{PKG}"]
+    subprocess.check_call(cmd)
+    return out
+
+
+def test_header_compiles_and_links(harness):
+    assert harness.exists()
+
+
+def test_without_a_device_calls_fail_loudly(harness):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    r = subprocess.run([str(harness), "--selftest"], capture_output=True, text=True)
+    assert r.returncode != 0, "no CUDA device: the drop-in must report failure, not fall back to a CPU coder"
+
+
+@pytest.mark.gpu
+def test_selftests_on_gpu(harness):
+    r = subprocess.run([str(harness), "--selftest"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "test_rangecoder ok" in r.stdout and "test_adaptive_chunked ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_canterbury_rows_on_gpu(harness, tmp_path, golden):
+    with tarfile.open(ROOT / "tests" / "golden" / "cantrbry.tar.bz2", "r:bz2") as tf:
+        tf.extractall(tmp_path)
+    files = sorted(str(p) for p in (tmp_path / "cantrbry").iterdir())
+    r = subprocess.run([str(harness)] + files, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [line.split("|") for line in r.stdout.splitlines() if line.startswith("|")]
+    assert len(rows) == 2 * len(files)
+    # ratio column = original / container bytes: block framing costs a little against the whole-file README ratio
+    for row in rows:
+        name = Path(row[1]).name
+        whole = golden["canterbury"][name]["bytes"] / golden["canterbury"][name]["whole"]["static"]["size"]
+        assert 0.5 * whole < float(row[2]) < 1.6 * whole
