@@ -278,6 +278,7 @@ __device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, u3
                                                  u32 magic, u32 shift, u32 lane)
 {
     const u32 ntiles = (n_max + TILE - 1) / TILE;
+    u32 tcur = POW2 ? (st.range >> shift) : 0u;  // the power-of-two chain carries t, not range
     // tile 0 was staged (and committed) by the caller
 #pragma unroll 1
     for(u32 tix = 0; tix < ntiles; ++tix) {
@@ -305,12 +306,18 @@ __device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, u3
             for(int k = 0; k < 4; ++k) {
                 tab.get((wnext >> (8 * k)) & 0xFFu, ncum[k], nfreq[k]);
             }
+            RcCut cuts[4];
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
                 const bool active = !RAGGED || tix * TILE + wi * 4 + k < n_b;
-                const u32 t = POW2 ? (st.range >> shift) : rc_div(st.range, total, magic);
-                rc_enc_step(st, cum[k], freq[k], t, sink, active);
+                if(POW2) {
+                    rc_enc_step_pow2<WIDE ? 3 : 2>(st, tcur, shift, cum[k], freq[k], cuts[k], active);
+                } else {
+                    const u32 t = rc_div(st.range, total, magic);
+                    rc_enc_step<WIDE ? 3 : 2>(st, cum[k], freq[k], t, cuts[k], active);
+                }
             }
+            rc_enc_commit(st, cuts, sink);
             if(__any_sync(FULL, sink.wcount - sink.flushed >= RING - 4)) {
                 sink.flushed = ring_flush_all(sink, ring_base, lane);
             }
@@ -570,6 +577,7 @@ __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, 
         for(int wi = 0; wi < TILE / 4; ++wi) {
             const u32 word = lds32(row + 4u * (u32)wi);
             const u32 mg = wi < 8 ? mg0 : mg1;
+            RcCut cuts[4];
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
                 const int j = wi * 4 + k;
@@ -581,8 +589,9 @@ __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, 
                     rc_model_encode(tab, sym, cum, freq);
                 }
                 const u32 t = rc_div(st.range, d0 + j, magic);
-                rc_enc_step(st, cum, freq, t, sink, active);
+                rc_enc_step<3>(st, cum, freq, t, cuts[k], active);
             }
+            rc_enc_commit(st, cuts, sink);
             if(__any_sync(FULL, sink.wcount - sink.flushed >= RING - 4)) {
                 sink.flushed = ring_flush_all(sink, ring_base, lane);
             }

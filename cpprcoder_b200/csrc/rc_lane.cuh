@@ -190,44 +190,127 @@ RC_COLD void rc_enc_word_slow(RcEnc& e, u32 word, u32 ovf, Sink& s)
 #define RC_WARP_ANY(p) (p)
 #endif
 
-// One symbol: cum/freq from the model, t = range / total already divided.
-// CONVERGED: every lane of the warp must call this together (it votes).
-template <class Sink>
-RC_HD void rc_enc_step(RcEnc& e, u32 cum, u32 freq, u32 t, Sink& s, bool active = true)
+// A stream word cut off the shift register by one step, waiting to be committed.
+struct RcCut {
+    u32 word, ovf;  // ovf: carry parked above the valid bits; it belongs to the word BEFORE this one
+    bool on;
+};
+
+// Renormalisation shift of a fresh range: 8 bits per round while range < 2^24
+// (cpprcoder.h:418, :783).  Compare-and-select instead of count-leading-zeros: the
+// selects are shorter than FLO on the serial chain.  MAXSH = 2 when range >= 2^8 is
+// guaranteed (total <= 2^16), else 3.
+template <int MAXSH>
+RC_HD u32 rc_norm_shift(u32 r)
 {
+    u32 sh = (r < 0x01000000u) ? 8u : 0u;
+    sh = (r < 0x00010000u) ? 16u : sh;
+    if(MAXSH >= 3) {
+        sh = (r < 0x00000100u) ? 24u : sh;
+    }
+    return sh;
+}
+
+// One symbol, branch free: cum/freq from the model, t = range / total already divided.
+// Leaves at most one cut word in `c`; rc_enc_commit() takes care of it later, off the chain.
+template <int MAXSH>
+RC_HD void rc_enc_step(RcEnc& e, u32 cum, u32 freq, u32 t, RcCut& c, bool active = true)
+{
+    u32 sh = 0;
     if(active) {
         rc_add96(e.low, e.o_lo, e.o_hi, cum * t);
         e.range = freq * t;
-        const u32 sh = rc_clz(e.range) & 24u;  // 8 bits per renormalisation round (cpprcoder.h:418, :783)
-        e.o_hi = rc_funnel_l(e.o_lo, e.o_hi, sh);
-        e.o_lo = rc_funnel_l(e.low, e.o_lo, sh);
-        e.low <<= sh;
+        sh = rc_norm_shift<MAXSH>(e.range);
         e.range <<= sh;
-        e.ocnt += (s32)sh;
     }
-    const bool cut = active && e.ocnt >= 32;
+    e.o_hi = rc_funnel_l(e.o_lo, e.o_hi, sh);
+    e.o_lo = rc_funnel_l(e.low, e.o_lo, sh);
+    e.low <<= sh;
+    e.ocnt += (s32)sh;
+    const bool cut = e.ocnt >= 32;
     const u32 k = (u32)(e.ocnt - 32) & 31u;  // 0..23 when cutting
-    const u32 word = rc_funnel_r(e.o_lo, e.o_hi, k);
-    const u32 ovf = e.o_hi >> k;  // carry parked above the valid bits: belongs to the deferred word
-    const bool slow = cut && (e.nff != 0u || word == 0xFFFFFFFFu);
-    if(RC_WARP_ANY(slow)) {
-        if(slow) {
+    c.word = rc_funnel_r(e.o_lo, e.o_hi, k);
+    c.ovf = e.o_hi >> k;
+    c.on = cut;
+    e.o_hi = cut ? 0u : e.o_hi;
+    e.o_lo = cut ? (e.o_lo & ((1u << k) - 1u)) : e.o_lo;
+    e.ocnt = cut ? (s32)k : e.ocnt;
+}
+
+// Power-of-two total (every full block of the static coder that never halved): the
+// chain is carried by t = range >> shift alone.  (r << sh) >> shift is picked among the
+// three candidates by the same compares that pick sh, so one link of the chain is
+// IMAD -> compare -> select -> select.  `e.range` is not maintained on this path.
+template <int MAXSH>
+RC_HD void rc_enc_step_pow2(RcEnc& e, u32& t, u32 shift, u32 cum, u32 freq, RcCut& c, bool active = true)
+{
+    u32 sh = 0;
+    if(active) {
+        rc_add96(e.low, e.o_lo, e.o_hi, cum * t);
+        const u32 r = freq * t;
+        const bool p8 = r < 0x01000000u, p16 = r < 0x00010000u, p24 = MAXSH >= 3 && r < 0x00000100u;
+        const u32 t0 = r >> shift, t8 = (r << 8) >> shift, t16 = (r << 16) >> shift, t24 = (r << 24) >> shift;
+        u32 tn = p8 ? t8 : t0;
+        tn = p16 ? t16 : tn;
+        sh = p8 ? 8u : 0u;
+        sh = p16 ? 16u : sh;
+        if(MAXSH >= 3) {
+            tn = p24 ? t24 : tn;
+            sh = p24 ? 24u : sh;
+        }
+        t = tn;
+    }
+    e.o_hi = rc_funnel_l(e.o_lo, e.o_hi, sh);
+    e.o_lo = rc_funnel_l(e.low, e.o_lo, sh);
+    e.low <<= sh;
+    e.ocnt += (s32)sh;
+    const bool cut = e.ocnt >= 32;
+    const u32 k = (u32)(e.ocnt - 32) & 31u;
+    c.word = rc_funnel_r(e.o_lo, e.o_hi, k);
+    c.ovf = e.o_hi >> k;
+    c.on = cut;
+    e.o_hi = cut ? 0u : e.o_hi;
+    e.o_lo = cut ? (e.o_lo & ((1u << k) - 1u)) : e.o_lo;
+    e.ocnt = cut ? (s32)k : e.ocnt;
+}
+
+// Commits the cuts of up to N consecutive steps, in order.  The common case is straight
+// line: the parked carry goes into the deferred word, which is pushed, and the new word
+// becomes the deferred one.  All-ones words (cpprcoder.h:431, :796) take the rare path,
+// entered by the whole warp on one vote.  CONVERGED: every lane must call this together.
+template <int N, class Sink>
+RC_HD void rc_enc_commit(RcEnc& e, const RcCut (&c)[N], Sink& s)
+{
+    bool rare = e.nff != 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int k = 0; k < N; ++k) {
+        rare = rare || (c[k].on && c[k].word == 0xFFFFFFFFu);
+    }
+    if(RC_WARP_ANY(rare)) {
+        if(rare) {
             RcEnc te = e;
             typename Sink::Checked ts(s);  // may push a long run: this one checks for room
-            rc_enc_word_slow(te, word, ovf, ts);
+            for(int k = 0; k < N; ++k) {
+                if(c[k].on) {
+                    rc_enc_word_slow(te, c[k].word, c[k].ovf, ts);
+                }
+            }
             e.pend = te.pend;
             e.nff = te.nff;
             ts.settle(s);
+            return;
         }
     }
-    if(cut) {
-        if(!slow) {
-            s.push(e.pend + ovf);
-            e.pend = word;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int k = 0; k < N; ++k) {
+        if(c[k].on) {
+            s.push(e.pend + c[k].ovf);
+            e.pend = c[k].word;
         }
-        e.o_hi = 0;
-        e.o_lo &= (1u << k) - 1u;
-        e.ocnt = (s32)k;
     }
 }
 

@@ -93,10 +93,21 @@ long sim_encode(int mode, const u8* src, u32 n, u8* dst, size_t cap, int force_e
         const u32 shT = pow2 ? 31u - rc_clz(total) : 0;
         rc_enc_init(e, RC_STATIC_RANGE0);
         if(!force_exact) {
-            for(u32 i = 0; i < n; ++i) {
-                const u32 c = src[i];
-                const u32 t = pow2 ? (e.range >> shT) : rc_div(e.range, total, magic);
-                rc_enc_step(e, cum[c], cum[c + 1] - cum[c], t, sink);
+            // groups of four steps, then one commit -- the shape of the kernel's hot loop
+            u32 t = pow2 ? (e.range >> shT) : 0;
+            for(u32 i = 0; i < n; i += 4) {
+                RcCut cuts[4];
+                for(u32 k = 0; k < 4; ++k) {
+                    const bool active = i + k < n;
+                    const u32 c = active ? src[i + k] : 0;
+                    if(pow2) {
+                        rc_enc_step_pow2<2>(e, t, shT, cum[c], cum[c + 1] - cum[c], cuts[k], active);
+                    } else {
+                        const u32 tt = active ? rc_div(e.range, total, magic) : 0;
+                        rc_enc_step<3>(e, cum[c], cum[c + 1] - cum[c], tt, cuts[k], active);
+                    }
+                }
+                rc_enc_commit(e, cuts, sink);
             }
         }
         if(force_exact || e.low == 0xFFFFFFFFu) {
@@ -112,12 +123,19 @@ long sim_encode(int mode, const u8* src, u32 n, u8* dst, size_t cap, int force_e
         ArrTab tab;
         memset(tab.v, 0, sizeof tab.v);
         rc_enc_init(e, RC_ADAPT_RANGE0);
-        for(u32 i = 0; i < n; ++i) {
-            u32 cum, freq;
-            rc_model_encode(tab, src[i], cum, freq);
-            const u32 d = 256u + i;
-            const u32 t = rc_div(e.range, d, rc_magic(d));
-            rc_enc_step(e, cum, freq, t, sink);
+        for(u32 i = 0; i < n; i += 4) {
+            RcCut cuts[4];
+            for(u32 k = 0; k < 4; ++k) {
+                const bool active = i + k < n;
+                u32 cum = 0, freq = 1, t = 0;
+                if(active) {
+                    rc_model_encode(tab, src[i + k], cum, freq);
+                    const u32 d = 256u + i + k;
+                    t = rc_div(e.range, d, rc_magic(d));
+                }
+                rc_enc_step<3>(e, cum, freq, t, cuts[k], active);
+            }
+            rc_enc_commit(e, cuts, sink);
         }
         const u32 nt = rc_enc_finish(e, sink, tail);
         out.insert(out.end(), tail, tail + nt);
