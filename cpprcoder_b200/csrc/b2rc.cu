@@ -104,19 +104,19 @@ u64 index_bytes(u64 nblocks)
 // dynamic shared memory of the coder kernels (one warp per CTA)
 constexpr u32 smem_enc_static(bool wide)
 {
-    return (wide ? 257u : 256u) * 128u + 2u * TILE_BYTES + RING_BYTES;
+    return (wide ? 257u : 256u) * 128u + 2u * TILE_BYTES;
 }
 constexpr u32 smem_enc_adaptive(bool wide)
 {
-    return 512u * 32u * (wide ? 4u : 2u) + 2u * TILE_BYTES + RING_BYTES;
+    return 512u * 32u * (wide ? 4u : 2u) + 2u * TILE_BYTES;
 }
 constexpr u32 smem_dec_static()
 {
-    return DEC_STATIC_TAB + TILE_BYTES + RING_BYTES;
+    return DEC_STATIC_TAB + TILE_BYTES;
 }
 constexpr u32 smem_dec_adaptive(bool wide)
 {
-    return 512u * 32u * (wide ? 4u : 2u) + TILE_BYTES + RING_BYTES;
+    return 512u * 32u * (wide ? 4u : 2u) + TILE_BYTES;
 }
 
 int set_smem_limits(b2rc_ctx* ctx)

@@ -13,9 +13,10 @@
 // instructions one step of a (lone) warp needs -- not from splitting a block over a
 // warp.  Per-warp shared memory holds
 //   * the model table, interleaved by lane ([entry][lane]: bank == lane),
-//   * input tiles staged by cp.async (encode) / a refilled word ring (decode),
-//   * an output word ring (encode) / an output tile (decode),
-// and all global traffic is done cooperatively by the warp in 128-byte rows.
+//   * input tiles staged by cp.async (encode) / an output tile (decode), moved by the
+//     whole warp in 16-byte vectors, 8 rows of 64 bytes per instruction.
+// The variable-rate side of each coder (coded words out of the encoder, into the decoder)
+// is per lane: 4-byte accesses that L2 / L1 merge into sectors (see SlotSink, WordSrc).
 // Hot-loop shared-memory accesses use explicit ld/st.shared on 32-bit shared
 // addresses: generic pointers made the compiler rebuild the shared window base
 // (S2UR SR_CgaCtaId) on every step and turned ring stores into generic ST.
@@ -29,11 +30,7 @@ namespace b2rc
 constexpr u32 FULL = 0xFFFFFFFFu;
 constexpr int TILE = 64;        // symbols per lane per staged tile
 constexpr int ROW = 80;         // bytes per lane row of a tile (64 + 16 pad; rows stay 16-byte aligned)
-constexpr int RING = 32;        // words per lane in the output (encode) / input (decode) ring
-constexpr int RING_ROW = 33;    // words between two lanes' rings: word i of lane r sits in bank (r + i) & 31,
-                                // so a lane's own accesses and the warp's row-wise sweeps both spread over banks
 constexpr int TILE_BYTES = 32 * ROW;
-constexpr int RING_BYTES = 32 * RING_ROW * 4;  // 4224, a multiple of 16
 
 enum : int {
     ERR_SLOT_OVERFLOW = 1,  // a payload outgrew its slot
@@ -126,87 +123,44 @@ __device__ __forceinline__ void stage_tile(u32 tile, const u8* src, u64 n, u64 b
 }
 
 // ------------------------------------------------------------ encoder output --
-// Words leave a lane through its ring in shared memory; the warp empties all 32
-// rings together, one lane's words per 128-byte row.  `wcount` starts at -1: the
-// encoder's first push is its placeholder word (rc_lane.cuh, Sink contract) and
-// lands in a ring slot that is never flushed.
-struct CheckedRingSink;
-struct RingSink {
-    typedef CheckedRingSink Checked;
-    u32 ring;  // shared address of this lane's ring row
+// A committed word is final (carries only ever reach the deferred word, rc_lane.cuh), so
+// each lane stores its words straight into its own staging slot: 4-byte stores to 32
+// different lines per instruction, which the L2 merges into full sectors long before they
+// are evicted.  An earlier version staged words in a shared-memory ring and flushed all
+// 32 rings cooperatively; the 32 serial shuffle/load/store rounds of that flush cost a
+// third of the kernel (profiles/r1_ncu_notes.md).
+// `wcount` starts at -1: the encoder's first push is its placeholder word (Sink contract)
+// and lands on the 4 bytes in front of the coded stream, which finish_block() restores.
+struct CheckedSlotSink;
+struct SlotSink {
+    typedef CheckedSlotSink Checked;
     u32* out;  // coded stream start of this lane's block (slot + header), 4-byte aligned
-    s32 wcount, flushed;
+    s32 wcount;
     u32 cap_words;
     int* err;
 
-    __device__ __forceinline__ void push(u32 w)  // hot path: room is guaranteed by the flush policy
+    __device__ __forceinline__ bool tight(int n) const { return (u32)(wcount + n) > cap_words; }
+    __device__ __forceinline__ void push(u32 w)  // hot path: rc_enc_commit checked tight() first
     {
-        sts32v(ring + (((u32)wcount & (RING - 1)) << 2), rc_bswap(w));
+        out[wcount] = rc_bswap(w);
         ++wcount;
     }
 };
 
-// Lane-local emptying of one ring: only when a single lane outruns the warp (long 0xFF runs).
-__device__ __noinline__ s32 ring_drain(u32 ring, u32* out, s32 flushed, s32 wcount, u32 cap_words)
-{
-    for(s32 i = flushed < 0 ? 0 : flushed; i < wcount; ++i) {
-        if((u32)i < cap_words) {
-            out[i] = lds32v(ring + (((u32)i & (RING - 1)) << 2));
-        }
-    }
-    return wcount;
-}
-
-struct CheckedRingSink {
-    RingSink s;
-    __device__ explicit CheckedRingSink(const RingSink& r) : s(r) {}
+struct CheckedSlotSink {
+    SlotSink s;
+    __device__ explicit CheckedSlotSink(const SlotSink& r) : s(r) {}
     __device__ void push(u32 w)
     {
-        if(s.wcount - s.flushed >= RING) {
-            s.flushed = ring_drain(s.ring, s.out, s.flushed, s.wcount, s.cap_words);
+        if(s.wcount < 0 || (u32)s.wcount < s.cap_words) {
+            s.out[s.wcount] = rc_bswap(w);
+        } else {
+            atomicOr(s.err, ERR_SLOT_OVERFLOW);
         }
-        s.push(w);
+        ++s.wcount;
     }
-    __device__ void settle(RingSink& r)
-    {
-        // leave room for the unchecked pushes that may still follow before the next flush check
-        if(s.wcount - s.flushed > RING - 8) {
-            s.flushed = ring_drain(s.ring, s.out, s.flushed, s.wcount, s.cap_words);
-        }
-        r.wcount = s.wcount;
-        r.flushed = s.flushed;
-    }
+    __device__ void settle(SlotSink& r) { r.wcount = s.wcount; }
 };
-
-// Cooperative flush of all 32 rings.  By value: the caller's sink stays in registers.
-__device__ __noinline__ s32 ring_flush_all(RingSink s, u32 ring_base, u32 lane)
-{
-    __syncwarp();
-#pragma unroll 1
-    for(int r = 0; r < 32; ++r) {
-        s32 f = __shfl_sync(FULL, s.flushed, r);
-        const s32 w = __shfl_sync(FULL, s.wcount, r);
-        if(f < 0) {
-            f = 0;
-        }
-        if(f >= w) {
-            continue;
-        }
-        u32* o = (u32*)__shfl_sync(FULL, (unsigned long long)s.out, r);
-        const u32 capw = __shfl_sync(FULL, s.cap_words, r);
-        const u32 row = ring_base + (u32)r * (RING_ROW * 4u);
-        for(s32 i = f + (s32)lane; i < w; i += 32) {
-            if((u32)i < capw) {
-                o[i] = lds32v(row + (((u32)i & (RING - 1)) << 2));
-            }
-        }
-    }
-    if(s.wcount > 0 && (u32)s.wcount > s.cap_words) {
-        atomicOr(s.err, ERR_SLOT_OVERFLOW);
-    }
-    __syncwarp();
-    return s.wcount;
-}
 
 struct EncArgs {
     const u8* src;
@@ -220,22 +174,19 @@ struct EncArgs {
     int* err;
 };
 
-// Tail of a block: the 4..7 bytes that do not fill a word, then the size.
-__device__ __forceinline__ void finish_block(RcEnc& st, RingSink& sink, u32 ring_base, u32 lane, bool has, u32 hdr,
-                                             u8* slot, u32* size_out)
+// Tail of a block: the 4..7 bytes that do not fill a word, then the size.  `front` is what
+// the 4 bytes in front of the coded stream must hold (the placeholder word overwrote them).
+__device__ __forceinline__ void finish_block(RcEnc& st, SlotSink& sink, bool has, u32 hdr, u32 front, u8* slot,
+                                             u32* size_out)
 {
-    u8 tail[8];
-    u32 ntail = 0;
     if(has) {
-        CheckedRingSink cs(sink);
-        ntail = rc_enc_finish(st, cs, tail);
+        u8 tail[8];
+        CheckedSlotSink cs(sink);
+        const u32 ntail = rc_enc_finish(st, cs, tail);
         sink.wcount = cs.s.wcount;
-        sink.flushed = cs.s.flushed;
-    }
-    sink.flushed = ring_flush_all(sink, ring_base, lane);
-    if(has) {
+        sink.out[-1] = front;
         const u32 at = hdr + 4u * (u32)sink.wcount;
-        if((u64)at + ntail <= (u64)hdr + 4ull * sink.cap_words) {
+        if((u32)sink.wcount <= sink.cap_words && (u64)at + ntail <= (u64)hdr + 4ull * sink.cap_words) {
             for(u32 k = 0; k < ntail; ++k) {
                 slot[at + k] = tail[k];
             }
@@ -273,9 +224,9 @@ struct StaticTab {
 };
 
 template <bool WIDE, bool POW2, bool RAGGED>
-__device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, u32 ring_base, const StaticTab<WIDE>& tab,
-                                                 RcEnc& st, RingSink& sink, u64 b0, u32 n_b, u32 n_max, u32 total,
-                                                 u32 magic, u32 shift, u32 lane)
+__device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, const StaticTab<WIDE>& tab, RcEnc& st,
+                                                 SlotSink& sink, u64 b0, u32 n_b, u32 n_max, u32 total, u32 magic,
+                                                 u32 shift, u32 lane)
 {
     const u32 ntiles = (n_max + TILE - 1) / TILE;
     u32 tcur = POW2 ? (st.range >> shift) : 0u;  // the power-of-two chain carries t, not range
@@ -318,9 +269,6 @@ __device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, u3
                 }
             }
             rc_enc_commit(st, cuts, sink);
-            if(__any_sync(FULL, sink.wcount - sink.flushed >= RING - 4)) {
-                sink.flushed = ring_flush_all(sink, ring_base, lane);
-            }
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
                 cum[k] = ncum[k];
@@ -338,7 +286,6 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
     constexpr u32 TAB_BYTES = WIDE ? ENC_STATIC_TAB_WIDE : ENC_STATIC_TAB_NARROW;
     const u32 sbase = smem_addr(smem);
     const u32 tiles = sbase + TAB_BYTES;
-    const u32 ring_base = tiles + 2 * TILE_BYTES;
 
     const u32 lane = lane_id();
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -351,6 +298,7 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
     }
     u8* slot = a.slots + b * a.slot_stride;
     u32 total = 0;
+    u32 front = 0;  // header bytes 512..515 (frequencies of symbols 254, 255)
 
     if(!WIDE) {
         // first input tile in flight while the tables are built
@@ -390,8 +338,10 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
                 run += f[k];
             }
             const u32 tot = __shfl_sync(FULL, incl, 31);
+            const u32 last = __shfl_sync(FULL, v.w, 31);
             if(lane == r) {
                 total = tot;
+                front = last;
             }
             // payload header: u32 LE size, then write16 (cpprcoder.h:386-395, :604-619)
             u8* slot_r = a.slots + (b0 + r) * a.slot_stride;
@@ -455,6 +405,7 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
             }
             mine[256u * 32u] = run;
             total = run;
+            front = *reinterpret_cast<const u32*>(slot + RC_STATIC_HDR - 4u);
         }
         __syncwarp();
         stage_tile(tiles, a.src, a.n, b0, a.block, 0, lane);
@@ -463,11 +414,9 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
 
     RcEnc st;
     rc_enc_init(st, RC_STATIC_RANGE0);
-    RingSink sink;
-    sink.ring = ring_base + lane * (RING_ROW * 4u);
+    SlotSink sink;
     sink.out = reinterpret_cast<u32*>(slot + RC_STATIC_HDR);
     sink.wcount = -1;
-    sink.flushed = 0;
     sink.cap_words = has ? (u32)((a.slot_stride - RC_STATIC_HDR) / 4u) : 0u;
     sink.err = a.err;
 
@@ -480,11 +429,11 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
     const bool ragged = __any_sync(FULL, n_b != n_max);
 
     if(all_pow2 && !ragged) {
-        enc_static_tiles<WIDE, true, false>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
+        enc_static_tiles<WIDE, true, false>(a, tiles, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
     } else if(!ragged) {
-        enc_static_tiles<WIDE, false, false>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
+        enc_static_tiles<WIDE, false, false>(a, tiles, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
     } else {
-        enc_static_tiles<WIDE, false, true>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
+        enc_static_tiles<WIDE, false, true>(a, tiles, tab, st, sink, b0, n_b, n_max, total, magic, shift, lane);
     }
 
     // cpprcoder.h:439-451: when the block ends on low_ == 0xFFFFFFFF the reference bumps
@@ -493,8 +442,7 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
     bool exact = false;
     if(has && st.low == 0xFFFFFFFFu) {
         exact = true;
-        sink.wcount = sink.flushed < 0 ? 0 : sink.flushed;  // drop what the ring still holds
-        sink.flushed = sink.wcount;
+        sink.out[-1] = front;
         u32 at = RC_STATIC_HDR;
         const u8* blk = a.src + b * (u64)a.block;
         const u32 cap = (u32)a.slot_stride;
@@ -531,7 +479,7 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
         }
         a.sizes[b] = at;
     }
-    finish_block(st, sink, ring_base, lane, has && !exact, RC_STATIC_HDR, slot, a.sizes + b);
+    finish_block(st, sink, has && !exact, RC_STATIC_HDR, front, slot, a.sizes + b);
 }
 
 // ======================================================================= K2a ==
@@ -557,8 +505,8 @@ struct LaneTab {
 };
 
 template <class W, bool RAGGED>
-__device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, u32 ring_base, LaneTab<W>& tab,
-                                                   RcEnc& st, RingSink& sink, u64 b0, u32 n_b, u32 n_max, u32 lane)
+__device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, LaneTab<W>& tab, RcEnc& st,
+                                                   SlotSink& sink, u64 b0, u32 n_b, u32 n_max, u32 lane)
 {
     const u32 ntiles = (n_max + TILE - 1) / TILE;
 #pragma unroll 1
@@ -592,9 +540,6 @@ __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, 
                 rc_enc_step<3>(st, cum, freq, t, cuts[k], active);
             }
             rc_enc_commit(st, cuts, sink);
-            if(__any_sync(FULL, sink.wcount - sink.flushed >= RING - 4)) {
-                sink.flushed = ring_flush_all(sink, ring_base, lane);
-            }
         }
         __syncwarp();
     }
@@ -607,7 +552,6 @@ __global__ void __launch_bounds__(32) k_enc_adaptive(EncArgs a)
     constexpr u32 TAB_BYTES = 512u * 32u * sizeof(W);
     const u32 sbase = smem_addr(smem);
     const u32 tiles = sbase + TAB_BYTES;
-    const u32 ring_base = tiles + 2 * TILE_BYTES;
 
     const u32 lane = lane_id();
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -635,28 +579,25 @@ __global__ void __launch_bounds__(32) k_enc_adaptive(EncArgs a)
 
     RcEnc st;
     rc_enc_init(st, RC_ADAPT_RANGE0);
-    RingSink sink;
-    sink.ring = ring_base + lane * (RING_ROW * 4u);
+    SlotSink sink;
     sink.out = reinterpret_cast<u32*>(slot + RC_ADAPT_HDR);
     sink.wcount = -1;
-    sink.flushed = 0;
     sink.cap_words = has ? (u32)((a.slot_stride - RC_ADAPT_HDR) / 4u) : 0u;
     sink.err = a.err;
     LaneTab<W> tab{sbase + lane * (u32)sizeof(W)};
 
     const u32 n_max = __reduce_max_sync(FULL, n_b);
     if(__any_sync(FULL, n_b != n_max)) {
-        enc_adaptive_tiles<W, true>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, lane);
+        enc_adaptive_tiles<W, true>(a, tiles, tab, st, sink, b0, n_b, n_max, lane);
     } else {
-        enc_adaptive_tiles<W, false>(a, tiles, ring_base, tab, st, sink, b0, n_b, n_max, lane);
+        enc_adaptive_tiles<W, false>(a, tiles, tab, st, sink, b0, n_b, n_max, lane);
     }
-    finish_block(st, sink, ring_base, lane, has, RC_ADAPT_HDR, slot, a.sizes + b);
+    finish_block(st, sink, has, RC_ADAPT_HDR, n_b, slot, a.sizes + b);
 }
 
 // ============================================================= decoder input ==
-// Each lane reads its own payload at its own pace.  The warp keeps a ring of
-// aligned stream words per lane topped up (128-byte rows, one lane's stream per
-// row); a lane pops one word whenever its bit window runs low.
+// Each lane reads its own payload at its own pace (WordSrc below); it pops one aligned
+// word whenever its bit window runs low.
 struct DecArgs {
     const u8* payload;    // payload base
     u64 payload_len;
@@ -668,28 +609,12 @@ struct DecArgs {
     int* err;
 };
 
-struct WordSrc {
-    u32 ring;         // shared address of this lane's ring row
-    const u8* wbase;  // aligned address of the word holding coded byte 0
-    const u8* end;    // one past the last readable stream byte
-    u32 consumed, filled, limit;
-
-    __device__ __forceinline__ u32 operator()()
-    {
-        u32 w = 0;
-        if(consumed < filled) {
-            w = rc_bswap(lds32v(ring + ((consumed & (RING - 1)) << 2)));
-        }
-        ++consumed;
-        return w;
-    }
-};
-
-__device__ __forceinline__ u32 load_stream_word(const u8* p, const u8* end)
+// Each lane reads its own payload at its own pace, one aligned word at a time, straight
+// from global memory (read-only path; a 32-byte sector serves 8 consecutive words out of
+// L1).  Two words are always in flight ahead of the one being consumed, so the load
+// latency stays off the decode chain.
+__device__ __noinline__ u32 load_stream_tail(const u8* p, const u8* end)
 {
-    if(p + 4 <= end) {
-        return *reinterpret_cast<const u32*>(p);
-    }
     u32 w = 0;
     for(int k = 0; k < 4; ++k) {
         if(p + k < end) {
@@ -699,35 +624,35 @@ __device__ __forceinline__ u32 load_stream_word(const u8* p, const u8* end)
     return w;
 }
 
-__device__ __noinline__ u32 ring_fill_all(WordSrc s, u32 ring_base, u32 lane)
-{
-    u32 mine = s.filled;
-    __syncwarp();
-#pragma unroll 1
-    for(int r = 0; r < 32; ++r) {
-        const u32 c = __shfl_sync(FULL, s.consumed, r);
-        const u32 f = __shfl_sync(FULL, s.filled, r);
-        const u32 lim = __shfl_sync(FULL, s.limit, r);
-        u32 target = c + (u32)RING;
-        if(target > lim) {
-            target = lim;
+struct WordSrc {
+    const u32* base;  // aligned word holding coded byte 0 of this lane's payload
+    const u8* end;    // one past the last byte of the whole stream buffer
+    u32 idx;          // next word to request
+    u32 nfull;        // words of `base` that lie wholly inside the stream buffer
+    u32 q0, q1;       // requested, not yet consumed (q0 first)
+
+    __device__ __forceinline__ u32 fetch(u32 i) const
+    {
+        if(i < nfull) {
+            return __ldg(base + i);
         }
-        if(f >= target) {
-            continue;
-        }
-        const u8* wb = (const u8*)__shfl_sync(FULL, (unsigned long long)s.wbase, r);
-        const u8* end = (const u8*)__shfl_sync(FULL, (unsigned long long)s.end, r);
-        const u32 row = ring_base + (u32)r * (RING_ROW * 4u);
-        for(u32 i = f + lane; i < target; i += 32u) {
-            sts32v(row + ((i & (RING - 1)) << 2), load_stream_word(wb + 4ull * i, end));
-        }
-        if(lane == (u32)r) {
-            mine = target;
-        }
+        return load_stream_tail(reinterpret_cast<const u8*>(base + i), end);
     }
-    __syncwarp();
-    return mine;
-}
+    __device__ __forceinline__ void prime()
+    {
+        q0 = fetch(0);
+        q1 = fetch(1);
+        idx = 2;
+    }
+    __device__ __forceinline__ u32 operator()()
+    {
+        const u32 w = rc_bswap(q0);
+        q0 = q1;
+        q1 = fetch(idx);
+        ++idx;
+        return w;
+    }
+};
 
 // Output tile -> global, 8 rows of 64 bytes per instruction.
 __device__ __forceinline__ void store_tile(const u8* tile, u8* dst, u64 n, u64 b0, u32 block, u32 tile_off, u32 lane)
@@ -759,8 +684,8 @@ __device__ __forceinline__ void store_tile(const u8* tile, u8* dst, u64 n, u64 b
     }
 }
 
-__device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u32 lane, u64 b, bool has, u32 n_b, u32 ring_base,
-                                          WordSrc& src, const u8*& pay, bool& ok)
+__device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u64 b, bool has, u32 n_b, WordSrc& src,
+                                          const u8*& pay, bool& ok)
 {
     pay = a.payload;
     u64 len = 0;
@@ -780,12 +705,16 @@ __device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u32 lane, u
         atomicOr(a.err, ERR_CORRUPT);
     }
     const u8* coded = pay + hdr;
-    src.ring = ring_base + lane * (RING_ROW * 4u);
-    src.consumed = 0;
-    src.filled = 0;
-    src.wbase = (const u8*)((uintptr_t)coded & ~(uintptr_t)3);
-    src.end = pay + len;
-    src.limit = ok ? (u32)((src.end - src.wbase + 3) / 4) : 0u;
+    const u8* wbase = (const u8*)((uintptr_t)coded & ~(uintptr_t)3);
+    src.base = reinterpret_cast<const u32*>(wbase);
+    src.end = a.payload + a.payload_len;
+    // reading past this block's own payload is harmless (those bits are never decisive for a
+    // valid stream); reading past the buffer is not, so only whole in-buffer words load directly
+    src.nfull = ok ? (u32)((u64)(src.end - wbase) / 4u < 0xFFFFFFFFull ? (u64)(src.end - wbase) / 4u : 0xFFFFFFFFull) : 0u;
+    if(!ok) {
+        src.end = wbase;  // everything reads as zero
+    }
+    src.prime();
 }
 
 // ======================================================================= K3s ==
@@ -803,7 +732,6 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     u32* table = reinterpret_cast<u32*>(smem);
     u8* otile = smem + DEC_STATIC_TAB;
     const u32 otile_a = sbase + DEC_STATIC_TAB;
-    const u32 ring_base = otile_a + TILE_BYTES;
 
     const u32 lane = lane_id();
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -817,7 +745,7 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     WordSrc src;
     const u8* pay;
     bool ok;
-    dec_setup(a, RC_STATIC_HDR, lane, b, has, n_b, ring_base, src, pay, ok);
+    dec_setup(a, RC_STATIC_HDR, b, has, n_b, src, pay, ok);
 
     // read16 + calcCumulatives (cpprcoder.h:585-602, :573-583); payloads are unaligned
     u32* mine = table + lane;
@@ -848,11 +776,10 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     }
     if(!ok) {
         n_b = 0;
-        src.limit = 0;
         total = 1;
     }
+    __syncwarp();
     const u32 magic = rc_magic(total);
-    src.filled = ring_fill_all(src, ring_base, lane);
     RcDec d;
     rc_dec_init(d, RC_STATIC_RANGE0, (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u), src);
 
@@ -862,33 +789,31 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     for(u32 tix = 0; tix < ntiles; ++tix) {
 #pragma unroll 1
         for(int wi = 0; wi < TILE / 4; ++wi) {
-            if((wi & 3) == 0 && __any_sync(FULL, src.filled < src.limit && src.filled - src.consumed < 13u)) {
-                src.filled = ring_fill_all(src, ring_base, lane);
-            }
             u32 word = 0;
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
                 if(tix * TILE + wi * 4 + k < n_b) {
                     const u32 t = rc_div(d.range, total, magic);
-                    u32 c1 = 0;
+                    u32 m1 = 0;  // minus the number of chunk boundaries at or below low
 #pragma unroll
                     for(int j = 1; j < 16; ++j) {
-                        c1 += (key[j] * t <= d.low) ? 1u : 0u;
+                        m1 += rc_le_mask(key[j], t, d.low);
                     }
-                    const u32 chunk = mine_a + c1 * (16u * 128u);
+                    const u32 chunk = mine_a - m1 * (16u * 128u);
                     u32 e[16];
 #pragma unroll
                     for(int j = 1; j < 16; ++j) {
                         e[j] = lds32(chunk + j * 128u);
                     }
-                    u32 c2 = 0;
+                    u32 m2 = 0;
 #pragma unroll
                     for(int j = 1; j < 16; ++j) {
-                        c2 += (e[j] * t <= d.low) ? 1u : 0u;
+                        m2 += rc_le_mask(e[j], t, d.low);
                     }
-                    const u32 sym = 16u * c1 + c2;
-                    const u32 cum = lds32(chunk + c2 * 128u);
-                    const u32 freq = lds32(chunk + c2 * 128u + 128u) - cum;
+                    const u32 at = chunk - m2 * 128u;
+                    const u32 sym = (at - mine_a) >> 7;
+                    const u32 cum = lds32(at);
+                    const u32 freq = lds32(at + 128u) - cum;
                     rc_dec_advance(d, cum, freq, t, src);
                     word |= sym << (8 * k);
                 }
@@ -913,7 +838,6 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
     const u32 sbase = smem_addr(smem);
     u8* otile = smem + TAB_BYTES;
     const u32 otile_a = sbase + TAB_BYTES;
-    const u32 ring_base = otile_a + TILE_BYTES;
 
     const u32 lane = lane_id();
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -927,7 +851,7 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
     WordSrc src;
     const u8* pay;
     bool ok;
-    dec_setup(a, RC_ADAPT_HDR, lane, b, has, n_b, ring_base, src, pay, ok);
+    dec_setup(a, RC_ADAPT_HDR, b, has, n_b, src, pay, ok);
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
         for(u32 i = lane; i < TAB_BYTES / 16u; i += 32u) {
@@ -936,11 +860,9 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
     }
     if(!ok) {
         n_b = 0;
-        src.limit = 0;
     }
     __syncwarp();
     LaneTab<W> tab{sbase + lane * (u32)sizeof(W)};
-    src.filled = ring_fill_all(src, ring_base, lane);
     RcDec d;
     rc_dec_init(d, RC_ADAPT_RANGE0, (u32)((uintptr_t)(pay + RC_ADAPT_HDR) & 3u), src);
 
@@ -953,9 +875,6 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
         const u32 mg1 = rc_magic(d0 + 32u + lane);
 #pragma unroll 1
         for(int wi = 0; wi < TILE / 4; ++wi) {
-            if((wi & 3) == 0 && __any_sync(FULL, src.filled < src.limit && src.filled - src.consumed < 13u)) {
-                src.filled = ring_fill_all(src, ring_base, lane);
-            }
             const u32 mg = wi < 8 ? mg0 : mg1;
             u32 word = 0;
 #pragma unroll

@@ -124,9 +124,9 @@ struct RcEnc {
 // Sink contract: push(word) appends one big-endian stream word.  The FIRST word an
 // encoder pushes is a placeholder (the initial `pend`) and must be discarded by the
 // sink -- that spares the hot path a "has a deferred word yet?" test.  push() on the
-// hot path may assume room for one word per symbol; Sink::Checked is the variant the
-// rare path uses for runs of any length, and Checked::settle(sink) writes its
-// bookkeeping back.
+// hot path may assume room: rc_enc_commit asks tight(n) first and takes the rare path
+// when fewer than n words are left.  Sink::Checked is the variant the rare path uses
+// (runs of any length, bounds checked); Checked::settle(sink) writes its bookkeeping back.
 RC_HD void rc_enc_init(RcEnc& e, u32 range0)
 {
     e.low = 0;
@@ -281,7 +281,7 @@ RC_HD void rc_enc_step_pow2(RcEnc& e, u32& t, u32 shift, u32 cum, u32 freq, RcCu
 template <int N, class Sink>
 RC_HD void rc_enc_commit(RcEnc& e, const RcCut (&c)[N], Sink& s)
 {
-    bool rare = e.nff != 0u;
+    bool rare = e.nff != 0u || s.tight(N);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -401,6 +401,15 @@ RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, 
     put((u8)low);
 }
 
+// All ones when key * t <= low, else zero -- from the high word of one 64-bit multiply-add
+// (key*t - low - 1 is negative exactly then; |.| < 2^32 because key*t <= total*t <= range).
+// Summing these masks counts the boundaries at or below `low` without a compare per key.
+RC_HD u32 rc_le_mask(u32 key, u32 t, u32 low)
+{
+    const u64 x = (u64)key * t + (0xFFFFFFFF00000000ull | (u64)(u32)~low);
+    return (u32)(x >> 32);
+}
+
 // -------------------------------------------------------------------- decoder --
 // Restates the state handling of RangeEncoder::decode (cpprcoder.h:494-517) and
 // AdaptiveRangeDecoder::decode/normalize (cpprcoder.h:889-917, :926-940).
@@ -451,7 +460,7 @@ RC_HD void rc_dec_advance(RcDec& d, u32 cum, u32 freq, u32 t, Next& next)
 {
     d.low -= cum * t;
     d.range = freq * t;
-    const u32 sh = rc_clz(d.range) & 24u;
+    const u32 sh = rc_norm_shift<3>(d.range);
     d.range <<= sh;
     d.low = rc_funnel_l(d.w_hi, d.low, sh);
     d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);

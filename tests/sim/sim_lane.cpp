@@ -14,6 +14,7 @@ struct VecSink {
     std::vector<u8>* out;
     bool first = true;
     void settle(VecSink& s) const { s = *this; }
+    bool tight(int) const { return false; }
     void push(u32 w)
     {
         if(first) {  // the encoder's placeholder word (rc_lane.cuh, Sink contract)
@@ -180,15 +181,15 @@ long sim_decode(int mode, const u8* stream, size_t stream_len, u32 lead, u8* dst
         for(u32 i = 0; i < want; ++i) {
             const u32 t = rc_div(d.range, total, magic);
             // two-level 16-ary search in the product domain, as the kernel does it
-            u32 k = 0;
+            u32 m1 = 0, m2 = 0;  // minus the boundary counts, from the multiply-add masks
             for(u32 j = 1; j < 16; ++j) {
-                k += (cum[16 * j] * t <= d.low) ? 1u : 0u;
+                m1 += rc_le_mask(cum[16 * j], t, d.low);
             }
-            u32 s = 0;
+            const u32 k = 0u - m1;
             for(u32 j = 1; j < 16; ++j) {
-                s += (cum[16 * k + j] * t <= d.low) ? 1u : 0u;
+                m2 += rc_le_mask(cum[16 * k + j], t, d.low);
             }
-            const u32 sym = 16 * k + s;
+            const u32 sym = 16 * k + (0u - m2);
             dst[i] = (u8)sym;
             rc_dec_advance(d, cum[sym], cum[sym + 1] - cum[sym], t, rd);
         }
