@@ -112,11 +112,11 @@ constexpr u32 smem_enc_adaptive(bool wide)
 }
 constexpr u32 smem_dec_static()
 {
-    return DEC_STATIC_TAB + TILE_BYTES;
+    return DEC_STATIC_TAB + TILE_BYTES + INQ_BYTES;
 }
 constexpr u32 smem_dec_adaptive(bool wide)
 {
-    return 512u * 32u * (wide ? 4u : 2u) + TILE_BYTES;
+    return 512u * 32u * (wide ? 4u : 2u) + TILE_BYTES + INQ_BYTES;
 }
 
 int set_smem_limits(b2rc_ctx* ctx)

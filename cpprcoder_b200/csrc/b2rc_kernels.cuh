@@ -609,10 +609,17 @@ struct DecArgs {
     int* err;
 };
 
-// Each lane reads its own payload at its own pace, one aligned word at a time, straight
-// from global memory (read-only path; a 32-byte sector serves 8 consecutive words out of
-// L1).  Two words are always in flight ahead of the one being consumed, so the load
-// latency stays off the decode chain.
+// Each lane reads its own payload at its own pace, one aligned word at a time.  Words
+// travel global -> shared by 4-byte cp.async into an 8-deep queue per lane ([slot][lane],
+// bank == lane) and shared -> register one word ahead of use.  No register ever waits on
+// a global load: in lock step the scoreboard is per register, not per lane, so a plain
+// prefetching LDG made every step wait for the previous step's load (profiles/).
+constexpr int INQ = 8;
+constexpr int INQ_BYTES = INQ * 128;
+__device__ __forceinline__ void cp_async4(u32 dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __noinline__ u32 load_stream_tail(const u8* p, const u8* end)
 {
     u32 w = 0;
@@ -627,29 +634,38 @@ __device__ __noinline__ u32 load_stream_tail(const u8* p, const u8* end)
 struct WordSrc {
     const u32* base;  // aligned word holding coded byte 0 of this lane's payload
     const u8* end;    // one past the last byte of the whole stream buffer
-    u32 idx;          // next word to request
     u32 nfull;        // words of `base` that lie wholly inside the stream buffer
-    u32 q0, q1;       // requested, not yet consumed (q0 first)
+    u32 q;            // shared address of this lane's queue column
+    u32 rd;           // index of the word held in `ahead`
+    u32 ahead;        // that word (raw little endian), already in a register
 
-    __device__ __forceinline__ u32 fetch(u32 i) const
+    __device__ __forceinline__ void request(u32 i) const
     {
+        const u32 slot = q + (i & (INQ - 1)) * 128u;
         if(i < nfull) {
-            return __ldg(base + i);
+            cp_async4(slot, base + i);
+        } else {
+            sts32v(slot, load_stream_tail(reinterpret_cast<const u8*>(base + i), end));
         }
-        return load_stream_tail(reinterpret_cast<const u8*>(base + i), end);
+        cp_async_commit();
     }
     __device__ __forceinline__ void prime()
     {
-        q0 = fetch(0);
-        q1 = fetch(1);
-        idx = 2;
+#pragma unroll
+        for(u32 i = 0; i < (u32)INQ; ++i) {
+            request(i);
+        }
+        cp_async_wait<0>();
+        rd = 0;
+        ahead = lds32v(q);
     }
     __device__ __forceinline__ u32 operator()()
     {
-        const u32 w = rc_bswap(q0);
-        q0 = q1;
-        q1 = fetch(idx);
-        ++idx;
+        const u32 w = rc_bswap(ahead);
+        request(rd + INQ);  // reuses the slot of the word just handed out
+        ++rd;
+        cp_async_wait<INQ - 1>();  // word rd was requested INQ - 1 groups before the newest
+        ahead = lds32v(q + (rd & (INQ - 1)) * 128u);
         return w;
     }
 };
@@ -684,7 +700,7 @@ __device__ __forceinline__ void store_tile(const u8* tile, u8* dst, u64 n, u64 b
     }
 }
 
-__device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u64 b, bool has, u32 n_b, WordSrc& src,
+__device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u64 b, bool has, u32 n_b, u32 queue, WordSrc& src,
                                           const u8*& pay, bool& ok)
 {
     pay = a.payload;
@@ -714,6 +730,7 @@ __device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u64 b, bool
     if(!ok) {
         src.end = wbase;  // everything reads as zero
     }
+    src.q = queue;
     src.prime();
 }
 
@@ -725,6 +742,51 @@ __device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u64 b, bool
 // The table is the plain 257-entry u32 cum array: trailing symbols that never occur
 // have cum == total, which can be 65536 and does not fit a packed 16-bit field.
 constexpr u32 DEC_STATIC_TAB = 257u * 32u * 4u;  // 32896, a multiple of 16
+
+struct CumTab {
+    u32 base;  // shared address of cum[0] for this lane
+    __device__ __forceinline__ u32 at(u32 sym) const { return lds32(base + sym * 128u); }
+};
+
+template <bool POW2, bool RAGGED>
+__device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const CumTab& tab, const u32 (&k1)[8], RcDec& d,
+                                                 WordSrc& src, u8* otile, u32 otile_a, u64 b0, u32 n_b, u32 n_max,
+                                                 u32 total, u32 magic, u32 shift, u32 lane)
+{
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+    u32 t = POW2 ? (d.range >> shift) : 0u;
+#pragma unroll 1
+    for(u32 tix = 0; tix < ntiles; ++tix) {
+#pragma unroll 1
+        for(int wi = 0; wi < TILE / 4; ++wi) {
+            u32 word = 0;
+#pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                if(!RAGGED || tix * TILE + wi * 4 + k < n_b) {
+                    if(!POW2) {
+                        t = rc_div(d.range, total, magic);
+                    }
+                    u32 sym, cum, freq;
+                    rc_static_find(tab, k1, t, d.low, sym, cum, freq);
+                    if(POW2) {
+                        rc_dec_advance_pow2(d, t, shift, cum, freq, src);
+                    } else {
+                        rc_dec_advance(d, cum, freq, t, src);
+                    }
+                    word |= sym << (8 * k);
+                }
+            }
+            sts32v(otile_a + lane * ROW + wi * 4, word);
+        }
+        __syncwarp();
+        store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
+        __syncwarp();
+    }
+    if(POW2) {
+        d.range = t;  // only its being non-zero is looked at afterwards
+    }
+}
+
 __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
@@ -732,6 +794,7 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     u32* table = reinterpret_cast<u32*>(smem);
     u8* otile = smem + DEC_STATIC_TAB;
     const u32 otile_a = sbase + DEC_STATIC_TAB;
+    const u32 queue_a = otile_a + TILE_BYTES;
 
     const u32 lane = lane_id();
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -745,13 +808,12 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     WordSrc src;
     const u8* pay;
     bool ok;
-    dec_setup(a, RC_STATIC_HDR, b, has, n_b, src, pay, ok);
+    dec_setup(a, RC_STATIC_HDR, b, has, n_b, queue_a + lane * 4u, src, pay, ok);
 
     // read16 + calcCumulatives (cpprcoder.h:585-602, :573-583); payloads are unaligned
     u32* mine = table + lane;
-    const u32 mine_a = sbase + lane * 4u;
     u32 total = 0;
-    u32 key[16];
+    u32 k1[8];
     {
         u32 run = 0;
 #pragma unroll 1
@@ -770,8 +832,8 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
             atomicOr(a.err, ERR_CORRUPT);
         }
 #pragma unroll
-        for(int j = 0; j < 16; ++j) {
-            key[j] = mine[(16u * j) * 32u];
+        for(int j = 0; j < 8; ++j) {
+            k1[j] = mine[(32u * j) * 32u];
         }
     }
     if(!ok) {
@@ -779,50 +841,22 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
         total = 1;
     }
     __syncwarp();
+    const CumTab tab{sbase + lane * 4u};
     const u32 magic = rc_magic(total);
+    const bool is_pow2 = (total & (total - 1u)) == 0;
+    const u32 shift = is_pow2 ? 31u - rc_clz(total) : 0u;
     RcDec d;
     rc_dec_init(d, RC_STATIC_RANGE0, (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u), src);
 
     const u32 n_max = __reduce_max_sync(FULL, n_b);
-    const u32 ntiles = (n_max + TILE - 1) / TILE;
-#pragma unroll 1
-    for(u32 tix = 0; tix < ntiles; ++tix) {
-#pragma unroll 1
-        for(int wi = 0; wi < TILE / 4; ++wi) {
-            u32 word = 0;
-#pragma unroll
-            for(int k = 0; k < 4; ++k) {
-                if(tix * TILE + wi * 4 + k < n_b) {
-                    const u32 t = rc_div(d.range, total, magic);
-                    u32 m1 = 0;  // minus the number of chunk boundaries at or below low
-#pragma unroll
-                    for(int j = 1; j < 16; ++j) {
-                        m1 += rc_le_mask(key[j], t, d.low);
-                    }
-                    const u32 chunk = mine_a - m1 * (16u * 128u);
-                    u32 e[16];
-#pragma unroll
-                    for(int j = 1; j < 16; ++j) {
-                        e[j] = lds32(chunk + j * 128u);
-                    }
-                    u32 m2 = 0;
-#pragma unroll
-                    for(int j = 1; j < 16; ++j) {
-                        m2 += rc_le_mask(e[j], t, d.low);
-                    }
-                    const u32 at = chunk - m2 * 128u;
-                    const u32 sym = (at - mine_a) >> 7;
-                    const u32 cum = lds32(at);
-                    const u32 freq = lds32(at + 128u) - cum;
-                    rc_dec_advance(d, cum, freq, t, src);
-                    word |= sym << (8 * k);
-                }
-            }
-            sts32v(otile_a + lane * ROW + wi * 4, word);
-        }
-        __syncwarp();
-        store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
-        __syncwarp();
+    const bool all_pow2 = __all_sync(FULL, is_pow2);
+    const bool ragged = __any_sync(FULL, n_b != n_max);
+    if(all_pow2 && !ragged) {
+        dec_static_tiles<true, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+    } else if(!ragged) {
+        dec_static_tiles<false, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+    } else {
+        dec_static_tiles<false, true>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
     }
     if(ok && d.range == 0) {
         atomicOr(a.err, ERR_CORRUPT);
@@ -851,7 +885,7 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
     WordSrc src;
     const u8* pay;
     bool ok;
-    dec_setup(a, RC_ADAPT_HDR, b, has, n_b, src, pay, ok);
+    dec_setup(a, RC_ADAPT_HDR, b, has, n_b, otile_a + TILE_BYTES + lane * 4u, src, pay, ok);
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
         for(u32 i = lane; i < TAB_BYTES / 16u; i += 32u) {

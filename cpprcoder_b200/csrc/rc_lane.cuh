@@ -401,13 +401,54 @@ RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, 
     put((u8)low);
 }
 
-// All ones when key * t <= low, else zero -- from the high word of one 64-bit multiply-add
-// (key*t - low - 1 is negative exactly then; |.| < 2^32 because key*t <= total*t <= range).
-// Summing these masks counts the boundaries at or below `low` without a compare per key.
-RC_HD u32 rc_le_mask(u32 key, u32 t, u32 low)
+// Static symbol search: smallest s with cum[s+1] * t > low, i.e. RangeEncoder::find
+// (cpprcoder.h:521-535) applied to low / t, done in the product domain so the decoder's
+// second divide (cpprcoder.h:502) disappears: cum*t <= low  <=>  cum <= low / t, and
+// cum*t never overflows because cum <= total and total * t <= range.
+// Three levels, 8 x 8 x 4: seven boundaries cum[32j] held in registers, seven cum[32a+4j]
+// and then five neighbours cum[4g .. 4g+4] from the table -- 17 compares instead of the
+// reference's 8 dependent steps, two table round trips, and the last level hands back
+// cum and freq of the symbol without another lookup.  (IMAD.HI is avoided on purpose:
+// it is a slow, scoreboarded instruction on sm_100a.)
+template <class Tab>
+RC_HD void rc_static_find(const Tab& tab, const u32 (&k1)[8], u32 t, u32 low, u32& sym, u32& cum, u32& freq)
 {
-    const u64 x = (u64)key * t + (0xFFFFFFFF00000000ull | (u64)(u32)~low);
-    return (u32)(x >> 32);
+    u32 a = 0, b = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int j = 1; j < 8; j += 2) {
+        a += (k1[j] * t <= low) ? 1u : 0u;
+        if(j + 1 < 8) {
+            b += (k1[j + 1] * t <= low) ? 1u : 0u;
+        }
+    }
+    const u32 s1 = (a + b) * 32u;
+    u32 e2[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int j = 1; j < 8; ++j) {
+        e2[j] = tab.at(s1 + 4u * j);
+    }
+    a = 0;
+    b = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int j = 1; j < 8; j += 2) {
+        a += (e2[j] * t <= low) ? 1u : 0u;
+        if(j + 1 < 8) {
+            b += (e2[j + 1] * t <= low) ? 1u : 0u;
+        }
+    }
+    const u32 s2 = s1 + (a + b) * 4u;
+    const u32 f0 = tab.at(s2), f1 = tab.at(s2 + 1), f2 = tab.at(s2 + 2), f3 = tab.at(s2 + 3), f4 = tab.at(s2 + 4);
+    const bool p1 = f1 * t <= low, p2 = f2 * t <= low, p3 = f3 * t <= low;  // monotone: p1 >= p2 >= p3
+    sym = s2 + (p1 ? 1u : 0u) + (p2 ? 1u : 0u) + (p3 ? 1u : 0u);
+    cum = p3 ? f3 : (p2 ? f2 : (p1 ? f1 : f0));
+    const u32 nxt = p3 ? f4 : (p2 ? f3 : (p1 ? f2 : f1));
+    freq = nxt - cum;
 }
 
 // -------------------------------------------------------------------- decoder --
@@ -467,6 +508,34 @@ RC_HD void rc_dec_advance(RcDec& d, u32 cum, u32 freq, u32 t, Next& next)
     d.w_lo <<= sh;
     d.wbits -= (s32)sh;
     if(d.wbits < 32) {  // 8, 16 or 24 valid bits left in w_hi; w_lo is empty
+        const u32 w = next();
+        d.w_hi |= w >> (u32)d.wbits;
+        d.w_lo = w << (32u - (u32)d.wbits);
+        d.wbits += 32;
+    }
+}
+
+// Same as rc_dec_advance for a power-of-two total: the chain is carried by
+// t = range >> shift (see rc_enc_step_pow2); d.range is not maintained.
+template <class Next>
+RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, Next& next)
+{
+    d.low -= cum * t;
+    const u32 r = freq * t;
+    const bool p8 = r < 0x01000000u, p16 = r < 0x00010000u, p24 = r < 0x00000100u;
+    const u32 t0 = r >> shift, t8 = (r << 8) >> shift, t16 = (r << 16) >> shift, t24 = (r << 24) >> shift;
+    u32 tn = p8 ? t8 : t0;
+    tn = p16 ? t16 : tn;
+    tn = p24 ? t24 : tn;
+    u32 sh = p8 ? 8u : 0u;
+    sh = p16 ? 16u : sh;
+    sh = p24 ? 24u : sh;
+    t = tn;
+    d.low = rc_funnel_l(d.w_hi, d.low, sh);
+    d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);
+    d.w_lo <<= sh;
+    d.wbits -= (s32)sh;
+    if(d.wbits < 32) {
         const u32 w = next();
         d.w_hi |= w >> (u32)d.wbits;
         d.w_lo = w << (32u - (u32)d.wbits);

@@ -177,19 +177,23 @@ long sim_decode(int mode, const u8* stream, size_t stream_len, u32 lead, u8* dst
             return -1;
         }
         const u32 magic = rc_magic(total);
+        struct CumTab {
+            const u32* c;
+            u32 at(u32 i) const { return c[i]; }
+        } ctab{cum};
+        u32 k1[8];
+        for(int j = 0; j < 8; ++j) {
+            k1[j] = cum[32 * j];
+        }
         rc_dec_init(d, RC_STATIC_RANGE0, (u32)(coded & 3), rd);
         for(u32 i = 0; i < want; ++i) {
             const u32 t = rc_div(d.range, total, magic);
             // two-level 16-ary search in the product domain, as the kernel does it
-            u32 m1 = 0, m2 = 0;  // minus the boundary counts, from the multiply-add masks
-            for(u32 j = 1; j < 16; ++j) {
-                m1 += rc_le_mask(cum[16 * j], t, d.low);
+            u32 sym, c0, fr;
+            rc_static_find(ctab, k1, t, d.low, sym, c0, fr);
+            if(c0 != cum[sym] || fr != cum[sym + 1] - cum[sym]) {
+                return -2;
             }
-            const u32 k = 0u - m1;
-            for(u32 j = 1; j < 16; ++j) {
-                m2 += rc_le_mask(cum[16 * k + j], t, d.low);
-            }
-            const u32 sym = 16 * k + (0u - m2);
             dst[i] = (u8)sym;
             rc_dec_advance(d, cum[sym], cum[sym + 1] - cum[sym], t, rd);
         }
