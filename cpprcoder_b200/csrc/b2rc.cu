@@ -14,6 +14,10 @@
 
 using namespace b2rc;
 
+#define B2RC_PIPE_STREAMS 16
+#define B2RC_PIPE_CHUNKS 16
+#define B2RC_PIPE_MIN_CHUNK (64ull << 20)  // bytes of input per chunk, at least
+
 struct b2rc_ctx {
     int device;
     cudaStream_t stream;
@@ -30,6 +34,12 @@ struct b2rc_ctx {
     size_t stage_out_cap;
     int* d_err;
     u64* d_total;
+    // chunked host pipeline: a few streams, per-chunk "scan done" / "chunk done" events,
+    // a device array of running payload ends (one per chunk) mirrored in pinned host memory
+    cudaStream_t pipe[B2RC_PIPE_STREAMS];
+    cudaEvent_t scan_done[B2RC_PIPE_CHUNKS], chunk_done[B2RC_PIPE_CHUNKS], index_ready;
+    u64* d_ends;  // B2RC_PIPE_CHUNKS + 1
+    u64* h_ends;  // pinned
     struct Result {
         int err;
         int pad;
@@ -268,6 +278,23 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
             rc = B2RC_E_CUDA;
             break;
         }
+        for(int k = 0; k < B2RC_PIPE_STREAMS && rc == B2RC_OK; ++k) {
+            if(!cuda_ok(ctx, cudaStreamCreateWithFlags(&ctx->pipe[k], cudaStreamNonBlocking), "cudaStreamCreate")) {
+                rc = B2RC_E_CUDA;
+            }
+        }
+        for(int k = 0; k < B2RC_PIPE_CHUNKS && rc == B2RC_OK; ++k) {
+            if(!cuda_ok(ctx, cudaEventCreateWithFlags(&ctx->scan_done[k], cudaEventDisableTiming), "cudaEventCreate") ||
+               !cuda_ok(ctx, cudaEventCreateWithFlags(&ctx->chunk_done[k], cudaEventDisableTiming), "cudaEventCreate")) {
+                rc = B2RC_E_CUDA;
+            }
+        }
+        if(rc == B2RC_OK &&
+           (!cuda_ok(ctx, cudaEventCreateWithFlags(&ctx->index_ready, cudaEventDisableTiming), "cudaEventCreate") ||
+            !cuda_ok(ctx, cudaMalloc((void**)&ctx->d_ends, 8 * (B2RC_PIPE_CHUNKS + 1)), "cudaMalloc") ||
+            !cuda_ok(ctx, cudaMallocHost((void**)&ctx->h_ends, 8 * (B2RC_PIPE_CHUNKS + 1)), "cudaMallocHost"))) {
+            rc = B2RC_E_CUDA;
+        }
         for(int k = 0; k < B2RC_K_COUNT && rc == B2RC_OK; ++k) {
             for(int e = 0; e < 2; ++e) {
                 if(!cuda_ok(ctx, cudaEventCreate(&ctx->ev[k][e]), "cudaEventCreate")) {
@@ -306,6 +333,27 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     cudaFree(ctx->d_total);
     if(ctx->h_res) {
         cudaFreeHost(ctx->h_res);
+    }
+    for(int k = 0; k < B2RC_PIPE_STREAMS; ++k) {
+        if(ctx->pipe[k]) {
+            cudaStreamSynchronize(ctx->pipe[k]);
+            cudaStreamDestroy(ctx->pipe[k]);
+        }
+    }
+    for(int k = 0; k < B2RC_PIPE_CHUNKS; ++k) {
+        if(ctx->scan_done[k]) {
+            cudaEventDestroy(ctx->scan_done[k]);
+        }
+        if(ctx->chunk_done[k]) {
+            cudaEventDestroy(ctx->chunk_done[k]);
+        }
+    }
+    if(ctx->index_ready) {
+        cudaEventDestroy(ctx->index_ready);
+    }
+    cudaFree(ctx->d_ends);
+    if(ctx->h_ends) {
+        cudaFreeHost(ctx->h_ends);
     }
     for(int k = 0; k < B2RC_K_COUNT; ++k) {
         for(int e = 0; e < 2; ++e) {
@@ -460,10 +508,10 @@ int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
 }
 
 static int scan_launch(b2rc_ctx* ctx, const u32* d_sizes, u64 nb, u64* d_offsets, u64* d_total, u8* d_header, u32 mode,
-                       u32 block, u64 n, cudaStream_t st)
+                       u32 block, u64 n, cudaStream_t st, const u64* d_base = nullptr)
 {
     KernelTimer kt(ctx, B2RC_K_SCAN, st);
-    k_scan<<<1, SCAN_THREADS, 0, st>>>(d_sizes, nb, d_offsets, d_total, d_header, mode, block, n);
+    k_scan<<<1, SCAN_THREADS, 0, st>>>(d_sizes, nb, d_offsets, d_total, d_header, mode, block, n, d_base);
     return launch_check(ctx, "k_scan");
 }
 
@@ -640,6 +688,42 @@ int b2rc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t*
 }
 
 // -------------------------------------------------------- container, host --
+// The host-pointer calls pipeline: the input is cut into chunks of whole blocks; each
+// chunk's H2D copy, kernels and D2H copy go to a stream of its own, so chunk c+1 is on
+// the wire while chunk c is being coded and chunk c-1 is on its way back.  The coder
+// kernels are latency bound (a launch takes as long for 64 MiB as for 1 GiB) and leave
+// most of the GPU idle, so the kernels of all chunks overlap; what must not happen is two
+// chunks queueing behind each other on one stream.  With pageable host memory the copies serialise inside the
+// driver; give pinned buffers for full overlap (bench.py does).
+namespace
+{
+struct Chunks {
+    u64 nb, per, count;
+    u64 lo(u64 c) const { return c * per < nb ? c * per : nb; }
+    u64 hi(u64 c) const { return (c + 1) * per < nb ? (c + 1) * per : nb; }
+};
+Chunks plan_chunks(u64 n, u32 block)
+{
+    Chunks ch;
+    ch.nb = b2rc_nblocks(n, block);
+    u64 count = n / B2RC_PIPE_MIN_CHUNK;
+    if(count > B2RC_PIPE_CHUNKS) {
+        count = B2RC_PIPE_CHUNKS;
+    }
+    if(count < 1) {
+        count = 1;
+    }
+    u64 per = (ch.nb + count - 1) / count;
+    per = (per + 31) & ~31ull;  // whole warps of blocks
+    if(per == 0) {
+        per = 32;
+    }
+    ch.per = per;
+    ch.count = ch.nb ? (ch.nb + per - 1) / per : 0;
+    return ch;
+}
+}  // namespace
+
 int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src, uint64_t n, uint8_t* dst,
                 uint64_t dst_cap, uint64_t* out_n)
 {
@@ -648,28 +732,99 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     }
     DeviceGuard g(ctx->device);
     const u64 bound = b2rc_bound(mode, n, block_size);
-    int rc;
-    if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
-       (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(bound + 16))) != B2RC_OK) {
-        return rc;
-    }
-    if(n) {
-        CK(cudaMemcpyAsync(ctx->stage_in, src, n, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    u64 made = 0;
-    rc = b2rc_encode_device(ctx, mode, block_size, ctx->stage_in, n, ctx->stage_out, bound, &made, ctx->stream);
+    const Chunks ch = plan_chunks(n, block_size);
+    const u64 nb = ch.nb;
+    const u64 idx = index_bytes(nb);
     if(out_n) {
-        *out_n = made;
+        *out_n = bound;
     }
-    if(rc != B2RC_OK) {
-        return rc;
-    }
-    if(made > dst_cap) {
+    if(dst_cap < idx) {
         return B2RC_E_DST_SMALL;
     }
-    CK(cudaMemcpyAsync(dst, ctx->stage_out, made, cudaMemcpyDeviceToHost, ctx->stream));
+    const u64 stride = b2rc_slot_bytes(block_size);
+    const bool need_hist = mode == B2RC_MODE_STATIC && block_size <= 65536u;
+    int rc;
+    if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
+       (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(bound + 16))) != B2RC_OK ||
+       (rc = grow(ctx, ctx->slots, ctx->slots_cap, (size_t)(nb * stride))) != B2RC_OK ||
+       (rc = grow(ctx, ctx->sizes, ctx->sizes_cap, (size_t)(nb * 4 + 16))) != B2RC_OK ||
+       (need_hist && (rc = grow(ctx, ctx->freq16, ctx->freq_cap, (size_t)(nb * 512 + 16))) != B2RC_OK)) {
+        return rc;
+    }
+    u8* d_payload = ctx->stage_out + idx;
+    u64* d_offsets = reinterpret_cast<u64*>(ctx->stage_out + B2RC_HEADER_BYTES);
+    cudaStream_t s0 = ctx->pipe[0];
+    CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), s0));
+    CK(cudaMemsetAsync(ctx->d_ends, 0, 8, s0));
+    if(nb == 0) {
+        CK(cudaMemsetAsync(d_offsets, 0, 8, s0));
+    }
+    CK(cudaEventRecord(ctx->index_ready, s0));
+    // enqueue every chunk
+    for(u64 c = 0; c < ch.count; ++c) {
+        cudaStream_t st = ctx->pipe[c % B2RC_PIPE_STREAMS];
+        const u64 b0 = ch.lo(c), b1 = ch.hi(c);
+        const u64 byte0 = b0 * block_size;
+        const u64 bytes = (b1 * (u64)block_size < n ? b1 * (u64)block_size : n) - byte0;
+        if(c == 0 || c < B2RC_PIPE_STREAMS) {
+            CK(cudaStreamWaitEvent(st, ctx->index_ready, 0));
+        }
+        CK(cudaMemcpyAsync(ctx->stage_in + byte0, src + byte0, bytes, cudaMemcpyHostToDevice, st));
+        u16* freq = need_hist ? ctx->freq16 + b0 * 256 : nullptr;
+        if(need_hist && (rc = b2rc_k_histogram(ctx, ctx->stage_in + byte0, bytes, block_size, freq, st)) != B2RC_OK) {
+            return rc;
+        }
+        if((rc = b2rc_k_encode_blocks(ctx, mode, block_size, ctx->stage_in + byte0, bytes, freq,
+                                      ctx->slots + b0 * stride, stride, ctx->sizes + b0, ctx->d_err, st)) != B2RC_OK) {
+            return rc;
+        }
+        if(c > 0) {
+            CK(cudaStreamWaitEvent(st, ctx->scan_done[c - 1], 0));
+        }
+        if((rc = scan_launch(ctx, ctx->sizes + b0, b1 - b0, d_offsets + b0, ctx->d_ends + c + 1, nullptr, 0, 0, 0, st,
+                             ctx->d_ends + c)) != B2RC_OK) {
+            return rc;
+        }
+        CK(cudaEventRecord(ctx->scan_done[c], st));
+        if((rc = b2rc_k_compact(ctx, ctx->slots + b0 * stride, stride, ctx->sizes + b0, d_offsets + b0, b1 - b0,
+                                d_payload, bound - idx, ctx->d_err, st)) != B2RC_OK) {
+            return rc;
+        }
+        CK(cudaMemcpyAsync(ctx->h_ends + c + 1, ctx->d_ends + c + 1, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->chunk_done[c], st));
+    }
+    // drain: as each chunk's size becomes known, send its payload home on the chunk's own stream
+    ctx->h_ends[0] = 0;
+    int result = B2RC_OK;
+    for(u64 c = 0; c < ch.count; ++c) {
+        CK(cudaEventSynchronize(ctx->chunk_done[c]));
+        const u64 lo = ctx->h_ends[c], hi = ctx->h_ends[c + 1];
+        if(idx + hi > dst_cap) {
+            result = B2RC_E_DST_SMALL;
+            continue;
+        }
+        if(result == B2RC_OK && hi > lo) {
+            // on the context's own stream: the chunk's stream still has later chunks queued
+            CK(cudaMemcpyAsync(dst + idx + lo, d_payload + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    const u64 total = ch.count ? ctx->h_ends[ch.count] : 0;
+    if(out_n) {
+        *out_n = idx + total;
+    }
+    // header from the host, index from the device
+    u32 h[8] = {0x43523242u, 1u | ((u32)mode << 16), block_size, 0u, (u32)n, (u32)(n >> 32), (u32)nb, (u32)(nb >> 32)};
+    memcpy(dst, h, sizeof h);
+    CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, s0));
+    if(result == B2RC_OK) {
+        CK(cudaMemcpyAsync(dst + B2RC_HEADER_BYTES, d_offsets, 8 * (nb + 1), cudaMemcpyDeviceToHost, s0));
+    }
+    for(int k = 0; k < B2RC_PIPE_STREAMS; ++k) {
+        CK(cudaStreamSynchronize(ctx->pipe[k]));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
-    return B2RC_OK;
+    const int kerr = map_kernel_err(ctx->h_res->err);
+    return kerr != B2RC_OK ? kerr : result;
 }
 
 int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n)
@@ -692,30 +847,55 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     }
     // the index is in host memory here: check it before anything reaches the device
     const u64 idx = index_bytes(nb);
+    const u64 payload_len = n - idx;
     u64 prev = 0;
     for(u64 b = 0; b <= nb; ++b) {
         u64 o;
         memcpy(&o, src + B2RC_HEADER_BYTES + 8 * b, 8);
-        if(o < prev || o > n - idx || (b == 0 && o != 0)) {
+        if(o < prev || o > payload_len || (b == 0 && o != 0)) {
             return B2RC_E_CORRUPT;
         }
         prev = o;
+    }
+    if(nb == 0) {
+        return B2RC_OK;
     }
     DeviceGuard g(ctx->device);
     if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
        (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(total + 16))) != B2RC_OK) {
         return rc;
     }
-    CK(cudaMemcpyAsync(ctx->stage_in, src, n, cudaMemcpyHostToDevice, ctx->stream));
-    u64 made = 0;
-    rc = b2rc_decode_device(ctx, ctx->stage_in, n, ctx->stage_out, total, &made, ctx->stream);
-    if(rc != B2RC_OK) {
-        return rc;
+    const Chunks ch = plan_chunks(total, block);
+    cudaStream_t s0 = ctx->pipe[0];
+    const u64* d_offsets = reinterpret_cast<const u64*>(ctx->stage_in + B2RC_HEADER_BYTES);
+    CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), s0));
+    CK(cudaMemcpyAsync(ctx->stage_in, src, idx, cudaMemcpyHostToDevice, s0));  // header + index
+    CK(cudaEventRecord(ctx->index_ready, s0));
+    for(u64 c = 0; c < ch.count; ++c) {
+        cudaStream_t st = ctx->pipe[c % B2RC_PIPE_STREAMS];
+        const u64 b0 = ch.lo(c), b1 = ch.hi(c);
+        u64 p0, p1;
+        memcpy(&p0, src + B2RC_HEADER_BYTES + 8 * b0, 8);
+        memcpy(&p1, src + B2RC_HEADER_BYTES + 8 * b1, 8);
+        const u64 byte0 = b0 * (u64)block;
+        const u64 bytes = (b1 * (u64)block < total ? b1 * (u64)block : total) - byte0;
+        if(c < B2RC_PIPE_STREAMS) {
+            CK(cudaStreamWaitEvent(st, ctx->index_ready, 0));
+        }
+        if(p1 > p0) {
+            CK(cudaMemcpyAsync(ctx->stage_in + idx + p0, src + idx + p0, p1 - p0, cudaMemcpyHostToDevice, st));
+        }
+        if((rc = b2rc_k_decode_blocks(ctx, mode, block, ctx->stage_in + idx, payload_len, d_offsets + b0, b1 - b0,
+                                      ctx->stage_out + byte0, bytes, ctx->d_err, st)) != B2RC_OK) {
+            return rc;
+        }
+        CK(cudaMemcpyAsync(dst + byte0, ctx->stage_out + byte0, bytes, cudaMemcpyDeviceToHost, st));
     }
-    if(total) {
-        CK(cudaMemcpyAsync(dst, ctx->stage_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+    for(int k = 1; k < B2RC_PIPE_STREAMS; ++k) {
+        CK(cudaStreamSynchronize(ctx->pipe[k]));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    return B2RC_OK;
+    CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    return map_kernel_err(ctx->h_res->err);
 }
 }

@@ -990,8 +990,11 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_hist(const u8* src, u64 n, 
 // and, fused into it, the 32-byte container header when `header` is not null.
 constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32* sizes, u64 nblocks, u64* offsets, u64* total_out,
-                                                       u8* header, u32 mode, u32 block, u64 n)
+                                                       u8* header, u32 mode, u32 block, u64 n, const u64* base_in)
 {
+    // base_in: where this range of blocks starts in the payload area (chunked host pipeline:
+    // chunk c continues where chunk c-1 ended; total_out then receives the new end)
+    const u64 base = base_in ? *base_in : 0ull;
     __shared__ u64 part[SCAN_THREADS];
     const u32 t = threadIdx.x;
     const u64 per = (nblocks + SCAN_THREADS - 1) / SCAN_THREADS;
@@ -1017,15 +1020,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32* sizes, u64 nbl
         part[t] += add;
         __syncthreads();
     }
-    u64 run = part[t] - sum;
+    u64 run = base + part[t] - sum;
     for(u64 i = lo; i < hi; ++i) {
         offsets[i] = run;
         run += sizes[i];
     }
     if(t == SCAN_THREADS - 1) {
-        offsets[nblocks] = part[t];
+        offsets[nblocks] = base + part[t];
         if(total_out) {
-            *total_out = part[t];
+            *total_out = base + part[t];
         }
     }
     if(header && t == 0) {
