@@ -620,54 +620,51 @@ __device__ __forceinline__ void cp_async4(u32 dst, const void* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __noinline__ u32 load_stream_tail(const u8* p, const u8* end)
-{
-    u32 w = 0;
-    for(int k = 0; k < 4; ++k) {
-        if(p + k < end) {
-            w |= (u32)p[k] << (8 * k);
-        }
-    }
-    return w;
-}
-
 struct WordSrc {
     const u32* base;  // aligned word holding coded byte 0 of this lane's payload
-    const u8* end;    // one past the last byte of the whole stream buffer
-    u32 nfull;        // words of `base` that lie wholly inside the stream buffer
+    u32 lim;          // readable bytes from `base` to the end of the stream buffer
     u32 q;            // shared address of this lane's queue column
     u32 rd;           // index of the word held in `ahead`
     u32 ahead;        // that word (raw little endian), already in a register
 
-    __device__ __forceinline__ void request(u32 i) const
+    // word i -> queue slot i % INQ, when `on`; bytes past the buffer arrive as zeros
+    __device__ __forceinline__ void request(u32 i, bool on) const
     {
+        const u32 last = lim ? (lim - 1u) >> 2 : 0u;
+        const u32 at = i < last ? i : last;                                 // keep the address inside the buffer
+        const u32 left = (i << 2) < lim ? lim - (i << 2) : 0u;
+        const u32 bytes = left < 4u ? left : 4u;                            // src-size: the rest is zero filled
         const u32 slot = q + (i & (INQ - 1)) * 128u;
-        if(i < nfull) {
-            cp_async4(slot, base + i);
-        } else {
-            sts32v(slot, load_stream_tail(reinterpret_cast<const u8*>(base + i), end));
-        }
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4, %2; }" ::"r"(slot),
+                     "l"(base + at), "r"(bytes), "r"((u32)on)
+                     : "memory");
         cp_async_commit();
     }
     __device__ __forceinline__ void prime()
     {
 #pragma unroll
         for(u32 i = 0; i < (u32)INQ; ++i) {
-            request(i);
+            request(i, true);
         }
         cp_async_wait<0>();
         rd = 0;
         ahead = lds32v(q);
     }
-    __device__ __forceinline__ u32 operator()()
+    // Next stream word, big endian, when `need`; otherwise nothing moves.  Every call commits
+    // one (possibly empty) copy group, so "all but the newest INQ-1 groups" always covers the
+    // word that is read ahead here: it was requested INQ-1 or more calls ago.
+    __device__ __forceinline__ u32 take(bool need)
     {
         const u32 w = rc_bswap(ahead);
-        request(rd + INQ);  // reuses the slot of the word just handed out
-        ++rd;
-        cp_async_wait<INQ - 1>();  // word rd was requested INQ - 1 groups before the newest
-        ahead = lds32v(q + (rd & (INQ - 1)) * 128u);
+        request(rd + INQ, need);  // reuses the slot of the word just handed out
+        rd += need ? 1u : 0u;
+        cp_async_wait<INQ - 1>();
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1]; }"
+                     : "+r"(ahead)
+                     : "r"(q + (rd & (INQ - 1)) * 128u), "r"((u32)need));
         return w;
     }
+    __device__ __forceinline__ u32 operator()() { return take(true); }
 };
 
 // Output tile -> global, 8 rows of 64 bytes per instruction.
@@ -723,13 +720,10 @@ __device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u64 b, bool
     const u8* coded = pay + hdr;
     const u8* wbase = (const u8*)((uintptr_t)coded & ~(uintptr_t)3);
     src.base = reinterpret_cast<const u32*>(wbase);
-    src.end = a.payload + a.payload_len;
     // reading past this block's own payload is harmless (those bits are never decisive for a
-    // valid stream); reading past the buffer is not, so only whole in-buffer words load directly
-    src.nfull = ok ? (u32)((u64)(src.end - wbase) / 4u < 0xFFFFFFFFull ? (u64)(src.end - wbase) / 4u : 0xFFFFFFFFull) : 0u;
-    if(!ok) {
-        src.end = wbase;  // everything reads as zero
-    }
+    // valid stream); reading past the buffer is not: `lim` bounds every copy
+    const u64 room = (u64)((a.payload + a.payload_len) - wbase);
+    src.lim = ok ? (u32)(room < 0xFFFFFFF0ull ? room : 0xFFFFFFF0ull) : 0u;  // !ok: everything reads as zero
     src.q = queue;
     src.prime();
 }
@@ -744,8 +738,9 @@ __device__ __forceinline__ void dec_setup(const DecArgs& a, u32 hdr, u64 b, bool
 constexpr u32 DEC_STATIC_TAB = 257u * 32u * 4u;  // 32896, a multiple of 16
 
 struct CumTab {
-    u32 base;  // shared address of cum[0] for this lane
-    __device__ __forceinline__ u32 at(u32 sym) const { return lds32(base + sym * 128u); }
+    enum : u32 { UNIT = 128 };  // position = symbol * 128 = byte offset inside the lane's column
+    u32 base;                   // shared address of cum[0] for this lane
+    __device__ __forceinline__ u32 at(u32 pos) const { return lds32(base + pos); }
 };
 
 template <bool POW2, bool RAGGED>

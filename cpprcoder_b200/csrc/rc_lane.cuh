@@ -401,6 +401,18 @@ RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, 
     put((u8)low);
 }
 
+// cnt += (prod > low), without a predicate: prod + ~low carries out exactly when
+// prod >= low + 1; the carry is added in.  `nlow` is ~low.  (add.cc/addc rather than
+// sub.cc/addc: mixing a borrow with a carry-in is not something PTX pins down.)
+RC_HD void rc_count_gt(u32& cnt, u32 prod, u32 nlow)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{ .reg .u32 d; add.cc.u32 d, %1, %2;\n\taddc.u32 %0, %0, 0; }" : "+r"(cnt) : "r"(prod), "r"(nlow));
+#else
+    cnt += ((u64)prod + nlow > 0xFFFFFFFFull) ? 1u : 0u;
+#endif
+}
+
 // Static symbol search: smallest s with cum[s+1] * t > low, i.e. RangeEncoder::find
 // (cpprcoder.h:521-535) applied to low / t, done in the product domain so the decoder's
 // second divide (cpprcoder.h:502) disappears: cum*t <= low  <=>  cum <= low / t, and
@@ -410,26 +422,30 @@ RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, 
 // reference's 8 dependent steps, two table round trips, and the last level hands back
 // cum and freq of the symbol without another lookup.  (IMAD.HI is avoided on purpose:
 // it is a slow, scoreboarded instruction on sm_100a.)
+// Tab::at(p) reads cum at POSITION p = symbol * Tab::UNIT, so that on the device the
+// position is the shared-memory byte offset and no index arithmetic sits on the chain.
 template <class Tab>
 RC_HD void rc_static_find(const Tab& tab, const u32 (&k1)[8], u32 t, u32 low, u32& sym, u32& cum, u32& freq)
 {
-    u32 a = 0, b = 0;
+    constexpr u32 U = Tab::UNIT;
+    const u32 nlow = ~low;
+    u32 a = 0, b = 0;  // boundaries ABOVE low
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for(int j = 1; j < 8; j += 2) {
-        a += (k1[j] * t <= low) ? 1u : 0u;
+        rc_count_gt(a, k1[j] * t, nlow);
         if(j + 1 < 8) {
-            b += (k1[j + 1] * t <= low) ? 1u : 0u;
+            rc_count_gt(b, k1[j + 1] * t, nlow);
         }
     }
-    const u32 s1 = (a + b) * 32u;
+    const u32 p1 = (7u - (a + b)) * (32u * U);
     u32 e2[8];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for(int j = 1; j < 8; ++j) {
-        e2[j] = tab.at(s1 + 4u * j);
+        e2[j] = tab.at(p1 + 4u * U * j);
     }
     a = 0;
     b = 0;
@@ -437,17 +453,18 @@ RC_HD void rc_static_find(const Tab& tab, const u32 (&k1)[8], u32 t, u32 low, u3
 #pragma unroll
 #endif
     for(int j = 1; j < 8; j += 2) {
-        a += (e2[j] * t <= low) ? 1u : 0u;
+        rc_count_gt(a, e2[j] * t, nlow);
         if(j + 1 < 8) {
-            b += (e2[j + 1] * t <= low) ? 1u : 0u;
+            rc_count_gt(b, e2[j + 1] * t, nlow);
         }
     }
-    const u32 s2 = s1 + (a + b) * 4u;
-    const u32 f0 = tab.at(s2), f1 = tab.at(s2 + 1), f2 = tab.at(s2 + 2), f3 = tab.at(s2 + 3), f4 = tab.at(s2 + 4);
-    const bool p1 = f1 * t <= low, p2 = f2 * t <= low, p3 = f3 * t <= low;  // monotone: p1 >= p2 >= p3
-    sym = s2 + (p1 ? 1u : 0u) + (p2 ? 1u : 0u) + (p3 ? 1u : 0u);
-    cum = p3 ? f3 : (p2 ? f2 : (p1 ? f1 : f0));
-    const u32 nxt = p3 ? f4 : (p2 ? f3 : (p1 ? f2 : f1));
+    const u32 p2 = p1 + (7u - (a + b)) * (4u * U);
+    const u32 f0 = tab.at(p2), f1 = tab.at(p2 + U), f2 = tab.at(p2 + 2 * U), f3 = tab.at(p2 + 3 * U),
+              f4 = tab.at(p2 + 4 * U);
+    const bool q1 = f1 * t <= low, q2 = f2 * t <= low, q3 = f3 * t <= low;  // monotone: q1 >= q2 >= q3
+    sym = p2 / U + (q1 ? 1u : 0u) + (q2 ? 1u : 0u) + (q3 ? 1u : 0u);
+    cum = q3 ? f3 : (q2 ? f2 : (q1 ? f1 : f0));
+    const u32 nxt = q3 ? f4 : (q2 ? f3 : (q1 ? f2 : f1));
     freq = nxt - cum;
 }
 
@@ -495,6 +512,21 @@ RC_HD void rc_dec_init(RcDec& d, u32 range0, u32 skip, Next& next)
     d.range = range0;
 }
 
+// Tops the window up when fewer than 32 bits are left (then 8, 16 or 24 valid bits sit in
+// w_hi and w_lo is empty).  Branch free: `next.take(need)` hands out the next stream word
+// and moves on only when `need` is set, so the whole warp runs the same few instructions
+// whether or not a given lane refills on this symbol.
+template <class Next>
+RC_HD void rc_dec_refill(RcDec& d, Next& next)
+{
+    const bool need = d.wbits < 32;
+    const u32 w = next.take(need);
+    const u32 have = (u32)d.wbits & 31u;
+    d.w_hi = need ? (d.w_hi | (w >> have)) : d.w_hi;
+    d.w_lo = need ? (w << (32u - have)) : d.w_lo;
+    d.wbits += need ? 32 : 0;
+}
+
 // After the symbol is known: low -= cum*t, range = freq*t, renormalise, refill.
 template <class Next>
 RC_HD void rc_dec_advance(RcDec& d, u32 cum, u32 freq, u32 t, Next& next)
@@ -507,12 +539,7 @@ RC_HD void rc_dec_advance(RcDec& d, u32 cum, u32 freq, u32 t, Next& next)
     d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);
     d.w_lo <<= sh;
     d.wbits -= (s32)sh;
-    if(d.wbits < 32) {  // 8, 16 or 24 valid bits left in w_hi; w_lo is empty
-        const u32 w = next();
-        d.w_hi |= w >> (u32)d.wbits;
-        d.w_lo = w << (32u - (u32)d.wbits);
-        d.wbits += 32;
-    }
+    rc_dec_refill(d, next);
 }
 
 // Same as rc_dec_advance for a power-of-two total: the chain is carried by
@@ -535,12 +562,7 @@ RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, N
     d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);
     d.w_lo <<= sh;
     d.wbits -= (s32)sh;
-    if(d.wbits < 32) {
-        const u32 w = next();
-        d.w_hi |= w >> (u32)d.wbits;
-        d.w_lo = w << (32u - (u32)d.wbits);
-        d.wbits += 32;
-    }
+    rc_dec_refill(d, next);
 }
 
 // ------------------------------------------------------------- adaptive model --

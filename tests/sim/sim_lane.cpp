@@ -51,8 +51,12 @@ void count64k(const u8* src, u32 n, u32 freq[256])
 struct WordReader {
     const u8* p;
     size_t n, pos;  // pos = byte index of the next aligned word
-    u32 operator()()
+    u32 operator()() { return take(true); }
+    u32 take(bool need)
     {
+        if(!need) {
+            return 0xDEADBEEFu;  // must be ignored by the caller
+        }
         u32 w = 0;
         for(int k = 0; k < 4; ++k) {
             const size_t at = pos + k;
@@ -178,6 +182,7 @@ long sim_decode(int mode, const u8* stream, size_t stream_len, u32 lead, u8* dst
         }
         const u32 magic = rc_magic(total);
         struct CumTab {
+            enum : u32 { UNIT = 1 };
             const u32* c;
             u32 at(u32 i) const { return c[i]; }
         } ctab{cum};
