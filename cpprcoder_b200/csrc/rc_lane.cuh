@@ -580,21 +580,26 @@ RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, N
 template <class Tab>
 RC_HD void rc_model_encode(Tab& tab, u32 b, u32& cum, u32& freq)
 {
-    u32 below = 0;
+    // All nine reads first, then the writes: the nine nodes are distinct, so nothing inside one
+    // symbol depends on a store, and the table latency is paid once instead of once per level.
     const u32 leaf = 256u | b;
+    u32 v[8];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for(s32 l = 7; l >= 0; --l) {
-        const u32 id = leaf >> (l + 1);
-        const u32 v = tab.ld(id);
-        if((b >> l) & 1u) {
-            below += v;
-        } else {
-            tab.st(id, v + 1u);
-        }
+        v[l] = tab.ld(leaf >> (l + 1));
     }
     const u32 f = tab.ld(leaf);
+    u32 below = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(s32 l = 7; l >= 0; --l) {
+        const u32 bit = (b >> l) & 1u;
+        below += bit ? v[l] : 0u;
+        tab.st(leaf >> (l + 1), v[l] + (bit ^ 1u));  // unchanged where the bit is set
+    }
     tab.st(leaf, f + 1u);
     cum = b + below;
     freq = 1u + f;
