@@ -613,24 +613,24 @@ RC_HD void rc_model_encode(Tab& tab, u32 b, u32& cum, u32& freq)
 template <class Tab>
 RC_HD void rc_model_decode(Tab& tab, u32 low, u32 t, u32& sym, u32& cum, u32& freq)
 {
+    // Both children are read while the compare that chooses between them is still in flight,
+    // so one level of the walk costs the compare chain, not a table round trip plus the chain.
     u32 id = 1, base = 0;
+    u32 v = tab.ld(1);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for(s32 l = 7; l >= 0; --l) {
-        const u32 v = tab.ld(id);
-        const u32 left = v + (1u << l);  // counts + the implicit one per symbol
-        if((base + left) * t <= low) {
-            base += left;
-            id = 2 * id + 1;
-        } else {
-            tab.st(id, v + 1u);
-            id = 2 * id;
-        }
+        const u32 vl = tab.ld(2 * id), vr = tab.ld(2 * id + 1);  // level l-1 nodes, or the two leaves
+        const u32 left = v + (1u << l);                          // counts + the implicit one per symbol
+        const bool right = (base + left) * t <= low;
+        tab.st(id, v + (right ? 0u : 1u));
+        base += right ? left : 0u;
+        id = 2 * id + (right ? 1u : 0u);
+        v = right ? vr : vl;
     }
-    const u32 f = tab.ld(id);  // id is now 256 | symbol
-    tab.st(id, f + 1u);
+    tab.st(id, v + 1u);  // id is now 256 | symbol, v its count
     sym = id & 255u;
     cum = base;
-    freq = 1u + f;
+    freq = 1u + v;
 }
