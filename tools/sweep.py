@@ -1,0 +1,60 @@
+"""BASELINE config 5: block-size sweep 4 KiB .. 1 MiB on kennedy.xls-like synthetic data.
+Reports device-resident encode / decode GB/s and the compression ratio per block size and coder;
+every configuration is round-trip checked, and one block per configuration is compared byte for
+byte with the oracle (test infrastructure, used here only as the checker)."""
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import torch
+
+from _oracle import Oracle
+from cpprcoder_b200 import api, container, synth
+
+
+def timed(fn, reps=3):
+    best = 1e9
+    for _ in range(reps):
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else (1 << 30)
+    out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/block_sweep.json"
+    ctx = api.Context(0)
+    oracle = Oracle.get()
+    data = synth.kennedy(n)
+    src = torch.from_numpy(data).cuda()
+    dst = torch.empty(n, dtype=torch.uint8, device="cuda")
+    rows = []
+    for block in [4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288, 1048576]:
+        for mode, name in ((0, "static"), (1, "adaptive")):
+            enc, used = ctx.encode_device(mode, src, block=block)
+            t_enc = timed(lambda: ctx.encode_device(mode, src, enc, block=block))
+            t_dec = timed(lambda: ctx.decode_device(enc, used, dst))
+            ok = bool(torch.equal(dst, src))
+            head = enc[:used].cpu().numpy()
+            info = container.parse(head)
+            b = info.nblocks // 2
+            exact = bytes(info.payload(head, b)) == oracle.encode(mode, data[b * block:(b + 1) * block])
+            rows.append({"block": block, "coder": name, "ratio": used / n, "encode_GBps": n / t_enc / 1e6,
+                         "decode_GBps": n / t_dec / 1e6, "round_trip": ok, "sampled_block_equals_oracle": exact})
+            print(rows[-1], flush=True)
+            del enc
+    Path(out).write_text(json.dumps({"bytes": n, "generator": "synth.kennedy", "rows": rows}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
