@@ -640,6 +640,18 @@ struct WordSrc {
                      : "memory");
         cp_async_commit();
     }
+    // the same without bounds: only for words known to lie wholly inside the buffer
+    __device__ __forceinline__ void request_inside(u32 i, bool on) const
+    {
+        const u32 slot = q + (i & (INQ - 1)) * 128u;
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4; }" ::"r"(slot),
+                     "l"(base + i), "r"((u32)on)
+                     : "memory");
+        cp_async_commit();
+    }
+    // true when every word a tile of TILE symbols can request (3 bytes per symbol at most, plus
+    // the queue's look-ahead) lies inside the buffer
+    __device__ __forceinline__ bool tile_is_inside() const { return (u64)(rd + TILE + 2u * INQ) * 4u <= (u64)lim; }
     __device__ __forceinline__ void prime()
     {
 #pragma unroll
@@ -653,10 +665,15 @@ struct WordSrc {
     // Next stream word, big endian, when `need`; otherwise nothing moves.  Every call commits
     // one (possibly empty) copy group, so "all but the newest INQ-1 groups" always covers the
     // word that is read ahead here: it was requested INQ-1 or more calls ago.
-    __device__ __forceinline__ u32 take(bool need)
+    template <bool INSIDE>
+    __device__ __forceinline__ u32 take_(bool need)
     {
         const u32 w = rc_bswap(ahead);
-        request(rd + INQ, need);  // reuses the slot of the word just handed out
+        if(INSIDE) {
+            request_inside(rd + INQ, need);  // reuses the slot of the word just handed out
+        } else {
+            request(rd + INQ, need);
+        }
         rd += need ? 1u : 0u;
         cp_async_wait<INQ - 1>();
         asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1]; }"
@@ -664,7 +681,13 @@ struct WordSrc {
                      : "r"(q + (rd & (INQ - 1)) * 128u), "r"((u32)need));
         return w;
     }
+    __device__ __forceinline__ u32 take(bool need) { return take_<false>(need); }
     __device__ __forceinline__ u32 operator()() { return take(true); }
+};
+// View of a WordSrc for a stretch of symbols whose words are all inside the buffer.
+struct WordSrcInside {
+    WordSrc& s;
+    __device__ __forceinline__ u32 take(bool need) { return s.take_<true>(need); }
 };
 
 // Output tile -> global, 8 rows of 64 bytes per instruction.
@@ -743,41 +766,58 @@ struct CumTab {
     __device__ __forceinline__ u32 at(u32 pos) const { return lds32(base + pos); }
 };
 
-template <bool POW2, bool RAGGED>
+// One tile (TILE symbols per lane).  MODE: 0 general divide, 2 / 3 power-of-two total with at
+// most 2 / 3 renormalisation rounds per symbol.
+template <int MODE, bool RAGGED, class Src>
+__device__ __forceinline__ void dec_static_tile(const CumTab& tab, const u32 (&k1)[8], RcDec& d, u32& t, Src& src,
+                                                u32 otile_a, u32 tile_off, u32 n_b, u32 total, u32 magic, u32 shift,
+                                                u32 lane)
+{
+#pragma unroll 1
+    for(int wi = 0; wi < TILE / 4; ++wi) {
+        u32 word = 0;
+#pragma unroll
+        for(int k = 0; k < 4; ++k) {
+            if(!RAGGED || tile_off + wi * 4 + k < n_b) {
+                if(MODE == 0) {
+                    t = rc_div(d.range, total, magic);
+                }
+                u32 sym, cum, freq;
+                rc_static_find(tab, k1, t, d.low, sym, cum, freq);
+                if(MODE == 0) {
+                    rc_dec_advance(d, cum, freq, t, src);
+                } else {
+                    rc_dec_advance_pow2<MODE>(d, t, shift, cum, freq, src);
+                }
+                word |= sym << (8 * k);
+            }
+        }
+        sts32v(otile_a + lane * ROW + wi * 4, word);
+    }
+}
+
+template <int MODE, bool RAGGED>
 __device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const CumTab& tab, const u32 (&k1)[8], RcDec& d,
                                                  WordSrc& src, u8* otile, u32 otile_a, u64 b0, u32 n_b, u32 n_max,
                                                  u32 total, u32 magic, u32 shift, u32 lane)
 {
     const u32 ntiles = (n_max + TILE - 1) / TILE;
-    u32 t = POW2 ? (d.range >> shift) : 0u;
+    u32 t = MODE ? (d.range >> shift) : 0u;
 #pragma unroll 1
     for(u32 tix = 0; tix < ntiles; ++tix) {
-#pragma unroll 1
-        for(int wi = 0; wi < TILE / 4; ++wi) {
-            u32 word = 0;
-#pragma unroll
-            for(int k = 0; k < 4; ++k) {
-                if(!RAGGED || tix * TILE + wi * 4 + k < n_b) {
-                    if(!POW2) {
-                        t = rc_div(d.range, total, magic);
-                    }
-                    u32 sym, cum, freq;
-                    rc_static_find(tab, k1, t, d.low, sym, cum, freq);
-                    if(POW2) {
-                        rc_dec_advance_pow2(d, t, shift, cum, freq, src);
-                    } else {
-                        rc_dec_advance(d, cum, freq, t, src);
-                    }
-                    word |= sym << (8 * k);
-                }
-            }
-            sts32v(otile_a + lane * ROW + wi * 4, word);
+        // all but the last tile or two of the last block of the stream read words that lie wholly
+        // inside the buffer: those tiles skip the bounds arithmetic of the copy requests
+        if(__all_sync(FULL, src.tile_is_inside())) {
+            WordSrcInside in{src};
+            dec_static_tile<MODE, RAGGED>(tab, k1, d, t, in, otile_a, tix * TILE, n_b, total, magic, shift, lane);
+        } else {
+            dec_static_tile<MODE, RAGGED>(tab, k1, d, t, src, otile_a, tix * TILE, n_b, total, magic, shift, lane);
         }
         __syncwarp();
         store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
         __syncwarp();
     }
-    if(POW2) {
+    if(MODE) {
         d.range = t;  // only its being non-zero is looked at afterwards
     }
 }
@@ -846,12 +886,14 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     const u32 n_max = __reduce_max_sync(FULL, n_b);
     const bool all_pow2 = __all_sync(FULL, is_pow2);
     const bool ragged = __any_sync(FULL, n_b != n_max);
-    if(all_pow2 && !ragged) {
-        dec_static_tiles<true, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+    if(all_pow2 && !ragged && a.block <= 65536u) {
+        dec_static_tiles<2, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+    } else if(all_pow2 && !ragged) {
+        dec_static_tiles<3, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
     } else if(!ragged) {
-        dec_static_tiles<false, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+        dec_static_tiles<0, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
     } else {
-        dec_static_tiles<false, true>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+        dec_static_tiles<0, true>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
     }
     if(ok && d.range == 0) {
         atomicOr(a.err, ERR_CORRUPT);
@@ -950,7 +992,25 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_hist(const u8* src, u64 n, 
         const u32 len = (u32)((n - lo < block) ? (n - lo) : block);
         const u8* p = src + lo;
         const u32 vec = len & ~15u;
-        for(u32 off = lane * 16u; off < vec; off += 512u) {
+        // four 16-byte loads in flight per lane before the first bin is touched: the kernel was
+        // stalled on load latency (long scoreboard), not on the shared-memory atomics
+        u32 off = lane * 16u;
+        for(; off + 3u * 512u < vec; off += 4u * 512u) {
+            uint4 v[4];
+#pragma unroll
+            for(int q = 0; q < 4; ++q) {
+                v[q] = __ldg(reinterpret_cast<const uint4*>(p + off + q * 512u));
+            }
+#pragma unroll
+            for(int q = 0; q < 4; ++q) {
+                const u32 w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for(int k = 0; k < 16; ++k) {
+                    atomicAdd(&h[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu], 1u);
+                }
+            }
+        }
+        for(; off < vec; off += 512u) {
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + off));
             const u32 w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -1069,7 +1129,20 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const u8* slots, u6
         u32* dw = reinterpret_cast<u32*>(d + head);
         const u32* sw = reinterpret_cast<const u32*>(s);
         const u32 sh = head * 8u;  // source byte offset of dst word j is head + 4j
-        for(u32 j = threadIdx.x; j < nwords; j += COMPACT_THREADS) {
+        u32 j = threadIdx.x;
+        for(; j + 3u * COMPACT_THREADS < nwords; j += 4u * COMPACT_THREADS) {  // four loads in flight per thread
+            u32 a0[4], a1[4];
+#pragma unroll
+            for(int q = 0; q < 4; ++q) {
+                a0[q] = __ldg(sw + j + q * COMPACT_THREADS);
+                a1[q] = sh ? __ldg(sw + j + q * COMPACT_THREADS + 1) : 0u;
+            }
+#pragma unroll
+            for(int q = 0; q < 4; ++q) {
+                dw[j + q * COMPACT_THREADS] = __funnelshift_r(a0[q], a1[q], sh);
+            }
+        }
+        for(; j < nwords; j += COMPACT_THREADS) {
             const u32 a0 = __ldg(sw + j);
             const u32 a1 = sh ? __ldg(sw + j + 1) : 0u;
             dw[j] = __funnelshift_r(a0, a1, sh);

@@ -544,19 +544,23 @@ RC_HD void rc_dec_advance(RcDec& d, u32 cum, u32 freq, u32 t, Next& next)
 
 // Same as rc_dec_advance for a power-of-two total: the chain is carried by
 // t = range >> shift (see rc_enc_step_pow2); d.range is not maintained.
-template <class Next>
+// MAXSH = 2 when range >= 2^8 is guaranteed (total <= 2^16), else 3.
+template <int MAXSH, class Next>
 RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, Next& next)
 {
     d.low -= cum * t;
     const u32 r = freq * t;
-    const bool p8 = r < 0x01000000u, p16 = r < 0x00010000u, p24 = r < 0x00000100u;
-    const u32 t0 = r >> shift, t8 = (r << 8) >> shift, t16 = (r << 16) >> shift, t24 = (r << 24) >> shift;
+    const bool p8 = r < 0x01000000u, p16 = r < 0x00010000u;
+    const u32 t0 = r >> shift, t8 = (r << 8) >> shift, t16 = (r << 16) >> shift;
     u32 tn = p8 ? t8 : t0;
     tn = p16 ? t16 : tn;
-    tn = p24 ? t24 : tn;
     u32 sh = p8 ? 8u : 0u;
     sh = p16 ? 16u : sh;
-    sh = p24 ? 24u : sh;
+    if(MAXSH >= 3) {
+        const bool p24 = r < 0x00000100u;
+        tn = p24 ? ((r << 24) >> shift) : tn;
+        sh = p24 ? 24u : sh;
+    }
     t = tn;
     d.low = rc_funnel_l(d.w_hi, d.low, sh);
     d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);

@@ -191,16 +191,27 @@ long sim_decode(int mode, const u8* stream, size_t stream_len, u32 lead, u8* dst
             k1[j] = cum[32 * j];
         }
         rc_dec_init(d, RC_STATIC_RANGE0, (u32)(coded & 3), rd);
+        // the kernel's three chains: general divide, power of two with 2 or 3 renormalisation rounds
+        const bool pow2 = (total & (total - 1)) == 0;
+        const u32 shT = pow2 ? 31u - rc_clz(total) : 0;
+        u32 t = pow2 ? (d.range >> shT) : 0;
         for(u32 i = 0; i < want; ++i) {
-            const u32 t = rc_div(d.range, total, magic);
-            // two-level 16-ary search in the product domain, as the kernel does it
+            if(!pow2) {
+                t = rc_div(d.range, total, magic);
+            }
             u32 sym, c0, fr;
             rc_static_find(ctab, k1, t, d.low, sym, c0, fr);
             if(c0 != cum[sym] || fr != cum[sym + 1] - cum[sym]) {
                 return -2;
             }
             dst[i] = (u8)sym;
-            rc_dec_advance(d, cum[sym], cum[sym + 1] - cum[sym], t, rd);
+            if(!pow2) {
+                rc_dec_advance(d, c0, fr, t, rd);
+            } else if(total <= 65536u && (i & 1)) {
+                rc_dec_advance_pow2<2>(d, t, shT, c0, fr, rd);
+            } else {
+                rc_dec_advance_pow2<3>(d, t, shT, c0, fr, rd);
+            }
         }
     } else {
         ArrTab tab;
