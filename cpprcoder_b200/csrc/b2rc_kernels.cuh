@@ -901,6 +901,33 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
 }
 
 // ======================================================================= K3a ==
+template <class W, class Src>
+__device__ __forceinline__ void dec_adaptive_tile(LaneTab<W>& tab, RcDec& d, Src& src, u32 otile_a, u32 tile_off,
+                                                  u32 n_b, u32 lane)
+{
+    const u32 d0 = 256u + tile_off;
+    const u32 mg0 = rc_magic(d0 + lane);
+    const u32 mg1 = rc_magic(d0 + 32u + lane);
+#pragma unroll 1
+    for(int wi = 0; wi < TILE / 4; ++wi) {
+        const u32 mg = wi < 8 ? mg0 : mg1;
+        u32 word = 0;
+#pragma unroll
+        for(int k = 0; k < 4; ++k) {
+            const int j = wi * 4 + k;
+            const u32 magic = __shfl_sync(FULL, mg, j & 31);
+            if(tile_off + j < n_b) {
+                const u32 t = rc_div(d.range, d0 + j, magic);
+                u32 sym, cum, freq;
+                rc_model_decode(tab, d.low, t, sym, cum, freq);
+                rc_dec_advance(d, cum, freq, t, src);
+                word |= sym << (8 * k);
+            }
+        }
+        sts32v(otile_a + lane * ROW + wi * 4, word);
+    }
+}
+
 template <class W>
 __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
 {
@@ -941,26 +968,11 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
     const u32 ntiles = (n_max + TILE - 1) / TILE;
 #pragma unroll 1
     for(u32 tix = 0; tix < ntiles; ++tix) {
-        const u32 d0 = 256u + tix * TILE;
-        const u32 mg0 = rc_magic(d0 + lane);
-        const u32 mg1 = rc_magic(d0 + 32u + lane);
-#pragma unroll 1
-        for(int wi = 0; wi < TILE / 4; ++wi) {
-            const u32 mg = wi < 8 ? mg0 : mg1;
-            u32 word = 0;
-#pragma unroll
-            for(int k = 0; k < 4; ++k) {
-                const int j = wi * 4 + k;
-                const u32 magic = __shfl_sync(FULL, mg, j & 31);
-                if(tix * TILE + j < n_b) {
-                    const u32 t = rc_div(d.range, d0 + j, magic);
-                    u32 sym, cum, freq;
-                    rc_model_decode(tab, d.low, t, sym, cum, freq);
-                    rc_dec_advance(d, cum, freq, t, src);
-                    word |= sym << (8 * k);
-                }
-            }
-            sts32v(otile_a + lane * ROW + wi * 4, word);
+        if(__all_sync(FULL, src.tile_is_inside())) {
+            WordSrcInside in{src};
+            dec_adaptive_tile<W>(tab, d, in, otile_a, tix * TILE, n_b, lane);
+        } else {
+            dec_adaptive_tile<W>(tab, d, src, otile_a, tix * TILE, n_b, lane);
         }
         __syncwarp();
         store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);

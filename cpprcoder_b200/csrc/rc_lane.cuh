@@ -66,7 +66,11 @@ RC_HD u32 rc_clz(u32 x)
 RC_HD u32 rc_umulhi(u32 a, u32 b)
 {
 #if defined(__CUDA_ARCH__)
-    return __umulhi(a, b);
+    // mul.wide + take the upper register: __umulhi becomes IMAD.HI.U32, which on sm_100a is a
+    // slow scoreboarded instruction (about 19 cycles measured, profiles/r1_ncu_notes.md)
+    unsigned long long p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    return (u32)(p >> 32);
 #else
     return (u32)(((u64)a * b) >> 32);
 #endif
