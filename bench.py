@@ -26,6 +26,10 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# The host-pointer pipeline keeps one stream per chunk busy (up to 16 + 2).  With the default
+# of 8 hardware queues, streams alias and one chunk's copy waits behind another chunk's
+# kernel; must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 

@@ -40,6 +40,7 @@ struct b2rc_ctx {
     cudaEvent_t scan_done[B2RC_PIPE_CHUNKS], chunk_done[B2RC_PIPE_CHUNKS], index_ready;
     u64* d_ends;  // B2RC_PIPE_CHUNKS + 1
     u64* h_ends;  // pinned
+    u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
     struct Result {
         int err;
         int pad;
@@ -251,6 +252,10 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         return B2RC_E_ARG;
     }
     *out = nullptr;
+    // one stream per pipeline chunk: ask for enough hardware queues that they do not alias.
+    // Only effective when this is the process's first CUDA call; callers that initialise CUDA
+    // themselves (PyTorch) should export CUDA_DEVICE_MAX_CONNECTIONS=32 beforehand.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     if(cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
         cudaGetLastError();
@@ -266,6 +271,13 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
     }
     memset(ctx, 0, sizeof *ctx);
     ctx->device = device;
+    ctx->max_chunks = B2RC_PIPE_CHUNKS;
+    if(const char* e = getenv("B2RC_PIPE_CHUNKS")) {
+        const long v = atol(e);
+        if(v >= 1 && v <= B2RC_PIPE_CHUNKS) {
+            ctx->max_chunks = (u64)v;
+        }
+    }
     int rc = B2RC_OK;
     do {
         if(!cuda_ok(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
@@ -702,13 +714,13 @@ struct Chunks {
     u64 lo(u64 c) const { return c * per < nb ? c * per : nb; }
     u64 hi(u64 c) const { return (c + 1) * per < nb ? (c + 1) * per : nb; }
 };
-Chunks plan_chunks(u64 n, u32 block)
+Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block)
 {
     Chunks ch;
     ch.nb = b2rc_nblocks(n, block);
     u64 count = n / B2RC_PIPE_MIN_CHUNK;
-    if(count > B2RC_PIPE_CHUNKS) {
-        count = B2RC_PIPE_CHUNKS;
+    if(count > ctx->max_chunks) {
+        count = ctx->max_chunks;
     }
     if(count < 1) {
         count = 1;
@@ -732,7 +744,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     }
     DeviceGuard g(ctx->device);
     const u64 bound = b2rc_bound(mode, n, block_size);
-    const Chunks ch = plan_chunks(n, block_size);
+    const Chunks ch = plan_chunks(ctx, n, block_size);
     const u64 nb = ch.nb;
     const u64 idx = index_bytes(nb);
     if(out_n) {
@@ -865,7 +877,7 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
        (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(total + 16))) != B2RC_OK) {
         return rc;
     }
-    const Chunks ch = plan_chunks(total, block);
+    const Chunks ch = plan_chunks(ctx, total, block);
     cudaStream_t s0 = ctx->pipe[0];
     const u64* d_offsets = reinterpret_cast<const u64*>(ctx->stage_in + B2RC_HEADER_BYTES);
     CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), s0));
