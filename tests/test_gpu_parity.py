@@ -211,3 +211,55 @@ def test_error_paths(ctx):
     with pytest.raises(B2rcError) as e:
         ctx.encode_device(STATIC, src, small)
     assert e.value.code == E_DST_SMALL
+
+
+# ------------------------------------------------------------- more coverage --
+def test_random_shapes_match_oracle(ctx, oracle):
+    """Seeded fuzz over block sizes (narrow and wide tables), lengths and byte patterns."""
+    rng = np.random.default_rng(20261018)
+    for it in range(14):
+        block = int(rng.choice([64, 128, 1024, 4096, 16384, 65536, 131072])) if it % 3 else 64 * int(rng.integers(1, 1500))
+        nblocks = int(rng.integers(1, 80 if block <= 16384 else 40))
+        ragged = int(rng.integers(0, block))
+        data = crafted_stream(nblocks, block, seed=1000 + it, ragged=ragged)
+        for mode, key in MODES:
+            enc = ctx.encode(mode, data, block)
+            _, pays = payloads_of(enc)
+            assert_blocks_equal(pays, oracle.encode_blocks(mode, data, block, threads=4), f"fuzz {it} block {block}/{key}")
+            assert ctx.decode(enc).tobytes() == data.tobytes()
+
+
+def test_side_stream_and_second_context(ctx, oracle):
+    import torch
+    from cpprcoder_b200 import api
+    data = synth.mixed(20 * 65536 + 99, start=1 << 20)
+    src = torch.from_numpy(data).cuda()
+    other = api.Context(0)
+    side = torch.cuda.Stream()
+    try:
+        with torch.cuda.stream(side):
+            enc, used = other.encode_device(ADAPTIVE, src)
+            dst = torch.empty(data.size, dtype=torch.uint8, device="cuda")
+            assert other.decode_device(enc, used, dst) == data.size
+        side.synchronize()
+        assert torch.equal(dst, src)
+        enc2, used2 = ctx.encode_device(ADAPTIVE, src)  # same answer from the other context on the default stream
+        assert used2 == used and torch.equal(enc2[:used2], enc[:used])
+        head = enc[:used].cpu().numpy()
+        info = container.parse(head)
+        assert bytes(info.payload(head, 7)) == oracle.encode(ADAPTIVE, data[7 * 65536:8 * 65536])
+    finally:
+        other.close()
+
+
+def test_pipelined_host_calls_on_many_chunks(ctx, oracle):
+    """Large enough for the host-pointer pipeline to cut several chunks (64 MiB each)."""
+    n = (3 << 26) + 65536 * 5 + 17
+    data = synth.kennedy(n)
+    for mode, key in MODES:
+        enc = ctx.encode(mode, data, 65536)
+        info = container.parse(enc)
+        assert info.nblocks == (n + 65535) // 65536
+        for b in [0, 1023, 1024, 2047, 2048, info.nblocks - 1]:  # around the chunk seams
+            assert bytes(info.payload(enc, b)) == oracle.encode(mode, data[b * 65536:(b + 1) * 65536]), f"block {b}"
+        assert ctx.decode(enc).tobytes() == data.tobytes()
