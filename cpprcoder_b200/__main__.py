@@ -1,0 +1,86 @@
+"""File-level front end: B2RC containers on disk and the reference
+harness's row format.
+
+    python -m cpprcoder_b200 encode [--adaptive] [--block N] IN OUT
+    python -m cpprcoder_b200 decode IN OUT
+    python -m cpprcoder_b200 rows   [--block N] FILE...     # |file|ratio|enc MiB/s|dec MiB/s| per coder
+
+`rows` prints what the reference's run_rangecoder / run_adaptive print (test/main.cpp:104-107,
+:290-294): ratio = original / coded bytes, speeds in MiB/s, and fails loudly on a mismatch.
+All coding happens on the GPU through libb2rc.so.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+from . import api
+
+
+def _read(path: str) -> np.ndarray:
+    return np.fromfile(path, dtype=np.uint8)
+
+
+def cmd_encode(a) -> int:
+    ctx = api.Context()
+    data = _read(a.input)
+    out = ctx.encode(api.MODE_ADAPTIVE if a.adaptive else api.MODE_STATIC, data, a.block)
+    Path(a.output).write_bytes(out.tobytes())
+    print(f"{a.input}: {data.size} -> {out.size} bytes ({out.size / max(data.size, 1):.6f})")
+    return 0
+
+
+def cmd_decode(a) -> int:
+    ctx = api.Context()
+    out = ctx.decode(_read(a.input))
+    Path(a.output).write_bytes(out.tobytes())
+    print(f"{a.input}: -> {out.size} bytes")
+    return 0
+
+
+def cmd_rows(a) -> int:
+    ctx = api.Context()
+    bad = 0
+    for path in a.files:
+        data = _read(path)
+        for mode in (api.MODE_STATIC, api.MODE_ADAPTIVE):
+            t0 = time.perf_counter()
+            enc = ctx.encode(mode, data, a.block)
+            t1 = time.perf_counter()
+            dec = ctx.decode(enc)
+            t2 = time.perf_counter()
+            mib = data.size / (1024.0 * 1024.0)
+            print("|%s|%f|%f|%f|" % (path, data.size / max(enc.size, 1), mib / (t1 - t0), mib / (t2 - t1)))
+            if dec.tobytes() != data.tobytes():
+                print(f"{path}: round trip MISMATCH", file=sys.stderr)
+                bad += 1
+    return 1 if bad else 0
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="python -m cpprcoder_b200")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    e = sub.add_parser("encode")
+    e.add_argument("--adaptive", action="store_true")
+    e.add_argument("--block", type=int, default=api.DEFAULT_BLOCK)
+    e.add_argument("input")
+    e.add_argument("output")
+    e.set_defaults(fn=cmd_encode)
+    d = sub.add_parser("decode")
+    d.add_argument("input")
+    d.add_argument("output")
+    d.set_defaults(fn=cmd_decode)
+    r = sub.add_parser("rows")
+    r.add_argument("--block", type=int, default=api.DEFAULT_BLOCK)
+    r.add_argument("files", nargs="+")
+    r.set_defaults(fn=cmd_rows)
+    a = ap.parse_args(argv)
+    return a.fn(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -53,3 +53,19 @@ def test_canterbury_rows_on_gpu(harness, tmp_path, golden):
         name = Path(row[1]).name
         whole = golden["canterbury"][name]["bytes"] / golden["canterbury"][name]["whole"]["static"]["size"]
         assert 0.5 * whole < float(row[2]) < 1.6 * whole
+
+
+@pytest.mark.gpu
+def test_file_cli_round_trip(tmp_path):
+    import subprocess
+    import sys
+    with tarfile.open(ROOT / "tests" / "golden" / "cantrbry.tar.bz2", "r:bz2") as tf:
+        tf.extractall(tmp_path, filter="data")
+    src = tmp_path / "cantrbry" / "lcet10.txt"
+    for flag in ([], ["--adaptive"]):
+        enc, dec = tmp_path / "x.b2rc", tmp_path / "x.out"
+        subprocess.check_call([sys.executable, "-m", "cpprcoder_b200", "encode", *flag, str(src), str(enc)], cwd=ROOT)
+        subprocess.check_call([sys.executable, "-m", "cpprcoder_b200", "decode", str(enc), str(dec)], cwd=ROOT)
+        assert dec.read_bytes() == src.read_bytes()
+    r = subprocess.run([sys.executable, "-m", "cpprcoder_b200", "rows", str(src)], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.count("|") == 10
