@@ -242,9 +242,10 @@ RC_HD void rc_enc_step(RcEnc& e, u32 cum, u32 freq, u32 t, RcCut& c, bool active
 }
 
 // Power-of-two total (every full block of the static coder that never halved): the
-// chain is carried by t = range >> shift alone.  (r << sh) >> shift is picked among the
-// three candidates by the same compares that pick sh, so one link of the chain is
-// IMAD -> compare -> select -> select.  `e.range` is not maintained on this path.
+// chain is carried by t = range >> shift alone: t' = (freq * t << sh) >> shift.  One link of
+// the chain is IMAD -> compare -> select -> shift -> shift; a lone warp issues roughly one
+// instruction every two cycles, so the instruction count, not the last few cycles of chain,
+// decides (profiles/r1_ncu_notes.md).  `e.range` is not maintained on this path.
 template <int MAXSH>
 RC_HD void rc_enc_step_pow2(RcEnc& e, u32& t, u32 shift, u32 cum, u32 freq, RcCut& c, bool active = true)
 {
@@ -252,17 +253,8 @@ RC_HD void rc_enc_step_pow2(RcEnc& e, u32& t, u32 shift, u32 cum, u32 freq, RcCu
     if(active) {
         rc_add96(e.low, e.o_lo, e.o_hi, cum * t);
         const u32 r = freq * t;
-        const bool p8 = r < 0x01000000u, p16 = r < 0x00010000u, p24 = MAXSH >= 3 && r < 0x00000100u;
-        const u32 t0 = r >> shift, t8 = (r << 8) >> shift, t16 = (r << 16) >> shift, t24 = (r << 24) >> shift;
-        u32 tn = p8 ? t8 : t0;
-        tn = p16 ? t16 : tn;
-        sh = p8 ? 8u : 0u;
-        sh = p16 ? 16u : sh;
-        if(MAXSH >= 3) {
-            tn = p24 ? t24 : tn;
-            sh = p24 ? 24u : sh;
-        }
-        t = tn;
+        sh = rc_norm_shift<MAXSH>(r);
+        t = (r << sh) >> shift;  // two shifts on the chain instead of three candidates and two selects: fewer instructions
     }
     e.o_hi = rc_funnel_l(e.o_lo, e.o_hi, sh);
     e.o_lo = rc_funnel_l(e.low, e.o_lo, sh);
@@ -554,18 +546,8 @@ RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, N
 {
     d.low -= cum * t;
     const u32 r = freq * t;
-    const bool p8 = r < 0x01000000u, p16 = r < 0x00010000u;
-    const u32 t0 = r >> shift, t8 = (r << 8) >> shift, t16 = (r << 16) >> shift;
-    u32 tn = p8 ? t8 : t0;
-    tn = p16 ? t16 : tn;
-    u32 sh = p8 ? 8u : 0u;
-    sh = p16 ? 16u : sh;
-    if(MAXSH >= 3) {
-        const bool p24 = r < 0x00000100u;
-        tn = p24 ? ((r << 24) >> shift) : tn;
-        sh = p24 ? 24u : sh;
-    }
-    t = tn;
+    const u32 sh = rc_norm_shift<MAXSH>(r);
+    t = (r << sh) >> shift;
     d.low = rc_funnel_l(d.w_hi, d.low, sh);
     d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);
     d.w_lo <<= sh;
@@ -599,17 +581,21 @@ RC_HD void rc_model_encode(Tab& tab, u32 b, u32& cum, u32& freq)
         v[l] = tab.ld(leaf >> (l + 1));
     }
     const u32 f = tab.ld(leaf);
-    u32 below = 0;
+    u32 below = b;  // the implicit one per symbol below b
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for(s32 l = 7; l >= 0; --l) {
-        const u32 bit = (b >> l) & 1u;
-        below += bit ? v[l] : 0u;
-        tab.st(leaf >> (l + 1), v[l] + (bit ^ 1u));  // unchanged where the bit is set
+        u32 x = v[l];
+        if(b & (1u << l)) {
+            below += x;  // everything in the left subtree is below b
+        } else {
+            x += 1u;     // b goes into the left subtree
+        }
+        tab.st(leaf >> (l + 1), x);  // unchanged where the bit is set
     }
     tab.st(leaf, f + 1u);
-    cum = b + below;
+    cum = below;
     freq = 1u + f;
 }
 
