@@ -71,7 +71,7 @@ __device__ __forceinline__ u32 lds32(u32 a)
 __device__ __forceinline__ u32 lds16(u32 a)
 {
     u32 v;
-    asm("{ .reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(v) : "r"(a));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));  // a wider destination is zero extended: no cvt
     return v;
 }
 // read-write data (adaptive model, rings): volatile keeps program order among them
@@ -84,7 +84,7 @@ __device__ __forceinline__ u32 lds32v(u32 a)
 __device__ __forceinline__ u32 lds16v(u32 a)
 {
     u32 v;
-    asm volatile("{ .reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(v) : "r"(a));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ void sts32v(u32 a, u32 v)
@@ -93,7 +93,7 @@ __device__ __forceinline__ void sts32v(u32 a, u32 v)
 }
 __device__ __forceinline__ void sts16v(u32 a, u32 v)
 {
-    asm volatile("{ .reg .u16 h; cvt.u16.u32 h, %1; st.shared.u16 [%0], h; }" ::"r"(a), "r"(v));
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v));  // a wider source is truncated: no cvt
 }
 
 // Stage tile `tile_off .. tile_off+TILE` of 32 consecutive blocks into shared memory.
@@ -504,6 +504,116 @@ struct LaneTab {
     }
 };
 
+// Hand-scheduled forms of rc_model_encode / rc_model_decode (rc_lane.cuh holds the portable
+// statements of the same walks, which tests/sim checks against the oracle).  The compiler
+// turned the per-level "bit set? add : increment" into 7 mask-arithmetic instructions and
+// rebuilt every node address from shifts and masks (163 instructions per symbol in the
+// encoder, profiles/r1_ncu_notes.md); written out with predicates a level is: address (2),
+// load, test+two predicated adds (3), store.
+template <class W>
+struct TreeOps {
+    static constexpr u32 S = 32u * sizeof(W);  // bytes between consecutive nodes of one lane
+    static __device__ __forceinline__ u32 ld(u32 a) { return sizeof(W) == 2 ? lds16v(a) : lds32v(a); }
+    static __device__ __forceinline__ void st(u32 a, u32 v)
+    {
+        if(sizeof(W) == 2) {
+            sts16v(a, v);
+        } else {
+            sts32v(a, v);
+        }
+    }
+    template <int L>
+    static __device__ __forceinline__ u32 node_addr(u32 base, u32 leaf)  // node (leaf >> (L+1)) of the lane at `base`
+    {
+        u32 idx, a;
+        asm("shr.u32 %0, %1, %2;" : "=r"(idx) : "r"(leaf), "n"(L + 1));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(idx), "n"(S), "r"(base));
+        return a;
+    }
+    template <int L>
+    static __device__ __forceinline__ void enc_level(u32 b, u32& below, u32& x)
+    {
+        asm("{ .reg .pred p; .reg .u32 m;\n\tand.b32 m, %2, %3;\n\tsetp.ne.u32 p, m, 0;\n\t@p add.u32 %0, %0, %1;\n\t@!p add.u32 %1, %1, 1; }"
+            : "+r"(below), "+r"(x)
+            : "r"(b), "n"(1u << L));
+    }
+    // cum / freq of b under the current counts, then count b (AdaptiveFrequencyTable::cumulative
+    // + update, cpprcoder.h:1134-1187, for a model that never halves)
+    static __device__ __forceinline__ void encode(u32 base, u32 b, u32& cum, u32& freq)
+    {
+        const u32 leaf = 256u | b;
+        u32 a[8], v[8];
+        a[7] = node_addr<7>(base, leaf);
+        a[6] = node_addr<6>(base, leaf);
+        a[5] = node_addr<5>(base, leaf);
+        a[4] = node_addr<4>(base, leaf);
+        a[3] = node_addr<3>(base, leaf);
+        a[2] = node_addr<2>(base, leaf);
+        a[1] = node_addr<1>(base, leaf);
+        a[0] = node_addr<0>(base, leaf);
+        u32 al;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(al) : "r"(leaf), "n"(S), "r"(base));
+#pragma unroll
+        for(int l = 7; l >= 0; --l) {
+            v[l] = ld(a[l]);
+        }
+        const u32 f = ld(al);
+        u32 below = b;  // the implicit one per symbol below b
+        enc_level<7>(b, below, v[7]);
+        enc_level<6>(b, below, v[6]);
+        enc_level<5>(b, below, v[5]);
+        enc_level<4>(b, below, v[4]);
+        enc_level<3>(b, below, v[3]);
+        enc_level<2>(b, below, v[2]);
+        enc_level<1>(b, below, v[1]);
+        enc_level<0>(b, below, v[0]);
+#pragma unroll
+        for(int l = 7; l >= 0; --l) {
+            st(a[l], v[l]);
+        }
+        st(al, f + 1u);
+        cum = below;
+        freq = f + 1u;
+    }
+
+    // One level of the decoder's walk.  `rem` = low minus everything already known to lie
+    // below the symbol (times t); `aid` = address of the current node, `v` its count.
+    template <int L>
+    static __device__ __forceinline__ void dec_level(u32 base, u32 t, u32& rem, u32& aid, u32& v)
+    {
+        u32 ca;  // address of the left child: base + 2*id*S = 2*aid - base
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(ca) : "r"(aid), "r"(0u - base));
+        const u32 vl = ld(ca), vr = ld(ca + S);  // read while the compare below is still in flight
+        const u32 prod = (v + (1u << L)) * t;    // left subtree: counts + the implicit one per symbol
+        u32 anext, vnext;
+        asm("{ .reg .pred p;\n\tsetp.le.u32 p, %4, %0;\n\t@p sub.u32 %0, %0, %4;\n\t@!p add.u32 %1, %1, 1;\n\t"
+            "selp.u32 %2, %5, %6, p;\n\tselp.u32 %3, %7, %8, p; }"
+            : "+r"(rem), "+r"(v), "=r"(anext), "=r"(vnext)
+            : "r"(prod), "r"(ca + S), "r"(ca), "r"(vr), "r"(vl));
+        st(aid, v);  // incremented when the symbol went left, unchanged otherwise
+        aid = anext;
+        v = vnext;
+    }
+    // AdaptiveFrequencyTable::find (cpprcoder.h:1221-1241) in the product domain + update.
+    // Returns the symbol; `rem` comes back as low - cum*t, freq as the symbol's frequency.
+    static __device__ __forceinline__ u32 decode(u32 base, u32 t, u32& rem, u32& freq)
+    {
+        u32 aid = base + S;  // node 1, the root
+        u32 v = ld(aid);
+        dec_level<7>(base, t, rem, aid, v);
+        dec_level<6>(base, t, rem, aid, v);
+        dec_level<5>(base, t, rem, aid, v);
+        dec_level<4>(base, t, rem, aid, v);
+        dec_level<3>(base, t, rem, aid, v);
+        dec_level<2>(base, t, rem, aid, v);
+        dec_level<1>(base, t, rem, aid, v);
+        dec_level<0>(base, t, rem, aid, v);
+        st(aid, v + 1u);  // aid is now the leaf 256 | symbol, v its count
+        freq = v + 1u;
+        return ((aid - base) / S) & 255u;
+    }
+};
+
 template <class W, bool RAGGED>
 __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, LaneTab<W>& tab, RcEnc& st,
                                                    SlotSink& sink, u64 b0, u32 n_b, u32 n_max, u32 lane)
@@ -534,7 +644,7 @@ __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, 
                 const bool active = !RAGGED || tix * TILE + j < n_b;
                 u32 cum = 0, freq = 1;
                 if(active) {
-                    rc_model_encode(tab, sym, cum, freq);
+                    TreeOps<W>::encode(tab.base, sym, cum, freq);
                 }
                 const u32 t = rc_div(st.range, d0 + j, magic);
                 rc_enc_step<3>(st, cum, freq, t, cuts[k], active);
@@ -918,9 +1028,9 @@ __device__ __forceinline__ void dec_adaptive_tile(LaneTab<W>& tab, RcDec& d, Src
             const u32 magic = __shfl_sync(FULL, mg, j & 31);
             if(tile_off + j < n_b) {
                 const u32 t = rc_div(d.range, d0 + j, magic);
-                u32 sym, cum, freq;
-                rc_model_decode(tab, d.low, t, sym, cum, freq);
-                rc_dec_advance(d, cum, freq, t, src);
+                u32 freq;
+                const u32 sym = TreeOps<W>::decode(tab.base, t, d.low, freq);  // d.low -= cum * t on the way
+                rc_dec_advance(d, 0u, freq, t, src);
                 word |= sym << (8 * k);
             }
         }
