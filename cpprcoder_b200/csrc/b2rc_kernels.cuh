@@ -577,37 +577,50 @@ struct TreeOps {
     }
 
     // One level of the decoder's walk.  `rem` = low minus everything already known to lie
-    // below the symbol (times t); `aid` = address of the current node, `v` its count.
+    // below the symbol (times t); `aid` = address of the current node, `v` its count, `cl`/`cr`
+    // the counts of its two children.  The four GRANDCHILDREN are read here, two levels ahead
+    // of their use, so that no table latency is left on the compare chain of the walk.
     template <int L>
-    static __device__ __forceinline__ void dec_level(u32 base, u32 t, u32& rem, u32& aid, u32& v)
+    static __device__ __forceinline__ void dec_level(u32 base, u32 t, u32& rem, u32& aid, u32& v, u32& cl, u32& cr)
     {
+        u32 g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+        if(L >= 1) {
+            u32 ga;  // base + 4*id*S = 4*aid - 3*base
+            asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(ga) : "r"(aid), "r"(0u - 3u * base));
+            g0 = ld(ga);
+            g1 = ld(ga + S);
+            g2 = ld(ga + 2u * S);
+            g3 = ld(ga + 3u * S);
+        }
         u32 ca;  // address of the left child: base + 2*id*S = 2*aid - base
         asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(ca) : "r"(aid), "r"(0u - base));
-        const u32 vl = ld(ca), vr = ld(ca + S);  // read while the compare below is still in flight
-        const u32 prod = (v + (1u << L)) * t;    // left subtree: counts + the implicit one per symbol
-        u32 anext, vnext;
-        asm("{ .reg .pred p;\n\tsetp.le.u32 p, %4, %0;\n\t@p sub.u32 %0, %0, %4;\n\t@!p add.u32 %1, %1, 1;\n\t"
-            "selp.u32 %2, %5, %6, p;\n\tselp.u32 %3, %7, %8, p; }"
-            : "+r"(rem), "+r"(v), "=r"(anext), "=r"(vnext)
-            : "r"(prod), "r"(ca + S), "r"(ca), "r"(vr), "r"(vl));
+        const u32 prod = (v + (1u << L)) * t;  // left subtree: counts + the implicit one per symbol
+        u32 anext, vnext, nl, nr;
+        asm("{ .reg .pred p;\n\tsetp.le.u32 p, %6, %0;\n\t@p sub.u32 %0, %0, %6;\n\t@!p add.u32 %1, %1, 1;\n\t"
+            "selp.u32 %2, %7, %8, p;\n\tselp.u32 %3, %9, %10, p;\n\t"
+            "selp.u32 %4, %11, %12, p;\n\tselp.u32 %5, %13, %14, p; }"
+            : "+r"(rem), "+r"(v), "=r"(anext), "=r"(vnext), "=r"(nl), "=r"(nr)
+            : "r"(prod), "r"(ca + S), "r"(ca), "r"(cr), "r"(cl), "r"(g2), "r"(g0), "r"(g3), "r"(g1));
         st(aid, v);  // incremented when the symbol went left, unchanged otherwise
         aid = anext;
         v = vnext;
+        cl = nl;
+        cr = nr;
     }
     // AdaptiveFrequencyTable::find (cpprcoder.h:1221-1241) in the product domain + update.
     // Returns the symbol; `rem` comes back as low - cum*t, freq as the symbol's frequency.
     static __device__ __forceinline__ u32 decode(u32 base, u32 t, u32& rem, u32& freq)
     {
         u32 aid = base + S;  // node 1, the root
-        u32 v = ld(aid);
-        dec_level<7>(base, t, rem, aid, v);
-        dec_level<6>(base, t, rem, aid, v);
-        dec_level<5>(base, t, rem, aid, v);
-        dec_level<4>(base, t, rem, aid, v);
-        dec_level<3>(base, t, rem, aid, v);
-        dec_level<2>(base, t, rem, aid, v);
-        dec_level<1>(base, t, rem, aid, v);
-        dec_level<0>(base, t, rem, aid, v);
+        u32 v = ld(aid), cl = ld(base + 2u * S), cr = ld(base + 3u * S);
+        dec_level<7>(base, t, rem, aid, v, cl, cr);
+        dec_level<6>(base, t, rem, aid, v, cl, cr);
+        dec_level<5>(base, t, rem, aid, v, cl, cr);
+        dec_level<4>(base, t, rem, aid, v, cl, cr);
+        dec_level<3>(base, t, rem, aid, v, cl, cr);
+        dec_level<2>(base, t, rem, aid, v, cl, cr);
+        dec_level<1>(base, t, rem, aid, v, cl, cr);
+        dec_level<0>(base, t, rem, aid, v, cl, cr);
         st(aid, v + 1u);  // aid is now the leaf 256 | symbol, v its count
         freq = v + 1u;
         return ((aid - base) / S) & 255u;
