@@ -8,6 +8,7 @@
  * the lines it restates.  All arithmetic is uint32_t, as in the reference.
  */
 #include "rc_oracle.h"
+#include "ans_oracle.h"
 
 #include <pthread.h>
 #include <stdatomic.h>
@@ -460,6 +461,29 @@ typedef struct {
     atomic_ullong next;
 } job;
 
+/* modes 0/1 are the range coders of this file, 2/3 the rANS variants of ans_oracle.c */
+static long one_encode(int mode, const uint8_t* src, uint32_t n, uint8_t* dst, size_t cap)
+{
+    switch(mode) {
+    case RCO_STATIC: return rco_static_encode(src, n, dst, cap, NULL);
+    case RCO_ADAPTIVE: return rco_adaptive_encode(src, n, dst, cap, NULL);
+    case RAO_BYTE:
+    case RAO_WORD: return rao_encode(mode, src, n, dst, cap);
+    default: return -1;
+    }
+}
+
+static long one_decode(int mode, const uint8_t* src, size_t n, uint8_t* dst, size_t cap)
+{
+    switch(mode) {
+    case RCO_STATIC: return rco_static_decode(src, n, dst, cap);
+    case RCO_ADAPTIVE: return rco_adaptive_decode(src, n, dst, cap);
+    case RAO_BYTE:
+    case RAO_WORD: return rao_decode(mode, src, n, dst, cap);
+    default: return -1;
+    }
+}
+
 static void* worker(void* arg)
 {
     job* j = (job*)arg;
@@ -473,8 +497,7 @@ static void* worker(void* arg)
         long r;
         if(!j->decode) {
             uint8_t* slot = j->slots + b * j->slot_stride;
-            r = (j->mode == RCO_STATIC) ? rco_static_encode(j->src + at, len, slot, j->slot_stride, NULL)
-                                        : rco_adaptive_encode(j->src + at, len, slot, j->slot_stride, NULL);
+            r = one_encode(j->mode, j->src + at, len, slot, j->slot_stride);
             if(r < 0) {
                 j->failed = 1;
             } else {
@@ -483,8 +506,7 @@ static void* worker(void* arg)
         } else {
             const uint8_t* pay = j->src + j->offsets[b];
             const size_t paylen = (size_t)(j->offsets[b + 1] - j->offsets[b]);
-            r = (j->mode == RCO_STATIC) ? rco_static_decode(pay, paylen, j->dst + at, len)
-                                        : rco_adaptive_decode(pay, paylen, j->dst + at, len);
+            r = one_decode(j->mode, pay, paylen, j->dst + at, len);
             if(r != (long)len) {
                 j->failed = 1;
             }

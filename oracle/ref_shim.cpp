@@ -10,14 +10,27 @@
 //
 // Per-block calls follow how the reference harness drives the coder:
 // run_rangecoder (test/main.cpp:254-301) and run_adaptive (test/main.cpp:305-363).
-#define CPPRCODER_IMPLEMENTATION
-#include CPPRCODER_H
-
 #include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <thread>
 #include <vector>
+
+#define CPPRCODER_IMPLEMENTATION
+#include CPPRCODER_H
+
+// The sibling rANS coder (cppans.h), modes 2 and 3 below.
+// The header does not compile with g++ as written: its restrict macro is defined for
+// MSVC and clang only (it tests `__gnuc__`, cppans.h:92-99), and `static alignas(16)
+// const` (cppans.h:445) is ill-formed for GCC.  Two macros around the include repair
+// both; the header is used as it lies.
+#ifdef CPPANS_H
+#define CPPANS_RESTRICT __restrict
+#define alignas(x) __attribute__((aligned(x)))
+#define CPPANS_IMPLEMENTATION
+#include CPPANS_H
+#undef alignas
+#endif
 
 namespace
 {
@@ -25,8 +38,52 @@ using namespace cpprcoder;
 
 // MemoryStream::writeByte never grows (cpprcoder.h:1047-1054), so the stream is
 // pre-sized to the caller's slot, as the harness pre-sizes it to the input size.
+#ifdef CPPANS_H
+// rANS::encode / encode_simd write the payload at the END of the buffer they are given
+// (cppans.h:515-529, :591-605); it is moved to the front of dst here.
+long ans_encode_one(int mode, const u8* src, u32 n, u8* dst, size_t cap, std::vector<u8>& buf)
+{
+    if(n == 0) {
+        return -1;  // asserted against by the reference (cppans.h:502, :572)
+    }
+    buf.resize(static_cast<size_t>(n) * 2 + 1032 + 64);
+    const u32 got = mode == 3 ? cppans::rANS::encode_simd(static_cast<u32>(buf.size()), buf.data(), n, src)
+                              : cppans::rANS::encode(static_cast<u32>(buf.size()), buf.data(), n, src);
+    if(got == 0 || got > cap) {
+        return -1;
+    }
+    memcpy(dst, buf.data() + buf.size() - got, got);
+    return static_cast<long>(got);
+}
+
+// decode_simd reads up to 6 bytes past the coded words (cppans.h:476-478), so the payload
+// is copied into a padded buffer first.  Returns the symbol count of the header.
+long ans_decode_one(int mode, const u8* src, size_t n, u8* dst, size_t cap, std::vector<u8>& buf)
+{
+    if(n < 1032 + 4) {
+        return -1;
+    }
+    u32 want;
+    memcpy(&want, src, 4);
+    if(want > cap) {
+        return -1;
+    }
+    buf.assign(src, src + n);
+    buf.resize(n + 16, 0);
+    const u32 got = mode == 3 ? cppans::rANS::decode_simd(static_cast<u32>(cap), dst, static_cast<u32>(n), buf.data())
+                              : cppans::rANS::decode(static_cast<u32>(cap), dst, static_cast<u32>(n), buf.data());
+    return got == 0 ? -1 : static_cast<long>(want);
+}
+#endif
+
 long encode_one(int mode, const u8* src, u32 n, u8* dst, size_t cap, MemoryStream& scratch)
 {
+#ifdef CPPANS_H
+    if(mode == 2 || mode == 3) {
+        thread_local std::vector<u8> buf;
+        return ans_encode_one(mode, src, n, dst, cap, buf);
+    }
+#endif
     scratch.resize(0);
     if(mode == 0) {
         RangeEncoder<> coder;
@@ -56,6 +113,12 @@ long encode_one(int mode, const u8* src, u32 n, u8* dst, size_t cap, MemoryStrea
 
 long decode_one(int mode, const u8* src, size_t n, u8* dst, size_t cap, MemoryStream& scratch)
 {
+#ifdef CPPANS_H
+    if(mode == 2 || mode == 3) {
+        thread_local std::vector<u8> buf;
+        return ans_decode_one(mode, src, n, dst, cap, buf);
+    }
+#endif
     scratch.resize(0);
     if(mode == 0) {
         RangeEncoder<> coder;

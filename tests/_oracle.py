@@ -23,11 +23,15 @@ ORACLE_DIR = ROOT / "oracle"
 GOLDEN = ROOT / "tests" / "golden"
 
 STATIC, ADAPTIVE = 0, 1
+RANS_BYTE, RANS_WORD = 2, 3  # cppans::rANS::encode / encode_simd (oracle/ans_oracle.h)
+RANS_HEADER = 1032
 FNV_OFFSET = 1469598103934665603
 FNV_PRIME = 1099511628211
 
 
-def slot_bytes(n: int) -> int:
+def slot_bytes(n: int, mode: int = STATIC) -> int:
+    if mode in (RANS_BYTE, RANS_WORD):
+        return (RANS_HEADER + 32 + 2 * n + 15) & ~15
     s = n + n // 8 + 1024
     return (s + 127) & ~127
 
@@ -65,7 +69,7 @@ class _Coder:
         src = _u8(src)
         n = src.size
         nblocks = (n + block - 1) // block
-        stride = slot_bytes(block)
+        stride = slot_bytes(block, mode)
         slots = np.empty(max(nblocks, 1) * stride, dtype=np.uint8)
         sizes = np.zeros(max(nblocks, 1), dtype=np.uint32)
         rc = self._encode_blocks(mode, src.ctypes.data_as(C.c_void_p), n, block, slots.ctypes.data_as(C.c_void_p),
@@ -119,11 +123,22 @@ class Oracle(_Coder):
                                           C.c_uint64, C.c_int]
         self._encode_blocks = lib.rco_encode_blocks
         self._decode_blocks = lib.rco_decode_blocks
+        lib.rao_encode.restype = C.c_long
+        lib.rao_encode.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
+        lib.rao_decode.restype = C.c_long
+        lib.rao_decode.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        lib.rao_model.restype = None
+        lib.rao_model.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
 
     def encode(self, mode: int, src, with_stats: bool = False):
         src = _u8(src)
         cap = slot_bytes(src.size) + 2 * src.size
         dst = np.empty(cap, dtype=np.uint8)
+        if mode in (RANS_BYTE, RANS_WORD):
+            r = self.lib.rao_encode(mode, src.ctypes.data_as(C.c_void_p), src.size, dst.ctypes.data_as(C.c_void_p), cap)
+            if r < 0:
+                raise RuntimeError("oracle rANS encode failed")
+            return dst[:r].tobytes()
         st = _Stats()
         fn = self.lib.rco_static_encode if mode == STATIC else self.lib.rco_adaptive_encode
         r = fn(src.ctypes.data_as(C.c_void_p), src.size, dst.ctypes.data_as(C.c_void_p), cap, C.byref(st))
@@ -137,11 +152,24 @@ class Oracle(_Coder):
     def decode(self, mode: int, payload, cap: int) -> bytes:
         payload = _u8(payload)
         dst = np.empty(max(cap, 1), dtype=np.uint8)
-        fn = self.lib.rco_static_decode if mode == STATIC else self.lib.rco_adaptive_decode
-        r = fn(payload.ctypes.data_as(C.c_void_p), payload.size, dst.ctypes.data_as(C.c_void_p), cap)
+        if mode in (RANS_BYTE, RANS_WORD):
+            r = self.lib.rao_decode(mode, payload.ctypes.data_as(C.c_void_p), payload.size,
+                                    dst.ctypes.data_as(C.c_void_p), cap)
+        else:
+            fn = self.lib.rco_static_decode if mode == STATIC else self.lib.rco_adaptive_decode
+            r = fn(payload.ctypes.data_as(C.c_void_p), payload.size, dst.ctypes.data_as(C.c_void_p), cap)
         if r < 0:
             raise RuntimeError("oracle decode failed")
         return dst[:r].tobytes()
+
+    def rans_model(self, src, bits: int) -> tuple[np.ndarray, np.ndarray]:
+        """(freq[256], cum[257]) after the reference's normalize (cppans.h:138-177)."""
+        src = _u8(src)
+        freq = np.zeros(256, dtype=np.uint32)
+        cum = np.zeros(257, dtype=np.uint32)
+        self.lib.rao_model(src.ctypes.data_as(C.c_void_p), src.size, 1 << bits, freq.ctypes.data_as(C.c_void_p),
+                           cum.ctypes.data_as(C.c_void_p))
+        return freq, cum
 
     def static_count(self, src) -> tuple[np.ndarray, int]:
         src = _u8(src)
