@@ -10,6 +10,8 @@ SO = PKG / "libb2rc.so"
 
 OK, E_ARG, E_DST_SMALL, E_CORRUPT, E_CUDA, E_EXPAND, E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 MODE_STATIC, MODE_ADAPTIVE = 0, 1
+MODE_RANS_BYTE, MODE_RANS_WORD = 2, 3  # cppans::rANS::encode / ::encode_simd
+MODE_NAMES = {"static": 0, "adaptive": 1, "rans": 2, "rans-word": 3}
 HEADER_BYTES = 32
 DEFAULT_BLOCK = 65536
 
@@ -25,6 +27,7 @@ SIGNATURES = {
     "b2rc_last_cuda_error": (C.c_char_p, [_P]),
     "b2rc_bound": (_U64, [C.c_int, _U64, _U32]),
     "b2rc_slot_bytes": (_U64, [_U32]),
+    "b2rc_slot_bytes_for": (_U64, [C.c_int, _U32]),
     "b2rc_nblocks": (_U64, [_U64, _U32]),
     "b2rc_encode": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, C.POINTER(_U64)]),
     "b2rc_decode": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64)]),
@@ -35,6 +38,7 @@ SIGNATURES = {
     "b2rc_k_encode_blocks": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _P, _U64, _P, _P, _P]),
     "b2rc_k_scan": (C.c_int, [_P, _P, _U64, _P, _P]),
     "b2rc_k_compact": (C.c_int, [_P, _P, _U64, _P, _P, _U64, _P, _U64, _P, _P]),
+    "b2rc_k_compact_for": (C.c_int, [_P, C.c_int, _P, _U64, _P, _P, _U64, _P, _U64, _P, _P]),
     "b2rc_k_decode_blocks": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, _P, _U64, _P, _P]),
     "b2rc_launch_count": (_U64, [_P]),
     "b2rc_profile": (C.c_int, [_P, C.c_int]),

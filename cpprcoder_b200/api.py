@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import B2rcError, MODE_ADAPTIVE, MODE_STATIC  # noqa: F401
+from ._lib import B2rcError, MODE_ADAPTIVE, MODE_NAMES, MODE_RANS_BYTE, MODE_RANS_WORD, MODE_STATIC  # noqa: F401
 
 DEFAULT_BLOCK = _lib.DEFAULT_BLOCK
 
@@ -28,8 +28,8 @@ def bound(mode: int, n: int, block: int = DEFAULT_BLOCK) -> int:
     return int(_lib.load().b2rc_bound(mode, n, block))
 
 
-def slot_bytes(n: int) -> int:
-    return int(_lib.load().b2rc_slot_bytes(n))
+def slot_bytes(n: int, mode: int = MODE_STATIC) -> int:
+    return int(_lib.load().b2rc_slot_bytes_for(mode, n))
 
 
 def nblocks(n: int, block: int) -> int:
@@ -148,7 +148,7 @@ class Context:
         """K1 (when needed) + K2.  Returns (slots, slot_stride, sizes, err)."""
         n = src.numel()
         nb = nblocks(n, block)
-        stride = slot_bytes(block)
+        stride = slot_bytes(block, mode)
         dev = src.device
         if slots is None:
             slots = torch.empty(max(nb, 1) * stride, dtype=torch.uint8, device=dev)
@@ -168,9 +168,11 @@ class Context:
         self._check(self.lib.b2rc_k_scan(self.h, _ptr(sizes), nb, _ptr(offsets), _stream()), "b2rc_k_scan")
         return offsets
 
-    def compact(self, slots, stride, sizes, offsets, nb, payload: torch.Tensor, err: torch.Tensor):
-        self._check(self.lib.b2rc_k_compact(self.h, _ptr(slots), stride, _ptr(sizes), _ptr(offsets), nb, _ptr(payload),
-                                            payload.numel(), _ptr(err), _stream()), "b2rc_k_compact")
+    def compact(self, slots, stride, sizes, offsets, nb, payload: torch.Tensor, err: torch.Tensor,
+                mode: int = MODE_STATIC):
+        self._check(self.lib.b2rc_k_compact_for(self.h, mode, _ptr(slots), stride, _ptr(sizes), _ptr(offsets), nb,
+                                                _ptr(payload), payload.numel(), _ptr(err), _stream()),
+                    "b2rc_k_compact_for")
 
     def decode_blocks(self, mode: int, payload: torch.Tensor, payload_len: int, offsets: torch.Tensor, nb: int,
                       dst: torch.Tensor, n: int, block: int = DEFAULT_BLOCK, err: torch.Tensor | None = None):

@@ -47,7 +47,7 @@ def parse(buf) -> Info:
     if buf.size < HEADER + 8:
         raise ValueError("container shorter than its header")
     magic, version, mode, block, flags, total, nblocks = struct.unpack("<IHHIIQQ", buf[:HEADER].tobytes())
-    if magic != MAGIC or version != 1 or mode > 1 or flags != 0 or not block_ok(block):
+    if magic != MAGIC or version != 1 or mode > 3 or flags != 0 or not block_ok(block):
         raise ValueError("bad container header")
     if nblocks != nblocks_of(total, block) or HEADER + 8 * (nblocks + 1) > buf.size:
         raise ValueError("container index does not fit")

@@ -11,6 +11,7 @@
 #include <new>
 
 #include "b2rc_kernels.cuh"
+#include "b2rc_ans.cuh"
 
 using namespace b2rc;
 
@@ -102,6 +103,14 @@ int grow(b2rc_ctx* ctx, T*& p, size_t& cap, size_t want_bytes)
 bool block_ok(u32 block)
 {
     return block >= B2RC_MIN_BLOCK && block <= B2RC_MAX_BLOCK && (block % 64u) == 0;
+}
+bool mode_ok(int mode)
+{
+    return mode == B2RC_MODE_STATIC || mode == B2RC_MODE_ADAPTIVE || mode == B2RC_MODE_RANS_WORD;
+}
+bool is_ans(int mode)
+{
+    return mode == B2RC_MODE_RANS_BYTE || mode == B2RC_MODE_RANS_WORD;
 }
 bool aligned16(const void* p)
 {
@@ -227,6 +236,16 @@ uint64_t b2rc_slot_bytes(uint32_t n)
     return (s + 127) & ~127ull;
 }
 
+uint64_t b2rc_slot_bytes_for(int mode, uint32_t n)
+{
+    if(is_ans(mode)) {
+        // header + the flushed states + at most one 16-bit word per symbol (the word coder
+        // emits one for EVERY symbol of a block that holds a single distinct byte)
+        return ((u64)ANS_HDR + 32u + 2ull * n + 15u) & ~15ull;
+    }
+    return b2rc_slot_bytes(n);
+}
+
 uint64_t b2rc_nblocks(uint64_t n, uint32_t block_size)
 {
     return block_size ? (n + block_size - 1) / block_size : 0;
@@ -234,7 +253,6 @@ uint64_t b2rc_nblocks(uint64_t n, uint32_t block_size)
 
 uint64_t b2rc_bound(int mode, uint64_t n, uint32_t block_size)
 {
-    (void)mode;
     if(!block_ok(block_size)) {
         return 0;
     }
@@ -243,7 +261,7 @@ uint64_t b2rc_bound(int mode, uint64_t n, uint32_t block_size)
         return index_bytes(0);
     }
     const u64 last = n - (nb - 1) * block_size;
-    return index_bytes(nb) + (nb - 1) * b2rc_slot_bytes(block_size) + b2rc_slot_bytes((u32)last);
+    return index_bytes(nb) + (nb - 1) * b2rc_slot_bytes_for(mode, block_size) + b2rc_slot_bytes_for(mode, (u32)last);
 }
 
 int b2rc_ctx_create(int device, b2rc_ctx** out)
@@ -316,6 +334,13 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         }
         if(rc == B2RC_OK) {
             rc = set_smem_limits(ctx);
+        }
+        if(rc == B2RC_OK) {
+            k_ans_magic_init<<<(ANS_MAGIC_N + 255u) / 256u, 256, 0, ctx->stream>>>();
+            if(!cuda_ok(ctx, cudaGetLastError(), "k_ans_magic_init") ||
+               !cuda_ok(ctx, cudaStreamSynchronize(ctx->stream), "k_ans_magic_init")) {
+                rc = B2RC_E_CUDA;
+            }
         }
     } while(0);
     if(rc != B2RC_OK) {
@@ -428,7 +453,7 @@ int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, u
     memcpy(h, src, sizeof h);
     const u32 version = h[1] & 0xFFFFu, md = h[1] >> 16;
     const u64 tot = (u64)h[4] | ((u64)h[5] << 32), nb = (u64)h[6] | ((u64)h[7] << 32);
-    if(h[0] != 0x43523242u || version != 1u || md > 1u || !block_ok(h[2]) || h[3] != 0u) {
+    if(h[0] != 0x43523242u || version != 1u || !mode_ok((int)md) || !block_ok(h[2]) || h[3] != 0u) {
         return B2RC_E_CORRUPT;
     }
     if(nb != b2rc_nblocks(tot, h[2]) || nb > (n - B2RC_HEADER_BYTES) / 8 - 1) {
@@ -447,6 +472,51 @@ int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, u
         *nblocks = nb;
     }
     return B2RC_OK;
+}
+
+// ------------------------------------------------------------ rANS launches --
+static int ans_encode_blocks(b2rc_ctx* ctx, int mode, u32 block, const u8* d_src, u64 n, u8* d_slots, u64 stride,
+                             u32* d_sizes, int* d_err, cudaStream_t st)
+{
+    const u64 nb = b2rc_nblocks(n, block);
+    if(nb == 0) {
+        return B2RC_OK;
+    }
+    DeviceGuard g(ctx->device);
+    u64 grid = (nb + HIST_WARPS - 1) / HIST_WARPS;
+    if(grid > 148ull * 16) {
+        grid = 148ull * 16;
+    }
+    {
+        KernelTimer kt(ctx, B2RC_K_HISTOGRAM, st);
+        k_ans_model<(int)ANS_WORD_BITS><<<(unsigned)grid, HIST_WARPS * 32, 0, st>>>(d_src, n, block, nb, d_slots, stride);
+        const int rc = launch_check(ctx, "k_ans_model");
+        if(rc != B2RC_OK) {
+            return rc;
+        }
+    }
+    EncArgs a;
+    a.src = d_src;
+    a.n = n;
+    a.block = block;
+    a.nblocks = nb;
+    a.freq16 = nullptr;
+    a.slots = d_slots;
+    a.slot_stride = stride;
+    a.sizes = d_sizes;
+    a.err = d_err;
+    (void)mode;
+    KernelTimer kt(ctx, B2RC_K_ENCODE, st);
+    k_ans_enc_word<<<(unsigned)((nb + 3) / 4), 32, 0, st>>>(a);
+    return launch_check(ctx, "k_ans_enc_word");
+}
+
+static int ans_decode_blocks(b2rc_ctx* ctx, int mode, const DecArgs& a, cudaStream_t st)
+{
+    (void)mode;
+    KernelTimer kt(ctx, B2RC_K_DECODE, st);
+    k_ans_dec_word<<<(unsigned)((a.nblocks + 3) / 4), 32, ANS_DEC_WORD_SMEM, st>>>(a);
+    return launch_check(ctx, "k_ans_dec_word");
 }
 
 // ------------------------------------------------------------ kernel doors --
@@ -476,10 +546,14 @@ int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
                          const uint16_t* d_freq16, uint8_t* d_slots, uint64_t slot_stride, uint32_t* d_sizes,
                          int* d_err, void* cuda_stream)
 {
-    if(!ctx || !d_src || !d_slots || !d_sizes || !d_err || (mode != B2RC_MODE_STATIC && mode != B2RC_MODE_ADAPTIVE) ||
-       !block_ok(block_size) || !aligned16(d_src) || !aligned16(d_slots) || (slot_stride & 15u) ||
-       slot_stride < b2rc_slot_bytes(block_size)) {
+    if(!ctx || !d_src || !d_slots || !d_sizes || !d_err || !mode_ok(mode) || !block_ok(block_size) ||
+       !aligned16(d_src) || !aligned16(d_slots) || (slot_stride & 15u) ||
+       slot_stride < b2rc_slot_bytes_for(mode, block_size) || slot_stride > 0xFFFFFFF0ull) {
         return B2RC_E_ARG;
+    }
+    if(is_ans(mode)) {
+        return ans_encode_blocks(ctx, mode, block_size, d_src, n, d_slots, slot_stride, d_sizes, d_err,
+                                 (cudaStream_t)cuda_stream);
     }
     const bool wide = block_size > 65536u;
     if(mode == B2RC_MODE_STATIC && !wide && (!d_freq16 || !aligned16(d_freq16))) {
@@ -541,7 +615,16 @@ int b2rc_k_compact(b2rc_ctx* ctx, const uint8_t* d_slots, uint64_t slot_stride, 
                    const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_payload, uint64_t payload_cap, int* d_err,
                    void* cuda_stream)
 {
-    if(!ctx || !d_slots || !d_sizes || !d_offsets || !d_payload || !d_err || !aligned16(d_slots) || (slot_stride & 15u)) {
+    return b2rc_k_compact_for(ctx, B2RC_MODE_STATIC, d_slots, slot_stride, d_sizes, d_offsets, nblocks, d_payload,
+                              payload_cap, d_err, cuda_stream);
+}
+
+int b2rc_k_compact_for(b2rc_ctx* ctx, int mode, const uint8_t* d_slots, uint64_t slot_stride, const uint32_t* d_sizes,
+                       const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_payload, uint64_t payload_cap,
+                       int* d_err, void* cuda_stream)
+{
+    if(!ctx || !mode_ok(mode) || !d_slots || !d_sizes || !d_offsets || !d_payload || !d_err || !aligned16(d_slots) ||
+       (slot_stride & 15u)) {
         return B2RC_E_ARG;
     }
     if(nblocks == 0) {
@@ -554,8 +637,13 @@ int b2rc_k_compact(b2rc_ctx* ctx, const uint8_t* d_slots, uint64_t slot_stride, 
         grid = 148ull * 8;
     }
     KernelTimer kt(ctx, B2RC_K_COMPACT, st);
-    k_compact<<<(unsigned)grid, COMPACT_THREADS, 0, st>>>(d_slots, slot_stride, d_sizes, d_offsets, nblocks, d_payload,
-                                                          payload_cap, d_err);
+    if(is_ans(mode)) {
+        k_compact_split<<<(unsigned)grid, COMPACT_THREADS, 0, st>>>(d_slots, slot_stride, d_sizes, d_offsets, nblocks,
+                                                                    d_payload, payload_cap, d_err, ANS_HDR);
+    } else {
+        k_compact<<<(unsigned)grid, COMPACT_THREADS, 0, st>>>(d_slots, slot_stride, d_sizes, d_offsets, nblocks,
+                                                              d_payload, payload_cap, d_err);
+    }
     return launch_check(ctx, "k_compact");
 }
 
@@ -563,9 +651,9 @@ int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
                          uint64_t payload_len, const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n,
                          int* d_err, void* cuda_stream)
 {
-    if(!ctx || !d_payload || !d_offsets || !d_dst || !d_err || (mode != B2RC_MODE_STATIC && mode != B2RC_MODE_ADAPTIVE) ||
-       !block_ok(block_size) || !aligned16(d_dst) || ((uintptr_t)d_offsets & 7u) ||
-       nblocks != b2rc_nblocks(n, block_size)) {
+    if(!ctx || !d_payload || !d_offsets || !d_dst || !d_err || !mode_ok(mode) || !block_ok(block_size) ||
+       !aligned16(d_dst) || ((uintptr_t)d_offsets & 7u) || nblocks != b2rc_nblocks(n, block_size) ||
+       (mode == B2RC_MODE_RANS_WORD && ((uintptr_t)d_payload & 1u))) {
         return B2RC_E_ARG;
     }
     if(nblocks == 0) {
@@ -582,6 +670,9 @@ int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     a.dst = d_dst;
     a.n = n;
     a.err = d_err;
+    if(is_ans(mode)) {
+        return ans_decode_blocks(ctx, mode, a, st);
+    }
     const bool wide = block_size > 65536u;
     const unsigned grid = (unsigned)((nblocks + 31) / 32);
     KernelTimer kt(ctx, B2RC_K_DECODE, st);
@@ -601,8 +692,8 @@ int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
 int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
                        uint8_t* d_dst, uint64_t dst_cap, uint64_t* out_n, void* cuda_stream)
 {
-    if(!ctx || !d_dst || (n && !d_src) || (mode != B2RC_MODE_STATIC && mode != B2RC_MODE_ADAPTIVE) ||
-       !block_ok(block_size) || !aligned16(d_src) || !aligned16(d_dst)) {
+    if(!ctx || !d_dst || (n && !d_src) || !mode_ok(mode) || !block_ok(block_size) || !aligned16(d_src) ||
+       !aligned16(d_dst)) {
         return B2RC_E_ARG;
     }
     const u64 nb = b2rc_nblocks(n, block_size);
@@ -615,7 +706,7 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
     }
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const u64 stride = b2rc_slot_bytes(block_size);
+    const u64 stride = b2rc_slot_bytes_for(mode, block_size);
     int rc;
     if((rc = grow(ctx, ctx->slots, ctx->slots_cap, (size_t)(nb * stride))) != B2RC_OK ||
        (rc = grow(ctx, ctx->sizes, ctx->sizes_cap, (size_t)(nb * 4 + 16))) != B2RC_OK) {
@@ -639,9 +730,9 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
                          (u32)mode, block_size, n, st)) != B2RC_OK) {
         return rc;
     }
-    if(nb && (rc = b2rc_k_compact(ctx, ctx->slots, stride, ctx->sizes,
-                                  reinterpret_cast<const u64*>(d_dst + B2RC_HEADER_BYTES), nb, d_dst + idx,
-                                  dst_cap - idx, ctx->d_err, st)) != B2RC_OK) {
+    if(nb && (rc = b2rc_k_compact_for(ctx, mode, ctx->slots, stride, ctx->sizes,
+                                      reinterpret_cast<const u64*>(d_dst + B2RC_HEADER_BYTES), nb, d_dst + idx,
+                                      dst_cap - idx, ctx->d_err, st)) != B2RC_OK) {
         return rc;
     }
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -739,7 +830,7 @@ Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block)
 int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src, uint64_t n, uint8_t* dst,
                 uint64_t dst_cap, uint64_t* out_n)
 {
-    if(!ctx || !dst || (n && !src) || (mode != B2RC_MODE_STATIC && mode != B2RC_MODE_ADAPTIVE) || !block_ok(block_size)) {
+    if(!ctx || !dst || (n && !src) || !mode_ok(mode) || !block_ok(block_size)) {
         return B2RC_E_ARG;
     }
     DeviceGuard g(ctx->device);
@@ -753,7 +844,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     if(dst_cap < idx) {
         return B2RC_E_DST_SMALL;
     }
-    const u64 stride = b2rc_slot_bytes(block_size);
+    const u64 stride = b2rc_slot_bytes_for(mode, block_size);
     const bool need_hist = mode == B2RC_MODE_STATIC && block_size <= 65536u;
     int rc;
     if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
@@ -798,8 +889,8 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
             return rc;
         }
         CK(cudaEventRecord(ctx->scan_done[c], st));
-        if((rc = b2rc_k_compact(ctx, ctx->slots + b0 * stride, stride, ctx->sizes + b0, d_offsets + b0, b1 - b0,
-                                d_payload, bound - idx, ctx->d_err, st)) != B2RC_OK) {
+        if((rc = b2rc_k_compact_for(ctx, mode, ctx->slots + b0 * stride, stride, ctx->sizes + b0, d_offsets + b0,
+                                    b1 - b0, d_payload, bound - idx, ctx->d_err, st)) != B2RC_OK) {
             return rc;
         }
         CK(cudaMemcpyAsync(ctx->h_ends + c + 1, ctx->d_ends + c + 1, 8, cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,372 @@
+// b2rc_ans.cuh -- the sm_100a kernels of the block rANS coder (cppans::rANS of the
+// reference's cppans.h), on the same block framework as the
+// range coder: same container, same scan, one payload per block that is byte for byte
+// what the reference emits for that block.
+//
+//   A1  k_ans_model<BITS>   count + cumulative + normalize     (cppans.h:102-177)
+//   A2  k_ans_enc_word      rANS::encode_simd                   (cppans.h:567-607)
+//   A3  k_ans_dec_word      rANS::decode_simd                   (cppans.h:609-649)
+//   A4  k_compact_split     header + tail-aligned coded bytes -> contiguous payload
+//
+// Mapping of the word variant: the reference interleaves EIGHT rANS states per stream so
+// that SSE can step four at a time; here the eight states of a block are eight LANES, a
+// warp carries four blocks, and the only communication is the one the format demands --
+// who emits / refills in this round, in lane order -- which is a ballot and a popcount.
+// That is eight times the parallelism per block the range coder offers, and no carries.
+//
+// Slot layout while encoding: the model kernel leaves the 1032-byte header (u32 size,
+// u32 cum[257]) at the START of the block's slot; the coder writes its words from the END
+// of the slot downwards, as the reference writes from the end of dst (cppans.h:591);
+// k_compact_split joins the two pieces.
+#pragma once
+#include "b2rc_kernels.cuh"
+
+namespace b2rc
+{
+constexpr u32 ANS_HDR = 1032u;          // 258 x u32 (cppans.h:598-604)
+constexpr u32 ANS_WORD_BITS = 12u;      // rANS::WordScaleBits (cppans.h:31)
+constexpr u32 ANS_BYTE_BITS = 14u;      // rANS::ProbBits      (cppans.h:27)
+constexpr u32 ANS_WORD_LOW = 1u << 16;  // rANS::WordLowBounds (cppans.h:30)
+constexpr u32 ANS_MAGIC_N = (1u << ANS_BYTE_BITS) + 1u;
+
+// reciprocals for rc_div by every frequency a normalised model can hold; one table for
+// the whole device (64 KiB, L1/L2 resident), filled once per context
+__device__ u32 g_ans_magic[ANS_MAGIC_N];
+__global__ void k_ans_magic_init()
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < ANS_MAGIC_N) {
+        g_ans_magic[i] = rc_magic(i);
+    }
+}
+
+__device__ __forceinline__ u32 lds8(u32 a)
+{
+    u32 v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// little-endian u32 / u16 at a 2-byte aligned address
+__device__ __forceinline__ u32 ld32_a2(const u8* p)
+{
+    const u16* q = reinterpret_cast<const u16*>(p);
+    return (u32)__ldg(q) | ((u32)__ldg(q + 1) << 16);
+}
+
+// ======================================================================== A1 ==
+// One warp per block: exact byte counts (as K1, without its 16-bit scaling), then the
+// reference's normalize -- scale the cumulative table to 2^BITS, and wherever a symbol
+// that occurs was squeezed to nothing, take one unit from the narrowest slice wider than
+// one (first such slice on ties), sliding the boundaries in between (cppans.h:138-177).
+// The repair loop runs in the reference's order; each repair is a warp-wide arg-min.
+template <int BITS>
+__global__ void __launch_bounds__(HIST_WARPS * 32) k_ans_model(const u8* src, u64 n, u32 block, u64 nblocks, u8* slots,
+                                                               u64 slot_stride)
+{
+    __shared__ u32 bins[HIST_WARPS][256];
+    __shared__ u32 cums[HIST_WARPS][264];
+    const u32 lane = lane_id();
+    const u32 warp = threadIdx.x >> 5;
+    u32* h = bins[warp];
+    u32* sc = cums[warp];
+    for(u64 b = (u64)blockIdx.x * HIST_WARPS + warp; b < nblocks; b += (u64)gridDim.x * HIST_WARPS) {
+        const u64 lo = b * (u64)block;
+        const u32 len = (u32)((n - lo < block) ? (n - lo) : block);
+        hist_block(h, src + lo, len, lane);
+        u32 f[8], sum = 0;
+#pragma unroll
+        for(int k = 0; k < 8; ++k) {
+            f[k] = h[8u * lane + k];
+            sum += f[k];
+        }
+        u32 inc = sum;
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(FULL, inc, d);
+            if(lane >= (u32)d) {
+                inc += t;
+            }
+        }
+        u32 run = inc - sum;
+        if(lane == 0) {
+            sc[0] = 0;
+        }
+#pragma unroll
+        for(int k = 0; k < 8; ++k) {
+            run += f[k];
+            sc[8u * lane + k + 1u] = (u32)((((u64)run) << BITS) / len);
+        }
+        __syncwarp();
+        for(u32 i = 0; i < 256u; ++i) {
+            if(h[i] == 0u || sc[i + 1u] != sc[i]) {  // same words for every lane: uniform
+                continue;
+            }
+            u32 key = FULL;
+            u32 prev = sc[8u * lane];
+#pragma unroll
+            for(int k = 0; k < 8; ++k) {
+                const u32 nx = sc[8u * lane + k + 1u];
+                const u32 w = nx - prev;
+                prev = nx;
+                const u32 cand = (w << 8) | (8u * lane + k);
+                if(w > 1u && cand < key) {
+                    key = cand;
+                }
+            }
+            key = __reduce_min_sync(FULL, key);
+            if(key == FULL) {
+                continue;
+            }
+            const u32 donor = key & 255u;
+            __syncwarp();
+            if(donor < i) {
+                for(u32 j = donor + 1u + lane; j <= i; j += 32u) {
+                    sc[j] -= 1u;
+                }
+            } else {
+                for(u32 j = i + 1u + lane; j <= donor; j += 32u) {
+                    sc[j] += 1u;
+                }
+            }
+            __syncwarp();
+        }
+        u32* hdr = reinterpret_cast<u32*>(slots + b * slot_stride);
+        for(u32 w = lane; w < 258u; w += 32u) {
+            hdr[w] = w == 0u ? len : sc[w - 1u];
+        }
+        __syncwarp();
+    }
+}
+
+// ======================================================================== A2 ==
+// Word-variant encode: lane j of an 8-lane group is state j of its block and takes the
+// symbols at positions p with p & 7 == j, last round first (cppans.h:591-594).  A state
+// emits its low 16 bits when it reaches freq << 20 -- a u32 product in the reference
+// (wordEncPut, cppans.h:357), so a symbol that owns the whole scale emits every time --
+// and within a round the states emit in descending lane order at descending addresses.
+// Symbol, (start, freq) and the reciprocal are looked up ahead of the state chain.
+__global__ void __launch_bounds__(32) k_ans_enc_word(EncArgs a)
+{
+    __shared__ u32 tab[4][256];
+    const u32 lane = lane_id(), grp = lane >> 3, j = lane & 7u;
+    const u64 b = (u64)blockIdx.x * 4u + grp;
+    const bool live = b < a.nblocks;
+    const u64 lo = live ? b * (u64)a.block : 0ull;
+    const u32 len = live ? (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block) : 0u;
+    u8* slot = a.slots + (live ? b : 0ull) * a.slot_stride;
+    if(live) {
+        const u32* hdr = reinterpret_cast<const u32*>(slot);
+        for(u32 s = j; s < 256u; s += 8u) {
+            const u32 c0 = hdr[1u + s], c1 = hdr[2u + s];
+            tab[grp][s] = (c0 << 16) | (c1 - c0);
+        }
+    }
+    __syncwarp();
+    const u32 tb = smem_addr(tab[grp]);
+    const u8* __restrict__ sp = a.src + lo;
+    const u32 gshift = grp * 8u;
+    u32 x = ANS_WORD_LOW;                // wordEncInit (cppans.h:336-339)
+    u32 w = (u32)a.slot_stride;          // write cursor, bytes from the slot start
+    const u32 rmax = __reduce_max_sync(FULL, (len + 7u) >> 3);
+    // symbols are fetched two quads of rounds ahead of their use
+    u32 sA[4], sB[4];
+#pragma unroll
+    for(int q = 0; q < 4; ++q) {
+        const s32 pa = 8 * ((s32)rmax - 1 - q) + (s32)j, pb = pa - 32;
+        sA[q] = (pa >= 0 && (u32)pa < len) ? (u32)__ldg(sp + pa) : 0u;
+        sB[q] = (pb >= 0 && (u32)pb < len) ? (u32)__ldg(sp + pb) : 0u;
+    }
+    for(s32 r = (s32)rmax; r > 0; r -= 4) {
+        u32 sC[4], e[4], mg[4];
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+            const s32 pc = 8 * (r - 9 - q) + (s32)j;
+            sC[q] = (pc >= 0 && (u32)pc < len) ? (u32)__ldg(sp + pc) : 0u;
+        }
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+            e[q] = lds32(tb + 4u * sA[q]);
+        }
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+            mg[q] = __ldg(&g_ans_magic[e[q] & 0xFFFFu]);
+        }
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+            const s32 p = 8 * (r - 1 - q) + (s32)j;
+            const bool act = p >= 0 && (u32)p < len;
+            const u32 f = e[q] & 0xFFFFu, start = e[q] >> 16;
+            const bool emit = act && ((f << 20) <= x);
+            const u32 g = (__ballot_sync(FULL, emit) >> gshift) & 0xFFu;
+            if(emit) {
+                const u32 at = w - 2u * (__popc(g >> (j + 1u)) + 1u);
+                *reinterpret_cast<u16*>(slot + at) = (u16)x;
+                x >>= 16;
+            }
+            w -= 2u * __popc(g);
+            if(act) {
+                const u32 quo = rc_div(x, f, mg[q]);
+                x = (quo << ANS_WORD_BITS) + (x - quo * f) + start;  // cppans.h:363
+            }
+        }
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+            sA[q] = sB[q];
+            sB[q] = sC[q];
+        }
+    }
+    if(live) {
+        // wordEncFlush, states 7 .. 0 at descending addresses (cppans.h:595-597)
+        const u32 at = w - 32u + 4u * j;
+        *reinterpret_cast<u16*>(slot + at) = (u16)x;
+        *reinterpret_cast<u16*>(slot + at + 2u) = (u16)(x >> 16);
+        if(j == 0u) {
+            a.sizes[b] = ANS_HDR + ((u32)a.slot_stride - (w - 32u));
+        }
+    }
+}
+
+// ======================================================================== A3 ==
+// Word-variant decode.  Two tables per block in shared memory: slot -> symbol (4096 x u8,
+// initSymbols' slot2symbol_, cppans.h:342-351) and symbol -> (start, freq); freq and bias
+// of a slot follow from its symbol, so the reference's 16 KiB WordSlot array is not kept
+// and 11 warps fit an SM instead of 3.  After each round of eight symbols the states below
+// 2^16 take the next u16s of the stream in lane order (simdDecRenorm, cppans.h:443-488).
+constexpr u32 ANS_DEC_WORD_SMEM = 4u * (4096u + 1024u);
+
+__global__ void __launch_bounds__(32) k_ans_dec_word(DecArgs a)
+{
+    extern __shared__ __align__(16) u8 ans_sm[];
+    const u32 lane = lane_id(), grp = lane >> 3, j = lane & 7u;
+    const u64 b = (u64)blockIdx.x * 4u + grp;
+    const bool has = b < a.nblocks;
+    const u64 lo = has ? b * (u64)a.block : 0ull;
+    const u32 n_b = has ? (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block) : 0u;
+    u8* s2s = ans_sm + grp * 5120u;
+    u32* st = reinterpret_cast<u32*>(s2s + 4096u);
+    const u8* pay = a.payload;
+    u32 paylen = 0;
+    bool ok = false;
+    if(has) {
+        const u64 o0 = a.offsets[b], o1 = a.offsets[b + 1];
+        if(o0 <= o1 && o1 <= a.payload_len && ((o0 | o1) & 1u) == 0u && o1 - o0 >= ANS_HDR + 32u &&
+           o1 - o0 < 0xFFFFFFF0ull) {
+            pay = a.payload + o0;
+            paylen = (u32)(o1 - o0);
+            ok = ld32_a2(pay) == n_b;  // the container, not the payload, says how long block b is
+        }
+    }
+    if(ok) {
+        for(u32 s = j; s < 256u; s += 8u) {
+            const u32 c0 = ld32_a2(pay + 4u + 4u * s), c1 = ld32_a2(pay + 8u + 4u * s);
+            const bool sane = c0 <= c1 && c1 <= (1u << ANS_WORD_BITS) && (s != 0u || c0 == 0u) &&
+                              (s != 255u || c1 == (1u << ANS_WORD_BITS));
+            ok = ok && sane;
+            st[s] = c0 | ((c1 - c0) << 16);
+            if(sane) {
+                for(u32 k = c0; k < c1; ++k) {
+                    s2s[k] = (u8)s;
+                }
+            }
+        }
+    }
+    const u32 gshift = grp * 8u;
+    ok = ((__ballot_sync(FULL, ok) >> gshift) & 0xFFu) == 0xFFu;
+    if(has && !ok && j == 0u) {
+        atomicOr(a.err, ERR_CORRUPT);
+    }
+    __syncwarp();
+    const u32 want = ok ? n_b : 0u;
+    const u32 full = want >> 3;
+    const u32 sb = smem_addr(s2s), tb = smem_addr(st);
+    u32 x = ok ? ld32_a2(pay + ANS_HDR + 4u * j) : 0u;  // simdDecInit (cppans.h:405-409)
+    u32 rp = ANS_HDR + 32u;
+    u8* out = a.dst + lo + j;
+    const u32 below = (1u << j) - 1u;
+    bool bad = false;
+    const u32 rmax = __reduce_max_sync(FULL, full);
+    for(u32 r = 0; r < rmax; ++r) {
+        const bool act = r < full;
+        const u32 slt = x & ((1u << ANS_WORD_BITS) - 1u);
+        const u32 s = lds8(sb + slt);
+        const u32 e = lds32(tb + 4u * s);
+        u32 xn = (e >> 16) * (x >> ANS_WORD_BITS) + slt - (e & 0xFFFFu);  // simdDecSym (cppans.h:412-440)
+        if(act) {
+            out[8u * r] = (u8)s;
+        }
+        const bool need = act && xn < ANS_WORD_LOW;
+        const u32 g = (__ballot_sync(FULL, need) >> gshift) & 0xFFu;
+        if(need) {
+            const u32 at = rp + 2u * __popc(g & below);
+            u32 wv = 0;
+            if(at + 2u <= paylen) {
+                wv = __ldg(reinterpret_cast<const u16*>(pay + at));
+            } else {
+                bad = true;
+            }
+            xn = (xn << 16) | wv;
+        }
+        rp += 2u * __popc(g);
+        if(act) {
+            x = xn;
+        }
+    }
+    // the last (size & 7) symbols: one more symbol from states 0.. without a refill (cppans.h:643-647)
+    if(8u * full + j < want) {
+        out[8u * full] = (u8)lds8(sb + (x & ((1u << ANS_WORD_BITS) - 1u)));
+    }
+    if(bad) {
+        atomicOr(a.err, ERR_CORRUPT);
+    }
+}
+
+// ======================================================================== A4 ==
+// Copies n bytes with a whole CTA; any alignment on either side.  Destination-aligned
+// 4-byte words are assembled from the two aligned source words they straddle.
+__device__ __forceinline__ void cta_copy(u8* d, const u8* s, u32 n)
+{
+    u32 head = (u32)((4u - ((uintptr_t)d & 3u)) & 3u);
+    if(head > n) {
+        head = n;
+    }
+    if(threadIdx.x < head) {
+        d[threadIdx.x] = s[threadIdx.x];
+    }
+    const u32 nwords = (n - head) >> 2;
+    u32* dw = reinterpret_cast<u32*>(d + head);
+    const u8* s0 = s + head;
+    const u32 mis = (u32)((uintptr_t)s0 & 3u);
+    const u32* sw = reinterpret_cast<const u32*>(s0 - mis);
+    const u32 sh = mis * 8u;
+    for(u32 k = threadIdx.x; k < nwords; k += blockDim.x) {
+        const u32 a0 = __ldg(sw + k);
+        const u32 a1 = sh ? __ldg(sw + k + 1) : 0u;
+        dw[k] = __funnelshift_r(a0, a1, sh);
+    }
+    const u32 done = head + 4u * nwords;
+    if(done + threadIdx.x < n) {
+        d[done + threadIdx.x] = s[done + threadIdx.x];
+    }
+}
+
+// payload b = [head_bytes from the slot start][sizes[b] - head_bytes from the slot end]
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact_split(const u8* slots, u64 slot_stride, const u32* sizes,
+                                                                   const u64* offsets, u64 nblocks, u8* payload,
+                                                                   u64 payload_cap, int* err, u32 head_bytes)
+{
+    for(u64 b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const u8* s = slots + b * slot_stride;
+        const u32 len = sizes[b];
+        const u64 off = offsets[b];
+        if(off + len > payload_cap || len < head_bytes) {
+            if(threadIdx.x == 0) {
+                atomicOr(err, len < head_bytes ? ERR_SLOT_OVERFLOW : ERR_DST_SMALL);
+            }
+            continue;
+        }
+        cta_copy(payload + off, s, head_bytes);
+        cta_copy(payload + off + head_bytes, s + slot_stride - (len - head_bytes), len - head_bytes);
+    }
+}
+
+}  // namespace b2rc

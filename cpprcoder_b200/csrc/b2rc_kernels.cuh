@@ -1111,6 +1111,48 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
 // warp-private shared-memory bins.  For such blocks RangeEncoder::count never halves
 // except when all 65536 bytes are equal, where it ends at 0x8000.
 constexpr int HIST_WARPS = 8;
+
+// Exact byte counts of one block into 256 warp-private shared-memory bins (one warp).
+__device__ __forceinline__ void hist_block(u32* h, const u8* p, u32 len, u32 lane)
+{
+#pragma unroll
+    for(int k = 0; k < 8; ++k) {
+        h[lane + 32 * k] = 0;
+    }
+    __syncwarp();
+    const u32 vec = len & ~15u;
+    // four 16-byte loads in flight per lane before the first bin is touched: the kernel was
+    // stalled on load latency (long scoreboard), not on the shared-memory atomics
+    u32 off = lane * 16u;
+    for(; off + 3u * 512u < vec; off += 4u * 512u) {
+        uint4 v[4];
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+            v[q] = __ldg(reinterpret_cast<const uint4*>(p + off + q * 512u));
+        }
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+            const u32 w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+            for(int k = 0; k < 16; ++k) {
+                atomicAdd(&h[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu], 1u);
+            }
+        }
+    }
+    for(; off < vec; off += 512u) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + off));
+        const u32 w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for(int k = 0; k < 16; ++k) {
+            atomicAdd(&h[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu], 1u);
+        }
+    }
+    for(u32 o2 = vec + lane; o2 < len; o2 += 32u) {
+        atomicAdd(&h[p[o2]], 1u);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(HIST_WARPS * 32) k_hist(const u8* src, u64 n, u32 block, u64 nblocks, u16* freq16)
 {
     __shared__ u32 bins[HIST_WARPS][256];
@@ -1118,45 +1160,9 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_hist(const u8* src, u64 n, 
     const u32 warp = threadIdx.x >> 5;
     u32* h = bins[warp];
     for(u64 b = (u64)blockIdx.x * HIST_WARPS + warp; b < nblocks; b += (u64)gridDim.x * HIST_WARPS) {
-#pragma unroll
-        for(int k = 0; k < 8; ++k) {
-            h[lane + 32 * k] = 0;
-        }
-        __syncwarp();
         const u64 lo = b * (u64)block;
         const u32 len = (u32)((n - lo < block) ? (n - lo) : block);
-        const u8* p = src + lo;
-        const u32 vec = len & ~15u;
-        // four 16-byte loads in flight per lane before the first bin is touched: the kernel was
-        // stalled on load latency (long scoreboard), not on the shared-memory atomics
-        u32 off = lane * 16u;
-        for(; off + 3u * 512u < vec; off += 4u * 512u) {
-            uint4 v[4];
-#pragma unroll
-            for(int q = 0; q < 4; ++q) {
-                v[q] = __ldg(reinterpret_cast<const uint4*>(p + off + q * 512u));
-            }
-#pragma unroll
-            for(int q = 0; q < 4; ++q) {
-                const u32 w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-                for(int k = 0; k < 16; ++k) {
-                    atomicAdd(&h[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu], 1u);
-                }
-            }
-        }
-        for(; off < vec; off += 512u) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + off));
-            const u32 w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for(int k = 0; k < 16; ++k) {
-                atomicAdd(&h[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu], 1u);
-            }
-        }
-        for(u32 off = vec + lane; off < len; off += 32u) {
-            atomicAdd(&h[p[off]], 1u);
-        }
-        __syncwarp();
+        hist_block(h, src + lo, len, lane);
         u32 f[8];
 #pragma unroll
         for(int k = 0; k < 8; ++k) {

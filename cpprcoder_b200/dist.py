@@ -87,7 +87,7 @@ def encode_shard(ctx, mode: int, src_shard: torch.Tensor, n_total: int, block: i
     offsets = global_offsets(all_sizes)
     total_local = int((offsets[blk_hi] - offsets[blk_lo]).item())
     payload = torch.empty(max(total_local, 1) + 16, dtype=torch.uint8, device=src_shard.device)
-    ctx.compact(slots, stride, sizes, local_offsets, nb, payload, err)
+    ctx.compact(slots, stride, sizes, local_offsets, nb, payload, err, mode)
     return Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, payload, total_local, local_offsets, offsets, err)
 
 

@@ -36,6 +36,11 @@ extern "C" {
 
 #define B2RC_MODE_STATIC 0   /* RangeEncoder<T>          cpprcoder.h:321-619 */
 #define B2RC_MODE_ADAPTIVE 1 /* AdaptiveRangeEncoder/Decoder<T>  cpprcoder.h:626-940 */
+/* The sibling static rANS coder of the reference (cppans.h), on the same container:
+ * payload = u32 LE size, 257 x u32 LE normalised cumulative counts, coded bytes -- what
+ * cppans::rANS leaves at the END of its dst buffer (cppans.h:521-529, :598-605). */
+#define B2RC_MODE_RANS_BYTE 2 /* rANS::encode / ::decode            cppans.h:497-564 (not built yet) */
+#define B2RC_MODE_RANS_WORD 3 /* rANS::encode_simd / ::decode_simd  cppans.h:567-649 */
 
 #define B2RC_DEFAULT_BLOCK 65536u
 #define B2RC_MIN_BLOCK 64u          /* block_size must be a multiple of 64 ... */
@@ -69,6 +74,9 @@ const char* b2rc_last_cuda_error(const b2rc_ctx* ctx);
  * b2rc_slot_bytes: staging slot (and per-block payload bound) for a block of n bytes. */
 uint64_t b2rc_bound(int mode, uint64_t n, uint32_t block_size);
 uint64_t b2rc_slot_bytes(uint32_t n);
+/* The same for any mode (the rANS payload bound is 2n + 1064: cppans.h:492-495 and the
+ * word coder's wrap at :357). */
+uint64_t b2rc_slot_bytes_for(int mode, uint32_t n);
 uint64_t b2rc_nblocks(uint64_t n, uint32_t block_size);
 
 /* ---- whole-container calls, HOST pointers (what the C++ drop-in classes call) ----
@@ -101,8 +109,9 @@ int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t b
                      void* cuda_stream);
 /* K2  b2rc_k_encode_blocks: block b's payload -> d_slots + b*slot_stride, its length ->
  *     d_sizes[b].  Static mode with block_size <= 65536 needs d_freq16 from K1; larger
- *     static blocks count inside the kernel (pass NULL).  slot_stride >= b2rc_slot_bytes(block_size),
- *     multiple of 16. */
+ *     static blocks count inside the kernel (pass NULL), and so do the rANS modes (their
+ *     model kernel, cppans.h:504-508, runs as part of this call).
+ *     slot_stride >= b2rc_slot_bytes_for(mode, block_size), multiple of 16. */
 int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
                          const uint16_t* d_freq16, uint8_t* d_slots, uint64_t slot_stride, uint32_t* d_sizes,
                          int* d_err, void* cuda_stream);
@@ -112,6 +121,11 @@ int b2rc_k_scan(b2rc_ctx* ctx, const uint32_t* d_sizes, uint64_t nblocks, uint64
 int b2rc_k_compact(b2rc_ctx* ctx, const uint8_t* d_slots, uint64_t slot_stride, const uint32_t* d_sizes,
                    const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_payload, uint64_t payload_cap, int* d_err,
                    void* cuda_stream);
+/* The same for any mode: rANS slots hold the header at their start and the coded bytes at
+ * their end (the reference codes backwards from the end of dst, cppans.h:515, :591). */
+int b2rc_k_compact_for(b2rc_ctx* ctx, int mode, const uint8_t* d_slots, uint64_t slot_stride, const uint32_t* d_sizes,
+                       const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_payload, uint64_t payload_cap,
+                       int* d_err, void* cuda_stream);
 /* K3  b2rc_k_decode_blocks: payload b = d_payload[d_offsets[b] .. d_offsets[b+1]) -> block b of d_dst
  *     (n bytes in all, 16-byte aligned).  Offsets beyond payload_len mark the block corrupt. */
 int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload,

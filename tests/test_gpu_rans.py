@@ -1,0 +1,220 @@
+"""rANS (cppans::rANS of the reference) on the block framework: the
+CUDA path through the C ABI against the pinned oracle -- bit exact, per block.  `-m gpu`."""
+import json
+
+import numpy as np
+import pytest
+
+from _cases import crafted_stream
+from _oracle import CANTERBURY, GOLDEN, RANS_HEADER, RANS_WORD, Oracle, canterbury, fnv1a64, offsets_of
+from cpprcoder_b200 import container, synth
+
+pytestmark = pytest.mark.gpu
+MODES = [(RANS_WORD, "rans_word")]
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    import torch
+    from cpprcoder_b200 import api
+    built.build_native()
+    assert torch.cuda.is_available()
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def oracle(built):
+    return Oracle.get()
+
+
+@pytest.fixture(scope="module")
+def golden_rans():
+    return json.loads((GOLDEN / "golden_rans.json").read_text())
+
+
+def payloads_of(buf):
+    info = container.parse(buf)
+    return info, [bytes(info.payload(buf, b)) for b in range(info.nblocks)]
+
+
+def assert_blocks_equal(got, want, what):
+    assert len(got) == len(want), what
+    for b, (g, w) in enumerate(zip(got, want)):
+        if g != w:
+            k = next((i for i in range(min(len(g), len(w))) if g[i] != w[i]), min(len(g), len(w)))
+            raise AssertionError(f"{what}: block {b} differs at byte {k} (sizes {len(g)} vs {len(w)})")
+
+
+@pytest.mark.parametrize("name", CANTERBURY)
+def test_canterbury_every_block_is_the_reference_payload(ctx, oracle, golden_rans, name):
+    data = np.frombuffer(canterbury(name), dtype=np.uint8)
+    ent = golden_rans["canterbury"][name]
+    for mode, key in MODES:
+        enc = ctx.encode(mode, data, 65536)
+        info, pays = payloads_of(enc)
+        assert (info.mode, info.block, info.total) == (mode, 65536, data.size)
+        assert [len(p) for p in pays] == ent["blocks64k"][key]["sizes"]
+        assert f"{fnv1a64(b''.join(pays)):016x}" == ent["blocks64k"][key]["cat_fnv"]  # golden = unmodified reference
+        assert_blocks_equal(pays, oracle.encode_blocks(mode, data, 65536), f"{name}/{key}")
+        assert ctx.decode(enc).tobytes() == data.tobytes()
+
+
+def test_single_block_equals_whole_file_reference_output(ctx, golden_rans):
+    for name in ("alice29.txt", "kennedy.xls", "xargs.1"):
+        data = np.frombuffer(canterbury(name), dtype=np.uint8)
+        block = 1 << 20 if data.size <= (1 << 20) else 1 << 21
+        for mode, key in MODES:
+            enc = ctx.encode(mode, data, block)
+            _, pays = payloads_of(enc)
+            assert len(pays) == 1
+            want = golden_rans["canterbury"][name]["whole"][key]
+            assert len(pays[0]) == want["size"] and f"{fnv1a64(pays[0]):016x}" == want["fnv"]
+            assert ctx.decode(enc).tobytes() == data.tobytes()
+
+
+@pytest.mark.parametrize("block,nblocks,ragged", [(65536, 70, 12345), (65536, 33, 0), (4096, 200, 1), (16384, 64, 16383),
+                                                  (64, 300, 7), (1024, 31, 5), (262144, 5, 99999)])
+def test_crafted_streams_match_oracle(ctx, oracle, block, nblocks, ragged):
+    data = crafted_stream(nblocks, block, seed=block + nblocks, ragged=ragged)
+    for mode, key in MODES:
+        enc = ctx.encode(mode, data, block)
+        _, pays = payloads_of(enc)
+        assert_blocks_equal(pays, oracle.encode_blocks(mode, data, block, threads=4), f"crafted {block}/{key}")
+        assert ctx.decode(enc).tobytes() == data.tobytes()
+
+
+def test_edges(ctx, oracle, golden_rans):
+    cases = [b"", b"A", b"AA", b"A" * 7, b"A" * 8, b"A" * 9, b"AB" * 32, b"A" * 65535, b"A" * 65536, b"A" * 65537,
+             b"\xff" * 65536, bytes(range(256)) * 3, b"A" * 60000 + bytes(range(256)), b"AB" * 4097]
+    for d in cases:
+        data = np.frombuffer(d, dtype=np.uint8)
+        for mode, key in MODES:
+            enc = ctx.encode(mode, data, 65536)
+            info, pays = payloads_of(enc)
+            assert info.nblocks == (len(d) + 65535) // 65536
+            assert_blocks_equal(pays, oracle.encode_blocks(mode, data, 65536), f"edge {len(d)}/{key}")
+            assert ctx.decode(enc).tobytes() == d
+    # single-block inputs of the golden file: the reference's own bytes
+    from test_ans_oracle import EDGE
+    for ent in golden_rans["edge"]:
+        if ent["mode"] != "rans_word":
+            continue
+        d = np.frombuffer(EDGE[ent["label"]], dtype=np.uint8)
+        _, pays = payloads_of(ctx.encode(RANS_WORD, d, 65536))
+        assert len(pays[0]) == ent["size"] and f"{fnv1a64(pays[0]):016x}" == ent["fnv"], ent["label"]
+
+
+def test_synthetic_golden_vectors(ctx, golden_rans):
+    for ent in golden_rans["synthetic"]:
+        if ent["mode"] != "rans_word":
+            continue
+        d = synth.GENERATORS[ent["gen"]](ent["n"])
+        enc = ctx.encode(RANS_WORD, d, ent["block"])
+        _, pays = payloads_of(enc)
+        assert [len(p) for p in pays] == ent["sizes"], (ent["gen"], ent["block"])
+        assert f"{fnv1a64(b''.join(pays)):016x}" == ent["cat_fnv"]
+        assert ctx.decode(enc).tobytes() == d.tobytes()
+
+
+def test_decodes_what_the_oracle_encoded(ctx, oracle):
+    # decoder alone: containers assembled on the host from oracle payloads
+    for block, n in [(65536, 65536 * 9 + 4321), (4096, 4096 * 37 + 5), (64, 64 * 50 + 63)]:
+        data = synth.mixed(n)
+        for mode, _ in MODES:
+            pays = oracle.encode_blocks(mode, data, block, threads=4)
+            buf = container.build(mode, block, data.size, pays)
+            assert ctx.decode(buf).tobytes() == data.tobytes()
+
+
+def test_kernel_doors_step_by_step(ctx, oracle):
+    import torch
+    block = 65536
+    data = crafted_stream(41, block, seed=5, ragged=777)
+    n = data.size
+    nb = (n + block - 1) // block
+    src = torch.from_numpy(data).cuda()
+    for mode, key in MODES:
+        slots, stride, sizes, err = ctx.encode_blocks(mode, src, block)
+        # the model kernel left size + normalised cumulative counts at the head of every slot
+        head = slots.view(-1, stride)[:nb, :RANS_HEADER].cpu().numpy().copy().view(np.uint32)
+        for b in (0, 1, nb // 2, nb - 1):
+            blk = data[b * block:(b + 1) * block]
+            _, cum = oracle.rans_model(blk, 12)
+            assert head[b][0] == blk.size and (head[b][1:] == cum).all(), f"model of block {b}"
+        offsets = ctx.scan(sizes, nb)
+        total = int(offsets[nb].item())
+        payload = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+        ctx.compact(slots, stride, sizes, offsets, nb, payload[2:], err, mode)   # a 2-byte aligned destination
+        want = oracle.encode_blocks(mode, data, block, threads=4)
+        assert total == sum(len(p) for p in want)
+        assert payload[2:2 + total].cpu().numpy().tobytes() == b"".join(want)
+        dst = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        pl = payload[2:2 + total + 32]
+        ctx.decode_blocks(mode, pl, total, offsets, nb, dst, n, block, err)
+        torch.cuda.synchronize()
+        assert int(err[0].item()) == 0
+        assert dst.cpu().numpy().tobytes() == data.tobytes()
+
+
+def test_corrupt_payloads_are_rejected(ctx, oracle):
+    from cpprcoder_b200.api import B2rcError
+    data = synth.zipf(65536 * 3 + 100)
+    enc = ctx.encode(RANS_WORD, data, 65536)
+    info = container.parse(enc)
+    base = info.payload_base + int(info.offsets[1])
+    bad = enc.copy()
+    bad[base + 4 + 4 * 256 + 1] ^= 0x40          # cum[256] of block 1 is no longer the scale
+    with pytest.raises(B2rcError) as e:
+        ctx.decode(bad)
+    assert e.value.code == -3
+    bad = enc.copy()
+    bad[base] ^= 1                                # size field disagrees with the container
+    with pytest.raises(B2rcError) as e:
+        ctx.decode(bad)
+    assert e.value.code == -3
+    bad = enc.copy()
+    bad[base + 4 + 4 * 10] ^= 0xFF                # cumulative counts not monotone
+    with pytest.raises(B2rcError) as e:
+        ctx.decode(bad)
+    assert e.value.code == -3
+    # an odd offset in the index (word payloads are 2-byte aligned)
+    bad = enc.copy()
+    off = bad[32:32 + 8 * (info.nblocks + 1)].view(np.uint64)
+    off[1] += 1
+    with pytest.raises(B2rcError) as e:
+        ctx.decode(bad)
+    assert e.value.code == -3
+    # flipped coded bits decode to something, without faulting, and the next call is clean
+    bad = enc.copy()
+    bad[base + RANS_HEADER + 40: base + RANS_HEADER + 400] ^= 0x5A
+    try:
+        ctx.decode(bad)
+    except B2rcError as e2:
+        assert e2.code == -3
+    assert ctx.decode(enc).tobytes() == data.tobytes()
+
+
+def test_device_api_and_large_property(ctx, oracle):
+    import torch
+    n = (256 << 20) + 12345
+    data = synth.zipf(n)
+    src = torch.from_numpy(data).cuda()
+    enc, used = ctx.encode_device(RANS_WORD, src, block=65536)
+    dec = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    got = ctx.decode_device(enc, used, dec)
+    assert got == n and torch.equal(dec, src)
+    host = enc[:used].cpu().numpy()
+    info = container.parse(host)
+    rng = np.random.default_rng(0)
+    for b in [0, info.nblocks - 1] + [int(v) for v in rng.integers(0, info.nblocks, 6)]:
+        blk = data[b * 65536:(b + 1) * 65536]
+        assert bytes(info.payload(host, b)) == oracle.encode(RANS_WORD, blk), f"block {b}"
+    # a different shape of data through the same context
+    d2 = synth.kennedy(64 << 20)
+    s2 = torch.from_numpy(d2).cuda()
+    e2, u2 = ctx.encode_device(RANS_WORD, s2, block=16384)
+    o2 = torch.zeros(d2.size, dtype=torch.uint8, device="cuda")
+    g2 = ctx.decode_device(e2, u2, o2)
+    assert g2 == d2.size and torch.equal(o2, s2)

@@ -36,7 +36,9 @@ def main():
     src = torch.from_numpy(data).cuda()
     print(f"generated {n} bytes of {gen} in {time.time() - t0:.1f}s, block {block}", flush=True)
     nb = api.nblocks(n, block)
-    for mode, name in ((0, "static"), (1, "adaptive")):
+    which = sys.argv[4].split(",") if len(sys.argv) > 4 else ["static", "adaptive", "rans-word"]
+    for name in which:
+        mode = api.MODE_NAMES[name]
         freq = None
         if mode == 0 and block <= 65536:
             freq = ctx.histogram(src, block)
@@ -45,12 +47,19 @@ def main():
         slots, stride, sizes, err = ctx.encode_blocks(mode, src, block, freq16=freq)
         ms = timed(lambda: ctx.encode_blocks(mode, src, block, freq16=freq, slots=slots, sizes=sizes, err=err))
         print(f"{name:9s} K2 encode    {ms:8.3f} ms  {n / ms / 1e6:8.1f} GB/s")
+        if mode >= 2:
+            ctx.profile(True)
+            ctx.encode_blocks(mode, src, block, slots=slots, sizes=sizes, err=err)
+            torch.cuda.synchronize()
+            km = ctx.kernel_ms()
+            ctx.profile(False)
+            print(f"{name:9s}    model {km.get('histogram', -1):.3f} ms, coder {km.get('encode', -1):.3f} ms")
         offsets = ctx.scan(sizes, nb)
         ms = timed(lambda: ctx.scan(sizes, nb, offsets))
         total = int(offsets[nb].item())
         print(f"{name:9s} K4 scan      {ms:8.3f} ms  ratio {total / n:.6f}")
         payload = torch.empty(total + 16, dtype=torch.uint8, device="cuda")
-        ms = timed(lambda: ctx.compact(slots, stride, sizes, offsets, nb, payload, err))
+        ms = timed(lambda: ctx.compact(slots, stride, sizes, offsets, nb, payload, err, mode))
         print(f"{name:9s} K4 compact   {ms:8.3f} ms  {2 * total / ms / 1e6:8.1f} GB/s (r+w)")
         dst = torch.empty(n, dtype=torch.uint8, device="cuda")
         ms = timed(lambda: ctx.decode_blocks(mode, payload, total, offsets, nb, dst, n, block))
