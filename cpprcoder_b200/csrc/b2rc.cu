@@ -335,13 +335,7 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         if(rc == B2RC_OK) {
             rc = set_smem_limits(ctx);
         }
-        if(rc == B2RC_OK) {
-            k_ans_magic_init<<<(ANS_MAGIC_N + 255u) / 256u, 256, 0, ctx->stream>>>();
-            if(!cuda_ok(ctx, cudaGetLastError(), "k_ans_magic_init") ||
-               !cuda_ok(ctx, cudaStreamSynchronize(ctx->stream), "k_ans_magic_init")) {
-                rc = B2RC_E_CUDA;
-            }
-        }
+
     } while(0);
     if(rc != B2RC_OK) {
         fprintf(stderr, "b2rc_ctx_create: %s\n", ctx->last_err);

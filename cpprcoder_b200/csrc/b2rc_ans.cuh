@@ -27,19 +27,11 @@ constexpr u32 ANS_HDR = 1032u;          // 258 x u32 (cppans.h:598-604)
 constexpr u32 ANS_WORD_BITS = 12u;      // rANS::WordScaleBits (cppans.h:31)
 constexpr u32 ANS_BYTE_BITS = 14u;      // rANS::ProbBits      (cppans.h:27)
 constexpr u32 ANS_WORD_LOW = 1u << 16;  // rANS::WordLowBounds (cppans.h:30)
-constexpr u32 ANS_MAGIC_N = (1u << ANS_BYTE_BITS) + 1u;
 
-// reciprocals for rc_div by every frequency a normalised model can hold; one table for
-// the whole device (64 KiB, L1/L2 resident), filled once per context
-__device__ u32 g_ans_magic[ANS_MAGIC_N];
-__global__ void k_ans_magic_init()
+__device__ __forceinline__ void lds64(u32 a, u32& lo, u32& hi)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i < ANS_MAGIC_N) {
-        g_ans_magic[i] = rc_magic(i);
-    }
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
 }
-
 __device__ __forceinline__ u32 lds8(u32 a)
 {
     u32 v;
@@ -144,10 +136,101 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_ans_model(const u8* src, u6
 // emits its low 16 bits when it reaches freq << 20 -- a u32 product in the reference
 // (wordEncPut, cppans.h:357), so a symbol that owns the whole scale emits every time --
 // and within a round the states emit in descending lane order at descending addresses.
-// Symbol, (start, freq) and the reciprocal are looked up ahead of the state chain.
+//
+// Everything that does not depend on the state runs ahead of it, one quad (4 rounds, 32
+// input bytes per block) per loop trip:
+//   A  one aligned u32 per lane = the quad's 32 bytes per group, five quads ahead;
+//   B  the quad's four symbols per lane by shuffle + byte select, then {start, freq,
+//      reciprocal of freq} in one 8-byte load from the block's table, one quad ahead;
+//   D  the state chain itself: compare, ballot, store, divide, update.
+// (The reciprocals first lived in one device-wide table indexed by freq and read through
+// L1: 13 sectors per request, and the L1 tag stage became the bottleneck.)
+__device__ __forceinline__ void st_u16(u8* p, u32 v)
+{
+    asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool RAGGED>
+__device__ __forceinline__ u32 ans_quad_word(const u8* __restrict__ sp, u32 len, s32 k, u32 j)
+{
+    if(k < 0) {
+        return 0u;
+    }
+    const u32 off = 32u * (u32)k + 4u * j;
+    if(!RAGGED || off + 4u <= len) {
+        return __ldg(reinterpret_cast<const u32*>(sp + off));
+    }
+    u32 v = 0;
+    for(u32 t = 0; t < 4u; ++t) {
+        if(off + t < len) {
+            v |= (u32)__ldg(sp + off + t) << (8u * t);
+        }
+    }
+    return v;
+}
+
+template <bool RAGGED>
+__device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32 len, s32 K, u32 tb, u8* slot, u32& x,
+                                                  u32& w, u32 lane)
+{
+    const u32 j = lane & 7u, gbase = lane & 24u;
+    const u32 above = (0xFEu << j) & 0xFFu;          // the states of my block that emit before me
+    const u32 gmask = 0xFFu << gbase, amask = above << gbase;
+    const u32 bsel = 0x4440u + (j & 3u);             // byte (j & 3) of a word, zero extended
+    const u32 src_lo = gbase + (j >> 2);             // lane holding byte 8*rr + j of a quad: src_lo + 2*rr
+
+    // table entry of a symbol: {start << 16 | freq, reciprocal of freq}, one 8-byte load
+    auto symbols = [&](u32 word, u32 (&e)[4], u32 (&m)[4]) {
+#pragma unroll
+        for(int rr = 0; rr < 4; ++rr) {
+            const u32 v = __shfl_sync(FULL, word, src_lo + 2 * rr);
+            lds64(tb + 8u * __byte_perm(v, 0u, bsel), e[rr], m[rr]);
+        }
+    };
+
+    u32 eC[4], mC[4], eN[4], mN[4];
+    u32 W0, W1, W2, W3;
+    symbols(ans_quad_word<RAGGED>(sp, len, K - 1, j), eC, mC);
+    W0 = ans_quad_word<RAGGED>(sp, len, K - 2, j);
+    W1 = ans_quad_word<RAGGED>(sp, len, K - 3, j);
+    W2 = ans_quad_word<RAGGED>(sp, len, K - 4, j);
+    W3 = ans_quad_word<RAGGED>(sp, len, K - 5, j);
+    for(s32 k = K - 1; k >= 0; --k) {
+        symbols(W0, eN, mN);                          // B: quad k-1
+        W0 = W1;                                      // A: quad k-5
+        W1 = W2;
+        W2 = W3;
+        W3 = ans_quad_word<RAGGED>(sp, len, k - 5, j);
+#pragma unroll
+        for(int rr = 3; rr >= 0; --rr) {              // D: quad k, last round first
+            const u32 f = eC[rr] & 0xFFFFu, start = eC[rr] >> 16;
+            const bool act = !RAGGED || (32u * (u32)k + 8u * (u32)rr + j) < len;
+            const bool emit = act && ((f << 20) <= x);
+            const u32 bal = __ballot_sync(FULL, emit);
+            const u32 at = w - 2u - 2u * __popc(bal & amask);
+            const u32 xl = x;
+            if(emit) {
+                st_u16(slot + at, xl);
+            }
+            x = emit ? (x >> 16) : x;
+            w -= 2u * __popc(bal & gmask);
+            u32 quo = rc_umulhi(x, mC[rr]);
+            const u32 rem = x - quo * f;
+            quo += rem >= f ? 1u : 0u;
+            const u32 xn = x + start + quo * ((1u << ANS_WORD_BITS) - f);  // = (quo << 12) + x % f + start, cppans.h:363
+            x = act ? xn : x;
+        }
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+            eC[q] = eN[q];
+            mC[q] = mN[q];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(32) k_ans_enc_word(EncArgs a)
 {
-    __shared__ u32 tab[4][256];
+    __shared__ uint2 tab[4][256];
     const u32 lane = lane_id(), grp = lane >> 3, j = lane & 7u;
     const u64 b = (u64)blockIdx.x * 4u + grp;
     const bool live = b < a.nblocks;
@@ -158,68 +241,25 @@ __global__ void __launch_bounds__(32) k_ans_enc_word(EncArgs a)
         const u32* hdr = reinterpret_cast<const u32*>(slot);
         for(u32 s = j; s < 256u; s += 8u) {
             const u32 c0 = hdr[1u + s], c1 = hdr[2u + s];
-            tab[grp][s] = (c0 << 16) | (c1 - c0);
+            tab[grp][s] = make_uint2((c0 << 16) | (c1 - c0), rc_magic(c1 - c0));
         }
     }
     __syncwarp();
     const u32 tb = smem_addr(tab[grp]);
     const u8* __restrict__ sp = a.src + lo;
-    const u32 gshift = grp * 8u;
-    u32 x = ANS_WORD_LOW;                // wordEncInit (cppans.h:336-339)
-    u32 w = (u32)a.slot_stride;          // write cursor, bytes from the slot start
-    const u32 rmax = __reduce_max_sync(FULL, (len + 7u) >> 3);
-    // symbols are fetched two quads of rounds ahead of their use
-    u32 sA[4], sB[4];
-#pragma unroll
-    for(int q = 0; q < 4; ++q) {
-        const s32 pa = 8 * ((s32)rmax - 1 - q) + (s32)j, pb = pa - 32;
-        sA[q] = (pa >= 0 && (u32)pa < len) ? (u32)__ldg(sp + pa) : 0u;
-        sB[q] = (pb >= 0 && (u32)pb < len) ? (u32)__ldg(sp + pb) : 0u;
-    }
-    for(s32 r = (s32)rmax; r > 0; r -= 4) {
-        u32 sC[4], e[4], mg[4];
-#pragma unroll
-        for(int q = 0; q < 4; ++q) {
-            const s32 pc = 8 * (r - 9 - q) + (s32)j;
-            sC[q] = (pc >= 0 && (u32)pc < len) ? (u32)__ldg(sp + pc) : 0u;
-        }
-#pragma unroll
-        for(int q = 0; q < 4; ++q) {
-            e[q] = lds32(tb + 4u * sA[q]);
-        }
-#pragma unroll
-        for(int q = 0; q < 4; ++q) {
-            mg[q] = __ldg(&g_ans_magic[e[q] & 0xFFFFu]);
-        }
-#pragma unroll
-        for(int q = 0; q < 4; ++q) {
-            const s32 p = 8 * (r - 1 - q) + (s32)j;
-            const bool act = p >= 0 && (u32)p < len;
-            const u32 f = e[q] & 0xFFFFu, start = e[q] >> 16;
-            const bool emit = act && ((f << 20) <= x);
-            const u32 g = (__ballot_sync(FULL, emit) >> gshift) & 0xFFu;
-            if(emit) {
-                const u32 at = w - 2u * (__popc(g >> (j + 1u)) + 1u);
-                *reinterpret_cast<u16*>(slot + at) = (u16)x;
-                x >>= 16;
-            }
-            w -= 2u * __popc(g);
-            if(act) {
-                const u32 quo = rc_div(x, f, mg[q]);
-                x = (quo << ANS_WORD_BITS) + (x - quo * f) + start;  // cppans.h:363
-            }
-        }
-#pragma unroll
-        for(int q = 0; q < 4; ++q) {
-            sA[q] = sB[q];
-            sB[q] = sC[q];
-        }
+    u32 x = ANS_WORD_LOW;        // wordEncInit (cppans.h:336-339)
+    u32 w = (u32)a.slot_stride;  // write cursor, bytes from the slot start
+    const s32 K = (s32)((__reduce_max_sync(FULL, len) + 31u) >> 5);
+    if(__all_sync(FULL, live && len == 32u * (u32)K)) {
+        ans_enc_word_loop<false>(sp, len, K, tb, slot, x, w, lane);
+    } else {
+        ans_enc_word_loop<true>(sp, len, K, tb, slot, x, w, lane);
     }
     if(live) {
         // wordEncFlush, states 7 .. 0 at descending addresses (cppans.h:595-597)
         const u32 at = w - 32u + 4u * j;
-        *reinterpret_cast<u16*>(slot + at) = (u16)x;
-        *reinterpret_cast<u16*>(slot + at + 2u) = (u16)(x >> 16);
+        st_u16(slot + at, x);
+        st_u16(slot + at + 2u, x >> 16);
         if(j == 0u) {
             a.sizes[b] = ANS_HDR + ((u32)a.slot_stride - (w - 32u));
         }
@@ -232,7 +272,41 @@ __global__ void __launch_bounds__(32) k_ans_enc_word(EncArgs a)
 // of a slot follow from its symbol, so the reference's 16 KiB WordSlot array is not kept
 // and 11 warps fit an SM instead of 3.  After each round of eight symbols the states below
 // 2^16 take the next u16s of the stream in lane order (simdDecRenorm, cppans.h:443-488).
+// The stream is read straight from global memory, 2 bytes per refilling lane; one lane per
+// block keeps the L1 a few hundred bytes ahead of the read cursor with prefetches.
 constexpr u32 ANS_DEC_WORD_SMEM = 4u * (4096u + 1024u);
+constexpr u32 ANS_PREFETCH_AHEAD = 384u;
+
+template <bool RAGGED>
+__device__ __forceinline__ void ans_dec_word_loop(const u8* __restrict__ pay, u32 cap, u32 full, u32 rmax, u32 sb, u32 tb,
+                                                  u8* out, u32& x, u32& rp, u32 lane)
+{
+    const u32 j = lane & 7u, gbase = lane & 24u;
+    const u32 below = ((1u << j) - 1u) << gbase, gmask = 0xFFu << gbase;
+    for(u32 r = 0; r < rmax; ++r) {
+        const bool act = !RAGGED || r < full;
+        if(j == 0u) {
+            const u32 pf = rp + ANS_PREFETCH_AHEAD;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pay + (pf < cap ? pf : cap)));
+        }
+        const u32 slt = x & ((1u << ANS_WORD_BITS) - 1u);
+        const u32 s = lds8(sb + slt);
+        const u32 e = lds32(tb + 4u * s);
+        u32 xn = (e >> 16) * (x >> ANS_WORD_BITS) + slt - (e & 0xFFFFu);  // simdDecSym (cppans.h:412-440)
+        if(act) {
+            out[8u * r] = (u8)s;
+        }
+        const bool need = act && xn < ANS_WORD_LOW;
+        const u32 bal = __ballot_sync(FULL, need);
+        u32 at = rp + 2u * __popc(bal & below);
+        at = at < cap ? at : cap;  // a corrupt stream may ask for more than there is; checked after the loop
+        if(need) {
+            xn = (xn << 16) | (u32)__ldg(reinterpret_cast<const u16*>(pay + at));
+        }
+        rp += 2u * __popc(bal & gmask);
+        x = act ? xn : x;
+    }
+}
 
 __global__ void __launch_bounds__(32) k_ans_dec_word(DecArgs a)
 {
@@ -282,41 +356,21 @@ __global__ void __launch_bounds__(32) k_ans_dec_word(DecArgs a)
     u32 x = ok ? ld32_a2(pay + ANS_HDR + 4u * j) : 0u;  // simdDecInit (cppans.h:405-409)
     u32 rp = ANS_HDR + 32u;
     u8* out = a.dst + lo + j;
-    const u32 below = (1u << j) - 1u;
-    bool bad = false;
+    // reads are clamped to the last whole u16 of the payload area (never past the buffer)
+    const u64 room = (u64)((a.payload + a.payload_len) - pay);
+    const u32 cap = ok ? (u32)((room < 0xFFFFFFF0ull ? room : 0xFFFFFFF0ull) - 2u) & ~1u : 0u;
     const u32 rmax = __reduce_max_sync(FULL, full);
-    for(u32 r = 0; r < rmax; ++r) {
-        const bool act = r < full;
-        const u32 slt = x & ((1u << ANS_WORD_BITS) - 1u);
-        const u32 s = lds8(sb + slt);
-        const u32 e = lds32(tb + 4u * s);
-        u32 xn = (e >> 16) * (x >> ANS_WORD_BITS) + slt - (e & 0xFFFFu);  // simdDecSym (cppans.h:412-440)
-        if(act) {
-            out[8u * r] = (u8)s;
-        }
-        const bool need = act && xn < ANS_WORD_LOW;
-        const u32 g = (__ballot_sync(FULL, need) >> gshift) & 0xFFu;
-        if(need) {
-            const u32 at = rp + 2u * __popc(g & below);
-            u32 wv = 0;
-            if(at + 2u <= paylen) {
-                wv = __ldg(reinterpret_cast<const u16*>(pay + at));
-            } else {
-                bad = true;
-            }
-            xn = (xn << 16) | wv;
-        }
-        rp += 2u * __popc(g);
-        if(act) {
-            x = xn;
-        }
+    if(__all_sync(FULL, full == rmax)) {
+        ans_dec_word_loop<false>(pay, cap, full, rmax, sb, tb, out, x, rp, lane);
+    } else {
+        ans_dec_word_loop<true>(pay, cap, full, rmax, sb, tb, out, x, rp, lane);
     }
     // the last (size & 7) symbols: one more symbol from states 0.. without a refill (cppans.h:643-647)
     if(8u * full + j < want) {
         out[8u * full] = (u8)lds8(sb + (x & ((1u << ANS_WORD_BITS) - 1u)));
     }
-    if(bad) {
-        atomicOr(a.err, ERR_CORRUPT);
+    if(ok && rp > paylen) {
+        atomicOr(a.err, ERR_CORRUPT);  // the coder ran past this block's payload
     }
 }
 
