@@ -170,7 +170,7 @@ __device__ __forceinline__ u32 ans_quad_word(const u8* __restrict__ sp, u32 len,
 }
 
 template <bool RAGGED>
-__device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32 len, s32 K, u32 tb, u8* slot, u32& x,
+__device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32 len, s32 K4, u32 tb, u8* slot, u32& x,
                                                   u32& w, u32 lane)
 {
     const u32 j = lane & 7u, gbase = lane & 24u;
@@ -188,42 +188,42 @@ __device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32
         }
     };
 
-    u32 eC[4], mC[4], eN[4], mN[4];
-    u32 W0, W1, W2, W3;
-    symbols(ans_quad_word<RAGGED>(sp, len, K - 1, j), eC, mC);
-    W0 = ans_quad_word<RAGGED>(sp, len, K - 2, j);
-    W1 = ans_quad_word<RAGGED>(sp, len, K - 3, j);
-    W2 = ans_quad_word<RAGGED>(sp, len, K - 4, j);
-    W3 = ans_quad_word<RAGGED>(sp, len, K - 5, j);
-    for(s32 k = K - 1; k >= 0; --k) {
-        symbols(W0, eN, mN);                          // B: quad k-1
-        W0 = W1;                                      // A: quad k-5
-        W1 = W2;
-        W2 = W3;
-        W3 = ans_quad_word<RAGGED>(sp, len, k - 5, j);
+    // Quad q keeps its input word in W[q & 3] and its table entries in e/m[q & 1]; the trip
+    // count is a multiple of four quads and the body is unrolled four times, so every
+    // index below is a compile-time constant and nothing is moved between registers (a
+    // register-to-register rotation would wait for the newest load every trip).
+    u32 e[2][4], m[2][4], W[4];
+    symbols(ans_quad_word<RAGGED>(sp, len, K4 - 1, j), e[1], m[1]);
+    W[2] = ans_quad_word<RAGGED>(sp, len, K4 - 2, j);
+    W[1] = ans_quad_word<RAGGED>(sp, len, K4 - 3, j);
+    W[0] = ans_quad_word<RAGGED>(sp, len, K4 - 4, j);
+    W[3] = ans_quad_word<RAGGED>(sp, len, K4 - 5, j);
+    for(s32 k = K4 - 1; k >= 0; k -= 4) {
 #pragma unroll
-        for(int rr = 3; rr >= 0; --rr) {              // D: quad k, last round first
-            const u32 f = eC[rr] & 0xFFFFu, start = eC[rr] >> 16;
-            const bool act = !RAGGED || (32u * (u32)k + 8u * (u32)rr + j) < len;
-            const bool emit = act && ((f << 20) <= x);
-            const u32 bal = __ballot_sync(FULL, emit);
-            const u32 at = w - 2u - 2u * __popc(bal & amask);
-            const u32 xl = x;
-            if(emit) {
-                st_u16(slot + at, xl);
+        for(int u = 0; u < 4; ++u) {
+            const s32 q = k - u;                      // q & 3 == 3 - u
+            const int par = (3 - u) & 1, nxt = (2 - u) & 3;
+            symbols(W[nxt], e[par ^ 1], m[par ^ 1]);  // B: quad q-1
+            W[nxt] = ans_quad_word<RAGGED>(sp, len, q - 5, j);  // A: quad q-5
+#pragma unroll
+            for(int rr = 3; rr >= 0; --rr) {          // D: quad q, last round first
+                const u32 f = e[par][rr] & 0xFFFFu, start = e[par][rr] >> 16;
+                const bool act = !RAGGED || (32u * (u32)q + 8u * (u32)rr + j) < len;
+                const bool emit = act && ((f << 20) <= x);
+                const u32 bal = __ballot_sync(FULL, emit);
+                const u32 at = w - 2u - 2u * __popc(bal & amask);
+                const u32 xl = x;
+                if(emit) {
+                    st_u16(slot + at, xl);
+                }
+                x = emit ? (x >> 16) : x;
+                w -= 2u * __popc(bal & gmask);
+                u32 quo = rc_umulhi(x, m[par][rr]);
+                const u32 rem = x - quo * f;
+                quo += rem >= f ? 1u : 0u;
+                const u32 xn = x + start + quo * ((1u << ANS_WORD_BITS) - f);  // (quo << 12) + x % f + start, cppans.h:363
+                x = act ? xn : x;
             }
-            x = emit ? (x >> 16) : x;
-            w -= 2u * __popc(bal & gmask);
-            u32 quo = rc_umulhi(x, mC[rr]);
-            const u32 rem = x - quo * f;
-            quo += rem >= f ? 1u : 0u;
-            const u32 xn = x + start + quo * ((1u << ANS_WORD_BITS) - f);  // = (quo << 12) + x % f + start, cppans.h:363
-            x = act ? xn : x;
-        }
-#pragma unroll
-        for(int q = 0; q < 4; ++q) {
-            eC[q] = eN[q];
-            mC[q] = mN[q];
         }
     }
 }
@@ -249,11 +249,11 @@ __global__ void __launch_bounds__(32) k_ans_enc_word(EncArgs a)
     const u8* __restrict__ sp = a.src + lo;
     u32 x = ANS_WORD_LOW;        // wordEncInit (cppans.h:336-339)
     u32 w = (u32)a.slot_stride;  // write cursor, bytes from the slot start
-    const s32 K = (s32)((__reduce_max_sync(FULL, len) + 31u) >> 5);
-    if(__all_sync(FULL, live && len == 32u * (u32)K)) {
-        ans_enc_word_loop<false>(sp, len, K, tb, slot, x, w, lane);
+    const s32 K4 = (s32)(((__reduce_max_sync(FULL, len) + 127u) >> 7) << 2);  // quads, a multiple of four
+    if(__all_sync(FULL, live && len == 32u * (u32)K4)) {
+        ans_enc_word_loop<false>(sp, len, K4, tb, slot, x, w, lane);
     } else {
-        ans_enc_word_loop<true>(sp, len, K, tb, slot, x, w, lane);
+        ans_enc_word_loop<true>(sp, len, K4, tb, slot, x, w, lane);
     }
     if(live) {
         // wordEncFlush, states 7 .. 0 at descending addresses (cppans.h:595-597)
@@ -272,8 +272,10 @@ __global__ void __launch_bounds__(32) k_ans_enc_word(EncArgs a)
 // of a slot follow from its symbol, so the reference's 16 KiB WordSlot array is not kept
 // and 11 warps fit an SM instead of 3.  After each round of eight symbols the states below
 // 2^16 take the next u16s of the stream in lane order (simdDecRenorm, cppans.h:443-488).
-// The stream is read straight from global memory, 2 bytes per refilling lane; one lane per
-// block keeps the L1 a few hundred bytes ahead of the read cursor with prefetches.
+// Each round the eight lanes of a block load the block's next eight u16s, one each, as soon
+// as the read cursor is known; a refilling lane then takes its word from the lane that
+// holds it by shuffle.  One lane per block keeps the L1 a few hundred bytes ahead of the
+// cursor with prefetches.
 constexpr u32 ANS_DEC_WORD_SMEM = 4u * (4096u + 1024u);
 constexpr u32 ANS_PREFETCH_AHEAD = 384u;
 
@@ -283,6 +285,13 @@ __device__ __forceinline__ void ans_dec_word_loop(const u8* __restrict__ pay, u3
 {
     const u32 j = lane & 7u, gbase = lane & 24u;
     const u32 below = ((1u << j) - 1u) << gbase, gmask = 0xFFu << gbase;
+    // the block's next eight u16s, one per lane, fetched before anyone knows who needs one:
+    // the load overlaps the table lookups of the round instead of following them
+    auto window = [&](u32 pos) -> u32 {
+        const u32 at = pos + 2u * j;
+        return (u32)__ldg(reinterpret_cast<const u16*>(pay + (at < cap ? at : cap)));
+    };
+    u32 wnext = window(rp);
     for(u32 r = 0; r < rmax; ++r) {
         const bool act = !RAGGED || r < full;
         if(j == 0u) {
@@ -298,12 +307,10 @@ __device__ __forceinline__ void ans_dec_word_loop(const u8* __restrict__ pay, u3
         }
         const bool need = act && xn < ANS_WORD_LOW;
         const u32 bal = __ballot_sync(FULL, need);
-        u32 at = rp + 2u * __popc(bal & below);
-        at = at < cap ? at : cap;  // a corrupt stream may ask for more than there is; checked after the loop
-        if(need) {
-            xn = (xn << 16) | (u32)__ldg(reinterpret_cast<const u16*>(pay + at));
-        }
+        const u32 wv = __shfl_sync(FULL, wnext, gbase + __popc(bal & below));
         rp += 2u * __popc(bal & gmask);
+        wnext = window(rp);
+        xn = need ? ((xn << 16) | wv) : xn;
         x = act ? xn : x;
     }
 }
