@@ -139,9 +139,9 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_ans_model(const u8* src, u6
 //
 // Everything that does not depend on the state runs ahead of it, one quad (4 rounds, 32
 // input bytes per block) per loop trip:
-//   A  one aligned u32 per lane = the quad's 32 bytes per group, five quads ahead;
-//   B  the quad's four symbols per lane by shuffle + byte select, then {start, freq,
-//      reciprocal of freq} in one 8-byte load from the block's table, one quad ahead;
+//   A  the lane's four symbols of a quad, byte loads through L1, five quads ahead;
+//   B  {start, freq, reciprocal of freq} of each symbol in one 8-byte load from the
+//      block's table in shared memory, one quad ahead;
 //   D  the state chain itself: compare, ballot, store, divide, update.
 // (The reciprocals first lived in one device-wide table indexed by freq and read through
 // L1: 13 sectors per request, and the L1 tag stage became the bottleneck.)
@@ -151,70 +151,59 @@ __device__ __forceinline__ void st_u16(u8* p, u32 v)
 }
 
 template <bool RAGGED>
-__device__ __forceinline__ u32 ans_quad_word(const u8* __restrict__ sp, u32 len, s32 k, u32 j)
-{
-    if(k < 0) {
-        return 0u;
-    }
-    const u32 off = 32u * (u32)k + 4u * j;
-    if(!RAGGED || off + 4u <= len) {
-        return __ldg(reinterpret_cast<const u32*>(sp + off));
-    }
-    u32 v = 0;
-    for(u32 t = 0; t < 4u; ++t) {
-        if(off + t < len) {
-            v |= (u32)__ldg(sp + off + t) << (8u * t);
-        }
-    }
-    return v;
-}
-
-template <bool RAGGED>
 __device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32 len, s32 K4, u32 tb, u8* slot, u32& x,
                                                   u32& w, u32 lane)
 {
     const u32 j = lane & 7u, gbase = lane & 24u;
     const u32 above = (0xFEu << j) & 0xFFu;          // the states of my block that emit before me
     const u32 gmask = 0xFFu << gbase, amask = above << gbase;
-    const u32 bsel = 0x4440u + (j & 3u);             // byte (j & 3) of a word, zero extended
-    const u32 src_lo = gbase + (j >> 2);             // lane holding byte 8*rr + j of a quad: src_lo + 2*rr
+    const u8* __restrict__ pl = sp + j;              // my state's symbols: pl[8 * round]
 
-    // table entry of a symbol: {start << 16 | freq, reciprocal of freq}, one 8-byte load
-    auto symbols = [&](u32 word, u32 (&e)[4], u32 (&m)[4]) {
+    // A: the four symbols of quad q for this lane (one byte each; the eight lanes of a group
+    // share a sector, the four rounds of a quad share it too)
+    auto fetch = [&](s32 q, u32 (&sy)[4]) {
 #pragma unroll
         for(int rr = 0; rr < 4; ++rr) {
-            const u32 v = __shfl_sync(FULL, word, src_lo + 2 * rr);
-            lds64(tb + 8u * __byte_perm(v, 0u, bsel), e[rr], m[rr]);
+            const u32 pos = 32u * (u32)q + 8u * (u32)rr;
+            sy[rr] = (q >= 0 && (!RAGGED || pos + j < len)) ? (u32)__ldg(pl + pos) : 0u;
+        }
+    };
+    // B: table entry of a symbol: {start << 16 | freq, reciprocal of freq}, one 8-byte load
+    auto lookup = [&](const u32 (&sy)[4], u32 (&e)[4], u32 (&m)[4]) {
+#pragma unroll
+        for(int rr = 0; rr < 4; ++rr) {
+            lds64(tb + 8u * sy[rr], e[rr], m[rr]);
         }
     };
 
-    // Quad q keeps its input word in W[q & 3] and its table entries in e/m[q & 1]; the trip
+    // Quad q keeps its symbols in S[q & 3] and its table entries in e/m[q & 1]; the trip
     // count is a multiple of four quads and the body is unrolled four times, so every
     // index below is a compile-time constant and nothing is moved between registers (a
     // register-to-register rotation would wait for the newest load every trip).
-    u32 e[2][4], m[2][4], W[4];
-    symbols(ans_quad_word<RAGGED>(sp, len, K4 - 1, j), e[1], m[1]);
-    W[2] = ans_quad_word<RAGGED>(sp, len, K4 - 2, j);
-    W[1] = ans_quad_word<RAGGED>(sp, len, K4 - 3, j);
-    W[0] = ans_quad_word<RAGGED>(sp, len, K4 - 4, j);
-    W[3] = ans_quad_word<RAGGED>(sp, len, K4 - 5, j);
+    u32 e[2][4], m[2][4], S[4][4];
+    fetch(K4 - 1, S[3]);
+    fetch(K4 - 2, S[2]);
+    fetch(K4 - 3, S[1]);
+    fetch(K4 - 4, S[0]);
+    lookup(S[3], e[1], m[1]);
+    fetch(K4 - 5, S[3]);
     for(s32 k = K4 - 1; k >= 0; k -= 4) {
 #pragma unroll
         for(int u = 0; u < 4; ++u) {
             const s32 q = k - u;                      // q & 3 == 3 - u
             const int par = (3 - u) & 1, nxt = (2 - u) & 3;
-            symbols(W[nxt], e[par ^ 1], m[par ^ 1]);  // B: quad q-1
-            W[nxt] = ans_quad_word<RAGGED>(sp, len, q - 5, j);  // A: quad q-5
+            lookup(S[nxt], e[par ^ 1], m[par ^ 1]);   // B: quad q-1
+            fetch(q - 5, S[nxt]);                     // A: quad q-5
 #pragma unroll
             for(int rr = 3; rr >= 0; --rr) {          // D: quad q, last round first
                 const u32 f = e[par][rr] & 0xFFFFu, start = e[par][rr] >> 16;
                 const bool act = !RAGGED || (32u * (u32)q + 8u * (u32)rr + j) < len;
                 const bool emit = act && ((f << 20) <= x);
                 const u32 bal = __ballot_sync(FULL, emit);
-                const u32 at = w - 2u - 2u * __popc(bal & amask);
-                const u32 xl = x;
+                const u32 at = w - 2u * __popc(bal & amask);
+                const u32 xl = x & 0xFFFFu;           // its own register: the store must not hold up the chain
                 if(emit) {
-                    st_u16(slot + at, xl);
+                    st_u16(slot + at - 2, xl);
                 }
                 x = emit ? (x >> 16) : x;
                 w -= 2u * __popc(bal & gmask);
