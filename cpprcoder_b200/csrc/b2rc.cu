@@ -509,7 +509,8 @@ static int ans_decode_blocks(b2rc_ctx* ctx, int mode, const DecArgs& a, cudaStre
 {
     (void)mode;
     KernelTimer kt(ctx, B2RC_K_DECODE, st);
-    k_ans_dec_word<<<(unsigned)((a.nblocks + 3) / 4), 32, ANS_DEC_WORD_SMEM, st>>>(a);
+    k_ans_dec_word<<<(unsigned)((a.nblocks + 4 * ANS_DEC_WARPS - 1) / (4 * ANS_DEC_WARPS)), 32 * ANS_DEC_WARPS,
+                     ANS_DEC_WORD_SMEM, st>>>(a);
     return launch_check(ctx, "k_ans_dec_word");
 }
 

@@ -150,6 +150,8 @@ __device__ __forceinline__ void st_u16(u8* p, u32 v)
     asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+constexpr int ANS_ENC_AHEAD = 6;
+
 template <bool RAGGED>
 __device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32 len, s32 K4, u32 tb, u8* slot, u32& x,
                                                   u32& w, u32 lane)
@@ -162,10 +164,11 @@ __device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32
     // A: the four symbols of quad q for this lane (one byte each; the eight lanes of a group
     // share a sector, the four rounds of a quad share it too)
     auto fetch = [&](s32 q, u32 (&sy)[4]) {
+        const u8* __restrict__ pq = pl + 32 * (s64)q;
 #pragma unroll
         for(int rr = 0; rr < 4; ++rr) {
             const u32 pos = 32u * (u32)q + 8u * (u32)rr;
-            sy[rr] = (q >= 0 && (!RAGGED || pos + j < len)) ? (u32)__ldg(pl + pos) : 0u;
+            sy[rr] = (q >= 0 && (!RAGGED || pos + j < len)) ? (u32)__ldg(pq + 8 * rr) : 0u;
         }
     };
     // B: table entry of a symbol: {start << 16 | freq, reciprocal of freq}, one 8-byte load
@@ -188,6 +191,11 @@ __device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32
     lookup(S[3], e[1], m[1]);
     fetch(K4 - 5, S[3]);
     for(s32 k = K4 - 1; k >= 0; k -= 4) {
+        // the 128 input bytes of the trip ANS_ENC_AHEAD trips from now: towards L2, one
+        // sector per lane 0..3 of the group, so the byte loads above never wait for DRAM
+        if(j < 4u && k >= 4 * ANS_ENC_AHEAD + 3) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + 32 * (s64)(k - 3 - 4 * ANS_ENC_AHEAD) + 32u * j));
+        }
 #pragma unroll
         for(int u = 0; u < 4; ++u) {
             const s32 q = k - u;                      // q & 3 == 3 - u
@@ -259,34 +267,43 @@ __global__ void __launch_bounds__(32) k_ans_enc_word(EncArgs a)
 // Word-variant decode.  Two tables per block in shared memory: slot -> symbol (4096 x u8,
 // initSymbols' slot2symbol_, cppans.h:342-351) and symbol -> (start, freq); freq and bias
 // of a slot follow from its symbol, so the reference's 16 KiB WordSlot array is not kept
-// and 11 warps fit an SM instead of 3.  After each round of eight symbols the states below
+// and 10 warps fit an SM instead of 3.  After each round of eight symbols the states below
 // 2^16 take the next u16s of the stream in lane order (simdDecRenorm, cppans.h:443-488).
-// Each round the eight lanes of a block load the block's next eight u16s, one each, as soon
-// as the read cursor is known; a refilling lane then takes its word from the lane that
-// holds it by shuffle.  One lane per block keeps the L1 a few hundred bytes ahead of the
-// cursor with prefetches.
-constexpr u32 ANS_DEC_WORD_SMEM = 4u * (4096u + 1024u);
-constexpr u32 ANS_PREFETCH_AHEAD = 384u;
+//
+// The stream reaches the states through a 512-byte ring per block in shared memory, filled
+// by cp.async a quarter (128 bytes, 16 per lane) at a time: when the read cursor enters
+// quarter q the group requests quarter q+3 and waits for everything older, so q, q+1 and
+// q+2 are always complete and the request is ~32 rounds ahead of its use.  No register
+// ever waits for global memory inside the loop.
+constexpr u32 ANS_RING = 512u, ANS_QUARTER = 128u;
+constexpr u32 ANS_DEC_WARPS = 2u;  // per CTA: halves the per-CTA shared-memory reserve per warp
+constexpr u32 ANS_DEC_WARP_SMEM = 4u * (4096u + 1024u + ANS_RING);
+constexpr u32 ANS_DEC_WORD_SMEM = ANS_DEC_WARPS * ANS_DEC_WARP_SMEM;
+
+struct AnsRing {
+    const u8* abase;  // 16-byte aligned address at or below the block's payload
+    u32 lim;          // readable bytes from abase to the end of the whole payload area
+    u32 ring;         // shared address of the block's ring
+    u32 j;
+
+    // quarter `qi` (bytes [128 qi, 128 qi + 128) from abase) -> ring; 16 bytes per lane
+    __device__ __forceinline__ void request(u32 qi) const
+    {
+        const u32 at = qi * ANS_QUARTER + 16u * j;
+        const u32 bytes = at < lim ? (lim - at < 16u ? lim - at : 16u) : 0u;
+        cp_async16(ring + (at & (ANS_RING - 1u)), abase + (bytes ? at : 0u), bytes);
+        cp_async_commit();
+    }
+};
 
 template <bool RAGGED>
-__device__ __forceinline__ void ans_dec_word_loop(const u8* __restrict__ pay, u32 cap, u32 full, u32 rmax, u32 sb, u32 tb,
-                                                  u8* out, u32& x, u32& rp, u32 lane)
+__device__ __forceinline__ void ans_dec_word_loop(const AnsRing& rg, u32 full, u32 rmax, u32 sb, u32 tb, u8* out, u32& x,
+                                                  u32& rp, u32 lane)
 {
     const u32 j = lane & 7u, gbase = lane & 24u;
     const u32 below = ((1u << j) - 1u) << gbase, gmask = 0xFFu << gbase;
-    // the block's next eight u16s, one per lane, fetched before anyone knows who needs one:
-    // the load overlaps the table lookups of the round instead of following them
-    auto window = [&](u32 pos) -> u32 {
-        const u32 at = pos + 2u * j;
-        return (u32)__ldg(reinterpret_cast<const u16*>(pay + (at < cap ? at : cap)));
-    };
-    u32 wnext = window(rp);
     for(u32 r = 0; r < rmax; ++r) {
         const bool act = !RAGGED || r < full;
-        if(j == 0u) {
-            const u32 pf = rp + ANS_PREFETCH_AHEAD;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pay + (pf < cap ? pf : cap)));
-        }
         const u32 slt = x & ((1u << ANS_WORD_BITS) - 1u);
         const u32 s = lds8(sb + slt);
         const u32 e = lds32(tb + 4u * s);
@@ -296,24 +313,34 @@ __device__ __forceinline__ void ans_dec_word_loop(const u8* __restrict__ pay, u3
         }
         const bool need = act && xn < ANS_WORD_LOW;
         const u32 bal = __ballot_sync(FULL, need);
-        const u32 wv = __shfl_sync(FULL, wnext, gbase + __popc(bal & below));
-        rp += 2u * __popc(bal & gmask);
-        wnext = window(rp);
+        const u32 wv = lds16v(rg.ring + ((rp + 2u * __popc(bal & below)) & (ANS_RING - 1u)));
+        const u32 rp1 = rp + 2u * __popc(bal & gmask);
         xn = need ? ((xn << 16) | wv) : xn;
         x = act ? xn : x;
+        // entering a new quarter: request the one three ahead, wait for the older ones
+        const bool cross = ((rp ^ rp1) & ANS_QUARTER) != 0u;
+        rp = rp1;
+        if(__any_sync(FULL, cross)) {
+            if(cross) {
+                rg.request((rp >> 7) + 3u);
+            }
+            cp_async_wait<1>();
+            __syncwarp();
+        }
     }
 }
 
-__global__ void __launch_bounds__(32) k_ans_dec_word(DecArgs a)
+__global__ void __launch_bounds__(32 * ANS_DEC_WARPS) k_ans_dec_word(DecArgs a)
 {
     extern __shared__ __align__(16) u8 ans_sm[];
-    const u32 lane = lane_id(), grp = lane >> 3, j = lane & 7u;
-    const u64 b = (u64)blockIdx.x * 4u + grp;
+    const u32 lane = lane_id(), grp = lane >> 3, j = lane & 7u, warp = threadIdx.x >> 5;
+    const u64 b = ((u64)blockIdx.x * ANS_DEC_WARPS + warp) * 4u + grp;
     const bool has = b < a.nblocks;
     const u64 lo = has ? b * (u64)a.block : 0ull;
     const u32 n_b = has ? (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block) : 0u;
-    u8* s2s = ans_sm + grp * 5120u;
-    u32* st = reinterpret_cast<u32*>(s2s + 4096u);
+    u8* wsm = ans_sm + warp * ANS_DEC_WARP_SMEM;
+    u8* s2s = wsm + grp * 4096u;
+    u32* st = reinterpret_cast<u32*>(wsm + 4u * 4096u + grp * 1024u);
     const u8* pay = a.payload;
     u32 paylen = 0;
     bool ok = false;
@@ -345,27 +372,38 @@ __global__ void __launch_bounds__(32) k_ans_dec_word(DecArgs a)
     if(has && !ok && j == 0u) {
         atomicOr(a.err, ERR_CORRUPT);
     }
-    __syncwarp();
     const u32 want = ok ? n_b : 0u;
     const u32 full = want >> 3;
     const u32 sb = smem_addr(s2s), tb = smem_addr(st);
     u32 x = ok ? ld32_a2(pay + ANS_HDR + 4u * j) : 0u;  // simdDecInit (cppans.h:405-409)
-    u32 rp = ANS_HDR + 32u;
+    // the ring mirrors memory from a 16-byte aligned base; rp counts from that base
+    AnsRing rg;
+    const u32 mis = (u32)((uintptr_t)pay & 15u);
+    rg.abase = pay - mis;
+    const u64 room = (u64)((a.payload + a.payload_len) - rg.abase);
+    rg.lim = ok ? (u32)(room < 0xFFFFFFF0ull ? room : 0xFFFFFFF0ull) : 0u;
+    rg.ring = smem_addr(wsm + 4u * (4096u + 1024u) + grp * ANS_RING);
+    rg.j = j;
+    u32 rp = mis + ANS_HDR + 32u;
+    const u32 end = mis + paylen;
+    rg.request((rp >> 7) + 0u);
+    rg.request((rp >> 7) + 1u);
+    rg.request((rp >> 7) + 2u);
+    rg.request((rp >> 7) + 3u);
+    cp_async_wait<0>();
+    __syncwarp();
     u8* out = a.dst + lo + j;
-    // reads are clamped to the last whole u16 of the payload area (never past the buffer)
-    const u64 room = (u64)((a.payload + a.payload_len) - pay);
-    const u32 cap = ok ? (u32)((room < 0xFFFFFFF0ull ? room : 0xFFFFFFF0ull) - 2u) & ~1u : 0u;
     const u32 rmax = __reduce_max_sync(FULL, full);
     if(__all_sync(FULL, full == rmax)) {
-        ans_dec_word_loop<false>(pay, cap, full, rmax, sb, tb, out, x, rp, lane);
+        ans_dec_word_loop<false>(rg, full, rmax, sb, tb, out, x, rp, lane);
     } else {
-        ans_dec_word_loop<true>(pay, cap, full, rmax, sb, tb, out, x, rp, lane);
+        ans_dec_word_loop<true>(rg, full, rmax, sb, tb, out, x, rp, lane);
     }
     // the last (size & 7) symbols: one more symbol from states 0.. without a refill (cppans.h:643-647)
     if(8u * full + j < want) {
         out[8u * full] = (u8)lds8(sb + (x & ((1u << ANS_WORD_BITS) - 1u)));
     }
-    if(ok && rp > paylen) {
+    if(ok && rp > end) {
         atomicOr(a.err, ERR_CORRUPT);  // the coder ran past this block's payload
     }
 }
