@@ -297,29 +297,38 @@ struct AnsRing {
 };
 
 template <bool RAGGED>
-__device__ __forceinline__ void ans_dec_word_loop(const AnsRing& rg, u32 full, u32 rmax, u32 sb, u32 tb, u8* out, u32& x,
+__device__ __forceinline__ void ans_dec_word_loop(const AnsRing& rg, u32 full, u32 rmax4, u32 sb, u32 tb, u8* out, u32& x,
                                                   u32& rp, u32 lane)
 {
     const u32 j = lane & 7u, gbase = lane & 24u;
     const u32 below = ((1u << j) - 1u) << gbase, gmask = 0xFFu << gbase;
-    for(u32 r = 0; r < rmax; ++r) {
-        const bool act = !RAGGED || r < full;
-        const u32 slt = x & ((1u << ANS_WORD_BITS) - 1u);
-        const u32 s = lds8(sb + slt);
-        const u32 e = lds32(tb + 4u * s);
-        u32 xn = (e >> 16) * (x >> ANS_WORD_BITS) + slt - (e & 0xFFFFu);  // simdDecSym (cppans.h:412-440)
-        if(act) {
-            out[8u * r] = (u8)s;
+    // the block's next eight u16s, one per lane, read from the ring as soon as the cursor is
+    // known; a refilling lane takes its word from the lane that holds it (8-lane shuffle)
+    auto window = [&](u32 pos) -> u32 { return lds16v(rg.ring + ((pos + 2u * j) & (ANS_RING - 1u))); };
+    u32 wnext = window(rp);
+    for(u32 r = 0; r < rmax4; r += 4u) {
+        const u32 rp0 = rp;
+#pragma unroll
+        for(u32 t = 0; t < 4u; ++t) {
+            const bool act = !RAGGED || r + t < full;
+            const u32 slt = x & ((1u << ANS_WORD_BITS) - 1u);
+            const u32 s = lds8(sb + slt);
+            const u32 e = lds32(tb + 4u * s);
+            u32 xn = (e >> 16) * (x >> ANS_WORD_BITS) + slt - (e & 0xFFFFu);  // simdDecSym (cppans.h:412-440)
+            if(act) {
+                out[8u * (r + t)] = (u8)s;
+            }
+            const bool need = act && xn < ANS_WORD_LOW;
+            const u32 bal = __ballot_sync(FULL, need);
+            const u32 wv = __shfl_sync(FULL, wnext, __popc(bal & below), 8);
+            rp += 2u * __popc(bal & gmask);
+            wnext = window(rp);
+            xn = need ? ((xn << 16) | wv) : xn;
+            x = act ? xn : x;
         }
-        const bool need = act && xn < ANS_WORD_LOW;
-        const u32 bal = __ballot_sync(FULL, need);
-        const u32 wv = lds16v(rg.ring + ((rp + 2u * __popc(bal & below)) & (ANS_RING - 1u)));
-        const u32 rp1 = rp + 2u * __popc(bal & gmask);
-        xn = need ? ((xn << 16) | wv) : xn;
-        x = act ? xn : x;
-        // entering a new quarter: request the one three ahead, wait for the older ones
-        const bool cross = ((rp ^ rp1) & ANS_QUARTER) != 0u;
-        rp = rp1;
+        // entered a new quarter (at most 64 bytes ago): request the one three ahead and wait
+        // for the older ones; the rounds above never read past quarter q+2
+        const bool cross = ((rp ^ rp0) & ANS_QUARTER) != 0u;
         if(__any_sync(FULL, cross)) {
             if(cross) {
                 rg.request((rp >> 7) + 3u);
@@ -393,11 +402,11 @@ __global__ void __launch_bounds__(32 * ANS_DEC_WARPS) k_ans_dec_word(DecArgs a)
     cp_async_wait<0>();
     __syncwarp();
     u8* out = a.dst + lo + j;
-    const u32 rmax = __reduce_max_sync(FULL, full);
-    if(__all_sync(FULL, full == rmax)) {
-        ans_dec_word_loop<false>(rg, full, rmax, sb, tb, out, x, rp, lane);
+    const u32 rmax4 = (__reduce_max_sync(FULL, full) + 3u) & ~3u;
+    if(__all_sync(FULL, full == rmax4)) {
+        ans_dec_word_loop<false>(rg, full, rmax4, sb, tb, out, x, rp, lane);
     } else {
-        ans_dec_word_loop<true>(rg, full, rmax, sb, tb, out, x, rp, lane);
+        ans_dec_word_loop<true>(rg, full, rmax4, sb, tb, out, x, rp, lane);
     }
     // the last (size & 7) symbols: one more symbol from states 0.. without a refill (cppans.h:643-647)
     if(8u * full + j < want) {
