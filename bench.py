@@ -38,7 +38,12 @@ WORKLOADS = {
     "zipf1g-static-64k": ("zipf", 1 << 30, 0, 65536),
     "mixed-adaptive-64k": ("mixed", 1 << 30, 1, 65536),
     "kennedy-static-64k": ("kennedy", 1 << 30, 0, 65536),
+    # the sibling rANS coder of the reference (cppans.h), eight interleaved states
+    "zipf1g-rans-word-64k": ("zipf", 1 << 30, 3, 65536),
+    "mixed-rans-word-64k": ("mixed", 1 << 30, 3, 65536),
 }
+KERNEL_NAMES = {0: ("k_enc_static", "k_dec_static"), 1: ("k_enc_adaptive", "k_dec_adaptive"),
+                2: ("k_ans_enc_byte", "k_ans_dec_byte"), 3: ("k_ans_enc_word", "k_ans_dec_word")}
 METRIC = "roundtrip_GBps"
 UNIT = "GB/s"
 
@@ -64,7 +69,7 @@ def config_of(args, world):
     return {
         "workload": args.workload,
         "generator": f"cpprcoder_b200.synth.{gen}",
-        "coder": "static" if mode == 0 else "adaptive",
+        "coder": {0: "static", 1: "adaptive", 2: "rans-byte", 3: "rans-word"}[mode],
         "block_size": block,
         "bytes_per_gpu": nbytes,
         "global_bytes": nbytes * world,
@@ -341,7 +346,8 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
         kavg = {k: float(np.mean(v)) for k, v in ksum.items()}
-        algo = {"histogram": n + 512 * (blk_hi - blk_lo), "encode": n + comp_bytes, "scan": 12 * (blk_hi - blk_lo),
+        algo = {"histogram": n + (512 if mode == 0 else 1032) * (blk_hi - blk_lo), "encode": n + comp_bytes,
+                "scan": 12 * (blk_hi - blk_lo),
                 "compact": 2 * comp_bytes, "decode": comp_bytes + n}
         kernels = {k: {"ms": ms, "algorithmic_bytes": algo[k], "GBps": algo[k] / ms / 1e6, "hbm_frac": algo[k] / ms / 1e6 / peak}
                    for k, ms in kavg.items() if k in algo and ms > 0}
@@ -354,8 +360,7 @@ def run_ours(args):
             pass
         roofline = None
         if dom:
-            roofline = {"kernel": {"encode": "k_enc_static" if mode == 0 else "k_enc_adaptive",
-                                   "decode": "k_dec_static" if mode == 0 else "k_dec_adaptive"}[dom],
+            roofline = {"kernel": KERNEL_NAMES[mode][0 if dom == "encode" else 1],
                         "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                         "frac": kernels[dom]["hbm_frac"], "traffic": traffic, "peak_source": peak_src,
                         "note": "latency-bound coder kernel (one serial chain per block); HBM fraction shown for "

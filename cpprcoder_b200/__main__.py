@@ -1,12 +1,13 @@
 """File-level front end: B2RC containers on disk and the reference
 harness's row format.
 
-    python -m cpprcoder_b200 encode [--adaptive] [--block N] IN OUT
+    python -m cpprcoder_b200 encode [--adaptive | --coder static|adaptive|rans|rans-word] [--block N] IN OUT
     python -m cpprcoder_b200 decode IN OUT
     python -m cpprcoder_b200 rows   [--block N] FILE...     # |file|ratio|enc MiB/s|dec MiB/s| per coder
 
-`rows` prints what the reference's run_rangecoder / run_adaptive print (test/main.cpp:104-107,
-:290-294): ratio = original / coded bytes, speeds in MiB/s, and fails loudly on a mismatch.
+`rows` prints what the reference's run_rangecoder / run_adaptive / run_ans / run_ans_simd print
+(test/main.cpp:104-107, :290-294, :367-395, :457-485): ratio = original / coded bytes, speeds in
+MiB/s, and fails loudly on a mismatch.
 All coding happens on the GPU through libb2rc.so.
 """
 from __future__ import annotations
@@ -28,7 +29,8 @@ def _read(path: str) -> np.ndarray:
 def cmd_encode(a) -> int:
     ctx = api.Context()
     data = _read(a.input)
-    out = ctx.encode(api.MODE_ADAPTIVE if a.adaptive else api.MODE_STATIC, data, a.block)
+    mode = api.MODE_ADAPTIVE if a.adaptive else api.MODE_NAMES[a.coder]
+    out = ctx.encode(mode, data, a.block)
     Path(a.output).write_bytes(out.tobytes())
     print(f"{a.input}: {data.size} -> {out.size} bytes ({out.size / max(data.size, 1):.6f})")
     return 0
@@ -47,7 +49,7 @@ def cmd_rows(a) -> int:
     bad = 0
     for path in a.files:
         data = _read(path)
-        for mode in (api.MODE_STATIC, api.MODE_ADAPTIVE):
+        for mode in ctx.supported_modes():
             t0 = time.perf_counter()
             enc = ctx.encode(mode, data, a.block)
             t1 = time.perf_counter()
@@ -66,6 +68,7 @@ def main(argv=None) -> int:
     sub = ap.add_subparsers(dest="cmd", required=True)
     e = sub.add_parser("encode")
     e.add_argument("--adaptive", action="store_true")
+    e.add_argument("--coder", default="static", choices=sorted(api.MODE_NAMES))
     e.add_argument("--block", type=int, default=api.DEFAULT_BLOCK)
     e.add_argument("input")
     e.add_argument("output")

@@ -71,6 +71,11 @@ class Context:
 
     KERNELS = {"histogram": 0, "encode": 1, "scan": 2, "compact": 3, "decode": 4}
 
+    @staticmethod
+    def supported_modes() -> tuple:
+        """Coders this build carries kernels for, in container mode numbers."""
+        return (MODE_STATIC, MODE_ADAPTIVE, MODE_RANS_BYTE, MODE_RANS_WORD)
+
     def profile(self, enable: bool = True):
         self._check(self.lib.b2rc_profile(self.h, 1 if enable else 0), "b2rc_profile")
 

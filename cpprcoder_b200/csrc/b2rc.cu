@@ -106,7 +106,8 @@ bool block_ok(u32 block)
 }
 bool mode_ok(int mode)
 {
-    return mode == B2RC_MODE_STATIC || mode == B2RC_MODE_ADAPTIVE || mode == B2RC_MODE_RANS_WORD;
+    return mode == B2RC_MODE_STATIC || mode == B2RC_MODE_ADAPTIVE || mode == B2RC_MODE_RANS_BYTE ||
+           mode == B2RC_MODE_RANS_WORD;
 }
 bool is_ans(int mode)
 {
@@ -148,6 +149,7 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_static, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static()));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(false)));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
+    CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
     return B2RC_OK;
 }
 
@@ -483,7 +485,13 @@ static int ans_encode_blocks(b2rc_ctx* ctx, int mode, u32 block, const u8* d_src
     }
     {
         KernelTimer kt(ctx, B2RC_K_HISTOGRAM, st);
-        k_ans_model<(int)ANS_WORD_BITS><<<(unsigned)grid, HIST_WARPS * 32, 0, st>>>(d_src, n, block, nb, d_slots, stride);
+        if(mode == B2RC_MODE_RANS_WORD) {
+            k_ans_model<(int)ANS_WORD_BITS><<<(unsigned)grid, HIST_WARPS * 32, 0, st>>>(d_src, n, block, nb, d_slots,
+                                                                                      stride);
+        } else {
+            k_ans_model<(int)ANS_BYTE_BITS><<<(unsigned)grid, HIST_WARPS * 32, 0, st>>>(d_src, n, block, nb, d_slots,
+                                                                                      stride);
+        }
         const int rc = launch_check(ctx, "k_ans_model");
         if(rc != B2RC_OK) {
             return rc;
@@ -499,16 +507,22 @@ static int ans_encode_blocks(b2rc_ctx* ctx, int mode, u32 block, const u8* d_src
     a.slot_stride = stride;
     a.sizes = d_sizes;
     a.err = d_err;
-    (void)mode;
     KernelTimer kt(ctx, B2RC_K_ENCODE, st);
-    k_ans_enc_word<<<(unsigned)((nb + 3) / 4), 32, 0, st>>>(a);
-    return launch_check(ctx, "k_ans_enc_word");
+    if(mode == B2RC_MODE_RANS_WORD) {
+        k_ans_enc_word<<<(unsigned)((nb + 3) / 4), 32, 0, st>>>(a);
+    } else {
+        k_ans_enc_byte<<<(unsigned)((nb + 31) / 32), 32, ANS_ENC_BYTE_SMEM, st>>>(a);
+    }
+    return launch_check(ctx, "k_ans_enc");
 }
 
 static int ans_decode_blocks(b2rc_ctx* ctx, int mode, const DecArgs& a, cudaStream_t st)
 {
-    (void)mode;
     KernelTimer kt(ctx, B2RC_K_DECODE, st);
+    if(mode == B2RC_MODE_RANS_BYTE) {
+        k_ans_dec_byte<<<(unsigned)((a.nblocks + 31) / 32), 32, ANS_DEC_BYTE_SMEM, st>>>(a);
+        return launch_check(ctx, "k_ans_dec_byte");
+    }
     k_ans_dec_word<<<(unsigned)((a.nblocks + 4 * ANS_DEC_WARPS - 1) / (4 * ANS_DEC_WARPS)), 32 * ANS_DEC_WARPS,
                      ANS_DEC_WORD_SMEM, st>>>(a);
     return launch_check(ctx, "k_ans_dec_word");

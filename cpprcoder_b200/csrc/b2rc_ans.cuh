@@ -7,6 +7,8 @@
 //   A2  k_ans_enc_word      rANS::encode_simd                   (cppans.h:567-607)
 //   A3  k_ans_dec_word      rANS::decode_simd                   (cppans.h:609-649)
 //   A4  k_compact_split     header + tail-aligned coded bytes -> contiguous payload
+//   A5  k_ans_enc_byte      rANS::encode                        (cppans.h:497-530)
+//   A6  k_ans_dec_byte      rANS::decode                        (cppans.h:532-564)
 //
 // Mapping of the word variant: the reference interleaves EIGHT rANS states per stream so
 // that SSE can step four at a time; here the eight states of a block are eight LANES, a
@@ -14,11 +16,17 @@
 // who emits / refills in this round, in lane order -- which is a ballot and a popcount.
 // That is eight times the parallelism per block the range coder offers, and no carries.
 //
+// The byte variant has ONE state per stream: a block is one serial chain and gets one lane,
+// 32 blocks per warp, tables interleaved by lane -- the mapping of the range coder kernels
+// (b2rc_kernels.cuh), whose input staging, stream queue and output tiles it reuses; its
+// arithmetic is in ans_lane.cuh and is also run on the CPU by tests/sim.
+//
 // Slot layout while encoding: the model kernel leaves the 1032-byte header (u32 size,
 // u32 cum[257]) at the START of the block's slot; the coder writes its words from the END
 // of the slot downwards, as the reference writes from the end of dst (cppans.h:591);
 // k_compact_split joins the two pieces.
 #pragma once
+#include "ans_lane.cuh"
 #include "b2rc_kernels.cuh"
 
 namespace b2rc
@@ -463,6 +471,271 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_compact_split(const u8* slo
         }
         cta_copy(payload + off, s, head_bytes);
         cta_copy(payload + off + head_bytes, s + slot_stride - (len - head_bytes), len - head_bytes);
+    }
+}
+
+// ======================================================================== A5 ==
+// Byte-variant encode, one block per lane.  Per warp in shared memory: the 257 cumulative
+// counts as u16 (<= 2^14) and the 256 reciprocals as u32, both [entry][lane], and two input
+// tiles staged by cp.async.  The block is walked from its last tile to its first and each
+// tile from its last symbol to its first (cppans.h:516-519).  Emitted bytes collect in a
+// 64-bit register and leave as aligned 32-bit words, downwards from the end of the slot.
+constexpr u32 ANS_ENC_BYTE_CUM = 257u * 64u;                 // u16 x 32 lanes per entry
+constexpr u32 ANS_ENC_BYTE_MAGIC = 256u * 128u;
+constexpr u32 ANS_ENC_BYTE_SMEM = ANS_ENC_BYTE_CUM + ANS_ENC_BYTE_MAGIC + 2u * TILE_BYTES;
+
+struct AnsSlotOut {
+    u8* slot;
+    u32 w;  // write cursor: bytes from the slot start; everything at and above it is written
+    __device__ __forceinline__ void word(u32 v, bool on)
+    {
+        w -= on ? 4u : 0u;
+        if(on) {
+            *reinterpret_cast<u32*>(slot + w) = v;
+        }
+    }
+    __device__ __forceinline__ void byte(u8 v)
+    {
+        w -= 1u;
+        slot[w] = v;
+    }
+};
+
+template <bool RAGGED>
+__device__ __forceinline__ void ans_enc_byte_tiles(const EncArgs& a, u32 cum_a, u32 mag_a, u32 tiles, u64 b0, u32 n_b,
+                                                   u32 ntiles, u32& x, AnsByteAcc& acc, AnsSlotOut& out, u32 lane)
+{
+    auto entry = [&](u32 sym, u32& start, u32& f, u32& mg) {
+        start = lds16(cum_a + sym * 64u);
+        f = lds16(cum_a + sym * 64u + 64u) - start;
+        mg = lds32(mag_a + sym * 128u);
+    };
+    // the last tile was staged (and committed) by the caller into buffer (ntiles - 1) & 1
+#pragma unroll 1
+    for(u32 tix = ntiles; tix-- > 0;) {
+        if(tix > 0) {
+            stage_tile(tiles + ((tix - 1) & 1u) * TILE_BYTES, a.src, a.n, b0, a.block, (tix - 1) * TILE, lane);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+        // four symbols per trip, last word of the tile first; the table entries of the next
+        // trip's symbols are fetched before this trip's are coded
+        u32 word = lds32(row + 4u * (TILE / 4 - 1));
+        u32 st[4], fr[4], mg[4];
+#pragma unroll
+        for(int k = 0; k < 4; ++k) {
+            entry((word >> (8 * k)) & 0xFFu, st[k], fr[k], mg[k]);
+        }
+#pragma unroll 1
+        for(int wi = TILE / 4 - 1; wi >= 0; --wi) {
+            const u32 wnext = lds32(row + 4u * (u32)((wi - 1) & (TILE / 4 - 1)));
+            u32 nst[4], nfr[4], nmg[4];
+#pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                entry((wnext >> (8 * k)) & 0xFFu, nst[k], nfr[k], nmg[k]);
+            }
+#pragma unroll
+            for(int k = 3; k >= 0; --k) {
+                const bool active = !RAGGED || tix * TILE + wi * 4 + k < n_b;
+                AnsPut put;
+                ans_byte_put(x, st[k], fr[k], mg[k], put, active);
+                ans_acc_push(acc, put);
+                if((k & 1) == 0) {
+                    ans_acc_commit(acc, out);
+                }
+            }
+#pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                st[k] = nst[k];
+                fr[k] = nfr[k];
+                mg[k] = nmg[k];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32) k_ans_enc_byte(EncArgs a)
+{
+    extern __shared__ __align__(16) u8 ans_sm[];
+    const u32 sbase = smem_addr(ans_sm);
+    const u32 lane = lane_id();
+    const u32 cum_a = sbase + lane * 2u, mag_a = sbase + ANS_ENC_BYTE_CUM + lane * 4u;
+    const u32 tiles = sbase + ANS_ENC_BYTE_CUM + ANS_ENC_BYTE_MAGIC;
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    u8* slot = a.slots + (has ? b : b0) * a.slot_stride;
+    const u32 n_max = __reduce_max_sync(FULL, n_b);
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+    stage_tile(tiles + ((ntiles - 1) & 1u) * TILE_BYTES, a.src, a.n, b0, a.block, (ntiles - 1) * TILE, lane);
+    cp_async_commit();
+    {
+        // the normalised model the model kernel left at the head of the slot
+        const u32* hdr = reinterpret_cast<const u32*>(slot);
+        u32 c0 = 0;
+#pragma unroll 1
+        for(u32 s = 0; s < 256u; ++s) {
+            const u32 c1 = has ? hdr[2u + s] : 0u;
+            sts16v(cum_a + s * 64u, c0);
+            sts32v(mag_a + s * 128u, rc_magic(c1 - c0));
+            c0 = c1;
+        }
+        sts16v(cum_a + 256u * 64u, c0);
+    }
+    __syncwarp();
+    u32 x = ANS_BYTE_LOW;  // init (cppans.h:260-263)
+    AnsByteAcc acc;
+    ans_acc_init(acc);
+    AnsSlotOut out{slot, (u32)a.slot_stride};
+    if(__any_sync(FULL, n_b != ntiles * TILE)) {
+        ans_enc_byte_tiles<true>(a, cum_a, mag_a, tiles, b0, n_b, ntiles, x, acc, out, lane);
+    } else {
+        ans_enc_byte_tiles<false>(a, cum_a, mag_a, tiles, b0, n_b, ntiles, x, acc, out, lane);
+    }
+    if(has) {
+        ans_acc_finish(acc, x, out);
+        a.sizes[b] = ANS_HDR + ((u32)a.slot_stride - out.w);
+    }
+}
+
+// ======================================================================== A6 ==
+// Byte-variant decode, one block per lane: cumulative counts as u16 [entry][lane] in shared
+// memory, symbol by the 8 x 8 x 4 search of ans_lane.cuh, stream through the per-lane word
+// queue of the range decoder (WordSrc), output through its 64-symbol tiles.
+constexpr u32 ANS_DEC_BYTE_CUM = 257u * 64u;
+constexpr u32 ANS_DEC_BYTE_SMEM = ANS_DEC_BYTE_CUM + TILE_BYTES + INQ_BYTES;
+
+struct AnsCumTab {
+    enum : u32 { UNIT = 64 };  // position = symbol * 64 = byte offset inside the lane's column
+    u32 base;
+    __device__ __forceinline__ u32 at(u32 pos) const { return lds16(base + pos); }
+};
+
+template <bool RAGGED, class Src>
+__device__ __forceinline__ void ans_dec_byte_tile(const AnsCumTab& tab, const u32 (&k1)[8], RcDec& d, u32& x, Src& src,
+                                                  u32 otile_a, u32 tile_off, u32 n_b, u32 lane)
+{
+#pragma unroll 1
+    for(int wi = 0; wi < TILE / 4; ++wi) {
+        u32 word = 0;
+#pragma unroll
+        for(int k = 0; k < 4; ++k) {
+            if(!RAGGED || tile_off + wi * 4 + k < n_b) {
+                const u32 slot = x & ((1u << ANS_BYTE_SCALE_BITS) - 1u);
+                u32 sym, start, f;
+                ans_find(tab, k1, slot, sym, start, f);
+                ans_byte_advance(d, x, slot, start, f, src);
+                word |= sym << (8 * k);
+            }
+        }
+        sts32v(otile_a + lane * ROW + wi * 4, word);
+    }
+}
+
+__global__ void __launch_bounds__(32) k_ans_dec_byte(DecArgs a)
+{
+    extern __shared__ __align__(16) u8 ans_sm[];
+    const u32 sbase = smem_addr(ans_sm);
+    u8* otile = ans_sm + ANS_DEC_BYTE_CUM;
+    const u32 otile_a = sbase + ANS_DEC_BYTE_CUM;
+    const u32 queue_a = otile_a + TILE_BYTES;
+    const u32 lane = lane_id();
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    const u8* pay = a.payload;
+    u64 len = 0;
+    if(has) {
+        const u64 o0 = a.offsets[b], o1 = a.offsets[b + 1];
+        if(o0 <= o1 && o1 <= a.payload_len) {
+            pay = a.payload + o0;
+            len = o1 - o0;
+        }
+    }
+    bool ok = has && len >= (u64)ANS_HDR + 4u;
+    auto ld32u = [&](u32 off) -> u32 {
+        return (u32)pay[off] | ((u32)pay[off + 1u] << 8) | ((u32)pay[off + 2u] << 16) | ((u32)pay[off + 3u] << 24);
+    };
+    if(ok) {
+        ok = ld32u(0) == n_b;  // the container, not the payload, says how long block b is
+    }
+    const u32 cum_a = sbase + lane * 2u;
+    u32 k1[8];
+    {
+        u32 prev = 0;
+        bool sane = true;
+#pragma unroll 1
+        for(u32 s = 0; s <= 256u; ++s) {
+            const u32 c = ok ? ld32u(4u + 4u * s) : (s == 256u ? (1u << ANS_BYTE_SCALE_BITS) : 0u);
+            sane = sane && c >= prev && c <= (1u << ANS_BYTE_SCALE_BITS) && (s != 0u || c == 0u);
+            sts16v(cum_a + s * 64u, c);
+            prev = c;
+        }
+        sane = sane && prev == (1u << ANS_BYTE_SCALE_BITS);
+        if(ok && !sane) {
+            ok = false;
+            // keep the search well defined: one symbol owning the whole scale
+            for(u32 s = 0; s <= 256u; ++s) {
+                sts16v(cum_a + s * 64u, s == 0u ? 0u : (1u << ANS_BYTE_SCALE_BITS));
+            }
+        }
+#pragma unroll
+        for(int j = 0; j < 8; ++j) {
+            k1[j] = lds16v(cum_a + (32u * j) * 64u);
+        }
+    }
+    if(has && !ok) {
+        atomicOr(a.err, ERR_CORRUPT);
+    }
+    if(!ok) {
+        n_b = 0;
+    }
+    WordSrc src;
+    {
+        const u8* coded = pay + ANS_HDR;
+        const u8* wbase = (const u8*)((uintptr_t)coded & ~(uintptr_t)3);
+        src.base = reinterpret_cast<const u32*>(wbase);
+        const u64 room = (u64)((a.payload + a.payload_len) - wbase);
+        src.lim = ok ? (u32)(room < 0xFFFFFFF0ull ? room : 0xFFFFFFF0ull) : 0u;
+        src.q = queue_a + lane * 4u;
+        src.prime();
+    }
+    __syncwarp();
+    const AnsCumTab tab{cum_a};
+    RcDec d;
+    u32 x = ans_byte_dec_init(d, (u32)((uintptr_t)(pay + ANS_HDR) & 3u), src);
+    const u32 n_max = __reduce_max_sync(FULL, n_b);
+    const bool ragged = __any_sync(FULL, n_b != n_max) || (n_max % TILE) != 0u;
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+#pragma unroll 1
+    for(u32 tix = 0; tix < ntiles; ++tix) {
+        const bool inside = __all_sync(FULL, src.tile_is_inside());
+        if(!ragged && inside) {
+            WordSrcInside in{src};
+            ans_dec_byte_tile<false>(tab, k1, d, x, in, otile_a, tix * TILE, n_b, lane);
+        } else {
+            ans_dec_byte_tile<true>(tab, k1, d, x, src, otile_a, tix * TILE, n_b, lane);
+        }
+        __syncwarp();
+        store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
+        __syncwarp();
+    }
+    // a valid stream hands the state back where the encoder started it (cppans.h:260-263)
+    if(ok && x != ANS_BYTE_LOW) {
+        atomicOr(a.err, ERR_CORRUPT);
     }
 }
 

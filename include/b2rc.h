@@ -39,7 +39,7 @@ extern "C" {
 /* The sibling static rANS coder of the reference (cppans.h), on the same container:
  * payload = u32 LE size, 257 x u32 LE normalised cumulative counts, coded bytes -- what
  * cppans::rANS leaves at the END of its dst buffer (cppans.h:521-529, :598-605). */
-#define B2RC_MODE_RANS_BYTE 2 /* rANS::encode / ::decode            cppans.h:497-564 (not built yet) */
+#define B2RC_MODE_RANS_BYTE 2 /* rANS::encode / ::decode            cppans.h:497-564 */
 #define B2RC_MODE_RANS_WORD 3 /* rANS::encode_simd / ::decode_simd  cppans.h:567-649 */
 
 #define B2RC_DEFAULT_BLOCK 65536u

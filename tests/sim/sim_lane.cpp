@@ -3,6 +3,7 @@
 // decoder, count-tree model, magic division) can be checked against the oracle
 // without a GPU.  TEST INFRASTRUCTURE: built and loaded by tests/test_sim_lane.py only.
 #include "../../cpprcoder_b200/csrc/rc_lane.cuh"
+#include "../../cpprcoder_b200/csrc/ans_lane.cuh"
 
 #include <cstring>
 #include <vector>
@@ -224,6 +225,95 @@ long sim_decode(int mode, const u8* stream, size_t stream_len, u32 lead, u8* dst
             rc_model_decode(tab, d.low, t, sym, cum, freq);
             dst[i] = (u8)sym;
             rc_dec_advance(d, cum, freq, t, rd);
+        }
+    }
+    return (long)want;
+}
+
+// ---- byte-wise rANS (ans_lane.cuh).  `cum` = the normalised 257-entry cumulative table the
+// model step produced (tests take it from the oracle; the kernels from k_ans_model).
+long sim_ans_byte_encode(const u8* src, u32 n, const u32* cum, u8* dst, size_t cap)
+{
+    struct BackSink {
+        std::vector<u8> rev;  // bytes in emission order = descending address
+        void word(u32 w, bool on)
+        {
+            if(on) {
+                rev.push_back((u8)(w >> 24));
+                rev.push_back((u8)(w >> 16));
+                rev.push_back((u8)(w >> 8));
+                rev.push_back((u8)w);
+            }
+        }
+        void byte(u8 b) { rev.push_back(b); }
+    } sink;
+    u32 magic[256];
+    for(int s = 0; s < 256; ++s) {
+        magic[s] = rc_magic(cum[s + 1] - cum[s]);
+    }
+    u32 x = ANS_BYTE_LOW;
+    AnsByteAcc acc;
+    ans_acc_init(acc);
+    // last symbol first, two puts per commit -- the shape of the kernel's loop
+    const u32 n2 = (n + 1u) & ~1u;
+    for(u32 i = n2; i > 0; i -= 2) {
+        for(u32 k = 0; k < 2; ++k) {
+            const u32 p = i - 1u - k;
+            const bool active = p < n;
+            const u32 c = active ? src[p] : 0;
+            AnsPut put;
+            ans_byte_put(x, cum[c], cum[c + 1] - cum[c], magic[c], put, active);
+            ans_acc_push(acc, put);
+        }
+        ans_acc_commit(acc, sink);
+    }
+    ans_acc_finish(acc, x, sink);
+    const size_t total = ANS_HDR_BYTES + sink.rev.size();
+    if(total > cap) {
+        return -1;
+    }
+    memcpy(dst, &n, 4);
+    memcpy(dst + 4, cum, 257 * 4);
+    for(size_t i = 0; i < sink.rev.size(); ++i) {
+        dst[ANS_HDR_BYTES + i] = sink.rev[sink.rev.size() - 1 - i];
+    }
+    return (long)total;
+}
+
+long sim_ans_byte_decode(const u8* stream, size_t stream_len, u32 lead, u8* dst, size_t cap)
+{
+    const u8* pay = stream + lead;
+    u32 want;
+    memcpy(&want, pay, 4);
+    if(want > cap) {
+        return -1;
+    }
+    u32 cum[257];
+    memcpy(cum, pay + 4, sizeof cum);
+    struct CumTab {
+        enum : u32 { UNIT = 1 };
+        const u32* c;
+        u32 at(u32 i) const { return c[i]; }
+    } ctab{cum};
+    u32 k1[8];
+    for(int j = 0; j < 8; ++j) {
+        k1[j] = cum[32 * j];
+    }
+    const size_t coded = lead + ANS_HDR_BYTES;
+    WordReader rd{stream, stream_len, coded & ~(size_t)3};
+    RcDec d;
+    u32 x = ans_byte_dec_init(d, (u32)(coded & 3), rd);
+    for(u32 i = 0; i < want; ++i) {
+        const u32 slot = x & ((1u << ANS_BYTE_SCALE_BITS) - 1u);
+        u32 sym, start, f;
+        ans_find(ctab, k1, slot, sym, start, f);
+        if(start != cum[sym] || f != cum[sym + 1] - cum[sym] || slot < start || slot - start >= f) {
+            return -2;
+        }
+        dst[i] = (u8)sym;
+        ans_byte_advance(d, x, slot, start, f, rd);
+        if(x < ANS_BYTE_LOW) {
+            return -3;
         }
     }
     return (long)want;

@@ -6,11 +6,12 @@ import numpy as np
 import pytest
 
 from _cases import crafted_stream
-from _oracle import CANTERBURY, GOLDEN, RANS_HEADER, RANS_WORD, Oracle, canterbury, fnv1a64, offsets_of
+from _oracle import CANTERBURY, GOLDEN, RANS_BYTE, RANS_HEADER, RANS_WORD, Oracle, canterbury, fnv1a64, offsets_of
 from cpprcoder_b200 import container, synth
 
 pytestmark = pytest.mark.gpu
-MODES = [(RANS_WORD, "rans_word")]
+MODES = [(RANS_BYTE, "rans_byte"), (RANS_WORD, "rans_word")]
+KEY_OF = dict(MODES)
 
 
 @pytest.fixture(scope="module")
@@ -99,19 +100,17 @@ def test_edges(ctx, oracle, golden_rans):
     # single-block inputs of the golden file: the reference's own bytes
     from test_ans_oracle import EDGE
     for ent in golden_rans["edge"]:
-        if ent["mode"] != "rans_word":
-            continue
+        mode = RANS_BYTE if ent["mode"] == "rans_byte" else RANS_WORD
         d = np.frombuffer(EDGE[ent["label"]], dtype=np.uint8)
-        _, pays = payloads_of(ctx.encode(RANS_WORD, d, 65536))
-        assert len(pays[0]) == ent["size"] and f"{fnv1a64(pays[0]):016x}" == ent["fnv"], ent["label"]
+        _, pays = payloads_of(ctx.encode(mode, d, 65536))
+        assert len(pays[0]) == ent["size"] and f"{fnv1a64(pays[0]):016x}" == ent["fnv"], (ent["label"], ent["mode"])
 
 
 def test_synthetic_golden_vectors(ctx, golden_rans):
     for ent in golden_rans["synthetic"]:
-        if ent["mode"] != "rans_word":
-            continue
+        mode = RANS_BYTE if ent["mode"] == "rans_byte" else RANS_WORD
         d = synth.GENERATORS[ent["gen"]](ent["n"])
-        enc = ctx.encode(RANS_WORD, d, ent["block"])
+        enc = ctx.encode(mode, d, ent["block"])
         _, pays = payloads_of(enc)
         assert [len(p) for p in pays] == ent["sizes"], (ent["gen"], ent["block"])
         assert f"{fnv1a64(b''.join(pays)):016x}" == ent["cat_fnv"]
@@ -141,27 +140,29 @@ def test_kernel_doors_step_by_step(ctx, oracle):
         head = slots.view(-1, stride)[:nb, :RANS_HEADER].cpu().numpy().copy().view(np.uint32)
         for b in (0, 1, nb // 2, nb - 1):
             blk = data[b * block:(b + 1) * block]
-            _, cum = oracle.rans_model(blk, 12)
+            _, cum = oracle.rans_model(blk, 12 if mode == RANS_WORD else 14)
             assert head[b][0] == blk.size and (head[b][1:] == cum).all(), f"model of block {b}"
         offsets = ctx.scan(sizes, nb)
         total = int(offsets[nb].item())
         payload = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
-        ctx.compact(slots, stride, sizes, offsets, nb, payload[2:], err, mode)   # a 2-byte aligned destination
+        lead = 2 if mode == RANS_WORD else 3                                     # word payloads need even addresses
+        ctx.compact(slots, stride, sizes, offsets, nb, payload[lead:], err, mode)
         want = oracle.encode_blocks(mode, data, block, threads=4)
         assert total == sum(len(p) for p in want)
-        assert payload[2:2 + total].cpu().numpy().tobytes() == b"".join(want)
+        assert payload[lead:lead + total].cpu().numpy().tobytes() == b"".join(want)
         dst = torch.zeros(n, dtype=torch.uint8, device="cuda")
-        pl = payload[2:2 + total + 32]
+        pl = payload[lead:lead + total + 32]
         ctx.decode_blocks(mode, pl, total, offsets, nb, dst, n, block, err)
         torch.cuda.synchronize()
         assert int(err[0].item()) == 0
         assert dst.cpu().numpy().tobytes() == data.tobytes()
 
 
-def test_corrupt_payloads_are_rejected(ctx, oracle):
+@pytest.mark.parametrize("mode", [RANS_BYTE, RANS_WORD])
+def test_corrupt_payloads_are_rejected(ctx, oracle, mode):
     from cpprcoder_b200.api import B2rcError
     data = synth.zipf(65536 * 3 + 100)
-    enc = ctx.encode(RANS_WORD, data, 65536)
+    enc = ctx.encode(mode, data, 65536)
     info = container.parse(enc)
     base = info.payload_base + int(info.offsets[1])
     bad = enc.copy()
@@ -179,7 +180,8 @@ def test_corrupt_payloads_are_rejected(ctx, oracle):
     with pytest.raises(B2rcError) as e:
         ctx.decode(bad)
     assert e.value.code == -3
-    # an odd offset in the index (word payloads are 2-byte aligned)
+    # an odd offset in the index: word payloads are 2-byte aligned; for the byte coder the
+    # shifted block no longer starts with its size
     bad = enc.copy()
     off = bad[32:32 + 8 * (info.nblocks + 1)].view(np.uint64)
     off[1] += 1
@@ -196,8 +198,10 @@ def test_corrupt_payloads_are_rejected(ctx, oracle):
     assert ctx.decode(enc).tobytes() == data.tobytes()
 
 
-def test_device_api_and_large_property(ctx, oracle):
+@pytest.mark.parametrize("mode", [RANS_BYTE, RANS_WORD])
+def test_device_api_and_large_property(ctx, oracle, mode):
     import torch
+    RANS_WORD = mode  # noqa: N806 -- the body below is the same for both coders
     n = (256 << 20) + 12345
     data = synth.zipf(n)
     src = torch.from_numpy(data).cuda()

@@ -76,3 +76,47 @@ def test_lane_coder_on_canterbury_blocks(sim, name):
             blk = data[i * 65536:(i + 1) * 65536]
             assert _enc(sim, mode, np.frombuffer(blk, np.uint8)) == p
             assert _dec(sim, mode, p, len(blk), (i + 1) % 4) == blk
+
+
+# ---- byte-wise rANS lane arithmetic (cpprcoder_b200/csrc/ans_lane.cuh) --------------------
+def _ans_fns(sim):
+    sim.sim_ans_byte_encode.restype = C.c_long
+    sim.sim_ans_byte_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]
+    sim.sim_ans_byte_decode.restype = C.c_long
+    sim.sim_ans_byte_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t]
+    return sim
+
+
+def _ans_enc(sim, o, d):
+    d = np.ascontiguousarray(d, dtype=np.uint8)
+    _, cum = o.rans_model(d, 14)
+    cap = 2 * d.size + 2048
+    out = np.empty(cap, np.uint8)
+    r = sim.sim_ans_byte_encode(d.ctypes.data_as(C.c_void_p), d.size, cum.ctypes.data_as(C.c_void_p),
+                                out.ctypes.data_as(C.c_void_p), cap)
+    assert r >= 0
+    return out[:r].tobytes()
+
+
+def _ans_dec(sim, pay, n, lead):
+    st = np.frombuffer(bytes(lead) + pay + bytes(11), dtype=np.uint8).copy()
+    st[:lead] = 0xA5
+    out = np.empty(max(n, 1), np.uint8)
+    r = sim.sim_ans_byte_decode(st.ctypes.data_as(C.c_void_p), len(st) - 11, lead, out.ctypes.data_as(C.c_void_p), n)
+    assert r == n, r
+    return out[:n].tobytes()
+
+
+def test_rans_byte_lane_matches_oracle(sim):
+    from _oracle import RANS_BYTE
+    _ans_fns(sim)
+    o = Oracle.get()
+    rng = np.random.default_rng(11)
+    cases = [crafted(it % 7, 65536 if it % 3 == 0 else int(rng.integers(1, 65537)), rng) for it in range(60)]
+    cases += [np.frombuffer(b, np.uint8) for b in (b"A", b"AB", b"A" * 65536, bytes(range(256)) * 5,
+                                                   b"A" * 60000 + bytes(range(256)))]
+    cases += [np.frombuffer(canterbury(n)[:65536], np.uint8) for n in ("alice29.txt", "kennedy.xls", "ptt5", "sum")]
+    for it, d in enumerate(cases):
+        want = o.encode(RANS_BYTE, d)
+        assert _ans_enc(sim, o, d) == want, (it, d.size)
+        assert _ans_dec(sim, want, d.size, it % 4) == d.tobytes(), (it, d.size)

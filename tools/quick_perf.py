@@ -36,7 +36,7 @@ def main():
     src = torch.from_numpy(data).cuda()
     print(f"generated {n} bytes of {gen} in {time.time() - t0:.1f}s, block {block}", flush=True)
     nb = api.nblocks(n, block)
-    which = sys.argv[4].split(",") if len(sys.argv) > 4 else ["static", "adaptive", "rans-word"]
+    which = sys.argv[4].split(",") if len(sys.argv) > 4 else ["static", "adaptive", "rans", "rans-word"]
     for name in which:
         mode = api.MODE_NAMES[name]
         freq = None
