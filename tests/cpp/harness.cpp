@@ -5,8 +5,10 @@
 // :1170-1197); unlike the reference's harness, a mismatch or a failed call is an error exit.
 //
 //   harness <file>...            static + adaptive round trip of every file
+//   harness --ans <file>...      rANS byte + word round trip (run_ans / run_ans_simd, test/main.cpp:367-545)
 //   harness --selftest           the 127-nibble static test and the chunked adaptive API
 #include "../../cpprcoder_b200/include/cpprcoder_b200.h"
+#include "../../cpprcoder_b200/include/cppans_b200.h"
 
 #include <chrono>
 #include <cstdio>
@@ -171,6 +173,54 @@ bool test_adaptive_chunked()
     }
     return r.status_ == cpprcoder::Status_Success && same(decstream, src);
 }
+// run_ans / run_ans_simd (test/main.cpp:397-455, :487-545): the encoder fills `encoded` from its
+// end, the decoder is handed encoded + dst_size - result0.
+bool run_ans(const char* filepath, const std::vector<cpprcoder::u8>& src, bool simd)
+{
+    using namespace cppans;
+    const u32 size = static_cast<u32>(src.size());
+    if(0 == size) {
+        return true;  // the reference asserts 0 < src_size
+    }
+    const u64 dst_size = rANS::calc_encoded_size(size);
+    std::vector<u8> encoded(dst_size), decoded(size);
+    double t = now();
+    const u32 result0 = simd ? rANS::encode_simd(static_cast<u32>(dst_size), encoded.data(), size, src.data())
+                             : rANS::encode(static_cast<u32>(dst_size), encoded.data(), size, src.data());
+    if(0 == result0) {
+        printf("%s: rANS encode failed\n", filepath);
+        return false;
+    }
+    const double deflateTime = now() - t;
+    t = now();
+    const u8* encoded_start = encoded.data() + dst_size - result0;
+    const u32 result1 = simd ? rANS::decode_simd(size, decoded.data(), result0, encoded_start)
+                             : rANS::decode(size, decoded.data(), result0, encoded_start);
+    if(0 == result1) {
+        printf("%s: rANS decode failed\n", filepath);
+        return false;
+    }
+    const double inflateTime = now() - t;
+    print(filepath, (double)size / result0, size / deflateTime / (1024.0 * 1024.0), size / inflateTime / (1024.0 * 1024.0));
+    // too small a destination is refused with 0, as in the reference (cppans.h:523-525, :541-543)
+    if(0 != (simd ? rANS::encode_simd(result0 - 1, encoded.data(), size, src.data())
+                  : rANS::encode(result0 - 1, encoded.data(), size, src.data()))) {
+        printf("%s: rANS encode into too small a buffer did not fail\n", filepath);
+        return false;
+    }
+    if(size > 1 && 0 != (simd ? rANS::decode_simd(size - 1, decoded.data(), result0, encoded_start)
+                              : rANS::decode(size - 1, decoded.data(), result0, encoded_start))) {
+        printf("%s: rANS decode into too small a buffer did not fail\n", filepath);
+        return false;
+    }
+    for(u32 i = 0; i < size; ++i) {
+        if(decoded[i] != src[i]) {
+            printf("[%u] %d != %d\n", i, decoded[i], src[i]);
+            return false;
+        }
+    }
+    return true;
+}
 }  // namespace
 
 int main(int argc, char** argv)
@@ -182,7 +232,8 @@ int main(int argc, char** argv)
         return (a && b) ? 0 : 1;
     }
     int bad = 0;
-    for(int i = 1; i < argc; ++i) {
+    const bool ans = argc >= 2 && std::string(argv[1]) == "--ans";
+    for(int i = ans ? 2 : 1; i < argc; ++i) {
         std::ifstream file(argv[i], std::ios::binary);
         if(!file.is_open()) {
             printf("cannot open %s\n", argv[i]);
@@ -190,6 +241,11 @@ int main(int argc, char** argv)
             continue;
         }
         std::vector<cpprcoder::u8> src((std::istreambuf_iterator<char>(file)), std::istreambuf_iterator<char>());
+        if(ans) {
+            bad += run_ans(argv[i], src, false) ? 0 : 1;
+            bad += run_ans(argv[i], src, true) ? 0 : 1;
+            continue;
+        }
         bad += run_rangecoder(argv[i], src) ? 0 : 1;
         bad += run_adaptive(argv[i], src) ? 0 : 1;
     }

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from _oracle import ADAPTIVE, STATIC, Oracle
+from _oracle import ADAPTIVE, RANS_BYTE, RANS_WORD, STATIC, Oracle
 from cpprcoder_b200 import container
 from cpprcoder_b200 import dist as rcdist
 from cpprcoder_b200 import synth
@@ -51,7 +51,8 @@ def _worker(rank, world, port, n_total, block, mode, out_dir):
 
 
 @pytest.mark.parametrize("world,n_total,block,mode", [(2, 5 * 4096 + 123, 4096, STATIC), (2, 300, 4096, ADAPTIVE),
-                                                      (3, 10 * 1024, 1024, ADAPTIVE)])
+                                                      (3, 10 * 1024, 1024, ADAPTIVE),
+                                                      (2, 9 * 4096 + 77, 4096, RANS_WORD), (3, 7 * 1024 + 1, 1024, RANS_BYTE)])
 def test_sharded_index_exchange_and_stitching(tmp_path, built, world, n_total, block, mode):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, n_total, block, mode, str(tmp_path)), nprocs=world, join=True)

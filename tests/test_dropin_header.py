@@ -56,16 +56,29 @@ def test_canterbury_rows_on_gpu(harness, tmp_path, golden):
 
 
 @pytest.mark.gpu
+def test_rans_rows_on_gpu(harness, tmp_path):
+    # cppans::rANS through the drop-in header, both variants, the reference harness's call sequence
+    with tarfile.open(ROOT / "tests" / "golden" / "cantrbry.tar.bz2", "r:bz2") as tf:
+        tf.extractall(tmp_path, filter="data")
+    files = sorted(str(p) for p in (tmp_path / "cantrbry").iterdir())
+    r = subprocess.run([str(harness), "--ans"] + files, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [line.split("|") for line in r.stdout.splitlines() if line.startswith("|")]
+    assert len(rows) == 2 * len(files)
+    assert all(float(row[2]) > 0.9 for row in rows)
+
+
+@pytest.mark.gpu
 def test_file_cli_round_trip(tmp_path):
     import subprocess
     import sys
     with tarfile.open(ROOT / "tests" / "golden" / "cantrbry.tar.bz2", "r:bz2") as tf:
         tf.extractall(tmp_path, filter="data")
     src = tmp_path / "cantrbry" / "lcet10.txt"
-    for flag in ([], ["--adaptive"]):
+    for flag in ([], ["--adaptive"], ["--coder", "rans"], ["--coder", "rans-word"]):
         enc, dec = tmp_path / "x.b2rc", tmp_path / "x.out"
         subprocess.check_call([sys.executable, "-m", "cpprcoder_b200", "encode", *flag, str(src), str(enc)], cwd=ROOT)
         subprocess.check_call([sys.executable, "-m", "cpprcoder_b200", "decode", str(enc), str(dec)], cwd=ROOT)
         assert dec.read_bytes() == src.read_bytes()
     r = subprocess.run([sys.executable, "-m", "cpprcoder_b200", "rows", str(src)], cwd=ROOT, capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.count("|") == 10
+    assert r.returncode == 0 and r.stdout.count("|") == 20  # four coders, five bars per row
