@@ -632,7 +632,11 @@ __device__ __forceinline__ void ans_dec_byte_tile(const AnsCumTab& tab, const u3
                 const u32 slot = x & ((1u << ANS_BYTE_SCALE_BITS) - 1u);
                 u32 sym, start, f;
                 ans_find(tab, k1, slot, sym, start, f);
-                ans_byte_advance(d, x, slot, start, f, src);
+                if(k & 1) {
+                    ans_byte_advance<true>(d, x, slot, start, f, src);
+                } else {
+                    ans_byte_advance<false>(d, x, slot, start, f, src);
+                }
                 word |= sym << (8 * k);
             }
         }

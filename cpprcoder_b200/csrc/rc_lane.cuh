@@ -517,9 +517,9 @@ RC_HD void rc_dec_refill(RcDec& d, Next& next)
 {
     const bool need = d.wbits < 32;
     const u32 w = next.take(need);
-    const u32 have = (u32)d.wbits & 31u;
+    const u32 have = (u32)d.wbits & 31u;  // 0 when a pair of symbols drained the window exactly
     d.w_hi = need ? (d.w_hi | (w >> have)) : d.w_hi;
-    d.w_lo = need ? (w << (32u - have)) : d.w_lo;
+    d.w_lo = need ? rc_funnel_r(0u, w, have) : d.w_lo;  // w << (32 - have), and 0 for have == 0
     d.wbits += need ? 32 : 0;
 }
 
@@ -541,7 +541,10 @@ RC_HD void rc_dec_advance(RcDec& d, u32 cum, u32 freq, u32 t, Next& next)
 // Same as rc_dec_advance for a power-of-two total: the chain is carried by
 // t = range >> shift (see rc_enc_step_pow2); d.range is not maintained.
 // MAXSH = 2 when range >= 2^8 is guaranteed (total <= 2^16), else 3.
-template <int MAXSH, class Next>
+// REFILL = false skips the top-up: with MAXSH = 2 a symbol takes at most 16 bits, so a
+// window holding >= 32 bits serves two symbols and is topped up after every second one
+// (one stream word covers what a pair can take).
+template <int MAXSH, bool REFILL = true, class Next>
 RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, Next& next)
 {
     d.low -= cum * t;
@@ -552,7 +555,9 @@ RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, N
     d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);
     d.w_lo <<= sh;
     d.wbits -= (s32)sh;
-    rc_dec_refill(d, next);
+    if(REFILL) {
+        rc_dec_refill(d, next);
+    }
 }
 
 // ------------------------------------------------------------- adaptive model --
