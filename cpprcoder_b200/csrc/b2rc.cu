@@ -18,6 +18,8 @@ using namespace b2rc;
 #define B2RC_PIPE_STREAMS 16
 #define B2RC_PIPE_CHUNKS 16
 #define B2RC_PIPE_MIN_CHUNK (64ull << 20)  // bytes of input per chunk, at least
+#define B2RC_PHASES 8                       // launches per chunk of the phased static decode, at most
+#define B2RC_PHASE_MIN_SYMS 16384u          // symbols per block and launch, at least
 
 struct b2rc_ctx {
     int device;
@@ -39,9 +41,16 @@ struct b2rc_ctx {
     // a device array of running payload ends (one per chunk) mirrored in pinned host memory
     cudaStream_t pipe[B2RC_PIPE_STREAMS];
     cudaEvent_t scan_done[B2RC_PIPE_CHUNKS], chunk_done[B2RC_PIPE_CHUNKS], index_ready;
+    // phased static decode (b2rc_decode): per (chunk, phase) "kernel done" events, one D2H stream
+    // per phase index, the parked coder state of every block
+    cudaEvent_t phase_done[B2RC_PIPE_CHUNKS][B2RC_PHASES];
+    cudaStream_t d2h[B2RC_PHASES];
+    u32* dec_state;
+    size_t dec_state_cap;
     u64* d_ends;  // B2RC_PIPE_CHUNKS + 1
     u64* h_ends;  // pinned
     u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
+    u64 max_phases;  // <= B2RC_PHASES; env B2RC_PHASES overrides (1 switches the phased decode off)
     struct Result {
         int err;
         int pad;
@@ -298,6 +307,13 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
             ctx->max_chunks = (u64)v;
         }
     }
+    ctx->max_phases = 4;  // measured on B200: 4 and 8 launches per chunk time the same
+    if(const char* e = getenv("B2RC_PHASES")) {
+        const long v = atol(e);
+        if(v >= 1 && v <= B2RC_PHASES) {
+            ctx->max_phases = (u64)v;
+        }
+    }
     int rc = B2RC_OK;
     do {
         if(!cuda_ok(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
@@ -326,6 +342,17 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
             !cuda_ok(ctx, cudaMalloc((void**)&ctx->d_ends, 8 * (B2RC_PIPE_CHUNKS + 1)), "cudaMalloc") ||
             !cuda_ok(ctx, cudaMallocHost((void**)&ctx->h_ends, 8 * (B2RC_PIPE_CHUNKS + 1)), "cudaMallocHost"))) {
             rc = B2RC_E_CUDA;
+        }
+        for(int k = 0; k < B2RC_PHASES && rc == B2RC_OK; ++k) {
+            if(!cuda_ok(ctx, cudaStreamCreateWithFlags(&ctx->d2h[k], cudaStreamNonBlocking), "cudaStreamCreate")) {
+                rc = B2RC_E_CUDA;
+            }
+            for(int c = 0; c < B2RC_PIPE_CHUNKS && rc == B2RC_OK; ++c) {
+                if(!cuda_ok(ctx, cudaEventCreateWithFlags(&ctx->phase_done[c][k], cudaEventDisableTiming),
+                            "cudaEventCreate")) {
+                    rc = B2RC_E_CUDA;
+                }
+            }
         }
         for(int k = 0; k < B2RC_K_COUNT && rc == B2RC_OK; ++k) {
             for(int e = 0; e < 2; ++e) {
@@ -384,6 +411,18 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     if(ctx->index_ready) {
         cudaEventDestroy(ctx->index_ready);
     }
+    for(int k = 0; k < B2RC_PHASES; ++k) {
+        if(ctx->d2h[k]) {
+            cudaStreamSynchronize(ctx->d2h[k]);
+            cudaStreamDestroy(ctx->d2h[k]);
+        }
+        for(int c = 0; c < B2RC_PIPE_CHUNKS; ++c) {
+            if(ctx->phase_done[c][k]) {
+                cudaEventDestroy(ctx->phase_done[c][k]);
+            }
+        }
+    }
+    cudaFree(ctx->dec_state);
     cudaFree(ctx->d_ends);
     if(ctx->h_ends) {
         cudaFreeHost(ctx->h_ends);
@@ -656,9 +695,22 @@ int b2rc_k_compact_for(b2rc_ctx* ctx, int mode, const uint8_t* d_slots, uint64_t
     return launch_check(ctx, "k_compact");
 }
 
+static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload, uint64_t payload_len,
+                         const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n, int* d_err,
+                         void* cuda_stream, u32 sym0, u32 nsym, u32* d_state);
+
 int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload,
                          uint64_t payload_len, const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n,
                          int* d_err, void* cuda_stream)
+{
+    return decode_launch(ctx, mode, block_size, d_payload, payload_len, d_offsets, nblocks, d_dst, n, d_err, cuda_stream,
+                         0u, 0u, nullptr);
+}
+
+// sym0 / nsym / d_state: phased decode of the static coder (DecArgs); 0, 0, null = whole blocks
+static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload, uint64_t payload_len,
+                         const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n, int* d_err,
+                         void* cuda_stream, u32 sym0, u32 nsym, u32* d_state)
 {
     if(!ctx || !d_payload || !d_offsets || !d_dst || !d_err || !mode_ok(mode) || !block_ok(block_size) ||
        !aligned16(d_dst) || ((uintptr_t)d_offsets & 7u) || nblocks != b2rc_nblocks(n, block_size) ||
@@ -679,6 +731,12 @@ int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     a.dst = d_dst;
     a.n = n;
     a.err = d_err;
+    a.sym0 = sym0;
+    a.nsym = nsym;
+    a.state = d_state;
+    if(nsym && (mode != B2RC_MODE_STATIC || !d_state || (sym0 % TILE) || (nsym % TILE))) {
+        return B2RC_E_ARG;
+    }
     if(is_ans(mode)) {
         return ans_decode_blocks(ctx, mode, a, st);
     }
@@ -978,6 +1036,19 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
         return rc;
     }
     const Chunks ch = plan_chunks(ctx, total, block);
+    // static coder, long blocks, more than one chunk in flight: decode in phases (see below)
+    u32 phases = 1, per = block;
+    if(mode == B2RC_MODE_STATIC && block >= 2u * B2RC_PHASE_MIN_SYMS && ch.count > 1 && ctx->max_phases > 1) {
+        phases = block / B2RC_PHASE_MIN_SYMS;
+        if(phases > ctx->max_phases) {
+            phases = (u32)ctx->max_phases;
+        }
+        per = ((block / phases) + 63u) & ~63u;
+        phases = (block + per - 1) / per;
+        if((rc = grow(ctx, ctx->dec_state, ctx->dec_state_cap, (size_t)(nb * 32 + 64))) != B2RC_OK) {
+            return rc;
+        }
+    }
     cudaStream_t s0 = ctx->pipe[0];
     const u64* d_offsets = reinterpret_cast<const u64*>(ctx->stage_in + B2RC_HEADER_BYTES);
     CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), s0));
@@ -997,14 +1068,49 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
         if(p1 > p0) {
             CK(cudaMemcpyAsync(ctx->stage_in + idx + p0, src + idx + p0, p1 - p0, cudaMemcpyHostToDevice, st));
         }
-        if((rc = b2rc_k_decode_blocks(ctx, mode, block, ctx->stage_in + idx, payload_len, d_offsets + b0, b1 - b0,
-                                      ctx->stage_out + byte0, bytes, ctx->d_err, st)) != B2RC_OK) {
-            return rc;
+        if(phases <= 1) {
+            if((rc = b2rc_k_decode_blocks(ctx, mode, block, ctx->stage_in + idx, payload_len, d_offsets + b0, b1 - b0,
+                                          ctx->stage_out + byte0, bytes, ctx->d_err, st)) != B2RC_OK) {
+                return rc;
+            }
+            CK(cudaMemcpyAsync(dst + byte0, ctx->stage_out + byte0, bytes, cudaMemcpyDeviceToHost, st));
+            continue;
         }
-        CK(cudaMemcpyAsync(dst + byte0, ctx->stage_out + byte0, bytes, cudaMemcpyDeviceToHost, st));
+        // Phased: a launch decodes the next `per` symbols of every block of the chunk, and that
+        // stripe of the output goes home (a 2-D copy, one row per block) while the next launch
+        // runs.  A static decode launch takes as long for one block as for a thousand -- the
+        // chain is serial per block -- so without this the first byte of a chunk's output would
+        // only leave the GPU when the whole chunk is done.
+        const u64 full_rows = bytes / block;          // blocks of the chunk that are complete
+        const u32 tail = (u32)(bytes - full_rows * block);  // the stream's ragged last block, if here
+        for(u32 p = 0; p < phases; ++p) {
+            const u32 s0 = p * per;
+            const u32 ns = (p + 1 == phases) ? (((block - s0) + 63u) & ~63u) : per;
+            if((rc = decode_launch(ctx, mode, block, ctx->stage_in + idx, payload_len, d_offsets + b0, b1 - b0,
+                                   ctx->stage_out + byte0, bytes, ctx->d_err, st, s0, ns, ctx->dec_state + b0 * 8)) !=
+               B2RC_OK) {
+                return rc;
+            }
+            CK(cudaEventRecord(ctx->phase_done[c][p], st));
+            cudaStream_t out = ctx->d2h[p];
+            CK(cudaStreamWaitEvent(out, ctx->phase_done[c][p], 0));
+            const u32 width = (s0 + ns <= block) ? ns : block - s0;
+            if(full_rows) {
+                CK(cudaMemcpy2DAsync(dst + byte0 + s0, block, ctx->stage_out + byte0 + s0, block, width, full_rows,
+                                     cudaMemcpyDeviceToHost, out));
+            }
+            if(tail > s0) {
+                const u32 tw = tail - s0 < width ? tail - s0 : width;
+                CK(cudaMemcpyAsync(dst + byte0 + full_rows * block + s0, ctx->stage_out + byte0 + full_rows * block + s0,
+                                   tw, cudaMemcpyDeviceToHost, out));
+            }
+        }
     }
     for(int k = 1; k < B2RC_PIPE_STREAMS; ++k) {
         CK(cudaStreamSynchronize(ctx->pipe[k]));
+    }
+    for(int k = 0; k < B2RC_PHASES; ++k) {
+        CK(cudaStreamSynchronize(ctx->d2h[k]));
     }
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, s0));
     CK(cudaStreamSynchronize(s0));

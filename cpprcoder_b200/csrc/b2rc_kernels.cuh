@@ -730,6 +730,11 @@ struct DecArgs {
     u8* dst;
     u64 n;
     int* err;
+    // Phased decode (host pipeline): symbols [sym0, sym0 + nsym) of every block in this launch,
+    // coder state carried between launches in `state` (8 words per block).  nsym == 0: the
+    // whole block in one launch, `state` unused.
+    u32 sym0, nsym;
+    u32* state;
 };
 
 // Each lane reads its own payload at its own pace, one aligned word at a time.  Words
@@ -775,15 +780,15 @@ struct WordSrc {
     // true when every word a tile of TILE symbols can request (3 bytes per symbol at most, plus
     // the queue's look-ahead) lies inside the buffer
     __device__ __forceinline__ bool tile_is_inside() const { return (u64)(rd + TILE + 2u * INQ) * 4u <= (u64)lim; }
-    __device__ __forceinline__ void prime()
+    __device__ __forceinline__ void prime(u32 start = 0)
     {
 #pragma unroll
         for(u32 i = 0; i < (u32)INQ; ++i) {
-            request(i, true);
+            request(start + i, true);
         }
         cp_async_wait<0>();
-        rd = 0;
-        ahead = lds32v(q);
+        rd = start;
+        ahead = lds32v(q + (rd & (INQ - 1)) * 128u);
     }
     // Next stream word, big endian, when `need`; otherwise nothing moves.  Every call commits
     // one (possibly empty) copy group, so "all but the newest INQ-1 groups" always covers the
@@ -921,13 +926,13 @@ __device__ __forceinline__ void dec_static_tile(const CumTab& tab, const u32 (&k
 
 template <int MODE, bool RAGGED>
 __device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const CumTab& tab, const u32 (&k1)[8], RcDec& d,
-                                                 WordSrc& src, u8* otile, u32 otile_a, u64 b0, u32 n_b, u32 n_max,
-                                                 u32 total, u32 magic, u32 shift, u32 lane)
+                                                 WordSrc& src, u8* otile, u32 otile_a, u64 b0, u32 n_b, u32 tix0,
+                                                 u32 tix1, bool resume, u32 total, u32 magic, u32 shift, u32 lane)
 {
-    const u32 ntiles = (n_max + TILE - 1) / TILE;
-    u32 t = MODE ? (d.range >> shift) : 0u;
+    // a resumed power-of-two chain finds t where the previous launch left it (in d.range)
+    u32 t = MODE ? (resume ? d.range : (d.range >> shift)) : 0u;
 #pragma unroll 1
-    for(u32 tix = 0; tix < ntiles; ++tix) {
+    for(u32 tix = tix0; tix < tix1; ++tix) {
         // all but the last tile or two of the last block of the stream read words that lie wholly
         // inside the buffer: those tiles skip the bounds arithmetic of the copy requests
         if(__all_sync(FULL, src.tile_is_inside())) {
@@ -1004,21 +1009,48 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     const bool is_pow2 = (total & (total - 1u)) == 0;
     const u32 shift = is_pow2 ? 31u - rc_clz(total) : 0u;
     RcDec d;
-    rc_dec_init(d, RC_STATIC_RANGE0, (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u), src);
+    const bool resume = a.nsym != 0u && a.sym0 != 0u;
+    u32* saved = a.state ? a.state + (has ? b : b0) * 8u : nullptr;
+    if(!resume) {
+        rc_dec_init(d, RC_STATIC_RANGE0, (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u), src);
+    } else {
+        d.low = saved[0];
+        d.range = saved[1];
+        d.w_hi = saved[2];
+        d.w_lo = saved[3];
+        d.wbits = (s32)saved[4];
+        src.prime(ok ? saved[5] : 0u);
+    }
 
     const u32 n_max = __reduce_max_sync(FULL, n_b);
     const bool all_pow2 = __all_sync(FULL, is_pow2);
     const bool ragged = __any_sync(FULL, n_b != n_max);
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+    const u32 tix0 = a.nsym ? a.sym0 / TILE : 0u;
+    u32 tix1 = a.nsym ? (a.sym0 + a.nsym) / TILE : ntiles;
+    tix1 = tix1 < ntiles ? tix1 : ntiles;
     if(all_pow2 && !ragged && a.block <= 65536u) {
-        dec_static_tiles<2, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+        dec_static_tiles<2, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, tix0, tix1, resume, total, magic, shift,
+                                   lane);
     } else if(all_pow2 && !ragged) {
-        dec_static_tiles<3, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+        dec_static_tiles<3, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, tix0, tix1, resume, total, magic, shift,
+                                   lane);
     } else if(!ragged) {
-        dec_static_tiles<0, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+        dec_static_tiles<0, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, tix0, tix1, resume, total, magic, shift,
+                                   lane);
     } else {
-        dec_static_tiles<0, true>(a, tab, k1, d, src, otile, otile_a, b0, n_b, n_max, total, magic, shift, lane);
+        dec_static_tiles<0, true>(a, tab, k1, d, src, otile, otile_a, b0, n_b, tix0, tix1, resume, total, magic, shift,
+                                  lane);
     }
-    if(ok && d.range == 0) {
+    if(has && saved) {  // phased: park the chain for the next launch (also when this block is already done)
+        saved[0] = d.low;
+        saved[1] = d.range;
+        saved[2] = d.w_hi;
+        saved[3] = d.w_lo;
+        saved[4] = (u32)d.wbits;
+        saved[5] = src.rd;
+    }
+    if(tix1 >= ntiles && ok && d.range == 0) {
         atomicOr(a.err, ERR_CORRUPT);
     }
 }
