@@ -161,7 +161,7 @@ class Context:
             sizes = torch.zeros(max(nb, 1), dtype=torch.int32, device=dev)
         if err is None:
             err = torch.zeros(4, dtype=torch.int32, device=dev)
-        if mode == MODE_STATIC and block <= 65536 and freq16 is None:
+        if mode == MODE_STATIC and freq16 is None:
             freq16 = self.histogram(src, block)
         self._check(self.lib.b2rc_k_encode_blocks(self.h, mode, block, _ptr(src), n, _ptr(freq16), _ptr(slots), stride,
                                                   _ptr(sizes), _ptr(err), _stream()), "b2rc_k_encode_blocks")

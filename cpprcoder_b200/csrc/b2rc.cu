@@ -571,8 +571,7 @@ static int ans_decode_blocks(b2rc_ctx* ctx, int mode, const DecArgs& a, cudaStre
 int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t block_size, uint16_t* d_freq16,
                      void* cuda_stream)
 {
-    if(!ctx || !d_src || !d_freq16 || !block_ok(block_size) || block_size > 65536u || !aligned16(d_src) ||
-       !aligned16(d_freq16)) {
+    if(!ctx || !d_src || !d_freq16 || !block_ok(block_size) || !aligned16(d_src) || !aligned16(d_freq16)) {
         return B2RC_E_ARG;
     }
     const u64 nb = b2rc_nblocks(n, block_size);
@@ -586,7 +585,11 @@ int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t b
         grid = 148ull * 16;
     }
     KernelTimer kt(ctx, B2RC_K_HISTOGRAM, st);
-    k_hist<<<(unsigned)grid, HIST_WARPS * 32, 0, st>>>(d_src, n, block_size, nb, d_freq16);
+    if(block_size <= 65536u) {
+        k_hist<<<(unsigned)grid, HIST_WARPS * 32, 0, st>>>(d_src, n, block_size, nb, d_freq16);
+    } else {
+        k_hist_wide<<<(unsigned)grid, HIST_WARPS * 32, 0, st>>>(d_src, n, block_size, nb, d_freq16);
+    }
     return launch_check(ctx, "k_hist");
 }
 
@@ -604,7 +607,7 @@ int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
                                  (cudaStream_t)cuda_stream);
     }
     const bool wide = block_size > 65536u;
-    if(mode == B2RC_MODE_STATIC && !wide && (!d_freq16 || !aligned16(d_freq16))) {
+    if(mode == B2RC_MODE_STATIC && ((!wide && !d_freq16) || (d_freq16 && !aligned16(d_freq16)))) {
         return B2RC_E_ARG;
     }
     const u64 nb = b2rc_nblocks(n, block_size);
@@ -779,7 +782,7 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
        (rc = grow(ctx, ctx->sizes, ctx->sizes_cap, (size_t)(nb * 4 + 16))) != B2RC_OK) {
         return rc;
     }
-    const bool need_hist = mode == B2RC_MODE_STATIC && block_size <= 65536u;
+    const bool need_hist = mode == B2RC_MODE_STATIC;
     if(need_hist && (rc = grow(ctx, ctx->freq16, ctx->freq_cap, (size_t)(nb * 512 + 16))) != B2RC_OK) {
         return rc;
     }
@@ -788,8 +791,8 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
         if(need_hist && (rc = b2rc_k_histogram(ctx, d_src, n, block_size, ctx->freq16, st)) != B2RC_OK) {
             return rc;
         }
-        if((rc = b2rc_k_encode_blocks(ctx, mode, block_size, d_src, n, ctx->freq16, ctx->slots, stride, ctx->sizes,
-                                      ctx->d_err, st)) != B2RC_OK) {
+        if((rc = b2rc_k_encode_blocks(ctx, mode, block_size, d_src, n, need_hist ? ctx->freq16 : nullptr, ctx->slots,
+                                      stride, ctx->sizes, ctx->d_err, st)) != B2RC_OK) {
             return rc;
         }
     }
@@ -912,7 +915,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         return B2RC_E_DST_SMALL;
     }
     const u64 stride = b2rc_slot_bytes_for(mode, block_size);
-    const bool need_hist = mode == B2RC_MODE_STATIC && block_size <= 65536u;
+    const bool need_hist = mode == B2RC_MODE_STATIC;
     int rc;
     if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
        (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(bound + 16))) != B2RC_OK ||

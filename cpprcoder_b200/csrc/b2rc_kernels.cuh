@@ -356,8 +356,37 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
             }
         }
         __syncwarp();
+    } else if(a.freq16) {
+        // counts from k_hist_wide (order-dependent halving applied there); the cumulative table
+        // needs 32 bits here, so each lane sums its own block's 256 counts
+        u32* mine = reinterpret_cast<u32*>(smem) + lane;
+        if(has) {
+            *reinterpret_cast<u32*>(slot) = n_b;
+            const u16* fq = a.freq16 + b * 256u;
+            u32 run = 0;
+#pragma unroll 1
+            for(u32 s = 0; s < 256; s += 2) {
+                const u32 pair = __ldg(reinterpret_cast<const u32*>(fq + s));
+                *reinterpret_cast<u32*>(slot + 4u + 2u * s) = pair;
+                mine[s * 32u] = run;
+                run += pair & 0xFFFFu;
+                mine[(s + 1u) * 32u] = run;
+                run += pair >> 16;
+            }
+            mine[256u * 32u] = run;
+            total = run;
+            front = *reinterpret_cast<const u32*>(slot + RC_STATIC_HDR - 4u);
+        } else {
+            for(u32 s = 0; s < 257; ++s) {
+                mine[s * 32u] = 0;
+            }
+        }
+        __syncwarp();
+        stage_tile(tiles, a.src, a.n, b0, a.block, 0, lane);
+        cp_async_commit();
     } else {
-        // count(): the halving is order dependent, so each lane walks its own block once
+        // no table given: count() here, each lane walking its own block once (the halving is
+        // order dependent)
         u32* mine = reinterpret_cast<u32*>(smem) + lane;
         for(u32 s = 0; s < 257; ++s) {
             mine[s * 32u] = 0;
@@ -1210,6 +1239,86 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_hist(const u8* src, u64 n, 
         o.w = f[6] | (f[7] << 16);
         reinterpret_cast<uint4*>(freq16 + b * 256u)[lane] = o;
         __syncwarp();
+    }
+}
+
+// K1 for blocks above 65536 bytes, where RangeEncoder::count is order dependent: whenever the
+// symbol about to be counted already stands at 0xFFFF, EVERY non-zero count becomes
+// (x >> 1) | 1 first (cpprcoder.h:549-555).  One warp per block walks it in segments: the
+// segment's histogram is taken in parallel, and if no count can reach the limit inside the
+// segment (count + hits <= 0xFFFF for every symbol) it is simply added -- exact, because
+// then no halving happens in it.  Otherwise one lane replays the segment byte by byte with
+// the reference's rule.  A halving leaves the largest count at 0x8000, so at most one segment
+// in eight takes the slow road even on a block of equal bytes.  Counts end <= 0xFFFF.
+constexpr u32 HIST_SEG = 4096u;
+__global__ void __launch_bounds__(HIST_WARPS * 32) k_hist_wide(const u8* src, u64 n, u32 block, u64 nblocks, u16* freq16)
+{
+    __shared__ u32 bins[HIST_WARPS][256];
+    __shared__ u32 tots[HIST_WARPS][256];
+    const u32 lane = lane_id();
+    const u32 warp = threadIdx.x >> 5;
+    u32* h = bins[warp];
+    u32* tot = tots[warp];
+    for(u64 b = (u64)blockIdx.x * HIST_WARPS + warp; b < nblocks; b += (u64)gridDim.x * HIST_WARPS) {
+        const u64 lo = b * (u64)block;
+        const u32 len = (u32)((n - lo < block) ? (n - lo) : block);
+        u32 f[8];
+#pragma unroll
+        for(int k = 0; k < 8; ++k) {
+            f[k] = 0;
+        }
+        for(u32 at = 0; at < len; at += HIST_SEG) {
+            const u32 seg = len - at < HIST_SEG ? len - at : HIST_SEG;
+            hist_block(h, src + lo + at, seg, lane);
+            bool fits = true;
+            u32 add[8];
+#pragma unroll
+            for(int k = 0; k < 8; ++k) {
+                add[k] = h[8u * lane + k];
+                fits = fits && (f[k] + add[k] <= 0xFFFFu);
+            }
+            if(__all_sync(FULL, fits)) {
+#pragma unroll
+                for(int k = 0; k < 8; ++k) {
+                    f[k] += add[k];
+                }
+            } else {
+#pragma unroll
+                for(int k = 0; k < 8; ++k) {
+                    tot[8u * lane + k] = f[k];
+                }
+                __syncwarp();
+                if(lane == 0) {
+                    const u8* p = src + lo + at;
+                    for(u32 i = 0; i < seg; ++i) {
+                        const u32 c = p[i];
+                        u32 x = tot[c];
+                        if(x >= 0xFFFFu) {
+                            for(u32 s2 = 0; s2 < 256u; ++s2) {
+                                const u32 y = tot[s2];
+                                if(y) {
+                                    tot[s2] = (y >> 1) | 1u;
+                                }
+                            }
+                            x = tot[c];
+                        }
+                        tot[c] = x + 1u;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for(int k = 0; k < 8; ++k) {
+                    f[k] = tot[8u * lane + k];
+                }
+            }
+            __syncwarp();
+        }
+        uint4 o;
+        o.x = f[0] | (f[1] << 16);
+        o.y = f[2] | (f[3] << 16);
+        o.z = f[4] | (f[5] << 16);
+        o.w = f[6] | (f[7] << 16);
+        reinterpret_cast<uint4*>(freq16 + b * 256u)[lane] = o;
     }
 }
 

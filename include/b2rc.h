@@ -103,13 +103,14 @@ int b2rc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t*
  * unless stated.  `d_err` is one int the kernels OR error bits into (0 = clean).
  *
  * K1  b2rc_k_histogram: per-block symbol counts with the reference's scaling rule,
- *     RangeEncoder::count (cpprcoder.h:543-571), for block_size <= 65536.
- *     d_freq16[b*256 + s] = u16 frequency of symbol s in block b. */
+ *     RangeEncoder::count (cpprcoder.h:543-571), including its order-dependent halving for
+ *     blocks above 65536 bytes.  d_freq16[b*256 + s] = u16 frequency of symbol s in block b. */
 int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t block_size, uint16_t* d_freq16,
                      void* cuda_stream);
 /* K2  b2rc_k_encode_blocks: block b's payload -> d_slots + b*slot_stride, its length ->
  *     d_sizes[b].  Static mode with block_size <= 65536 needs d_freq16 from K1; larger
- *     static blocks count inside the kernel (pass NULL), and so do the rANS modes (their
+ *     static blocks take it when given and otherwise count inside the kernel (NULL, slower);
+ *     the rANS modes ignore it (their
  *     model kernel, cppans.h:504-508, runs as part of this call).
  *     slot_stride >= b2rc_slot_bytes_for(mode, block_size), multiple of 16. */
 int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,

@@ -96,6 +96,27 @@ def test_blocks_above_64k_follow_the_order_dependent_count(ctx, oracle, block):
             assert ctx.decode(enc).tobytes() == d.tobytes()
 
 
+@pytest.mark.parametrize("block", [131072, 524288])
+def test_wide_histogram_is_the_order_dependent_count(ctx, oracle, block):
+    # K1 for blocks above 64 KiB: segments that cannot reach 0xFFFF are added in parallel, the
+    # others replayed with the reference's halving rule (cpprcoder.h:549-555)
+    import torch
+    rng = np.random.default_rng(block)
+    parts = [np.zeros(block, np.uint8),                                   # a halving every 32 Ki bytes
+             synth.kennedy(block),                                        # 44 % zeros
+             np.where(rng.random(block) < 0.7, 7, rng.integers(0, 256, block)).astype(np.uint8),
+             rng.integers(0, 4, block // 2 + 4097, dtype=np.uint8)]      # short last block
+    data = np.concatenate(parts)
+    src = torch.from_numpy(data).cuda()
+    f16 = ctx.histogram(src, block).cpu().numpy().view(np.uint16)
+    events = 0
+    for b in range((data.size + block - 1) // block):
+        want, ev = oracle.static_count(data[b * block:(b + 1) * block])
+        events += ev
+        assert (f16[b].astype(np.uint32) == want).all(), f"histogram of block {b}"
+    assert events >= 3
+
+
 def test_edges(ctx, oracle):
     for d in [b"", b"A", b"AB" * 32, b"A" * 65535, b"A" * 65536, b"A" * 65537, b"\xff" * 65536, bytes(range(256)) * 3]:
         data = np.frombuffer(d, dtype=np.uint8)
