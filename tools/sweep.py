@@ -40,7 +40,7 @@ def main():
     dst = torch.empty(n, dtype=torch.uint8, device="cuda")
     rows = []
     for block in [4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288, 1048576]:
-        for mode, name in ((0, "static"), (1, "adaptive")):
+        for mode, name in ((0, "static"), (1, "adaptive"), (2, "rans"), (3, "rans-word")):
             enc, used = ctx.encode_device(mode, src, block=block)
             t_enc = timed(lambda: ctx.encode_device(mode, src, enc, block=block))
             t_dec = timed(lambda: ctx.decode_device(enc, used, dst))
