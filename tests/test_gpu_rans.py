@@ -201,11 +201,10 @@ def test_corrupt_payloads_are_rejected(ctx, oracle, mode):
 @pytest.mark.parametrize("mode", [RANS_BYTE, RANS_WORD])
 def test_device_api_and_large_property(ctx, oracle, mode):
     import torch
-    RANS_WORD = mode  # noqa: N806 -- the body below is the same for both coders
     n = (256 << 20) + 12345
     data = synth.zipf(n)
     src = torch.from_numpy(data).cuda()
-    enc, used = ctx.encode_device(RANS_WORD, src, block=65536)
+    enc, used = ctx.encode_device(mode, src, block=65536)
     dec = torch.zeros(n, dtype=torch.uint8, device="cuda")
     got = ctx.decode_device(enc, used, dec)
     assert got == n and torch.equal(dec, src)
@@ -214,11 +213,11 @@ def test_device_api_and_large_property(ctx, oracle, mode):
     rng = np.random.default_rng(0)
     for b in [0, info.nblocks - 1] + [int(v) for v in rng.integers(0, info.nblocks, 6)]:
         blk = data[b * 65536:(b + 1) * 65536]
-        assert bytes(info.payload(host, b)) == oracle.encode(RANS_WORD, blk), f"block {b}"
+        assert bytes(info.payload(host, b)) == oracle.encode(mode, blk), f"block {b}"
     # a different shape of data through the same context
     d2 = synth.kennedy(64 << 20)
     s2 = torch.from_numpy(d2).cuda()
-    e2, u2 = ctx.encode_device(RANS_WORD, s2, block=16384)
+    e2, u2 = ctx.encode_device(mode, s2, block=16384)
     o2 = torch.zeros(d2.size, dtype=torch.uint8, device="cuda")
     g2 = ctx.decode_device(e2, u2, o2)
     assert g2 == d2.size and torch.equal(o2, s2)
