@@ -149,14 +149,14 @@ RC_HD u32 ans_byte_dec_init(RcDec& d, u32 skip, Next& next)
     d.w_hi = d.w_lo;
     d.w_lo = 0;
     d.wbits = 32 - (s32)drop;
-    rc_dec_refill(d, next);
+    rc_dec_refill_pair(d, next);
     return rc_bswap(first);
 }
 
 // advance (cppans.h:321-334): x = f * (x >> 14) + slot - start, then 0, 1 or 2 bytes in.
 // A valid stream never needs a third (x >= 2^9 after the update); a corrupt one may, and
 // then x stays below 2^23 -- the caller checks.  At most 16 bits per symbol: the window is
-// topped up after every second symbol (REFILL), as in rc_dec_advance_pow2<2>.
+// topped up after every second symbol (REFILL, rc_dec_refill_pair).
 template <bool REFILL = true, class Next>
 RC_HD void ans_byte_advance(RcDec& d, u32& x, u32 slot, u32 start, u32 f, Next& next)
 {
@@ -167,6 +167,6 @@ RC_HD void ans_byte_advance(RcDec& d, u32& x, u32 slot, u32 start, u32 f, Next& 
     d.w_lo <<= sh;
     d.wbits -= (s32)sh;
     if(REFILL) {
-        rc_dec_refill(d, next);
+        rc_dec_refill_pair(d, next);
     }
 }

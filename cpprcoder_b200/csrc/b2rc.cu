@@ -155,7 +155,8 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_enc_static<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_static(true)));
     CK(cudaFuncSetAttribute(k_enc_adaptive<u16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_adaptive(false)));
     CK(cudaFuncSetAttribute(k_enc_adaptive<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_adaptive(true)));
-    CK(cudaFuncSetAttribute(k_dec_static, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static()));
+    CK(cudaFuncSetAttribute(k_dec_static<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static()));
+    CK(cudaFuncSetAttribute(k_dec_static<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static()));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(false)));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
@@ -747,7 +748,11 @@ static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     const unsigned grid = (unsigned)((nblocks + 31) / 32);
     KernelTimer kt(ctx, B2RC_K_DECODE, st);
     if(mode == B2RC_MODE_STATIC) {
-        k_dec_static<<<grid, 32, smem_dec_static(), st>>>(a);
+        if(nsym) {
+            k_dec_static<true><<<grid, 32, smem_dec_static(), st>>>(a);
+        } else {
+            k_dec_static<false><<<grid, 32, smem_dec_static(), st>>>(a);
+        }
     } else {
         if(wide) {
             k_dec_adaptive<u32><<<grid, 32, smem_dec_adaptive(true), st>>>(a);

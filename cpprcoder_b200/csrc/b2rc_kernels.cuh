@@ -958,7 +958,8 @@ __device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const CumTab&
                                                  WordSrc& src, u8* otile, u32 otile_a, u64 b0, u32 n_b, u32 tix0,
                                                  u32 tix1, bool resume, u32 total, u32 magic, u32 shift, u32 lane)
 {
-    // a resumed power-of-two chain finds t where the previous launch left it (in d.range)
+    // a resumed power-of-two chain finds t where the previous launch left it (in d.range).
+    // In the one-launch kernel tix0, tix1 and resume are compile-time constants / ntiles.
     u32 t = MODE ? (resume ? d.range : (d.range >> shift)) : 0u;
 #pragma unroll 1
     for(u32 tix = tix0; tix < tix1; ++tix) {
@@ -979,6 +980,11 @@ __device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const CumTab&
     }
 }
 
+// PHASED = false: the whole block in one launch (the device API, what bench.py times).
+// PHASED = true: symbols [a.sym0, a.sym0 + a.nsym) with the coder state parked in a.state --
+// its own instantiation, so that the one-launch kernel's hot loop is compiled exactly as it
+// was before phases existed (it is sensitive to the slightest change, profiles/r1_ncu_notes.md).
+template <bool PHASED>
 __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
@@ -1038,8 +1044,8 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     const bool is_pow2 = (total & (total - 1u)) == 0;
     const u32 shift = is_pow2 ? 31u - rc_clz(total) : 0u;
     RcDec d;
-    const bool resume = a.nsym != 0u && a.sym0 != 0u;
-    u32* saved = a.state ? a.state + (has ? b : b0) * 8u : nullptr;
+    const bool resume = PHASED && a.sym0 != 0u;
+    u32* saved = PHASED ? a.state + (has ? b : b0) * 8u : nullptr;
     if(!resume) {
         rc_dec_init(d, RC_STATIC_RANGE0, (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u), src);
     } else {
@@ -1055,8 +1061,8 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     const bool all_pow2 = __all_sync(FULL, is_pow2);
     const bool ragged = __any_sync(FULL, n_b != n_max);
     const u32 ntiles = (n_max + TILE - 1) / TILE;
-    const u32 tix0 = a.nsym ? a.sym0 / TILE : 0u;
-    u32 tix1 = a.nsym ? (a.sym0 + a.nsym) / TILE : ntiles;
+    const u32 tix0 = PHASED ? a.sym0 / TILE : 0u;
+    u32 tix1 = PHASED ? (a.sym0 + a.nsym) / TILE : ntiles;
     tix1 = tix1 < ntiles ? tix1 : ntiles;
     if(all_pow2 && !ragged && a.block <= 65536u) {
         dec_static_tiles<2, false>(a, tab, k1, d, src, otile, otile_a, b0, n_b, tix0, tix1, resume, total, magic, shift,
@@ -1071,7 +1077,7 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
         dec_static_tiles<0, true>(a, tab, k1, d, src, otile, otile_a, b0, n_b, tix0, tix1, resume, total, magic, shift,
                                   lane);
     }
-    if(has && saved) {  // phased: park the chain for the next launch (also when this block is already done)
+    if(PHASED && has) {  // park the chain for the next launch (also when this block is already done)
         saved[0] = d.low;
         saved[1] = d.range;
         saved[2] = d.w_hi;

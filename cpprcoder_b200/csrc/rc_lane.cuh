@@ -517,7 +517,22 @@ RC_HD void rc_dec_refill(RcDec& d, Next& next)
 {
     const bool need = d.wbits < 32;
     const u32 w = next.take(need);
-    const u32 have = (u32)d.wbits & 31u;  // 0 when a pair of symbols drained the window exactly
+    const u32 have = (u32)d.wbits & 31u;
+    d.w_hi = need ? (d.w_hi | (w >> have)) : d.w_hi;
+    d.w_lo = need ? (w << (32u - have)) : d.w_lo;
+    d.wbits += need ? 32 : 0;
+}
+
+// The same for a window that is topped up after every SECOND symbol (a symbol takes at most 16
+// bits, so >= 32 bits last for two): the pair may drain it exactly, have == 0, and the shift
+// above would be by 32.  Kept apart from rc_dec_refill on purpose: k_dec_static's hot loop
+// lost 7 % when this form replaced the plain shift there (profiles/r1_ncu_notes.md).
+template <class Next>
+RC_HD void rc_dec_refill_pair(RcDec& d, Next& next)
+{
+    const bool need = d.wbits < 32;
+    const u32 w = next.take(need);
+    const u32 have = (u32)d.wbits & 31u;
     d.w_hi = need ? (d.w_hi | (w >> have)) : d.w_hi;
     d.w_lo = need ? rc_funnel_r(0u, w, have) : d.w_lo;  // w << (32 - have), and 0 for have == 0
     d.wbits += need ? 32 : 0;
@@ -541,10 +556,7 @@ RC_HD void rc_dec_advance(RcDec& d, u32 cum, u32 freq, u32 t, Next& next)
 // Same as rc_dec_advance for a power-of-two total: the chain is carried by
 // t = range >> shift (see rc_enc_step_pow2); d.range is not maintained.
 // MAXSH = 2 when range >= 2^8 is guaranteed (total <= 2^16), else 3.
-// REFILL = false skips the top-up: with MAXSH = 2 a symbol takes at most 16 bits, so a
-// window holding >= 32 bits serves two symbols and is topped up after every second one
-// (one stream word covers what a pair can take).
-template <int MAXSH, bool REFILL = true, class Next>
+template <int MAXSH, class Next>
 RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, Next& next)
 {
     d.low -= cum * t;
@@ -555,9 +567,7 @@ RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, N
     d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);
     d.w_lo <<= sh;
     d.wbits -= (s32)sh;
-    if(REFILL) {
-        rc_dec_refill(d, next);
-    }
+    rc_dec_refill(d, next);
 }
 
 // ------------------------------------------------------------- adaptive model --

@@ -208,14 +208,8 @@ long sim_decode(int mode, const u8* stream, size_t stream_len, u32 lead, u8* dst
             dst[i] = (u8)sym;
             if(!pow2) {
                 rc_dec_advance(d, c0, fr, t, rd);
-            } else if(total <= 65536u && (want & 1u) == 0) {
-                // top-up after every second symbol (the rANS byte decoder's cadence; measured slower in
-                // k_dec_static, which tops up every symbol)
-                if(i & 1) {
-                    rc_dec_advance_pow2<2, true>(d, t, shT, c0, fr, rd);
-                } else {
-                    rc_dec_advance_pow2<2, false>(d, t, shT, c0, fr, rd);
-                }
+            } else if(total <= 65536u && (i & 1)) {
+                rc_dec_advance_pow2<2>(d, t, shT, c0, fr, rd);
             } else {
                 rc_dec_advance_pow2<3>(d, t, shT, c0, fr, rd);
             }
