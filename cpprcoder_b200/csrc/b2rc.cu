@@ -47,6 +47,8 @@ struct b2rc_ctx {
     cudaStream_t d2h[B2RC_PHASES];
     u32* dec_state;
     size_t dec_state_cap;
+    u8* dec_model;  // adaptive coder: the count tables of every warp of blocks between launches
+    size_t dec_model_cap;
     u64* d_ends;  // B2RC_PIPE_CHUNKS + 1
     u64* h_ends;  // pinned
     u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
@@ -157,8 +159,10 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_enc_adaptive<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_enc_adaptive(true)));
     CK(cudaFuncSetAttribute(k_dec_static<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static()));
     CK(cudaFuncSetAttribute(k_dec_static<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_static()));
-    CK(cudaFuncSetAttribute(k_dec_adaptive<u16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(false)));
-    CK(cudaFuncSetAttribute(k_dec_adaptive<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
+    CK(cudaFuncSetAttribute(k_dec_adaptive<u16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(false)));
+    CK(cudaFuncSetAttribute(k_dec_adaptive<u16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(false)));
+    CK(cudaFuncSetAttribute(k_dec_adaptive<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
+    CK(cudaFuncSetAttribute(k_dec_adaptive<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
     return B2RC_OK;
 }
@@ -424,6 +428,7 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
         }
     }
     cudaFree(ctx->dec_state);
+    cudaFree(ctx->dec_model);
     cudaFree(ctx->d_ends);
     if(ctx->h_ends) {
         cudaFreeHost(ctx->h_ends);
@@ -701,20 +706,21 @@ int b2rc_k_compact_for(b2rc_ctx* ctx, int mode, const uint8_t* d_slots, uint64_t
 
 static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload, uint64_t payload_len,
                          const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n, int* d_err,
-                         void* cuda_stream, u32 sym0, u32 nsym, u32* d_state);
+                         void* cuda_stream, u32 sym0, u32 nsym, u32* d_state, u8* d_model);
 
 int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload,
                          uint64_t payload_len, const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n,
                          int* d_err, void* cuda_stream)
 {
     return decode_launch(ctx, mode, block_size, d_payload, payload_len, d_offsets, nblocks, d_dst, n, d_err, cuda_stream,
-                         0u, 0u, nullptr);
+                         0u, 0u, nullptr, nullptr);
 }
 
-// sym0 / nsym / d_state: phased decode of the static coder (DecArgs); 0, 0, null = whole blocks
+// sym0 / nsym / d_state / d_model: phased decode of the range coders (DecArgs); 0, 0, null, null =
+// whole blocks
 static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload, uint64_t payload_len,
                          const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n, int* d_err,
-                         void* cuda_stream, u32 sym0, u32 nsym, u32* d_state)
+                         void* cuda_stream, u32 sym0, u32 nsym, u32* d_state, u8* d_model)
 {
     if(!ctx || !d_payload || !d_offsets || !d_dst || !d_err || !mode_ok(mode) || !block_ok(block_size) ||
        !aligned16(d_dst) || ((uintptr_t)d_offsets & 7u) || nblocks != b2rc_nblocks(n, block_size) ||
@@ -738,7 +744,8 @@ static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     a.sym0 = sym0;
     a.nsym = nsym;
     a.state = d_state;
-    if(nsym && (mode != B2RC_MODE_STATIC || !d_state || (sym0 % TILE) || (nsym % TILE))) {
+    a.model = d_model;
+    if(nsym && (is_ans(mode) || !d_state || (mode == B2RC_MODE_ADAPTIVE && !d_model) || (sym0 % TILE) || (nsym % TILE))) {
         return B2RC_E_ARG;
     }
     if(is_ans(mode)) {
@@ -755,9 +762,17 @@ static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
         }
     } else {
         if(wide) {
-            k_dec_adaptive<u32><<<grid, 32, smem_dec_adaptive(true), st>>>(a);
+            if(nsym) {
+                k_dec_adaptive<u32, true><<<grid, 32, smem_dec_adaptive(true), st>>>(a);
+            } else {
+                k_dec_adaptive<u32, false><<<grid, 32, smem_dec_adaptive(true), st>>>(a);
+            }
         } else {
-            k_dec_adaptive<u16><<<grid, 32, smem_dec_adaptive(false), st>>>(a);
+            if(nsym) {
+                k_dec_adaptive<u16, true><<<grid, 32, smem_dec_adaptive(false), st>>>(a);
+            } else {
+                k_dec_adaptive<u16, false><<<grid, 32, smem_dec_adaptive(false), st>>>(a);
+            }
         }
     }
     return launch_check(ctx, "k_dec");
@@ -1044,16 +1059,19 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
         return rc;
     }
     const Chunks ch = plan_chunks(ctx, total, block);
-    // static coder, long blocks, more than one chunk in flight: decode in phases (see below)
+    // range coders, long blocks, more than one chunk in flight: decode in phases (see below)
     u32 phases = 1, per = block;
-    if(mode == B2RC_MODE_STATIC && block >= 2u * B2RC_PHASE_MIN_SYMS && ch.count > 1 && ctx->max_phases > 1) {
+    const u64 model_bytes = 512ull * 32ull * (block > 65536u ? 4u : 2u);  // per warp of 32 blocks
+    if(!is_ans(mode) && block >= 2u * B2RC_PHASE_MIN_SYMS && ch.count > 1 && ctx->max_phases > 1) {
         phases = block / B2RC_PHASE_MIN_SYMS;
         if(phases > ctx->max_phases) {
             phases = (u32)ctx->max_phases;
         }
         per = ((block / phases) + 63u) & ~63u;
         phases = (block + per - 1) / per;
-        if((rc = grow(ctx, ctx->dec_state, ctx->dec_state_cap, (size_t)(nb * 32 + 64))) != B2RC_OK) {
+        if((rc = grow(ctx, ctx->dec_state, ctx->dec_state_cap, (size_t)(nb * 32 + 64))) != B2RC_OK ||
+           (mode == B2RC_MODE_ADAPTIVE &&
+            (rc = grow(ctx, ctx->dec_model, ctx->dec_model_cap, (size_t)(((nb + 31) / 32) * model_bytes))) != B2RC_OK)) {
             return rc;
         }
     }
@@ -1095,7 +1113,8 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
             const u32 s0 = p * per;
             const u32 ns = (p + 1 == phases) ? (((block - s0) + 63u) & ~63u) : per;
             if((rc = decode_launch(ctx, mode, block, ctx->stage_in + idx, payload_len, d_offsets + b0, b1 - b0,
-                                   ctx->stage_out + byte0, bytes, ctx->d_err, st, s0, ns, ctx->dec_state + b0 * 8)) !=
+                                   ctx->stage_out + byte0, bytes, ctx->d_err, st, s0, ns, ctx->dec_state + b0 * 8,
+                                   mode == B2RC_MODE_ADAPTIVE ? ctx->dec_model + (b0 / 32) * model_bytes : nullptr)) !=
                B2RC_OK) {
                 return rc;
             }

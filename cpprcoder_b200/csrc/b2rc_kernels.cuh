@@ -764,6 +764,7 @@ struct DecArgs {
     // whole block in one launch, `state` unused.
     u32 sym0, nsym;
     u32* state;
+    u8* model;  // adaptive coder only: the count tables of 32 blocks (one CTA) per slot, parked alongside
 };
 
 // Each lane reads its own payload at its own pace, one aligned word at a time.  Words
@@ -1118,7 +1119,9 @@ __device__ __forceinline__ void dec_adaptive_tile(LaneTab<W>& tab, RcDec& d, Src
     }
 }
 
-template <class W>
+// PHASED: as for k_dec_static -- symbols [a.sym0, a.sym0 + a.nsym) per launch, the coder state in
+// a.state and the warp's count tables (the model after sym0 symbols) in a.model between launches.
+template <class W, bool PHASED>
 __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
@@ -1140,10 +1143,12 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
     const u8* pay;
     bool ok;
     dec_setup(a, RC_ADAPT_HDR, b, has, n_b, otile_a + TILE_BYTES + lane * 4u, src, pay, ok);
+    const bool resume = PHASED && a.sym0 != 0u;
+    uint4* parked = PHASED ? reinterpret_cast<uint4*>(a.model + (u64)blockIdx.x * TAB_BYTES) : nullptr;
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
         for(u32 i = lane; i < TAB_BYTES / 16u; i += 32u) {
-            z[i] = make_uint4(0, 0, 0, 0);
+            z[i] = resume ? parked[i] : make_uint4(0, 0, 0, 0);
         }
     }
     if(!ok) {
@@ -1152,12 +1157,25 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
     __syncwarp();
     LaneTab<W> tab{sbase + lane * (u32)sizeof(W)};
     RcDec d;
-    rc_dec_init(d, RC_ADAPT_RANGE0, (u32)((uintptr_t)(pay + RC_ADAPT_HDR) & 3u), src);
+    u32* saved = PHASED ? a.state + (has ? b : b0) * 8u : nullptr;
+    if(!resume) {
+        rc_dec_init(d, RC_ADAPT_RANGE0, (u32)((uintptr_t)(pay + RC_ADAPT_HDR) & 3u), src);
+    } else {
+        d.low = saved[0];
+        d.range = saved[1];
+        d.w_hi = saved[2];
+        d.w_lo = saved[3];
+        d.wbits = (s32)saved[4];
+        src.prime(ok ? saved[5] : 0u);
+    }
 
     const u32 n_max = __reduce_max_sync(FULL, n_b);
     const u32 ntiles = (n_max + TILE - 1) / TILE;
+    const u32 tix0 = PHASED ? a.sym0 / TILE : 0u;
+    u32 tix1 = PHASED ? (a.sym0 + a.nsym) / TILE : ntiles;
+    tix1 = tix1 < ntiles ? tix1 : ntiles;
 #pragma unroll 1
-    for(u32 tix = 0; tix < ntiles; ++tix) {
+    for(u32 tix = tix0; tix < tix1; ++tix) {
         if(__all_sync(FULL, src.tile_is_inside())) {
             WordSrcInside in{src};
             dec_adaptive_tile<W>(tab, d, in, otile_a, tix * TILE, n_b, lane);
@@ -1168,7 +1186,21 @@ __global__ void __launch_bounds__(32) k_dec_adaptive(DecArgs a)
         store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
         __syncwarp();
     }
-    if(ok && d.range == 0) {
+    if(PHASED) {
+        const uint4* z = reinterpret_cast<const uint4*>(smem);
+        for(u32 i = lane; i < TAB_BYTES / 16u; i += 32u) {
+            parked[i] = z[i];
+        }
+        if(has) {
+            saved[0] = d.low;
+            saved[1] = d.range;
+            saved[2] = d.w_hi;
+            saved[3] = d.w_lo;
+            saved[4] = (u32)d.wbits;
+            saved[5] = src.rd;
+        }
+    }
+    if(tix1 >= ntiles && ok && d.range == 0) {
         atomicOr(a.err, ERR_CORRUPT);
     }
 }

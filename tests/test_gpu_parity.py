@@ -286,14 +286,16 @@ def test_pipelined_host_calls_on_many_chunks(ctx, oracle):
         assert ctx.decode(enc).tobytes() == data.tobytes()
 
 
+@pytest.mark.parametrize("mode", [STATIC, ADAPTIVE])
 @pytest.mark.parametrize("gen,block,extra", [("zipf", 65536, 0), ("kennedy", 32768, 4097), ("mixed", 131072, 65536 + 5),
                                              ("kennedy", 1 << 20, 12345)])
-def test_phased_static_decode_through_the_host_api(ctx, gen, block, extra):
-    """b2rc_decode cuts long static blocks into launches of >= 16 Ki symbols per block and ships each
-    stripe home while the next launch runs; the coder state is parked between launches."""
+def test_phased_decode_through_the_host_api(ctx, mode, gen, block, extra):
+    """b2rc_decode cuts long range-coder blocks into launches of >= 16 Ki symbols per block and ships
+    each stripe home while the next launch runs; the coder state (and the adaptive model) is parked
+    between launches."""
     n = (2 << 26) + extra                      # two or three pipeline chunks
     data = synth.GENERATORS[gen](n)
-    enc = ctx.encode(STATIC, data, block)
+    enc = ctx.encode(mode, data, block)
     out = ctx.decode(enc)
     assert out.size == n
     if out.tobytes() != data.tobytes():
