@@ -158,8 +158,6 @@ __device__ __forceinline__ void st_u16(u8* p, u32 v)
     asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-constexpr int ANS_ENC_AHEAD = 6;
-
 template <bool RAGGED>
 __device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32 len, s32 K4, u32 tb, u8* slot, u32& x,
                                                   u32& w, u32 lane)
@@ -199,11 +197,6 @@ __device__ __forceinline__ void ans_enc_word_loop(const u8* __restrict__ sp, u32
     lookup(S[3], e[1], m[1]);
     fetch(K4 - 5, S[3]);
     for(s32 k = K4 - 1; k >= 0; k -= 4) {
-        // the 128 input bytes of the trip ANS_ENC_AHEAD trips from now: towards L2, one
-        // sector per lane 0..3 of the group, so the byte loads above never wait for DRAM
-        if(j < 4u && k >= 4 * ANS_ENC_AHEAD + 3) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + 32 * (s64)(k - 3 - 4 * ANS_ENC_AHEAD) + 32u * j));
-        }
 #pragma unroll
         for(int u = 0; u < 4; ++u) {
             const s32 q = k - u;                      // q & 3 == 3 - u

@@ -774,10 +774,6 @@ struct DecArgs {
 // prefetching LDG made every step wait for the previous step's load (profiles/).
 constexpr int INQ = 8;
 constexpr int INQ_BYTES = INQ * 128;
-__device__ __forceinline__ void cp_async4(u32 dst, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src) : "memory");
-}
 struct WordSrc {
     const u32* base;  // aligned word holding coded byte 0 of this lane's payload
     u32 lim;          // readable bytes from `base` to the end of the stream buffer

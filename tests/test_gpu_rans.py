@@ -221,3 +221,33 @@ def test_device_api_and_large_property(ctx, oracle, mode):
     o2 = torch.zeros(d2.size, dtype=torch.uint8, device="cuda")
     g2 = ctx.decode_device(e2, u2, o2)
     assert g2 == d2.size and torch.equal(o2, s2)
+
+
+@pytest.mark.parametrize("mode", [0, 1, RANS_BYTE, RANS_WORD])
+def test_random_damage_never_faults(ctx, mode):
+    """Bytes flipped anywhere in the payload area (the index stays valid): every decode either succeeds
+    with some output or reports corruption; nothing faults, and the context keeps working."""
+    from cpprcoder_b200.api import B2rcError
+    data = synth.mixed((4 << 20) + 777)
+    enc = ctx.encode(mode, data, 65536)
+    info = container.parse(enc)
+    rng = np.random.default_rng(100 + mode)
+    outcomes = {"ok": 0, "corrupt": 0}
+    for trial in range(12):
+        bad = enc.copy()
+        k = int(rng.integers(1, 200))
+        at = rng.integers(info.payload_base, bad.size, k)
+        bad[at] ^= rng.integers(1, 256, k).astype(np.uint8)
+        if trial % 3 == 0:   # a burst inside one block's header / model
+            b = int(rng.integers(0, info.nblocks))
+            lo = info.payload_base + int(info.offsets[b])
+            bad[lo:lo + 64] = rng.integers(0, 256, 64, dtype=np.uint8)
+        try:
+            out = ctx.decode(bad)
+            assert out.size == data.size
+            outcomes["ok"] += 1
+        except B2rcError as e:
+            assert e.code == -3, e
+            outcomes["corrupt"] += 1
+    assert outcomes["corrupt"] >= 1
+    assert ctx.decode(enc).tobytes() == data.tobytes()
