@@ -30,6 +30,8 @@ sys.path.insert(0, str(ROOT))
 # of 8 hardware queues, streams alias and one chunk's copy waits behind another chunk's
 # kernel; must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# NCCL writes its banner / debug lines to stdout unless told otherwise; stdout carries ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
