@@ -30,8 +30,6 @@ sys.path.insert(0, str(ROOT))
 # of 8 hardware queues, streams alias and one chunk's copy waits behind another chunk's
 # kernel; must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# NCCL writes its banner / debug lines to stdout unless told otherwise; stdout carries ONE JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
@@ -209,6 +207,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class _StdoutToStderr:
+    """NCCL prints its version banner with a C-level printf to stdout when the communicator comes up.
+    stdout carries ONE JSON line, so file descriptor 1 points at stderr while that can happen."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 # ------------------------------------------------------------------ our arm --
 def run_ours(args):
     import torch
@@ -228,7 +243,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()  # brings the communicator up (and its banner out) here
 
     cfg, gen, nbytes, mode, block = config_of(args, world)
     n_total = nbytes * world
