@@ -14,7 +14,7 @@ src = torch.minimum(torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda"
                     torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda"))
 ctx = api.Context(0)
 o = Oracle.get()
-for mode in (0, 1):
+for mode in (0, 1, 2, 3):
     enc, used = ctx.encode_device(mode, src)
     nb = (n + 65535) // 65536
     idx = enc[:32 + 8 * (nb + 1)].cpu().numpy()
