@@ -36,6 +36,9 @@ SIGNATURES = {
     "b2rc_decode_device": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
     "b2rc_k_histogram": (C.c_int, [_P, _P, _U64, _U32, _P, _P]),
     "b2rc_k_encode_blocks": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _P, _U64, _P, _P, _P]),
+    "b2rc_restart_records": (_U32, [_U32, _U32]),
+    "b2rc_k_encode_blocks_r": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _P, _U64, _P, _P, _U32, _P, _P]),
+    "b2rc_k_decode_blocks_r": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, _P, _U64, _P, _U32, _P, _P]),
     "b2rc_k_scan": (C.c_int, [_P, _P, _U64, _P, _P]),
     "b2rc_k_compact": (C.c_int, [_P, _P, _U64, _P, _P, _U64, _P, _U64, _P, _P]),
     "b2rc_k_compact_for": (C.c_int, [_P, C.c_int, _P, _U64, _P, _P, _U64, _P, _U64, _P, _P]),

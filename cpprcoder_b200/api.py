@@ -149,8 +149,9 @@ class Context:
         return freq16
 
     def encode_blocks(self, mode: int, src: torch.Tensor, block: int = DEFAULT_BLOCK, freq16=None, slots=None,
-                      sizes=None, err=None):
-        """K1 (when needed) + K2.  Returns (slots, slot_stride, sizes, err)."""
+                      sizes=None, err=None, restart=None, seg_syms: int = 0):
+        """K1 (when needed) + K2.  Returns (slots, slot_stride, sizes, err).  `restart` (int32 tensor,
+        nblocks * restart_records(block, seg_syms) * 3) receives the static coder's restart points."""
         n = src.numel()
         nb = nblocks(n, block)
         stride = slot_bytes(block, mode)
@@ -163,8 +164,9 @@ class Context:
             err = torch.zeros(4, dtype=torch.int32, device=dev)
         if mode == MODE_STATIC and freq16 is None:
             freq16 = self.histogram(src, block)
-        self._check(self.lib.b2rc_k_encode_blocks(self.h, mode, block, _ptr(src), n, _ptr(freq16), _ptr(slots), stride,
-                                                  _ptr(sizes), _ptr(err), _stream()), "b2rc_k_encode_blocks")
+        self._check(self.lib.b2rc_k_encode_blocks_r(self.h, mode, block, _ptr(src), n, _ptr(freq16), _ptr(slots), stride,
+                                                    _ptr(sizes), _ptr(restart), seg_syms, _ptr(err), _stream()),
+                    "b2rc_k_encode_blocks_r")
         return slots, stride, sizes, err
 
     def scan(self, sizes: torch.Tensor, nb: int, offsets: torch.Tensor | None = None) -> torch.Tensor:
@@ -180,9 +182,15 @@ class Context:
                     "b2rc_k_compact_for")
 
     def decode_blocks(self, mode: int, payload: torch.Tensor, payload_len: int, offsets: torch.Tensor, nb: int,
-                      dst: torch.Tensor, n: int, block: int = DEFAULT_BLOCK, err: torch.Tensor | None = None):
+                      dst: torch.Tensor, n: int, block: int = DEFAULT_BLOCK, err: torch.Tensor | None = None,
+                      restart=None, seg_syms: int = 0):
         if err is None:
             err = torch.zeros(4, dtype=torch.int32, device=dst.device)
-        self._check(self.lib.b2rc_k_decode_blocks(self.h, mode, block, _ptr(payload), payload_len, _ptr(offsets), nb,
-                                                  _ptr(dst), n, _ptr(err), _stream()), "b2rc_k_decode_blocks")
+        self._check(self.lib.b2rc_k_decode_blocks_r(self.h, mode, block, _ptr(payload), payload_len, _ptr(offsets), nb,
+                                                    _ptr(dst), n, _ptr(restart), seg_syms, _ptr(err), _stream()),
+                    "b2rc_k_decode_blocks_r")
         return err
+
+    @staticmethod
+    def restart_records(block: int, seg_syms: int) -> int:
+        return int(_lib.load().b2rc_restart_records(block, seg_syms))

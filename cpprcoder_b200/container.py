@@ -31,6 +31,8 @@ class Info:
     nblocks: int
     offsets: np.ndarray  # uint64, nblocks + 1
     payload_base: int
+    seg_syms: int = 0                 # restart points of the static coder every so many symbols (0: none)
+    restart: np.ndarray | None = None  # uint32 [nblocks][records][3]: bytes shifted, encoder low, range
 
     def payload(self, buf: np.ndarray, b: int) -> np.ndarray:
         lo = self.payload_base + int(self.offsets[b])
@@ -38,8 +40,14 @@ class Info:
         return buf[lo:hi]
 
 
-def pack_header(mode: int, block: int, total: int, nblocks: int) -> bytes:
-    return struct.pack("<IHHIIQQ", MAGIC, 1, mode, block, 0, total, nblocks)
+def restart_records(block: int, seg_syms: int) -> int:
+    ok = seg_syms >= 64 and seg_syms % 64 == 0 and seg_syms < block
+    return (block + seg_syms - 1) // seg_syms - 1 if ok else 0
+
+
+def pack_header(mode: int, block: int, total: int, nblocks: int, seg_syms: int = 0) -> bytes:
+    flags = (1 | ((seg_syms // 64) << 8)) if seg_syms else 0
+    return struct.pack("<IHHIIQQ", MAGIC, 1, mode, block, flags, total, nblocks)
 
 
 def parse(buf) -> Info:
@@ -47,15 +55,25 @@ def parse(buf) -> Info:
     if buf.size < HEADER + 8:
         raise ValueError("container shorter than its header")
     magic, version, mode, block, flags, total, nblocks = struct.unpack("<IHHIIQQ", buf[:HEADER].tobytes())
-    if magic != MAGIC or version != 1 or mode > 3 or flags != 0 or not block_ok(block):
+    if magic != MAGIC or version != 1 or mode > 3 or not block_ok(block):
         raise ValueError("bad container header")
+    seg_syms = (flags >> 8) * 64
+    if flags and ((flags & 0xFF) != 1 or mode != 0 or restart_records(block, seg_syms) == 0):
+        raise ValueError("bad container flags")
     if nblocks != nblocks_of(total, block) or HEADER + 8 * (nblocks + 1) > buf.size:
         raise ValueError("container index does not fit")
     offsets = np.frombuffer(buf[HEADER:HEADER + 8 * (nblocks + 1)].tobytes(), dtype=np.uint64)
     base = HEADER + 8 * (nblocks + 1)
     if offsets[0] != 0 or np.any(np.diff(offsets.astype(np.int64)) < 0) or base + int(offsets[-1]) > buf.size:
         raise ValueError("container offsets are not monotone / in range")
-    return Info(mode, block, total, nblocks, offsets, base)
+    restart = None
+    if flags:
+        at = base + ((int(offsets[-1]) + 3) & ~3)
+        words = nblocks * restart_records(block, seg_syms) * 3
+        if at + 4 * words > buf.size:
+            raise ValueError("restart table does not fit")
+        restart = np.frombuffer(buf[at:at + 4 * words].tobytes(), dtype=np.uint32).reshape(nblocks, -1, 3)
+    return Info(mode, block, total, nblocks, offsets, base, seg_syms if flags else 0, restart)
 
 
 def build(mode: int, block: int, total: int, payloads) -> np.ndarray:

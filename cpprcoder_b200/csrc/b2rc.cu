@@ -53,6 +53,9 @@ struct b2rc_ctx {
     u64* h_ends;  // pinned
     u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
     u64 max_phases;  // <= B2RC_PHASES; env B2RC_PHASES overrides (1 switches the phased decode off)
+    u32 seg_syms;    // restart points of the static coder every so many symbols; env B2RC_RESTART_SYMS (0: none)
+    u32* restart;    // device scratch: the table while a container is being written / read
+    size_t restart_cap;
     struct Result {
         int err;
         int pad;
@@ -124,6 +127,15 @@ bool is_ans(int mode)
 {
     return mode == B2RC_MODE_RANS_BYTE || mode == B2RC_MODE_RANS_WORD;
 }
+bool seg_ok(u32 block_size, u32 seg_syms)
+{
+    return seg_syms >= 64u && (seg_syms % 64u) == 0u && seg_syms < block_size;
+}
+// segment length a container of this mode / block size is written with by this context
+u32 seg_for(const b2rc_ctx* ctx, int mode, u32 block_size)
+{
+    return (mode == B2RC_MODE_STATIC && seg_ok(block_size, ctx->seg_syms)) ? ctx->seg_syms : 0u;
+}
 bool aligned16(const void* p)
 {
     return ((uintptr_t)p & 15u) == 0;
@@ -131,6 +143,15 @@ bool aligned16(const void* p)
 u64 index_bytes(u64 nblocks)
 {
     return (u64)B2RC_HEADER_BYTES + 8ull * (nblocks + 1);
+}
+// header flags: bit 0 = a restart table follows the payloads, bits 8.. = its segment length / 64
+u32 flags_of(u32 seg_syms)
+{
+    return seg_syms ? (1u | ((seg_syms / 64u) << 8)) : 0u;
+}
+u64 align4(u64 x)
+{
+    return (x + 3ull) & ~3ull;
 }
 
 // dynamic shared memory of the coder kernels (one warp per CTA)
@@ -164,6 +185,7 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
+    CK(cudaFuncSetAttribute(k_dec_static_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SEG_SMEM));
     return B2RC_OK;
 }
 
@@ -277,7 +299,12 @@ uint64_t b2rc_bound(int mode, uint64_t n, uint32_t block_size)
         return index_bytes(0);
     }
     const u64 last = n - (nb - 1) * block_size;
-    return index_bytes(nb) + (nb - 1) * b2rc_slot_bytes_for(mode, block_size) + b2rc_slot_bytes_for(mode, (u32)last);
+    // room for a restart table at the shortest segment length a context can be set to
+    const u64 table = mode == B2RC_MODE_STATIC
+                          ? 4ull + nb * 12ull * b2rc_restart_records(block_size, B2RC_MIN_RESTART_SYMS)
+                          : 0ull;
+    return index_bytes(nb) + (nb - 1) * b2rc_slot_bytes_for(mode, block_size) + b2rc_slot_bytes_for(mode, (u32)last) +
+           table;
 }
 
 int b2rc_ctx_create(int device, b2rc_ctx** out)
@@ -313,6 +340,13 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         }
     }
     ctx->max_phases = 4;  // measured on B200: 4 and 8 launches per chunk time the same
+    ctx->seg_syms = B2RC_DEFAULT_RESTART_SYMS;
+    if(const char* e = getenv("B2RC_RESTART_SYMS")) {
+        const long v = atol(e);
+        if(v == 0 || (v >= (long)B2RC_MIN_RESTART_SYMS && v <= (1 << 22) && v % 64 == 0)) {
+            ctx->seg_syms = (u32)v;
+        }
+    }
     if(const char* e = getenv("B2RC_PHASES")) {
         const long v = atol(e);
         if(v >= 1 && v <= B2RC_PHASES) {
@@ -428,6 +462,7 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
         }
     }
     cudaFree(ctx->dec_state);
+    cudaFree(ctx->restart);
     cudaFree(ctx->dec_model);
     cudaFree(ctx->d_ends);
     if(ctx->h_ends) {
@@ -494,8 +529,14 @@ int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, u
     memcpy(h, src, sizeof h);
     const u32 version = h[1] & 0xFFFFu, md = h[1] >> 16;
     const u64 tot = (u64)h[4] | ((u64)h[5] << 32), nb = (u64)h[6] | ((u64)h[7] << 32);
-    if(h[0] != 0x43523242u || version != 1u || !mode_ok((int)md) || !block_ok(h[2]) || h[3] != 0u) {
+    if(h[0] != 0x43523242u || version != 1u || !mode_ok((int)md) || !block_ok(h[2])) {
         return B2RC_E_CORRUPT;
+    }
+    if(h[3] != 0u) {  // a restart table: static coder only, a legal segment length, nothing else set
+        const u32 seg = (h[3] >> 8) * 64u;
+        if((h[3] & 0xFFu) != 1u || md != (u32)B2RC_MODE_STATIC || !seg_ok(h[2], seg)) {
+            return B2RC_E_CORRUPT;
+        }
     }
     if(nb != b2rc_nblocks(tot, h[2]) || nb > (n - B2RC_HEADER_BYTES) / 8 - 1) {
         return B2RC_E_CORRUPT;
@@ -552,6 +593,8 @@ static int ans_encode_blocks(b2rc_ctx* ctx, int mode, u32 block, const u8* d_src
     a.slot_stride = stride;
     a.sizes = d_sizes;
     a.err = d_err;
+    a.restart = nullptr;
+    a.seg_syms = 0;
     KernelTimer kt(ctx, B2RC_K_ENCODE, st);
     if(mode == B2RC_MODE_RANS_WORD) {
         k_ans_enc_word<<<(unsigned)((nb + 3) / 4), 32, 0, st>>>(a);
@@ -599,10 +642,27 @@ int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t b
     return launch_check(ctx, "k_hist");
 }
 
+
+uint32_t b2rc_restart_records(uint32_t block_size, uint32_t seg_syms)
+{
+    return seg_ok(block_size, seg_syms) ? (block_size + seg_syms - 1u) / seg_syms - 1u : 0u;
+}
+
 int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
                          const uint16_t* d_freq16, uint8_t* d_slots, uint64_t slot_stride, uint32_t* d_sizes,
                          int* d_err, void* cuda_stream)
 {
+    return b2rc_k_encode_blocks_r(ctx, mode, block_size, d_src, n, d_freq16, d_slots, slot_stride, d_sizes, nullptr, 0u,
+                                  d_err, cuda_stream);
+}
+
+int b2rc_k_encode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
+                           const uint16_t* d_freq16, uint8_t* d_slots, uint64_t slot_stride, uint32_t* d_sizes,
+                           uint32_t* d_restart, uint32_t seg_syms, int* d_err, void* cuda_stream)
+{
+    if(d_restart && (mode != B2RC_MODE_STATIC || !seg_ok(block_size, seg_syms) || ((uintptr_t)d_restart & 3u))) {
+        return B2RC_E_ARG;
+    }
     if(!ctx || !d_src || !d_slots || !d_sizes || !d_err || !mode_ok(mode) || !block_ok(block_size) ||
        !aligned16(d_src) || !aligned16(d_slots) || (slot_stride & 15u) ||
        slot_stride < b2rc_slot_bytes_for(mode, block_size) || slot_stride > 0xFFFFFFF0ull) {
@@ -632,6 +692,12 @@ int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     a.slot_stride = slot_stride;
     a.sizes = d_sizes;
     a.err = d_err;
+    a.restart = d_restart;
+    a.seg_syms = d_restart ? seg_syms : 0u;
+    if(d_restart) {
+        // 0xFF: "no such point" for blocks shorter than the segment start
+        CK(cudaMemsetAsync(d_restart, 0xFF, (size_t)(nb * b2rc_restart_records(block_size, seg_syms) * 12u), st));
+    }
     const unsigned grid = (unsigned)((nb + 31) / 32);
     KernelTimer kt(ctx, B2RC_K_ENCODE, st);
     if(mode == B2RC_MODE_STATIC) {
@@ -651,10 +717,10 @@ int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
 }
 
 static int scan_launch(b2rc_ctx* ctx, const u32* d_sizes, u64 nb, u64* d_offsets, u64* d_total, u8* d_header, u32 mode,
-                       u32 block, u64 n, cudaStream_t st, const u64* d_base = nullptr)
+                       u32 block, u64 n, cudaStream_t st, const u64* d_base = nullptr, u32 flags = 0)
 {
     KernelTimer kt(ctx, B2RC_K_SCAN, st);
-    k_scan<<<1, SCAN_THREADS, 0, st>>>(d_sizes, nb, d_offsets, d_total, d_header, mode, block, n, d_base);
+    k_scan<<<1, SCAN_THREADS, 0, st>>>(d_sizes, nb, d_offsets, d_total, d_header, mode, block, n, d_base, flags);
     return launch_check(ctx, "k_scan");
 }
 
@@ -716,6 +782,46 @@ int b2rc_k_decode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
                          0u, 0u, nullptr, nullptr);
 }
 
+int b2rc_k_decode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload,
+                           uint64_t payload_len, const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n,
+                           const uint32_t* d_restart, uint32_t seg_syms, int* d_err, void* cuda_stream)
+{
+    if(!d_restart) {
+        return b2rc_k_decode_blocks(ctx, mode, block_size, d_payload, payload_len, d_offsets, nblocks, d_dst, n, d_err,
+                                    cuda_stream);
+    }
+    if(!ctx || !d_payload || !d_offsets || !d_dst || !d_err || mode != B2RC_MODE_STATIC || !block_ok(block_size) ||
+       !seg_ok(block_size, seg_syms) || !aligned16(d_dst) || ((uintptr_t)d_offsets & 7u) || ((uintptr_t)d_restart & 3u) ||
+       nblocks != b2rc_nblocks(n, block_size)) {
+        return B2RC_E_ARG;
+    }
+    if(nblocks == 0) {
+        return B2RC_OK;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DecArgs a;
+    a.payload = d_payload;
+    a.payload_len = payload_len;
+    a.offsets = d_offsets;
+    a.nblocks = nblocks;
+    a.block = block_size;
+    a.dst = d_dst;
+    a.n = n;
+    a.err = d_err;
+    a.sym0 = 0;
+    a.nsym = 0;
+    a.state = nullptr;
+    a.model = nullptr;
+    a.restart = d_restart;
+    a.seg_syms = seg_syms;
+    const u32 nseg = b2rc_restart_records(block_size, seg_syms) + 1u;
+    const dim3 grid((unsigned)((nblocks + 31) / 32), (nseg + SEG_WARPS - 1u) / SEG_WARPS);
+    KernelTimer kt(ctx, B2RC_K_DECODE, st);
+    k_dec_static_seg<<<grid, 32 * SEG_WARPS, DEC_SEG_SMEM, st>>>(a);
+    return launch_check(ctx, "k_dec_static_seg");
+}
+
 // sym0 / nsym / d_state / d_model: phased decode of the range coders (DecArgs); 0, 0, null, null =
 // whole blocks
 static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload, uint64_t payload_len,
@@ -745,6 +851,8 @@ static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     a.nsym = nsym;
     a.state = d_state;
     a.model = d_model;
+    a.restart = nullptr;
+    a.seg_syms = 0;
     if(nsym && (is_ans(mode) || !d_state || (mode == B2RC_MODE_ADAPTIVE && !d_model) || (sym0 % TILE) || (nsym % TILE))) {
         return B2RC_E_ARG;
     }
@@ -806,18 +914,24 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
     if(need_hist && (rc = grow(ctx, ctx->freq16, ctx->freq_cap, (size_t)(nb * 512 + 16))) != B2RC_OK) {
         return rc;
     }
+    const u32 seg = nb ? seg_for(ctx, mode, block_size) : 0u;
+    const u64 table_words = seg ? nb * 3ull * b2rc_restart_records(block_size, seg) : 0ull;
+    if(seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(table_words * 4 + 16))) != B2RC_OK) {
+        return rc;
+    }
     CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
     if(nb) {
         if(need_hist && (rc = b2rc_k_histogram(ctx, d_src, n, block_size, ctx->freq16, st)) != B2RC_OK) {
             return rc;
         }
-        if((rc = b2rc_k_encode_blocks(ctx, mode, block_size, d_src, n, need_hist ? ctx->freq16 : nullptr, ctx->slots,
-                                      stride, ctx->sizes, ctx->d_err, st)) != B2RC_OK) {
+        if((rc = b2rc_k_encode_blocks_r(ctx, mode, block_size, d_src, n, need_hist ? ctx->freq16 : nullptr, ctx->slots,
+                                        stride, ctx->sizes, seg ? ctx->restart : nullptr, seg, ctx->d_err, st)) !=
+           B2RC_OK) {
             return rc;
         }
     }
     if((rc = scan_launch(ctx, ctx->sizes, nb, reinterpret_cast<u64*>(d_dst + B2RC_HEADER_BYTES), ctx->d_total, d_dst,
-                         (u32)mode, block_size, n, st)) != B2RC_OK) {
+                         (u32)mode, block_size, n, st, nullptr, flags_of(seg))) != B2RC_OK) {
         return rc;
     }
     if(nb && (rc = b2rc_k_compact_for(ctx, mode, ctx->slots, stride, ctx->sizes,
@@ -825,11 +939,17 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
                                       dst_cap - idx, ctx->d_err, st)) != B2RC_OK) {
         return rc;
     }
+    if(seg) {
+        k_put_table<<<148, 256, 0, st>>>(ctx->restart, table_words, d_dst + idx, ctx->d_total, dst_cap - idx, ctx->d_err);
+        if((rc = launch_check(ctx, "k_put_table")) != B2RC_OK) {
+            return rc;
+        }
+    }
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&ctx->h_res->total, ctx->d_total, sizeof(u64), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if(out_n) {
-        *out_n = idx + ctx->h_res->total;
+        *out_n = idx + (seg ? align4(ctx->h_res->total) + 4ull * table_words : ctx->h_res->total);
     }
     return map_kernel_err(ctx->h_res->err);
 }
@@ -847,6 +967,8 @@ int b2rc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t*
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CK(cudaMemcpyAsync(ctx->h_res->header, d_src, B2RC_HEADER_BYTES, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    u32 flags;
+    memcpy(&flags, ctx->h_res->header + 12, 4);
     int mode;
     u32 block;
     u64 total, nb;
@@ -868,11 +990,25 @@ int b2rc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t*
         return B2RC_OK;
     }
     const u64 idx = index_bytes(nb);
+    const u32* d_restart = nullptr;
+    u32 seg = 0;
+    if(flags) {
+        // the table sits behind the payloads: one more small read to learn where they end
+        seg = (flags >> 8) * 64u;
+        CK(cudaMemcpyAsync(&ctx->h_res->total, d_src + B2RC_HEADER_BYTES + 8 * nb, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const u64 pay = ctx->h_res->total;
+        const u64 bytes = nb * 12ull * b2rc_restart_records(block, seg);
+        if(pay > n - idx || align4(pay) + bytes > n - idx) {
+            return B2RC_E_CORRUPT;
+        }
+        d_restart = reinterpret_cast<const u32*>(d_src + idx + align4(pay));
+    }
     CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
     // payload_len bounds every offset the kernel reads (dec_setup)
-    if((rc = b2rc_k_decode_blocks(ctx, mode, block, d_src + idx, n - idx,
-                                  reinterpret_cast<const u64*>(d_src + B2RC_HEADER_BYTES), nb, d_dst, total, ctx->d_err,
-                                  st)) != B2RC_OK) {
+    if((rc = b2rc_k_decode_blocks_r(ctx, mode, block, d_src + idx, n - idx,
+                                    reinterpret_cast<const u64*>(d_src + B2RC_HEADER_BYTES), nb, d_dst, total, d_restart,
+                                    seg, ctx->d_err, st)) != B2RC_OK) {
         return rc;
     }
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -936,7 +1072,12 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     }
     const u64 stride = b2rc_slot_bytes_for(mode, block_size);
     const bool need_hist = mode == B2RC_MODE_STATIC;
+    const u32 seg = nb ? seg_for(ctx, mode, block_size) : 0u;
+    const u32 nrec = seg ? b2rc_restart_records(block_size, seg) : 0u;
     int rc;
+    if(seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(nb * nrec * 12ull + 16))) != B2RC_OK) {
+        return rc;
+    }
     if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
        (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(bound + 16))) != B2RC_OK ||
        (rc = grow(ctx, ctx->slots, ctx->slots_cap, (size_t)(nb * stride))) != B2RC_OK ||
@@ -967,8 +1108,9 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         if(need_hist && (rc = b2rc_k_histogram(ctx, ctx->stage_in + byte0, bytes, block_size, freq, st)) != B2RC_OK) {
             return rc;
         }
-        if((rc = b2rc_k_encode_blocks(ctx, mode, block_size, ctx->stage_in + byte0, bytes, freq,
-                                      ctx->slots + b0 * stride, stride, ctx->sizes + b0, ctx->d_err, st)) != B2RC_OK) {
+        if((rc = b2rc_k_encode_blocks_r(ctx, mode, block_size, ctx->stage_in + byte0, bytes, freq,
+                                        ctx->slots + b0 * stride, stride, ctx->sizes + b0,
+                                        seg ? ctx->restart + b0 * nrec * 3ull : nullptr, seg, ctx->d_err, st)) != B2RC_OK) {
             return rc;
         }
         if(c > 0) {
@@ -1002,11 +1144,23 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         }
     }
     const u64 total = ch.count ? ctx->h_ends[ch.count] : 0;
+    const u64 table_bytes = (u64)nb * nrec * 12ull;
+    const u64 made = idx + (seg ? align4(total) + table_bytes : total);
     if(out_n) {
-        *out_n = idx + total;
+        *out_n = made;
+    }
+    if(seg && result == B2RC_OK) {
+        if(made > dst_cap) {
+            result = B2RC_E_DST_SMALL;
+        } else {
+            // every chunk_done event has been waited for: the records are complete
+            memset(dst + idx + total, 0, (size_t)(align4(total) - total));
+            CK(cudaMemcpyAsync(dst + idx + align4(total), ctx->restart, table_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
     }
     // header from the host, index from the device
-    u32 h[8] = {0x43523242u, 1u | ((u32)mode << 16), block_size, 0u, (u32)n, (u32)(n >> 32), (u32)nb, (u32)(nb >> 32)};
+    u32 h[8] = {0x43523242u, 1u | ((u32)mode << 16), block_size, flags_of(seg), (u32)n, (u32)(n >> 32), (u32)nb,
+                (u32)(nb >> 32)};
     memcpy(dst, h, sizeof h);
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, s0));
     if(result == B2RC_OK) {
@@ -1053,16 +1207,26 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     if(nb == 0) {
         return B2RC_OK;
     }
+    // a restart table behind the payloads (static coder): the decoder then runs a chain per segment
+    u32 flags;
+    memcpy(&flags, src + 12, 4);
+    const u32 seg = flags ? (flags >> 8) * 64u : 0u;
+    const u32 nrec = seg ? b2rc_restart_records(block, seg) : 0u;
+    const u64 table_bytes = (u64)nb * nrec * 12ull;
+    if(seg && (align4(prev) + table_bytes > payload_len)) {
+        return B2RC_E_CORRUPT;
+    }
     DeviceGuard g(ctx->device);
     if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
-       (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(total + 16))) != B2RC_OK) {
+       (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(total + 16))) != B2RC_OK ||
+       (seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(table_bytes + 16))) != B2RC_OK)) {
         return rc;
     }
     const Chunks ch = plan_chunks(ctx, total, block);
     // range coders, long blocks, more than one chunk in flight: decode in phases (see below)
     u32 phases = 1, per = block;
     const u64 model_bytes = 512ull * 32ull * (block > 65536u ? 4u : 2u);  // per warp of 32 blocks
-    if(!is_ans(mode) && block >= 2u * B2RC_PHASE_MIN_SYMS && ch.count > 1 && ctx->max_phases > 1) {
+    if(!is_ans(mode) && !seg && block >= 2u * B2RC_PHASE_MIN_SYMS && ch.count > 1 && ctx->max_phases > 1) {
         phases = block / B2RC_PHASE_MIN_SYMS;
         if(phases > ctx->max_phases) {
             phases = (u32)ctx->max_phases;
@@ -1079,6 +1243,9 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     const u64* d_offsets = reinterpret_cast<const u64*>(ctx->stage_in + B2RC_HEADER_BYTES);
     CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), s0));
     CK(cudaMemcpyAsync(ctx->stage_in, src, idx, cudaMemcpyHostToDevice, s0));  // header + index
+    if(seg) {
+        CK(cudaMemcpyAsync(ctx->restart, src + idx + align4(prev), table_bytes, cudaMemcpyHostToDevice, s0));
+    }
     CK(cudaEventRecord(ctx->index_ready, s0));
     for(u64 c = 0; c < ch.count; ++c) {
         cudaStream_t st = ctx->pipe[c % B2RC_PIPE_STREAMS];
@@ -1095,8 +1262,9 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
             CK(cudaMemcpyAsync(ctx->stage_in + idx + p0, src + idx + p0, p1 - p0, cudaMemcpyHostToDevice, st));
         }
         if(phases <= 1) {
-            if((rc = b2rc_k_decode_blocks(ctx, mode, block, ctx->stage_in + idx, payload_len, d_offsets + b0, b1 - b0,
-                                          ctx->stage_out + byte0, bytes, ctx->d_err, st)) != B2RC_OK) {
+            if((rc = b2rc_k_decode_blocks_r(ctx, mode, block, ctx->stage_in + idx, payload_len, d_offsets + b0, b1 - b0,
+                                            ctx->stage_out + byte0, bytes, seg ? ctx->restart + b0 * nrec * 3ull : nullptr,
+                                            seg, ctx->d_err, st)) != B2RC_OK) {
                 return rc;
             }
             CK(cudaMemcpyAsync(dst + byte0, ctx->stage_out + byte0, bytes, cudaMemcpyDeviceToHost, st));

@@ -172,6 +172,11 @@ struct EncArgs {
     u64 slot_stride;
     u32* sizes;
     int* err;
+    // Restart points of the static coder: before symbol j * seg_syms of block
+    // b, j >= 1, the encoder records {bytes shifted out so far, low, range} at
+    // restart[(b * nrec + j - 1) * 3], nrec = ceil(block / seg_syms) - 1.  Null: none.
+    u32* restart;
+    u32 seg_syms;
 };
 
 // Tail of a block: the 4..7 bytes that do not fill a word, then the size.  `front` is what
@@ -239,6 +244,15 @@ __device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, co
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
+        if(a.restart && tix != 0u && (tix * TILE) % a.seg_syms == 0u && tix * TILE < n_b) {
+            // a segment starts here: what a decoder needs to start here too
+            const u32 nrec = (a.block + a.seg_syms - 1u) / a.seg_syms - 1u;
+            u32* rec = a.restart + ((b0 + lane) * nrec + (tix * TILE) / a.seg_syms - 1u) * 3u;
+            const u32 words = (u32)(sink.wcount + 1) + st.nff;  // words cut off the shift register so far
+            rec[0] = 4u * words + (u32)st.ocnt / 8u - 1u;       // bytes shifted out of low, the dummy byte aside
+            rec[1] = st.low;
+            rec[2] = POW2 ? (tcur << shift) : st.range;         // any range with the same range / total serves
+        }
         const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
         // Four symbols per trip.  The trip stays small on purpose: with one warp per SM
         // nothing hides an instruction fetch.  Table entries of the NEXT four symbols are
@@ -502,6 +516,15 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
                     over = true;
                 }
                 ++at;
+            },
+            [&](u32 i, u32 shifted, u32 low, u32 range) {
+                if(a.restart && i != 0u && i % a.seg_syms == 0u) {
+                    const u32 nrec = (a.block + a.seg_syms - 1u) / a.seg_syms - 1u;
+                    u32* rec = a.restart + (b * nrec + i / a.seg_syms - 1u) * 3u;
+                    rec[0] = shifted;
+                    rec[1] = low;
+                    rec[2] = range;
+                }
             });
         if(over) {
             atomicOr(a.err, ERR_SLOT_OVERFLOW);
@@ -765,6 +788,9 @@ struct DecArgs {
     u32 sym0, nsym;
     u32* state;
     u8* model;  // adaptive coder only: the count tables of 32 blocks (one CTA) per slot, parked alongside
+    // Restart points (k_dec_static_seg): the records the encoder left, see EncArgs
+    const u32* restart;
+    u32 seg_syms;
 };
 
 // Each lane reads its own payload at its own pace, one aligned word at a time.  Words
@@ -1087,6 +1113,145 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
     }
 }
 
+// ---------------------------------------------------------------- K3s, segmented --
+// Static decode from restart points: the container carries, for every block and every
+// seg_syms-th symbol, what the decoder's state is there -- {bytes shifted so far, the encoder's
+// low, range}; the decoder's own low is the stream's next four bytes minus the encoder's low
+// (DESIGN.md section 10).  A block is then seg-many independent chains instead of one.
+// Mapping: a CTA of SEG_WARPS warps takes 32 blocks; lane = block as everywhere, WARP = segment,
+// so the cumulative tables of the 32 blocks are built once and shared by the CTA with the usual
+// bank == lane layout.  blockIdx.y walks groups of SEG_WARPS segments for long blocks.
+constexpr u32 SEG_WARPS = 4;
+constexpr u32 DEC_SEG_SMEM = DEC_STATIC_TAB + SEG_WARPS * (TILE_BYTES + INQ_BYTES);
+
+__global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    const u32 sbase = smem_addr(smem);
+    u32* table = reinterpret_cast<u32*>(smem);
+    const u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u8* otile = smem + DEC_STATIC_TAB + warp * (TILE_BYTES + INQ_BYTES);
+    const u32 otile_a = sbase + DEC_STATIC_TAB + warp * (TILE_BYTES + INQ_BYTES);
+    const u32 queue_a = otile_a + TILE_BYTES;
+
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    const u32 nseg = (a.block + a.seg_syms - 1u) / a.seg_syms;
+    const u32 seg = blockIdx.y * SEG_WARPS + warp;
+
+    // where this lane's payload is; every warp needs that, warp 0 also reports a bad one
+    const u8* pay = a.payload;
+    u64 len = 0;
+    if(has) {
+        const u64 o0 = a.offsets[b], o1 = a.offsets[b + 1];
+        if(o0 <= o1 && o1 <= a.payload_len) {
+            pay = a.payload + o0;
+            len = o1 - o0;
+        }
+    }
+    bool ok = has && len >= (u64)RC_STATIC_HDR + 5u;
+    if(ok) {
+        const u32 want = (u32)pay[0] | ((u32)pay[1] << 8) | ((u32)pay[2] << 16) | ((u32)pay[3] << 24);
+        ok = want == n_b;
+    }
+    u32* mine = table + lane;
+    if(warp == 0) {
+        // read16 + calcCumulatives (cpprcoder.h:585-602, :573-583), once for the CTA
+        u32 run = 0;
+#pragma unroll 1
+        for(u32 s = 0; s < 256; ++s) {
+            u32 f = 0;
+            if(ok) {
+                f = (u32)pay[4u + 2u * s] | ((u32)pay[5u + 2u * s] << 8);
+            }
+            mine[s * 32u] = run;
+            run += f;
+        }
+        mine[256u * 32u] = run;
+        if(has && (!ok || run == 0) && blockIdx.y == 0) {
+            atomicOr(a.err, ERR_CORRUPT);
+        }
+    }
+    __syncthreads();
+    if(seg >= nseg) {
+        return;
+    }
+    u32 total = mine[256u * 32u];
+    if(total == 0) {
+        ok = false;
+        total = 1;
+    }
+    u32 k1[8];
+#pragma unroll
+    for(int j = 0; j < 8; ++j) {
+        k1[j] = mine[(32u * j) * 32u];
+    }
+    const u32 seg_lo = seg * a.seg_syms;
+    u32 seg_hi = seg_lo + a.seg_syms;
+    seg_hi = seg_hi < n_b ? seg_hi : n_b;  // my symbols: [seg_lo, seg_hi)
+    bool mine_ok = ok && seg_lo < n_b;
+    u32 skip = (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u), word0 = 0, range0 = RC_STATIC_RANGE0, enc_low = 0;
+    if(seg != 0u && mine_ok) {
+        const u32 nrec = nseg - 1u;
+        const u32* rec = a.restart + (b * nrec + seg - 1u) * 3u;
+        const u32 m = rec[0];
+        enc_low = rec[1];
+        range0 = rec[2];
+        if(m == 0xFFFFFFFFu || (u64)m + RC_STATIC_HDR + 5u > len) {
+            mine_ok = false;
+            atomicOr(a.err, ERR_CORRUPT);
+        } else {
+            // the byte at offset m of the coded stream plays the part of the dummy first byte
+            word0 = (skip + m) >> 2;
+            skip = (skip + m) & 3u;
+        }
+    }
+    WordSrc src;
+    {
+        const u8* coded = pay + RC_STATIC_HDR;
+        const u8* wbase = (const u8*)((uintptr_t)coded & ~(uintptr_t)3);
+        src.base = reinterpret_cast<const u32*>(wbase);
+        const u64 room = (u64)((a.payload + a.payload_len) - wbase);
+        src.lim = mine_ok ? (u32)(room < 0xFFFFFFF0ull ? room : 0xFFFFFFF0ull) : 0u;
+        src.q = queue_a + lane * 4u;
+        src.prime(mine_ok ? word0 : 0u);
+    }
+    const u32 n_eff = mine_ok ? seg_hi : 0u;  // symbols at or beyond this are not mine
+    const CumTab tab{sbase + lane * 4u};
+    const u32 magic = rc_magic(total);
+    const bool is_pow2 = (total & (total - 1u)) == 0;
+    const u32 shift = is_pow2 ? 31u - rc_clz(total) : 0u;
+    RcDec d;
+    rc_dec_init(d, range0, skip, src);
+    d.low -= enc_low;
+
+    const u32 n_max = __reduce_max_sync(FULL, n_eff);
+    const bool all_pow2 = __all_sync(FULL, is_pow2);
+    const bool ragged = __any_sync(FULL, n_eff != n_max);
+    const u32 tix0 = seg_lo / TILE;
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+    const u32 tix1 = ntiles > tix0 ? ntiles : tix0;
+    if(all_pow2 && !ragged && a.block <= 65536u) {
+        dec_static_tiles<2, false>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
+                                   lane);
+    } else if(all_pow2 && !ragged) {
+        dec_static_tiles<3, false>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
+                                   lane);
+    } else if(!ragged) {
+        dec_static_tiles<0, false>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
+                                   lane);
+    } else {
+        dec_static_tiles<0, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
+                                  lane);
+    }
+}
+
 // ======================================================================= K3a ==
 template <class W, class Src>
 __device__ __forceinline__ void dec_adaptive_tile(LaneTab<W>& tab, RcDec& d, Src& src, u32 otile_a, u32 tile_off,
@@ -1361,7 +1526,8 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_hist_wide(const u8* src, u6
 // and, fused into it, the 32-byte container header when `header` is not null.
 constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32* sizes, u64 nblocks, u64* offsets, u64* total_out,
-                                                       u8* header, u32 mode, u32 block, u64 n, const u64* base_in)
+                                                       u8* header, u32 mode, u32 block, u64 n, const u64* base_in,
+                                                       u32 flags)
 {
     // base_in: where this range of blocks starts in the payload area (chunked host pipeline:
     // chunk c continues where chunk c-1 ended; total_out then receives the new end)
@@ -1407,11 +1573,32 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32* sizes, u64 nbl
         h[0] = 0x43523242u;  // 'B','2','R','C'
         h[1] = 1u | (mode << 16);
         h[2] = block;
-        h[3] = 0;
+        h[3] = flags;
         h[4] = (u32)n;
         h[5] = (u32)(n >> 32);
         h[6] = (u32)nblocks;
         h[7] = (u32)(nblocks >> 32);
+    }
+}
+
+// The restart table goes behind the payloads, at the next 4-byte boundary; where that is, is only
+// known on the device when this runs (*total).
+__global__ void __launch_bounds__(256) k_put_table(const u32* table, u64 words, u8* payload, const u64* total, u64 cap,
+                                                   int* err)
+{
+    const u64 at = (*total + 3ull) & ~3ull;
+    if(at + 4ull * words > cap) {
+        if(blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicOr(err, ERR_DST_SMALL);
+        }
+        return;
+    }
+    if(blockIdx.x == 0 && threadIdx.x < (u32)(at - *total)) {
+        payload[*total + threadIdx.x] = 0;  // the padding in front of the table
+    }
+    u32* d = reinterpret_cast<u32*>(payload + at);
+    for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (u64)gridDim.x * blockDim.x) {
+        d[i] = table[i];
     }
 }
 

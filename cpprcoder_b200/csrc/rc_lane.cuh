@@ -349,12 +349,15 @@ RC_HD u32 rc_enc_finish(RcEnc& e, Sink& s, u8 tail[8])
 // 2^-32 flush quirk (final low_ == 0xFFFFFFFF, cpprcoder.h:439-451), where the
 // reference's output is NOT the big-endian sum, and as a cross-check in tests.
 // cum[257] is the exclusive prefix of the block's frequencies.  `put(byte)` appends.
-template <class CumAt, class SymAt, class Put>
-RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, Put put)
+// `mark(i, shifted, low, range)` sees the coder before symbol i: the bytes shifted out of low so
+// far, low and range -- what a restart point records.
+template <class CumAt, class SymAt, class Put, class Mark>
+RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, Put put, Mark mark)
 {
-    u32 range = RC_STATIC_RANGE0, low = 0, run = 0, held = 0;
+    u32 range = RC_STATIC_RANGE0, low = 0, run = 0, held = 0, shifted = 0;
     const u32 magic = rc_magic(total);
     for(u32 i = 0; i < n; ++i) {
+        mark(i, shifted, low, range);
         const u32 c = sym_at(i);
         const u32 t = rc_div(range, total, magic);
         const u32 lo_c = cum_at(c);
@@ -380,6 +383,7 @@ RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, 
             }
             low <<= 8;
             range <<= 8;
+            ++shifted;
         }
     }
     u8 fill = 0xFF;
@@ -395,6 +399,12 @@ RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, 
     put((u8)(low >> 16));
     put((u8)(low >> 8));
     put((u8)low);
+}
+
+template <class CumAt, class SymAt, class Put>
+RC_HD void rc_static_encode_exact(u32 n, u32 total, CumAt cum_at, SymAt sym_at, Put put)
+{
+    rc_static_encode_exact(n, total, cum_at, sym_at, put, [](u32, u32, u32, u32) {});
 }
 
 // cnt += (prod > low), without a predicate: prod + ~low carries out exactly when

@@ -19,6 +19,8 @@ import torch.distributed as dist
 
 from . import container
 
+RESTART_SYMS = 8192  # B2RC_DEFAULT_RESTART_SYMS (include/b2rc.h)
+
 
 def shard_of(n_total: int, block: int, rank: int, world: int):
     """(byte_lo, byte_hi, blk_lo, blk_hi) of `rank`'s contiguous share of an n_total-byte stream."""
@@ -68,6 +70,8 @@ class Shard:
     local_offsets: torch.Tensor  # int64, blk_hi - blk_lo + 1, relative to `payload`
     offsets: torch.Tensor        # int64, global index, replicated on every rank
     err: torch.Tensor
+    restart: torch.Tensor | None = None  # static coder: this rank's restart records (int32, device)
+    seg_syms: int = 0
 
     @property
     def base(self) -> int:
@@ -81,21 +85,27 @@ def encode_shard(ctx, mode: int, src_shard: torch.Tensor, n_total: int, block: i
     lo, hi, blk_lo, blk_hi = shard_of(n_total, block, rank, world)
     assert src_shard.numel() == hi - lo, "src_shard must hold exactly this rank's byte range"
     nb = blk_hi - blk_lo
-    slots, stride, sizes, err = ctx.encode_blocks(mode, src_shard, block)
+    # restart points (static coder): each block becomes several independent chains for the decoder
+    seg = RESTART_SYMS if mode == 0 and ctx.restart_records(block, RESTART_SYMS) else 0
+    restart = None
+    if seg:
+        restart = torch.empty(max(nb, 1) * ctx.restart_records(block, seg) * 3, dtype=torch.int32, device=src_shard.device)
+    slots, stride, sizes, err = ctx.encode_blocks(mode, src_shard, block, restart=restart, seg_syms=seg)
     local_offsets = ctx.scan(sizes, nb)
     all_sizes = allgather_sizes(sizes[:nb], n_total, block, group)  # the one collective
     offsets = global_offsets(all_sizes)
     total_local = int((offsets[blk_hi] - offsets[blk_lo]).item())
     payload = torch.empty(max(total_local, 1) + 16, dtype=torch.uint8, device=src_shard.device)
     ctx.compact(slots, stride, sizes, local_offsets, nb, payload, err, mode)
-    return Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, payload, total_local, local_offsets, offsets, err)
+    return Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, payload, total_local, local_offsets, offsets, err,
+                 restart, seg)
 
 
 def decode_shard(ctx, shard: Shard, dst_shard: torch.Tensor) -> torch.Tensor:
     """Inverse of encode_shard on the same rank; no collective."""
     lo, hi, blk_lo, blk_hi = shard_of(shard.n_total, shard.block, shard.rank, shard.world)
     return ctx.decode_blocks(shard.mode, shard.payload, shard.payload_bytes, shard.local_offsets, blk_hi - blk_lo,
-                             dst_shard, hi - lo, shard.block)
+                             dst_shard, hi - lo, shard.block, restart=shard.restart, seg_syms=shard.seg_syms)
 
 
 def stitch_on_host(shard: Shard, group=None) -> np.ndarray | None:
@@ -103,11 +113,15 @@ def stitch_on_host(shard: Shard, group=None) -> np.ndarray | None:
     B2RC container there (None elsewhere)."""
     world, rank = shard.world, shard.rank
     mine = shard.payload[:shard.payload_bytes].cpu().numpy().tobytes()
+    recs = shard.restart.cpu().numpy().tobytes() if shard.restart is not None and shard.blk_hi > shard.blk_lo else b""
     parts = [None] * world if rank == 0 else None
-    dist.gather_object(mine, parts, dst=0, group=group)
+    dist.gather_object((mine, recs), parts, dst=0, group=group)
     if rank != 0:
         return None
     nb = shard.offsets.numel() - 1
-    head = container.pack_header(shard.mode, shard.block, shard.n_total, nb)
+    head = container.pack_header(shard.mode, shard.block, shard.n_total, nb, shard.seg_syms)
     index = shard.offsets.cpu().numpy().astype(np.uint64).tobytes()
-    return np.frombuffer(head + index + b"".join(parts), dtype=np.uint8)
+    body = b"".join(p for p, _ in parts)
+    if shard.seg_syms:
+        body += bytes(-len(body) % 4) + b"".join(r for _, r in parts)
+    return np.frombuffer(head + index + body, dtype=np.uint8)

@@ -15,10 +15,12 @@
  * Framing ("B2RC" container, little endian; ours -- the reference codes one stream):
  *     0   u32  magic 'B','2','R','C'
  *     4   u16  version (1)          6  u16 mode (0 static, 1 adaptive)
- *     8   u32  block_size          12  u32 flags (0)
+ *     8   u32  block_size          12  u32 flags (0, or 1 | (seg_syms / 64) << 8: restart table)
  *     16  u64  total_uncompressed  24  u64 nblocks
  *     32  u64  offsets[nblocks+1]  relative to the payload base, offsets[0] = 0
  *     32 + 8*(nblocks+1)           payloads, back to back
+ *     [at the next 4-byte boundary, when flags say so: the restart table of the static coder,
+ *      3 x u32 per point, see b2rc_k_encode_blocks_r]
  * Payload b is byte-for-byte what the reference encoder emits for block b alone:
  * static  = u32 LE size, 256 x u16 LE frequencies, coded bytes  (cpprcoder.h:386-457)
  * adaptive = u32 LE size, coded bytes                            (cpprcoder.h:689-762)
@@ -47,6 +49,8 @@ extern "C" {
 #define B2RC_MAX_BLOCK (1u << 23)   /* ... and small enough that neither model rescales by size
                                        (cpprcoder.h:561, :1138) */
 #define B2RC_HEADER_BYTES 32u
+#define B2RC_DEFAULT_RESTART_SYMS 8192u /* restart points of the static coder, see b2rc_k_encode_blocks_r */
+#define B2RC_MIN_RESTART_SYMS 1024u     /* shortest segment a context accepts (env B2RC_RESTART_SYMS; 0 = none) */
 
 /* Status codes.  0 = the reference's `true` / Status_Success (cpprcoder.h:112-117);
  * negatives map to `false` / Status_Error in the C++ header. */
@@ -116,6 +120,19 @@ int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t b
 int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
                          const uint16_t* d_freq16, uint8_t* d_slots, uint64_t slot_stride, uint32_t* d_sizes,
                          int* d_err, void* cuda_stream);
+/* Restart points of the static coder: while encoding, K2 can record, before every seg_syms-th
+ * symbol of every block, what a decoder needs to start there -- {bytes shifted out so far, the
+ * encoder's low, range}, 3 x u32 per point, b2rc_restart_records(block, seg) points per block
+ * (0xFFFFFFFF in the first word: the block ends before that point).  The payloads do not change;
+ * a block becomes several independent chains for K3.  seg_syms: a multiple of 64 below block_size.
+ * d_restart: nblocks * records * 3 u32, 4-byte aligned; NULL = the calls above. */
+uint32_t b2rc_restart_records(uint32_t block_size, uint32_t seg_syms);
+int b2rc_k_encode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
+                           const uint16_t* d_freq16, uint8_t* d_slots, uint64_t slot_stride, uint32_t* d_sizes,
+                           uint32_t* d_restart, uint32_t seg_syms, int* d_err, void* cuda_stream);
+int b2rc_k_decode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_payload,
+                           uint64_t payload_len, const uint64_t* d_offsets, uint64_t nblocks, uint8_t* d_dst, uint64_t n,
+                           const uint32_t* d_restart, uint32_t seg_syms, int* d_err, void* cuda_stream);
 /* K4  b2rc_k_scan: d_offsets[0..nblocks] = exclusive prefix of d_sizes (u64).
  *     b2rc_k_compact: payload b -> d_payload + d_offsets[b] (payload_cap bytes available). */
 int b2rc_k_scan(b2rc_ctx* ctx, const uint32_t* d_sizes, uint64_t nblocks, uint64_t* d_offsets, void* cuda_stream);

@@ -153,6 +153,136 @@ long sim_encode(int mode, const u8* src, u32 n, u8* dst, size_t cap, int force_e
     return (long)out.size();
 }
 
+// Static encode with restart points: besides the payload, reports the
+// encoder's (bytes shifted out so far, low, range) before symbol j * seg for j = 1 .. nseg-1,
+// taken exactly where the kernel takes them -- at a commit boundary, from the words pushed so far
+// and the bits still in the shift register.  rec[(j-1)*3 + {0,1,2}]; 0xFFFFFFFF when not reached.
+long sim_encode_restart(const u8* src, u32 n, u8* dst, size_t cap, u32 seg, u32 nseg, u32* rec)
+{
+    struct CountSink {
+        typedef CountSink Checked;
+        std::vector<u8>* out;
+        s32 wcount = -1;  // as SlotSink: the first push is the placeholder
+        void settle(CountSink& s) const { s = *this; }
+        bool tight(int) const { return false; }
+        void push(u32 w)
+        {
+            if(wcount >= 0) {
+                out->push_back((u8)(w >> 24));
+                out->push_back((u8)(w >> 16));
+                out->push_back((u8)(w >> 8));
+                out->push_back((u8)w);
+            }
+            ++wcount;
+        }
+    };
+    for(u32 i = 0; i < 3 * (nseg - 1); ++i) {
+        rec[i] = 0xFFFFFFFFu;
+    }
+    std::vector<u8> out;
+    for(int k = 0; k < 4; ++k) {
+        out.push_back((u8)(n >> (8 * k)));
+    }
+    u32 freq[256], cum[257];
+    count64k(src, n, freq);
+    u32 run = 0;
+    for(int s2 = 0; s2 < 256; ++s2) {
+        out.push_back((u8)freq[s2]);
+        out.push_back((u8)(freq[s2] >> 8));
+        cum[s2] = run;
+        run += freq[s2];
+    }
+    cum[256] = run;
+    const u32 total = run, magic = rc_magic(total);
+    const bool pow2 = total && (total & (total - 1)) == 0;
+    const u32 shT = pow2 ? 31u - rc_clz(total) : 0;
+    CountSink sink;
+    sink.out = &out;
+    RcEnc e;
+    rc_enc_init(e, RC_STATIC_RANGE0);
+    u32 t = pow2 ? (e.range >> shT) : 0;
+    for(u32 i = 0; i < n; i += 4) {
+        if(i && i % seg == 0 && i / seg < nseg) {
+            u32* r = rec + 3 * (i / seg - 1);
+            const u32 words = (u32)(sink.wcount + 1) + e.nff;      // words cut off the shift register so far
+            r[0] = 4u * words + (u32)e.ocnt / 8u - 1u;              // bytes shifted out of low after the dummy byte
+            r[1] = e.low;
+            r[2] = pow2 ? (t << shT) : e.range;                     // any range with the same range >> shT serves
+        }
+        RcCut cuts[4];
+        for(u32 k = 0; k < 4; ++k) {
+            const bool active = i + k < n;
+            const u32 c = active ? src[i + k] : 0;
+            if(pow2) {
+                rc_enc_step_pow2<2>(e, t, shT, cum[c], cum[c + 1] - cum[c], cuts[k], active);
+            } else {
+                const u32 tt = active ? rc_div(e.range, total, magic) : 0;
+                rc_enc_step<3>(e, cum[c], cum[c + 1] - cum[c], tt, cuts[k], active);
+            }
+        }
+        rc_enc_commit(e, cuts, sink);
+    }
+    if(e.low == 0xFFFFFFFFu) {
+        return -2;  // the flush quirk: the kernel re-encodes such a block and drops its restart points
+    }
+    u8 tail[8];
+    const u32 nt = rc_enc_finish(e, sink, tail);
+    out.insert(out.end(), tail, tail + nt);
+    if(out.size() > cap) {
+        return -1;
+    }
+    memcpy(dst, out.data(), out.size());
+    return (long)out.size();
+}
+
+// Static decode of symbols [k, k + count) from a restart point (m, low, range) of sim_encode_restart.
+long sim_decode_from(const u8* stream, size_t stream_len, u32 lead, u32 k, u32 m, u32 enc_low, u32 range, u32 count,
+                     u8* dst)
+{
+    const u8* pay = stream + lead;
+    u32 cum[257];
+    u32 run = 0;
+    for(int s2 = 0; s2 < 256; ++s2) {
+        cum[s2] = run;
+        run += (u32)pay[4 + 2 * s2] | ((u32)pay[5 + 2 * s2] << 8);
+    }
+    cum[256] = run;
+    const u32 total = run, magic = rc_magic(total);
+    struct CumTab {
+        enum : u32 { UNIT = 1 };
+        const u32* c;
+        u32 at(u32 i) const { return c[i]; }
+    } ctab{cum};
+    u32 k1[8];
+    for(int j = 0; j < 8; ++j) {
+        k1[j] = cum[32 * j];
+    }
+    // the byte at offset m of the coded stream plays the part of the dummy first byte
+    const size_t at = lead + RC_STATIC_HDR + m;
+    WordReader rd{stream, stream_len, at & ~(size_t)3};
+    RcDec d;
+    rc_dec_init(d, range, (u32)(at & 3), rd);
+    d.low -= enc_low;
+    (void)k;
+    const bool pow2 = (total & (total - 1)) == 0;
+    const u32 shT = pow2 ? 31u - rc_clz(total) : 0;
+    u32 t = pow2 ? (d.range >> shT) : 0;
+    for(u32 i = 0; i < count; ++i) {
+        if(!pow2) {
+            t = rc_div(d.range, total, magic);
+        }
+        u32 sym, c0, fr;
+        rc_static_find(ctab, k1, t, d.low, sym, c0, fr);
+        dst[i] = (u8)sym;
+        if(!pow2) {
+            rc_dec_advance(d, c0, fr, t, rd);
+        } else {
+            rc_dec_advance_pow2<3>(d, t, shT, c0, fr, rd);
+        }
+    }
+    return (long)count;
+}
+
 // `lead` = how many bytes precede the payload inside an (aligned) stream, to exercise
 // the misaligned-start path of rc_dec_init.  src points at the aligned stream start.
 long sim_decode(int mode, const u8* stream, size_t stream_len, u32 lead, u8* dst, size_t cap)

@@ -307,3 +307,67 @@ def test_phased_decode_through_the_host_api(ctx, mode, gen, block, extra):
     d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
     assert ctx.decode_device(d_enc, enc.size, d_out) == n
     assert d_out.cpu().numpy().tobytes() == data.tobytes()
+
+
+# ---------------------------------------------------------------- restart points --
+def _sim_lib(built):
+    lib = C.CDLL(str(built.build_sim()))
+    lib.sim_encode_restart.restype = C.c_long
+    lib.sim_encode_restart.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("gen,block,extra", [("zipf", 65536, 0), ("kennedy", 65536, 4097), ("mixed", 16384, 77),
+                                             ("kennedy", 262144, 100000)])
+def test_static_container_carries_restart_points(ctx, oracle, built, gen, block, extra):
+    """The static coder's containers end in a table of restart points (one per 8192 symbols): the
+    payloads are still the reference's, the records are what the lane code computes on the CPU, and
+    the decoder -- which now runs a chain per segment -- gives the input back."""
+    n = 20 * block + extra
+    data = synth.GENERATORS[gen](n)
+    enc = ctx.encode(STATIC, data, block)
+    info = container.parse(enc)
+    assert info.seg_syms == 8192 and info.restart.shape == (info.nblocks, block // 8192 - 1, 3)
+    want = oracle.encode_blocks(STATIC, data, block, threads=4)
+    assert_blocks_equal([bytes(info.payload(enc, b)) for b in range(info.nblocks)], want, f"{gen}/{block}")
+    assert ctx.decode(enc).tobytes() == data.tobytes()
+    if block <= 65536:
+        sim = _sim_lib(built)
+        nseg = block // 8192
+        for b in (0, info.nblocks // 2, info.nblocks - 1):
+            blk = np.ascontiguousarray(data[b * block:(b + 1) * block])
+            out = np.empty(2 * blk.size + 4096, np.uint8)
+            rec = np.zeros(3 * (nseg - 1), np.uint32)
+            r = sim.sim_encode_restart(blk.ctypes.data_as(C.c_void_p), blk.size, out.ctypes.data_as(C.c_void_p), out.size,
+                                       8192, nseg, rec.ctypes.data_as(C.c_void_p))
+            assert r > 0
+            got, ref = info.restart[b].reshape(-1, 3), rec.reshape(-1, 3)
+            reached = ref[:, 0] != 0xFFFFFFFF
+            assert (got[reached][:, :2] == ref[reached][:, :2]).all(), f"position / low of block {b}"
+            # any range with the same range / total serves the decoder (a power-of-two total keeps only that)
+            total = int(np.bincount(blk, minlength=256).clip(max=0x8000 if blk.size == 65536 else None).sum())
+            assert (got[reached][:, 2] // total == ref[reached][:, 2] // total).all(), f"range of block {b}"
+            assert (got[~reached][:, 0] == 0xFFFFFFFF).all()
+    # the device API writes the same container
+    import torch
+    d_enc, used = ctx.encode_device(STATIC, torch.from_numpy(data).cuda(), block=block)
+    assert used == enc.size and d_enc[:used].cpu().numpy().tobytes() == enc.tobytes()
+    # and a container without the table (what container.build makes) decodes as before
+    plain = container.build(STATIC, block, n, want)
+    assert container.parse(plain).restart is None
+    assert ctx.decode(plain).tobytes() == data.tobytes()
+
+
+def test_restart_points_can_be_switched_off(built, oracle, monkeypatch):
+    import torch
+    from cpprcoder_b200 import api
+    monkeypatch.setenv("B2RC_RESTART_SYMS", "0")
+    other = api.Context(0)
+    try:
+        data = synth.zipf(65536 * 9 + 5)
+        enc = other.encode(STATIC, data, 65536)
+        info = container.parse(enc)
+        assert info.restart is None and enc.size == info.payload_base + int(info.offsets[-1])
+        assert other.decode(enc).tobytes() == data.tobytes()
+    finally:
+        other.close()

@@ -120,3 +120,43 @@ def test_rans_byte_lane_matches_oracle(sim):
         want = o.encode(RANS_BYTE, d)
         assert _ans_enc(sim, o, d) == want, (it, d.size)
         assert _ans_dec(sim, want, d.size, it % 4) == d.tobytes(), (it, d.size)
+
+
+# ---- restart points of the static coder (decode a block from several entry points) ----------
+def test_static_restart_points(sim):
+    sim.sim_encode_restart.restype = C.c_long
+    sim.sim_encode_restart.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p]
+    sim.sim_decode_from.restype = C.c_long
+    sim.sim_decode_from.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.c_uint32, C.c_void_p]
+    o = Oracle.get()
+    rng = np.random.default_rng(21)
+    for it in range(80):
+        n = 65536 if it % 2 == 0 else int(rng.integers(300, 65537))
+        d = np.ascontiguousarray(crafted(it % 7, n, rng))
+        nseg = 4
+        seg = 16384 if n == 65536 else max(64, (n // nseg) & ~63)
+        cap = slot_bytes(n) + 2 * n
+        out = np.empty(cap, np.uint8)
+        rec = np.zeros(3 * (nseg - 1), np.uint32)
+        r = sim.sim_encode_restart(d.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), cap, seg, nseg,
+                                   rec.ctypes.data_as(C.c_void_p))
+        if r == -2:
+            continue
+        assert r >= 0
+        pay = out[:r].tobytes()
+        assert pay == o.encode(STATIC, d), (it, n)        # capturing changes nothing in the payload
+        lead = it % 4
+        st = np.frombuffer(bytes(lead) + pay + bytes(8), dtype=np.uint8).copy()
+        for j in range(1, nseg):
+            k = j * seg
+            m, low, rge = (int(v) for v in rec[3 * (j - 1):3 * j])
+            if k >= n:
+                assert m == 0xFFFFFFFF
+                continue
+            count = min(seg, n - k)
+            got = np.empty(count, np.uint8)
+            rr = sim.sim_decode_from(st.ctypes.data_as(C.c_void_p), len(st) - 8, lead, k, m, low, rge, count,
+                                     got.ctypes.data_as(C.c_void_p))
+            assert rr == count
+            assert got.tobytes() == d[k:k + count].tobytes(), (it, n, j)
