@@ -235,6 +235,8 @@ __device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, co
 {
     const u32 ntiles = (n_max + TILE - 1) / TILE;
     u32 tcur = POW2 ? (st.range >> shift) : 0u;  // the power-of-two chain carries t, not range
+    const u32 seg_tiles = a.restart ? a.seg_syms / TILE : 0u;
+    u32 next_mark = a.restart ? seg_tiles : 0xFFFFFFFFu;  // tile index of the next restart point
     // tile 0 was staged (and committed) by the caller
 #pragma unroll 1
     for(u32 tix = 0; tix < ntiles; ++tix) {
@@ -244,14 +246,17 @@ __device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, co
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
-        if(a.restart && tix != 0u && (tix * TILE) % a.seg_syms == 0u && tix * TILE < n_b) {
+        if(tix == next_mark) {
             // a segment starts here: what a decoder needs to start here too
-            const u32 nrec = (a.block + a.seg_syms - 1u) / a.seg_syms - 1u;
-            u32* rec = a.restart + ((b0 + lane) * nrec + (tix * TILE) / a.seg_syms - 1u) * 3u;
-            const u32 words = (u32)(sink.wcount + 1) + st.nff;  // words cut off the shift register so far
-            rec[0] = 4u * words + (u32)st.ocnt / 8u - 1u;       // bytes shifted out of low, the dummy byte aside
-            rec[1] = st.low;
-            rec[2] = POW2 ? (tcur << shift) : st.range;         // any range with the same range / total serves
+            next_mark += seg_tiles;
+            if(tix * TILE < n_b) {
+                const u32 nrec = (a.block + a.seg_syms - 1u) / a.seg_syms - 1u;
+                u32* rec = a.restart + ((b0 + lane) * nrec + tix / seg_tiles - 1u) * 3u;
+                const u32 words = (u32)(sink.wcount + 1) + st.nff;  // words cut off the shift register so far
+                rec[0] = 4u * words + (u32)st.ocnt / 8u - 1u;       // bytes shifted out of low, the dummy byte aside
+                rec[1] = st.low;
+                rec[2] = POW2 ? (tcur << shift) : st.range;         // any range with the same range / total serves
+            }
         }
         const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
         // Four symbols per trip.  The trip stays small on purpose: with one warp per SM
