@@ -42,7 +42,7 @@ WORKLOADS = {
     "zipf1g-rans-word-64k": ("zipf", 1 << 30, 3, 65536),
     "mixed-rans-word-64k": ("mixed", 1 << 30, 3, 65536),
 }
-KERNEL_NAMES = {0: ("k_enc_static", "k_dec_static"), 1: ("k_enc_adaptive", "k_dec_adaptive"),
+KERNEL_NAMES = {0: ("k_enc_static", "k_dec_static_seg"), 1: ("k_enc_adaptive", "k_dec_adaptive"),
                 2: ("k_ans_enc_byte", "k_ans_dec_byte"), 3: ("k_ans_enc_word", "k_ans_dec_word")}
 METRIC = "roundtrip_GBps"
 UNIT = "GB/s"
@@ -75,6 +75,8 @@ def config_of(args, world):
         "global_bytes": nbytes * world,
         "parallelism": f"blocks sharded by contiguous range over {world} GPU(s)",
         "l2": "inputs (1 GiB per GPU) are larger than the 126 MB L2; no explicit flush",
+        "restart_points": ("every 8192 symbols (static coder: 84 B per 64 KiB block behind the payloads, counted in "
+                           "compressed_ratio; the payloads are the reference's)") if mode == 0 else "none",
     }, gen, nbytes, mode, block
 
 
@@ -382,8 +384,8 @@ def run_ours(args):
             roofline = {"kernel": KERNEL_NAMES[mode][0 if dom == "encode" else 1],
                         "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                         "frac": kernels[dom]["hbm_frac"], "traffic": traffic, "peak_source": peak_src,
-                        "note": "latency-bound coder kernel (one serial chain per block); HBM fraction shown for "
-                                "context, issue utilisation is in profiles/"}
+                        "note": "integer-pipe / latency bound coder kernel (serial chains, ~100 instructions per "
+                                "symbol); HBM fraction shown for context, issue utilisation is in profiles/"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg, "clocks": clocks,
