@@ -953,7 +953,7 @@ struct CumTab {
 
 // One tile (TILE symbols per lane).  MODE: 0 general divide, 2 / 3 power-of-two total with at
 // most 2 / 3 renormalisation rounds per symbol.
-template <int MODE, bool RAGGED, class Src>
+template <int MODE, bool RAGGED, bool PAIR = false, class Src>
 __device__ __forceinline__ void dec_static_tile(const CumTab& tab, const u32 (&k1)[8], RcDec& d, u32& t, Src& src,
                                                 u32 otile_a, u32 tile_off, u32 n_b, u32 total, u32 magic, u32 shift,
                                                 u32 lane)
@@ -971,6 +971,8 @@ __device__ __forceinline__ void dec_static_tile(const CumTab& tab, const u32 (&k
                 rc_static_find(tab, k1, t, d.low, sym, cum, freq);
                 if(MODE == 0) {
                     rc_dec_advance(d, cum, freq, t, src);
+                } else if(MODE == 2 && PAIR) {
+                    rc_dec_advance_pow2_pair(d, t, shift, cum, freq, src, (k & 1) != 0);  // the window lasts for two
                 } else {
                     rc_dec_advance_pow2<MODE>(d, t, shift, cum, freq, src);
                 }
@@ -981,7 +983,7 @@ __device__ __forceinline__ void dec_static_tile(const CumTab& tab, const u32 (&k
     }
 }
 
-template <int MODE, bool RAGGED>
+template <int MODE, bool RAGGED, bool PAIR = false>
 __device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const CumTab& tab, const u32 (&k1)[8], RcDec& d,
                                                  WordSrc& src, u8* otile, u32 otile_a, u64 b0, u32 n_b, u32 tix0,
                                                  u32 tix1, bool resume, u32 total, u32 magic, u32 shift, u32 lane)
@@ -995,9 +997,9 @@ __device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const CumTab&
         // inside the buffer: those tiles skip the bounds arithmetic of the copy requests
         if(__all_sync(FULL, src.tile_is_inside())) {
             WordSrcInside in{src};
-            dec_static_tile<MODE, RAGGED>(tab, k1, d, t, in, otile_a, tix * TILE, n_b, total, magic, shift, lane);
+            dec_static_tile<MODE, RAGGED, PAIR>(tab, k1, d, t, in, otile_a, tix * TILE, n_b, total, magic, shift, lane);
         } else {
-            dec_static_tile<MODE, RAGGED>(tab, k1, d, t, src, otile_a, tix * TILE, n_b, total, magic, shift, lane);
+            dec_static_tile<MODE, RAGGED, PAIR>(tab, k1, d, t, src, otile_a, tix * TILE, n_b, total, magic, shift, lane);
         }
         __syncwarp();
         store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
@@ -1243,7 +1245,7 @@ __global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
     const u32 ntiles = (n_max + TILE - 1) / TILE;
     const u32 tix1 = ntiles > tix0 ? ntiles : tix0;
     if(all_pow2 && !ragged && a.block <= 65536u) {
-        dec_static_tiles<2, false>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
+        dec_static_tiles<2, false, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
                                    lane);
     } else if(all_pow2 && !ragged) {
         dec_static_tiles<3, false>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,

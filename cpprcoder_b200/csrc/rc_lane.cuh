@@ -580,6 +580,24 @@ RC_HD void rc_dec_advance_pow2(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, N
     rc_dec_refill(d, next);
 }
 
+// The two halves of rc_dec_advance_pow2<2> for a window that is topped up after every second
+// symbol (k_dec_static_seg, where issue slots and not latency are the limit).
+template <class Next>
+RC_HD void rc_dec_advance_pow2_pair(RcDec& d, u32& t, u32 shift, u32 cum, u32 freq, Next& next, bool top_up)
+{
+    d.low -= cum * t;
+    const u32 r = freq * t;
+    const u32 sh = rc_norm_shift<2>(r);
+    t = (r << sh) >> shift;
+    d.low = rc_funnel_l(d.w_hi, d.low, sh);
+    d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, sh);
+    d.w_lo <<= sh;
+    d.wbits -= (s32)sh;
+    if(top_up) {
+        rc_dec_refill_pair(d, next);
+    }
+}
+
 // ------------------------------------------------------------- adaptive model --
 // AdaptiveFrequencyTable (cpprcoder.h:256-314, :1094-1261) for blocks short enough
 // that it never halves (total = 256 + i stays below 2^24, cpprcoder.h:1138): then
