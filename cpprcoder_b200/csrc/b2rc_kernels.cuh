@@ -968,7 +968,12 @@ __device__ __forceinline__ void dec_static_tile(const CumTab& tab, const u32 (&k
                     t = rc_div(d.range, total, magic);
                 }
                 u32 sym, cum, freq;
-                rc_static_find(tab, k1, t, d.low, sym, cum, freq);
+                if(PAIR) {  // the segmented kernel: fewer instructions beat a shorter chain there
+                    const u32 k0[4] = {k1[0], k1[2], k1[4], k1[6]};
+                    rc_static_find4(tab, k0, t, d.low, sym, cum, freq);
+                } else {
+                    rc_static_find(tab, k1, t, d.low, sym, cum, freq);
+                }
                 if(MODE == 0) {
                     rc_dec_advance(d, cum, freq, t, src);
                 } else if(MODE == 2 && PAIR) {
@@ -1248,13 +1253,13 @@ __global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
         dec_static_tiles<2, false, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
                                    lane);
     } else if(all_pow2 && !ragged) {
-        dec_static_tiles<3, false>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
+        dec_static_tiles<3, false, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
                                    lane);
     } else if(!ragged) {
-        dec_static_tiles<0, false>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
+        dec_static_tiles<0, false, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
                                    lane);
     } else {
-        dec_static_tiles<0, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
+        dec_static_tiles<0, true, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
                                   lane);
     }
 }

@@ -271,11 +271,20 @@ long sim_decode_from(const u8* stream, size_t stream_len, u32 lead, u32 k, u32 m
         if(!pow2) {
             t = rc_div(d.range, total, magic);
         }
-        u32 sym, c0, fr;
-        rc_static_find(ctab, k1, t, d.low, sym, c0, fr);
+        // the segmented kernel's search (four levels of four) and, for totals up to 2^16, its
+        // every-second-symbol top-up
+        u32 sym, c0, fr, s2, c2, f2;
+        const u32 k0[4] = {k1[0], k1[2], k1[4], k1[6]};
+        rc_static_find4(ctab, k0, t, d.low, sym, c0, fr);
+        rc_static_find(ctab, k1, t, d.low, s2, c2, f2);
+        if(sym != s2 || c0 != c2 || fr != f2) {
+            return -2;
+        }
         dst[i] = (u8)sym;
         if(!pow2) {
             rc_dec_advance(d, c0, fr, t, rd);
+        } else if(total <= 65536u && (count & 1u) == 0) {
+            rc_dec_advance_pow2_pair(d, t, shT, c0, fr, rd, (i & 1u) != 0);
         } else {
             rc_dec_advance_pow2<3>(d, t, shT, c0, fr, rd);
         }
