@@ -33,3 +33,28 @@ def test_merge_sizes():
     off = container.merge_sizes([[3, 4], [], [5]])
     assert off.tolist() == [0, 3, 7, 12]
     assert container.merge_sizes([]).tolist() == [0]
+
+
+def test_restart_table_framing():
+    # flags = 1 | (seg / 64) << 8; the table sits behind the payloads at the next 4-byte boundary
+    block, seg, total = 16384, 4096, 16384 * 2 + 5
+    assert container.restart_records(block, seg) == 3
+    assert container.restart_records(block, block) == 0 and container.restart_records(block, 100) == 0
+    pays = [b"x" * 7, b"yz", b"q" * 10]
+    plain = container.build(0, block, total, pays)
+    assert container.parse(plain).restart is None and container.parse(plain).seg_syms == 0
+    nb = 3
+    table = np.arange(nb * 3 * 3, dtype=np.uint32)
+    body = plain[32 + 8 * (nb + 1):].tobytes()
+    buf = np.frombuffer(container.pack_header(0, block, total, nb, seg) + plain[32:32 + 8 * (nb + 1)].tobytes() + body
+                        + bytes(-len(body) % 4) + table.tobytes(), dtype=np.uint8)
+    info = container.parse(buf)
+    assert info.seg_syms == seg and info.restart.shape == (nb, 3, 3)
+    assert (info.restart.reshape(-1) == table).all()
+    assert [bytes(info.payload(buf, b)) for b in range(nb)] == pays
+    with pytest.raises(ValueError):
+        container.parse(buf[:-4])                      # table cut short
+    bad = buf.copy()
+    bad[6] = 1                                         # adaptive mode with a restart table
+    with pytest.raises(ValueError):
+        container.parse(bad)
