@@ -69,3 +69,31 @@ def test_no_device_means_error_not_fallback(lib):
     from cpprcoder_b200 import api
     with pytest.raises(RuntimeError):
         api.Context()
+
+
+def test_restart_helpers_and_flags(lib):
+    from cpprcoder_b200 import container
+    # points per block: every seg_syms-th symbol after the first; seg must be a multiple of 64 below the block size
+    assert lib.b2rc_restart_records(65536, 8192) == 7
+    assert lib.b2rc_restart_records(1 << 20, 8192) == 127
+    assert lib.b2rc_restart_records(65536, 65536) == 0 and lib.b2rc_restart_records(65536, 100) == 0
+    assert lib.b2rc_restart_records(8192, 8192) == 0
+    # the bound leaves room for the densest table a context may be set to write (1024 symbols)
+    nb = 16
+    plain = 32 + 8 * (nb + 1) + nb * lib.b2rc_slot_bytes(65536)
+    assert lib.b2rc_bound(0, nb * 65536, 65536) >= plain + 3 + nb * 63 * 12
+    assert lib.b2rc_bound(1, nb * 65536, 65536) == plain  # the adaptive coder has no restart points
+    # peek accepts the flag for the static coder only, with a legal segment length
+    def peek(header):
+        raw = bytes(header) + bytes(8 * 17)
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        return lib.b2rc_peek(buf, len(raw), None, None, None, None)
+    assert peek(container.pack_header(0, 65536, nb * 65536, nb, 8192)) == 0
+    assert peek(container.pack_header(1, 65536, nb * 65536, nb, 8192)) == -3
+    bad = bytearray(container.pack_header(0, 65536, nb * 65536, nb, 8192))
+    bad[12] = 3                                   # unknown flag bit
+    assert peek(bad) == -3
+    bad = bytearray(container.pack_header(0, 65536, nb * 65536, nb))
+    bad[13], bad[12] = 0x10, 1                    # segment length 65536 * ... not below the block size
+    bad[14] = 0x10
+    assert peek(bad) == -3
