@@ -14,6 +14,7 @@ MODE_RANS_BYTE, MODE_RANS_WORD = 2, 3  # cppans::rANS::encode / ::encode_simd
 MODE_NAMES = {"static": 0, "adaptive": 1, "rans": 2, "rans-word": 3}
 HEADER_BYTES = 32
 DEFAULT_BLOCK = 65536
+BLK_BLOCK, BLK_CODED = 32768, 32770  # blksort::BlkSort::BlockSize / ::EncodedSize
 
 _P = C.c_void_p
 _U64 = C.c_uint64
@@ -46,6 +47,13 @@ SIGNATURES = {
     "b2rc_launch_count": (_U64, [_P]),
     "b2rc_profile": (C.c_int, [_P, C.c_int]),
     "b2rc_kernel_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
+    "b2rc_blk_encode_bound": (_U64, [_U64]),
+    "b2rc_blk_decoded_size": (_U64, [_U64]),
+    "b2rc_blk_encode_device": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
+    "b2rc_blk_decode_device": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
+    "b2rc_blk_encode": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64)]),
+    "b2rc_blk_decode": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64)]),
+    "b2rc_blk_rounds": (C.c_int, [_P, _P, _U64, C.POINTER(_U64)]),
     "b2rc_build_arch": (C.c_char_p, []),
 }
 

@@ -36,6 +36,15 @@ def nblocks(n: int, block: int) -> int:
     return int(_lib.load().b2rc_nblocks(n, block))
 
 
+def blk_encode_bound(n: int) -> int:
+    """BlkSort::encodeBound (blksort.h:404-409)."""
+    return int(_lib.load().b2rc_blk_encode_bound(n))
+
+
+def blk_decoded_size(n: int) -> int:
+    return int(_lib.load().b2rc_blk_decoded_size(n))
+
+
 class Context:
     """b2rc_ctx: one per host thread and device."""
 
@@ -69,7 +78,7 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.b2rc_launch_count(self.h))
 
-    KERNELS = {"histogram": 0, "encode": 1, "scan": 2, "compact": 3, "decode": 4}
+    KERNELS = {"histogram": 0, "encode": 1, "scan": 2, "compact": 3, "decode": 4, "blk_forward": 5, "blk_inverse": 6}
 
     @staticmethod
     def supported_modes() -> tuple:
@@ -194,3 +203,51 @@ class Context:
     @staticmethod
     def restart_records(block: int, seg_syms: int) -> int:
         return int(_lib.load().b2rc_restart_records(block, seg_syms))
+
+    # ---- block sort (blksort::BlkSort) ----------------
+    def blk_encode_device(self, src: torch.Tensor, dst: torch.Tensor | None = None) -> torch.Tensor:
+        """BlkSort::encode on device memory: every full 32 KiB block -> column + row number."""
+        n = src.numel()
+        need = blk_encode_bound(n)
+        if dst is None:
+            dst = torch.empty(max(need, 16), dtype=torch.uint8, device=src.device)
+        out_n = C.c_uint64(0)
+        self._check(self.lib.b2rc_blk_encode_device(self.h, _ptr(src), n, _ptr(dst), dst.numel(), C.byref(out_n),
+                                                    _stream()), "b2rc_blk_encode_device")
+        return dst[:int(out_n.value)]
+
+    def blk_decode_device(self, src: torch.Tensor, n_src: int | None = None, dst: torch.Tensor | None = None) -> torch.Tensor:
+        n = src.numel() if n_src is None else n_src
+        need = blk_decoded_size(n)
+        if dst is None:
+            dst = torch.empty(max(need, 16), dtype=torch.uint8, device=src.device)
+        out_n = C.c_uint64(0)
+        self._check(self.lib.b2rc_blk_decode_device(self.h, _ptr(src), n, _ptr(dst), dst.numel(), C.byref(out_n),
+                                                    _stream()), "b2rc_blk_decode_device")
+        return dst[:int(out_n.value)]
+
+    def _blk_host(self, fn, what: str, src, need: int, dst):
+        src = np.ascontiguousarray(np.frombuffer(src, dtype=np.uint8) if isinstance(src, (bytes, bytearray)) else src,
+                                   dtype=np.uint8)
+        if dst is None:
+            dst = np.empty(max(need(src.size), 1), dtype=np.uint8)
+        out_n = C.c_uint64(0)
+        self._check(fn(self.h, src.ctypes.data_as(C.c_void_p), src.size, dst.ctypes.data_as(C.c_void_p), dst.size,
+                       C.byref(out_n)), what)
+        return dst[:int(out_n.value)]
+
+    def blk_encode(self, src, dst: np.ndarray | None = None) -> np.ndarray:
+        return self._blk_host(self.lib.b2rc_blk_encode, "b2rc_blk_encode", src, blk_encode_bound, dst)
+
+    def blk_decode(self, src, dst: np.ndarray | None = None) -> np.ndarray:
+        return self._blk_host(self.lib.b2rc_blk_decode, "b2rc_blk_decode", src, blk_decoded_size, dst)
+
+    def blk_rounds(self) -> np.ndarray:
+        """Doubling rounds per block of the last forward call (bit 31: the block has a period)."""
+        nb = C.c_uint64(0)
+        self._check(self.lib.b2rc_blk_rounds(self.h, None, 0, C.byref(nb)), "b2rc_blk_rounds")
+        out = np.zeros(int(nb.value), dtype=np.uint32)
+        if out.size:
+            self._check(self.lib.b2rc_blk_rounds(self.h, out.ctypes.data_as(C.c_void_p), out.size, C.byref(nb)),
+                        "b2rc_blk_rounds")
+        return out

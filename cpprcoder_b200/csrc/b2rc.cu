@@ -9,9 +9,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "b2rc_kernels.cuh"
 #include "b2rc_ans.cuh"
+#include "b2rc_blk.cuh"
 
 using namespace b2rc;
 
@@ -62,6 +64,11 @@ struct b2rc_ctx {
         u64 total;
         u8 header[B2RC_HEADER_BYTES];
     } * h_res;  // pinned
+    u32* blk_rounds;  // block sort: doubling rounds per block of the last forward call
+    size_t blk_rounds_cap;
+    u8* blk_ties;     // block sort: scratch of the tie replay (block list, ranks, range queues)
+    size_t blk_ties_cap;
+    u64 blk_last_blocks;
     u64 launches;
     char last_err[256];
     // optional per-kernel timing (b2rc_profile): CUDA events on the launching stream
@@ -186,6 +193,9 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
     CK(cudaFuncSetAttribute(k_dec_static_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SEG_SMEM));
+    CK(cudaFuncSetAttribute(k_blk_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_FWD_SMEM));
+    CK(cudaFuncSetAttribute(k_blk_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_INV_SMEM));
+    CK(cudaFuncSetAttribute(k_blk_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_TIES_SMEM));
     return B2RC_OK;
 }
 
@@ -429,6 +439,8 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     cudaFree(ctx->stage_in);
     cudaFree(ctx->stage_out);
     cudaFree(ctx->d_err);
+    cudaFree(ctx->blk_rounds);
+    cudaFree(ctx->blk_ties);
     cudaFree(ctx->d_total);
     if(ctx->h_res) {
         cudaFreeHost(ctx->h_res);
@@ -1310,5 +1322,255 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, s0));
     CK(cudaStreamSynchronize(s0));
     return map_kernel_err(ctx->h_res->err);
+}
+
+// ------------------------------------------------------------- block sort --
+// blksort::BlkSort behind the C ABI (include/b2rc.h, "block sort").  Sizes are a function of n:
+// full 32 KiB blocks grow by two bytes, the rest is copied.
+uint64_t b2rc_blk_encode_bound(uint64_t n)
+{
+    const u64 blocks = n >> 15;
+    return blocks * BLK_CODED + (n - (blocks << 15));
+}
+
+uint64_t b2rc_blk_decoded_size(uint64_t n)
+{
+    const u64 blocks = n / BLK_CODED;
+    return blocks * BLK_N + (n - blocks * BLK_CODED);
+}
+
+static int blk_forward_launch(b2rc_ctx* ctx, const u8* d_src, u8* d_dst, u64 b0, u64 nb, cudaStream_t st)
+{
+    u64 done = 0;
+    while(done < nb) {  // a grid dimension holds 2^31 - 1 blocks: 64 TiB per launch, the loop is for form
+        const u64 now = nb - done < 0x7FFFFFFFull ? nb - done : 0x7FFFFFFFull;
+        KernelTimer kt(ctx, B2RC_K_BLK_FORWARD, st);
+        k_blk_fwd<<<(unsigned)now, BLK_THREADS, BLK_FWD_SMEM, st>>>(d_src + (b0 + done) * BLK_N, d_dst + (b0 + done) * BLK_CODED,
+                                                                    ctx->blk_rounds + b0 + done, nullptr, nullptr);
+        const int rc = launch_check(ctx, "k_blk_fwd");
+        if(rc != B2RC_OK) {
+            return rc;
+        }
+        done += now;
+    }
+    return B2RC_OK;
+}
+
+// Blocks with a period (bit 31 of their rounds word, not bit 30): the row number B1 wrote is the canonical
+// one; the reference's depends on the swaps of its quicksort.  k_blk_ties replays them (b2rc_blk.cuh, B3).
+// The stream must have drained: the rounds words are read here.  `fixed` (optional) receives the blocks
+// whose row number was rewritten.
+static int blk_fix_ties(b2rc_ctx* ctx, const u8* d_src, u8* d_dst, u64 nb, cudaStream_t st, std::vector<u64>* fixed)
+{
+    if(nb == 0) {
+        return B2RC_OK;
+    }
+    std::vector<u32> flags((size_t)nb);
+    CK(cudaMemcpyAsync(flags.data(), ctx->blk_rounds, (size_t)(nb * 4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<u32> list;
+    for(u64 b = 0; b < nb; ++b) {
+        if((flags[(size_t)b] >> 30) == 2u) {
+            list.push_back((u32)b);
+        }
+    }
+    if(list.empty()) {
+        return B2RC_OK;
+    }
+    const size_t batch = list.size() < 128 ? list.size() : 128;
+    const size_t rk_bytes = (size_t)BLK_N * 2, q_bytes = (size_t)2 * BLK_TIES_QUEUE * sizeof(TieRange);
+    int rc;
+    if((rc = grow(ctx, ctx->blk_ties, ctx->blk_ties_cap, batch * (rk_bytes + q_bytes + 4) + 256)) != B2RC_OK) {
+        return rc;
+    }
+    u16* d_rk = reinterpret_cast<u16*>(ctx->blk_ties);
+    TieRange* d_q = reinterpret_cast<TieRange*>(ctx->blk_ties + batch * rk_bytes);
+    u32* d_list = reinterpret_cast<u32*>(ctx->blk_ties + batch * (rk_bytes + q_bytes));
+    for(size_t at = 0; at < list.size(); at += batch) {
+        const size_t now = list.size() - at < batch ? list.size() - at : batch;
+        CK(cudaMemcpyAsync(d_list, list.data() + at, now * 4, cudaMemcpyHostToDevice, st));
+        k_blk_fwd<<<(unsigned)now, BLK_THREADS, BLK_FWD_SMEM, st>>>(d_src, d_dst, ctx->blk_rounds, d_list, d_rk);
+        if((rc = launch_check(ctx, "k_blk_fwd (ranks)")) != B2RC_OK) {
+            return rc;
+        }
+        k_blk_ties<<<(unsigned)now, BLK_THREADS, BLK_TIES_SMEM, st>>>(d_src, d_dst, d_list, d_rk, d_q);
+        if((rc = launch_check(ctx, "k_blk_ties")) != B2RC_OK) {
+            return rc;
+        }
+        CK(cudaStreamSynchronize(st));  // d_list is reused by the next batch
+    }
+    if(fixed) {
+        fixed->assign(list.begin(), list.end());
+    }
+    return B2RC_OK;
+}
+
+static int blk_inverse_launch(b2rc_ctx* ctx, const u8* d_src, u8* d_dst, u64 b0, u64 nb, cudaStream_t st)
+{
+    u64 done = 0;
+    while(done < nb) {
+        const u64 now = nb - done < 0x7FFFFFFFull ? nb - done : 0x7FFFFFFFull;
+        KernelTimer kt(ctx, B2RC_K_BLK_INVERSE, st);
+        k_blk_inv<<<(unsigned)now, BLK_THREADS, BLK_INV_SMEM, st>>>(d_src + (b0 + done) * BLK_CODED, d_dst + (b0 + done) * BLK_N,
+                                                                    ctx->d_err);
+        const int rc = launch_check(ctx, "k_blk_inv");
+        if(rc != B2RC_OK) {
+            return rc;
+        }
+        done += now;
+    }
+    return B2RC_OK;
+}
+
+int b2rc_blk_encode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t dst_cap,
+                           uint64_t* out_n, void* cuda_stream)
+{
+    if(!ctx || (n && (!d_src || !d_dst)) || !aligned16(d_src) || !aligned16(d_dst)) {
+        return B2RC_E_ARG;
+    }
+    const u64 need = b2rc_blk_encode_bound(n);
+    if(out_n) {
+        *out_n = need;
+    }
+    if(dst_cap < need) {
+        return B2RC_E_DST_SMALL;
+    }
+    const u64 nb = n >> 15;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc;
+    if((rc = grow(ctx, ctx->blk_rounds, ctx->blk_rounds_cap, (size_t)(nb * 4 + 16))) != B2RC_OK) {
+        return rc;
+    }
+    ctx->blk_last_blocks = nb;
+    if(nb && (rc = blk_forward_launch(ctx, d_src, d_dst, 0, nb, st)) != B2RC_OK) {
+        return rc;
+    }
+    if(n > nb * BLK_N) {
+        CK(cudaMemcpyAsync(d_dst + nb * BLK_CODED, d_src + nb * BLK_N, (size_t)(n - nb * BLK_N), cudaMemcpyDeviceToDevice, st));
+    }
+    return blk_fix_ties(ctx, d_src, d_dst, nb, st, nullptr);  // drains the stream
+}
+
+int b2rc_blk_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t dst_cap,
+                           uint64_t* out_n, void* cuda_stream)
+{
+    if(!ctx || (n && (!d_src || !d_dst)) || !aligned16(d_src) || !aligned16(d_dst)) {
+        return B2RC_E_ARG;
+    }
+    const u64 need = b2rc_blk_decoded_size(n);
+    if(out_n) {
+        *out_n = need;
+    }
+    if(dst_cap < need) {
+        return B2RC_E_DST_SMALL;
+    }
+    const u64 nb = n / BLK_CODED;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc;
+    CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
+    if(nb && (rc = blk_inverse_launch(ctx, d_src, d_dst, 0, nb, st)) != B2RC_OK) {
+        return rc;
+    }
+    if(n > nb * BLK_CODED) {
+        CK(cudaMemcpyAsync(d_dst + nb * BLK_N, d_src + nb * BLK_CODED, (size_t)(n - nb * BLK_CODED), cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return map_kernel_err(ctx->h_res->err);
+}
+
+// Host pointers: chunks of whole blocks, each on a stream of its own (copy in, kernel, copy out), so the
+// copies of one chunk overlap the sort of another.  Pinned buffers give full overlap.
+static int blk_host(b2rc_ctx* ctx, bool forward, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n)
+{
+    if(!ctx || (n && (!src || !dst))) {
+        return B2RC_E_ARG;
+    }
+    const u64 need = forward ? b2rc_blk_encode_bound(n) : b2rc_blk_decoded_size(n);
+    if(out_n) {
+        *out_n = need;
+    }
+    if(dst_cap < need) {
+        return B2RC_E_DST_SMALL;
+    }
+    const u64 in_unit = forward ? BLK_N : BLK_CODED, out_unit = forward ? BLK_CODED : BLK_N;
+    const u64 nb = n / in_unit;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
+       (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(need + 16))) != B2RC_OK ||
+       (forward && (rc = grow(ctx, ctx->blk_rounds, ctx->blk_rounds_cap, (size_t)(nb * 4 + 16))) != B2RC_OK)) {
+        return rc;
+    }
+    if(forward) {
+        ctx->blk_last_blocks = nb;
+    }
+    cudaStream_t s0 = ctx->pipe[0];
+    CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), s0));
+    CK(cudaEventRecord(ctx->index_ready, s0));
+    // chunk boundaries at even block numbers keep every chunk 4-byte aligned on the coded side
+    u64 count = n / (16ull << 20);
+    count = count < 1 ? 1 : (count > ctx->max_chunks ? ctx->max_chunks : count);
+    u64 per = ((nb + count - 1) / count + 1) & ~1ull;
+    per = per ? per : 2;
+    u64 c = 0;
+    for(u64 b0 = 0; b0 < nb; b0 += per, ++c) {
+        const u64 b1 = b0 + per < nb ? b0 + per : nb;
+        cudaStream_t st = ctx->pipe[1 + c % (B2RC_PIPE_STREAMS - 1)];
+        CK(cudaStreamWaitEvent(st, ctx->index_ready, 0));
+        CK(cudaMemcpyAsync(ctx->stage_in + b0 * in_unit, src + b0 * in_unit, (size_t)((b1 - b0) * in_unit), cudaMemcpyHostToDevice, st));
+        rc = forward ? blk_forward_launch(ctx, ctx->stage_in, ctx->stage_out, b0, b1 - b0, st)
+                     : blk_inverse_launch(ctx, ctx->stage_in, ctx->stage_out, b0, b1 - b0, st);
+        if(rc != B2RC_OK) {
+            return rc;
+        }
+        CK(cudaMemcpyAsync(dst + b0 * out_unit, ctx->stage_out + b0 * out_unit, (size_t)((b1 - b0) * out_unit), cudaMemcpyDeviceToHost, st));
+    }
+    if(n > nb * in_unit) {
+        memcpy(dst + nb * out_unit, src + nb * in_unit, (size_t)(n - nb * in_unit));  // the tail never visits the device
+    }
+    for(int k = 1; k < B2RC_PIPE_STREAMS; ++k) {
+        CK(cudaStreamSynchronize(ctx->pipe[k]));
+    }
+    if(forward) {
+        std::vector<u64> fixed;
+        if((rc = blk_fix_ties(ctx, ctx->stage_in, ctx->stage_out, nb, s0, &fixed)) != B2RC_OK) {
+            return rc;
+        }
+        for(u64 b : fixed) {  // two bytes per replayed block
+            CK(cudaMemcpyAsync(dst + b * BLK_CODED + BLK_N, ctx->stage_out + b * BLK_CODED + BLK_N, 2, cudaMemcpyDeviceToHost, s0));
+        }
+    }
+    CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    return map_kernel_err(ctx->h_res->err);
+}
+
+int b2rc_blk_encode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n)
+{
+    return blk_host(ctx, true, src, n, dst, dst_cap, out_n);
+}
+
+int b2rc_blk_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n)
+{
+    return blk_host(ctx, false, src, n, dst, dst_cap, out_n);
+}
+
+int b2rc_blk_rounds(b2rc_ctx* ctx, uint32_t* rounds, uint64_t cap, uint64_t* nblocks)
+{
+    if(!ctx || (cap && !rounds)) {
+        return B2RC_E_ARG;
+    }
+    if(nblocks) {
+        *nblocks = ctx->blk_last_blocks;
+    }
+    const u64 k = cap < ctx->blk_last_blocks ? cap : ctx->blk_last_blocks;
+    if(k) {
+        DeviceGuard g(ctx->device);
+        CK(cudaMemcpy(rounds, ctx->blk_rounds, (size_t)(k * 4), cudaMemcpyDeviceToHost));
+    }
+    return B2RC_OK;
 }
 }

@@ -1,0 +1,582 @@
+// b2rc_blk.cuh -- the block-sort transform of the reference (blksort::BlkSort, blksort.h) on sm_100a.
+// the pre-transform the reference's own pipelines put in front of a coder.
+//
+//   B1  k_blk_fwd   BlkSort::encode_internal (blksort.h:444-543): the last column of the sorted cyclic
+//                   rotations of a 32 KiB block + the row of the unrotated block
+//   B2  k_blk_inv   BlkSort::decode_internal (blksort.h:545-672): stable counting sort of the column,
+//                   then the walk  p = next[p]  -- 32 768 dependent loads in the reference
+//
+// Mapping: one 32 KiB block per CTA of 1024 threads, everything in shared memory (3 x 64 KiB of u16
+// rows/ranks + 16 KiB of counters: the 227 KB of an sm_100 SM is what makes this a one-CTA problem).
+//
+// Forward: the reference sorts rotations with a multikey quicksort that compares byte by byte
+// (O(n * common prefix): 1-2 s for one block of zeros).  Here: prefix doubling.  Rows are sorted by their
+// first two bytes, ranked, and then each round turns the order by h bytes into the order by 2h: walking
+// the current order and stepping every row h back lists all rows by their SECOND half; two stable 8-bit
+// counting passes on the rank of the FIRST half finish the round.  Ranks are bucket heads, so rows that
+// are already alone stay where they are.  The loop stops as soon as all ranks differ (log2 of the longest
+// repeat, 4-9 rounds on text) or at h = 32 768 (a block with a period: equal rotations have equal last
+// bytes, the column does not depend on the tie order; the row number is fixed by B3).
+// The stable pass is warp-chunked: warp w owns rows [1024 w, 1024 w + 1024) of the input order, counts
+// them per digit (match.any elects one lane per distinct digit: no atomics), a CTA scan in (digit, warp)
+// order gives each warp its first slot per digit, and the warp then places its rows 32 at a time, rank
+// within the 32 from the same match mask.
+//
+// Inverse: the walk is a linked list through a permutation; pointer doubling (J <- J o J) gives the
+// 2^k-th successor of every row, so after round k the first 2^(k+1) positions of the walk are known:
+// 15 rounds of 32 768 independent gathers instead of 32 768 dependent ones.  Works for permutations with
+// several cycles (blocks with a period) exactly like the reference's walk does.
+#pragma once
+#include "b2rc_kernels.cuh"
+
+namespace b2rc
+{
+constexpr u32 BLK_N = 32768u;      // BlkSort::BlockSize, blksort.h:80
+constexpr u32 BLK_M = BLK_N - 1u;
+constexpr u32 BLK_CODED = 32770u;  // BlkSort::EncodedSize, blksort.h:83
+constexpr u32 BLK_THREADS = 1024u;
+
+// forward kernel, byte offsets in dynamic shared memory
+constexpr u32 BF_SA = 0u, BF_TMP = 65536u, BF_RK = 131072u, BF_CNT = 196608u, BF_FB = 212992u, BF_MISC = 217088u;
+constexpr u32 BLK_FWD_SMEM = BF_MISC + 512u;
+// inverse kernel: two jump tables, the walk, the column; the counters of the one counting pass sit in the
+// second jump table, which is not in use yet
+constexpr u32 BI_JA = 0u, BI_JB = 65536u, BI_P = 131072u, BI_L = 196608u, BI_MISC = 229376u;
+constexpr u32 BLK_INV_SMEM = BI_MISC + 512u;
+
+__device__ __forceinline__ u32 lanemask_lt()
+{
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// One stable counting pass over the 32 768 rows of a block on an 8-bit digit.  `elem(i)` is the row at
+// place i of the input order, `digit(e)` its digit; rows land in `dst` ordered by digit, input order kept
+// within a digit.  cnt: u16[32 warps][256]; misc: u32[64].  Ends with a CTA barrier.
+template <class Elem, class Digit>
+__device__ __forceinline__ void blk_pass(Elem elem, Digit digit, u16* dst, u16* cnt, u32* misc)
+{
+    const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    u32* c32 = reinterpret_cast<u32*>(cnt);
+#pragma unroll
+    for(u32 k = 0; k < 4u; ++k) {
+        c32[t + k * BLK_THREADS] = 0u;
+    }
+    __syncthreads();
+    u16* mine = cnt + warp * 256u;
+    const u32 i0 = warp * 1024u + lane;
+#pragma unroll 4
+    for(u32 r = 0; r < 32u; ++r) {
+        const u32 e = elem(i0 + r * 32u);
+        const u32 d = digit(e);
+        const u32 m = __match_any_sync(FULL, d);
+        if(lane == (u32)__ffs((int)m) - 1u) {
+            mine[d] = (u16)(mine[d] + __popc(m));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        // exclusive scan of the 8192 counters in (digit, warp) order: 8 counters per thread
+        const u32 d = t >> 2, w0 = (t & 3u) * 8u;
+        u32 v[8], sum = 0;
+#pragma unroll
+        for(u32 k = 0; k < 8u; ++k) {
+            v[k] = cnt[(w0 + k) * 256u + d];
+            sum += v[k];
+        }
+        u32 incl = sum;
+#pragma unroll
+        for(u32 o = 1; o < 32u; o <<= 1) {
+            const u32 up = __shfl_up_sync(FULL, incl, o);
+            if(lane >= o) {
+                incl += up;
+            }
+        }
+        if(lane == 31u) {
+            misc[warp] = incl;
+        }
+        __syncthreads();
+        if(warp == 0u) {
+            const u32 x = misc[lane];
+            u32 xi = x;
+#pragma unroll
+            for(u32 o = 1; o < 32u; o <<= 1) {
+                const u32 up = __shfl_up_sync(FULL, xi, o);
+                if(lane >= o) {
+                    xi += up;
+                }
+            }
+            misc[32u + lane] = xi - x;
+        }
+        __syncthreads();
+        u32 run = misc[32u + warp] + incl - sum;
+#pragma unroll
+        for(u32 k = 0; k < 8u; ++k) {
+            cnt[(w0 + k) * 256u + d] = (u16)run;
+            run += v[k];
+        }
+    }
+    __syncthreads();
+    const u32 lt = lanemask_lt();
+#pragma unroll 4
+    for(u32 r = 0; r < 32u; ++r) {
+        const u32 e = elem(i0 + r * 32u);
+        const u32 d = digit(e);
+        const u32 m = __match_any_sync(FULL, d);
+        const u32 leader = (u32)__ffs((int)m) - 1u;
+        u32 first = 0;
+        if(lane == leader) {
+            first = mine[d];
+            mine[d] = (u16)(first + __popc(m));
+        }
+        first = __shfl_sync(FULL, first, leader);
+        dst[first + __popc(m & lt)] = (u16)e;
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+// New ranks after a sort: rank = place of the first row of the run of rows that do not differ (bucket
+// head).  `differs(e, ep)` compares a row with its predecessor in `sa` under the order just established;
+// it may read rk (or whatever lives there): nothing is written to rk before every flag is known.
+// fbits: u32[1024]; misc: u32[128], entries 64.. used here.  Returns the number of distinct ranks.
+template <class Differs>
+__device__ __forceinline__ u32 blk_rerank(const u16* sa, u16* rk, u32* fbits, u32* misc, Differs differs)
+{
+    const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const u32 base = warp * 1024u;
+    u32 last = 0, heads = 0;
+    u32 carry_row = warp ? sa[base - 1u] : 0u;
+#pragma unroll 4
+    for(u32 r = 0; r < 32u; ++r) {
+        const u32 i = base + r * 32u + lane;
+        const u32 e = sa[i];
+        u32 ep = __shfl_up_sync(FULL, e, 1);
+        if(lane == 0u) {
+            ep = carry_row;
+        }
+        const bool df = (i == 0u) || differs(e, ep);
+        const u32 bits = __ballot_sync(FULL, df);
+        if(lane == 0u) {
+            fbits[warp * 32u + r] = bits;
+        }
+        if(bits) {
+            last = base + r * 32u + 31u - (u32)__clz((int)bits);
+        }
+        heads += (u32)__popc(bits);
+        carry_row = __shfl_sync(FULL, e, 31);
+    }
+    if(lane == 0u) {
+        misc[64u + warp] = last;
+        misc[96u + warp] = heads;
+    }
+    __syncthreads();
+    u32 carry = __reduce_max_sync(FULL, lane < warp ? misc[64u + lane] : 0u);
+    const u32 distinct = __reduce_add_sync(FULL, misc[96u + lane]);
+    const u32 le = lanemask_lt() | (1u << lane);
+#pragma unroll 4
+    for(u32 r = 0; r < 32u; ++r) {
+        const u32 bits = fbits[warp * 32u + r];
+        const u32 i = base + r * 32u + lane;
+        const u32 mine = bits & le;
+        const u32 head = mine ? base + r * 32u + 31u - (u32)__clz((int)mine) : carry;
+        rk[sa[i]] = (u16)head;
+        if(bits) {
+            carry = base + r * 32u + 31u - (u32)__clz((int)bits);
+        }
+    }
+    __syncthreads();
+    return distinct;
+}
+
+// ------------------------------------------------------------------- B1 forward --
+// src: nblocks x 32 768 bytes (16-byte aligned); dst: nblocks x 32 770 bytes (2-byte aligned).
+// rounds (one u32 per block): how many doubling rounds the block took; bit 31 = the block has a period
+// (rotations tie): its row number is the canonical one (ties by position) until B3 has replayed it;
+// bit 30 = all rotations are equal (one repeated byte): row 0, which is what the reference reports.
+// list / rk_out (both optional, used together by the tie replay B3): CTA c sorts block list[c] and leaves the
+// final rank of every rotation in rk_out[c][32 768] instead of touching dst.
+__global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_fwd(const u8* __restrict__ src, u8* __restrict__ dst, u32* __restrict__ rounds,
+                                                             const u32* __restrict__ list, u16* __restrict__ rk_out)
+{
+    extern __shared__ __align__(16) u8 blk_sm[];
+    u16* sa = reinterpret_cast<u16*>(blk_sm + BF_SA);
+    u16* tmp = reinterpret_cast<u16*>(blk_sm + BF_TMP);
+    u16* rk = reinterpret_cast<u16*>(blk_sm + BF_RK);
+    u16* cnt = reinterpret_cast<u16*>(blk_sm + BF_CNT);
+    u32* fbits = reinterpret_cast<u32*>(blk_sm + BF_FB);
+    u32* misc = reinterpret_cast<u32*>(blk_sm + BF_MISC);
+    const u32 t = threadIdx.x;
+    const u64 blk = list ? list[blockIdx.x] : blockIdx.x;
+    const u8* s = src + blk * BLK_N;
+    // the block's bytes wait where the ranks will live: they are last read by the flags of the first ranking
+    u8* s8 = blk_sm + BF_RK;
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(s);
+        uint4* d4 = reinterpret_cast<uint4*>(s8);
+        d4[t] = __ldg(g + t);
+        d4[t + BLK_THREADS] = __ldg(g + t + BLK_THREADS);
+    }
+    __syncthreads();
+    // rows by their first two bytes: least significant byte first
+    blk_pass([&](u32 i) { return i; }, [&](u32 e) { return (u32)s8[(e + 1u) & BLK_M]; }, tmp, cnt, misc);
+    blk_pass([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)s8[e]; }, sa, cnt, misc);
+    u32 distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e, u32 ep) {
+        return s8[e] != s8[ep] || s8[(e + 1u) & BLK_M] != s8[(ep + 1u) & BLK_M];
+    });
+    u32 h = 2, nrounds = 0;
+    while(distinct < BLK_N && h < BLK_N) {
+        blk_pass([&](u32 i) { return ((u32)sa[i] - h) & BLK_M; }, [&](u32 e) { return (u32)rk[e] & 0xFFu; }, tmp, cnt, misc);
+        blk_pass([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)rk[e] >> 8; }, sa, cnt, misc);
+        distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e, u32 ep) {
+            return rk[e] != rk[ep] || rk[(e + h) & BLK_M] != rk[(ep + h) & BLK_M];
+        });
+        h <<= 1;
+        ++nrounds;
+    }
+    if(rk_out) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(rk);
+        uint4* o4 = reinterpret_cast<uint4*>(rk_out + (u64)blockIdx.x * BLK_N);
+#pragma unroll
+        for(u32 k = 0; k < 4u; ++k) {
+            o4[k * BLK_THREADS + t] = r4[k * BLK_THREADS + t];
+        }
+        return;
+    }
+    // the column: byte in front of each row; the bytes come back into the free half of tmp
+    u8* sb = blk_sm + BF_TMP;
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(s);
+        uint4* d4 = reinterpret_cast<uint4*>(sb);
+        d4[t] = __ldg(g + t);
+        d4[t + BLK_THREADS] = __ldg(g + t + BLK_THREADS);
+    }
+    __syncthreads();
+    u8* o = dst + blk * BLK_CODED;
+    const u32* sa2 = reinterpret_cast<const u32*>(sa);
+#pragma unroll 4
+    for(u32 k = 0; k < 16u; ++k) {
+        const u32 pair = sa2[k * BLK_THREADS + t];
+        const u32 a = sb[((pair & 0xFFFFu) + BLK_M) & BLK_M];
+        const u32 b = sb[((pair >> 16) + BLK_M) & BLK_M];
+        *reinterpret_cast<u16*>(o + 2u * (k * BLK_THREADS + t)) = (u16)(a | (b << 8));
+    }
+    if(t == 0u) {
+        // rank of rotation 0 = its row when all rows differ; with ties, the first row of its run
+        *reinterpret_cast<u16*>(o + BLK_N) = rk[0];
+        if(rounds) {
+            rounds[blk] = nrounds | (distinct < BLK_N ? 0x80000000u : 0u) | (distinct == 1u ? 0x40000000u : 0u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------- B2 inverse --
+// src: nblocks x 32 770 bytes (2-byte aligned); dst: nblocks x 32 768 bytes (4-byte aligned).
+__global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_inv(const u8* __restrict__ src, u8* __restrict__ dst, int* err)
+{
+    extern __shared__ __align__(16) u8 blk_sm[];
+    u16* ja = reinterpret_cast<u16*>(blk_sm + BI_JA);
+    u16* jb = reinterpret_cast<u16*>(blk_sm + BI_JB);
+    u16* walk = reinterpret_cast<u16*>(blk_sm + BI_P);
+    u8* col = blk_sm + BI_L;
+    u32* misc = reinterpret_cast<u32*>(blk_sm + BI_MISC);
+    const u32 t = threadIdx.x;
+    const u64 blk = blockIdx.x;
+    const u8* c = src + blk * BLK_CODED;
+    {
+        const u16* g = reinterpret_cast<const u16*>(c);
+        u16* d2 = reinterpret_cast<u16*>(col);
+#pragma unroll 4
+        for(u32 k = 0; k < 16u; ++k) {
+            d2[k * BLK_THREADS + t] = __ldg(g + k * BLK_THREADS + t);
+        }
+    }
+    u32 top = __ldg(reinterpret_cast<const u16*>(c + BLK_N));
+    if(top >= BLK_N) {  // the reference reads out of bounds here (blksort.h:652-654)
+        if(t == 0u) {
+            atomicOr(err, ERR_CORRUPT);
+        }
+        top = 0;
+    }
+    __syncthreads();
+    // counting_sort (blksort.h:379-402): next[k] = place in the column of the k-th smallest byte, stable
+    blk_pass([&](u32 i) { return i; }, [&](u32 e) { return (u32)col[e]; }, ja, jb, misc);
+    if(t == 0u) {
+        walk[0] = ja[top];
+    }
+    __syncthreads();
+    u16* cur = ja;
+    u16* nxt = jb;
+#pragma unroll 1
+    for(u32 k = 0; k < 15u; ++k) {
+        const u32 len = 1u << k;
+        for(u32 i = t; i < len; i += BLK_THREADS) {
+            walk[len + i] = cur[walk[i]];
+        }
+        if(k < 14u) {
+#pragma unroll 8
+            for(u32 j = 0; j < 32u; ++j) {
+                const u32 p = j * BLK_THREADS + t;
+                nxt[p] = cur[cur[p]];
+            }
+        }
+        __syncthreads();
+        u16* sw = cur;
+        cur = nxt;
+        nxt = sw;
+    }
+    u8* o = dst + blk * BLK_N;
+    const uint2* w4 = reinterpret_cast<const uint2*>(walk);
+#pragma unroll 4
+    for(u32 k = 0; k < 8u; ++k) {
+        const uint2 q = w4[k * BLK_THREADS + t];
+        const u32 v = (u32)col[q.x & 0xFFFFu] | ((u32)col[q.x >> 16] << 8) | ((u32)col[q.y & 0xFFFFu] << 16) |
+                      ((u32)col[q.y >> 16] << 24);
+        *reinterpret_cast<u32*>(o + 4u * (k * BLK_THREADS + t)) = v;
+    }
+}
+
+// ---------------------------------------------------------------- B3 tie replay --
+// A block with a period has runs of EQUAL rotations.  Their last bytes are equal, so the column is settled,
+// but the row number the reference reports for rotation 0 depends on where its unstable multikey quicksort
+// (mqsort, blksort.h:281-362, level 11, median of three on byte 0, insertion sort below 37 rows, heapsort
+// when the levels run out) happens to leave it inside its run.  This kernel replays that sort for such
+// blocks, swap for swap, with two shortcuts that cannot change a swap:
+//   * comparisons over the whole rotation (insertion sort, heapsort) are rank comparisons -- B1 has
+//     already ranked every rotation (rk_in);
+//   * a pass in which every row shows the same byte moves nothing, so a range goes straight to the first
+//     depth at which its smallest and largest rotation differ (none: all rows equal, nothing ever moves).
+// The "<", "=", ">" parts of a partition are disjoint ranges, so the order in which they are finished
+// does not matter: warps take ranges from a queue, wave after wave; lane 0 does the serial partition, the
+// warp does the range scans.
+struct TieRange {
+    u16 lo, size_m1, depth, level;
+};
+constexpr u32 BT_S = 0u, BT_V = 32768u, BT_RK = 98304u, BT_MISC = 163840u;
+constexpr u32 BLK_TIES_SMEM = BT_MISC + 64u;
+constexpr u32 BLK_TIES_QUEUE = 16384u;  // ranges per wave, at most (a range holds two rows or more)
+
+__device__ __forceinline__ void tie_sift(u16* h1, const u16* rk, int root, int last, u32 x)
+{
+    int i = root, j;
+    while((j = i << 1) <= last) {
+        if(j < last && rk[h1[j]] < rk[h1[j + 1]]) {
+            ++j;
+        }
+        if(!(rk[x] < rk[h1[j]])) {
+            break;
+        }
+        h1[i] = h1[j];
+        i = j;
+    }
+    h1[i] = (u16)x;
+}
+
+__global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_ties(const u8* __restrict__ src, u8* __restrict__ dst, const u32* __restrict__ list,
+                                                              const u16* __restrict__ rk_in, TieRange* __restrict__ queues)
+{
+    extern __shared__ __align__(16) u8 blk_sm[];
+    u8* s8 = blk_sm + BT_S;
+    u16* v = reinterpret_cast<u16*>(blk_sm + BT_V);
+    u16* rk = reinterpret_cast<u16*>(blk_sm + BT_RK);
+    u32* misc = reinterpret_cast<u32*>(blk_sm + BT_MISC);  // [0] next range to take, [1] ranges queued for the next wave
+    const u32 t = threadIdx.x, lane = t & 31u;
+    const u64 blk = list[blockIdx.x];
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(src + blk * BLK_N);
+        uint4* d4 = reinterpret_cast<uint4*>(s8);
+        d4[t] = __ldg(g + t);
+        d4[t + BLK_THREADS] = __ldg(g + t + BLK_THREADS);
+        const uint4* r4 = reinterpret_cast<const uint4*>(rk_in + (u64)blockIdx.x * BLK_N);
+        uint4* k4 = reinterpret_cast<uint4*>(rk);
+#pragma unroll
+        for(u32 k = 0; k < 4u; ++k) {
+            k4[k * BLK_THREADS + t] = r4[k * BLK_THREADS + t];
+        }
+        for(u32 k = 0; k < 32u; ++k) {
+            v[k * BLK_THREADS + t] = (u16)(k * BLK_THREADS + t);
+        }
+    }
+    TieRange* q_cur = queues + (u64)blockIdx.x * 2u * BLK_TIES_QUEUE;
+    TieRange* q_nxt = q_cur + BLK_TIES_QUEUE;
+    if(t == 0u) {
+        q_cur[0] = TieRange{0, (u16)(BLK_N - 1u), 0, 11};
+        misc[0] = 0;
+        misc[1] = 0;
+    }
+    u32 ncur = 1;
+    __syncthreads();
+    while(ncur) {
+        for(;;) {
+            u32 take = 0;
+            if(lane == 0u) {
+                take = atomicAdd(&misc[0], 1u);
+            }
+            take = __shfl_sync(FULL, take, 0);
+            if(take >= ncur) {
+                break;
+            }
+            const TieRange r = q_cur[take];
+            u16* w = v + r.lo;
+            const u32 size = (u32)r.size_m1 + 1u;
+            u32 d = r.depth;
+            if(r.level == 0u) {  // heapsort, blksort.h:235-279
+                if(lane == 0u) {
+                    u16* h1 = w - 1;
+                    int last = (int)size;
+                    for(int k = last >> 1; k >= 1; --k) {
+                        tie_sift(h1, rk, k, last, h1[k]);
+                    }
+                    while(last > 1) {
+                        const u32 x = h1[last];
+                        h1[last] = h1[1];
+                        --last;
+                        tie_sift(h1, rk, 1, last, x);
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+            if(size < 37u) {  // insertionsort, blksort.h:223-233
+                if(lane == 0u) {
+                    for(u32 i = 1; i < size; ++i) {
+                        const u32 x = w[i];
+                        int j = (int)i - 1;
+                        while(j >= 0 && rk[x] < rk[w[j]]) {
+                            w[j + 1] = w[j];
+                            --j;
+                        }
+                        w[j + 1] = (u16)x;
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+            // smallest and largest rotation of the range (rank in the high half, the row in the low half)
+            u32 mn = 0xFFFFFFFFu, mx = 0u;
+            for(u32 i = lane; i < size; i += 32u) {
+                const u32 row = w[i];
+                const u32 key = ((u32)rk[row] << 16) | row;
+                mn = key < mn ? key : mn;
+                mx = key > mx ? key : mx;
+            }
+            mn = __reduce_min_sync(FULL, mn);
+            mx = __reduce_max_sync(FULL, mx);
+            if((mn >> 16) == (mx >> 16)) {
+                continue;  // all rows equal: no pass, no insertion sort ever moves one of them
+            }
+            {
+                const u32 a = mn & 0xFFFFu, b = mx & 0xFFFFu;
+                u32 off = d;
+                for(;;) {
+                    const u32 o = off + lane;
+                    const bool ne = o < BLK_N && s8[(a + o) & BLK_M] != s8[(b + o) & BLK_M];
+                    const u32 bits = __ballot_sync(FULL, ne);
+                    if(bits) {
+                        d = off + (u32)__ffs((int)bits) - 1u;
+                        break;
+                    }
+                    off += 32u;
+                    if(off >= BLK_N) {  // cannot happen for ranks B1 produced (they differ, so do the rotations)
+                        d = BLK_N;
+                        break;
+                    }
+                }
+            }
+            if(d >= BLK_N) {
+                continue;
+            }
+            if(lane == 0u) {
+                // one pass of mqsort at depth d, blksort.h:293-358
+                const u32 q1 = size >> 2, q2 = q1 + q1, q3 = q1 + q2;
+                const u32 ba = s8[w[q1]], bb = s8[w[q2]], bc = s8[w[q3]];
+                const u32 pick = ba < bb ? (bb < bc ? w[q2] : (ba < bc ? w[q3] : w[q1])) : (ba < bc ? w[q1] : (bb < bc ? w[q3] : w[q2]));
+                const u32 p = s8[(pick + d) & BLK_M];
+                const int hi = (int)size - 1;
+                int lo = 0, up = hi, eql = 0, eqr = hi;
+                for(;;) {
+                    while(lo <= up) {
+                        const u32 row = w[lo];
+                        const u32 c = s8[(row + d) & BLK_M];
+                        if(p < c) {
+                            break;
+                        }
+                        if(p == c) {
+                            w[lo] = w[eql];
+                            w[eql] = (u16)row;
+                            ++eql;
+                        }
+                        ++lo;
+                    }
+                    while(lo <= up) {
+                        const u32 row = w[up];
+                        const u32 c = s8[(row + d) & BLK_M];
+                        if(c < p) {
+                            break;
+                        }
+                        if(p == c) {
+                            w[up] = w[eqr];
+                            w[eqr] = (u16)row;
+                            --eqr;
+                        }
+                        --up;
+                    }
+                    if(up < lo) {
+                        break;
+                    }
+                    const u16 x = w[lo];
+                    w[lo] = w[up];
+                    w[up] = x;
+                    ++lo;
+                    --up;
+                }
+                const int nl = eql < lo - eql ? eql : lo - eql;
+                for(int i = 0; i < nl; ++i) {
+                    const u16 x = w[i];
+                    w[i] = w[up - i];
+                    w[up - i] = x;
+                }
+                const int less_n = lo - eql;
+                const int ra = hi - eqr, rb = eqr - up;
+                const int nr = ra < rb ? ra : rb;
+                for(int i = 0; i < nr; ++i) {
+                    const u16 x = w[lo + i];
+                    w[lo + i] = w[hi - i];
+                    w[hi - i] = x;
+                }
+                const int gt_at = hi - (eqr - up) + 1;
+                if(less_n >= 2) {
+                    q_nxt[atomicAdd(&misc[1], 1u)] = TieRange{r.lo, (u16)(less_n - 1), (u16)d, (u16)(r.level - 1u)};
+                }
+                if((int)size - gt_at >= 2) {
+                    q_nxt[atomicAdd(&misc[1], 1u)] = TieRange{(u16)(r.lo + gt_at), (u16)((int)size - gt_at - 1), (u16)d, (u16)(r.level - 1u)};
+                }
+                if(gt_at - less_n >= 2 && d + 1u < BLK_N) {
+                    q_nxt[atomicAdd(&misc[1], 1u)] = TieRange{(u16)(r.lo + less_n), (u16)(gt_at - less_n - 1), (u16)(d + 1u), r.level};
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        ncur = misc[1];
+        __syncthreads();
+        if(t == 0u) {
+            misc[0] = 0;
+            misc[1] = 0;
+        }
+        TieRange* sw = q_cur;
+        q_cur = q_nxt;
+        q_nxt = sw;
+        __syncthreads();
+    }
+    for(u32 k = 0; k < 32u; ++k) {
+        const u32 i = k * BLK_THREADS + t;
+        if(v[i] == 0u) {
+            *reinterpret_cast<u16*>(dst + blk * BLK_CODED + BLK_N) = (u16)i;
+        }
+    }
+}
+
+}  // namespace b2rc

@@ -160,9 +160,42 @@ uint64_t b2rc_launch_count(const b2rc_ctx* ctx);
 #define B2RC_K_SCAN 2
 #define B2RC_K_COMPACT 3
 #define B2RC_K_DECODE 4
-#define B2RC_K_COUNT 5
+#define B2RC_K_BLK_FORWARD 5
+#define B2RC_K_BLK_INVERSE 6
+#define B2RC_K_COUNT 7
 int b2rc_profile(b2rc_ctx* ctx, int enable);
 int b2rc_kernel_ms(b2rc_ctx* ctx, int which, float* ms);
+/* ------------------------------------------------------------------ block sort --
+ * The reference's block-sort transform (blksort::BlkSort, blksort.h; SURVEY.md section 8f row
+ * N4), the pre-transform its own pipelines run in front of a coder (test/main.cpp:944-1002).
+ * Output format = the reference's, byte for byte: every FULL 32 KiB block of the input becomes
+ * 32 770 bytes -- the last column of its sorted cyclic rotations, then the u16 (little endian)
+ * row of the unrotated block -- and the bytes behind the last full block are copied as they
+ * are (blksort.h:418-442).  No container, no index: sizes are a function of n alone.
+ *   b2rc_blk_encode_bound   replaces BlkSort::encodeBound (blksort.h:404-409), 64-bit;
+ *   b2rc_blk_decoded_size   the exact size decode() writes for n coded bytes (the reference's
+ *                           decodeBound, blksort.h:411-416, returns n itself: an upper bound);
+ *   b2rc_blk_encode[_device] replaces BlkSort::encode (blksort.h:418-428);
+ *   b2rc_blk_decode[_device] replaces BlkSort::decode (blksort.h:430-442); B2RC_E_CORRUPT when a
+ *                           block's row number is >= 32 768 (the reference reads out of bounds).
+ * Device variants: d_src / d_dst 16-byte aligned, work queued on `cuda_stream`, the call returns
+ * after the stream has drained (it reads the error word).  Host variants pipeline chunks of
+ * blocks over copy and kernel streams.  *out_n = bytes written (or needed, on DST_SMALL). */
+#define B2RC_BLK_BLOCK 32768u
+#define B2RC_BLK_CODED 32770u
+uint64_t b2rc_blk_encode_bound(uint64_t n);
+uint64_t b2rc_blk_decoded_size(uint64_t n);
+int b2rc_blk_encode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t dst_cap,
+                           uint64_t* out_n, void* cuda_stream);
+int b2rc_blk_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t dst_cap,
+                           uint64_t* out_n, void* cuda_stream);
+int b2rc_blk_encode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n);
+int b2rc_blk_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n);
+/* Doubling rounds the forward kernel took per block in the last b2rc_blk_encode_device call of
+ * this context (bit 31: the block has a period); copies min(cap, blocks) words to host memory.
+ * Measurement / tests only. */
+int b2rc_blk_rounds(b2rc_ctx* ctx, uint32_t* rounds, uint64_t cap, uint64_t* nblocks);
+
 /* "sm_100a" etc.: the architecture the kernels were compiled for. */
 const char* b2rc_build_arch(void);
 

@@ -32,6 +32,12 @@
 #undef alignas
 #endif
 
+// The block-sort transform (blksort.h), ref_blk_* below.
+#ifdef BLKSORT_H
+#define BLKSORT_IMPLEMENTATION
+#include BLKSORT_H
+#endif
+
 namespace
 {
 using namespace cpprcoder;
@@ -251,4 +257,72 @@ int ref_hardware_threads(void)
     const unsigned h = std::thread::hardware_concurrency();
     return h ? static_cast<int>(h) : 1;
 }
+
+#ifdef BLKSORT_H
+// BlkSort::encode / ::decode over whole buffers (blksort.h:418-442).  With threads > 1 the full
+// blocks are spread over that many BlkSort objects -- the block-parallel CPU baseline.
+uint32_t ref_blk_encode_bound(uint32_t size)
+{
+    return blksort::BlkSort::encodeBound(size);
+}
+uint32_t ref_blk_decode_bound(uint32_t size)
+{
+    return blksort::BlkSort::decodeBound(size);
+}
+static void blk_run(bool enc, uint32_t blocks, uint8_t* dst, const uint8_t* src, int threads)
+{
+    std::atomic<uint32_t> next(0);
+    auto body = [&]() {
+        blksort::BlkSort bs;
+        for(;;) {
+            const uint32_t b = next.fetch_add(1);
+            if(b >= blocks) {
+                break;
+            }
+            if(enc) {
+                bs.encode(blksort::BlkSort::BlockSize, dst + static_cast<size_t>(b) * blksort::BlkSort::EncodedSize,
+                          src + static_cast<size_t>(b) * blksort::BlkSort::BlockSize);
+            } else {
+                bs.decode(blksort::BlkSort::EncodedSize, dst + static_cast<size_t>(b) * blksort::BlkSort::BlockSize,
+                          const_cast<uint8_t*>(src) + static_cast<size_t>(b) * blksort::BlkSort::EncodedSize);
+            }
+        }
+    };
+    if(threads <= 1) {
+        body();
+        return;
+    }
+    std::vector<std::thread> pool;
+    for(int i = 0; i < threads; ++i) {
+        pool.emplace_back(body);
+    }
+    for(auto& t : pool) {
+        t.join();
+    }
+}
+void ref_blk_encode(uint32_t size, uint8_t* dst, const uint8_t* src, int threads)
+{
+    if(threads <= 1) {
+        blksort::BlkSort bs;
+        bs.encode(size, dst, src);
+        return;
+    }
+    const uint32_t blocks = size >> blksort::BlkSort::BlockShift;
+    blk_run(true, blocks, dst, src, threads);
+    memcpy(dst + static_cast<size_t>(blocks) * blksort::BlkSort::EncodedSize,
+           src + static_cast<size_t>(blocks) * blksort::BlkSort::BlockSize, size - blocks * blksort::BlkSort::BlockSize);
+}
+void ref_blk_decode(uint32_t size, uint8_t* dst, const uint8_t* src, int threads)
+{
+    if(threads <= 1) {
+        blksort::BlkSort bs;
+        bs.decode(size, dst, const_cast<uint8_t*>(src));
+        return;
+    }
+    const uint32_t blocks = size / blksort::BlkSort::EncodedSize;
+    blk_run(false, blocks, dst, src, threads);
+    memcpy(dst + static_cast<size_t>(blocks) * blksort::BlkSort::BlockSize,
+           src + static_cast<size_t>(blocks) * blksort::BlkSort::EncodedSize, size - blocks * blksort::BlkSort::EncodedSize);
+}
+#endif
 }

@@ -35,3 +35,43 @@ def crafted_stream(nblocks: int, block: int, seed: int, ragged: int = 0) -> np.n
     if ragged:
         parts.append(crafted(int(rng.integers(0, 7)), ragged, rng))
     return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+
+
+def blk_cases() -> list:
+    """(label, bytes) inputs for the block-sort transform (blksort.h), shared by the CPU and GPU tests:
+    whole Canterbury files (full 32 KiB blocks + a raw tail), inputs shorter than a block, exact multiples,
+    long repeats (many doubling rounds) and blocks with a period (equal rotations: the tie cases)."""
+    from _oracle import CANTERBURY, canterbury
+    rng = np.random.default_rng(0xB150)
+    n = 32768
+    out = [(name, np.frombuffer(canterbury(name), dtype=np.uint8)) for name in CANTERBURY]
+    out += [
+        ("empty", np.zeros(0, np.uint8)),
+        ("short100", rng.integers(0, 256, 100, dtype=np.uint8)),
+        ("one-less", rng.integers(0, 256, n - 1, dtype=np.uint8)),
+        ("random-3-blocks+777", rng.integers(0, 256, 3 * n + 777, dtype=np.uint8)),
+        ("bits-2-blocks", rng.integers(0, 2, 2 * n, dtype=np.uint8)),
+        ("runs64", np.repeat(rng.integers(0, 3, n // 64, dtype=np.uint8), 64)),
+        ("zeros-then-one", np.concatenate([np.zeros(n - 1, np.uint8), np.ones(1, np.uint8)])),
+        ("two-halves-differ-last", np.concatenate([np.tile(rng.integers(0, 4, n // 2, dtype=np.uint8), 2)[:-1],
+                                                   np.full(1, 9, np.uint8)])),
+        ("crafted-7", crafted_stream(7, n, 0xB151, ragged=5000)),
+    ]
+    return out
+
+
+def blk_periodic_cases() -> list:
+    """Blocks whose rotations tie (period 1 ... 16 384).  The reference takes seconds for each on a CPU."""
+    rng = np.random.default_rng(0xB152)
+    n = 32768
+    out = [("period1", np.zeros(n, np.uint8))]
+    for p in (2, 4, 64, 1024, 16384):
+        base = rng.integers(0, 256 if p <= 64 else 4, p, dtype=np.uint8)
+        if p > 1 and np.all(base == base[0]):
+            base[0] ^= 1
+        out.append((f"period{p}", np.tile(base, n // p)))
+    for p, alpha in ((16384, 2), (4096, 2), (8192, 3), (256, 2)):  # few symbols: deep recursion, the heapsort fallback
+        out.append((f"period{p}-alpha{alpha}", np.tile(rng.integers(0, alpha, p, dtype=np.uint8), n // p)))
+    out.append(("periodic-among-others", np.concatenate([rng.integers(0, 256, n, dtype=np.uint8), np.tile(np.arange(8, dtype=np.uint8), n // 8),
+                                                         rng.integers(0, 7, n + 99, dtype=np.uint8)])))
+    return out

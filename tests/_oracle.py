@@ -234,6 +234,57 @@ class Ref(_Coder):
         return int(self.lib.ref_hardware_threads())
 
 
+# ----------------------------------------------------------------- block sort --
+BLK_BLOCK, BLK_CODED = 32768, 32770  # blksort::BlkSort::BlockSize / ::EncodedSize (blksort.h:80-83)
+
+
+def blk_encode_bound(n: int) -> int:
+    return (n >> 15) * BLK_CODED + (n & (BLK_BLOCK - 1))
+
+
+def blk_decoded_size(n: int) -> int:
+    return (n // BLK_CODED) * BLK_BLOCK + n % BLK_CODED
+
+
+class BlkSort:
+    """blksort::BlkSort on the CPU: ``BlkSort(Oracle.get())`` is the C restatement (oracle/blk_oracle.c),
+    ``BlkSort(Ref.get())`` the unmodified blksort.h (oracle/ref_shim.cpp, ref_blk_*)."""
+
+    def __init__(self, side):
+        self.name = side.name
+        lib = side.lib
+        self._enc, self._dec = (lib.bso_encode, lib.bso_decode) if isinstance(side, Oracle) else (lib.ref_blk_encode,
+                                                                                                  lib.ref_blk_decode)
+        for fn in (self._enc, self._dec):
+            fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        self._enc.restype = None
+        self._dec.restype = C.c_int if isinstance(side, Oracle) else None
+        if isinstance(side, Oracle):
+            lib.bso_block_is_periodic.restype = C.c_int
+            lib.bso_block_is_periodic.argtypes = [C.c_void_p]
+            self._periodic = lib.bso_block_is_periodic
+
+    def encode(self, src, threads: int = 1) -> np.ndarray:
+        src = _u8(src)
+        dst = np.zeros(max(blk_encode_bound(src.size), 1), dtype=np.uint8)
+        self._enc(src.size, dst.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), threads)
+        return dst[:blk_encode_bound(src.size)]
+
+    def decode(self, coded, threads: int = 1) -> np.ndarray:
+        coded = _u8(coded)
+        dst = np.zeros(max(blk_decoded_size(coded.size), 1), dtype=np.uint8)
+        rc = self._dec(coded.size, dst.ctypes.data_as(C.c_void_p), coded.ctypes.data_as(C.c_void_p), threads)
+        if rc not in (None, 0):
+            raise RuntimeError(f"{self.name}: block-sort decode failed")
+        return dst[:blk_decoded_size(coded.size)]
+
+    def periodic_blocks(self, src) -> list:
+        """Indices of the full blocks of ``src`` that have a period (some rotations are equal)."""
+        src = _u8(src)
+        return [b for b in range(src.size >> 15)
+                if self._periodic(src[b * BLK_BLOCK:(b + 1) * BLK_BLOCK].ctypes.data_as(C.c_void_p))]
+
+
 # --------------------------------------------------------------------- corpus --
 CANTERBURY = ["alice29.txt", "asyoulik.txt", "cp.html", "fields.c", "grammar.lsp", "kennedy.xls", "lcet10.txt",
               "plrabn12.txt", "ptt5", "sum", "xargs.1"]
