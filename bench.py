@@ -41,9 +41,14 @@ WORKLOADS = {
     # the sibling rANS coder of the reference (cppans.h), eight interleaved states
     "zipf1g-rans-word-64k": ("zipf", 1 << 30, 3, 65536),
     "mixed-rans-word-64k": ("mixed", 1 << 30, 3, 65536),
+    # the reference's block-sort transform (blksort.h): fixed 32 KiB blocks, step = forward + inverse
+    "zipf1g-blksort": ("zipf", 1 << 30, 4, 32768),
+    "mixed-blksort": ("mixed", 1 << 30, 4, 32768),
 }
+BLKSORT = 4
 KERNEL_NAMES = {0: ("k_enc_static", "k_dec_static_seg"), 1: ("k_enc_adaptive", "k_dec_adaptive"),
-                2: ("k_ans_enc_byte", "k_ans_dec_byte"), 3: ("k_ans_enc_word", "k_ans_dec_word")}
+                2: ("k_ans_enc_byte", "k_ans_dec_byte"), 3: ("k_ans_enc_word", "k_ans_dec_word"),
+                4: ("k_blk_fwd", "k_blk_inv")}
 METRIC = "roundtrip_GBps"
 UNIT = "GB/s"
 
@@ -69,7 +74,7 @@ def config_of(args, world):
     return {
         "workload": args.workload,
         "generator": f"cpprcoder_b200.synth.{gen}",
-        "coder": {0: "static", 1: "adaptive", 2: "rans-byte", 3: "rans-word"}[mode],
+        "coder": {0: "static", 1: "adaptive", 2: "rans-byte", 3: "rans-word", 4: "blksort (transform, no coder)"}[mode],
         "block_size": block,
         "bytes_per_gpu": nbytes,
         "global_bytes": nbytes * world,
@@ -146,6 +151,16 @@ def cpu_coder():
 
 
 def cpu_roundtrip(coder, offsets_of, data, mode, block, threads):
+    if mode == BLKSORT:  # blksort::BlkSort::encode / ::decode, blocks spread over `threads` BlkSort objects
+        from _oracle import BlkSort
+        bs = BlkSort(coder)
+        t0 = time.perf_counter()
+        coded = bs.encode(data, threads=threads)
+        t1 = time.perf_counter()
+        back = bs.decode(coded, threads=threads)
+        t2 = time.perf_counter()
+        assert back.tobytes() == data.tobytes(), "CPU baseline failed to round-trip"
+        return t1 - t0, t2 - t1, int(coded.size)
     t0 = time.perf_counter()
     pays = coder.encode_blocks(mode, data, block, threads=threads)
     t1 = time.perf_counter()
@@ -256,7 +271,8 @@ def run_ours(args):
     n = data.size
     ctx = api.Context(local)
     src = torch.from_numpy(data).to(dev)
-    enc = torch.empty(api.bound(mode, n, block), dtype=torch.uint8, device=dev)
+    bound = api.blk_encode_bound(n) if mode == BLKSORT else api.bound(mode, n, block)
+    enc = torch.empty(bound, dtype=torch.uint8, device=dev)
     dec = torch.empty(n, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -270,7 +286,12 @@ def run_ours(args):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timers is not None else None
         if ev:
             ev[0].record()
-        if world == 1:
+        if mode == BLKSORT:  # sizes are a function of n: the shards need no exchange at all
+            state["used"] = ctx.blk_encode_device(src, enc).numel()
+            if ev:
+                ev[1].record()
+            ctx.blk_decode_device(enc, state["used"], dec)
+        elif world == 1:
             _, used = ctx.encode_device(mode, src, enc, block)
             state["used"] = used
             if ev:
@@ -328,11 +349,15 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         h_src = torch.from_numpy(data).pin_memory()
-        h_enc = torch.empty(api.bound(mode, n, block), dtype=torch.uint8).pin_memory()
+        h_enc = torch.empty(bound, dtype=torch.uint8).pin_memory()
         h_dec = torch.empty(n, dtype=torch.uint8).pin_memory()
         a_src, a_enc, a_dec = h_src.numpy(), h_enc.numpy(), h_dec.numpy()
 
         def step_host():
+            if mode == BLKSORT:
+                out = ctx.blk_encode(a_src, dst=a_enc)                 # H2D n, kernels, D2H coded
+                ctx.blk_decode(out, dst=a_dec)                         # H2D coded, kernels, D2H n
+                return out.size
             out = ctx.encode(mode, a_src, block, dst=a_enc)           # H2D n, kernels, D2H container
             if world > 1:  # the stitched index needs every rank's sizes: the same small collective
                 info = container.parse(out)
@@ -356,7 +381,8 @@ def run_ours(args):
         wall = float(tw.item())
         e2e = {"value": n_total * args.steps / wall / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n + used_host),
                "d2h_bytes_per_step": int(used_host + n), "ms_per_step": 1e3 * wall / args.steps,
-               "api": "b2rc_encode + b2rc_decode (host pointers, pinned)"}
+               "api": ("b2rc_blk_encode + b2rc_blk_decode" if mode == BLKSORT else "b2rc_encode + b2rc_decode") +
+                      " (host pointers, pinned)"}
 
     if rank == 0:
         peaks = {}
@@ -369,10 +395,12 @@ def run_ours(args):
         kavg = {k: float(np.mean(v)) for k, v in ksum.items()}
         algo = {"histogram": n + (512 if mode == 0 else 1032) * (blk_hi - blk_lo), "encode": n + comp_bytes,
                 "scan": 12 * (blk_hi - blk_lo),
-                "compact": 2 * comp_bytes, "decode": comp_bytes + n}
+                "compact": 2 * comp_bytes, "decode": comp_bytes + n,
+                "blk_forward": n + comp_bytes, "blk_inverse": comp_bytes + n}
         kernels = {k: {"ms": ms, "algorithmic_bytes": algo[k], "GBps": algo[k] / ms / 1e6, "hbm_frac": algo[k] / ms / 1e6 / peak}
                    for k, ms in kavg.items() if k in algo and ms > 0}
-        dom = max((k for k in kernels if k in ("encode", "decode")), key=lambda k: kernels[k]["ms"]) if kernels else None
+        fwd_k, inv_k = ("blk_forward", "blk_inverse") if mode == BLKSORT else ("encode", "decode")
+        dom = max((k for k in kernels if k in (fwd_k, inv_k)), key=lambda k: kernels[k]["ms"]) if kernels else None
         traffic = None
         try:  # per-launch DRAM bytes from the committed ncu capture, when there is one for this kernel
             tj = json.loads((ROOT / "profiles" / "dram_traffic.json").read_text())
@@ -381,11 +409,13 @@ def run_ours(args):
             pass
         roofline = None
         if dom:
-            roofline = {"kernel": KERNEL_NAMES[mode][0 if dom == "encode" else 1],
+            roofline = {"kernel": KERNEL_NAMES[mode][0 if dom == fwd_k else 1],
                         "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                         "frac": kernels[dom]["hbm_frac"], "traffic": traffic, "peak_source": peak_src,
-                        "note": "integer-pipe / latency bound coder kernel (serial chains, ~100 instructions per "
-                                "symbol); HBM fraction shown for context, issue utilisation is in profiles/"}
+                        "note": ("shared-memory bound sort kernel (one 32 KiB block per CTA, every pass a gather and a "
+                                 "scatter through shared memory); HBM fraction shown for context") if mode == BLKSORT else
+                                ("integer-pipe / latency bound coder kernel (serial chains, ~100 instructions per "
+                                 "symbol); HBM fraction shown for context, issue utilisation is in profiles/")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg, "clocks": clocks,

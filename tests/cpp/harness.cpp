@@ -6,12 +6,16 @@
 //
 //   harness <file>...            static + adaptive round trip of every file
 //   harness --ans <file>...      rANS byte + word round trip (run_ans / run_ans_simd, test/main.cpp:367-545)
+//   harness --blk <file>...      block sort alone, and block sort in front of the static coder (run_blksort,
+//                                run_zlib_blk with this repository's coder where zlib stood, test/main.cpp:791-1002)
 //   harness --selftest           the 127-nibble static test and the chunked adaptive API
 #include "../../cpprcoder_b200/include/cpprcoder_b200.h"
 #include "../../cpprcoder_b200/include/cppans_b200.h"
+#include "../../cpprcoder_b200/include/blksort_b200.h"
 
 #include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <random>
 #include <string>
@@ -223,6 +227,67 @@ bool run_ans(const char* filepath, const std::vector<cpprcoder::u8>& src, bool s
 }
 }  // namespace
 
+// run_blksort (test/main.cpp:791-833): the transform and its inverse, ratio = size / encodeBound
+bool run_blksort(const char* filepath, const std::vector<cpprcoder::u8>& src)
+{
+    const uint32_t size = static_cast<uint32_t>(src.size());
+    blksort::BlkSort blk;
+    const uint32_t encoded_size = blksort::BlkSort::encodeBound(size);
+    std::vector<uint8_t> encoded(encoded_size + 1), decoded(size + 1);
+    double t = now();
+    blk.encode(size, encoded.data(), src.data());
+    const double deflateTime = now() - t;
+    if(!blk.ok()) {
+        printf("%s: block sort failed (%s)\n", filepath, b2rc_strerror(blk.status()));
+        return false;
+    }
+    t = now();
+    blk.decode(encoded_size, decoded.data(), encoded.data());
+    const double inflateTime = now() - t;
+    if(!blk.ok() || 0 != memcmp(decoded.data(), src.data(), size)) {
+        printf("%s: block sort round trip failed\n", filepath);
+        return false;
+    }
+    print(filepath, encoded_size ? static_cast<double>(size) / encoded_size : 1.0, size / deflateTime / (1024.0 * 1024.0),
+          size / inflateTime / (1024.0 * 1024.0));
+    return true;
+}
+
+// run_zlib_blk (test/main.cpp:944-1002) with the static range coder in the place of zlib:
+// block sort -> encode, decode -> inverse block sort.
+bool run_rc_blk(const char* filepath, const std::vector<cpprcoder::u8>& src)
+{
+    const uint32_t size = static_cast<uint32_t>(src.size());
+    blksort::BlkSort blk;
+    const uint32_t encoded_size = blksort::BlkSort::encodeBound(size);
+    std::vector<uint8_t> encoded(encoded_size + 1), decoded(size + 1);
+    cpprcoder::MemoryStream encstream(size);
+    cpprcoder::MemoryStream decstream(size);
+    cpprcoder::RangeEncoder<> coder;
+    double t = now();
+    blk.encode(size, encoded.data(), src.data());
+    if(!blk.ok() || !coder.encode(encstream, encoded_size, encoded.data())) {
+        printf("%s: block sort + encode failed\n", filepath);
+        return false;
+    }
+    const double deflateTime = now() - t;
+    t = now();
+    if(!coder.decode(decstream, static_cast<cpprcoder::u32>(encstream.size()), encstream.get()) ||
+       decstream.size() != static_cast<cpprcoder::s32>(encoded_size)) {
+        printf("%s: decode behind the block sort failed\n", filepath);
+        return false;
+    }
+    blk.decode(encoded_size, decoded.data(), &decstream[0]);
+    const double inflateTime = now() - t;
+    if(!blk.ok() || 0 != memcmp(decoded.data(), src.data(), size)) {
+        printf("%s: block sort + coder round trip failed\n", filepath);
+        return false;
+    }
+    print(filepath, static_cast<double>(size) / encstream.size(), size / deflateTime / (1024.0 * 1024.0),
+          size / inflateTime / (1024.0 * 1024.0));
+    return true;
+}
+
 int main(int argc, char** argv)
 {
     if(argc >= 2 && std::string(argv[1]) == "--selftest") {
@@ -233,7 +298,8 @@ int main(int argc, char** argv)
     }
     int bad = 0;
     const bool ans = argc >= 2 && std::string(argv[1]) == "--ans";
-    for(int i = ans ? 2 : 1; i < argc; ++i) {
+    const bool blk = argc >= 2 && std::string(argv[1]) == "--blk";
+    for(int i = (ans || blk) ? 2 : 1; i < argc; ++i) {
         std::ifstream file(argv[i], std::ios::binary);
         if(!file.is_open()) {
             printf("cannot open %s\n", argv[i]);
@@ -241,6 +307,11 @@ int main(int argc, char** argv)
             continue;
         }
         std::vector<cpprcoder::u8> src((std::istreambuf_iterator<char>(file)), std::istreambuf_iterator<char>());
+        if(blk) {
+            bad += run_blksort(argv[i], src) ? 0 : 1;
+            bad += run_rc_blk(argv[i], src) ? 0 : 1;
+            continue;
+        }
         if(ans) {
             bad += run_ans(argv[i], src, false) ? 0 : 1;
             bad += run_ans(argv[i], src, true) ? 0 : 1;

@@ -69,6 +69,22 @@ def test_rans_rows_on_gpu(harness, tmp_path):
 
 
 @pytest.mark.gpu
+def test_blksort_rows_on_gpu(harness, tmp_path, golden):
+    # blksort::BlkSort through the drop-in header: alone (ratio = size / encodeBound) and in front of the static coder
+    with tarfile.open(ROOT / "tests" / "golden" / "cantrbry.tar.bz2", "r:bz2") as tf:
+        tf.extractall(tmp_path, filter="data")
+    files = sorted(str(p) for p in (tmp_path / "cantrbry").iterdir())
+    r = subprocess.run([str(harness), "--blk"] + files, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [line.split("|") for line in r.stdout.splitlines() if line.startswith("|")]
+    assert len(rows) == 2 * len(files)
+    for alone, coded in zip(rows[0::2], rows[1::2]):
+        n = golden["canterbury"][Path(alone[1]).name]["bytes"]
+        assert abs(float(alone[2]) - n / ((n >> 15) * 32770 + n % 32768)) < 1e-5
+        assert float(coded[2]) > 0.9
+
+
+@pytest.mark.gpu
 def test_file_cli_round_trip(tmp_path):
     import subprocess
     import sys
