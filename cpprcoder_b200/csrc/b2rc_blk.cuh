@@ -18,9 +18,9 @@
 // repeat, 4-9 rounds on text) or at h = 32 768 (a block with a period: equal rotations have equal last
 // bytes, the column does not depend on the tie order; the row number is fixed by B3).
 // The stable pass is warp-chunked: warp w owns rows [1024 w, 1024 w + 1024) of the input order, counts
-// them per digit (match.any elects one lane per distinct digit: no atomics), a CTA scan in (digit, warp)
-// order gives each warp its first slot per digit, and the warp then places its rows 32 at a time, rank
-// within the 32 from the same match mask.
+// them per digit (ballots find the lanes with equal digits, the first of them adds the group: no atomics)
+// and remembers each row's rank within the warp, a CTA scan in (digit, warp) order gives each warp its
+// first slot per digit, and every row is then stored at slot + rank.
 //
 // Inverse: the walk is a linked list through a permutation; pointer doubling (J <- J o J) gives the
 // 2^k-th successor of every row, so after round k the first 2^(k+1) positions of the walk are known:
@@ -51,10 +51,15 @@ __device__ __forceinline__ u32 lanemask_lt()
     return m;
 }
 
-// One stable counting pass over the 32 768 rows of a block on an 8-bit digit.  `elem(i)` is the row at
-// place i of the input order, `digit(e)` its digit; rows land in `dst` ordered by digit, input order kept
-// within a digit.  cnt: u16[32 warps][256]; misc: u32[64].  Ends with a CTA barrier.
-template <class Elem, class Digit>
+// One stable counting pass over the 32 768 rows of a block on a BITS-bit digit (BITS <= 8).  `elem(i)` is
+// the row at place i of the input order, `digit(e)` its digit; rows land in `dst` ordered by digit, input
+// order kept within a digit.  cnt: u16[32 warps][256]; misc: u32[64].  Ends with a CTA barrier.
+// Warp w owns places [1024 w, 1024 w + 1024).  Counting walks them 32 at a time: the lanes that hold the
+// same digit find each other with one ballot per digit bit (match.any costs ~50 cycles of the ADU pipe on
+// sm_100 and was 85 % of the first version of this kernel), the first of them adds the group to the warp's
+// counter, and every lane keeps (digit, rank among the warp's rows of that digit) in registers -- so the
+// placing phase after the CTA scan is one counter read and one store per row, no warp traffic at all.
+template <u32 BITS, class Elem, class Digit>
 __device__ __forceinline__ void blk_pass(Elem elem, Digit digit, u16* dst, u16* cnt, u32* misc)
 {
     const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
@@ -66,14 +71,35 @@ __device__ __forceinline__ void blk_pass(Elem elem, Digit digit, u16* dst, u16* 
     __syncthreads();
     u16* mine = cnt + warp * 256u;
     const u32 i0 = warp * 1024u + lane;
-#pragma unroll 4
+    const u32 lt = lanemask_lt();
+    u32 dig[8];   // four 8-bit digits per word
+    u32 rnk[11];  // three 10-bit ranks per word
+#pragma unroll
+    for(u32 k = 0; k < 8u; ++k) {
+        dig[k] = 0u;
+    }
+#pragma unroll
+    for(u32 k = 0; k < 11u; ++k) {
+        rnk[k] = 0u;
+    }
+#pragma unroll
     for(u32 r = 0; r < 32u; ++r) {
-        const u32 e = elem(i0 + r * 32u);
-        const u32 d = digit(e);
-        const u32 m = __match_any_sync(FULL, d);
-        if(lane == (u32)__ffs((int)m) - 1u) {
-            mine[d] = (u16)(mine[d] + __popc(m));
+        const u32 d = digit(elem(i0 + r * 32u));
+        u32 peers = FULL;
+#pragma unroll
+        for(u32 b = 0; b < BITS; ++b) {
+            const u32 bit = (d >> b) & 1u;
+            peers &= __ballot_sync(FULL, bit) ^ (bit - 1u);
         }
+        const u32 leader = (u32)__ffs((int)peers) - 1u;
+        u32 before = 0;
+        if(lane == leader) {
+            before = mine[d];
+            mine[d] = (u16)(before + __popc(peers));
+        }
+        before = __shfl_sync(FULL, before, leader) + __popc(peers & lt);
+        dig[r >> 2] |= d << (8u * (r & 3u));
+        rnk[r / 3u] |= before << (10u * (r % 3u));
         __syncwarp();
     }
     __syncthreads();
@@ -119,45 +145,36 @@ __device__ __forceinline__ void blk_pass(Elem elem, Digit digit, u16* dst, u16* 
         }
     }
     __syncthreads();
-    const u32 lt = lanemask_lt();
-#pragma unroll 4
+#pragma unroll
     for(u32 r = 0; r < 32u; ++r) {
-        const u32 e = elem(i0 + r * 32u);
-        const u32 d = digit(e);
-        const u32 m = __match_any_sync(FULL, d);
-        const u32 leader = (u32)__ffs((int)m) - 1u;
-        u32 first = 0;
-        if(lane == leader) {
-            first = mine[d];
-            mine[d] = (u16)(first + __popc(m));
-        }
-        first = __shfl_sync(FULL, first, leader);
-        dst[first + __popc(m & lt)] = (u16)e;
-        __syncwarp();
+        const u32 d = (dig[r >> 2] >> (8u * (r & 3u))) & 0xFFu;
+        const u32 at = (u32)mine[d] + ((rnk[r / 3u] >> (10u * (r % 3u))) & 0x3FFu);
+        dst[at] = (u16)elem(i0 + r * 32u);
     }
     __syncthreads();
 }
 
 // New ranks after a sort: rank = place of the first row of the run of rows that do not differ (bucket
-// head).  `differs(e, ep)` compares a row with its predecessor in `sa` under the order just established;
-// it may read rk (or whatever lives there): nothing is written to rk before every flag is known.
+// head).  `keys(e)` gives the pair a row is compared by under the order just established, packed into one
+// word; it may read rk (or whatever lives there): nothing is written to rk before every flag is known.
+// A row's predecessor is in the lane below, so its keys arrive by shuffle instead of two more gathers.
 // fbits: u32[1024]; misc: u32[128], entries 64.. used here.  Returns the number of distinct ranks.
-template <class Differs>
-__device__ __forceinline__ u32 blk_rerank(const u16* sa, u16* rk, u32* fbits, u32* misc, Differs differs)
+template <class Keys>
+__device__ __forceinline__ u32 blk_rerank(const u16* sa, u16* rk, u32* fbits, u32* misc, Keys keys)
 {
     const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
     const u32 base = warp * 1024u;
     u32 last = 0, heads = 0;
-    u32 carry_row = warp ? sa[base - 1u] : 0u;
-#pragma unroll 4
+    u32 carry_key = warp ? keys((u32)sa[base - 1u]) : 0u;
+#pragma unroll 8
     for(u32 r = 0; r < 32u; ++r) {
         const u32 i = base + r * 32u + lane;
-        const u32 e = sa[i];
-        u32 ep = __shfl_up_sync(FULL, e, 1);
+        const u32 key = keys((u32)sa[i]);
+        u32 prev = __shfl_up_sync(FULL, key, 1);
         if(lane == 0u) {
-            ep = carry_row;
+            prev = carry_key;
         }
-        const bool df = (i == 0u) || differs(e, ep);
+        const bool df = (i == 0u) || key != prev;
         const u32 bits = __ballot_sync(FULL, df);
         if(lane == 0u) {
             fbits[warp * 32u + r] = bits;
@@ -166,7 +183,7 @@ __device__ __forceinline__ u32 blk_rerank(const u16* sa, u16* rk, u32* fbits, u3
             last = base + r * 32u + 31u - (u32)__clz((int)bits);
         }
         heads += (u32)__popc(bits);
-        carry_row = __shfl_sync(FULL, e, 31);
+        carry_key = __shfl_sync(FULL, key, 31);
     }
     if(lane == 0u) {
         misc[64u + warp] = last;
@@ -176,7 +193,7 @@ __device__ __forceinline__ u32 blk_rerank(const u16* sa, u16* rk, u32* fbits, u3
     u32 carry = __reduce_max_sync(FULL, lane < warp ? misc[64u + lane] : 0u);
     const u32 distinct = __reduce_add_sync(FULL, misc[96u + lane]);
     const u32 le = lanemask_lt() | (1u << lane);
-#pragma unroll 4
+#pragma unroll 8
     for(u32 r = 0; r < 32u; ++r) {
         const u32 bits = fbits[warp * 32u + r];
         const u32 i = base + r * 32u + lane;
@@ -221,18 +238,14 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_fwd(const u8* __restrict
     }
     __syncthreads();
     // rows by their first two bytes: least significant byte first
-    blk_pass([&](u32 i) { return i; }, [&](u32 e) { return (u32)s8[(e + 1u) & BLK_M]; }, tmp, cnt, misc);
-    blk_pass([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)s8[e]; }, sa, cnt, misc);
-    u32 distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e, u32 ep) {
-        return s8[e] != s8[ep] || s8[(e + 1u) & BLK_M] != s8[(ep + 1u) & BLK_M];
-    });
+    blk_pass<8>([&](u32 i) { return i; }, [&](u32 e) { return (u32)s8[(e + 1u) & BLK_M]; }, tmp, cnt, misc);
+    blk_pass<8>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)s8[e]; }, sa, cnt, misc);
+    u32 distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e) { return ((u32)s8[e] << 8) | (u32)s8[(e + 1u) & BLK_M]; });
     u32 h = 2, nrounds = 0;
     while(distinct < BLK_N && h < BLK_N) {
-        blk_pass([&](u32 i) { return ((u32)sa[i] - h) & BLK_M; }, [&](u32 e) { return (u32)rk[e] & 0xFFu; }, tmp, cnt, misc);
-        blk_pass([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)rk[e] >> 8; }, sa, cnt, misc);
-        distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e, u32 ep) {
-            return rk[e] != rk[ep] || rk[(e + h) & BLK_M] != rk[(ep + h) & BLK_M];
-        });
+        blk_pass<8>([&](u32 i) { return ((u32)sa[i] - h) & BLK_M; }, [&](u32 e) { return (u32)rk[e] & 0xFFu; }, tmp, cnt, misc);
+        blk_pass<7>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)rk[e] >> 8; }, sa, cnt, misc);
+        distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e) { return ((u32)rk[e] << 16) | (u32)rk[(e + h) & BLK_M]; });
         h <<= 1;
         ++nrounds;
     }
@@ -302,7 +315,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_inv(const u8* __restrict
     }
     __syncthreads();
     // counting_sort (blksort.h:379-402): next[k] = place in the column of the k-th smallest byte, stable
-    blk_pass([&](u32 i) { return i; }, [&](u32 e) { return (u32)col[e]; }, ja, jb, misc);
+    blk_pass<8>([&](u32 i) { return i; }, [&](u32 e) { return (u32)col[e]; }, ja, jb, misc);
     if(t == 0u) {
         walk[0] = ja[top];
     }
