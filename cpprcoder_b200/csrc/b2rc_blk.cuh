@@ -38,7 +38,8 @@ constexpr u32 BLK_THREADS = 1024u;
 
 // forward kernel, byte offsets in dynamic shared memory
 constexpr u32 BF_SA = 0u, BF_TMP = 65536u, BF_RK = 131072u, BF_CNT = 196608u, BF_FB = 212992u, BF_MISC = 217088u;
-constexpr u32 BLK_FWD_SMEM = BF_MISC + 512u;
+constexpr u32 BF_LB = BF_MISC + 512u;  // short rounds: two ballot arrays of 512 words
+constexpr u32 BLK_FWD_SMEM = BF_LB + 4096u;
 // inverse kernel: two jump tables, the walk, the column; the counters of the one counting pass sit in the
 // second jump table, which is not in use yet
 constexpr u32 BI_JA = 0u, BI_JB = 65536u, BI_P = 131072u, BI_L = 196608u, BI_MISC = 229376u;
@@ -49,6 +50,53 @@ __device__ __forceinline__ u32 lanemask_lt()
     u32 m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+}
+
+// Exclusive scan of the 32 x 256 per-warp digit counters in (digit, warp) order, in place: afterwards
+// cnt[w][d] is the first slot of warp w's rows with digit d.  Called by all threads between two barriers
+// of the caller; contains two of its own.
+__device__ __forceinline__ void blk_scan_counters(u16* cnt, u32* misc)
+{
+    const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    // 8 counters per thread
+    const u32 d = t >> 2, w0 = (t & 3u) * 8u;
+    u32 v[8], sum = 0;
+#pragma unroll
+    for(u32 k = 0; k < 8u; ++k) {
+        v[k] = cnt[(w0 + k) * 256u + d];
+        sum += v[k];
+    }
+    u32 incl = sum;
+#pragma unroll
+    for(u32 o = 1; o < 32u; o <<= 1) {
+        const u32 up = __shfl_up_sync(FULL, incl, o);
+        if(lane >= o) {
+            incl += up;
+        }
+    }
+    if(lane == 31u) {
+        misc[warp] = incl;
+    }
+    __syncthreads();
+    if(warp == 0u) {
+        const u32 x = misc[lane];
+        u32 xi = x;
+#pragma unroll
+        for(u32 o = 1; o < 32u; o <<= 1) {
+            const u32 up = __shfl_up_sync(FULL, xi, o);
+            if(lane >= o) {
+                xi += up;
+            }
+        }
+        misc[32u + lane] = xi - x;
+    }
+    __syncthreads();
+    u32 run = misc[32u + warp] + incl - sum;
+#pragma unroll
+    for(u32 k = 0; k < 8u; ++k) {
+        cnt[(w0 + k) * 256u + d] = (u16)run;
+        run += v[k];
+    }
 }
 
 // One stable counting pass over the 32 768 rows of a block on a BITS-bit digit (BITS <= 8).  `elem(i)` is
@@ -103,47 +151,7 @@ __device__ __forceinline__ void blk_pass(Elem elem, Digit digit, u16* dst, u16* 
         __syncwarp();
     }
     __syncthreads();
-    {
-        // exclusive scan of the 8192 counters in (digit, warp) order: 8 counters per thread
-        const u32 d = t >> 2, w0 = (t & 3u) * 8u;
-        u32 v[8], sum = 0;
-#pragma unroll
-        for(u32 k = 0; k < 8u; ++k) {
-            v[k] = cnt[(w0 + k) * 256u + d];
-            sum += v[k];
-        }
-        u32 incl = sum;
-#pragma unroll
-        for(u32 o = 1; o < 32u; o <<= 1) {
-            const u32 up = __shfl_up_sync(FULL, incl, o);
-            if(lane >= o) {
-                incl += up;
-            }
-        }
-        if(lane == 31u) {
-            misc[warp] = incl;
-        }
-        __syncthreads();
-        if(warp == 0u) {
-            const u32 x = misc[lane];
-            u32 xi = x;
-#pragma unroll
-            for(u32 o = 1; o < 32u; o <<= 1) {
-                const u32 up = __shfl_up_sync(FULL, xi, o);
-                if(lane >= o) {
-                    xi += up;
-                }
-            }
-            misc[32u + lane] = xi - x;
-        }
-        __syncthreads();
-        u32 run = misc[32u + warp] + incl - sum;
-#pragma unroll
-        for(u32 k = 0; k < 8u; ++k) {
-            cnt[(w0 + k) * 256u + d] = (u16)run;
-            run += v[k];
-        }
-    }
+    blk_scan_counters(cnt, misc);
     __syncthreads();
 #pragma unroll
     for(u32 r = 0; r < 32u; ++r) {
@@ -208,6 +216,219 @@ __device__ __forceinline__ u32 blk_rerank(const u16* sa, u16* rk, u32* fbits, u3
     return distinct;
 }
 
+// ------------------------------------------------------------ short rounds --
+// Once most rows are alone in their bucket a round only has to deal with the others ("active" rows: their
+// bucket holds two rows or more).  Such a round lists the active rows by their second half (the same walk
+// as before, filtered), sorts the list by bucket with the same two stable passes -- over n <= 16 384
+// entries instead of 32 768 -- and puts every row at  bucket head + its index within the bucket's part of
+// the list;  rows that are alone never move.  The list and the first pass's output share tmp (two halves).
+
+// Rows in buckets of two or more, from the head flags: a row is alone when its place and the next are heads.
+__device__ __forceinline__ u32 blk_count_active(const u32* fbits, u32* misc)
+{
+    const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const u32 w = fbits[t];
+    const u32 nx = t + 1u < BLK_THREADS ? fbits[t + 1u] : 1u;  // the place behind the last row counts as a head
+    u32 alone = (u32)__popc(w & ((w >> 1) | (nx << 31)));
+    alone = __reduce_add_sync(FULL, alone);
+    if(lane == 0u) {
+        misc[warp] = alone;
+    }
+    __syncthreads();
+    const u32 total = __reduce_add_sync(FULL, misc[lane]);
+    __syncthreads();
+    return BLK_N - total;
+}
+
+// The active rows in the order of their second half -> list[0 .. n).  Returns n.
+__device__ __forceinline__ u32 blk_list_active(const u16* sa, const u16* rk, const u32* fbits, u32 h, u16* list, u32* misc)
+{
+    const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const u32 base = warp * 1024u + lane;
+    u32 mine = 0;  // bit r: my row of step r is active
+#pragma unroll 8
+    for(u32 r = 0; r < 32u; ++r) {
+        const u32 q = ((u32)sa[base + r * 32u] - h) & BLK_M;
+        const u32 nx = (u32)rk[q] + 1u;  // the place behind the head of q's bucket: a head itself when q is alone
+        const u32 word = nx < BLK_N ? fbits[nx >> 5] : 0xFFFFFFFFu;
+        mine |= (((word >> (nx & 31u)) & 1u) ^ 1u) << r;
+    }
+    u32 total = __reduce_add_sync(FULL, (u32)__popc(mine));
+    if(lane == 0u) {
+        misc[warp] = total;
+    }
+    __syncthreads();
+    const u32 other = misc[lane];
+    u32 at = __reduce_add_sync(FULL, lane < warp ? other : 0u);
+    const u32 n = __reduce_add_sync(FULL, other);
+    const u32 lt = lanemask_lt();
+#pragma unroll 8
+    for(u32 r = 0; r < 32u; ++r) {
+        const bool act = (mine >> r) & 1u;
+        const u32 bits = __ballot_sync(FULL, act);
+        if(act) {
+            list[at + (u32)__popc(bits & lt)] = (u16)(((u32)sa[base + r * 32u] - h) & BLK_M);
+        }
+        at += (u32)__popc(bits);
+    }
+    __syncthreads();
+    return n;
+}
+
+// blk_pass over a list of n <= 16 384 rows: warp w owns entries [32 w steps, 32 (w + 1) steps), steps = ceil(n / 1024).
+template <u32 BITS, class Elem, class Digit>
+__device__ __forceinline__ void blk_pass_short(u32 n, Elem elem, Digit digit, u16* dst, u16* cnt, u32* misc)
+{
+    const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    u32* c32 = reinterpret_cast<u32*>(cnt);
+#pragma unroll
+    for(u32 k = 0; k < 4u; ++k) {
+        c32[t + k * BLK_THREADS] = 0u;
+    }
+    __syncthreads();
+    u16* mine = cnt + warp * 256u;
+    const u32 steps = (n + 1023u) >> 10;
+    const u32 j0 = warp * steps * 32u + lane;
+    const u32 lt = lanemask_lt();
+    u32 dig[4], rnk[6];
+#pragma unroll
+    for(u32 k = 0; k < 4u; ++k) {
+        dig[k] = 0u;
+    }
+#pragma unroll
+    for(u32 k = 0; k < 6u; ++k) {
+        rnk[k] = 0u;
+    }
+#pragma unroll
+    for(u32 r = 0; r < 16u; ++r) {
+        if(r < steps) {
+            const u32 j = j0 + r * 32u;
+            const bool valid = j < n;
+            const u32 d = valid ? digit(elem(j)) : 0u;
+            u32 peers = __ballot_sync(FULL, valid);
+#pragma unroll
+            for(u32 b = 0; b < BITS; ++b) {
+                const u32 bit = (d >> b) & 1u;
+                peers &= __ballot_sync(FULL, bit) ^ (bit - 1u);
+            }
+            const u32 leader = valid ? (u32)__ffs((int)peers) - 1u : 0u;
+            u32 before = 0;
+            if(valid && lane == leader) {
+                before = mine[d];
+                mine[d] = (u16)(before + __popc(peers));
+            }
+            before = __shfl_sync(FULL, before, leader) + __popc(peers & lt);
+            if(valid) {
+                dig[r >> 2] |= d << (8u * (r & 3u));
+                rnk[r / 3u] |= before << (10u * (r % 3u));
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    blk_scan_counters(cnt, misc);
+    __syncthreads();
+#pragma unroll
+    for(u32 r = 0; r < 16u; ++r) {
+        const u32 j = j0 + r * 32u;
+        if(r < steps && j < n) {
+            const u32 d = (dig[r >> 2] >> (8u * (r & 3u))) & 0xFFu;
+            const u32 at = (u32)mine[d] + ((rnk[r / 3u] >> (10u * (r % 3u))) & 0x3FFu);
+            dst[at] = (u16)elem(j);
+        }
+    }
+    __syncthreads();
+}
+
+// The sorted list (by bucket, then by second half) goes home: row j of the list lands at
+//   head of its bucket + (j - first j of that bucket),
+// its new rank is the place of the first row of its run of equal (bucket, second half) pairs, and every
+// such run that does not start a bucket sets a new head flag.  lb / lg: 512 words each (ballots of the
+// list: bucket starts, run starts).  Returns the number of new heads.
+__device__ __forceinline__ u32 blk_place_short(u32 n, const u16* list, u16* sa, u16* rk, u32* fbits, u32 h, u32* lb, u32* lg, u32* misc)
+{
+    const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const u32 steps = (n + 1023u) >> 10;
+    const u32 jw = warp * steps * 32u;
+    auto key_of = [&](u32 q) { return ((u32)rk[q] << 16) | (u32)rk[(q + h) & BLK_M]; };
+    u32 last_b = 0, last_g = 0, fresh = 0;
+    u32 carry_key = (jw > 0u && jw - 1u < n) ? key_of((u32)list[jw - 1u]) : 0u;
+#pragma unroll 4
+    for(u32 r = 0; r < steps; ++r) {
+        const u32 j = jw + r * 32u + lane;
+        const bool valid = j < n;
+        const u32 key = valid ? key_of((u32)list[j]) : 0u;
+        u32 prev = __shfl_up_sync(FULL, key, 1);
+        if(lane == 0u) {
+            prev = carry_key;
+        }
+        const bool b = valid && (j == 0u || (key >> 16) != (prev >> 16));
+        const bool g = valid && (b || key != prev);
+        const u32 bb = __ballot_sync(FULL, b), gb = __ballot_sync(FULL, g);
+        if(lane == 0u) {
+            lb[warp * steps + r] = bb;
+            lg[warp * steps + r] = gb;
+        }
+        if(bb) {
+            last_b = jw + r * 32u + 31u - (u32)__clz((int)bb);
+        }
+        if(gb) {
+            last_g = jw + r * 32u + 31u - (u32)__clz((int)gb);
+        }
+        fresh += (u32)__popc(gb & ~bb);
+        carry_key = __shfl_sync(FULL, key, 31);
+    }
+    if(lane == 0u) {
+        misc[64u + warp] = last_b;
+        misc[96u + warp] = last_g;
+        misc[warp] = fresh;
+    }
+    __syncthreads();
+    u32 cb = __reduce_max_sync(FULL, lane < warp ? misc[64u + lane] : 0u);
+    u32 cg = __reduce_max_sync(FULL, lane < warp ? misc[96u + lane] : 0u);
+    const u32 total_fresh = __reduce_add_sync(FULL, misc[lane]);
+    const u32 le = lanemask_lt() | (1u << lane);
+    u32 out[16];  // place | new rank << 16
+#pragma unroll
+    for(u32 r = 0; r < 16u; ++r) {
+        out[r] = 0u;
+        if(r < steps) {
+            const u32 bb = lb[warp * steps + r], gb = lg[warp * steps + r];
+            const u32 j = jw + r * 32u + lane;
+            const u32 mb = bb & le, mg = gb & le;
+            const u32 jf = mb ? jw + r * 32u + 31u - (u32)__clz((int)mb) : cb;
+            const u32 jg = mg ? jw + r * 32u + 31u - (u32)__clz((int)mg) : cg;
+            if(j < n) {
+                const u32 head = rk[list[j]];
+                out[r] = (head + (j - jf)) | ((head + (jg - jf)) << 16);
+            }
+            if(bb) {
+                cb = jw + r * 32u + 31u - (u32)__clz((int)bb);
+            }
+            if(gb) {
+                cg = jw + r * 32u + 31u - (u32)__clz((int)gb);
+            }
+        }
+    }
+    __syncthreads();  // every rank has been read
+#pragma unroll
+    for(u32 r = 0; r < 16u; ++r) {
+        const u32 j = jw + r * 32u + lane;
+        if(r < steps && j < n) {
+            const u32 q = list[j];
+            const u32 place = out[r] & 0xFFFFu;
+            sa[place] = (u16)q;
+            rk[q] = (u16)(out[r] >> 16);
+            const u32 bb = lb[warp * steps + r], gb = lg[warp * steps + r];
+            if(((gb & ~bb) >> lane) & 1u) {
+                atomicOr(&fbits[place >> 5], 1u << (place & 31u));
+            }
+        }
+    }
+    __syncthreads();
+    return total_fresh;
+}
+
 // ------------------------------------------------------------------- B1 forward --
 // src: nblocks x 32 768 bytes (16-byte aligned); dst: nblocks x 32 770 bytes (2-byte aligned).
 // rounds (one u32 per block): how many doubling rounds the block took; bit 31 = the block has a period
@@ -242,10 +463,20 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_fwd(const u8* __restrict
     blk_pass<8>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)s8[e]; }, sa, cnt, misc);
     u32 distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e) { return ((u32)s8[e] << 8) | (u32)s8[(e + 1u) & BLK_M]; });
     u32 h = 2, nrounds = 0;
+    u32* lb = reinterpret_cast<u32*>(blk_sm + BF_LB);
+    u16* half = tmp + BLK_N / 2u;
     while(distinct < BLK_N && h < BLK_N) {
-        blk_pass<8>([&](u32 i) { return ((u32)sa[i] - h) & BLK_M; }, [&](u32 e) { return (u32)rk[e] & 0xFFu; }, tmp, cnt, misc);
-        blk_pass<7>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)rk[e] >> 8; }, sa, cnt, misc);
-        distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e) { return ((u32)rk[e] << 16) | (u32)rk[(e + h) & BLK_M]; });
+        if(blk_count_active(fbits, misc) > BLK_N / 2u) {
+            blk_pass<8>([&](u32 i) { return ((u32)sa[i] - h) & BLK_M; }, [&](u32 e) { return (u32)rk[e] & 0xFFu; }, tmp, cnt, misc);
+            blk_pass<7>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)rk[e] >> 8; }, sa, cnt, misc);
+            distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e) { return ((u32)rk[e] << 16) | (u32)rk[(e + h) & BLK_M]; });
+        } else {
+            const u32 n = blk_list_active(sa, rk, fbits, h, tmp, misc);
+            blk_pass_short<8>(n, [&](u32 j) { return (u32)tmp[j]; }, [&](u32 e) { return (u32)rk[e] & 0xFFu; }, half, cnt, misc);
+            blk_pass_short<7>(n, [&](u32 j) { return (u32)half[j]; }, [&](u32 e) { return (u32)rk[e] >> 8; }, tmp, cnt, misc);
+            distinct += blk_place_short(n, tmp, sa, rk, fbits, h, lb, lb + 512u, misc);
+            nrounds += 0x100u;  // bits 8..15 of the rounds word: how many of the rounds were short ones
+        }
         h <<= 1;
         ++nrounds;
     }

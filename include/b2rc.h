@@ -192,7 +192,7 @@ int b2rc_blk_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint
 int b2rc_blk_encode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n);
 int b2rc_blk_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n);
 /* Doubling rounds the forward kernel took per block in the last b2rc_blk_encode_device call of
- * this context (bit 31: the block has a period); copies min(cap, blocks) words to host memory.
+ * this context (bit 31: the block has a period; bit 30: one repeated byte; bits 8..15: how many of the rounds were short ones); copies min(cap, blocks) words to host memory.
  * Measurement / tests only. */
 int b2rc_blk_rounds(b2rc_ctx* ctx, uint32_t* rounds, uint64_t cap, uint64_t* nblocks);
 

@@ -29,8 +29,10 @@ def main():
         f, i = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
         print(f"{gen} {n} B: forward {f:.2f} ms = {n / f / 1e6:.1f} GB/s, inverse {i:.2f} ms = {n / i / 1e6:.1f} GB/s")
     assert torch.equal(back, src)
-    r = ctx.blk_rounds() & 0x7FFFFFFF
-    print("doubling rounds per block:", dict(zip(*[x.tolist() for x in np.unique(r, return_counts=True)])))
+    r = ctx.blk_rounds()
+    total, short = r & 0xFF, (r >> 8) & 0xFF
+    print("doubling rounds per block (total, of which short):",
+          {(int(a), int(b)): int(c) for (a, b), c in zip(*np.unique(np.stack([total, short], 1), axis=0, return_counts=True))})
 
 
 if __name__ == "__main__":
