@@ -3,7 +3,9 @@ harness's row format.
 
     python -m cpprcoder_b200 encode [--adaptive | --coder static|adaptive|rans|rans-word] [--block N] IN OUT
     python -m cpprcoder_b200 decode IN OUT
-    python -m cpprcoder_b200 rows   [--block N] FILE...     # |file|ratio|enc MiB/s|dec MiB/s| per coder
+    python -m cpprcoder_b200 rows   [--block N] [--blk] FILE...   # |file|ratio|enc MiB/s|dec MiB/s| per coder
+    python -m cpprcoder_b200 blksort IN OUT                 # blksort::BlkSort::encode, the reference's byte format
+    python -m cpprcoder_b200 unblksort IN OUT               # blksort::BlkSort::decode
 
 `rows` prints what the reference's run_rangecoder / run_adaptive / run_ans / run_ans_simd print
 (test/main.cpp:104-107, :290-294, :367-395, :457-485): ratio = original / coded bytes, speeds in
@@ -44,11 +46,41 @@ def cmd_decode(a) -> int:
     return 0
 
 
+def cmd_blksort(a) -> int:
+    ctx = api.Context()
+    data = _read(a.input)
+    out = ctx.blk_decode(data) if a.cmd == "unblksort" else ctx.blk_encode(data)
+    Path(a.output).write_bytes(out.tobytes())
+    print(f"{a.input}: {data.size} -> {out.size} bytes")
+    return 0
+
+
+def _blk_rows(ctx, path, data, block) -> int:
+    """run_blksort and run_zlib_blk (test/main.cpp:791-1002) with the static coder where zlib stood."""
+    mib = data.size / (1024.0 * 1024.0)
+    t0 = time.perf_counter()
+    coded = ctx.blk_encode(data)
+    t1 = time.perf_counter()
+    back = ctx.blk_decode(coded)
+    t2 = time.perf_counter()
+    print("|%s|%f|%f|%f|" % (path, data.size / max(coded.size, 1), mib / (t1 - t0), mib / (t2 - t1)))
+    t0 = time.perf_counter()
+    enc = ctx.encode(api.MODE_STATIC, ctx.blk_encode(data), block)
+    t1 = time.perf_counter()
+    back2 = ctx.blk_decode(ctx.decode(enc))
+    t2 = time.perf_counter()
+    print("|%s|%f|%f|%f|" % (path, data.size / max(enc.size, 1), mib / (t1 - t0), mib / (t2 - t1)))
+    return int(back.tobytes() != data.tobytes()) + int(back2.tobytes() != data.tobytes())
+
+
 def cmd_rows(a) -> int:
     ctx = api.Context()
     bad = 0
     for path in a.files:
         data = _read(path)
+        if a.blk:
+            bad += _blk_rows(ctx, path, data, a.block)
+            continue
         for mode in ctx.supported_modes():
             t0 = time.perf_counter()
             enc = ctx.encode(mode, data, a.block)
@@ -79,8 +111,14 @@ def main(argv=None) -> int:
     d.set_defaults(fn=cmd_decode)
     r = sub.add_parser("rows")
     r.add_argument("--block", type=int, default=api.DEFAULT_BLOCK)
+    r.add_argument("--blk", action="store_true", help="block sort alone, and block sort in front of the static coder")
     r.add_argument("files", nargs="+")
     r.set_defaults(fn=cmd_rows)
+    for name in ("blksort", "unblksort"):
+        b = sub.add_parser(name)
+        b.add_argument("input")
+        b.add_argument("output")
+        b.set_defaults(fn=cmd_blksort)
     a = ap.parse_args(argv)
     return a.fn(a)
 

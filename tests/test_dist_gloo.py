@@ -73,3 +73,32 @@ def test_shard_of_covers_the_stream():
             spans = [rcdist.shard_of(n_total, block, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n_total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _blk_worker(rank, world, port, n_total, out_dir):
+    """Block sort over ranks: shards at 32 KiB block boundaries, no exchange on the data path (sizes are a
+    function of n); rank 0 gathers the pieces only to check them."""
+    from _oracle import BLK_BLOCK, BlkSort
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        data = synth.kennedy(n_total)
+        lo, hi, _, _ = rcdist.shard_of(n_total, BLK_BLOCK, rank, world)
+        piece = BlkSort(Oracle.get()).encode(data[lo:hi]) if hi > lo else np.zeros(0, np.uint8)
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(piece.tobytes(), parts, dst=0)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "blk.npy"), np.frombuffer(b"".join(parts), dtype=np.uint8))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total", [(2, 5 * 32768 + 999), (3, 4 * 32768), (2, 1000)])
+def test_block_sort_shards_concatenate(tmp_path, built, world, n_total):
+    from _oracle import BlkSort
+    port = _free_port()
+    mp.spawn(_blk_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "blk.npy")
+    want = BlkSort(Oracle.get()).encode(synth.kennedy(n_total))
+    assert np.array_equal(got, want), "shards cut at block boundaries must concatenate to the single-rank output"

@@ -98,3 +98,9 @@ def test_file_cli_round_trip(tmp_path):
         assert dec.read_bytes() == src.read_bytes()
     r = subprocess.run([sys.executable, "-m", "cpprcoder_b200", "rows", str(src)], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.count("|") == 20  # four coders, five bars per row
+    bs, back = tmp_path / "x.bs", tmp_path / "x.back"
+    subprocess.check_call([sys.executable, "-m", "cpprcoder_b200", "blksort", str(src), str(bs)], cwd=ROOT)
+    subprocess.check_call([sys.executable, "-m", "cpprcoder_b200", "unblksort", str(bs), str(back)], cwd=ROOT)
+    assert back.read_bytes() == src.read_bytes() and bs.stat().st_size == src.stat().st_size + 2 * (src.stat().st_size >> 15)
+    r = subprocess.run([sys.executable, "-m", "cpprcoder_b200", "rows", "--blk", str(src)], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.count("|") == 10
