@@ -31,8 +31,9 @@ class Info:
     nblocks: int
     offsets: np.ndarray  # uint64, nblocks + 1
     payload_base: int
-    seg_syms: int = 0                 # restart points of the static coder every so many symbols (0: none)
-    restart: np.ndarray | None = None  # uint32 [nblocks][records][3]: bytes shifted, encoder low, range
+    seg_syms: int = 0                 # restart points (static range coder, byte rANS) every so many symbols (0: none)
+    restart: np.ndarray | None = None  # uint32 [nblocks][records][3]: static: bytes shifted, encoder low, range;
+    #                                    byte rANS: coded bytes still ahead of the decoder, its state x, 0
 
     def payload(self, buf: np.ndarray, b: int) -> np.ndarray:
         lo = self.payload_base + int(self.offsets[b])
@@ -58,7 +59,7 @@ def parse(buf) -> Info:
     if magic != MAGIC or version != 1 or mode > 3 or not block_ok(block):
         raise ValueError("bad container header")
     seg_syms = (flags >> 8) * 64
-    if flags and ((flags & 0xFF) != 1 or mode != 0 or restart_records(block, seg_syms) == 0):
+    if flags and ((flags & 0xFF) != 1 or mode not in (0, 2) or restart_records(block, seg_syms) == 0):
         raise ValueError("bad container flags")
     if nblocks != nblocks_of(total, block) or HEADER + 8 * (nblocks + 1) > buf.size:
         raise ValueError("container index does not fit")

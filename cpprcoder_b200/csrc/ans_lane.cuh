@@ -153,6 +153,21 @@ RC_HD u32 ans_byte_dec_init(RcDec& d, u32 skip, Next& next)
     return rc_bswap(first);
 }
 
+// The window alone, for a decoder that starts inside the stream with a state it was given
+// (restart points): `skip` bytes of the first word precede the next coded byte.
+template <class Next>
+RC_HD void ans_byte_win_init(RcDec& d, u32 skip, Next& next)
+{
+    d.low = 0;
+    d.range = 0;
+    d.w_hi = next();
+    d.w_lo = next();
+    const u32 drop = skip * 8u;
+    d.w_hi = rc_funnel_l(d.w_lo, d.w_hi, drop);
+    d.w_lo <<= drop;
+    d.wbits = 64 - (s32)drop;
+}
+
 // advance (cppans.h:321-334): x = f * (x >> 14) + slot - start, then 0, 1 or 2 bytes in.
 // A valid stream never needs a third (x >= 2^9 after the update); a corrupt one may, and
 // then x stays below 2^23 -- the caller checks.  At most 16 bits per symbol: the window is

@@ -139,9 +139,13 @@ bool seg_ok(u32 block_size, u32 seg_syms)
     return seg_syms >= 64u && (seg_syms % 64u) == 0u && seg_syms < block_size;
 }
 // segment length a container of this mode / block size is written with by this context
+bool has_restart(int mode)
+{
+    return mode == B2RC_MODE_STATIC || mode == B2RC_MODE_RANS_BYTE;  // the two one-chain-per-block coders with a static model
+}
 u32 seg_for(const b2rc_ctx* ctx, int mode, u32 block_size)
 {
-    return (mode == B2RC_MODE_STATIC && seg_ok(block_size, ctx->seg_syms)) ? ctx->seg_syms : 0u;
+    return (has_restart(mode) && seg_ok(block_size, ctx->seg_syms)) ? ctx->seg_syms : 0u;
 }
 bool aligned16(const void* p)
 {
@@ -193,6 +197,7 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
     CK(cudaFuncSetAttribute(k_dec_static_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SEG_SMEM));
+    CK(cudaFuncSetAttribute(k_ans_dec_byte_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_DEC_BYTE_SEG_SMEM));
     CK(cudaFuncSetAttribute(k_blk_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_FWD_SMEM));
     CK(cudaFuncSetAttribute(k_blk_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_INV_SMEM));
     CK(cudaFuncSetAttribute(k_blk_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_TIES_SMEM));
@@ -310,7 +315,7 @@ uint64_t b2rc_bound(int mode, uint64_t n, uint32_t block_size)
     }
     const u64 last = n - (nb - 1) * block_size;
     // room for a restart table at the shortest segment length a context can be set to
-    const u64 table = mode == B2RC_MODE_STATIC
+    const u64 table = (mode == B2RC_MODE_STATIC || mode == B2RC_MODE_RANS_BYTE)
                           ? 4ull + nb * 12ull * b2rc_restart_records(block_size, B2RC_MIN_RESTART_SYMS)
                           : 0ull;
     return index_bytes(nb) + (nb - 1) * b2rc_slot_bytes_for(mode, block_size) + b2rc_slot_bytes_for(mode, (u32)last) +
@@ -544,9 +549,9 @@ int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, u
     if(h[0] != 0x43523242u || version != 1u || !mode_ok((int)md) || !block_ok(h[2])) {
         return B2RC_E_CORRUPT;
     }
-    if(h[3] != 0u) {  // a restart table: static coder only, a legal segment length, nothing else set
+    if(h[3] != 0u) {  // a restart table: static range coder or byte rANS, a legal segment length, nothing else set
         const u32 seg = (h[3] >> 8) * 64u;
-        if((h[3] & 0xFFu) != 1u || md != (u32)B2RC_MODE_STATIC || !seg_ok(h[2], seg)) {
+        if((h[3] & 0xFFu) != 1u || (md != (u32)B2RC_MODE_STATIC && md != (u32)B2RC_MODE_RANS_BYTE) || !seg_ok(h[2], seg)) {
             return B2RC_E_CORRUPT;
         }
     }
@@ -570,7 +575,7 @@ int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, u
 
 // ------------------------------------------------------------ rANS launches --
 static int ans_encode_blocks(b2rc_ctx* ctx, int mode, u32 block, const u8* d_src, u64 n, u8* d_slots, u64 stride,
-                             u32* d_sizes, int* d_err, cudaStream_t st)
+                             u32* d_sizes, u32* d_restart, u32 seg_syms, int* d_err, cudaStream_t st)
 {
     const u64 nb = b2rc_nblocks(n, block);
     if(nb == 0) {
@@ -605,8 +610,11 @@ static int ans_encode_blocks(b2rc_ctx* ctx, int mode, u32 block, const u8* d_src
     a.slot_stride = stride;
     a.sizes = d_sizes;
     a.err = d_err;
-    a.restart = nullptr;
-    a.seg_syms = 0;
+    a.restart = mode == B2RC_MODE_RANS_BYTE ? d_restart : nullptr;
+    a.seg_syms = a.restart ? seg_syms : 0u;
+    if(a.restart) {
+        CK(cudaMemsetAsync(d_restart, 0xFF, (size_t)(nb * b2rc_restart_records(block, seg_syms) * 12u), st));
+    }
     KernelTimer kt(ctx, B2RC_K_ENCODE, st);
     if(mode == B2RC_MODE_RANS_WORD) {
         k_ans_enc_word<<<(unsigned)((nb + 3) / 4), 32, 0, st>>>(a);
@@ -672,7 +680,7 @@ int b2rc_k_encode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
                            const uint16_t* d_freq16, uint8_t* d_slots, uint64_t slot_stride, uint32_t* d_sizes,
                            uint32_t* d_restart, uint32_t seg_syms, int* d_err, void* cuda_stream)
 {
-    if(d_restart && (mode != B2RC_MODE_STATIC || !seg_ok(block_size, seg_syms) || ((uintptr_t)d_restart & 3u))) {
+    if(d_restart && (!has_restart(mode) || !seg_ok(block_size, seg_syms) || ((uintptr_t)d_restart & 3u))) {
         return B2RC_E_ARG;
     }
     if(!ctx || !d_src || !d_slots || !d_sizes || !d_err || !mode_ok(mode) || !block_ok(block_size) ||
@@ -681,7 +689,7 @@ int b2rc_k_encode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
         return B2RC_E_ARG;
     }
     if(is_ans(mode)) {
-        return ans_encode_blocks(ctx, mode, block_size, d_src, n, d_slots, slot_stride, d_sizes, d_err,
+        return ans_encode_blocks(ctx, mode, block_size, d_src, n, d_slots, slot_stride, d_sizes, d_restart, seg_syms, d_err,
                                  (cudaStream_t)cuda_stream);
     }
     const bool wide = block_size > 65536u;
@@ -802,7 +810,7 @@ int b2rc_k_decode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
         return b2rc_k_decode_blocks(ctx, mode, block_size, d_payload, payload_len, d_offsets, nblocks, d_dst, n, d_err,
                                     cuda_stream);
     }
-    if(!ctx || !d_payload || !d_offsets || !d_dst || !d_err || mode != B2RC_MODE_STATIC || !block_ok(block_size) ||
+    if(!ctx || !d_payload || !d_offsets || !d_dst || !d_err || !has_restart(mode) || !block_ok(block_size) ||
        !seg_ok(block_size, seg_syms) || !aligned16(d_dst) || ((uintptr_t)d_offsets & 7u) || ((uintptr_t)d_restart & 3u) ||
        nblocks != b2rc_nblocks(n, block_size)) {
         return B2RC_E_ARG;
@@ -828,8 +836,13 @@ int b2rc_k_decode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
     a.restart = d_restart;
     a.seg_syms = seg_syms;
     const u32 nseg = b2rc_restart_records(block_size, seg_syms) + 1u;
-    const dim3 grid((unsigned)((nblocks + 31) / 32), (nseg + SEG_WARPS - 1u) / SEG_WARPS);
     KernelTimer kt(ctx, B2RC_K_DECODE, st);
+    if(mode == B2RC_MODE_RANS_BYTE) {
+        const dim3 agrid((unsigned)((nblocks + 31) / 32), (nseg + ANS_SEG_WARPS - 1u) / ANS_SEG_WARPS);
+        k_ans_dec_byte_seg<<<agrid, 32 * ANS_SEG_WARPS, ANS_DEC_BYTE_SEG_SMEM, st>>>(a);
+        return launch_check(ctx, "k_ans_dec_byte_seg");
+    }
+    const dim3 grid((unsigned)((nblocks + 31) / 32), (nseg + SEG_WARPS - 1u) / SEG_WARPS);
     k_dec_static_seg<<<grid, 32 * SEG_WARPS, DEC_SEG_SMEM, st>>>(a);
     return launch_check(ctx, "k_dec_static_seg");
 }

@@ -546,6 +546,16 @@ __device__ __forceinline__ void ans_enc_byte_tiles(const EncArgs& a, u32 cum_a, 
                 mg[k] = nmg[k];
             }
         }
+        if(a.restart && tix != 0u && (tix * TILE) % a.seg_syms == 0u && tix * TILE < n_b) {
+            // everything from symbol tix * TILE on is coded: a decoder that has x and knows how many
+            // bytes were emitted so far can start at that symbol (the bytes it has consumed by then
+            // are exactly the ones emitted from here on)
+            const u32 nrec = (a.block + a.seg_syms - 1u) / a.seg_syms - 1u;
+            u32* rec = a.restart + ((b0 + lane) * nrec + (tix * TILE) / a.seg_syms - 1u) * 3u;
+            rec[0] = ((u32)a.slot_stride - out.w) + acc.cnt;  // bytes emitted, the ones still in the register included
+            rec[1] = x;
+            rec[2] = 0;
+        }
         __syncwarp();
     }
 }
@@ -732,6 +742,146 @@ __global__ void __launch_bounds__(32) k_ans_dec_byte(DecArgs a)
     }
     // a valid stream hands the state back where the encoder started it (cppans.h:260-263)
     if(ok && x != ANS_BYTE_LOW) {
+        atomicOr(a.err, ERR_CORRUPT);
+    }
+}
+
+// ---------------------------------------------------------------- A6, segmented --
+// Byte-variant decode from restart points: the encoder recorded, after
+// coding everything from symbol j * seg_syms on, its state x and the number of bytes it had
+// emitted; a decoder that reaches that symbol holds the same x and has consumed everything
+// emitted AFTER that moment, so it stands E bytes before the end of the payload.  CTA = 4 warps
+// over the same 32 blocks, warp = segment, one set of cumulative tables per CTA.
+constexpr u32 ANS_SEG_WARPS = 4;
+constexpr u32 ANS_DEC_BYTE_SEG_SMEM = ANS_DEC_BYTE_CUM + ANS_SEG_WARPS * (TILE_BYTES + INQ_BYTES);
+
+__global__ void __launch_bounds__(32 * ANS_SEG_WARPS) k_ans_dec_byte_seg(DecArgs a)
+{
+    extern __shared__ __align__(16) u8 ans_sm[];
+    const u32 sbase = smem_addr(ans_sm);
+    const u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u8* otile = ans_sm + ANS_DEC_BYTE_CUM + warp * (TILE_BYTES + INQ_BYTES);
+    const u32 otile_a = sbase + ANS_DEC_BYTE_CUM + warp * (TILE_BYTES + INQ_BYTES);
+    const u32 queue_a = otile_a + TILE_BYTES;
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    const u32 nseg = (a.block + a.seg_syms - 1u) / a.seg_syms;
+    const u32 seg = blockIdx.y * ANS_SEG_WARPS + warp;
+    const u8* pay = a.payload;
+    u64 len = 0;
+    if(has) {
+        const u64 o0 = a.offsets[b], o1 = a.offsets[b + 1];
+        if(o0 <= o1 && o1 <= a.payload_len && o1 - o0 < 0xFFFFFFF0ull) {
+            pay = a.payload + o0;
+            len = o1 - o0;
+        }
+    }
+    bool ok = has && len >= (u64)ANS_HDR + 4u;
+    auto ld32u = [&](u32 off) -> u32 {
+        return (u32)pay[off] | ((u32)pay[off + 1u] << 8) | ((u32)pay[off + 2u] << 16) | ((u32)pay[off + 3u] << 24);
+    };
+    if(ok) {
+        ok = ld32u(0) == n_b;
+    }
+    const u32 cum_a = sbase + lane * 2u;
+    if(warp == 0) {
+        u32 prev = 0;
+        bool sane = true;
+#pragma unroll 1
+        for(u32 s = 0; s <= 256u; ++s) {
+            const u32 c = ok ? ld32u(4u + 4u * s) : (s == 256u ? (1u << ANS_BYTE_SCALE_BITS) : 0u);
+            sane = sane && c >= prev && c <= (1u << ANS_BYTE_SCALE_BITS) && (s != 0u || c == 0u);
+            sts16v(cum_a + s * 64u, c);
+            prev = c;
+        }
+        sane = sane && prev == (1u << ANS_BYTE_SCALE_BITS);
+        if(!sane) {
+            for(u32 s = 0; s <= 256u; ++s) {
+                sts16v(cum_a + s * 64u, s == 0u ? 0u : (1u << ANS_BYTE_SCALE_BITS));
+            }
+        }
+        if(has && (!ok || !sane) && blockIdx.y == 0) {
+            atomicOr(a.err, ERR_CORRUPT);
+        }
+    }
+    __syncthreads();
+    if(seg >= nseg) {
+        return;
+    }
+    // a table that warp 0 had to replace marks the block as bad for everyone
+    ok = ok && !(lds16v(cum_a + 1u * 64u) == (1u << ANS_BYTE_SCALE_BITS) && lds16v(cum_a + 256u * 64u) == (1u << ANS_BYTE_SCALE_BITS) &&
+                 ld32u(4u + 4u) != (1u << ANS_BYTE_SCALE_BITS));
+    u32 k1[8];
+#pragma unroll
+    for(int j = 0; j < 8; ++j) {
+        k1[j] = lds16v(cum_a + (32u * j) * 64u);
+    }
+    const u32 seg_lo = seg * a.seg_syms;
+    u32 seg_hi = seg_lo + a.seg_syms;
+    seg_hi = seg_hi < n_b ? seg_hi : n_b;
+    bool mine_ok = ok && seg_lo < n_b;
+    const u32 coded_len = ok ? (u32)len - ANS_HDR : 0u;  // the 4-byte state and everything emitted
+    u32 x = ANS_BYTE_LOW, off = 0;                       // off: coded bytes in front of my first byte
+    u32 x_end = ANS_BYTE_LOW;                            // where a sound stream leaves me
+    const u32 nrec = nseg - 1u;
+    if(mine_ok && seg != 0u) {
+        const u32* rec = a.restart + (b * nrec + seg - 1u) * 3u;
+        const u32 emitted = rec[0];
+        x = rec[1];
+        if(emitted == 0xFFFFFFFFu || emitted > coded_len - 4u) {
+            mine_ok = false;
+            atomicOr(a.err, ERR_CORRUPT);
+        } else {
+            off = coded_len - emitted;
+        }
+    }
+    if(mine_ok && seg + 1u < nseg && (seg + 1u) * a.seg_syms < n_b) {
+        x_end = a.restart[(b * nrec + seg) * 3u + 1u];
+    }
+    WordSrc src;
+    const u32 skip0 = (u32)((uintptr_t)(pay + ANS_HDR) & 3u);
+    {
+        const u8* coded = pay + ANS_HDR;
+        const u8* wbase = (const u8*)((uintptr_t)coded & ~(uintptr_t)3);
+        src.base = reinterpret_cast<const u32*>(wbase);
+        const u64 room = (u64)((a.payload + a.payload_len) - wbase);
+        src.lim = mine_ok ? (u32)(room < 0xFFFFFFF0ull ? room : 0xFFFFFFF0ull) : 0u;
+        src.q = queue_a + lane * 4u;
+        src.prime(mine_ok ? (skip0 + off) >> 2 : 0u);
+    }
+    const AnsCumTab tab{cum_a};
+    RcDec d;
+    if(seg == 0u) {
+        x = ans_byte_dec_init(d, skip0, src);
+    } else {
+        ans_byte_win_init(d, (skip0 + off) & 3u, src);
+    }
+    const u32 n_eff = mine_ok ? seg_hi : 0u;
+    const u32 n_max = __reduce_max_sync(FULL, n_eff);
+    const bool ragged = __any_sync(FULL, n_eff != n_max) || (n_max % TILE) != 0u;
+    const u32 tix0 = seg_lo / TILE;
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+#pragma unroll 1
+    for(u32 tix = tix0; tix < ntiles; ++tix) {
+        const bool inside = __all_sync(FULL, src.tile_is_inside());
+        if(!ragged && inside) {
+            WordSrcInside in{src};
+            ans_dec_byte_tile<false>(tab, k1, d, x, in, otile_a, tix * TILE, n_eff, lane);
+        } else {
+            ans_dec_byte_tile<true>(tab, k1, d, x, src, otile_a, tix * TILE, n_eff, lane);
+        }
+        __syncwarp();
+        store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
+        __syncwarp();
+    }
+    // a sound stream hands the state on to the next segment exactly as the encoder recorded it
+    if(mine_ok && x != x_end) {
         atomicOr(a.err, ERR_CORRUPT);
     }
 }

@@ -19,8 +19,8 @@
  *     16  u64  total_uncompressed  24  u64 nblocks
  *     32  u64  offsets[nblocks+1]  relative to the payload base, offsets[0] = 0
  *     32 + 8*(nblocks+1)           payloads, back to back
- *     [at the next 4-byte boundary, when flags say so: the restart table of the static coder,
- *      3 x u32 per point, see b2rc_k_encode_blocks_r]
+ *     [at the next 4-byte boundary, when flags say so: the restart table (static range coder and
+ *      byte rANS), 3 x u32 per point, see b2rc_k_encode_blocks_r]
  * Payload b is byte-for-byte what the reference encoder emits for block b alone:
  * static  = u32 LE size, 256 x u16 LE frequencies, coded bytes  (cpprcoder.h:386-457)
  * adaptive = u32 LE size, coded bytes                            (cpprcoder.h:689-762)
@@ -49,7 +49,7 @@ extern "C" {
 #define B2RC_MAX_BLOCK (1u << 23)   /* ... and small enough that neither model rescales by size
                                        (cpprcoder.h:561, :1138) */
 #define B2RC_HEADER_BYTES 32u
-#define B2RC_DEFAULT_RESTART_SYMS 8192u /* restart points of the static coder, see b2rc_k_encode_blocks_r */
+#define B2RC_DEFAULT_RESTART_SYMS 8192u /* restart points (static coder, byte rANS), see b2rc_k_encode_blocks_r */
 #define B2RC_MIN_RESTART_SYMS 1024u     /* shortest segment a context accepts (env B2RC_RESTART_SYMS; 0 = none) */
 
 /* Status codes.  0 = the reference's `true` / Status_Success (cpprcoder.h:112-117);
@@ -125,6 +125,9 @@ int b2rc_k_encode_blocks(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
  * encoder's low, range}, 3 x u32 per point, b2rc_restart_records(block, seg) points per block
  * (0xFFFFFFFF in the first word: the block ends before that point).  The payloads do not change;
  * a block becomes several independent chains for K3.  seg_syms: a multiple of 64 below block_size.
+ * B2RC_MODE_RANS_BYTE records the same way (its encoder walks the block backwards, so a point is
+ * taken AFTER everything from that symbol on is coded): {coded bytes emitted so far = bytes still
+ * ahead of a decoder that stands at that symbol, the 32-bit state x, 0}.  Other modes: B2RC_E_ARG.
  * d_restart: nblocks * records * 3 u32, 4-byte aligned; NULL = the calls above. */
 uint32_t b2rc_restart_records(uint32_t block_size, uint32_t seg_syms);
 int b2rc_k_encode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,

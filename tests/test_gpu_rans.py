@@ -251,3 +251,67 @@ def test_random_damage_never_faults(ctx, mode):
             outcomes["corrupt"] += 1
     assert outcomes["corrupt"] >= 1
     assert ctx.decode(enc).tobytes() == data.tobytes()
+
+
+# ---------------------------------------------------------------- restart points --
+def _decode_segment(payload: bytes, x: int, ahead: int, count: int) -> tuple[bytes, int]:
+    """rANS::decode's loop (cppans.h:545-560; get :313-316, advance :321-334) from the middle of a payload:
+    state `x`, `ahead` coded bytes still unread (they are the LAST `ahead` bytes of the payload)."""
+    cum = np.frombuffer(payload[4:4 + 4 * 257], dtype="<u4").astype(np.int64)
+    sym_of = np.repeat(np.arange(256), np.diff(cum))
+    r = len(payload) - ahead
+    out = bytearray()
+    for _ in range(count):
+        slot = x & 0x3FFF
+        s = int(sym_of[slot])
+        out.append(s)
+        x = int(cum[s + 1] - cum[s]) * (x >> 14) + slot - int(cum[s])
+        while x < (1 << 23):
+            x = (x << 8) | payload[r]
+            r += 1
+    return bytes(out), x
+
+
+@pytest.mark.parametrize("gen,block,extra", [("zipf", 65536, 0), ("kennedy", 65536, 4097), ("mixed", 16384, 77)])
+def test_byte_rans_container_carries_restart_points(ctx, oracle, gen, block, extra):
+    """Containers of the byte variant end in a table of restart points like the static range coder's: after
+    coding everything from symbol 8192 k on, the encoder's state and how many bytes it had emitted.  The
+    payloads stay the reference's; every record lets a plain CPU decoder start in the middle of the block
+    (and end on the next record's state); the segmented kernel gives the input back."""
+    import torch
+    from cpprcoder_b200 import container
+    n = 12 * block + extra
+    data = synth.GENERATORS[gen](n)
+    enc = ctx.encode(RANS_BYTE, data, block)
+    info = container.parse(enc)
+    assert info.seg_syms == 8192 and info.restart.shape == (info.nblocks, block // 8192 - 1, 3)
+    want = oracle.encode_blocks(RANS_BYTE, data, block, threads=4)
+    assert_blocks_equal([bytes(info.payload(enc, b)) for b in range(info.nblocks)], want, f"{gen}/{block}")
+    for b in (0, info.nblocks - 2, info.nblocks - 1):
+        blk = data[b * block:(b + 1) * block]
+        recs = info.restart[b]
+        for k in (0, recs.shape[0] - 1):
+            at = 8192 * (k + 1)
+            if at >= blk.size:
+                assert recs[k][0] == 0xFFFFFFFF
+                continue
+            stop = min(at + 8192, blk.size)
+            got, x_end = _decode_segment(want[b], int(recs[k][1]), int(recs[k][0]), stop - at)
+            assert got == blk[at:stop].tobytes(), f"block {b} segment {k + 1}"
+            nxt = int(recs[k + 1][1]) if k + 1 < recs.shape[0] and 8192 * (k + 2) < blk.size else 1 << 23
+            assert x_end == nxt
+    assert ctx.decode(enc).tobytes() == data.tobytes()
+    d_enc, used = ctx.encode_device(RANS_BYTE, torch.from_numpy(data).cuda(), block=block)
+    assert used == enc.size and d_enc[:used].cpu().numpy().tobytes() == enc.tobytes()
+    d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert ctx.decode_device(d_enc, used, d_out) == n and d_out.cpu().numpy().tobytes() == data.tobytes()
+    # a container without the table (what container.build makes) takes the one-chain kernel as before
+    plain = container.build(RANS_BYTE, block, n, want)
+    assert container.parse(plain).restart is None
+    assert ctx.decode(plain).tobytes() == data.tobytes()
+    # a damaged record is an error or a clean decode, never a fault: the state handed on must match
+    bad = enc.copy()
+    table_at = info.payload_base + ((int(info.offsets[-1]) + 3) & ~3)
+    bad[table_at + 4] ^= 0x40  # x of block 0, first record
+    with pytest.raises(Exception):
+        ctx.decode(bad)
