@@ -11,7 +11,7 @@
 //
 // Forward: the reference sorts rotations with a multikey quicksort that compares byte by byte
 // (O(n * common prefix): 1-2 s for one block of zeros).  Here: prefix doubling.  Rows are sorted by their
-// first two bytes, ranked, and then each round turns the order by h bytes into the order by 2h: walking
+// first four bytes, ranked, and then each round turns the order by h bytes into the order by 2h: walking
 // the current order and stepping every row h back lists all rows by their SECOND half; two stable 8-bit
 // counting passes on the rank of the FIRST half finish the round.  Ranks are bucket heads, so rows that
 // are already alone stay where they are.  The loop stops as soon as all ranks differ (log2 of the longest
@@ -458,11 +458,16 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_fwd(const u8* __restrict
         d4[t + BLK_THREADS] = __ldg(g + t + BLK_THREADS);
     }
     __syncthreads();
-    // rows by their first two bytes: least significant byte first
-    blk_pass<8>([&](u32 i) { return i; }, [&](u32 e) { return (u32)s8[(e + 1u) & BLK_M]; }, tmp, cnt, misc);
+    // rows by their first four bytes, least significant byte first: four passes and one ranking, where two
+    // bytes + a doubling round would be four passes and two rankings
+    blk_pass<8>([&](u32 i) { return i; }, [&](u32 e) { return (u32)s8[(e + 3u) & BLK_M]; }, tmp, cnt, misc);
+    blk_pass<8>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)s8[(e + 2u) & BLK_M]; }, sa, cnt, misc);
+    blk_pass<8>([&](u32 i) { return (u32)sa[i]; }, [&](u32 e) { return (u32)s8[(e + 1u) & BLK_M]; }, tmp, cnt, misc);
     blk_pass<8>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)s8[e]; }, sa, cnt, misc);
-    u32 distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e) { return ((u32)s8[e] << 8) | (u32)s8[(e + 1u) & BLK_M]; });
-    u32 h = 2, nrounds = 0;
+    u32 distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e) {
+        return ((u32)s8[e] << 24) | ((u32)s8[(e + 1u) & BLK_M] << 16) | ((u32)s8[(e + 2u) & BLK_M] << 8) | (u32)s8[(e + 3u) & BLK_M];
+    });
+    u32 h = 4, nrounds = 0;
     u32* lb = reinterpret_cast<u32*>(blk_sm + BF_LB);
     u16* half = tmp + BLK_N / 2u;
     while(distinct < BLK_N && h < BLK_N) {
@@ -547,6 +552,124 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_inv(const u8* __restrict
     __syncthreads();
     // counting_sort (blksort.h:379-402): next[k] = place in the column of the k-th smallest byte, stable
     blk_pass<8>([&](u32 i) { return i; }, [&](u32 e) { return (u32)col[e]; }, ja, jb, misc);
+    u8* o = dst + blk * BLK_N;
+    // ---- the walk, cut at stations.  Every 8th row and the starting row p0 are stations; from each, a
+    // thread follows `next` to the following station (8 steps on average, four stations per thread in
+    // flight), which leaves a list of <= 4097 legs with their lengths.  Ranking that short list (13 rounds
+    // over 4097 entries instead of 14 over 32 768) tells every leg where in the output it starts, and the
+    // same threads walk their legs once more, this time writing bytes.  When the cycle through p0 is not
+    // the whole permutation (a block with a period) or a leg gets long (a `next` that dodges the
+    // stations), the doubling below does the job instead.
+    {
+        constexpr u32 NODES = 4608u, NIL = 0xFFFFu, LEG_MAX = 1024u;
+        u16* nx = jb;
+        u16* rr = jb + NODES;
+        u16* nx2 = jb + 2u * NODES;
+        u16* rr2 = jb + 3u * NODES;
+        u8* outb = reinterpret_cast<u8*>(walk);
+        const u32 p0 = ja[top];
+        const u32 start = (p0 & 7u) ? 4096u : (p0 >> 3);
+        const u32 nnodes = (p0 & 7u) ? 4097u : 4096u;
+        if(t == 0u) {
+            misc[0] = 0u;
+        }
+        __syncthreads();
+        auto station = [&](u32 q) { return (q & 7u) == 0u || q == p0; };
+        auto leg_end = [&](u32 q) { return q == p0 ? NIL : (q >> 3); };  // the leg that reaches p0 ends the list
+        u32 q[4], len[4];
+        bool act[4];
+#pragma unroll
+        for(u32 k = 0; k < 4u; ++k) {
+            q[k] = ja[8u * (t + BLK_THREADS * k)];
+            len[k] = 1u;
+            act[k] = !station(q[k]);
+        }
+        while(act[0] || act[1] || act[2] || act[3]) {
+#pragma unroll
+            for(u32 k = 0; k < 4u; ++k) {
+                if(act[k]) {
+                    q[k] = ja[q[k]];
+                    ++len[k];
+                    act[k] = !station(q[k]) && len[k] < LEG_MAX;
+                }
+            }
+        }
+        bool lost = false;
+#pragma unroll
+        for(u32 k = 0; k < 4u; ++k) {
+            lost = lost || !station(q[k]);
+            nx[t + BLK_THREADS * k] = (u16)leg_end(q[k]);
+            rr[t + BLK_THREADS * k] = (u16)len[k];
+        }
+        u32 xlen = 1u;
+        if(t == BLK_THREADS - 1u && nnodes == 4097u) {  // the leg that starts at p0 when p0 is no 8th row
+            u32 y = ja[p0];
+            while(!station(y) && xlen < LEG_MAX) {
+                y = ja[y];
+                ++xlen;
+            }
+            lost = lost || !station(y);
+            nx[4096] = (u16)leg_end(y);
+            rr[4096] = (u16)xlen;
+        }
+        if(lost) {
+            atomicOr(&misc[0], 1u);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for(u32 round = 0; round < 13u; ++round) {
+#pragma unroll
+            for(u32 k = 0; k < 5u; ++k) {
+                const u32 v = t + BLK_THREADS * k;
+                if(v < nnodes) {
+                    const u32 n = nx[v];
+                    const u32 r = rr[v];
+                    if(n != NIL) {
+                        rr2[v] = (u16)(r + rr[n]);
+                        nx2[v] = nx[n];
+                    } else {
+                        rr2[v] = (u16)r;
+                        nx2[v] = (u16)NIL;
+                    }
+                }
+            }
+            __syncthreads();
+            u16* sw = nx;
+            nx = nx2;
+            nx2 = sw;
+            sw = rr;
+            rr = rr2;
+            rr2 = sw;
+        }
+        // rr[v]: bytes from the start of leg v to the end of the walk; the leg of p0 sees all of it
+        const bool whole = misc[0] == 0u && (u32)rr[start] == (BLK_N & 0xFFFFu) && nx[start] == NIL;
+        if(whole) {
+#pragma unroll
+            for(u32 k = 0; k < 4u; ++k) {
+                const u32 v = t + BLK_THREADS * k;
+                u32 at = (BLK_N - (u32)rr[v]) & BLK_M;
+                u32 y = 8u * v;
+                for(u32 j = 0; j < len[k]; ++j) {
+                    outb[at + j] = col[y];
+                    y = ja[y];
+                }
+            }
+            if(t == BLK_THREADS - 1u && nnodes == 4097u) {
+                u32 y = p0;
+                for(u32 j = 0; j < xlen; ++j) {  // this leg opens the walk
+                    outb[j] = col[y];
+                    y = ja[y];
+                }
+            }
+            __syncthreads();
+            const uint4* o4 = reinterpret_cast<const uint4*>(outb);
+            reinterpret_cast<uint4*>(o)[t] = o4[t];
+            reinterpret_cast<uint4*>(o)[t + BLK_THREADS] = o4[t + BLK_THREADS];
+            return;
+        }
+        __syncthreads();
+    }
+    // ---- pointer doubling: jump tables J <- J o J, the known part of the walk doubles every round
     if(t == 0u) {
         walk[0] = ja[top];
     }
@@ -571,7 +694,6 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_inv(const u8* __restrict
         cur = nxt;
         nxt = sw;
     }
-    u8* o = dst + blk * BLK_N;
     const uint2* w4 = reinterpret_cast<const uint2*>(walk);
 #pragma unroll 4
     for(u32 k = 0; k < 8u; ++k) {
