@@ -75,3 +75,38 @@ def blk_periodic_cases() -> list:
     out.append(("periodic-among-others", np.concatenate([rng.integers(0, 256, n, dtype=np.uint8), np.tile(np.arange(8, dtype=np.uint8), n // 8),
                                                          rng.integers(0, 7, n + 99, dtype=np.uint8)])))
     return out
+
+
+def blk_fuzz_stream(seed: int, nblocks: int = 48) -> np.ndarray:
+    """Blocks of mixed structure for the block sort: iid over small and large alphabets, geometric runs, a
+    chunk repeated with a few mutations (long common prefixes, many doubling rounds, the switch between full
+    and short rounds at different depths), slices of text."""
+    from _oracle import canterbury
+    rng = np.random.default_rng(seed)
+    n = 32768
+    text = np.frombuffer(canterbury("lcet10.txt"), dtype=np.uint8)
+    parts = []
+    for b in range(nblocks):
+        kind = b % 6
+        if kind == 0:
+            blk = rng.integers(0, int(rng.choice([2, 3, 5, 17, 64, 256])), n, dtype=np.uint8)
+        elif kind == 1:
+            lens = rng.geometric(1.0 / float(rng.choice([3, 20, 200])), n)
+            blk = np.repeat(rng.integers(0, 4, n, dtype=np.uint8), lens)[:n]
+        elif kind == 2:
+            chunk = rng.integers(0, 8, int(rng.choice([100, 1000, 5000])), dtype=np.uint8)
+            blk = np.tile(chunk, n // chunk.size + 1)[:n].copy()
+            hits = rng.integers(0, n, int(rng.choice([1, 5, 50])))
+            blk[hits] = rng.integers(8, 16, hits.size, dtype=np.uint8)
+        elif kind == 3:
+            at = int(rng.integers(0, text.size - n))
+            blk = text[at:at + n].copy()
+        elif kind == 4:
+            blk = rng.choice(256, n, p=rng.dirichlet(np.ones(256) * 0.02)).astype(np.uint8)
+        else:
+            blk = np.zeros(n, np.uint8)
+            k = int(rng.choice([1, 2, 30]))
+            blk[rng.integers(0, n, k)] = 1
+        parts.append(blk)
+    parts.append(rng.integers(0, 256, int(rng.integers(0, n)), dtype=np.uint8))
+    return np.concatenate(parts)

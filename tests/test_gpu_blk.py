@@ -6,7 +6,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from _cases import blk_cases, blk_periodic_cases
+from _cases import blk_cases, blk_fuzz_stream, blk_periodic_cases
 from _oracle import BLK_BLOCK, BLK_CODED, BlkSort, Oracle, blk_decoded_size, blk_encode_bound, fnv1a64
 
 pytestmark = pytest.mark.gpu
@@ -52,6 +52,19 @@ def test_inverse_of_the_reference_output(ctx, oracle, label, data):
     back = ctx.blk_decode_device(_dev(coded)).cpu().numpy()
     assert back.size == data.size == blk_decoded_size(coded.size)
     assert np.array_equal(back, data)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_fuzz_blocks_equal_the_oracle(ctx, oracle, seed):
+    data = blk_fuzz_stream(seed)
+    want = oracle.encode(data, threads=16)
+    got = ctx.blk_encode_device(_dev(data)).cpu().numpy()
+    if not np.array_equal(got, want):
+        bad = int(np.flatnonzero(got != want)[0]) // BLK_CODED
+        raise AssertionError(f"seed {seed}: block {bad} (kind {bad % 6}) differs from the oracle")
+    assert np.array_equal(ctx.blk_decode_device(_dev(want)).cpu().numpy(), data)
+    r = ctx.blk_rounds()
+    assert ((r >> 8) & 0xFF).max() >= 3 and ((r & 0xFF) - ((r >> 8) & 0xFF)).max() >= 3  # both kinds of round ran
 
 
 def test_host_pointer_calls(ctx, oracle):
