@@ -39,7 +39,11 @@ constexpr u32 BLK_THREADS = 1024u;
 // forward kernel, byte offsets in dynamic shared memory
 constexpr u32 BF_SA = 0u, BF_TMP = 65536u, BF_RK = 131072u, BF_CNT = 196608u, BF_FB = 212992u, BF_MISC = 217088u;
 constexpr u32 BF_LB = BF_MISC + 512u;  // short rounds: two ballot arrays of 512 words
-constexpr u32 BLK_FWD_SMEM = BF_LB + 4096u;
+// the start (blk_start16): 65 536 packed u16 counters over sa + tmp, the block's bytes in the first half of rk,
+// the rows by their third and fourth byte in what lies behind (second half of rk, cnt, fbits, misc, lb + 7 KiB)
+constexpr u32 BF_START_OUT = BF_RK + 32768u, BF_START_X = BF_START_OUT + 65536u;
+constexpr u32 BLK_FWD_SMEM = BF_START_X + 512u;
+static_assert(BF_LB + 4096u <= BLK_FWD_SMEM && BLK_FWD_SMEM <= 232448u, "forward kernel shared memory");
 // inverse kernel: two jump tables, the walk, the column; the counters of the one counting pass sit in the
 // second jump table, which is not in use yet
 constexpr u32 BI_JA = 0u, BI_JB = 65536u, BI_P = 131072u, BI_L = 196608u, BI_MISC = 229376u;
@@ -214,6 +218,91 @@ __device__ __forceinline__ u32 blk_rerank(const u16* sa, u16* rk, u32* fbits, u3
     }
     __syncthreads();
     return distinct;
+}
+
+// ----------------------------------------------------------------- the start --
+// The first of the passes of a least-significant-digit-first sort need not be stable (nothing is ordered
+// yet), so the rows go by their third AND fourth byte in one unstable counting sort with plain shared
+// atomics on 65 536 counters (two u16 per word; a count never passes 32 768, so the halves never touch) --
+// where two stable passes would cost 16 ballots per row.  A warp whose 32 rows show the same two bytes (runs)
+// adds once for all of them.  s8: the block; c32: 32 768 words; out: u16[32 768]; xs: u32[64].
+__device__ __forceinline__ void blk_start16(const u8* s8, u32* c32, u16* out, u32* xs)
+{
+    const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    {
+        uint4* c4 = reinterpret_cast<uint4*>(c32);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for(u32 k = 0; k < 8u; ++k) {
+            c4[k * BLK_THREADS + t] = z;
+        }
+    }
+    __syncthreads();
+    auto key_of = [&](u32 i) { return ((u32)s8[(i + 2u) & BLK_M] << 8) | (u32)s8[(i + 3u) & BLK_M]; };
+#pragma unroll 4
+    for(u32 k = 0; k < 32u; ++k) {
+        const u32 key = key_of(k * BLK_THREADS + t);
+        const u32 inc = (key & 1u) ? 0x10000u : 1u;
+        if(__all_sync(FULL, key == __shfl_sync(FULL, key, 0))) {
+            if(lane == 0u) {
+                atomicAdd(&c32[key >> 1], inc * 32u);
+            }
+        } else {
+            atomicAdd(&c32[key >> 1], inc);
+        }
+    }
+    __syncthreads();
+    // exclusive scan in key order: warp w owns words [1024 w, 1024 w + 1024), a row of 32 words per step
+    u32* mine = c32 + warp * 1024u;
+    {
+        u32 sum = 0;
+#pragma unroll 8
+        for(u32 r = 0; r < 32u; ++r) {
+            const u32 v = mine[r * 32u + lane];
+            sum += (v & 0xFFFFu) + (v >> 16);
+        }
+        sum = __reduce_add_sync(FULL, sum);
+        if(lane == 0u) {
+            xs[warp] = sum;
+        }
+    }
+    __syncthreads();
+    u32 run = __reduce_add_sync(FULL, lane < warp ? xs[lane] : 0u);
+#pragma unroll 4
+    for(u32 r = 0; r < 32u; ++r) {
+        const u32 v = mine[r * 32u + lane];
+        const u32 lo = v & 0xFFFFu, both = lo + (v >> 16);
+        u32 incl = both;
+#pragma unroll
+        for(u32 o = 1; o < 32u; o <<= 1) {
+            const u32 up = __shfl_up_sync(FULL, incl, o);
+            if(lane >= o) {
+                incl += up;
+            }
+        }
+        const u32 first = run + incl - both;
+        mine[r * 32u + lane] = first | ((first + lo) << 16);
+        run += __shfl_sync(FULL, incl, 31);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for(u32 k = 0; k < 32u; ++k) {
+        const u32 i = k * BLK_THREADS + t;
+        const u32 key = key_of(i);
+        const u32 inc = (key & 1u) ? 0x10000u : 1u, sh = (key & 1u) * 16u;
+        u32 at;
+        if(__all_sync(FULL, key == __shfl_sync(FULL, key, 0))) {
+            u32 old = 0;
+            if(lane == 0u) {
+                old = atomicAdd(&c32[key >> 1], inc * 32u);
+            }
+            at = ((__shfl_sync(FULL, old, 0) >> sh) & 0xFFFFu) + lane;
+        } else {
+            at = (atomicAdd(&c32[key >> 1], inc) >> sh) & 0xFFFFu;
+        }
+        out[at] = (u16)i;
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------ short rounds --
@@ -458,10 +547,19 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_fwd(const u8* __restrict
         d4[t + BLK_THREADS] = __ldg(g + t + BLK_THREADS);
     }
     __syncthreads();
-    // rows by their first four bytes, least significant byte first: four passes and one ranking, where two
-    // bytes + a doubling round would be four passes and two rankings
-    blk_pass<8>([&](u32 i) { return i; }, [&](u32 e) { return (u32)s8[(e + 3u) & BLK_M]; }, tmp, cnt, misc);
-    blk_pass<8>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)s8[(e + 2u) & BLK_M]; }, sa, cnt, misc);
+    // rows by their first four bytes, least significant first: bytes 3 and 2 in one unstable counting sort,
+    // bytes 1 and 0 in two stable passes, then one ranking (two bytes + a doubling round would be two)
+    {
+        u16* start_out = reinterpret_cast<u16*>(blk_sm + BF_START_OUT);
+        blk_start16(s8, reinterpret_cast<u32*>(blk_sm + BF_SA), start_out, reinterpret_cast<u32*>(blk_sm + BF_START_X));
+        const uint4* o4 = reinterpret_cast<const uint4*>(start_out);
+        uint4* s4 = reinterpret_cast<uint4*>(sa);
+#pragma unroll
+        for(u32 k = 0; k < 4u; ++k) {
+            s4[k * BLK_THREADS + t] = o4[k * BLK_THREADS + t];
+        }
+        __syncthreads();
+    }
     blk_pass<8>([&](u32 i) { return (u32)sa[i]; }, [&](u32 e) { return (u32)s8[(e + 1u) & BLK_M]; }, tmp, cnt, misc);
     blk_pass<8>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)s8[e]; }, sa, cnt, misc);
     u32 distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e) {
