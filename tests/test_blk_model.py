@@ -20,7 +20,8 @@ def model_forward(s):
     """-> (column, row, rounds as a list of 'F' (full) / ('S', active rows))"""
     s = s.astype(np.int64)
     rows = np.arange(N)
-    for k in (3, 2, 1, 0):                                   # four byte passes, least significant first
+    for k in (3, 2, 1, 0):  # the kernel sorts bytes 3 and 2 at once, unstably: rows tied on all four bytes
+        #                     come out in another order, which nothing downstream depends on
         rows = stable_by(rows, s[(rows + k) & M])
     key = (s[rows] << 24) | (s[(rows + 1) & M] << 16) | (s[(rows + 2) & M] << 8) | s[(rows + 3) & M]
     head = np.ones(N + 1, bool)
