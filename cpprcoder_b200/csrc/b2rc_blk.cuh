@@ -138,10 +138,12 @@ __device__ __forceinline__ void blk_pass(Elem elem, Digit digit, u16* dst, u16* 
     for(u32 r = 0; r < 32u; ++r) {
         const u32 d = digit(elem(i0 + r * 32u));
         u32 peers = FULL;
+        if(!__all_sync(FULL, d == __shfl_sync(FULL, d, 0))) {  // 32 rows of one run share their digit: no search
 #pragma unroll
-        for(u32 b = 0; b < BITS; ++b) {
-            const u32 bit = (d >> b) & 1u;
-            peers &= __ballot_sync(FULL, bit) ^ (bit - 1u);
+            for(u32 b = 0; b < BITS; ++b) {
+                const u32 bit = (d >> b) & 1u;
+                peers &= __ballot_sync(FULL, bit) ^ (bit - 1u);
+            }
         }
         const u32 leader = (u32)__ffs((int)peers) - 1u;
         u32 before = 0;
