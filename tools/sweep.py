@@ -33,6 +33,7 @@ def timed(fn, reps=3):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else (1 << 30)
     out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/block_sweep.json"
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None  # e.g. "rans": refresh those rows of an older file
     ctx = api.Context(0)
     oracle = Oracle.get()
     data = synth.kennedy(n)
@@ -41,6 +42,8 @@ def main():
     rows = []
     for block in [4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288, 1048576]:
         for mode, name in ((0, "static"), (1, "adaptive"), (2, "rans"), (3, "rans-word")):
+            if only and name not in only:
+                continue
             enc, used = ctx.encode_device(mode, src, block=block)
             t_enc = timed(lambda: ctx.encode_device(mode, src, enc, block=block))
             t_dec = timed(lambda: ctx.decode_device(enc, used, dst))
