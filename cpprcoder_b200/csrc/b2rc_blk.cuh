@@ -431,6 +431,79 @@ __device__ __forceinline__ void blk_pass_short(u32 n, Elem elem, Digit digit, u1
     __syncthreads();
 }
 
+// A round over at most 2048 active rows.  The pair (bucket, rank of the second half) says all there is to say
+// about a row's new place, so ANY sort of the pairs will do -- no walk in second-half order, no stability:
+// the rows are picked up by place (straight from the head flags), keyed, and put through a bitonic network
+// in shared memory (66 compare-exchange steps for 2048 pairs) instead of two counting passes with their
+// 16 KiB of counters to clear and scan.  keys: u32[2048], rows: u16[2048]; the sorted rows land in list[0 .. n).
+__device__ __forceinline__ void blk_sort_tiny(u32 n, const u16* sa, const u16* rk, const u32* fbits, u32 h, u32* keys, u16* rows,
+                                              u16* list, u32* misc)
+{
+    const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const u32 w = fbits[t];
+    const u32 nx = t + 1u < BLK_THREADS ? fbits[t + 1u] : 1u;
+    u32 act = ~(w & ((w >> 1) | (nx << 31)));  // places whose bucket holds two rows or more
+    const u32 mine = (u32)__popc(act);
+    u32 incl = mine;
+#pragma unroll
+    for(u32 o = 1; o < 32u; o <<= 1) {
+        const u32 up = __shfl_up_sync(FULL, incl, o);
+        if(lane >= o) {
+            incl += up;
+        }
+    }
+    if(lane == 31u) {
+        misc[warp] = incl;
+    }
+    __syncthreads();
+    u32 at = __reduce_add_sync(FULL, lane < warp ? misc[lane] : 0u) + incl - mine;
+    while(act) {
+        const u32 bit = (u32)__ffs((int)act) - 1u;
+        act &= act - 1u;
+        const u32 q = sa[t * 32u + bit];
+        keys[at] = ((u32)rk[q] << 16) | (u32)rk[(q + h) & BLK_M];
+        rows[at] = (u16)q;
+        ++at;
+    }
+    u32 pow2 = 2u;
+    while(pow2 < n) {
+        pow2 <<= 1;
+    }
+    for(u32 i = n + t; i < pow2; i += BLK_THREADS) {
+        keys[i] = 0xFFFFFFFFu;  // larger than any pair: ranks stay below 2^15
+        rows[i] = 0;
+    }
+    __syncthreads();
+    for(u32 k = 2u; k <= pow2; k <<= 1) {
+        for(u32 j = k >> 1; j > 0u; j >>= 1) {
+            if(t < (pow2 >> 1)) {
+                const u32 i = 2u * t - (t & (j - 1u));
+                const u32 p = i + j;
+                const u32 a = keys[i], b = keys[p];
+                if((a > b) == ((i & k) == 0u)) {
+                    keys[i] = b;
+                    keys[p] = a;
+                    const u16 ra = rows[i];
+                    rows[i] = rows[p];
+                    rows[p] = ra;
+                }
+            }
+            // a thread's pair lies within its warp's 64 entries when j <= 32: only the wide steps, and the last
+            // step before a wide one, need the whole CTA (15 barriers instead of 66 for 2048 pairs)
+            if(j > 32u || (j == 1u && k >= 64u)) {
+                __syncthreads();
+            } else {
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    for(u32 i = t; i < n; i += BLK_THREADS) {
+        list[i] = rows[i];
+    }
+    __syncthreads();
+}
+
 // The sorted list (by bucket, then by second half) goes home: row j of the list lands at
 //   head of its bucket + (j - first j of that bucket),
 // its new rank is the place of the first row of its run of equal (bucket, second half) pairs, and every
@@ -571,7 +644,12 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_fwd(const u8* __restrict
     u32* lb = reinterpret_cast<u32*>(blk_sm + BF_LB);
     u16* half = tmp + BLK_N / 2u;
     while(distinct < BLK_N && h < BLK_N) {
-        if(blk_count_active(fbits, misc) > BLK_N / 2u) {
+        const u32 active = blk_count_active(fbits, misc);
+        if(active <= 2048u) {
+            blk_sort_tiny(active, sa, rk, fbits, h, reinterpret_cast<u32*>(half), half + 4096u, tmp, misc);
+            distinct += blk_place_short(active, tmp, sa, rk, fbits, h, lb, lb + 512u, misc);
+            nrounds += 0x100u;
+        } else if(active > BLK_N / 2u) {
             blk_pass<8>([&](u32 i) { return ((u32)sa[i] - h) & BLK_M; }, [&](u32 e) { return (u32)rk[e] & 0xFFu; }, tmp, cnt, misc);
             blk_pass<7>([&](u32 i) { return (u32)tmp[i]; }, [&](u32 e) { return (u32)rk[e] >> 8; }, sa, cnt, misc);
             distinct = blk_rerank(sa, rk, fbits, misc, [&](u32 e) { return ((u32)rk[e] << 16) | (u32)rk[(e + h) & BLK_M]; });
