@@ -1390,7 +1390,7 @@ static int blk_fix_ties(b2rc_ctx* ctx, const u8* d_src, u8* d_dst, u64 nb, cudaS
     if(list.empty()) {
         return B2RC_OK;
     }
-    const size_t batch = list.size() < 128 ? list.size() : 128;
+    const size_t batch = list.size() < 592 ? list.size() : 592;  // four waves of one CTA per SM; 320 KiB of scratch per block
     const size_t rk_bytes = (size_t)BLK_N * 2, q_bytes = (size_t)2 * BLK_TIES_QUEUE * sizeof(TieRange);
     int rc;
     if((rc = grow(ctx, ctx->blk_ties, ctx->blk_ties_cap, batch * (rk_bytes + q_bytes + 4) + 256)) != B2RC_OK) {

@@ -67,6 +67,19 @@ def test_fuzz_blocks_equal_the_oracle(ctx, oracle, seed):
     assert ((r >> 8) & 0xFF).max() >= 3 and ((r & 0xFF) - ((r >> 8) & 0xFF)).max() >= 3  # both kinds of round ran
 
 
+def test_many_periodic_blocks_replay_in_batches(ctx, oracle):
+    """More blocks with ties than one batch of the replay takes (592): every one gets the reference's row."""
+    rng = np.random.default_rng(11)
+    a = np.tile(rng.integers(0, 4, 16384, dtype=np.uint8), 2)
+    b = np.tile(rng.integers(0, 256, 8, dtype=np.uint8), 4096)
+    ra, rb = oracle.encode(a), oracle.encode(b)
+    blocks = [a] * 650 + [b] + [a] * 49
+    want = np.concatenate([ra] * 650 + [rb] + [ra] * 49)
+    got = ctx.blk_encode_device(_dev(np.concatenate(blocks))).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert (ctx.blk_rounds() >> 31).all()
+
+
 def test_host_pointer_calls(ctx, oracle):
     rng = np.random.default_rng(5)
     for n in (0, 1, BLK_BLOCK - 1, BLK_BLOCK, 9 * BLK_BLOCK + 4321):
