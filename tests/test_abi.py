@@ -41,6 +41,18 @@ def test_size_helpers_need_no_device(lib):
     assert lib.b2rc_strerror(-3) == b"corrupt container or payload"
 
 
+def test_block_sort_size_helpers_need_no_device(lib):
+    # BlkSort::encodeBound (blksort.h:404-409): two bytes per full 32 KiB block; the exact inverse of it for decode
+    for n, coded in [(0, 0), (1, 1), (32767, 32767), (32768, 32770), (32769, 32771), (152089, 152097), (5 << 30, (5 << 30) + 2 * 163840)]:
+        assert lib.b2rc_blk_encode_bound(n) == coded
+        assert lib.b2rc_blk_decoded_size(coded) == n
+    # without a context nothing is coded: null context is an argument error, never a CPU fallback
+    out = C.c_uint64(0)
+    buf = (C.c_uint8 * 64)()
+    assert lib.b2rc_blk_encode(None, buf, 64, buf, 64, C.byref(out)) == -1
+    assert lib.b2rc_blk_decode_device(None, buf, 64, buf, 64, C.byref(out), None) == -1
+
+
 def test_peek_validates_headers(lib):
     from cpprcoder_b200 import container
     good = container.build(1, 65536, 0, [])
