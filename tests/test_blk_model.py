@@ -98,6 +98,118 @@ def model_inverse(col, top):
     return out, by_legs
 
 
+def model_tie_replay(s, rk):
+    """What k_blk_ties does for a block whose rotations tie: the reference's multikey quicksort (mqsort,
+    blksort.h:281-362) replayed range by range -- rank comparisons where the reference compares whole rotations,
+    a jump to the first depth at which the smallest and the largest rotation of a range differ, no work at all for
+    a range of equal rotations -- and the place rotation 0 ends up in.  `rk`: final ranks (ties share one)."""
+    s = [int(x) for x in s]
+    rk = [int(x) for x in rk]
+    v = list(range(N))
+
+    def byte(row, d):
+        return s[(row + d) & M]
+
+    def sift(lo, root, last, x):       # 1-based heap over v[lo ..]
+        i = root
+        while 2 * i <= last:
+            j = 2 * i
+            if j < last and rk[v[lo + j - 1]] < rk[v[lo + j]]:
+                j += 1
+            if not rk[x] < rk[v[lo + j - 1]]:
+                break
+            v[lo + i - 1] = v[lo + j - 1]
+            i = j
+        v[lo + i - 1] = x
+
+    queue = [(0, N, 0, 11)]
+    while queue:
+        nxt = []
+        for lo, size, d, level in queue:
+            if level == 0:             # heapsort, blksort.h:235-279
+                for k in range(size // 2, 0, -1):
+                    sift(lo, k, size, v[lo + k - 1])
+                last = size
+                while last > 1:
+                    x = v[lo + last - 1]
+                    v[lo + last - 1] = v[lo]
+                    last -= 1
+                    sift(lo, 1, last, x)
+                continue
+            if size < 37:              # insertionsort, blksort.h:223-233
+                for i in range(1, size):
+                    x, j = v[lo + i], i - 1
+                    while j >= 0 and rk[x] < rk[v[lo + j]]:
+                        v[lo + j + 1] = v[lo + j]
+                        j -= 1
+                    v[lo + j + 1] = x
+                continue
+            w = v[lo:lo + size]
+            a, b = min(w, key=lambda r: (rk[r], r)), max(w, key=lambda r: (rk[r], r))
+            if rk[a] == rk[b]:
+                continue               # equal rotations: no pass ever moves one of them
+            while byte(a, d) == byte(b, d):
+                d += 1                 # passes in which every row shows the same byte move nothing
+            q1 = size >> 2
+            x0, x1, x2 = s[w[q1]], s[w[2 * q1]], s[w[3 * q1]]      # median on byte 0, whatever the depth
+            if x0 < x1:
+                pick = w[2 * q1] if x1 < x2 else (w[3 * q1] if x0 < x2 else w[q1])
+            else:
+                pick = w[q1] if x0 < x2 else (w[3 * q1] if x1 < x2 else w[2 * q1])
+            p, hi = byte(pick, d), size - 1
+            i0, i1, m0, m1 = 0, hi, 0, hi
+            while True:
+                while i0 <= i1:
+                    c = byte(w[i0], d)
+                    if p < c:
+                        break
+                    if p == c:
+                        w[i0], w[m0] = w[m0], w[i0]
+                        m0 += 1
+                    i0 += 1
+                while i0 <= i1:
+                    c = byte(w[i1], d)
+                    if c < p:
+                        break
+                    if p == c:
+                        w[i1], w[m1] = w[m1], w[i1]
+                        m1 -= 1
+                    i1 -= 1
+                if i1 < i0:
+                    break
+                w[i0], w[i1] = w[i1], w[i0]
+                i0 += 1
+                i1 -= 1
+            for i in range(min(m0, i0 - m0)):
+                w[i], w[i1 - i] = w[i1 - i], w[i]
+            less_n = i0 - m0
+            for i in range(min(hi - m1, m1 - i1)):
+                w[i0 + i], w[hi - i] = w[hi - i], w[i0 + i]
+            gt_at = hi - (m1 - i1) + 1
+            v[lo:lo + size] = w
+            if less_n >= 2:
+                nxt.append((lo, less_n, d, level - 1))
+            if size - gt_at >= 2:
+                nxt.append((lo + gt_at, size - gt_at, d, level - 1))
+            if gt_at - less_n >= 2 and d + 1 < N:
+                nxt.append((lo + less_n, gt_at - less_n, d + 1, level))
+        queue = nxt
+    return v.index(0)
+
+
+def model_ranks(s):
+    """Final ranks of all rotations (ties share the place of their run's first row), the slow sure way."""
+    twice = np.concatenate([s, s])
+    order = sorted(range(N), key=lambda r: twice[r:r + N].tobytes())
+    rk = np.empty(N, np.int64)
+    head = 0
+    for place, r in enumerate(order):
+        if place and twice[r:r + N].tobytes() != twice[order[place - 1]:order[place - 1] + N].tobytes():
+            head = place
+        rk[r] = head
+    return rk
+
+
 @pytest.fixture(scope="module")
 def oracle(built):
     return BlkSort(Oracle.get())
@@ -137,3 +249,13 @@ def test_model_on_periodic_blocks(oracle):
         assert np.array_equal(back2, s), label
         if label != "period1":
             assert not by_legs
+
+
+@pytest.mark.parametrize("label", ["period2", "period4", "period1024", "period16384", "period8192-alpha3"])
+def test_tie_replay_model_names_the_reference_row(oracle, label):
+    s = dict(blk_periodic_cases())[label]
+    rec = oracle.encode(s)
+    _, canonical, _ = model_forward(s)
+    rk = model_ranks(s)
+    assert canonical == rk[0]
+    assert model_tie_replay(s, rk) == int(rec[N]) | int(rec[N + 1]) << 8
