@@ -5,27 +5,35 @@
 //                   rotations of a 32 KiB block + the row of the unrotated block
 //   B2  k_blk_inv   BlkSort::decode_internal (blksort.h:545-672): stable counting sort of the column,
 //                   then the walk  p = next[p]  -- 32 768 dependent loads in the reference
+//   B3  k_blk_ties  the row number of blocks whose rotations tie: a replay of the reference's quicksort
 //
 // Mapping: one 32 KiB block per CTA of 1024 threads, everything in shared memory (3 x 64 KiB of u16
 // rows/ranks + 16 KiB of counters: the 227 KB of an sm_100 SM is what makes this a one-CTA problem).
 //
 // Forward: the reference sorts rotations with a multikey quicksort that compares byte by byte
-// (O(n * common prefix): 1-2 s for one block of zeros).  Here: prefix doubling.  Rows are sorted by their
-// first four bytes, ranked, and then each round turns the order by h bytes into the order by 2h: walking
-// the current order and stepping every row h back lists all rows by their SECOND half; two stable 8-bit
-// counting passes on the rank of the FIRST half finish the round.  Ranks are bucket heads, so rows that
-// are already alone stay where they are.  The loop stops as soon as all ranks differ (log2 of the longest
-// repeat, 4-9 rounds on text) or at h = 32 768 (a block with a period: equal rotations have equal last
-// bytes, the column does not depend on the tie order; the row number is fixed by B3).
+// (O(n * common prefix): 1-2 s for one block of zeros).  Here: prefix doubling.
+//   start   rows by their first four bytes: bytes 3 and 2 in one UNSTABLE counting sort on 65 536 shared
+//           counters (blk_start16; the first pass of an LSD sort need not be stable), bytes 1 and 0 in two
+//           stable passes (blk_pass), then ranks = bucket heads (blk_rerank);
+//   rounds  each turns the order by h bytes into the order by 2h.  A full round (more than half of the rows
+//           still share a bucket) walks the current order stepping every row h back -- all rows by their
+//           SECOND half -- and finishes with two stable passes on the rank of the FIRST half.  A short round
+//           does the same for the listed active rows only (blk_list_active, blk_pass_short, blk_place_short);
+//           at 2048 active rows or fewer the (bucket, second-half rank) pairs go through a bitonic network
+//           (blk_sort_tiny): any sort of the pairs will do.  Rows alone in their bucket never move again.
+//   end     all ranks differ (log2 of the longest repeat: 1-2 rounds on Zipf bytes, 6-8 on text), or
+//           h = 32 768: the block has a period, equal rotations have equal last bytes, the column does not
+//           depend on the tie order; the row number is settled by B3.
 // The stable pass is warp-chunked: warp w owns rows [1024 w, 1024 w + 1024) of the input order, counts
 // them per digit (ballots find the lanes with equal digits, the first of them adds the group: no atomics)
 // and remembers each row's rank within the warp, a CTA scan in (digit, warp) order gives each warp its
 // first slot per digit, and every row is then stored at slot + rank.
 //
-// Inverse: the walk is a linked list through a permutation; pointer doubling (J <- J o J) gives the
-// 2^k-th successor of every row, so after round k the first 2^(k+1) positions of the walk are known:
-// 15 rounds of 32 768 independent gathers instead of 32 768 dependent ones.  Works for permutations with
-// several cycles (blocks with a period) exactly like the reference's walk does.
+// Inverse: the walk is a linked list through a permutation.  It is cut at stations (every 8th row and the
+// start): threads follow the legs between stations, Wyllie's pointer jumping ranks the 4 097 legs, and
+// the legs are walked once more, writing.  Permutations with several cycles (blocks with a period) and
+// legs longer than 1024 steps fall back to pointer doubling over all rows (J <- J o J: after round k the
+// first 2^(k+1) positions of the walk are known), which leaves cycles exactly as the reference's walk does.
 #pragma once
 #include "b2rc_kernels.cuh"
 
