@@ -1,5 +1,5 @@
 """Block-sort timing on the device: forward / inverse GB/s for a synthetic stream, rounds histogram.
-    python tools/blk_perf.py [bytes] [zipf|mixed|kennedy]"""
+    python tools/blk_perf.py [bytes] [zipf|mixed|kennedy|text]      (text: the Canterbury text files, tiled)"""
 import sys
 from pathlib import Path
 
@@ -13,7 +13,13 @@ from cpprcoder_b200 import api, synth  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
     gen = sys.argv[2] if len(sys.argv) > 2 else "zipf"
-    data = synth.GENERATORS[gen](n)
+    if gen == "text":
+        sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+        from _oracle import canterbury
+        one = np.frombuffer(b"".join(canterbury(f) for f in ("lcet10.txt", "plrabn12.txt", "alice29.txt", "asyoulik.txt")), np.uint8)
+        data = np.tile(one, n // one.size + 1)[:n].copy()
+    else:
+        data = synth.GENERATORS[gen](n)
     ctx = api.Context(0)
     src = torch.from_numpy(data).cuda()
     coded = torch.empty(api.blk_encode_bound(n), dtype=torch.uint8, device="cuda")
