@@ -11,6 +11,8 @@ Weak scaling: every rank codes its own 1 GiB shard (blocks shard by contiguous r
 cpprcoder_b200/dist.py); the only collective is the all-gather of payload sizes.
 
     python bench.py [--gpus N --steps K --warmup W]            our arm
+    python bench.py --workload NAME                            other streams / coders of the same path, the rANS
+                                                               sibling, the block-sort transform (WORKLOADS below)
     python bench.py --impl reference [...]                      the reference's CPU coder
 under torchrun for N > 1 (one rank per GPU, NCCL).
 """
