@@ -43,6 +43,7 @@ constexpr u32 BLK_N = 32768u;      // BlkSort::BlockSize, blksort.h:80
 constexpr u32 BLK_M = BLK_N - 1u;
 constexpr u32 BLK_CODED = 32770u;  // BlkSort::EncodedSize, blksort.h:83
 constexpr u32 BLK_THREADS = 1024u;
+constexpr u32 BLK_TINY = 2048u;    // rounds over this many active rows or fewer sort pairs in a bitonic network (4096 measured slower)
 
 // forward kernel, byte offsets in dynamic shared memory
 constexpr u32 BF_SA = 0u, BF_TMP = 65536u, BF_RK = 131072u, BF_CNT = 196608u, BF_FB = 212992u, BF_MISC = 217088u;
@@ -484,8 +485,8 @@ __device__ __forceinline__ void blk_sort_tiny(u32 n, const u16* sa, const u16* r
     __syncthreads();
     for(u32 k = 2u; k <= pow2; k <<= 1) {
         for(u32 j = k >> 1; j > 0u; j >>= 1) {
-            if(t < (pow2 >> 1)) {
-                const u32 i = 2u * t - (t & (j - 1u));
+            for(u32 x = t; x < (pow2 >> 1); x += BLK_THREADS) {
+                const u32 i = 2u * x - (x & (j - 1u));
                 const u32 p = i + j;
                 const u32 a = keys[i], b = keys[p];
                 if((a > b) == ((i & k) == 0u)) {
@@ -653,8 +654,8 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_fwd(const u8* __restrict
     u16* half = tmp + BLK_N / 2u;
     while(distinct < BLK_N && h < BLK_N) {
         const u32 active = blk_count_active(fbits, misc);
-        if(active <= 2048u) {
-            blk_sort_tiny(active, sa, rk, fbits, h, reinterpret_cast<u32*>(half), half + 4096u, tmp, misc);
+        if(active <= BLK_TINY) {
+            blk_sort_tiny(active, sa, rk, fbits, h, reinterpret_cast<u32*>(half), half + 2u * BLK_TINY, tmp, misc);
             distinct += blk_place_short(active, tmp, sa, rk, fbits, h, lb, lb + 512u, misc);
             nrounds += 0x100u;
         } else if(active > BLK_N / 2u) {
