@@ -8,7 +8,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 SO = PKG / "libb2rc.so"
 
-OK, E_ARG, E_DST_SMALL, E_CORRUPT, E_CUDA, E_EXPAND, E_NOMEM = 0, -1, -2, -3, -4, -5, -6
+OK, E_ARG, E_DST_SMALL, E_CORRUPT, E_CUDA, E_EXPAND, E_NOMEM, E_INTERNAL = 0, -1, -2, -3, -4, -5, -6, -7
 MODE_STATIC, MODE_ADAPTIVE = 0, 1
 MODE_RANS_BYTE, MODE_RANS_WORD = 2, 3  # cppans::rANS::encode / ::encode_simd
 MODE_NAMES = {"static": 0, "adaptive": 1, "rans": 2, "rans-word": 3}

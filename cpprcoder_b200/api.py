@@ -78,7 +78,8 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.b2rc_launch_count(self.h))
 
-    KERNELS = {"histogram": 0, "encode": 1, "scan": 2, "compact": 3, "decode": 4, "blk_forward": 5, "blk_inverse": 6}
+    KERNELS = {"histogram": 0, "encode": 1, "scan": 2, "compact": 3, "decode": 4, "blk_forward": 5, "blk_inverse": 6,
+               "ranges": 7, "seams": 8}
 
     @staticmethod
     def supported_modes() -> tuple:

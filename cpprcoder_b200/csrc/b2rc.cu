@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "b2rc_kernels.cuh"
+#include "b2rc_encseg.cuh"
 #include "b2rc_ans.cuh"
 #include "b2rc_blk.cuh"
 
@@ -58,6 +59,13 @@ struct b2rc_ctx {
     u32 seg_syms;    // restart points of the static coder every so many symbols; env B2RC_RESTART_SYMS (0: none)
     u32* restart;    // device scratch: the table while a container is being written / read
     size_t restart_cap;
+    // segmented static encode (b2rc_encseg.cuh): the range pass's records and the segments' final lows
+    u32* seg_recs;
+    size_t seg_recs_cap;
+    u32* seg_lows;
+    size_t seg_lows_cap;
+    u32 enc_seg_syms;  // symbols per segment of the static encoder; env B2RC_ENC_SEG_SYMS (0: one chain per block, k_enc_static)
+    u32 force_exact;   // env B2RC_FORCE_EXACT=1 (tests): every static block takes the reference-shaped path
     struct Result {
         int err;
         int pad;
@@ -197,6 +205,8 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
     CK(cudaFuncSetAttribute(k_dec_static_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SEG_SMEM));
+    CK(cudaFuncSetAttribute(k_enc_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(false, ENC_SEG_WARPS)));
+    CK(cudaFuncSetAttribute(k_enc_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(true, ENC_SEG_WARPS)));
     CK(cudaFuncSetAttribute(k_ans_dec_byte_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_DEC_BYTE_SEG_SMEM));
     CK(cudaFuncSetAttribute(k_blk_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_FWD_SMEM));
     CK(cudaFuncSetAttribute(k_blk_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_INV_SMEM));
@@ -241,6 +251,9 @@ int map_kernel_err(int bits)
     if(bits & ERR_DST_SMALL) {
         return B2RC_E_DST_SMALL;
     }
+    if(bits & ERR_INTERNAL) {
+        return B2RC_E_INTERNAL;
+    }
     return B2RC_OK;
 }
 
@@ -279,6 +292,7 @@ const char* b2rc_strerror(int code)
     case B2RC_E_CUDA: return "CUDA error or no device";
     case B2RC_E_EXPAND: return "payload outgrew its staging slot";
     case B2RC_E_NOMEM: return "out of device memory";
+    case B2RC_E_INTERNAL: return "internal inconsistency (a segment's bytes did not end where the range pass put them)";
     default: return "unknown";
     }
 }
@@ -361,6 +375,16 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         if(v == 0 || (v >= (long)B2RC_MIN_RESTART_SYMS && v <= (1 << 22) && v % 64 == 0)) {
             ctx->seg_syms = (u32)v;
         }
+    }
+    ctx->enc_seg_syms = 2048;
+    if(const char* e = getenv("B2RC_ENC_SEG_SYMS")) {
+        const long v = atol(e);
+        if(v == 0 || (v >= 64 && v <= (1 << 22) && v % 64 == 0)) {
+            ctx->enc_seg_syms = (u32)v;
+        }
+    }
+    if(const char* e = getenv("B2RC_FORCE_EXACT")) {
+        ctx->force_exact = atol(e) ? 1u : 0u;
     }
     if(const char* e = getenv("B2RC_PHASES")) {
         const long v = atol(e);
@@ -480,6 +504,8 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     }
     cudaFree(ctx->dec_state);
     cudaFree(ctx->restart);
+    cudaFree(ctx->seg_recs);
+    cudaFree(ctx->seg_lows);
     cudaFree(ctx->dec_model);
     cudaFree(ctx->d_ends);
     if(ctx->h_ends) {
@@ -911,6 +937,96 @@ static int decode_launch(b2rc_ctx* ctx, int mode, uint32_t block_size, const uin
     return launch_check(ctx, "k_dec");
 }
 
+
+// ------------------------------------------- segmented static encode (b2rc_encseg.cuh) --
+// Symbols per segment for this block size; it must divide the restart spacing so that every
+// restart point is a segment start.  0: this context codes one chain per block (k_enc_static).
+static u32 enc_seg_plan(const b2rc_ctx* ctx, u32 block, u32 restart_seg)
+{
+    u32 P = ctx->enc_seg_syms;
+    if(P == 0) {
+        return 0;
+    }
+    if(restart_seg) {
+        while(restart_seg % P) {
+            P -= 64;
+        }
+    }
+    return P < block ? P : block;
+}
+
+static int seg_scratch(b2rc_ctx* ctx, u64 nb, u32 block, u32 P)
+{
+    const u64 nseg = (block + P - 1) / P;
+    int rc;
+    if((rc = grow(ctx, ctx->seg_recs, ctx->seg_recs_cap, (size_t)(nb * (nseg + 1) * 8 + 16))) != B2RC_OK ||
+       (rc = grow(ctx, ctx->seg_lows, ctx->seg_lows_cap, (size_t)(nb * nseg * 4 + 16))) != B2RC_OK) {
+        return rc;
+    }
+    return B2RC_OK;
+}
+
+// `first` = index of the range's first block in the context's scratch (chunked host pipeline)
+static SegArgs seg_args(b2rc_ctx* ctx, u32 block, u32 P, const u8* d_src, u64 n, const u16* freq, u64 first, u32* d_sizes,
+                        const u64* d_offsets, u8* d_payload, u64 payload_cap, u32* d_restart, u32 seg)
+{
+    SegArgs a;
+    a.src = d_src;
+    a.n = n;
+    a.block = block;
+    a.nblocks = b2rc_nblocks(n, block);
+    a.freq16 = freq;
+    a.P = P;
+    a.nseg = (block + P - 1) / P;
+    a.recs = ctx->seg_recs + first * (u64)(a.nseg + 1) * 2;
+    a.lows = ctx->seg_lows + first * (u64)a.nseg;
+    a.sizes = d_sizes;
+    a.offsets = d_offsets;
+    a.payload = d_payload;
+    a.payload_cap = payload_cap;
+    a.restart = d_restart;
+    a.seg_syms = d_restart ? seg : 0u;
+    a.err = ctx->d_err;
+    a.force_exact = ctx->force_exact;
+    return a;
+}
+
+// K2r: sizes of all payloads (and where every segment starts), before a byte is coded
+static int static_ranges_launch(b2rc_ctx* ctx, const SegArgs& a, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((a.nblocks + 31) / 32);
+    KernelTimer kt(ctx, B2RC_K_RANGES, st);
+    if(a.block > 65536u) {
+        k_enc_ranges<true><<<grid, 32, ENC_RANGES_SMEM, st>>>(a);
+    } else {
+        k_enc_ranges<false><<<grid, 32, ENC_RANGES_SMEM, st>>>(a);
+    }
+    return launch_check(ctx, "k_enc_ranges");
+}
+
+// K2s + K2m: the segments into their final place, then the seams
+static int static_segments_launch(b2rc_ctx* ctx, const SegArgs& a, cudaStream_t st)
+{
+    const u32 warps = a.nseg < ENC_SEG_WARPS ? a.nseg : ENC_SEG_WARPS;
+    const dim3 grid((unsigned)((a.nblocks + 31) / 32), (a.nseg + warps - 1) / warps);
+    const bool wide = a.block > 65536u;
+    {
+        KernelTimer kt(ctx, B2RC_K_ENCODE, st);
+        if(wide) {
+            k_enc_seg<true><<<grid, 32 * warps, enc_seg_smem(true, warps), st>>>(a);
+        } else {
+            k_enc_seg<false><<<grid, 32 * warps, enc_seg_smem(false, warps), st>>>(a);
+        }
+        const int rc = launch_check(ctx, "k_enc_seg");
+        if(rc != B2RC_OK) {
+            return rc;
+        }
+    }
+    KernelTimer kt(ctx, B2RC_K_SEAMS, st);
+    k_enc_seams<<<(unsigned)((a.nblocks + SEAM_THREADS - 1) / SEAM_THREADS), SEAM_THREADS, 0, st>>>(a);
+    return launch_check(ctx, "k_enc_seams");
+}
+
 // ------------------------------------------------------ container, device --
 int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
                        uint8_t* d_dst, uint64_t dst_cap, uint64_t* out_n, void* cuda_stream)
@@ -930,8 +1046,12 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const u64 stride = b2rc_slot_bytes_for(mode, block_size);
+    const u32 seg = nb ? seg_for(ctx, mode, block_size) : 0u;
+    // static coder: many chains per block, coded straight into the container (b2rc_encseg.cuh)
+    const u32 P = (mode == B2RC_MODE_STATIC && nb) ? enc_seg_plan(ctx, block_size, seg) : 0u;
     int rc;
-    if((rc = grow(ctx, ctx->slots, ctx->slots_cap, (size_t)(nb * stride))) != B2RC_OK ||
+    if((!P && (rc = grow(ctx, ctx->slots, ctx->slots_cap, (size_t)(nb * stride))) != B2RC_OK) ||
+       (P && (rc = seg_scratch(ctx, nb, block_size, P)) != B2RC_OK) ||
        (rc = grow(ctx, ctx->sizes, ctx->sizes_cap, (size_t)(nb * 4 + 16))) != B2RC_OK) {
         return rc;
     }
@@ -939,30 +1059,41 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
     if(need_hist && (rc = grow(ctx, ctx->freq16, ctx->freq_cap, (size_t)(nb * 512 + 16))) != B2RC_OK) {
         return rc;
     }
-    const u32 seg = nb ? seg_for(ctx, mode, block_size) : 0u;
     const u64 table_words = seg ? nb * 3ull * b2rc_restart_records(block_size, seg) : 0ull;
     if(seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(table_words * 4 + 16))) != B2RC_OK) {
         return rc;
     }
     CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
-    if(nb) {
-        if(need_hist && (rc = b2rc_k_histogram(ctx, d_src, n, block_size, ctx->freq16, st)) != B2RC_OK) {
+    u64* d_offsets = reinterpret_cast<u64*>(d_dst + B2RC_HEADER_BYTES);
+    if(P) {
+        const SegArgs a = seg_args(ctx, block_size, P, d_src, n, ctx->freq16, 0, ctx->sizes, d_offsets, d_dst + idx,
+                                   dst_cap - idx, seg ? ctx->restart : nullptr, seg);
+        if((rc = b2rc_k_histogram(ctx, d_src, n, block_size, ctx->freq16, st)) != B2RC_OK ||
+           (rc = static_ranges_launch(ctx, a, st)) != B2RC_OK ||
+           (rc = scan_launch(ctx, ctx->sizes, nb, d_offsets, ctx->d_total, d_dst, (u32)mode, block_size, n, st, nullptr,
+                             flags_of(seg))) != B2RC_OK ||
+           (rc = static_segments_launch(ctx, a, st)) != B2RC_OK) {
             return rc;
         }
-        if((rc = b2rc_k_encode_blocks_r(ctx, mode, block_size, d_src, n, need_hist ? ctx->freq16 : nullptr, ctx->slots,
-                                        stride, ctx->sizes, seg ? ctx->restart : nullptr, seg, ctx->d_err, st)) !=
-           B2RC_OK) {
+    } else {
+        if(nb) {
+            if(need_hist && (rc = b2rc_k_histogram(ctx, d_src, n, block_size, ctx->freq16, st)) != B2RC_OK) {
+                return rc;
+            }
+            if((rc = b2rc_k_encode_blocks_r(ctx, mode, block_size, d_src, n, need_hist ? ctx->freq16 : nullptr, ctx->slots,
+                                            stride, ctx->sizes, seg ? ctx->restart : nullptr, seg, ctx->d_err, st)) !=
+               B2RC_OK) {
+                return rc;
+            }
+        }
+        if((rc = scan_launch(ctx, ctx->sizes, nb, d_offsets, ctx->d_total, d_dst, (u32)mode, block_size, n, st, nullptr,
+                             flags_of(seg))) != B2RC_OK) {
             return rc;
         }
-    }
-    if((rc = scan_launch(ctx, ctx->sizes, nb, reinterpret_cast<u64*>(d_dst + B2RC_HEADER_BYTES), ctx->d_total, d_dst,
-                         (u32)mode, block_size, n, st, nullptr, flags_of(seg))) != B2RC_OK) {
-        return rc;
-    }
-    if(nb && (rc = b2rc_k_compact_for(ctx, mode, ctx->slots, stride, ctx->sizes,
-                                      reinterpret_cast<const u64*>(d_dst + B2RC_HEADER_BYTES), nb, d_dst + idx,
-                                      dst_cap - idx, ctx->d_err, st)) != B2RC_OK) {
-        return rc;
+        if(nb && (rc = b2rc_k_compact_for(ctx, mode, ctx->slots, stride, ctx->sizes, d_offsets, nb, d_dst + idx,
+                                          dst_cap - idx, ctx->d_err, st)) != B2RC_OK) {
+            return rc;
+        }
     }
     if(seg) {
         k_put_table<<<148, 256, 0, st>>>(ctx->restart, table_words, d_dst + idx, ctx->d_total, dst_cap - idx, ctx->d_err);
@@ -1099,13 +1230,15 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     const bool need_hist = mode == B2RC_MODE_STATIC;
     const u32 seg = nb ? seg_for(ctx, mode, block_size) : 0u;
     const u32 nrec = seg ? b2rc_restart_records(block_size, seg) : 0u;
+    const u32 P = (mode == B2RC_MODE_STATIC && nb) ? enc_seg_plan(ctx, block_size, seg) : 0u;  // b2rc_encseg.cuh
     int rc;
     if(seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(nb * nrec * 12ull + 16))) != B2RC_OK) {
         return rc;
     }
     if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
        (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(bound + 16))) != B2RC_OK ||
-       (rc = grow(ctx, ctx->slots, ctx->slots_cap, (size_t)(nb * stride))) != B2RC_OK ||
+       (!P && (rc = grow(ctx, ctx->slots, ctx->slots_cap, (size_t)(nb * stride))) != B2RC_OK) ||
+       (P && (rc = seg_scratch(ctx, nb, block_size, P)) != B2RC_OK) ||
        (rc = grow(ctx, ctx->sizes, ctx->sizes_cap, (size_t)(nb * 4 + 16))) != B2RC_OK ||
        (need_hist && (rc = grow(ctx, ctx->freq16, ctx->freq_cap, (size_t)(nb * 512 + 16))) != B2RC_OK)) {
         return rc;
@@ -1133,9 +1266,17 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         if(need_hist && (rc = b2rc_k_histogram(ctx, ctx->stage_in + byte0, bytes, block_size, freq, st)) != B2RC_OK) {
             return rc;
         }
-        if((rc = b2rc_k_encode_blocks_r(ctx, mode, block_size, ctx->stage_in + byte0, bytes, freq,
-                                        ctx->slots + b0 * stride, stride, ctx->sizes + b0,
-                                        seg ? ctx->restart + b0 * nrec * 3ull : nullptr, seg, ctx->d_err, st)) != B2RC_OK) {
+        SegArgs sa;
+        if(P) {  // sizes first (the range pass), the payloads then go straight to their final place
+            sa = seg_args(ctx, block_size, P, ctx->stage_in + byte0, bytes, freq, b0, ctx->sizes + b0, d_offsets + b0,
+                          d_payload, bound - idx, seg ? ctx->restart + b0 * nrec * 3ull : nullptr, seg);
+            if((rc = static_ranges_launch(ctx, sa, st)) != B2RC_OK) {
+                return rc;
+            }
+        } else if((rc = b2rc_k_encode_blocks_r(ctx, mode, block_size, ctx->stage_in + byte0, bytes, freq,
+                                               ctx->slots + b0 * stride, stride, ctx->sizes + b0,
+                                               seg ? ctx->restart + b0 * nrec * 3ull : nullptr, seg, ctx->d_err, st)) !=
+                  B2RC_OK) {
             return rc;
         }
         if(c > 0) {
@@ -1146,8 +1287,13 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
             return rc;
         }
         CK(cudaEventRecord(ctx->scan_done[c], st));
-        if((rc = b2rc_k_compact_for(ctx, mode, ctx->slots + b0 * stride, stride, ctx->sizes + b0, d_offsets + b0,
-                                    b1 - b0, d_payload, bound - idx, ctx->d_err, st)) != B2RC_OK) {
+        if(P) {
+            rc = static_segments_launch(ctx, sa, st);
+        } else {
+            rc = b2rc_k_compact_for(ctx, mode, ctx->slots + b0 * stride, stride, ctx->sizes + b0, d_offsets + b0, b1 - b0,
+                                    d_payload, bound - idx, ctx->d_err, st);
+        }
+        if(rc != B2RC_OK) {
             return rc;
         }
         CK(cudaMemcpyAsync(ctx->h_ends + c + 1, ctx->d_ends + c + 1, 8, cudaMemcpyDeviceToHost, st));

@@ -706,3 +706,145 @@ RC_HD void rc_model_decode(Tab& tab, u32 low, u32 t, u32& sym, u32& cum, u32& fr
     cum = base;
     freq = 1u + v;
 }
+
+// ================================================== segmented static encode ==
+// RangeEncoder::encode (cpprcoder.h:400-457) as MANY chains per block.  `range` never
+// depends on `low` (cpprcoder.h:401-404: t = range / total; low += cum * t; range = freq * t),
+// so a range-only pass (rc_range_step*) knows, for every P-th symbol, the range there and how
+// many bytes the coder has shifted out by then.  A segment then codes its P symbols from low = 0
+// straight into the bytes of the payload that are its own; the coded bytes are one big-endian sum
+// of terms, so the payload is the sum of the segments' outputs: the four bytes of `low` a segment
+// is left with overlap the first four bytes of the next segment's output and are added there
+// afterwards (rc_seam_add), carry and all.
+//
+// Byte positions, in coded-stream coordinates (byte 0 = the reference's initial buffer_ = 0,
+// always 0 in the result): a segment that starts after S bytes have been shifted out owns
+// [S + 1, S' + 1), S' the same count at its end; the last segment also owns the final four bytes
+// of low: [S + 1, S_total + 5).  Payload size = header + 5 + S_total, known before a byte is coded.
+
+// One link of the range-only chain; returns the renormalisation shift in bits.
+template <int MAXSH>
+RC_HD u32 rc_range_step(u32& range, u32 freq, u32 t)
+{
+    const u32 r = freq * t;
+    const u32 sh = rc_norm_shift<MAXSH>(r);
+    range = r << sh;
+    return sh;
+}
+// The same for a power-of-two total: the chain carries t = range >> shift (see rc_enc_step_pow2).
+template <int MAXSH>
+RC_HD u32 rc_range_step_pow2(u32& t, u32 shift, u32 freq)
+{
+    const u32 r = freq * t;
+    const u32 sh = rc_norm_shift<MAXSH>(r);
+    t = (r << sh) >> shift;
+    return sh;
+}
+
+// Sink of one segment: aligned 4-byte words of the destination, which the segment shares with its
+// neighbours at both ends.  The shift register starts with as many phantom (zero) bytes as the
+// segment's first byte lies behind a word boundary, so every word it cuts is a destination word.
+// Words that lie wholly inside the segment's own bytes are stored whole on the hot path; the
+// first and last words go through the checked sink, which stores own bytes only.
+struct RcSegSinkChecked;
+struct RcSegSink {
+    typedef RcSegSinkChecked Checked;
+    u32* out;     // the aligned word that holds the segment's first own byte
+    s32 wcount;   // index of the next word; -1: the encoder's placeholder push is still to come
+    u32 hot_lim;  // words wcount .. wcount+3 are whole own words  <=>  (u32)(wcount - 1) < hot_lim
+    u32 lo, hi;   // own bytes, as offsets from `out`: [lo, hi), lo < 4
+    RC_HD bool tight(int) const { return !((u32)(wcount - 1) < hot_lim); }
+    RC_HD void push(u32 w)
+    {
+        out[wcount] = rc_bswap(w);
+        ++wcount;
+    }
+};
+struct RcSegSinkChecked {
+    RcSegSink s;
+    RC_HD explicit RcSegSinkChecked(const RcSegSink& r) : s(r) {}
+    RC_HD void push(u32 w)
+    {
+        if(s.wcount >= 0) {
+            const u32 at = 4u * (u32)s.wcount;
+            if(at >= s.lo && at + 4u <= s.hi) {
+                s.out[s.wcount] = rc_bswap(w);
+            } else {
+                u8* ob = reinterpret_cast<u8*>(s.out);
+                for(u32 k = 0; k < 4u; ++k) {
+                    if(at + k >= s.lo && at + k < s.hi) {
+                        ob[at + k] = (u8)(w >> (24u - 8u * k));
+                    }
+                }
+            }
+        }
+        ++s.wcount;
+    }
+    RC_HD void settle(RcSegSink& r) { r.wcount = s.wcount; }
+};
+
+// Start of a segment whose first own byte is *first and which owns `nbytes` bytes.
+RC_HD void rc_seg_begin(RcEnc& e, RcSegSink& s, u8* first, u32 nbytes, u32 range0)
+{
+    const u32 ph = (u32)((uintptr_t)first & 3u);
+    s.out = reinterpret_cast<u32*>(first - ph);
+    s.wcount = -1;
+    s.lo = ph;
+    s.hi = ph + nbytes;
+    s.hot_lim = (s.hi >> 2) >= 4u ? (s.hi >> 2) - 4u : 0u;
+    e.low = 0;
+    e.range = range0;
+    e.o_lo = 0;
+    e.o_hi = 0;
+    e.ocnt = (s32)(8u * ph);  // phantom bytes: they belong to whoever owns the bytes in front
+    e.pend = 0;
+    e.nff = 0;
+}
+
+// End of a segment: the deferred words, then the bytes that do not fill a word; the last segment
+// of a block also writes the four bytes of low (cpprcoder.h:453-456).  Returns false when the
+// bytes written do not end where the range-only pass said they would.
+RC_HD bool rc_seg_end(RcEnc& e, RcSegSink& s, bool last)
+{
+    RcSegSinkChecked cs(s);
+    u8 tail[8];
+    const u32 nt = rc_enc_finish(e, cs, tail);
+    const u32 at = 4u * (u32)cs.s.wcount;
+    const u32 nw = last ? nt : nt - 4u;
+    u8* ob = reinterpret_cast<u8*>(s.out);
+    for(u32 k = 0; k < nw; ++k) {
+        if(at + k >= s.lo && at + k < s.hi) {
+            ob[at + k] = tail[k];
+        }
+    }
+    s.wcount = cs.s.wcount;
+    return at + nw == s.hi;
+}
+
+// (big-endian 32 bits at p) += tail; a carry runs towards lower addresses through 0xFF bytes
+// (the reference's buffer_ / count_ bookkeeping, cpprcoder.h:405-416, done after the fact).
+// It never runs past the first coded byte: every partial sum is below the full one.
+RC_HD void rc_seam_add(u8* p, u32 tail)
+{
+    const u32 have = ((u32)p[0] << 24) | ((u32)p[1] << 16) | ((u32)p[2] << 8) | (u32)p[3];
+    const u32 sum = have + tail;
+    p[0] = (u8)(sum >> 24);
+    p[1] = (u8)(sum >> 16);
+    p[2] = (u8)(sum >> 8);
+    p[3] = (u8)sum;
+    if(sum < have) {
+        u8* q = p - 1;
+        while(*q == 0xFFu) {
+            *q = 0;
+            --q;
+        }
+        *q = (u8)(*q + 1u);
+    }
+}
+
+// The encoder's 32-bit low at the end of a segment that shifted `d` bytes out, from its own
+// final low and the low at its start (what a restart point records).
+RC_HD u32 rc_seam_low(u32 low_before, u32 own_low, u32 d)
+{
+    return own_low + (d >= 4u ? 0u : (low_before << (8u * d)));
+}

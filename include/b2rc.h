@@ -63,6 +63,7 @@ extern "C" {
                                 the reference fails the same way when its MemoryStream is full
                                 (cpprcoder.h:409-411, :1047-1051) */
 #define B2RC_E_NOMEM (-6)
+#define B2RC_E_INTERNAL (-7) /* the library contradicted itself (a bug); nothing usable was written */
 
 typedef struct b2rc_ctx b2rc_ctx;
 
@@ -165,7 +166,9 @@ uint64_t b2rc_launch_count(const b2rc_ctx* ctx);
 #define B2RC_K_DECODE 4
 #define B2RC_K_BLK_FORWARD 5
 #define B2RC_K_BLK_INVERSE 6
-#define B2RC_K_COUNT 7
+#define B2RC_K_RANGES 7 /* static encode: the range-only pass (sizes up front) */
+#define B2RC_K_SEAMS 8  /* static encode: the seams between segments */
+#define B2RC_K_COUNT 9
 int b2rc_profile(b2rc_ctx* ctx, int enable);
 int b2rc_kernel_ms(b2rc_ctx* ctx, int which, float* ms);
 /* ------------------------------------------------------------------ block sort --

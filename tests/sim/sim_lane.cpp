@@ -235,6 +235,117 @@ long sim_encode_restart(const u8* src, u32 n, u8* dst, size_t cap, u32 seg, u32 
     return (long)out.size();
 }
 
+// Static encode as the segmented kernels do it (rc_lane.cuh, "segmented static encode"): a range-only
+// pass records, before every P-th symbol, the bytes shifted out so far and the range; every segment
+// is then coded from low = 0 straight into its own bytes of the payload at dst + lead (any
+// alignment; dst itself 4-byte aligned), LAST SEGMENT FIRST so that a segment that touched a
+// neighbour's bytes would be found out; the seams are added afterwards.  rec as in
+// sim_encode_restart (restart points every `seg` symbols, seg a multiple of P).  Returns the
+// payload size, -1 no room, -2 flush quirk, -3 a segment did not end where the range pass said.
+long sim_encode_segmented(const u8* src, u32 n, u8* dst, size_t cap, u32 lead, u32 P, u32 seg, u32 nrec, u32* rec)
+{
+    for(u32 i = 0; i < 3 * nrec; ++i) {
+        rec[i] = 0xFFFFFFFFu;
+    }
+    u32 freq[256], cum[257];
+    count64k(src, n, freq);
+    u32 run = 0;
+    for(int s2 = 0; s2 < 256; ++s2) {
+        cum[s2] = run;
+        run += freq[s2];
+    }
+    cum[256] = run;
+    const u32 total = run, magic = rc_magic(total);
+    const bool pow2 = total && (total & (total - 1)) == 0;
+    const u32 shT = pow2 ? 31u - rc_clz(total) : 0;
+    const u32 nseg = n ? (n + P - 1) / P : 1;
+    // ---- the range-only pass
+    std::vector<u32> S(nseg + 1), R(nseg + 1);
+    {
+        u32 range = RC_STATIC_RANGE0, t = pow2 ? (range >> shT) : 0, bits = 0;
+        for(u32 i = 0; i < n; ++i) {
+            if(i % P == 0) {
+                S[i / P] = bits / 8;
+                R[i / P] = pow2 ? (t << shT) : range;
+            }
+            const u32 f = cum[src[i] + 1] - cum[src[i]];
+            if(pow2) {
+                bits += rc_range_step_pow2<2>(t, shT, f);
+            } else {
+                bits += rc_range_step<3>(range, f, rc_div(range, total, magic));
+            }
+        }
+        if(n == 0) {
+            S[0] = 0;
+            R[0] = RC_STATIC_RANGE0;
+        }
+        S[nseg] = bits / 8;
+    }
+    const size_t size = RC_STATIC_HDR + 5u + S[nseg];
+    if(lead + size > cap) {
+        return -1;
+    }
+    u8* pay = dst + lead;
+    memset(pay, 0xAA, size);  // every byte must be written by somebody
+    for(int k = 0; k < 4; ++k) {
+        pay[k] = (u8)(n >> (8 * k));
+    }
+    for(int s2 = 0; s2 < 256; ++s2) {
+        pay[4 + 2 * s2] = (u8)freq[s2];
+        pay[5 + 2 * s2] = (u8)(freq[s2] >> 8);
+    }
+    u8* coded = pay + RC_STATIC_HDR;
+    coded[0] = 0;  // the reference's initial buffer_ (cpprcoder.h:385): written with the header
+    // ---- the segments, last first
+    std::vector<u32> lows(nseg);
+    for(u32 j = nseg; j-- > 0;) {
+        const bool last = j + 1 == nseg;
+        const u32 own = (last ? S[nseg] + 5u : S[j + 1] + 1u) - (S[j] + 1u);
+        RcEnc e;
+        RcSegSink sink;
+        rc_seg_begin(e, sink, coded + S[j] + 1u, own, R[j]);
+        u32 t = pow2 ? (e.range >> shT) : 0;
+        const u32 hi = (j + 1) * P < n ? (j + 1) * P : n;
+        for(u32 i = j * P; i < hi; i += 4) {
+            RcCut cuts[4];
+            for(u32 k = 0; k < 4; ++k) {
+                const bool active = i + k < hi;
+                const u32 c = active ? src[i + k] : 0;
+                if(pow2) {
+                    rc_enc_step_pow2<2>(e, t, shT, cum[c], cum[c + 1] - cum[c], cuts[k], active);
+                } else {
+                    const u32 tt = active ? rc_div(e.range, total, magic) : 0;
+                    rc_enc_step<3>(e, cum[c], cum[c + 1] - cum[c], tt, cuts[k], active);
+                }
+            }
+            rc_enc_commit(e, cuts, sink);
+        }
+        if(!rc_seg_end(e, sink, last)) {
+            return -3;
+        }
+        lows[j] = e.low;
+    }
+    // ---- the seams, in order, and the restart points
+    u32 low = 0;
+    for(u32 j = 0; j < nseg; ++j) {
+        low = rc_seam_low(low, lows[j], S[j + 1] - S[j]);
+        if(j + 1 < nseg) {
+            rc_seam_add(coded + S[j + 1] + 1u, lows[j]);
+            const u32 at = (j + 1) * P;
+            if(seg && at % seg == 0 && at / seg - 1 < nrec) {
+                u32* r = rec + 3 * (at / seg - 1);
+                r[0] = S[j + 1];
+                r[1] = low;
+                r[2] = R[j + 1];
+            }
+        }
+    }
+    if(low == 0xFFFFFFFFu) {
+        return -2;
+    }
+    return (long)size;
+}
+
 // Static decode of symbols [k, k + count) from a restart point (m, low, range) of sim_encode_restart.
 long sim_decode_from(const u8* stream, size_t stream_len, u32 lead, u32 k, u32 m, u32 enc_low, u32 range, u32 count,
                      u8* dst)

@@ -1,0 +1,149 @@
+"""The static encoder as many chains per block (cpprcoder_b200/csrc/b2rc_encseg.cuh: range pass,
+segments coded straight into the container, seams), through the C ABI against the oracle, and
+against the one-chain kernel it replaces (same containers, byte for byte, restart table included)."""
+import os
+
+import numpy as np
+import pytest
+
+from _cases import crafted, crafted_stream
+from _oracle import STATIC, Oracle
+from cpprcoder_b200 import container, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ctx(**env):
+    """A context created under the given B2RC_* environment (read once, at creation)."""
+    from cpprcoder_b200 import api
+    saved = {k: os.environ.get(k) for k in env}
+    try:
+        for k, v in env.items():
+            os.environ[k] = str(v)
+        return api.Context(0)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.fixture(scope="module")
+def oracle(built):
+    built.build_native()
+    return Oracle.get()
+
+
+@pytest.fixture(scope="module")
+def one_chain(oracle):
+    c = make_ctx(B2RC_ENC_SEG_SYMS=0)  # k_enc_static: one chain per block, staging slots, compaction
+    yield c
+    c.close()
+
+
+def payloads(buf):
+    info = container.parse(buf)
+    return [bytes(info.payload(buf, b)) for b in range(info.nblocks)]
+
+
+@pytest.mark.parametrize("P", [64, 512, 2048, 8192])
+@pytest.mark.parametrize("block,nblocks,ragged", [(65536, 37, 4321), (65536, 32, 0), (4096, 70, 1), (16384, 33, 16383),
+                                                  (64, 100, 7), (262144, 5, 70000)])
+def test_segments_give_the_reference_payloads(oracle, one_chain, P, block, nblocks, ragged):
+    import torch
+    data = crafted_stream(nblocks, block, seed=7 * block + P, ragged=ragged)
+    want = oracle.encode_blocks(STATIC, data, block, threads=4)
+    ctx = make_ctx(B2RC_ENC_SEG_SYMS=P)
+    try:
+        host = ctx.encode(STATIC, data, block)                       # chunked host pipeline
+        assert payloads(host) == want
+        enc, used = ctx.encode_device(STATIC, torch.from_numpy(data).cuda(), block=block)
+        dev = enc[:used].cpu().numpy()
+        assert dev.tobytes() == host.tobytes()
+        # the same container as the one-chain kernel writes, restart points and all
+        assert one_chain.encode(STATIC, data, block).tobytes() == host.tobytes()
+        assert ctx.decode(host).tobytes() == data.tobytes()
+    finally:
+        ctx.close()
+
+
+def test_every_alignment_of_the_payloads(oracle):
+    """Payload offsets take every residue mod 4 (sizes are data dependent); a canary behind the
+    container stays intact and the bound is respected."""
+    import torch
+    rng = np.random.default_rng(5)
+    ctx = make_ctx(B2RC_ENC_SEG_SYMS=256)
+    try:
+        for it in range(6):
+            block = int(rng.choice([1024, 4096, 65536]))
+            data = np.concatenate([crafted(int(k) % 7, block, rng) for k in rng.integers(0, 7, 40)] +
+                                  [crafted(2, int(rng.integers(1, block)), rng)])
+            src = torch.from_numpy(data).cuda()
+            from cpprcoder_b200 import api
+            bound = api.bound(STATIC, data.size, block)
+            dst = torch.full((bound + 64,), 0x5A, dtype=torch.uint8, device="cuda")
+            _, used = ctx.encode_device(STATIC, src, dst[:bound], block=block)
+            out = dst.cpu().numpy()
+            assert (out[used:] == 0x5A).all()
+            info = container.parse(out[:used])
+            assert {int(o) % 4 for o in info.offsets[:-1]} == {0, 1, 2, 3}
+            assert payloads(out[:used]) == oracle.encode_blocks(STATIC, data, block, threads=4)
+    finally:
+        ctx.close()
+
+
+def test_reference_shaped_path_of_the_flush_quirk(oracle):
+    """low_ == 0xFFFFFFFF at the end of a block (cpprcoder.h:439-451) happens once in 2^32 blocks;
+    B2RC_FORCE_EXACT sends every block down that path, which must give the reference's bytes too."""
+    data = crafted_stream(35, 65536, seed=11, ragged=999)
+    ctx = make_ctx(B2RC_FORCE_EXACT=1)
+    plain = make_ctx()
+    try:
+        enc = ctx.encode(STATIC, data, 65536)
+        assert payloads(enc) == oracle.encode_blocks(STATIC, data, 65536, threads=4)
+        assert enc.tobytes() == plain.encode(STATIC, data, 65536).tobytes()   # the restart points as well
+        assert plain.decode(enc).tobytes() == data.tobytes()
+    finally:
+        ctx.close()
+        plain.close()
+
+
+def test_destination_too_small_is_reported_and_respected(oracle):
+    import torch
+    from cpprcoder_b200._lib import B2rcError, E_DST_SMALL
+    data = synth.zipf(40 * 65536)
+    src = torch.from_numpy(data).cuda()
+    ctx = make_ctx()
+    try:
+        _, used = ctx.encode_device(STATIC, src)
+        dst = torch.full((used + 64,), 0x5A, dtype=torch.uint8, device="cuda")
+        cap = used - 100000
+        with pytest.raises(B2rcError) as e:
+            ctx.encode_device(STATIC, src, dst[:cap])
+        assert e.value.code == E_DST_SMALL
+        assert (dst[cap:].cpu().numpy() == 0x5A).all()
+    finally:
+        ctx.close()
+
+
+def test_full_size_every_block_hash(oracle):
+    """256 MiB + a ragged tail: EVERY payload against the oracle's (hashes of all 4097 blocks)."""
+    import torch
+    from _oracle import fnv1a64
+    n = (1 << 28) + 4321
+    data = synth.zipf(n)
+    ctx = make_ctx()
+    try:
+        enc, used = ctx.encode_device(STATIC, torch.from_numpy(data).cuda())
+        head = enc[:used].cpu().numpy()
+        got = payloads(head)
+        want = oracle.encode_blocks(STATIC, data, 65536, threads=os.cpu_count() or 4)
+        assert len(got) == len(want)
+        bad = [b for b in range(len(got)) if got[b] != want[b]]
+        assert not bad, bad[:10]
+        dst = torch.empty(n, dtype=torch.uint8, device="cuda")
+        assert ctx.decode_device(enc, used, dst) == n
+        assert torch.equal(dst.cpu(), torch.from_numpy(data))
+    finally:
+        ctx.close()

@@ -160,3 +160,51 @@ def test_static_restart_points(sim):
                                      got.ctypes.data_as(C.c_void_p))
             assert rr == count
             assert got.tobytes() == d[k:k + count].tobytes(), (it, n, j)
+
+
+# ---- static encode as many chains per block (range-only pass, segments from low = 0, seams) ----
+def test_segmented_static_encode_matches_oracle(sim):
+    """The CPU model of k_enc_ranges / k_enc_seg / k_enc_seams: every payload equals the oracle's at
+    every alignment, and the restart points equal those of the one-chain encoder."""
+    sim.sim_encode_segmented.restype = C.c_long
+    sim.sim_encode_segmented.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32,
+                                         C.c_uint32, C.c_uint32, C.c_void_p]
+    sim.sim_encode_restart.restype = C.c_long
+    sim.sim_encode_restart.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p]
+    o = Oracle.get()
+    rng = np.random.default_rng(33)
+    quirks = 0
+    for it in range(160):
+        n = 65536 if it % 2 == 0 else int(rng.integers(1, 65537))
+        d = np.ascontiguousarray(crafted(it % 7, n, rng))
+        P = int(rng.choice([64, 128, 256, 1024, 2048, 8192]))
+        seg = P * int(rng.choice([1, 2, 4]))
+        nrec = (65536 + seg - 1) // seg - 1
+        lead = int(rng.integers(0, 8))
+        cap = slot_bytes(n) + 2 * n + 16
+        out = np.full(cap, 0x5C, np.uint8)
+        rec = np.zeros(3 * max(nrec, 1), np.uint32)
+        r = sim.sim_encode_segmented(d.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), cap, lead, P, seg,
+                                     nrec, rec.ctypes.data_as(C.c_void_p))
+        if r == -2:
+            quirks += 1
+            continue
+        assert r >= 0, (it, n, P, r)
+        want = o.encode(STATIC, d)
+        assert out[lead:lead + r].tobytes() == want, (it, n, P, lead)
+        assert bytes(out[:lead]) == b"\x5c" * lead and out[lead + r] == 0x5C     # nothing outside the payload
+        # the same restart points as the one-chain encoder records
+        nseg = nrec + 1
+        out2 = np.empty(cap, np.uint8)
+        rec2 = np.zeros(3 * max(nrec, 1), np.uint32)
+        if nrec:
+            r2 = sim.sim_encode_restart(d.ctypes.data_as(C.c_void_p), n, out2.ctypes.data_as(C.c_void_p), cap, seg, nseg,
+                                        rec2.ctypes.data_as(C.c_void_p))
+            assert r2 == r
+            for j in range(nrec):
+                a, b = rec[3 * j:3 * j + 3], rec2[3 * j:3 * j + 3]
+                assert a[0] == b[0] and a[1] == b[1], (it, n, P, seg, j, a, b)
+                if a[0] != 0xFFFFFFFF:  # any range with the same range / total serves
+                    tot = int(np.bincount(d, minlength=256).clip(max=0x8000 if n == 65536 else None).sum())
+                    assert int(a[2]) // tot == int(b[2]) // tot
+    assert quirks == 0
