@@ -204,7 +204,8 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
-    CK(cudaFuncSetAttribute(k_dec_static_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SEG_SMEM));
+    CK(cudaFuncSetAttribute(k_dec_static_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(true)));
+    CK(cudaFuncSetAttribute(k_dec_static_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(false)));
     CK(cudaFuncSetAttribute(k_enc_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(false, ENC_SEG_WARPS)));
     CK(cudaFuncSetAttribute(k_enc_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(true, ENC_SEG_WARPS)));
     CK(cudaFuncSetAttribute(k_ans_dec_byte_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_DEC_BYTE_SEG_SMEM));
@@ -342,10 +343,6 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         return B2RC_E_ARG;
     }
     *out = nullptr;
-    // one stream per pipeline chunk: ask for enough hardware queues that they do not alias.
-    // Only effective when this is the process's first CUDA call; callers that initialise CUDA
-    // themselves (PyTorch) should export CUDA_DEVICE_MAX_CONNECTIONS=32 beforehand.
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     if(cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
         cudaGetLastError();
@@ -361,7 +358,20 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
     }
     memset(ctx, 0, sizeof *ctx);
     ctx->device = device;
+    // The host-pointer pipeline gives every chunk a stream of its own.  Streams beyond the number of
+    // hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 unless the PROCESS exported more before its
+    // first CUDA call -- a library must not edit the environment) alias, and one chunk's copy then
+    // waits behind another chunk's kernel: with fewer queues, fewer chunks.
     ctx->max_chunks = B2RC_PIPE_CHUNKS;
+    {
+        long conn = 8;
+        if(const char* e = getenv("CUDA_DEVICE_MAX_CONNECTIONS")) {
+            conn = atol(e);
+        }
+        if(conn < B2RC_PIPE_CHUNKS + 2) {
+            ctx->max_chunks = conn > 4 ? (u64)(conn - 2) : 2;
+        }
+    }
     if(const char* e = getenv("B2RC_PIPE_CHUNKS")) {
         const long v = atol(e);
         if(v >= 1 && v <= B2RC_PIPE_CHUNKS) {
@@ -666,8 +676,8 @@ static int ans_decode_blocks(b2rc_ctx* ctx, int mode, const DecArgs& a, cudaStre
 int b2rc_k_histogram(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint32_t block_size, uint16_t* d_freq16,
                      void* cuda_stream)
 {
-    if(!ctx || !d_src || !d_freq16 || !block_ok(block_size) || !aligned16(d_src) || !aligned16(d_freq16)) {
-        return B2RC_E_ARG;
+    if(!ctx || (n && (!d_src || !d_freq16)) || !block_ok(block_size) || !aligned16(d_src) || !aligned16(d_freq16)) {
+        return B2RC_E_ARG;  // an empty range (a rank without blocks) may come with null pointers
     }
     const u64 nb = b2rc_nblocks(n, block_size);
     if(nb == 0) {
@@ -708,6 +718,9 @@ int b2rc_k_encode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
 {
     if(d_restart && (!has_restart(mode) || !seg_ok(block_size, seg_syms) || ((uintptr_t)d_restart & 3u))) {
         return B2RC_E_ARG;
+    }
+    if(ctx && n == 0 && mode_ok(mode) && block_ok(block_size)) {
+        return B2RC_OK;  // nothing to code: a rank without blocks (world > nblocks) passes null pointers
     }
     if(!ctx || !d_src || !d_slots || !d_sizes || !d_err || !mode_ok(mode) || !block_ok(block_size) ||
        !aligned16(d_src) || !aligned16(d_slots) || (slot_stride & 15u) ||
@@ -869,7 +882,11 @@ int b2rc_k_decode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
         return launch_check(ctx, "k_ans_dec_byte_seg");
     }
     const dim3 grid((unsigned)((nblocks + 31) / 32), (nseg + SEG_WARPS - 1u) / SEG_WARPS);
-    k_dec_static_seg<<<grid, 32 * SEG_WARPS, DEC_SEG_SMEM, st>>>(a);
+    if(block_size <= 65536u) {
+        k_dec_static_seg<true><<<grid, 32 * SEG_WARPS, dec_seg_smem(true), st>>>(a);
+    } else {
+        k_dec_static_seg<false><<<grid, 32 * SEG_WARPS, dec_seg_smem(false), st>>>(a);
+    }
     return launch_check(ctx, "k_dec_static_seg");
 }
 

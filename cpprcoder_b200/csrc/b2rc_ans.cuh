@@ -40,12 +40,6 @@ __device__ __forceinline__ void lds64(u32 a, u32& lo, u32& hi)
 {
     asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
 }
-__device__ __forceinline__ u32 lds8(u32 a)
-{
-    u32 v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
 // little-endian u32 / u16 at a 2-byte aligned address
 __device__ __forceinline__ u32 ld32_a2(const u8* p)
 {

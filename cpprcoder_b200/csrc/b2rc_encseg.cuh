@@ -123,6 +123,94 @@ __device__ __forceinline__ void enc_range_tiles(const SegArgs& a, u32 tiles, u32
     }
 }
 
+// The chain for total == 65536 (every full 64 KiB block that is not one repeated byte), three
+// instructions deep.  It carries u = t - 256, t = range >> 16 in [2^8, 2^16).  With r = freq * t the
+// next t is r >> 16, r >> 8 or r, whichever lies in [2^8, 2^16) (cpprcoder.h:418: shift left by 8
+// while range < 2^24).  Subtracting the lower end of each candidate's home range BEFORE shifting
+//     A = (r - 2^24) >> 16     B = (r - 2^16) >> 8     C = r - 2^8
+// makes the candidate that applies come out as t' - 256 (below 65280) and the others wrap around
+// to 65280 or more, so the next u is the minimum of the three (VIMNMX3) -- no compares, no selects.
+// r - K is one IMAD: freq * u + (256 * freq - K).  The shift counts are recovered off the chain from
+// the leading zero bytes of r.
+__device__ __forceinline__ void range_step16(u32& u, u32& bits, u32 f)
+{
+    // three multiply-adds side by side (not one product and three adds: that is a level more);
+    // a lone warp gets one instruction per pipe every other cycle, so what is off the chain is
+    // spread over the pipes too: the fourth product (r itself, for the shift count) on the multiplier
+    u32 r0, r1, r2, r3, top;
+    const u32 g = f << 8;
+    const u32 k1 = g - 0x01000000u, k2 = g - 0x00010000u, k3 = g - 0x00000100u;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r1) : "r"(f), "r"(u), "r"(k1));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r2) : "r"(f), "r"(u), "r"(k2));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r3) : "r"(f), "r"(u), "r"(k3));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r0) : "r"(f), "r"(u), "r"(g));
+    u = min(min(r1 >> 16, r2 >> 8), r3);
+    // shift = 8 * leading zero bytes of r (2^8 <= r): 24 & (31 - top), top the highest set bit
+    asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(r0));
+    bits += ~top & 24u;
+}
+
+template <bool RAGGED>
+__device__ __forceinline__ void enc_range_tiles16(const SegArgs& a, u32 tiles, u32 ftab, u64 b0, u32 n_b, u32 n_max,
+                                                  u32 lane, u32* rec)
+{
+    u32 u = (RC_STATIC_RANGE0 >> 16) - 256u;
+    u32 bits = 0;
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+    const u32 seg_tiles = a.P / TILE;
+    u32 next_mark = 0;
+#pragma unroll 1
+    for(u32 tix = 0; tix < ntiles; ++tix) {
+        if(tix + 1 < ntiles) {
+            stage_tile(tiles + ((tix + 1) & 1u) * TILE_BYTES, a.src, a.n, b0, a.block, (tix + 1) * TILE, lane);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        if(tix == next_mark) {  // a segment starts here
+            next_mark += seg_tiles;
+            if(tix * TILE < n_b) {
+                const u32 j = tix / seg_tiles;
+                rec[2u * j] = bits >> 3;
+                rec[2u * j + 1u] = (u + 256u) << 16;  // any range with the same range >> 16 serves
+            }
+        }
+        const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
+        // symbols by byte loads (the load pipe is idle, the integer pipe is not); frequencies of the
+        // NEXT four symbols are requested before the current four are chained
+        u32 f[4];
+#pragma unroll
+        for(int k = 0; k < 4; ++k) {
+            f[k] = lds16(ftab + lds8(row + k) * 64u);
+        }
+#pragma unroll 1
+        for(u32 at = row; at != row + TILE; at += 4u) {
+            const u32 nx = at + 4u == row + TILE ? row : at + 4u;
+            u32 nf[4];
+#pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                nf[k] = lds16(ftab + lds8(nx + k) * 64u);
+            }
+#pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                if(!RAGGED || tix * TILE + (at - row) + k < n_b) {
+                    range_step16(u, bits, f[k]);
+                }
+            }
+#pragma unroll
+            for(int k = 0; k < 4; ++k) {
+                f[k] = nf[k];
+            }
+        }
+        __syncwarp();
+    }
+    if(n_b) {
+        const u32 nseg_b = (n_b + a.P - 1u) / a.P;
+        rec[2u * nseg_b] = bits >> 3;
+        rec[2u * nseg_b + 1u] = 0u;
+    }
+}
+
 template <bool WIDE>
 __global__ void __launch_bounds__(32) k_enc_ranges(SegArgs a)
 {
@@ -170,7 +258,12 @@ __global__ void __launch_bounds__(32) k_enc_ranges(SegArgs a)
     u32* rec = a.recs + (has ? b : b0) * (u64)(a.nseg + 1u) * 2u;
     const u32 ftab = sbase + lane * 2u;
     constexpr int MAXSH = WIDE ? 3 : 2;
-    if(all_pow2 && !ragged) {
+    const bool all16 = !WIDE && __all_sync(FULL, total == 65536u || !has);
+    if(all16 && !ragged) {
+        enc_range_tiles16<false>(a, tiles, ftab, b0, n_b, n_max, lane, rec);
+    } else if(all16) {
+        enc_range_tiles16<true>(a, tiles, ftab, b0, n_b, n_max, lane, rec);
+    } else if(all_pow2 && !ragged) {
         enc_range_tiles<MAXSH, true, false>(a, tiles, ftab, b0, n_b, n_max, total, magic, shift, lane, rec);
     } else if(all_pow2) {
         enc_range_tiles<MAXSH, true, true>(a, tiles, ftab, b0, n_b, n_max, total, magic, shift, lane, rec);
@@ -265,7 +358,7 @@ __global__ void __launch_bounds__(32 * ENC_SEG_WARPS) k_enc_seg(SegArgs a)
 
     // this warp's first input tile in flight while the tables are built
     if(seg < a.nseg) {
-        stage_tile(tiles, a.src, a.n, b0, a.block, tix0 * TILE, lane);
+        stage_tile(tiles + (tix0 & 1u) * TILE_BYTES, a.src, a.n, b0, a.block, tix0 * TILE, lane);  // buffer = tile index & 1
     }
     cp_async_commit();
 

@@ -23,6 +23,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "rc_lane.cuh"
 
 namespace b2rc
@@ -72,6 +74,12 @@ __device__ __forceinline__ u32 lds16(u32 a)
 {
     u32 v;
     asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));  // a wider destination is zero extended: no cvt
+    return v;
+}
+__device__ __forceinline__ u32 lds8(u32 a)
+{
+    u32 v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 // read-write data (adaptive model, rings): volatile keeps program order among them
@@ -951,12 +959,26 @@ struct CumTab {
     __device__ __forceinline__ u32 at(u32 pos) const { return lds32(base + pos); }
 };
 
+// The same table in 16 bits (k_dec_static_seg: half the shared memory, seven CTAs per SM instead of
+// four).  Only one value does not fit: cum == total == 65536, which the entries BEHIND the last
+// symbol that occurs hold; they are stored as 65535.  The search is exact whenever it lands in
+// front of that symbol; where it lands on or behind it, the symbol IS the last one that occurs
+// (symbols behind it have no interval), so its cum and freq come from registers (Last below).
+struct CumTab16 {
+    enum : u32 { UNIT = 64 };
+    u32 base;
+    __device__ __forceinline__ u32 at(u32 pos) const { return lds16(base + pos); }
+};
+struct Last {
+    u32 sym, cum, freq;  // the last symbol with a non-zero count, its cum and freq
+};
+
 // One tile (TILE symbols per lane).  MODE: 0 general divide, 2 / 3 power-of-two total with at
 // most 2 / 3 renormalisation rounds per symbol.
-template <int MODE, bool RAGGED, bool PAIR = false, class Src>
-__device__ __forceinline__ void dec_static_tile(const CumTab& tab, const u32 (&k1)[8], RcDec& d, u32& t, Src& src,
+template <int MODE, bool RAGGED, bool PAIR = false, class Tab = CumTab, class Src>
+__device__ __forceinline__ void dec_static_tile(const Tab& tab, const u32 (&k1)[8], RcDec& d, u32& t, Src& src,
                                                 u32 otile_a, u32 tile_off, u32 n_b, u32 total, u32 magic, u32 shift,
-                                                u32 lane)
+                                                u32 lane, const Last* last = nullptr)
 {
 #pragma unroll 1
     for(int wi = 0; wi < TILE / 4; ++wi) {
@@ -971,6 +993,12 @@ __device__ __forceinline__ void dec_static_tile(const CumTab& tab, const u32 (&k
                 if(PAIR) {  // the segmented kernel: fewer instructions beat a shorter chain there
                     const u32 k0[4] = {k1[0], k1[2], k1[4], k1[6]};
                     rc_static_find4(tab, k0, t, d.low, sym, cum, freq);
+                    if(Tab::UNIT == CumTab16::UNIT) {  // see CumTab16
+                        const bool at_last = sym >= last->sym;
+                        sym = at_last ? last->sym : sym;
+                        cum = at_last ? last->cum : cum;
+                        freq = at_last ? last->freq : freq;
+                    }
                 } else {
                     rc_static_find(tab, k1, t, d.low, sym, cum, freq);
                 }
@@ -988,10 +1016,11 @@ __device__ __forceinline__ void dec_static_tile(const CumTab& tab, const u32 (&k
     }
 }
 
-template <int MODE, bool RAGGED, bool PAIR = false>
-__device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const CumTab& tab, const u32 (&k1)[8], RcDec& d,
+template <int MODE, bool RAGGED, bool PAIR = false, class Tab = CumTab>
+__device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const Tab& tab, const u32 (&k1)[8], RcDec& d,
                                                  WordSrc& src, u8* otile, u32 otile_a, u64 b0, u32 n_b, u32 tix0,
-                                                 u32 tix1, bool resume, u32 total, u32 magic, u32 shift, u32 lane)
+                                                 u32 tix1, bool resume, u32 total, u32 magic, u32 shift, u32 lane,
+                                                 const Last* last = nullptr)
 {
     // a resumed power-of-two chain finds t where the previous launch left it (in d.range).
     // In the one-launch kernel tix0, tix1 and resume are compile-time constants / ntiles.
@@ -1002,9 +1031,9 @@ __device__ __forceinline__ void dec_static_tiles(const DecArgs& a, const CumTab&
         // inside the buffer: those tiles skip the bounds arithmetic of the copy requests
         if(__all_sync(FULL, src.tile_is_inside())) {
             WordSrcInside in{src};
-            dec_static_tile<MODE, RAGGED, PAIR>(tab, k1, d, t, in, otile_a, tix * TILE, n_b, total, magic, shift, lane);
+            dec_static_tile<MODE, RAGGED, PAIR>(tab, k1, d, t, in, otile_a, tix * TILE, n_b, total, magic, shift, lane, last);
         } else {
-            dec_static_tile<MODE, RAGGED, PAIR>(tab, k1, d, t, src, otile_a, tix * TILE, n_b, total, magic, shift, lane);
+            dec_static_tile<MODE, RAGGED, PAIR>(tab, k1, d, t, src, otile_a, tix * TILE, n_b, total, magic, shift, lane, last);
         }
         __syncwarp();
         store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
@@ -1134,16 +1163,30 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
 // so the cumulative tables of the 32 blocks are built once and shared by the CTA with the usual
 // bank == lane layout.  blockIdx.y walks groups of SEG_WARPS segments for long blocks.
 constexpr u32 SEG_WARPS = 4;
-constexpr u32 DEC_SEG_SMEM = DEC_STATIC_TAB + SEG_WARPS * (TILE_BYTES + INQ_BYTES);
+// NARROW: blocks <= 65536 bytes, u16 table (CumTab16); else the u32 table of k_dec_static.
+constexpr u32 dec_seg_tab(bool narrow)
+{
+    return 257u * 32u * (narrow ? 2u : 4u);
+}
+constexpr u32 dec_seg_smem(bool narrow)
+{
+    return dec_seg_tab(narrow) + 3u * 128u + SEG_WARPS * (TILE_BYTES + INQ_BYTES);
+}
 
+template <bool NARROW>
 __global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
+    constexpr u32 DEC_SEG_TAB = dec_seg_tab(NARROW);
+    typedef typename std::conditional<NARROW, u16, u32>::type Entry;
+    typedef typename std::conditional<NARROW, CumTab16, CumTab>::type Tab;
+    constexpr u32 CLAMP = NARROW ? 65535u : 0xFFFFFFFFu;
     const u32 sbase = smem_addr(smem);
-    u32* table = reinterpret_cast<u32*>(smem);
+    Entry* table = reinterpret_cast<Entry*>(smem);
+    u32* tots = reinterpret_cast<u32*>(smem + DEC_SEG_TAB);  // per block: total, last symbol that occurs, its cum
     const u32 warp = threadIdx.x >> 5, lane = lane_id();
-    u8* otile = smem + DEC_STATIC_TAB + warp * (TILE_BYTES + INQ_BYTES);
-    const u32 otile_a = sbase + DEC_STATIC_TAB + warp * (TILE_BYTES + INQ_BYTES);
+    u8* otile = smem + DEC_SEG_TAB + 384u + warp * (TILE_BYTES + INQ_BYTES);
+    const u32 otile_a = sbase + DEC_SEG_TAB + 384u + warp * (TILE_BYTES + INQ_BYTES);
     const u32 queue_a = otile_a + TILE_BYTES;
 
     const u64 b0 = (u64)blockIdx.x * 32u;
@@ -1172,21 +1215,30 @@ __global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
         const u32 want = (u32)pay[0] | ((u32)pay[1] << 8) | ((u32)pay[2] << 16) | ((u32)pay[3] << 24);
         ok = want == n_b;
     }
-    u32* mine = table + lane;
+    Entry* mine = table + lane;
     if(warp == 0) {
         // read16 + calcCumulatives (cpprcoder.h:585-602, :573-583), once for the CTA
-        u32 run = 0;
+        u32 run = 0, lsym = 0, lcum = 0;
 #pragma unroll 1
         for(u32 s = 0; s < 256; ++s) {
             u32 f = 0;
             if(ok) {
                 f = (u32)pay[4u + 2u * s] | ((u32)pay[5u + 2u * s] << 8);
             }
-            mine[s * 32u] = run;
+            mine[s * 32u] = (Entry)(run < CLAMP ? run : CLAMP);
+            if(f) {
+                lsym = s;
+                lcum = run;
+            }
             run += f;
         }
-        mine[256u * 32u] = run;
-        if(has && (!ok || run == 0) && blockIdx.y == 0) {
+        mine[256u * 32u] = (Entry)(run < CLAMP ? run : CLAMP);
+        tots[lane] = run;
+        tots[32u + lane] = lsym;
+        tots[64u + lane] = lcum;
+        // a table that sums to more than 2^16 is not one an encoder of <= 64 KiB blocks writes, and
+        // the 16-bit entries could not hold it
+        if(has && (!ok || run == 0 || (NARROW && run > 65536u)) && blockIdx.y == 0) {
             atomicOr(a.err, ERR_CORRUPT);
         }
     }
@@ -1194,23 +1246,27 @@ __global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
     if(seg >= nseg) {
         return;
     }
-    u32 total = mine[256u * 32u];
-    if(total == 0) {
+    u32 total = tots[lane];
+    if(total == 0 || (NARROW && total > 65536u)) {
         ok = false;
         total = 1;
     }
+    const Last last{tots[32u + lane], tots[64u + lane], total - tots[64u + lane]};
+    const Tab tab{sbase + lane * (u32)sizeof(Entry)};
     u32 k1[8];
 #pragma unroll
     for(int j = 0; j < 8; ++j) {
-        k1[j] = mine[(32u * j) * 32u];
+        k1[j] = tab.at((32u * j) * Tab::UNIT);
+        k1[j] = (32u * (u32)j > last.sym) ? total : k1[j];  // exact in registers: 65536 fits here
     }
     const u32 seg_lo = seg * a.seg_syms;
     u32 seg_hi = seg_lo + a.seg_syms;
     seg_hi = seg_hi < n_b ? seg_hi : n_b;  // my symbols: [seg_lo, seg_hi)
     bool mine_ok = ok && seg_lo < n_b;
-    u32 skip = (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u), word0 = 0, range0 = RC_STATIC_RANGE0, enc_low = 0;
+    const u32 skip0 = (u32)((uintptr_t)(pay + RC_STATIC_HDR) & 3u);
+    u32 skip = skip0, word0 = 0, range0 = RC_STATIC_RANGE0, enc_low = 0;
+    const u32 nrec = nseg - 1u;
     if(seg != 0u && mine_ok) {
-        const u32 nrec = nseg - 1u;
         const u32* rec = a.restart + (b * nrec + seg - 1u) * 3u;
         const u32 m = rec[0];
         enc_low = rec[1];
@@ -1235,7 +1291,6 @@ __global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
         src.prime(mine_ok ? word0 : 0u);
     }
     const u32 n_eff = mine_ok ? seg_hi : 0u;  // symbols at or beyond this are not mine
-    const CumTab tab{sbase + lane * 4u};
     const u32 magic = rc_magic(total);
     const bool is_pow2 = (total & (total - 1u)) == 0;
     const u32 shift = is_pow2 ? 31u - rc_clz(total) : 0u;
@@ -1249,18 +1304,46 @@ __global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
     const u32 tix0 = seg_lo / TILE;
     const u32 ntiles = (n_max + TILE - 1) / TILE;
     const u32 tix1 = ntiles > tix0 ? ntiles : tix0;
-    if(all_pow2 && !ragged && a.block <= 65536u) {
+    const bool pow2_path = all_pow2 && !ragged;
+    if(pow2_path && NARROW) {
         dec_static_tiles<2, false, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
-                                   lane);
-    } else if(all_pow2 && !ragged) {
+                                         lane, &last);
+    } else if(pow2_path) {
         dec_static_tiles<3, false, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
-                                   lane);
+                                         lane, &last);
     } else if(!ragged) {
         dec_static_tiles<0, false, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
-                                   lane);
+                                         lane, &last);
     } else {
         dec_static_tiles<0, true, true>(a, tab, k1, d, src, otile, otile_a, b0, n_eff, tix0, tix1, false, total, magic, shift,
-                                  lane);
+                                        lane, &last);
+    }
+
+    // ---- the records are part of the container and as untrusted as the rest of it: a chain that was
+    //      started from a damaged record must not pass for a decode.  A segment has to END where the
+    //      next record says the coder stands -- the decoder's low is the stream's next four bytes minus
+    //      the encoder's low there, and range / total is the same on both sides; the last segment of a
+    //      block has to end with exactly the block's coded bytes used up (5 + shifts, cpprcoder.h:494-517).
+    if(mine_ok) {
+        const u32 used = 4u * src.rd - skip0 - (u32)d.wbits / 8u;  // bytes of the coded stream taken into low so far
+        bool good;
+        if(seg_hi < n_b) {
+            const u32* rec = a.restart + (b * nrec + seg) * 3u;
+            const u32 m = rec[0];
+            good = m != 0xFFFFFFFFu && (u64)m + RC_STATIC_HDR + 5u <= len && used == m + 5u;
+            if(good) {
+                const u8* p = pay + RC_STATIC_HDR + 1u + m;
+                const u32 be = ((u32)p[0] << 24) | ((u32)p[1] << 16) | ((u32)p[2] << 8) | (u32)p[3];
+                const u32 t_mine = pow2_path ? d.range : rc_div(d.range, total, magic);
+                const u32 t_rec = is_pow2 ? (rec[2] >> shift) : rc_div(rec[2], total, magic);
+                good = d.low == be - rec[1] && t_mine == t_rec;
+            }
+        } else {
+            good = (u64)used + RC_STATIC_HDR == len;
+        }
+        if(!good) {
+            atomicOr(a.err, ERR_CORRUPT);
+        }
     }
 }
 

@@ -19,9 +19,6 @@ import torch.distributed as dist
 
 from . import container
 
-RESTART_SYMS = 8192  # B2RC_DEFAULT_RESTART_SYMS (include/b2rc.h)
-
-
 def shard_of(n_total: int, block: int, rank: int, world: int):
     """(byte_lo, byte_hi, blk_lo, blk_hi) of `rank`'s contiguous share of an n_total-byte stream."""
     nb = container.nblocks_of(n_total, block)
@@ -65,13 +62,27 @@ class Shard:
     n_total: int
     blk_lo: int
     blk_hi: int
-    payload: torch.Tensor       # this rank's payloads, back to back (device)
-    payload_bytes: int
-    local_offsets: torch.Tensor  # int64, blk_hi - blk_lo + 1, relative to `payload`
+    container: torch.Tensor      # this rank's blocks as a B2RC container of their own (device), b2rc_encode_device's output
+    used: int                    # its length
     offsets: torch.Tensor        # int64, global index, replicated on every rank
-    err: torch.Tensor
-    restart: torch.Tensor | None = None  # static coder: this rank's restart records (int32, device)
-    seg_syms: int = 0
+
+    @property
+    def nblocks(self) -> int:
+        return self.blk_hi - self.blk_lo
+
+    @property
+    def local_offsets(self) -> torch.Tensor:
+        """int64, nblocks + 1, relative to this rank's payload area (the shard container's own index)."""
+        return self.container[container.HEADER:container.HEADER + 8 * (self.nblocks + 1)].view(torch.int64)
+
+    @property
+    def payload_bytes(self) -> int:
+        return int((self.offsets[self.blk_hi] - self.offsets[self.blk_lo]).item())
+
+    @property
+    def payload(self) -> torch.Tensor:
+        at = container.HEADER + 8 * (self.nblocks + 1)
+        return self.container[at:at + self.payload_bytes]
 
     @property
     def base(self) -> int:
@@ -79,49 +90,48 @@ class Shard:
         return int(self.offsets[self.blk_lo].item())
 
 
-def encode_shard(ctx, mode: int, src_shard: torch.Tensor, n_total: int, block: int, group=None) -> Shard:
-    """Code this rank's blocks on its GPU (K1, K2, K4 through the C ABI) and all-gather the sizes."""
+def encode_shard(ctx, mode: int, src_shard: torch.Tensor, n_total: int, block: int, group=None,
+                 dst: torch.Tensor | None = None) -> Shard:
+    """Code this rank's blocks on its GPU -- ONE b2rc_encode_device call, the same one a single GPU makes for
+    a whole stream -- and all-gather the payload sizes (4 bytes per block), the path's only exchange.
+    A rank without blocks (world > nblocks) still enters the collective."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi, blk_lo, blk_hi = shard_of(n_total, block, rank, world)
     assert src_shard.numel() == hi - lo, "src_shard must hold exactly this rank's byte range"
     nb = blk_hi - blk_lo
-    # restart points (static coder): each block becomes several independent chains for the decoder
-    seg = RESTART_SYMS if mode == 0 and ctx.restart_records(block, RESTART_SYMS) else 0
-    restart = None
-    if seg:
-        restart = torch.empty(max(nb, 1) * ctx.restart_records(block, seg) * 3, dtype=torch.int32, device=src_shard.device)
-    slots, stride, sizes, err = ctx.encode_blocks(mode, src_shard, block, restart=restart, seg_syms=seg)
-    local_offsets = ctx.scan(sizes, nb)
-    all_sizes = allgather_sizes(sizes[:nb], n_total, block, group)  # the one collective
-    offsets = global_offsets(all_sizes)
-    total_local = int((offsets[blk_hi] - offsets[blk_lo]).item())
-    payload = torch.empty(max(total_local, 1) + 16, dtype=torch.uint8, device=src_shard.device)
-    ctx.compact(slots, stride, sizes, local_offsets, nb, payload, err, mode)
-    return Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, payload, total_local, local_offsets, offsets, err,
-                 restart, seg)
+    enc, used = ctx.encode_device(mode, src_shard, dst, block)   # raises B2rcError on any device-side error bit
+    local = enc[container.HEADER:container.HEADER + 8 * (nb + 1)].view(torch.int64)
+    sizes = (local[1:] - local[:-1]).to(torch.int32)
+    all_sizes = allgather_sizes(sizes, n_total, block, group)  # the one collective
+    return Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, enc, used, global_offsets(all_sizes))
 
 
-def decode_shard(ctx, shard: Shard, dst_shard: torch.Tensor) -> torch.Tensor:
-    """Inverse of encode_shard on the same rank; no collective."""
-    lo, hi, blk_lo, blk_hi = shard_of(shard.n_total, shard.block, shard.rank, shard.world)
-    return ctx.decode_blocks(shard.mode, shard.payload, shard.payload_bytes, shard.local_offsets, blk_hi - blk_lo,
-                             dst_shard, hi - lo, shard.block, restart=shard.restart, seg_syms=shard.seg_syms)
+def decode_shard(ctx, shard: Shard, dst_shard: torch.Tensor) -> int:
+    """Inverse of encode_shard on the same rank; no collective.  Returns the bytes decoded."""
+    return ctx.decode_device(shard.container, shard.used, dst_shard)
 
 
 def stitch_on_host(shard: Shard, group=None) -> np.ndarray | None:
     """Convenience, not on the timed path: gather every rank's payload to rank 0 and return the
-    B2RC container there (None elsewhere)."""
+    B2RC container of the whole stream there (None elsewhere)."""
     world, rank = shard.world, shard.rank
-    mine = shard.payload[:shard.payload_bytes].cpu().numpy().tobytes()
-    recs = shard.restart.cpu().numpy().tobytes() if shard.restart is not None and shard.blk_hi > shard.blk_lo else b""
+    host = shard.container[:shard.used].cpu().numpy()
+    info = container.parse(host)
+    mine = host[info.payload_base:info.payload_base + int(info.offsets[-1])].tobytes()
+    recs = info.restart.tobytes() if info.restart is not None and shard.nblocks else b""
     parts = [None] * world if rank == 0 else None
-    dist.gather_object((mine, recs), parts, dst=0, group=group)
+    dist.gather_object((mine, recs, info.seg_syms), parts, dst=0, group=group)
     if rank != 0:
         return None
-    nb = shard.offsets.numel() - 1
-    head = container.pack_header(shard.mode, shard.block, shard.n_total, nb, shard.seg_syms)
-    index = shard.offsets.cpu().numpy().astype(np.uint64).tobytes()
-    body = b"".join(p for p, _ in parts)
-    if shard.seg_syms:
-        body += bytes(-len(body) % 4) + b"".join(r for _, r in parts)
-    return np.frombuffer(head + index + body, dtype=np.uint8)
+    return stitch(shard.mode, shard.block, shard.n_total, shard.offsets.cpu().numpy(), parts)
+
+
+def stitch(mode: int, block: int, n_total: int, offsets: np.ndarray, parts) -> np.ndarray:
+    """The container of the whole stream from every rank's (payload bytes, restart records, segment length)."""
+    nb = len(offsets) - 1
+    seg = max((p[2] for p in parts), default=0)
+    head = container.pack_header(mode, block, n_total, nb, seg)
+    body = b"".join(p[0] for p in parts)
+    if seg:
+        body += bytes(-len(body) % 4) + b"".join(p[1] for p in parts)
+    return np.frombuffer(head + np.asarray(offsets).astype(np.uint64).tobytes() + body, dtype=np.uint8)

@@ -22,6 +22,25 @@ def _free_port():
         return s.getsockname()[1]
 
 
+class OracleCtx:
+    """Stands in for api.Context on CPU tensors: the same two calls dist.py makes, answered by the oracle
+    (test infrastructure -- the product's context launches CUDA kernels and has no CPU path)."""
+
+    def encode_device(self, mode, src, dst=None, block=65536):
+        data = src.numpy()
+        pays = Oracle.get().encode_blocks(mode, data, block) if data.size else []
+        buf = container.build(mode, block, data.size, pays)
+        return torch.from_numpy(buf.copy()), buf.size
+
+    def decode_device(self, enc, used, dst):
+        buf = enc[:used].numpy()
+        info = container.parse(buf)
+        if info.total:
+            back = Oracle.get().decode_blocks(info.mode, buf[info.payload_base:], info.offsets, info.block, info.total)
+            dst[:info.total] = torch.from_numpy(back.copy())
+        return info.total
+
+
 def _worker(rank, world, port, n_total, block, mode, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -29,29 +48,29 @@ def _worker(rank, world, port, n_total, block, mode, out_dir):
     try:
         data = synth.kennedy(n_total)
         lo, hi, blk_lo, blk_hi = rcdist.shard_of(n_total, block, rank, world)
-        pays = Oracle.get().encode_blocks(mode, data[lo:hi], block) if hi > lo else []
-        assert len(pays) == blk_hi - blk_lo
-        sizes = torch.tensor([len(p) for p in pays], dtype=torch.int32)
-        all_sizes = rcdist.allgather_sizes(sizes, n_total, block)
-        offsets = rcdist.global_offsets(all_sizes)
+        ctx = OracleCtx()
+        shard = rcdist.encode_shard(ctx, mode, torch.from_numpy(data[lo:hi].copy()), n_total, block)
+        assert shard.nblocks == blk_hi - blk_lo
         # every rank must now hold the same, complete index
         gathered = [None] * world
-        dist.all_gather_object(gathered, offsets.tolist())
+        dist.all_gather_object(gathered, shard.offsets.tolist())
         assert all(g == gathered[0] for g in gathered)
-        assert int(offsets[blk_hi] - offsets[blk_lo]) == sum(len(p) for p in pays)
-        parts = [None] * world if rank == 0 else None
-        dist.gather_object(b"".join(pays), parts, dst=0)
+        assert shard.payload_bytes == int(shard.local_offsets[-1])
+        back = torch.zeros(max(hi - lo, 1), dtype=torch.uint8)
+        assert rcdist.decode_shard(ctx, shard, back) == hi - lo
+        assert back[:hi - lo].numpy().tobytes() == data[lo:hi].tobytes()
+        buf = rcdist.stitch_on_host(shard)
         if rank == 0:
-            nb = container.nblocks_of(n_total, block)
-            buf = np.frombuffer(container.pack_header(mode, block, n_total, nb)
-                                + offsets.numpy().astype(np.uint64).tobytes() + b"".join(parts), dtype=np.uint8)
             np.save(os.path.join(out_dir, "stitched.npy"), buf)
+        else:
+            assert buf is None
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world,n_total,block,mode", [(2, 5 * 4096 + 123, 4096, STATIC), (2, 300, 4096, ADAPTIVE),
                                                       (3, 10 * 1024, 1024, ADAPTIVE),
+                                                      (4, 2 * 4096 + 5, 4096, STATIC),   # world > nblocks: a rank with no block
                                                       (2, 9 * 4096 + 77, 4096, RANS_WORD), (3, 7 * 1024 + 1, 1024, RANS_BYTE)])
 def test_sharded_index_exchange_and_stitching(tmp_path, built, world, n_total, block, mode):
     port = _free_port()

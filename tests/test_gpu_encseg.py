@@ -102,7 +102,14 @@ def test_reference_shaped_path_of_the_flush_quirk(oracle):
     try:
         enc = ctx.encode(STATIC, data, 65536)
         assert payloads(enc) == oracle.encode_blocks(STATIC, data, 65536, threads=4)
-        assert enc.tobytes() == plain.encode(STATIC, data, 65536).tobytes()   # the restart points as well
+        # the restart points as well: same place, same low, a range with the same range / total
+        a, b = container.parse(enc), container.parse(plain.encode(STATIC, data, 65536))
+        assert np.array_equal(a.restart[:, :, :2], b.restart[:, :, :2])
+        for blk in range(a.nblocks):
+            n_b = min(65536, data.size - blk * 65536)
+            total = 0x8000 if (n_b == 65536 and len(set(data[blk * 65536:(blk + 1) * 65536].tolist())) == 1) else n_b
+            live = a.restart[blk, :, 0] != 0xFFFFFFFF
+            assert np.array_equal(a.restart[blk, live, 2] // total, b.restart[blk, live, 2] // total)
         assert plain.decode(enc).tobytes() == data.tobytes()
     finally:
         ctx.close()
@@ -145,5 +152,71 @@ def test_full_size_every_block_hash(oracle):
         dst = torch.empty(n, dtype=torch.uint8, device="cuda")
         assert ctx.decode_device(enc, used, dst) == n
         assert torch.equal(dst.cpu(), torch.from_numpy(data))
+    finally:
+        ctx.close()
+
+
+# ---------------------------------------------------------- restart records are untrusted --
+def test_damaged_restart_records_are_detected(oracle):
+    """The static decoder starts a chain at every restart record; a damaged record (place, low or range)
+    must end in B2RC_E_CORRUPT, never in silently wrong bytes: every segment has to end where the next
+    record stands, the last one with the block's coded bytes used up (k_dec_static_seg)."""
+    from cpprcoder_b200._lib import B2rcError, E_CORRUPT
+    data = np.concatenate([synth.zipf(20 * 65536), synth.mixed(12 * 65536 + 3000)])
+    ctx = make_ctx()
+    try:
+        enc = ctx.encode(STATIC, data, 65536)
+        info = container.parse(enc)
+        assert info.restart is not None and info.restart.shape[1] == 7
+        table_at = info.payload_base + ((int(info.offsets[-1]) + 3) & ~3)
+        rng = np.random.default_rng(77)
+        for trial in range(40):
+            bad = enc.copy()
+            b = int(rng.integers(0, info.nblocks - 1))        # a full block: all seven records are live
+            j = int(rng.integers(0, 7))
+            w = trial % 3                                      # 0: bytes shifted, 1: low, 2: range
+            at = table_at + 4 * ((b * 7 + j) * 3 + w)
+            word = int(np.frombuffer(bad[at:at + 4].tobytes(), dtype="<u4")[0])
+            if w == 2:   # range: only range / total matters (total = 65536 for these blocks): damage the quotient
+                word ^= 1 << int(rng.integers(16, 32))
+            elif w == 1:
+                word ^= 1 << int(rng.integers(0, 32))
+            else:
+                word = (word + int(rng.choice([-3, -1, 1, 2, 300]))) & 0xFFFFFFFF
+            bad[at:at + 4] = np.frombuffer(np.uint32(word).tobytes(), dtype=np.uint8)
+            with pytest.raises(B2rcError) as e:
+                ctx.decode(bad)
+            assert e.value.code == E_CORRUPT, (trial, b, j, w)
+        assert ctx.decode(enc).tobytes() == data.tobytes()
+        # low bits of a recorded range do not matter (any range with the same range / total serves)
+        ok = enc.copy()
+        at = table_at + 4 * ((3 * 7 + 2) * 3 + 2)
+        ok[at] ^= 0x55
+        assert ctx.decode(ok).tobytes() == data.tobytes()
+    finally:
+        ctx.close()
+
+
+def test_last_symbol_and_trailing_absent_symbols(oracle):
+    """The 16-bit cumulative table of the segmented decoder stores 65535 where the true value is 65536
+    (behind the last symbol that occurs); blocks whose LAST occurring symbol is frequent, rare, 255 or 0
+    exercise the rule that replaces the search result there."""
+    import torch
+    rng = np.random.default_rng(9)
+    blocks = []
+    for hi in (255, 254, 128, 7, 1, 0):
+        for p_hi in (0.9, 0.5, 0.01, 1.0 / 65536):
+            sym = rng.integers(0, hi + 1, 65536) if hi else np.zeros(65536, np.int64)
+            d = np.where(rng.random(65536) < p_hi, hi, sym).astype(np.uint8)
+            d[int(rng.integers(0, 65536))] = hi
+            blocks.append(d)
+    data = np.concatenate(blocks)
+    ctx = make_ctx()
+    try:
+        enc, used = ctx.encode_device(STATIC, torch.from_numpy(data).cuda())
+        assert payloads(enc[:used].cpu().numpy()) == oracle.encode_blocks(STATIC, data, 65536, threads=4)
+        dst = torch.empty(data.size, dtype=torch.uint8, device="cuda")
+        assert ctx.decode_device(enc, used, dst) == data.size
+        assert dst.cpu().numpy().tobytes() == data.tobytes()
     finally:
         ctx.close()
