@@ -5,8 +5,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-SO = PKG / "libb2rc.so"
+# B2RC_LIB: another build of the same library (kernel experiments, tools/ only); default the in-tree one
+SO = Path(os.environ["B2RC_LIB"]) if os.environ.get("B2RC_LIB") else PKG / "libb2rc.so"
 
 OK, E_ARG, E_DST_SMALL, E_CORRUPT, E_CUDA, E_EXPAND, E_NOMEM, E_INTERNAL = 0, -1, -2, -3, -4, -5, -6, -7
 MODE_STATIC, MODE_ADAPTIVE = 0, 1
@@ -33,6 +36,9 @@ SIGNATURES = {
     "b2rc_encode": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, C.POINTER(_U64)]),
     "b2rc_decode": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64)]),
     "b2rc_peek": (C.c_int, [_P, _U64, C.POINTER(C.c_int), C.POINTER(_U32), C.POINTER(_U64), C.POINTER(_U64)]),
+    "b2rc_check": (C.c_int, [_P, _U64, C.POINTER(_U64)]),
+    "b2rc_encode_staged": (C.c_int, [_P, C.c_int, _U32, _P, _U64, C.POINTER(_P), C.POINTER(_U64)]),
+    "b2rc_decode_staged": (C.c_int, [_P, _P, _U64, C.POINTER(_P), C.POINTER(_U64)]),
     "b2rc_encode_device": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
     "b2rc_decode_device": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
     "b2rc_k_histogram": (C.c_int, [_P, _P, _U64, _U32, _P, _P]),

@@ -60,6 +60,8 @@ struct b2rc_ctx {
     u32* restart;    // device scratch: the table while a container is being written / read
     size_t restart_cap;
     // segmented static encode (b2rc_encseg.cuh): the range pass's records and the segments' final lows
+    u8* h_stage;  // pinned host staging of the *_staged calls
+    size_t h_stage_cap;
     u32* seg_recs;
     size_t seg_recs_cap;
     u32* seg_lows;
@@ -483,6 +485,9 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     cudaFree(ctx->d_total);
     if(ctx->h_res) {
         cudaFreeHost(ctx->h_res);
+    }
+    if(ctx->h_stage) {
+        cudaFreeHost(ctx->h_stage);
     }
     for(int k = 0; k < B2RC_PIPE_STREAMS; ++k) {
         if(ctx->pipe[k]) {
@@ -1380,18 +1385,14 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     if(dst_cap < total || (total && !dst)) {
         return B2RC_E_DST_SMALL;
     }
-    // the index is in host memory here: check it before anything reaches the device
+    // the index is in host memory here: check it (b2rc_check) before anything is allocated or reaches the device
     const u64 idx = index_bytes(nb);
     const u64 payload_len = n - idx;
-    u64 prev = 0;
-    for(u64 b = 0; b <= nb; ++b) {
-        u64 o;
-        memcpy(&o, src + B2RC_HEADER_BYTES + 8 * b, 8);
-        if(o < prev || o > payload_len || (b == 0 && o != 0)) {
-            return B2RC_E_CORRUPT;
-        }
-        prev = o;
+    if((rc = b2rc_check(src, n, nullptr)) != B2RC_OK) {
+        return rc;
     }
+    u64 prev = 0;
+    memcpy(&prev, src + B2RC_HEADER_BYTES + 8 * nb, 8);
     if(nb == 0) {
         return B2RC_OK;
     }
@@ -1498,6 +1499,94 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, s0));
     CK(cudaStreamSynchronize(s0));
     return map_kernel_err(ctx->h_res->err);
+}
+
+// ------------------------------------------------------- host-side validation --
+int b2rc_check(const uint8_t* src, uint64_t n, uint64_t* total_out)
+{
+    int mode;
+    u32 block;
+    u64 total, nb;
+    const int rc = b2rc_peek(src, n, &mode, &block, &total, &nb);
+    if(rc != B2RC_OK) {
+        return rc;
+    }
+    const u64 idx = index_bytes(nb);
+    const u64 payload_len = n - idx;
+    const u64 min_pay = is_ans(mode) ? (u64)ANS_HDR + 4u : (mode == B2RC_MODE_STATIC ? (u64)RC_STATIC_HDR + 5u : (u64)RC_ADAPT_HDR + 5u);
+    u64 prev = 0;
+    for(u64 b = 0; b <= nb; ++b) {
+        u64 o;
+        memcpy(&o, src + B2RC_HEADER_BYTES + 8 * b, 8);
+        if(o < prev || o > payload_len || (b == 0 && o != 0) || (b > 0 && o - prev < min_pay)) {
+            return B2RC_E_CORRUPT;
+        }
+        prev = o;
+    }
+    u32 flags;
+    memcpy(&flags, src + 12, 4);
+    if(flags) {
+        const u32 seg = (flags >> 8) * 64u;
+        if(align4(prev) + (u64)nb * b2rc_restart_records(block, seg) * 12ull > payload_len) {
+            return B2RC_E_CORRUPT;
+        }
+    }
+    if(total_out) {
+        *total_out = total;
+    }
+    return B2RC_OK;
+}
+
+static int grow_host(b2rc_ctx* ctx, size_t want)
+{
+    if(want <= ctx->h_stage_cap) {
+        return B2RC_OK;
+    }
+    if(ctx->h_stage) {
+        CK(cudaFreeHost(ctx->h_stage));
+        ctx->h_stage = nullptr;
+        ctx->h_stage_cap = 0;
+    }
+    void* q = nullptr;
+    if(!cuda_ok(ctx, cudaMallocHost(&q, want), "cudaMallocHost")) {
+        return B2RC_E_NOMEM;
+    }
+    ctx->h_stage = static_cast<u8*>(q);
+    ctx->h_stage_cap = want;
+    return B2RC_OK;
+}
+
+int b2rc_encode_staged(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src, uint64_t n,
+                       const uint8_t** out, uint64_t* out_n)
+{
+    if(!ctx || !out || !out_n || !mode_ok(mode) || !block_ok(block_size)) {
+        return B2RC_E_ARG;
+    }
+    DeviceGuard g(ctx->device);
+    const int rc = grow_host(ctx, (size_t)b2rc_bound(mode, n, block_size) + 16);
+    if(rc != B2RC_OK) {
+        return rc;
+    }
+    *out = ctx->h_stage;
+    return b2rc_encode(ctx, mode, block_size, src, n, ctx->h_stage, ctx->h_stage_cap, out_n);
+}
+
+int b2rc_decode_staged(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, const uint8_t** out, uint64_t* out_n)
+{
+    if(!ctx || !src || !out || !out_n) {
+        return B2RC_E_ARG;
+    }
+    u64 total = 0;
+    int rc = b2rc_check(src, n, &total);  // before any allocation sized by the header
+    if(rc != B2RC_OK) {
+        return rc;
+    }
+    DeviceGuard g(ctx->device);
+    if((rc = grow_host(ctx, (size_t)total + 16)) != B2RC_OK) {
+        return rc;
+    }
+    *out = ctx->h_stage;
+    return b2rc_decode(ctx, src, n, ctx->h_stage, ctx->h_stage_cap, out_n);
 }
 
 // ------------------------------------------------------------- block sort --

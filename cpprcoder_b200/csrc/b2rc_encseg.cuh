@@ -123,28 +123,26 @@ __device__ __forceinline__ void enc_range_tiles(const SegArgs& a, u32 tiles, u32
     }
 }
 
-// The chain for total == 65536 (every full 64 KiB block that is not one repeated byte), three
-// instructions deep.  It carries u = t - 256, t = range >> 16 in [2^8, 2^16).  With r = freq * t the
-// next t is r >> 16, r >> 8 or r, whichever lies in [2^8, 2^16) (cpprcoder.h:418: shift left by 8
-// while range < 2^24).  Subtracting the lower end of each candidate's home range BEFORE shifting
+// The chain for total == 65536 (every full 64 KiB block that is not one repeated byte).
+// t = range >> 16 lies in [2^8, 2^16).  With r = freq * t the next t is r >> 16, r >> 8 or r, whichever
+// lies in [2^8, 2^16) (cpprcoder.h:418: shift left by 8 while range < 2^24).  Subtracting the lower
+// end of each candidate's home range BEFORE shifting
 //     A = (r - 2^24) >> 16     B = (r - 2^16) >> 8     C = r - 2^8
-// makes the candidate that applies come out as t' - 256 (below 65280) and the others wrap around
-// to 65280 or more, so the next u is the minimum of the three (VIMNMX3) -- no compares, no selects.
-// r - K is one IMAD: freq * u + (256 * freq - K).  The shift counts are recovered off the chain from
-// the leading zero bytes of r.
-__device__ __forceinline__ void range_step16(u32& u, u32& bits, u32 f)
+// makes the candidate that applies come out as t' - 256 (below 65280) and the others wrap around to
+// 65280 or more, so t' - 256 is the minimum of the three (VIMNMX3) -- no compares, no selects.  The
+// three r - K are three multiply-adds with an immediate addend, side by side.  A lone warp per
+// scheduler pays for every instruction it issues (about 2.3 cycles each, profiles/r2_ncu_notes.md),
+// so the count matters more than the depth: 4 multiply-adds, 2 shifts, the minimum, one add, and the
+// shift count from the leading zero bytes of r (conversion pipe) -- 14 instructions per symbol with
+// the two loads and their address.
+__device__ __forceinline__ void range_step16(u32& t, u32& bits, u32 f)
 {
-    // three multiply-adds side by side (not one product and three adds: that is a level more);
-    // a lone warp gets one instruction per pipe every other cycle, so what is off the chain is
-    // spread over the pipes too: the fourth product (r itself, for the shift count) on the multiplier
     u32 r0, r1, r2, r3, top;
-    const u32 g = f << 8;
-    const u32 k1 = g - 0x01000000u, k2 = g - 0x00010000u, k3 = g - 0x00000100u;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r1) : "r"(f), "r"(u), "r"(k1));
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r2) : "r"(f), "r"(u), "r"(k2));
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r3) : "r"(f), "r"(u), "r"(k3));
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r0) : "r"(f), "r"(u), "r"(g));
-    u = min(min(r1 >> 16, r2 >> 8), r3);
+    asm("mad.lo.u32 %0, %1, %2, 0xFF000000;" : "=r"(r1) : "r"(f), "r"(t));
+    asm("mad.lo.u32 %0, %1, %2, 0xFFFF0000;" : "=r"(r2) : "r"(f), "r"(t));
+    asm("mad.lo.u32 %0, %1, %2, 0xFFFFFF00;" : "=r"(r3) : "r"(f), "r"(t));
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(r0) : "r"(f), "r"(t));
+    t = min(min(r1 >> 16, r2 >> 8), r3) + 256u;
     // shift = 8 * leading zero bytes of r (2^8 <= r): 24 & (31 - top), top the highest set bit
     asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(r0));
     bits += ~top & 24u;
@@ -154,7 +152,7 @@ template <bool RAGGED>
 __device__ __forceinline__ void enc_range_tiles16(const SegArgs& a, u32 tiles, u32 ftab, u64 b0, u32 n_b, u32 n_max,
                                                   u32 lane, u32* rec)
 {
-    u32 u = (RC_STATIC_RANGE0 >> 16) - 256u;
+    u32 u = RC_STATIC_RANGE0 >> 16;  // t
     u32 bits = 0;
     const u32 ntiles = (n_max + TILE - 1) / TILE;
     const u32 seg_tiles = a.P / TILE;
@@ -172,7 +170,7 @@ __device__ __forceinline__ void enc_range_tiles16(const SegArgs& a, u32 tiles, u
             if(tix * TILE < n_b) {
                 const u32 j = tix / seg_tiles;
                 rec[2u * j] = bits >> 3;
-                rec[2u * j + 1u] = (u + 256u) << 16;  // any range with the same range >> 16 serves
+                rec[2u * j + 1u] = u << 16;  // any range with the same range >> 16 serves
             }
         }
         const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
@@ -183,9 +181,9 @@ __device__ __forceinline__ void enc_range_tiles16(const SegArgs& a, u32 tiles, u
         for(int k = 0; k < 4; ++k) {
             f[k] = lds16(ftab + lds8(row + k) * 64u);
         }
-#pragma unroll 1
-        for(u32 at = row; at != row + TILE; at += 4u) {
-            const u32 nx = at + 4u == row + TILE ? row : at + 4u;
+#pragma unroll 2
+        for(u32 at = 0; at < (u32)TILE; at += 4u) {
+            const u32 nx = row + ((at + 4u) & (TILE - 1u));
             u32 nf[4];
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
@@ -193,7 +191,7 @@ __device__ __forceinline__ void enc_range_tiles16(const SegArgs& a, u32 tiles, u
             }
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
-                if(!RAGGED || tix * TILE + (at - row) + k < n_b) {
+                if(!RAGGED || tix * TILE + at + k < n_b) {
                     range_step16(u, bits, f[k]);
                 }
             }
@@ -289,7 +287,7 @@ constexpr u32 enc_seg_smem(bool wide, u32 warps)
 }
 
 template <bool WIDE, bool POW2, bool RAGGED>
-__device__ __forceinline__ void enc_seg_tiles(const SegArgs& a, u32 tiles, const StaticTab<WIDE>& tab, RcEnc& st,
+__device__ __forceinline__ void enc_seg_tiles(const SegArgs& a, u32 tiles, const StaticTab<WIDE>& tab, RcEnc2& st,
                                               RcSegSink& sink, u64 b0, u32 n_eff, u32 tix0, u32 tix1, u32 total,
                                               u32 magic, u32 shift, u32 lane)
 {
@@ -304,32 +302,34 @@ __device__ __forceinline__ void enc_seg_tiles(const SegArgs& a, u32 tiles, const
         cp_async_wait<1>();
         __syncwarp();
         const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
-        u32 word = lds32(row);
+        // symbols by byte loads: the load pipe has room, the integer pipe (which a word load's shifts and
+        // masks would use) is what bounds this kernel.  Table entries of the NEXT four symbols are
+        // requested before the current four are coded.
         u32 cum[4], freq[4];
 #pragma unroll
         for(int k = 0; k < 4; ++k) {
-            tab.get((word >> (8 * k)) & 0xFFu, cum[k], freq[k]);
+            tab.get(lds8(row + k), cum[k], freq[k]);
         }
 #pragma unroll 1
-        for(int wi = 0; wi < TILE / 4; ++wi) {
-            const u32 wnext = lds32(row + 4u * (u32)((wi + 1) & (TILE / 4 - 1)));
+        for(u32 at = 0; at < (u32)TILE; at += 4u) {
+            const u32 nx = row + ((at + 4u) & (TILE - 1u));
             u32 ncum[4], nfreq[4];
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
-                tab.get((wnext >> (8 * k)) & 0xFFu, ncum[k], nfreq[k]);
+                tab.get(lds8(nx + k), ncum[k], nfreq[k]);
             }
             RcCut cuts[4];
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
-                const bool active = !RAGGED || tix * TILE + wi * 4 + k < n_eff;
+                const bool active = !RAGGED || tix * TILE + at + k < n_eff;
                 if(POW2) {
-                    rc_enc_step_pow2<WIDE ? 3 : 2>(st, tcur, shift, cum[k], freq[k], cuts[k], active);
+                    rc_enc2_step_pow2<WIDE ? 3 : 2>(st, tcur, shift, cum[k], freq[k], cuts[k], active);
                 } else {
                     const u32 t = rc_div(st.range, total, magic);
-                    rc_enc_step<WIDE ? 3 : 2>(st, cum[k], freq[k], t, cuts[k], active);
+                    rc_enc2_step<WIDE ? 3 : 2>(st, cum[k], freq[k], t, cuts[k], active);
                 }
             }
-            rc_enc_commit(st, cuts, sink);
+            rc_enc2_commit(st, cuts, sink);
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
                 cum[k] = ncum[k];
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(32 * ENC_SEG_WARPS) k_enc_seg(SegArgs a)
     }
     const bool last = seg + 1u == nseg_b;
     const u32 own = (last ? S1 + 5u : S1 + 1u) - (S0 + 1u);
-    RcEnc st;
+    RcEnc2 st;  // the multiplier form of the step: this kernel is bound by the integer pipe (rc_lane.cuh)
     RcSegSink sink;
     rc_seg_begin(st, sink, a.payload + off + RC_STATIC_HDR + S0 + 1u, mine ? own : 0u, range0);
     const u32 total = has ? tots[lane] : 0u;
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(32 * ENC_SEG_WARPS) k_enc_seg(SegArgs a)
         if(!rc_seg_end(st, sink, last)) {
             atomicOr(a.err, ERR_INTERNAL);
         }
-        a.lows[b * (u64)a.nseg + seg] = st.low;
+        a.lows[b * (u64)a.nseg + seg] = (u32)st.x;
     }
 }
 

@@ -162,8 +162,8 @@ RC_HD void rc_add96(u32& low, u32& o_lo, u32& o_hi, u32 term)
 // Rare part of cutting a word: all-ones words in play (cpprcoder.h:405-435 / :767-800 at
 // word granularity).  Kept out of line; callers pass copies so that the lane state proper
 // never has its address taken and stays in registers.
-template <class Sink>
-RC_COLD void rc_enc_word_slow(RcEnc& e, u32 word, u32 ovf, Sink& s)
+template <class Sink, class Enc>
+RC_COLD void rc_enc_word_slow(Enc& e, u32 word, u32 ovf, Sink& s)
 {
     if(ovf) {  // a carry reaches the deferred word: the 0xFF run behind it rolls over to zeros
         e.pend += ovf;
@@ -270,12 +270,156 @@ RC_HD void rc_enc_step_pow2(RcEnc& e, u32& t, u32 shift, u32 cum, u32 freq, RcCu
     e.ocnt = cut ? (s32)k : e.ocnt;
 }
 
+// ---------------------------------------------------- the encoder step, multiplier form --
+// The same step as rc_enc_step_pow2 / rc_enc_step with the shifting done by MULTIPLYING: the integer
+// pipe of an SM issues half as many warp instructions per cycle as the scheduler can hand out, and the
+// kernels that run many chains per scheduler (k_enc_seg) are bound by exactly that pipe; the
+// multiplier pipe idles.  With m = 2^sh (1, 2^8, 2^16 or 2^24):
+//     (o : low) += cum * t                    one 32 x 32 + 64 multiply-add, the carry ripples into o
+//     low * m                                 low half: the new low; high half: the bytes leaving low
+//     o * m + those bytes                     the new o, up to 25 + 24 bits
+//     2^ocnt * m                              high half non-zero <=> 32 valid bits have left low: cut a
+//                                             word; it IS 2^k, k the bits that stay behind
+// so that o, kept below 2^32 between steps, and 2^ocnt replace the three-word shift register, its
+// bit count, the variable funnel shifts, the mask and the selects of rc_enc_step.
+struct RcEnc2 {
+    u64 x;          // o : low
+    u32 oc;         // 2^ocnt, ocnt in {0, 8, 16, 24}: valid bits in o between steps
+    u32 range;
+    u32 pend, nff;  // as RcEnc
+};
+
+RC_HD u32 rc_norm_mult(u32 r, int maxsh)  // 2^(renormalisation shift of r), see rc_norm_shift
+{
+#if defined(__CUDA_ARCH__) && !defined(RC_NORM_BY_COMPARES)
+    // 8 * (leading zero bytes of r) from the position of its highest bit (one instruction on the
+    // conversion pipe instead of two compares and two selects on the integer pipe), and through asm:
+    // a compiler that sees "multiply by a power of two" turns the multiplications of the step back
+    // into variable shifts, which is the integer-pipe work this form exists to avoid
+    (void)maxsh;  // 2^8 <= r is the caller's promise when maxsh == 2; the same code serves both
+    u32 m;
+    asm("{ .reg .u32 top, sh;\n\tbfind.u32 top, %1;\n\tlop3.b32 sh, top, 24, 0, 0x0C;\n\tshl.b32 %0, 1, sh; }"
+        : "=r"(m)
+        : "r"(r));  // lop3 0x0C: ~a & b
+    return m;
+#elif defined(__CUDA_ARCH__)
+    u32 m;  // two compares and two selects, through asm for the same reason
+    asm("{ .reg .pred p, q;\n\tsetp.lt.u32 p, %1, 0x01000000;\n\tsetp.lt.u32 q, %1, 0x00010000;\n\t"
+        "selp.u32 %0, 0x100, 1, p;\n\tselp.u32 %0, 0x10000, %0, q; }"
+        : "=r"(m)
+        : "r"(r));
+    if(maxsh >= 3) {
+        asm("{ .reg .pred p;\n\tsetp.lt.u32 p, %1, 0x00000100;\n\tselp.u32 %0, 0x1000000, %0, p; }" : "+r"(m) : "r"(r));
+    }
+    return m;
+#else
+    u32 m = (r < 0x01000000u) ? 0x100u : 1u;
+    m = (r < 0x00010000u) ? 0x10000u : m;
+    if(maxsh >= 3) {
+        m = (r < 0x00000100u) ? 0x1000000u : m;
+    }
+    return m;
+#endif
+}
+
+// 32 x 32 -> (lo, hi) and 32 x 32 + 32 -> (lo, hi), the halves as separate 32-bit values so that no
+// 64-bit compare or shift is ever made of them
+RC_HD void rc_mul_wide(u32 a, u32 b, u32& lo, u32& hi)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{ .reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#else
+    const u64 p = (u64)a * b;
+    lo = (u32)p;
+    hi = (u32)(p >> 32);
+#endif
+}
+RC_HD void rc_mad_wide(u32 a, u32 b, u32 c, u32& lo, u32& hi)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{ .reg .u64 p, q;\n\tcvt.u64.u32 q, %4;\n\tmad.wide.u32 p, %2, %3, q;\n\tmov.b64 {%0, %1}, p; }"
+        : "=r"(lo), "=r"(hi)
+        : "r"(a), "r"(b), "r"(c));
+#else
+    const u64 p = (u64)a * b + c;
+    lo = (u32)p;
+    hi = (u32)(p >> 32);
+#endif
+}
+RC_HD u64 rc_mad_wide64(u32 a, u32 b, u64 c)
+{
+#if defined(__CUDA_ARCH__)
+    u64 p;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(a), "r"(b), "l"(c));
+    return p;
+#else
+    return (u64)a * b + c;
+#endif
+}
+
+// everything of a step behind "which multiplier": shift, cut.  When nothing is cut, c.word is o
+// itself (below 2^25): never all ones, which rc_enc2_commit relies on.
+template <int MAXSH>
+RC_HD void rc_enc2_shift(RcEnc2& e, u32 m, RcCut& c)
+{
+    u32 l_lo, l_hi, o_lo, o_hi, c_lo, chi;
+    rc_mul_wide((u32)e.x, m, l_lo, l_hi);
+    rc_mad_wide((u32)(e.x >> 32), m, l_hi, o_lo, o_hi);
+    rc_mul_wide(e.oc, m, c_lo, chi);  // chi: 0, or 2^k with k = ocnt + sh - 32 in {0, 8, 16}
+    const u32 k = MAXSH >= 3 ? (((chi >> 5) & 8u) | ((chi >> 12) & 16u)) : (chi >> 5);
+    c.word = rc_funnel_r(o_lo, o_hi, k);
+    c.ovf = o_hi >> k;
+    c.on = chi != 0u;
+    e.x = ((u64)(o_lo & (chi - 1u)) << 32) | l_lo;  // chi == 0: nothing is cut, the mask is all ones
+    e.oc = chi | c_lo;
+}
+
+// power-of-two total: the chain carries t = range >> shift (rc_enc_step_pow2)
+template <int MAXSH>
+RC_HD void rc_enc2_step_pow2(RcEnc2& e, u32& t, u32 shift, u32 cum, u32 freq, RcCut& c, bool active = true)
+{
+    u32 m = 1u;
+    if(active) {
+        e.x = rc_mad_wide64(cum, t, e.x);
+        const u32 r = freq * t;
+        m = rc_norm_mult(r, MAXSH);
+        t = (r * m) >> shift;
+    }
+    rc_enc2_shift<MAXSH>(e, m, c);
+}
+
+template <int MAXSH>
+RC_HD void rc_enc2_step(RcEnc2& e, u32 cum, u32 freq, u32 t, RcCut& c, bool active = true)
+{
+    u32 m = 1u;
+    if(active) {
+        e.x = rc_mad_wide64(cum, t, e.x);
+        const u32 r = freq * t;
+        m = rc_norm_mult(r, MAXSH);
+        e.range = r * m;
+    }
+    rc_enc2_shift<MAXSH>(e, m, c);
+}
+
+RC_HD RcEnc rc_enc2_view(const RcEnc2& e)  // the same state as the three-word register of RcEnc
+{
+    RcEnc v;
+    v.low = (u32)e.x;
+    v.range = e.range;
+    v.o_lo = (u32)(e.x >> 32);
+    v.o_hi = 0;
+    v.ocnt = (s32)(31u - rc_clz(e.oc));
+    v.pend = e.pend;
+    v.nff = e.nff;
+    return v;
+}
+
 // Commits the cuts of up to N consecutive steps, in order.  The common case is straight
 // line: the parked carry goes into the deferred word, which is pushed, and the new word
 // becomes the deferred one.  All-ones words (cpprcoder.h:431, :796) take the rare path,
 // entered by the whole warp on one vote.  CONVERGED: every lane must call this together.
-template <int N, class Sink>
-RC_HD void rc_enc_commit(RcEnc& e, const RcCut (&c)[N], Sink& s)
+template <int N, class Sink, class Enc>
+RC_HD void rc_enc_commit(Enc& e, const RcCut (&c)[N], Sink& s)
 {
     bool rare = e.nff != 0u || s.tight(N);
 #if defined(__CUDA_ARCH__)
@@ -286,7 +430,7 @@ RC_HD void rc_enc_commit(RcEnc& e, const RcCut (&c)[N], Sink& s)
     }
     if(RC_WARP_ANY(rare)) {
         if(rare) {
-            RcEnc te = e;
+            Enc te = e;
             typename Sink::Checked ts(s);  // may push a long run: this one checks for room
             for(int k = 0; k < N; ++k) {
                 if(c[k].on) {
@@ -303,6 +447,57 @@ RC_HD void rc_enc_commit(RcEnc& e, const RcCut (&c)[N], Sink& s)
 #pragma unroll
 #endif
     for(int k = 0; k < N; ++k) {
+        if(c[k].on) {
+            s.push(e.pend + c[k].ovf);
+            e.pend = c[k].word;
+        }
+    }
+}
+
+// rc_enc_commit for cuts made by rc_enc2_shift: a word that was not cut is never all ones there, so
+// "some cut word is all ones" is one maximum over the words and one compare.
+template <class Sink>
+RC_HD void rc_enc2_commit(RcEnc2& e, const RcCut (&c)[4], Sink& s)
+{
+    u32 top = c[0].word > c[1].word ? c[0].word : c[1].word;
+    top = top > c[2].word ? top : c[2].word;
+    top = top > c[3].word ? top : c[3].word;
+    const bool rare = e.nff != 0u || top == 0xFFFFFFFFu;  // all-ones words in play (cpprcoder.h:431)
+    const bool edge = s.tight(4);                         // first words of a segment / little room left
+    if(RC_WARP_ANY(rare || edge)) {
+        if(RC_WARP_ANY(rare)) {
+            if(rare) {
+                RcEnc2 te = e;
+                typename Sink::Checked ts(s);  // may push a long run: this one checks for room
+                for(int k = 0; k < 4; ++k) {
+                    if(c[k].on) {
+                        rc_enc_word_slow(te, c[k].word, c[k].ovf, ts);
+                    }
+                }
+                e.pend = te.pend;
+                e.nff = te.nff;
+                ts.settle(s);
+                return;
+            }
+        }
+        // no all-ones word anywhere near: the straight-line commit through the checked sink
+        typename Sink::Checked ts(s);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int k = 0; k < 4; ++k) {
+            if(c[k].on) {
+                ts.push(e.pend + c[k].ovf);
+                e.pend = c[k].word;
+            }
+        }
+        ts.settle(s);
+        return;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int k = 0; k < 4; ++k) {
         if(c[k].on) {
             s.push(e.pend + c[k].ovf);
             e.pend = c[k].word;
@@ -751,9 +946,13 @@ struct RcSegSink {
     typedef RcSegSinkChecked Checked;
     u32* out;     // the aligned word that holds the segment's first own byte
     s32 wcount;   // index of the next word; -1: the encoder's placeholder push is still to come
-    u32 hot_lim;  // words wcount .. wcount+3 are whole own words  <=>  (u32)(wcount - 1) < hot_lim
     u32 lo, hi;   // own bytes, as offsets from `out`: [lo, hi), lo < 4
-    RC_HD bool tight(int) const { return !((u32)(wcount - 1) < hot_lim); }
+    // Only the first two pushes need care: the placeholder (index -1) and the word that holds the
+    // phantom bytes (index 0).  Every later word a step cuts is a whole own word: the bytes cut
+    // off the shift register are exactly the bytes the range pass counted, the deferred word lags
+    // them by one, and what does not fill a word stays behind for rc_seg_end.  rc_seg_end checks
+    // that the count came out as promised.
+    RC_HD bool tight(int) const { return wcount < 1; }
     RC_HD void push(u32 w)
     {
         out[wcount] = rc_bswap(w);
@@ -791,12 +990,22 @@ RC_HD void rc_seg_begin(RcEnc& e, RcSegSink& s, u8* first, u32 nbytes, u32 range
     s.wcount = -1;
     s.lo = ph;
     s.hi = ph + nbytes;
-    s.hot_lim = (s.hi >> 2) >= 4u ? (s.hi >> 2) - 4u : 0u;
     e.low = 0;
     e.range = range0;
     e.o_lo = 0;
     e.o_hi = 0;
     e.ocnt = (s32)(8u * ph);  // phantom bytes: they belong to whoever owns the bytes in front
+    e.pend = 0;
+    e.nff = 0;
+}
+
+RC_HD void rc_seg_begin(RcEnc2& e, RcSegSink& s, u8* first, u32 nbytes, u32 range0)
+{
+    RcEnc v;
+    rc_seg_begin(v, s, first, nbytes, range0);
+    e.x = 0;
+    e.oc = 1u << (u32)v.ocnt;
+    e.range = range0;
     e.pend = 0;
     e.nff = 0;
 }
@@ -819,6 +1028,12 @@ RC_HD bool rc_seg_end(RcEnc& e, RcSegSink& s, bool last)
     }
     s.wcount = cs.s.wcount;
     return at + nw == s.hi;
+}
+
+RC_HD bool rc_seg_end(RcEnc2& e, RcSegSink& s, bool last)
+{
+    RcEnc v = rc_enc2_view(e);
+    return rc_seg_end(v, s, last);
 }
 
 // (big-endian 32 bits at p) += tail; a carry runs towards lower addresses through 0xFF bytes

@@ -16,10 +16,14 @@
 // C ABI of libb2rc.so.  There is no CPU coding path: without a CUDA device encode /
 // decode return false / Status_Error.
 //
-// This is new code written against the reference's interface; no reference source is
-// reused.  Stream concept kept: encoders need `s32 write(s32, const u8*)`, decoders
-// are given the whole output through write() as well (a superset of the reference,
-// whose writeByte() fails where capacity < output, cpprcoder.h:1047-1054).
+// The three coder classes are new code written against the reference's interface.  The
+// small host-side types below them in the file -- the typedef block, Status / Result,
+// IStream and MemoryStream -- FOLLOW the reference's bodies (cpprcoder.h:83-247, :964-1077)
+// statement for statement: MemoryStream's growth policy is observable through capacity(),
+// so reserve / resize / writeByte / expand have to behave identically.  Stream concept kept:
+// encoders need `s32 write(s32, const u8*)`, decoders are given the whole output through
+// write() as well (a superset of the reference, whose writeByte() fails where capacity <
+// output, cpprcoder.h:1047-1054).
 #ifndef INC_CPPRCODER_B200_H_
 #define INC_CPPRCODER_B200_H_
 
@@ -27,6 +31,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <vector>
 
 #include "../../include/b2rc.h"
@@ -177,6 +182,7 @@ private:
     MemoryStream(const MemoryStream&) = delete;
     MemoryStream& operator=(const MemoryStream&) = delete;
     static const s32 EXPAND_LIMIT_SIZE = 4096 * 4;
+    friend struct detail_access;  // the coder classes below write their output straight into buffer_
 
     bool expand(s32 size)
     {
@@ -207,6 +213,20 @@ private:
     s32 capacity_;
     s32 size_;
     u8* buffer_;
+};
+
+// Lets the coders use an EMPTY MemoryStream's buffer as the destination of the C ABI call itself:
+// reserve() (which may discard, cpprcoder.h:985-994 -- nothing is lost in an empty stream), code, resize().
+struct detail_access {
+    static u8* writable(MemoryStream& s, u64 need)
+    {
+        if(0 != s.size_ || 0x7FFFFFF0ULL < need) {
+            return CPPRCODER_NULL;
+        }
+        s.reserve(static_cast<s32>(need));
+        return (CPPRCODER_NULL != s.buffer_ && static_cast<u64>(s.capacity_) >= need) ? s.buffer_ : CPPRCODER_NULL;
+    }
+    static void written(MemoryStream& s, u64 made) { s.size_ = static_cast<s32>(made); }
 };
 
 namespace detail
@@ -243,6 +263,8 @@ bool write_all(T& stream, const u8* bytes, u64 size)
     return true;
 }
 
+// Any stream: the container is made in pinned host memory that the context owns (never initialised,
+// reused from call to call) and handed to write() from there.
 template<class T>
 bool encode_to(T& stream, int mode, u32 blockSize, u64 size, const u8* bytes)
 {
@@ -250,13 +272,35 @@ bool encode_to(T& stream, int mode, u32 blockSize, u64 size, const u8* bytes)
     if(CPPRCODER_NULL == ctx) {
         return false;
     }
-    std::vector<u8> out(static_cast<size_t>(b2rc_bound(mode, size, blockSize)));
-    u64 made = 0;
     static const u8 nothing = 0;
-    if(B2RC_OK != b2rc_encode(ctx, mode, blockSize, bytes ? bytes : &nothing, size, out.data(), out.size(), &made)) {
+    const u8* out = CPPRCODER_NULL;
+    u64 made = 0;
+    if(B2RC_OK != b2rc_encode_staged(ctx, mode, blockSize, bytes ? bytes : &nothing, size, &out, &made)) {
         return false;
     }
-    return write_all(stream, out.data(), made);
+    return write_all(stream, out, made);
+}
+
+// MemoryStream, empty (what run_rangecoder / run_adaptive pass, test/main.cpp:270-271): the stream's own
+// buffer is the destination of the C ABI call -- no staging, no second copy.
+inline bool encode_to(MemoryStream& stream, int mode, u32 blockSize, u64 size, const u8* bytes)
+{
+    b2rc_ctx* ctx = context();
+    if(CPPRCODER_NULL == ctx) {
+        return false;
+    }
+    const u64 bound = b2rc_bound(mode, size, blockSize);
+    u8* dst = (0 != bound) ? detail_access::writable(stream, bound) : CPPRCODER_NULL;
+    if(CPPRCODER_NULL == dst) {
+        return encode_to<MemoryStream>(stream, mode, blockSize, size, bytes);
+    }
+    static const u8 nothing = 0;
+    u64 made = 0;
+    if(B2RC_OK != b2rc_encode(ctx, mode, blockSize, bytes ? bytes : &nothing, size, dst, bound, &made)) {
+        return false;
+    }
+    detail_access::written(stream, made);
+    return true;
 }
 
 template<class T>
@@ -266,18 +310,37 @@ int decode_to(T& stream, u64 size, const u8* bytes)
     if(CPPRCODER_NULL == ctx) {
         return B2RC_E_CUDA;
     }
-    u64 total = 0;
-    int rc = b2rc_peek(bytes, size, CPPRCODER_NULL, CPPRCODER_NULL, &total, CPPRCODER_NULL);
-    if(B2RC_OK != rc) {
-        return rc;
-    }
-    std::vector<u8> out(static_cast<size_t>(total ? total : 1));
+    const u8* out = CPPRCODER_NULL;
     u64 made = 0;
-    rc = b2rc_decode(ctx, bytes, size, out.data(), out.size(), &made);
+    const int rc = b2rc_decode_staged(ctx, bytes, size, &out, &made);  // validates the index before it allocates
     if(B2RC_OK != rc) {
         return rc;
     }
-    return write_all(stream, out.data(), made) ? B2RC_OK : B2RC_E_DST_SMALL;
+    return write_all(stream, out, made) ? B2RC_OK : B2RC_E_DST_SMALL;
+}
+
+inline int decode_to(MemoryStream& stream, u64 size, const u8* bytes)
+{
+    b2rc_ctx* ctx = context();
+    if(CPPRCODER_NULL == ctx) {
+        return B2RC_E_CUDA;
+    }
+    u64 total = 0;
+    const int rc = b2rc_check(bytes, size, &total);  // header AND index: the size is believed only then
+    if(B2RC_OK != rc) {
+        return rc;
+    }
+    u8* dst = detail_access::writable(stream, total ? total : 1);
+    if(CPPRCODER_NULL == dst) {
+        return decode_to<MemoryStream>(stream, size, bytes);
+    }
+    u64 made = 0;
+    const int rc2 = b2rc_decode(ctx, bytes, size, dst, total ? total : 1, &made);
+    if(B2RC_OK != rc2) {
+        return rc2;
+    }
+    detail_access::written(stream, made);
+    return B2RC_OK;
 }
 } // namespace detail
 

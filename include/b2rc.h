@@ -94,6 +94,19 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
 int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n);
 /* Parses a container header held in host memory. */
 int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, uint64_t* total, uint64_t* nblocks);
+/* b2rc_peek + the whole index, on the host, before anything is allocated for the output: offsets
+ * monotone and inside the container, every payload at least as long as its mode's header, the
+ * restart table (if any) inside the container.  *total = bytes b2rc_decode will write.  A container
+ * of a kilobyte cannot make a caller allocate gigabytes: total <= nblocks * block_size, and
+ * nblocks is bounded by the index that is really there. */
+int b2rc_check(const uint8_t* src, uint64_t n, uint64_t* total);
+/* The same two calls with the RESULT left in host memory that the context owns (pinned, never
+ * initialised, reused by the next staged call on this context): what the C++ drop-in classes use
+ * when they cannot code straight into the caller's stream.  *out stays valid until the next
+ * b2rc_*_staged call or b2rc_ctx_destroy. */
+int b2rc_encode_staged(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src, uint64_t n,
+                       const uint8_t** out, uint64_t* out_n);
+int b2rc_decode_staged(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, const uint8_t** out, uint64_t* out_n);
 
 /* ---- whole-container calls, DEVICE pointers (what bench.py times as `value`) ----
  * d_src / d_dst must be 16-byte aligned.  `cuda_stream` is a cudaStream_t (NULL = the

@@ -301,7 +301,7 @@ long sim_encode_segmented(const u8* src, u32 n, u8* dst, size_t cap, u32 lead, u
     for(u32 j = nseg; j-- > 0;) {
         const bool last = j + 1 == nseg;
         const u32 own = (last ? S[nseg] + 5u : S[j + 1] + 1u) - (S[j] + 1u);
-        RcEnc e;
+        RcEnc2 e;  // the multiplier form of the step, as k_enc_seg runs it
         RcSegSink sink;
         rc_seg_begin(e, sink, coded + S[j] + 1u, own, R[j]);
         u32 t = pow2 ? (e.range >> shT) : 0;
@@ -312,18 +312,18 @@ long sim_encode_segmented(const u8* src, u32 n, u8* dst, size_t cap, u32 lead, u
                 const bool active = i + k < hi;
                 const u32 c = active ? src[i + k] : 0;
                 if(pow2) {
-                    rc_enc_step_pow2<2>(e, t, shT, cum[c], cum[c + 1] - cum[c], cuts[k], active);
+                    rc_enc2_step_pow2<2>(e, t, shT, cum[c], cum[c + 1] - cum[c], cuts[k], active);
                 } else {
                     const u32 tt = active ? rc_div(e.range, total, magic) : 0;
-                    rc_enc_step<3>(e, cum[c], cum[c + 1] - cum[c], tt, cuts[k], active);
+                    rc_enc2_step<3>(e, cum[c], cum[c + 1] - cum[c], tt, cuts[k], active);
                 }
             }
-            rc_enc_commit(e, cuts, sink);
+            rc_enc2_commit(e, cuts, sink);
         }
         if(!rc_seg_end(e, sink, last)) {
             return -3;
         }
-        lows[j] = e.low;
+        lows[j] = (u32)e.x;
     }
     // ---- the seams, in order, and the restart points
     u32 low = 0;
