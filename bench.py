@@ -608,6 +608,22 @@ def run_ours(args):
                            "compressed_ratio": r["compressed_ratio"], "parity_blocks_checked": pb, "steps": x_steps}
             del x
 
+    # ---- the C++ drop-in classes end to end (what a caller of RangeEncoder<> gets): tools/e2e_cpp, its own process
+    e2e_cpp = None
+    exe = ROOT / "tools" / "e2e_cpp"
+    if world == 1 and not args.no_e2e and not args.no_extra and mode in (0, 1) and block == 65536 and gen == "zipf" and exe.exists():
+        import subprocess
+        try:
+            r = subprocess.run([str(exe), str(n), str(min(args.steps, 3)), str(mode)], capture_output=True, text=True,
+                               timeout=600, env=dict(os.environ, CPPRCODER_B200_DEVICE=str(local)))
+            if r.returncode == 0:
+                e2e_cpp = json.loads(r.stdout.strip().splitlines()[-1])
+                assert e2e_cpp["first_mib_byte_sum"] == int(leg.data[:1 << 20].astype(np.uint64).sum()), "e2e_cpp coded another stream"
+            else:
+                e2e_cpp = {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:  # a missing compiler or binary must not cost the headline its line
+            e2e_cpp = {"error": repr(e)[:300]}
+
     if rank == 0:
         peaks = {}
         try:
@@ -660,6 +676,8 @@ def run_ours(args):
             line["strong_efficiency"] = strong["efficiency"]
         if extra:
             line["extra"] = extra
+        if e2e_cpp:
+            line["e2e_cpp"] = e2e_cpp
         if cpu_line:
             line["cpu_baseline"] = cpu_line
         print(json.dumps(line), flush=True)

@@ -39,6 +39,9 @@ SIGNATURES = {
     "b2rc_check": (C.c_int, [_P, _U64, C.POINTER(_U64)]),
     "b2rc_encode_staged": (C.c_int, [_P, C.c_int, _U32, _P, _U64, C.POINTER(_P), C.POINTER(_U64)]),
     "b2rc_decode_staged": (C.c_int, [_P, _P, _U64, C.POINTER(_P), C.POINTER(_U64)]),
+    "b2rc_host_alloc": (C.c_int, [_U64, C.POINTER(_P)]),
+    "b2rc_host_free": (None, [_P]),
+    "b2rc_host_copy": (None, [_P, _P, _U64]),
     "b2rc_encode_device": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
     "b2rc_decode_device": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
     "b2rc_k_histogram": (C.c_int, [_P, _P, _U64, _U32, _P, _P]),

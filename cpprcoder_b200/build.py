@@ -49,3 +49,16 @@ def build_sim(verbose: bool = False) -> Path:
         if verbose:
             print(out)
     return so
+
+
+def build_tools(verbose: bool = False) -> Path:
+    """tools/e2e_cpp: the drop-in C++ classes timed end to end (bench.py's e2e_cpp leg runs it)."""
+    out = ROOT / "tools" / "e2e_cpp"
+    src = ROOT / "tools" / "e2e_cpp.cpp"
+    deps = [src, PKG / "include" / "cpprcoder_b200.h", ROOT / "include" / "b2rc.h", PKG / "libb2rc.so"]
+    if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
+        log = _run(["g++", "-O2", "-std=c++17", "-Wall", str(src), "-o", str(out), f"-L{PKG}", "-lb2rc",
+                    "-Wl,-rpath,$ORIGIN/../cpprcoder_b200"], ROOT)
+        if verbose:
+            print(log)
+    return out

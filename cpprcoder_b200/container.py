@@ -13,6 +13,7 @@ import numpy as np
 MAGIC = 0x43523242  # 'B','2','R','C'
 HEADER = 32
 MIN_BLOCK, MAX_BLOCK = 64, 1 << 23
+ADAPTIVE_RESTART_WORDS = 131  # u32 per restart point of the adaptive coder: bytes shifted, low, range, 256 x u16 counts
 
 
 def nblocks_of(n: int, block: int) -> int:
@@ -33,7 +34,8 @@ class Info:
     payload_base: int
     seg_syms: int = 0                 # restart points (static range coder, byte rANS) every so many symbols (0: none)
     restart: np.ndarray | None = None  # uint32 [nblocks][records][3]: static: bytes shifted, encoder low, range;
-    #                                    byte rANS: coded bytes still ahead of the decoder, its state x, 0
+    #                                    byte rANS: coded bytes still ahead of the decoder, its state x, 0;
+    #                                    adaptive: [..][131]: the static coder's three, then 256 u16 symbol counts
 
     def payload(self, buf: np.ndarray, b: int) -> np.ndarray:
         lo = self.payload_base + int(self.offsets[b])
@@ -59,7 +61,7 @@ def parse(buf) -> Info:
     if magic != MAGIC or version != 1 or mode > 3 or not block_ok(block):
         raise ValueError("bad container header")
     seg_syms = (flags >> 8) * 64
-    if flags and ((flags & 0xFF) != 1 or mode not in (0, 2) or restart_records(block, seg_syms) == 0):
+    if flags and ((flags & 0xFF) != 1 or mode not in (0, 1, 2) or restart_records(block, seg_syms) == 0):
         raise ValueError("bad container flags")
     if nblocks != nblocks_of(total, block) or HEADER + 8 * (nblocks + 1) > buf.size:
         raise ValueError("container index does not fit")
@@ -70,10 +72,11 @@ def parse(buf) -> Info:
     restart = None
     if flags:
         at = base + ((int(offsets[-1]) + 3) & ~3)
-        words = nblocks * restart_records(block, seg_syms) * 3
+        per = ADAPTIVE_RESTART_WORDS if mode == 1 else 3
+        words = nblocks * restart_records(block, seg_syms) * per
         if at + 4 * words > buf.size:
             raise ValueError("restart table does not fit")
-        restart = np.frombuffer(buf[at:at + 4 * words].tobytes(), dtype=np.uint32).reshape(nblocks, -1, 3)
+        restart = np.frombuffer(buf[at:at + 4 * words].tobytes(), dtype=np.uint32).reshape(nblocks, -1, per)
     return Info(mode, block, total, nblocks, offsets, base, seg_syms if flags else 0, restart)
 
 

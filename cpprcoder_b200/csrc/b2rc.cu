@@ -9,10 +9,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "b2rc_kernels.cuh"
 #include "b2rc_encseg.cuh"
+#include "b2rc_adaptseg.cuh"
 #include "b2rc_ans.cuh"
 #include "b2rc_blk.cuh"
 
@@ -57,11 +59,14 @@ struct b2rc_ctx {
     u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
     u64 max_phases;  // <= B2RC_PHASES; env B2RC_PHASES overrides (1 switches the phased decode off)
     u32 seg_syms;    // restart points of the static coder every so many symbols; env B2RC_RESTART_SYMS (0: none)
+    u32 seg_syms_adaptive;  // the same for the adaptive coder (524 B per point); env B2RC_ADAPTIVE_RESTART_SYMS (0: none)
     u32* restart;    // device scratch: the table while a container is being written / read
     size_t restart_cap;
     // segmented static encode (b2rc_encseg.cuh): the range pass's records and the segments' final lows
     u8* h_stage;  // pinned host staging of the *_staged calls
     size_t h_stage_cap;
+    u8* h_in;     // pinned host staging of large pageable sources
+    size_t h_in_cap;
     u32* seg_recs;
     size_t seg_recs_cap;
     u32* seg_lows;
@@ -131,6 +136,12 @@ int grow(b2rc_ctx* ctx, T*& p, size_t& cap, size_t want_bytes)
     return B2RC_OK;
 }
 
+}  // namespace
+extern "C" {
+static int grow_host(b2rc_ctx* ctx, u8*& buf, size_t& cap, size_t want);  // pinned host staging, below
+}
+namespace
+{
 bool block_ok(u32 block)
 {
     return block >= B2RC_MIN_BLOCK && block <= B2RC_MAX_BLOCK && (block % 64u) == 0;
@@ -151,10 +162,20 @@ bool seg_ok(u32 block_size, u32 seg_syms)
 // segment length a container of this mode / block size is written with by this context
 bool has_restart(int mode)
 {
-    return mode == B2RC_MODE_STATIC || mode == B2RC_MODE_RANS_BYTE;  // the two one-chain-per-block coders with a static model
+    // the one-chain-per-block coders: static model (a point is three words) and, with the model's
+    // counts in every point, the adaptive range coder
+    return mode == B2RC_MODE_STATIC || mode == B2RC_MODE_RANS_BYTE || mode == B2RC_MODE_ADAPTIVE;
+}
+// u32 words per restart point: {bytes shifted, low, range}; the adaptive coder adds its 256 u16 symbol counts
+u32 rec_words(int mode)
+{
+    return mode == B2RC_MODE_ADAPTIVE ? 3u + 128u : 3u;
 }
 u32 seg_for(const b2rc_ctx* ctx, int mode, u32 block_size)
 {
+    if(mode == B2RC_MODE_ADAPTIVE) {  // the points hold u16 counts: blocks of at most 65536 bytes
+        return (block_size <= 65536u && seg_ok(block_size, ctx->seg_syms_adaptive)) ? ctx->seg_syms_adaptive : 0u;
+    }
     return (has_restart(mode) && seg_ok(block_size, ctx->seg_syms)) ? ctx->seg_syms : 0u;
 }
 bool aligned16(const void* p)
@@ -206,6 +227,7 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
+    CK(cudaFuncSetAttribute(k_dec_adaptive_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_ADAPT_SEG_SMEM));
     CK(cudaFuncSetAttribute(k_dec_static_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(true)));
     CK(cudaFuncSetAttribute(k_dec_static_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(false)));
     CK(cudaFuncSetAttribute(k_enc_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(false, ENC_SEG_WARPS)));
@@ -258,6 +280,28 @@ int map_kernel_err(int bits)
         return B2RC_E_INTERNAL;
     }
     return B2RC_OK;
+}
+
+// Pageable host memory makes every cudaMemcpyAsync a staged, synchronous copy inside the driver
+// (about a quarter of the PCIe rate).  Page-locking the caller's buffer for the call (cudaHostRegister)
+// was measured and is worse still (profiles/r2_ncu_notes.md).  Large pageable SOURCES are therefore
+// moved chunk by chunk into pinned staging by a few threads (b2rc_host_copy) while the previous
+// chunk is on the wire; B2RC_STAGE_HOST=0 switches that off.
+bool is_pageable(const void* ptr)
+{
+    static const bool enabled = [] {
+        const char* e = getenv("B2RC_STAGE_HOST");
+        return !(e && atol(e) == 0);
+    }();
+    if(!enabled || !ptr) {
+        return false;
+    }
+    cudaPointerAttributes a;
+    if(cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
 }
 
 struct DeviceGuard {
@@ -332,9 +376,10 @@ uint64_t b2rc_bound(int mode, uint64_t n, uint32_t block_size)
     }
     const u64 last = n - (nb - 1) * block_size;
     // room for a restart table at the shortest segment length a context can be set to
-    const u64 table = (mode == B2RC_MODE_STATIC || mode == B2RC_MODE_RANS_BYTE)
-                          ? 4ull + nb * 12ull * b2rc_restart_records(block_size, B2RC_MIN_RESTART_SYMS)
-                          : 0ull;
+    const u64 table = !has_restart(mode) ? 0ull
+                      : 4ull + nb * 4ull * rec_words(mode) *
+                                   b2rc_restart_records(block_size, mode == B2RC_MODE_ADAPTIVE ? B2RC_MIN_ADAPTIVE_RESTART_SYMS
+                                                                                              : B2RC_MIN_RESTART_SYMS);
     return index_bytes(nb) + (nb - 1) * b2rc_slot_bytes_for(mode, block_size) + b2rc_slot_bytes_for(mode, (u32)last) +
            table;
 }
@@ -397,6 +442,13 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
     }
     if(const char* e = getenv("B2RC_FORCE_EXACT")) {
         ctx->force_exact = atol(e) ? 1u : 0u;
+    }
+    ctx->seg_syms_adaptive = B2RC_DEFAULT_ADAPTIVE_RESTART_SYMS;
+    if(const char* e = getenv("B2RC_ADAPTIVE_RESTART_SYMS")) {
+        const long v = atol(e);
+        if(v == 0 || (v >= (long)B2RC_MIN_ADAPTIVE_RESTART_SYMS && v <= (1 << 22) && v % 64 == 0)) {
+            ctx->seg_syms_adaptive = (u32)v;
+        }
     }
     if(const char* e = getenv("B2RC_PHASES")) {
         const long v = atol(e);
@@ -488,6 +540,9 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     }
     if(ctx->h_stage) {
         cudaFreeHost(ctx->h_stage);
+    }
+    if(ctx->h_in) {
+        cudaFreeHost(ctx->h_in);
     }
     for(int k = 0; k < B2RC_PIPE_STREAMS; ++k) {
         if(ctx->pipe[k]) {
@@ -592,7 +647,7 @@ int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, u
     }
     if(h[3] != 0u) {  // a restart table: static range coder or byte rANS, a legal segment length, nothing else set
         const u32 seg = (h[3] >> 8) * 64u;
-        if((h[3] & 0xFFu) != 1u || (md != (u32)B2RC_MODE_STATIC && md != (u32)B2RC_MODE_RANS_BYTE) || !seg_ok(h[2], seg)) {
+        if((h[3] & 0xFFu) != 1u || !has_restart((int)md) || !seg_ok(h[2], seg)) {
             return B2RC_E_CORRUPT;
         }
     }
@@ -760,7 +815,7 @@ int b2rc_k_encode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
     a.seg_syms = d_restart ? seg_syms : 0u;
     if(d_restart) {
         // 0xFF: "no such point" for blocks shorter than the segment start
-        CK(cudaMemsetAsync(d_restart, 0xFF, (size_t)(nb * b2rc_restart_records(block_size, seg_syms) * 12u), st));
+        CK(cudaMemsetAsync(d_restart, 0xFF, (size_t)(nb * b2rc_restart_records(block_size, seg_syms) * 4u * rec_words(mode)), st));
     }
     const unsigned grid = (unsigned)((nb + 31) / 32);
     KernelTimer kt(ctx, B2RC_K_ENCODE, st);
@@ -881,6 +936,14 @@ int b2rc_k_decode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
     a.seg_syms = seg_syms;
     const u32 nseg = b2rc_restart_records(block_size, seg_syms) + 1u;
     KernelTimer kt(ctx, B2RC_K_DECODE, st);
+    if(mode == B2RC_MODE_ADAPTIVE) {
+        if(block_size > 65536u) {
+            return B2RC_E_ARG;
+        }
+        const dim3 agrid((unsigned)((nblocks + 31) / 32), nseg);
+        k_dec_adaptive_seg<<<agrid, 32, DEC_ADAPT_SEG_SMEM, st>>>(a);
+        return launch_check(ctx, "k_dec_adaptive_seg");
+    }
     if(mode == B2RC_MODE_RANS_BYTE) {
         const dim3 agrid((unsigned)((nblocks + 31) / 32), (nseg + ANS_SEG_WARPS - 1u) / ANS_SEG_WARPS);
         k_ans_dec_byte_seg<<<agrid, 32 * ANS_SEG_WARPS, ANS_DEC_BYTE_SEG_SMEM, st>>>(a);
@@ -1081,7 +1144,7 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
     if(need_hist && (rc = grow(ctx, ctx->freq16, ctx->freq_cap, (size_t)(nb * 512 + 16))) != B2RC_OK) {
         return rc;
     }
-    const u64 table_words = seg ? nb * 3ull * b2rc_restart_records(block_size, seg) : 0ull;
+    const u64 table_words = seg ? nb * (u64)rec_words(mode) * b2rc_restart_records(block_size, seg) : 0ull;
     if(seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(table_words * 4 + 16))) != B2RC_OK) {
         return rc;
     }
@@ -1176,7 +1239,7 @@ int b2rc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t*
         CK(cudaMemcpyAsync(&ctx->h_res->total, d_src + B2RC_HEADER_BYTES + 8 * nb, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const u64 pay = ctx->h_res->total;
-        const u64 bytes = nb * 12ull * b2rc_restart_records(block, seg);
+        const u64 bytes = nb * 4ull * rec_words(mode) * b2rc_restart_records(block, seg);
         if(pay > n - idx || align4(pay) + bytes > n - idx) {
             return B2RC_E_CORRUPT;
         }
@@ -1254,7 +1317,8 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     const u32 nrec = seg ? b2rc_restart_records(block_size, seg) : 0u;
     const u32 P = (mode == B2RC_MODE_STATIC && nb) ? enc_seg_plan(ctx, block_size, seg) : 0u;  // b2rc_encseg.cuh
     int rc;
-    if(seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(nb * nrec * 12ull + 16))) != B2RC_OK) {
+    const u64 rw = rec_words(mode);
+    if(seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(nb * nrec * 4ull * rw + 16))) != B2RC_OK) {
         return rc;
     }
     if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
@@ -1268,6 +1332,10 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     u8* d_payload = ctx->stage_out + idx;
     u64* d_offsets = reinterpret_cast<u64*>(ctx->stage_out + B2RC_HEADER_BYTES);
     cudaStream_t s0 = ctx->pipe[0];
+    const bool stage_src = n >= (16ull << 20) && is_pageable(src);
+    if(stage_src && (rc = grow_host(ctx, ctx->h_in, ctx->h_in_cap, (size_t)n + 16)) != B2RC_OK) {
+        return rc;
+    }
     CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), s0));
     CK(cudaMemsetAsync(ctx->d_ends, 0, 8, s0));
     if(nb == 0) {
@@ -1283,7 +1351,10 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         if(c == 0 || c < B2RC_PIPE_STREAMS) {
             CK(cudaStreamWaitEvent(st, ctx->index_ready, 0));
         }
-        CK(cudaMemcpyAsync(ctx->stage_in + byte0, src + byte0, bytes, cudaMemcpyHostToDevice, st));
+        if(stage_src) {
+            b2rc_host_copy(ctx->h_in + byte0, src + byte0, bytes);  // chunk c-1 is on the wire meanwhile
+        }
+        CK(cudaMemcpyAsync(ctx->stage_in + byte0, (stage_src ? ctx->h_in : src) + byte0, bytes, cudaMemcpyHostToDevice, st));
         u16* freq = need_hist ? ctx->freq16 + b0 * 256 : nullptr;
         if(need_hist && (rc = b2rc_k_histogram(ctx, ctx->stage_in + byte0, bytes, block_size, freq, st)) != B2RC_OK) {
             return rc;
@@ -1291,13 +1362,13 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         SegArgs sa;
         if(P) {  // sizes first (the range pass), the payloads then go straight to their final place
             sa = seg_args(ctx, block_size, P, ctx->stage_in + byte0, bytes, freq, b0, ctx->sizes + b0, d_offsets + b0,
-                          d_payload, bound - idx, seg ? ctx->restart + b0 * nrec * 3ull : nullptr, seg);
+                          d_payload, bound - idx, seg ? ctx->restart + b0 * nrec * rw : nullptr, seg);
             if((rc = static_ranges_launch(ctx, sa, st)) != B2RC_OK) {
                 return rc;
             }
         } else if((rc = b2rc_k_encode_blocks_r(ctx, mode, block_size, ctx->stage_in + byte0, bytes, freq,
                                                ctx->slots + b0 * stride, stride, ctx->sizes + b0,
-                                               seg ? ctx->restart + b0 * nrec * 3ull : nullptr, seg, ctx->d_err, st)) !=
+                                               seg ? ctx->restart + b0 * nrec * rw : nullptr, seg, ctx->d_err, st)) !=
                   B2RC_OK) {
             return rc;
         }
@@ -1337,7 +1408,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         }
     }
     const u64 total = ch.count ? ctx->h_ends[ch.count] : 0;
-    const u64 table_bytes = (u64)nb * nrec * 12ull;
+    const u64 table_bytes = (u64)nb * nrec * 4ull * rw;
     const u64 made = idx + (seg ? align4(total) + table_bytes : total);
     if(out_n) {
         *out_n = made;
@@ -1401,7 +1472,8 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     memcpy(&flags, src + 12, 4);
     const u32 seg = flags ? (flags >> 8) * 64u : 0u;
     const u32 nrec = seg ? b2rc_restart_records(block, seg) : 0u;
-    const u64 table_bytes = (u64)nb * nrec * 12ull;
+    const u64 rw = rec_words(mode);
+    const u64 table_bytes = (u64)nb * nrec * 4ull * rw;
     if(seg && (align4(prev) + table_bytes > payload_len)) {
         return B2RC_E_CORRUPT;
     }
@@ -1412,6 +1484,10 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
         return rc;
     }
     const Chunks ch = plan_chunks(ctx, total, block);
+    const bool stage_src = n >= (16ull << 20) && is_pageable(src);
+    if(stage_src && (rc = grow_host(ctx, ctx->h_in, ctx->h_in_cap, (size_t)n + 16)) != B2RC_OK) {
+        return rc;
+    }
     // range coders, long blocks, more than one chunk in flight: decode in phases (see below)
     u32 phases = 1, per = block;
     const u64 model_bytes = 512ull * 32ull * (block > 65536u ? 4u : 2u);  // per warp of 32 blocks
@@ -1448,11 +1524,15 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
             CK(cudaStreamWaitEvent(st, ctx->index_ready, 0));
         }
         if(p1 > p0) {
-            CK(cudaMemcpyAsync(ctx->stage_in + idx + p0, src + idx + p0, p1 - p0, cudaMemcpyHostToDevice, st));
+            if(stage_src) {
+                b2rc_host_copy(ctx->h_in + idx + p0, src + idx + p0, p1 - p0);
+            }
+            CK(cudaMemcpyAsync(ctx->stage_in + idx + p0, (stage_src ? ctx->h_in : src) + idx + p0, p1 - p0,
+                               cudaMemcpyHostToDevice, st));
         }
         if(phases <= 1) {
             if((rc = b2rc_k_decode_blocks_r(ctx, mode, block, ctx->stage_in + idx, payload_len, d_offsets + b0, b1 - b0,
-                                            ctx->stage_out + byte0, bytes, seg ? ctx->restart + b0 * nrec * 3ull : nullptr,
+                                            ctx->stage_out + byte0, bytes, seg ? ctx->restart + b0 * nrec * rw : nullptr,
                                             seg, ctx->d_err, st)) != B2RC_OK) {
                 return rc;
             }
@@ -1527,7 +1607,7 @@ int b2rc_check(const uint8_t* src, uint64_t n, uint64_t* total_out)
     memcpy(&flags, src + 12, 4);
     if(flags) {
         const u32 seg = (flags >> 8) * 64u;
-        if(align4(prev) + (u64)nb * b2rc_restart_records(block, seg) * 12ull > payload_len) {
+        if(align4(prev) + (u64)nb * b2rc_restart_records(block, seg) * 4ull * rec_words(mode) > payload_len) {
             return B2RC_E_CORRUPT;
         }
     }
@@ -1537,22 +1617,22 @@ int b2rc_check(const uint8_t* src, uint64_t n, uint64_t* total_out)
     return B2RC_OK;
 }
 
-static int grow_host(b2rc_ctx* ctx, size_t want)
+static int grow_host(b2rc_ctx* ctx, u8*& buf, size_t& cap, size_t want)
 {
-    if(want <= ctx->h_stage_cap) {
+    if(want <= cap) {
         return B2RC_OK;
     }
-    if(ctx->h_stage) {
-        CK(cudaFreeHost(ctx->h_stage));
-        ctx->h_stage = nullptr;
-        ctx->h_stage_cap = 0;
+    if(buf) {
+        CK(cudaFreeHost(buf));
+        buf = nullptr;
+        cap = 0;
     }
     void* q = nullptr;
     if(!cuda_ok(ctx, cudaMallocHost(&q, want), "cudaMallocHost")) {
         return B2RC_E_NOMEM;
     }
-    ctx->h_stage = static_cast<u8*>(q);
-    ctx->h_stage_cap = want;
+    buf = static_cast<u8*>(q);
+    cap = want;
     return B2RC_OK;
 }
 
@@ -1563,7 +1643,7 @@ int b2rc_encode_staged(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
         return B2RC_E_ARG;
     }
     DeviceGuard g(ctx->device);
-    const int rc = grow_host(ctx, (size_t)b2rc_bound(mode, n, block_size) + 16);
+    const int rc = grow_host(ctx, ctx->h_stage, ctx->h_stage_cap, (size_t)b2rc_bound(mode, n, block_size) + 16);
     if(rc != B2RC_OK) {
         return rc;
     }
@@ -1582,11 +1662,60 @@ int b2rc_decode_staged(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, const uint
         return rc;
     }
     DeviceGuard g(ctx->device);
-    if((rc = grow_host(ctx, (size_t)total + 16)) != B2RC_OK) {
+    if((rc = grow_host(ctx, ctx->h_stage, ctx->h_stage_cap, (size_t)total + 16)) != B2RC_OK) {
         return rc;
     }
     *out = ctx->h_stage;
     return b2rc_decode(ctx, src, n, ctx->h_stage, ctx->h_stage_cap, out_n);
+}
+
+void b2rc_host_copy(void* dst, const void* src, uint64_t n)
+{
+    // a single thread copies at a third of the PCIe rate; a few of them keep up with it
+    const unsigned hw = std::thread::hardware_concurrency();
+    unsigned threads = hw >= 8 ? 4u : (hw >= 4 ? 2u : 1u);
+    if(n < (32ull << 20)) {
+        threads = 1;
+    }
+    if(threads == 1) {
+        memcpy(dst, src, (size_t)n);
+        return;
+    }
+    const u64 per = ((n / threads) + 4095ull) & ~4095ull;
+    std::vector<std::thread> pool;
+    for(unsigned t = 1; t < threads; ++t) {
+        const u64 lo = per * t, hi = (t + 1 == threads) ? n : (per * (t + 1) < n ? per * (t + 1) : n);
+        if(lo < hi) {
+            pool.emplace_back([=] { memcpy((u8*)dst + lo, (const u8*)src + lo, (size_t)(hi - lo)); });
+        }
+    }
+    memcpy(dst, src, (size_t)(per < n ? per : n));
+    for(auto& th : pool) {
+        th.join();
+    }
+}
+
+int b2rc_host_alloc(uint64_t bytes, void** out)
+{
+    if(!out) {
+        return B2RC_E_ARG;
+    }
+    *out = nullptr;
+    void* q = nullptr;
+    if(cudaMallocHost(&q, bytes ? (size_t)bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        return B2RC_E_NOMEM;
+    }
+    *out = q;
+    return B2RC_OK;
+}
+
+void b2rc_host_free(void* p)
+{
+    if(p) {
+        cudaFreeHost(p);
+        cudaGetLastError();
+    }
 }
 
 // ------------------------------------------------------------- block sort --

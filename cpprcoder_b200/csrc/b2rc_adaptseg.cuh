@@ -1,0 +1,279 @@
+// b2rc_adaptseg.cuh -- restart points for the ADAPTIVE range coder: several chains per block for its
+// decoder (AdaptiveRangeDecoder::decode, cpprcoder.h:872-924), the slowest kernel of the path.
+//
+// The adaptive model is part of the coder's state, so a restart point carries it: besides {bytes
+// shifted out so far, the encoder's low, range} the 256 symbol counts the
+// model holds there (u16: blocks of at most 65536 bytes) -- 524 bytes per point, every 16384 symbols
+// by default.  The payloads stay the reference's bytes; the points live behind them in the container.
+//
+//   k_enc_adaptive (b2rc_kernels.cuh) records the points while it codes (adaptive_mark below);
+//   k_dec_adaptive_seg decodes every segment as a chain of its own: one warp = 32 blocks x one segment.
+//
+// The decoder's model here is the count tree WITHOUT its leaves: a node holds how many symbols so far
+// went into its left subtree; the number that went into the subtree the walk is in comes down with
+// the walk (total so far at the root, then v or sub - v at every level), so the symbol's own count --
+// its frequency -- is what is left at the bottom.  255 nodes instead of 511 entries: 16 KiB of shared
+// memory per warp instead of 32, eleven warps per SM instead of six; for a kernel that is bound by
+// how many chains an SM holds, that is most of the gain.  A segment builds its tree from the point's
+// counts; every segment has to END where the next point stands (records are as untrusted as the
+// rest of the container).
+#pragma once
+#include "b2rc_kernels.cuh"
+
+namespace b2rc
+{
+// ------------------------------------------------------------------ leafless tree --
+struct Leafless {
+    static constexpr u32 S = 64u;  // bytes between consecutive nodes of one lane (u16 [256][32])
+    static __device__ __forceinline__ u32 ld(u32 a) { return lds16v(a); }
+    static __device__ __forceinline__ void st(u32 a, u32 v) { sts16v(a, v); }
+
+    // One level of the walk, L >= 1.  `rem` = low minus everything known to lie below the symbol (times
+    // t); `aid` = address of the node, `v` its count, `cl` / `cr` the counts of its children, `sub` how
+    // many symbols so far lie in the subtree of this node.  Grandchildren are read two levels ahead.
+    template <int L>
+    static __device__ __forceinline__ void level(u32 base, u32 t, u32& rem, u32& aid, u32& v, u32& cl, u32& cr, u32& sub)
+    {
+        u32 g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+        if(L >= 2) {
+            u32 ga;  // base + 4*id*S = 4*aid - 3*base
+            asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(ga) : "r"(aid), "r"(0u - 3u * base));
+            g0 = ld(ga);
+            g1 = ld(ga + S);
+            g2 = ld(ga + 2u * S);
+            g3 = ld(ga + 3u * S);
+        }
+        u32 ca;  // address of the left child: base + 2*id*S = 2*aid - base
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(ca) : "r"(aid), "r"(0u - base));
+        const u32 prod = (v + (1u << L)) * t;  // left subtree: counts + the implicit one per symbol
+        u32 anext, vnext, nl, nr;
+        asm("{ .reg .pred p;\n\tsetp.le.u32 p, %7, %0;\n\t@p sub.u32 %0, %0, %7;\n\t@p sub.u32 %2, %2, %1;\n\t"
+            "@!p mov.u32 %2, %1;\n\t@!p add.u32 %1, %1, 1;\n\t"
+            "selp.u32 %3, %8, %9, p;\n\tselp.u32 %4, %10, %11, p;\n\t"
+            "selp.u32 %5, %12, %13, p;\n\tselp.u32 %6, %14, %15, p; }"
+            : "+r"(rem), "+r"(v), "+r"(sub), "=r"(anext), "=r"(vnext), "=r"(nl), "=r"(nr)
+            : "r"(prod), "r"(ca + S), "r"(ca), "r"(cr), "r"(cl), "r"(g2), "r"(g0), "r"(g3), "r"(g1));
+        st(aid, v);  // incremented when the symbol went left, unchanged otherwise
+        aid = anext;
+        v = vnext;
+        cl = nl;
+        cr = nr;
+    }
+
+    // AdaptiveFrequencyTable::find (cpprcoder.h:1221-1241) in the product domain + update (:1134-1177,
+    // for a model that never halves).  `seen` = symbols decoded so far in the block.  Returns the symbol;
+    // `rem` comes back as low - cum*t, freq as the symbol's frequency.
+    static __device__ __forceinline__ u32 decode(u32 base, u32 t, u32 seen, u32& rem, u32& freq)
+    {
+        u32 aid = base + S;  // node 1, the root
+        u32 v = ld(aid), cl = ld(base + 2u * S), cr = ld(base + 3u * S), sub = seen;
+        level<7>(base, t, rem, aid, v, cl, cr, sub);
+        level<6>(base, t, rem, aid, v, cl, cr, sub);
+        level<5>(base, t, rem, aid, v, cl, cr, sub);
+        level<4>(base, t, rem, aid, v, cl, cr, sub);
+        level<3>(base, t, rem, aid, v, cl, cr, sub);
+        level<2>(base, t, rem, aid, v, cl, cr, sub);
+        level<1>(base, t, rem, aid, v, cl, cr, sub);
+        // the last level: the node's two children are symbols
+        const u32 prod = (v + 1u) * t;
+        u32 bit;
+        asm("{ .reg .pred p;\n\tsetp.le.u32 p, %4, %0;\n\t@p sub.u32 %0, %0, %4;\n\t@p sub.u32 %2, %2, %1;\n\t"
+            "@!p mov.u32 %2, %1;\n\t@!p add.u32 %1, %1, 1;\n\tselp.u32 %3, 1, 0, p; }"
+            : "+r"(rem), "+r"(v), "+r"(sub), "=r"(bit)
+            : "r"(prod));
+        st(aid, v);
+        freq = sub + 1u;
+        return ((2u * ((aid - base) / S)) | bit) & 255u;
+    }
+
+    // The lane's tree from 256 symbol counts (two per word at `leaves`; null: an empty model).
+    static __device__ __forceinline__ void build(u32 base, const u32* leaves)
+    {
+        if(!leaves) {
+            for(u32 id = 0; id < 256u; ++id) {
+                st(base + id * S, 0u);
+            }
+            return;
+        }
+        // totals bottom up, in place ...
+        for(u32 id = 255u; id >= 128u; --id) {
+            const u32 pair = __ldg(leaves + (id - 128u));
+            st(base + id * S, (pair & 0xFFFFu) + (pair >> 16));
+        }
+        for(u32 id = 127u; id >= 1u; --id) {
+            st(base + id * S, ld(base + 2u * id * S) + ld(base + (2u * id + 1u) * S));
+        }
+        // ... then every node takes its LEFT child's total, parents before their children
+        for(u32 id = 1u; id < 128u; ++id) {
+            st(base + id * S, ld(base + 2u * id * S));
+        }
+        for(u32 id = 128u; id < 256u; ++id) {
+            st(base + id * S, __ldg(leaves + (id - 128u)) & 0xFFFFu);
+        }
+        st(base, 0u);
+    }
+};
+
+constexpr u32 DEC_ADAPT_SEG_SMEM = 256u * 32u * 2u + TILE_BYTES + INQ_BYTES;
+
+template <class Src>
+__device__ __forceinline__ void dec_adaptive_seg_tile(u32 tbase, RcDec& d, Src& src, u32 otile_a, u32 tile_off, u32 n_b,
+                                                      u32 lane)
+{
+    const u32 d0 = 256u + tile_off;
+    const u32 mg0 = rc_magic(d0 + lane);
+    const u32 mg1 = rc_magic(d0 + 32u + lane);
+#pragma unroll 1
+    for(int wi = 0; wi < TILE / 4; ++wi) {
+        const u32 mg = wi < 8 ? mg0 : mg1;
+        u32 word = 0;
+#pragma unroll
+        for(int k = 0; k < 4; ++k) {
+            const int j = wi * 4 + k;
+            const u32 magic = __shfl_sync(FULL, mg, j & 31);
+            if(tile_off + j < n_b) {
+                const u32 t = rc_div(d.range, d0 + j, magic);
+                u32 freq;
+                const u32 sym = Leafless::decode(tbase, t, tile_off + j, d.low, freq);  // d.low -= cum * t on the way
+                rc_dec_advance(d, 0u, freq, t, src);
+                word |= sym << (8 * k);
+            }
+        }
+        sts32v(otile_a + lane * ROW + wi * 4, word);
+    }
+}
+
+// grid = (ceil(nblocks / 32), segments per block); one warp per CTA.  Blocks of at most 65536 bytes.
+__global__ void __launch_bounds__(32) k_dec_adaptive_seg(DecArgs a)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    constexpr u32 TAB_BYTES = 256u * 32u * 2u;
+    const u32 sbase = smem_addr(smem);
+    u8* otile = smem + TAB_BYTES;
+    const u32 otile_a = sbase + TAB_BYTES;
+    const u32 queue_a = otile_a + TILE_BYTES;
+
+    const u32 lane = lane_id();
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    const u32 nseg = (a.block + a.seg_syms - 1u) / a.seg_syms;
+    const u32 nrec = nseg - 1u;
+    const u32 seg = blockIdx.y;
+
+    const u8* pay = a.payload;
+    u64 len = 0;
+    if(has) {
+        const u64 o0 = a.offsets[b], o1 = a.offsets[b + 1];
+        if(o0 <= o1 && o1 <= a.payload_len) {
+            pay = a.payload + o0;
+            len = o1 - o0;
+        }
+    }
+    bool ok = has && len >= (u64)RC_ADAPT_HDR + 5u;
+    if(ok) {
+        const u32 want = (u32)pay[0] | ((u32)pay[1] << 8) | ((u32)pay[2] << 16) | ((u32)pay[3] << 24);
+        ok = want == n_b;  // the container, not the payload, says how long block b is
+    }
+    if(has && !ok && seg == 0u) {
+        atomicOr(a.err, ERR_CORRUPT);
+    }
+    const u32 seg_lo = seg * a.seg_syms;
+    u32 seg_hi = seg_lo + a.seg_syms;
+    seg_hi = seg_hi < n_b ? seg_hi : n_b;  // my symbols: [seg_lo, seg_hi)
+    bool mine_ok = ok && seg_lo < n_b;
+    const u32 skip0 = (u32)((uintptr_t)(pay + RC_ADAPT_HDR) & 3u);
+    u32 skip = skip0, word0 = 0, range0 = RC_ADAPT_RANGE0, enc_low = 0;
+    const u32* leaves = nullptr;
+    if(seg != 0u && mine_ok) {
+        const u32* rec = a.restart + (b * nrec + seg - 1u) * (u64)ADAPT_REC_WORDS;
+        const u32 m = rec[0];
+        enc_low = rec[1];
+        range0 = rec[2];
+        leaves = rec + 3;
+        if(m == 0xFFFFFFFFu || (u64)m + RC_ADAPT_HDR + 5u > len) {
+            mine_ok = false;
+            atomicOr(a.err, ERR_CORRUPT);
+        } else {
+            // the byte at offset m of the coded stream plays the part of the dummy first byte
+            word0 = (skip + m) >> 2;
+            skip = (skip + m) & 3u;
+        }
+    }
+    const u32 tbase = sbase + lane * 2u;
+    Leafless::build(tbase, mine_ok ? leaves : nullptr);
+    if(mine_ok && leaves) {
+        // the counts of a point must add up to the symbols in front of it, or the walk's bookkeeping
+        // (and with it every frequency) would be off: the root's total is checked against the position
+        u32 total = 0;
+        for(u32 k = 0; k < 128u; ++k) {
+            const u32 pair = __ldg(leaves + k);
+            total += (pair & 0xFFFFu) + (pair >> 16);
+        }
+        if(total != seg_lo) {
+            mine_ok = false;
+            atomicOr(a.err, ERR_CORRUPT);
+        }
+    }
+    WordSrc src;
+    {
+        const u8* coded = pay + RC_ADAPT_HDR;
+        const u8* wbase = (const u8*)((uintptr_t)coded & ~(uintptr_t)3);
+        src.base = reinterpret_cast<const u32*>(wbase);
+        const u64 room = (u64)((a.payload + a.payload_len) - wbase);
+        src.lim = mine_ok ? (u32)(room < 0xFFFFFFF0ull ? room : 0xFFFFFFF0ull) : 0u;
+        src.q = queue_a + lane * 4u;
+        src.prime(mine_ok ? word0 : 0u);
+    }
+    __syncwarp();
+    const u32 n_eff = mine_ok ? seg_hi : 0u;
+    RcDec d;
+    rc_dec_init(d, range0, skip, src);
+    d.low -= enc_low;
+
+    const u32 n_max = __reduce_max_sync(FULL, n_eff);
+    const u32 tix0 = seg_lo / TILE;
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+    const u32 tix1 = ntiles > tix0 ? ntiles : tix0;
+#pragma unroll 1
+    for(u32 tix = tix0; tix < tix1; ++tix) {
+        if(__all_sync(FULL, src.tile_is_inside())) {
+            WordSrcInside in{src};
+            dec_adaptive_seg_tile(tbase, d, in, otile_a, tix * TILE, n_eff, lane);
+        } else {
+            dec_adaptive_seg_tile(tbase, d, src, otile_a, tix * TILE, n_eff, lane);
+        }
+        __syncwarp();
+        // only this segment's columns of the tile are this warp's to store
+        store_tile(otile, a.dst, a.n, b0, a.block, tix * TILE, lane);
+        __syncwarp();
+    }
+
+    // a segment has to end where the next point stands; the last one with the coded bytes used up
+    if(mine_ok) {
+        const u32 used = 4u * src.rd - skip0 - (u32)d.wbits / 8u;
+        bool good;
+        if(seg_hi < n_b) {
+            const u32* rec = a.restart + (b * nrec + seg) * (u64)ADAPT_REC_WORDS;
+            const u32 m = rec[0];
+            good = m != 0xFFFFFFFFu && (u64)m + RC_ADAPT_HDR + 5u <= len && used == m + 5u;
+            if(good) {
+                const u8* p = pay + RC_ADAPT_HDR + 1u + m;
+                const u32 be = ((u32)p[0] << 24) | ((u32)p[1] << 16) | ((u32)p[2] << 8) | (u32)p[3];
+                good = d.low == be - rec[1] && d.range == rec[2];
+            }
+        } else {
+            good = (u64)used + RC_ADAPT_HDR == len;
+        }
+        if(!good) {
+            atomicOr(a.err, ERR_CORRUPT);
+        }
+    }
+}
+
+}  // namespace b2rc

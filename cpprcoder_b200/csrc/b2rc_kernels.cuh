@@ -692,6 +692,23 @@ struct TreeOps {
     }
 };
 
+constexpr u32 ADAPT_REC_WORDS = 3u + 128u;  // B2RC_ADAPTIVE_RESTART_WORDS: a restart point of the adaptive coder
+
+// Called by k_enc_adaptive at the tile that starts segment j >= 1 of the lane's block: the point's three
+// words, then the model's 256 leaf counts (entries 256..511 of the lane's tree), two per word.
+template <class W>
+__device__ __forceinline__ void adaptive_mark(u32* rec, const RcEnc& st, s32 wcount, const LaneTab<W>& tab)
+{
+    const u32 words = (u32)(wcount + 1) + st.nff;       // words cut off the shift register so far
+    rec[0] = 4u * words + (u32)st.ocnt / 8u - 1u;       // bytes shifted out of low, the dummy byte aside
+    rec[1] = st.low;
+    rec[2] = st.range;
+#pragma unroll 4
+    for(u32 s = 0; s < 256u; s += 2u) {
+        rec[3u + s / 2u] = tab.ld(256u + s) | (tab.ld(257u + s) << 16);
+    }
+}
+
 template <class W, bool RAGGED>
 __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, LaneTab<W>& tab, RcEnc& st,
                                                    SlotSink& sink, u64 b0, u32 n_b, u32 n_max, u32 lane)
@@ -708,6 +725,12 @@ __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, 
         const u32 mg1 = rc_magic(d0 + 32u + lane);
         cp_async_wait<1>();
         __syncwarp();
+        if(a.restart && tix != 0u && (tix * TILE) % a.seg_syms == 0u && tix * TILE < n_b) {
+            // a segment starts here: what a decoder needs to start here too, the model included (b2rc_adaptseg.cuh)
+            const u32 nrec = (a.block + a.seg_syms - 1u) / a.seg_syms - 1u;
+            adaptive_mark(a.restart + ((b0 + lane) * nrec + tix * TILE / a.seg_syms - 1u) * (u64)ADAPT_REC_WORDS, st,
+                          sink.wcount, tab);
+        }
         const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
 #pragma unroll 1
         for(int wi = 0; wi < TILE / 4; ++wi) {

@@ -902,6 +902,27 @@ RC_HD void rc_model_decode(Tab& tab, u32 low, u32 t, u32& sym, u32& cum, u32& fr
     freq = 1u + v;
 }
 
+// The same walk over a tree WITHOUT its leaves (k_dec_adaptive_seg): how many symbols so far lie in
+// the subtree the walk is in comes down with it -- everything seen so far at the root, then the left
+// count or the rest -- and what is left at the bottom is the symbol's own count.  Nodes 1..255 only.
+template <class Tab>
+RC_HD void rc_model_decode_leafless(Tab& tab, u32 low, u32 t, u32 seen, u32& sym, u32& cum, u32& freq)
+{
+    u32 id = 1, base = 0, sub = seen;
+    for(s32 l = 7; l >= 0; --l) {
+        const u32 v = tab.ld(id);
+        const u32 left = v + (1u << l);
+        const bool right = (base + left) * t <= low;
+        tab.st(id, v + (right ? 0u : 1u));
+        base += right ? left : 0u;
+        sub = right ? sub - v : v;
+        id = 2 * id + (right ? 1u : 0u);
+    }
+    sym = id & 255u;
+    cum = base;
+    freq = 1u + sub;
+}
+
 // ================================================== segmented static encode ==
 // RangeEncoder::encode (cpprcoder.h:400-457) as MANY chains per block.  `range` never
 // depends on `low` (cpprcoder.h:401-404: t = range / total; low += cum * t; range = freq * t),

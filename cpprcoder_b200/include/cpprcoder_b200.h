@@ -215,6 +215,57 @@ private:
     u8* buffer_;
 };
 
+// A stream over page-locked host memory (not in the reference): same concept as MemoryStream, fixed
+// capacity, for callers that want the host <-> device copies at full PCIe speed.  The coders write
+// straight into it, as they do into an empty MemoryStream.
+class PinnedStream : public IStream<PinnedStream>
+{
+public:
+    explicit PinnedStream(u64 capacity) : capacity_(0), size_(0), buffer_(CPPRCODER_NULL)
+    {
+        void* p = CPPRCODER_NULL;
+        if(B2RC_OK == b2rc_host_alloc(capacity, &p)) {
+            buffer_ = static_cast<u8*>(p);
+            capacity_ = capacity;
+        }
+    }
+    ~PinnedStream() { b2rc_host_free(buffer_); }
+    u64 capacity() const { return capacity_; }
+    u64 size() const { return size_; }
+    const u8* get() const { return buffer_; }
+    u8* data() { return buffer_; }
+    void resize(u64 size)
+    {
+        CPPRCODER_ASSERT(size <= capacity_);
+        size_ = size;
+    }
+    const u8& operator[](u64 index) const { return buffer_[index]; }
+    s32 write(s32 size, const u8* bytes)
+    {
+        if(size < 0 || capacity_ < size_ + static_cast<u64>(size)) {
+            return -1;
+        }
+        ::memcpy(buffer_ + size_, bytes, static_cast<size_t>(size));
+        size_ += static_cast<u64>(size);
+        return size;
+    }
+    bool writeByte(u8 byte)
+    {
+        if(capacity_ <= size_) {
+            return false;
+        }
+        buffer_[size_++] = byte;
+        return true;
+    }
+
+private:
+    PinnedStream(const PinnedStream&) = delete;
+    PinnedStream& operator=(const PinnedStream&) = delete;
+    u64 capacity_;
+    u64 size_;
+    u8* buffer_;
+};
+
 // Lets the coders use an EMPTY MemoryStream's buffer as the destination of the C ABI call itself:
 // reserve() (which may discard, cpprcoder.h:985-994 -- nothing is lost in an empty stream), code, resize().
 struct detail_access {
@@ -281,25 +332,44 @@ bool encode_to(T& stream, int mode, u32 blockSize, u64 size, const u8* bytes)
     return write_all(stream, out, made);
 }
 
-// MemoryStream, empty (what run_rangecoder / run_adaptive pass, test/main.cpp:270-271): the stream's own
-// buffer is the destination of the C ABI call -- no staging, no second copy.
+// MemoryStream, empty (what run_rangecoder / run_adaptive pass, test/main.cpp:270-271): the container
+// is made in the context's pinned staging (a device-to-host copy into fresh malloc memory runs at a
+// fraction of the PCIe rate) and moved into the stream's own buffer, reserved at its exact size, by
+// a few threads -- no intermediate vector, no zero fill, no second pass through write().
 inline bool encode_to(MemoryStream& stream, int mode, u32 blockSize, u64 size, const u8* bytes)
 {
     b2rc_ctx* ctx = context();
     if(CPPRCODER_NULL == ctx) {
         return false;
     }
-    const u64 bound = b2rc_bound(mode, size, blockSize);
-    u8* dst = (0 != bound) ? detail_access::writable(stream, bound) : CPPRCODER_NULL;
+    static const u8 nothing = 0;
+    const u8* out = CPPRCODER_NULL;
+    u64 made = 0;
+    if(B2RC_OK != b2rc_encode_staged(ctx, mode, blockSize, bytes ? bytes : &nothing, size, &out, &made)) {
+        return false;
+    }
+    u8* dst = detail_access::writable(stream, made);
     if(CPPRCODER_NULL == dst) {
-        return encode_to<MemoryStream>(stream, mode, blockSize, size, bytes);
+        return write_all(stream, out, made);
+    }
+    b2rc_host_copy(dst, out, made);
+    detail_access::written(stream, made);
+    return true;
+}
+
+inline bool encode_to(PinnedStream& stream, int mode, u32 blockSize, u64 size, const u8* bytes)
+{
+    b2rc_ctx* ctx = context();
+    if(CPPRCODER_NULL == ctx || CPPRCODER_NULL == stream.data()) {
+        return false;
     }
     static const u8 nothing = 0;
     u64 made = 0;
-    if(B2RC_OK != b2rc_encode(ctx, mode, blockSize, bytes ? bytes : &nothing, size, dst, bound, &made)) {
+    if(B2RC_OK != b2rc_encode(ctx, mode, blockSize, bytes ? bytes : &nothing, size, stream.data() + stream.size(),
+                              stream.capacity() - stream.size(), &made)) {
         return false;
     }
-    detail_access::written(stream, made);
+    stream.resize(stream.size() + made);
     return true;
 }
 
@@ -319,26 +389,37 @@ int decode_to(T& stream, u64 size, const u8* bytes)
     return write_all(stream, out, made) ? B2RC_OK : B2RC_E_DST_SMALL;
 }
 
+inline int decode_to(PinnedStream& stream, u64 size, const u8* bytes)
+{
+    b2rc_ctx* ctx = context();
+    if(CPPRCODER_NULL == ctx || CPPRCODER_NULL == stream.data()) {
+        return B2RC_E_CUDA;
+    }
+    u64 made = 0;
+    const int rc = b2rc_decode(ctx, bytes, size, stream.data() + stream.size(), stream.capacity() - stream.size(), &made);
+    if(B2RC_OK == rc) {
+        stream.resize(stream.size() + made);
+    }
+    return rc;
+}
+
 inline int decode_to(MemoryStream& stream, u64 size, const u8* bytes)
 {
     b2rc_ctx* ctx = context();
     if(CPPRCODER_NULL == ctx) {
         return B2RC_E_CUDA;
     }
-    u64 total = 0;
-    const int rc = b2rc_check(bytes, size, &total);  // header AND index: the size is believed only then
+    const u8* out = CPPRCODER_NULL;
+    u64 made = 0;
+    const int rc = b2rc_decode_staged(ctx, bytes, size, &out, &made);  // validates the index before it allocates
     if(B2RC_OK != rc) {
         return rc;
     }
-    u8* dst = detail_access::writable(stream, total ? total : 1);
+    u8* dst = detail_access::writable(stream, made ? made : 1);
     if(CPPRCODER_NULL == dst) {
-        return decode_to<MemoryStream>(stream, size, bytes);
+        return write_all(stream, out, made) ? B2RC_OK : B2RC_E_DST_SMALL;
     }
-    u64 made = 0;
-    const int rc2 = b2rc_decode(ctx, bytes, size, dst, total ? total : 1, &made);
-    if(B2RC_OK != rc2) {
-        return rc2;
-    }
+    b2rc_host_copy(dst, out, made);
     detail_access::written(stream, made);
     return B2RC_OK;
 }

@@ -51,6 +51,12 @@ extern "C" {
 #define B2RC_HEADER_BYTES 32u
 #define B2RC_DEFAULT_RESTART_SYMS 8192u /* restart points (static coder, byte rANS), see b2rc_k_encode_blocks_r */
 #define B2RC_MIN_RESTART_SYMS 1024u     /* shortest segment a context accepts (env B2RC_RESTART_SYMS; 0 = none) */
+/* The adaptive coder's restart points carry the model as well (256 u16 symbol counts): 524 bytes each.
+ * Default every 16384 symbols: 3 points = 1572 B per 64 KiB block (+2.4 % of the input size, counted in
+ * every ratio the bench prints); env B2RC_ADAPTIVE_RESTART_SYMS, 0 = none (the reference's stream size). */
+#define B2RC_DEFAULT_ADAPTIVE_RESTART_SYMS 16384u
+#define B2RC_MIN_ADAPTIVE_RESTART_SYMS 4096u
+#define B2RC_ADAPTIVE_RESTART_WORDS 131u /* u32 per point: bytes shifted, low, range, then 256 x u16 counts */
 
 /* Status codes.  0 = the reference's `true` / Status_Success (cpprcoder.h:112-117);
  * negatives map to `false` / Status_Error in the C++ header. */
@@ -107,6 +113,13 @@ int b2rc_check(const uint8_t* src, uint64_t n, uint64_t* total);
 int b2rc_encode_staged(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src, uint64_t n,
                        const uint8_t** out, uint64_t* out_n);
 int b2rc_decode_staged(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, const uint8_t** out, uint64_t* out_n);
+/* Page-locked host memory for callers that want the copies of the host-pointer calls at full PCIe
+ * speed (with pageable memory the driver stages every copy through its own buffers).
+ * cpprcoder::PinnedStream in the C++ header sits on these.  NULL / B2RC_E_NOMEM without a device. */
+int b2rc_host_alloc(uint64_t bytes, void** out);
+void b2rc_host_free(void* p);
+/* memcpy over a few threads for large sizes (the staged results above are copied out with it). */
+void b2rc_host_copy(void* dst, const void* src, uint64_t n);
 
 /* ---- whole-container calls, DEVICE pointers (what bench.py times as `value`) ----
  * d_src / d_dst must be 16-byte aligned.  `cuda_stream` is a cudaStream_t (NULL = the

@@ -468,11 +468,17 @@ long sim_decode(int mode, const u8* stream, size_t stream_len, u32 lead, u8* dst
         ArrTab tab;
         memset(tab.v, 0, sizeof tab.v);
         rc_dec_init(d, RC_ADAPT_RANGE0, (u32)(coded & 3), rd);
+        ArrTab bare;  // the leafless tree of k_dec_adaptive_seg, walked side by side: same answers
+        memset(bare.v, 0, sizeof bare.v);
         for(u32 i = 0; i < want; ++i) {
             const u32 dd = 256u + i;
             const u32 t = rc_div(d.range, dd, rc_magic(dd));
-            u32 sym, cum, freq;
+            u32 sym, cum, freq, s2, c2, f2;
+            rc_model_decode_leafless(bare, d.low, t, i, s2, c2, f2);
             rc_model_decode(tab, d.low, t, sym, cum, freq);
+            if(s2 != sym || c2 != cum || f2 != freq) {
+                return -3;
+            }
             dst[i] = (u8)sym;
             rc_dec_advance(d, cum, freq, t, rd);
         }
