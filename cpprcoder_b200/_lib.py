@@ -27,6 +27,8 @@ _U32 = C.c_uint32
 SIGNATURES = {
     "b2rc_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "b2rc_ctx_destroy": (None, [_P]),
+    "b2rc_ctx_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "b2rc_ctx_devices": (C.c_int, [_P]),
     "b2rc_strerror": (C.c_char_p, [C.c_int]),
     "b2rc_last_cuda_error": (C.c_char_p, [_P]),
     "b2rc_bound": (_U64, [C.c_int, _U64, _U32]),

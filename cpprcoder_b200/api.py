@@ -48,13 +48,20 @@ def blk_decoded_size(n: int) -> int:
 class Context:
     """b2rc_ctx: one per host thread and device."""
 
-    def __init__(self, device: int | None = None):
+    def __init__(self, device: int | None = None, devices: list[int] | None = None):
+        """`devices`: b2rc_ctx_create_multi -- the host-pointer calls (encode / decode) shard the blocks over
+        these devices of this process; the device-pointer calls run on the first."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("cpprcoder_b200 needs a CUDA device: there is no CPU coding path")
-        self.device = torch.cuda.current_device() if device is None else int(device)
         h = C.c_void_p()
-        rc = self.lib.b2rc_ctx_create(self.device, C.byref(h))
+        if devices:
+            self.device = int(devices[0])
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.b2rc_ctx_create_multi(arr, len(devices), C.byref(h))
+        else:
+            self.device = torch.cuda.current_device() if device is None else int(device)
+            rc = self.lib.b2rc_ctx_create(self.device, C.byref(h))
         if rc != _lib.OK:
             raise B2rcError(rc, "b2rc_ctx_create")
         self.h = h

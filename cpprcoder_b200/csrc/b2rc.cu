@@ -26,8 +26,11 @@ using namespace b2rc;
 #define B2RC_PHASES 8                       // launches per chunk of the phased static decode, at most
 #define B2RC_PHASE_MIN_SYMS 16384u          // symbols per block and launch, at least
 
+#define B2RC_MAX_DEVICES 16
 struct b2rc_ctx {
     int device;
+    int ndev;                          // > 1: the host-pointer calls shard over sub[0 .. ndev)
+    b2rc_ctx* sub[B2RC_MAX_DEVICES];   // sub[0] is this context itself
     cudaStream_t stream;
     // device scratch, grown on demand
     u8* slots;
@@ -513,8 +516,39 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         b2rc_ctx_destroy(ctx);
         return rc;
     }
+    ctx->ndev = 1;
+    ctx->sub[0] = ctx;
     *out = ctx;
     return B2RC_OK;
+}
+
+int b2rc_ctx_create_multi(const int* devices, int ndev, b2rc_ctx** out)
+{
+    if(!out || !devices || ndev < 1 || ndev > B2RC_MAX_DEVICES) {
+        return B2RC_E_ARG;
+    }
+    *out = nullptr;
+    b2rc_ctx* head = nullptr;
+    int rc = b2rc_ctx_create(devices[0], &head);
+    if(rc != B2RC_OK) {
+        return rc;
+    }
+    for(int d = 1; d < ndev; ++d) {
+        b2rc_ctx* c = nullptr;
+        if((rc = b2rc_ctx_create(devices[d], &c)) != B2RC_OK) {
+            b2rc_ctx_destroy(head);
+            return rc;
+        }
+        head->sub[d] = c;
+        head->ndev = d + 1;
+    }
+    *out = head;
+    return B2RC_OK;
+}
+
+int b2rc_ctx_devices(const b2rc_ctx* ctx)
+{
+    return ctx ? ctx->ndev : 0;
 }
 
 void b2rc_ctx_destroy(b2rc_ctx* ctx)
@@ -522,6 +556,11 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     if(!ctx) {
         return;
     }
+    for(int d = 1; d < ctx->ndev; ++d) {
+        b2rc_ctx_destroy(ctx->sub[d]);
+        ctx->sub[d] = nullptr;
+    }
+    ctx->ndev = 0;
     DeviceGuard g(ctx->device);
     if(ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
@@ -1294,11 +1333,17 @@ Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block)
 }
 }  // namespace
 
+static int multi_encode(b2rc_ctx* ctx, int mode, u32 block_size, const u8* src, u64 n, u8* dst, u64 dst_cap, u64* out_n);
+static int multi_decode(b2rc_ctx* ctx, const u8* src, u64 n, u8* dst, u64 dst_cap, u64* out_n);
+
 int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src, uint64_t n, uint8_t* dst,
                 uint64_t dst_cap, uint64_t* out_n)
 {
     if(!ctx || !dst || (n && !src) || !mode_ok(mode) || !block_ok(block_size)) {
         return B2RC_E_ARG;
+    }
+    if(ctx->ndev > 1 && b2rc_nblocks(n, block_size) >= 2ull * (u64)ctx->ndev) {
+        return multi_encode(ctx, mode, block_size, src, n, dst, dst_cap, out_n);
     }
     DeviceGuard g(ctx->device);
     const u64 bound = b2rc_bound(mode, n, block_size);
@@ -1450,6 +1495,9 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     if(rc != B2RC_OK) {
         return rc;
     }
+    if(ctx->ndev > 1 && nb >= 2ull * (u64)ctx->ndev) {
+        return multi_decode(ctx, src, n, dst, dst_cap, out_n);
+    }
     if(out_n) {
         *out_n = total;
     }
@@ -1579,6 +1627,169 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, s0));
     CK(cudaStreamSynchronize(s0));
     return map_kernel_err(ctx->h_res->err);
+}
+
+// ------------------------------------------------------------ several devices --
+// b2rc_ctx_create_multi: the host-pointer calls over the devices of one process.  Device d takes the
+// blocks [d * nb / N, (d + 1) * nb / N) on a host thread of its own and codes them with
+// the single-device call into its pinned staging; the sizes meet on the host (no collective), the
+// pieces are stitched by a few copy threads into the container a single device would have written.
+namespace
+{
+struct Piece {
+    u64 blk_lo, blk_hi;
+    const u8* out;   // a container of its own in the device's pinned staging
+    u64 made;
+    int rc;
+};
+u64 rd64(const u8* p)
+{
+    u64 v;
+    memcpy(&v, p, 8);
+    return v;
+}
+}  // namespace
+
+static int multi_encode(b2rc_ctx* ctx, int mode, u32 block_size, const u8* src, u64 n, u8* dst, u64 dst_cap, u64* out_n)
+{
+    const int N = ctx->ndev;
+    const u64 nb = b2rc_nblocks(n, block_size);
+    const u64 idx = index_bytes(nb);
+    if(out_n) {
+        *out_n = b2rc_bound(mode, n, block_size);
+    }
+    if(dst_cap < idx) {
+        return B2RC_E_DST_SMALL;
+    }
+    std::vector<Piece> pc((size_t)N);
+    std::vector<std::thread> pool;
+    for(int d = 0; d < N; ++d) {
+        pc[d].blk_lo = nb * (u64)d / (u64)N;
+        pc[d].blk_hi = nb * (u64)(d + 1) / (u64)N;
+        pool.emplace_back([&, d] {
+            const u64 lo = pc[d].blk_lo * block_size;
+            const u64 hi = pc[d].blk_hi * (u64)block_size < n ? pc[d].blk_hi * (u64)block_size : n;
+            pc[d].rc = b2rc_encode_staged(ctx->sub[d], mode, block_size, src + lo, hi - lo, &pc[d].out, &pc[d].made);
+        });
+    }
+    for(auto& th : pool) {
+        th.join();
+    }
+    u64 total = 0, table = 0;
+    u32 flags = 0;
+    for(int d = 0; d < N; ++d) {
+        if(pc[d].rc != B2RC_OK) {
+            snprintf(ctx->last_err, sizeof ctx->last_err, "device %d: %.200s", ctx->sub[d]->device, ctx->sub[d]->last_err);
+            return pc[d].rc;
+        }
+        const u64 nbd = pc[d].blk_hi - pc[d].blk_lo;
+        const u64 pay = rd64(pc[d].out + B2RC_HEADER_BYTES + 8 * nbd);
+        memcpy(&flags, pc[d].out + 12, 4);
+        total += pay;
+        table += pc[d].made - index_bytes(nbd) - (flags ? align4(pay) : pay);
+    }
+    const u64 made = idx + (flags ? align4(total) + table : total);
+    if(out_n) {
+        *out_n = made;
+    }
+    if(made > dst_cap) {
+        return B2RC_E_DST_SMALL;
+    }
+    const u32 h[8] = {0x43523242u, 1u | ((u32)mode << 16), block_size, flags, (u32)n, (u32)(n >> 32), (u32)nb, (u32)(nb >> 32)};
+    memcpy(dst, h, sizeof h);
+    memset(dst + idx + total, 0, (size_t)((flags ? align4(total) : total) - total));
+    pool.clear();
+    u64 base = 0, tab_at = idx + align4(total);
+    for(int d = 0; d < N; ++d) {
+        const u64 nbd = pc[d].blk_hi - pc[d].blk_lo;
+        const u8* index = pc[d].out + B2RC_HEADER_BYTES;
+        const u64 pay = rd64(index + 8 * nbd);
+        const u64 tab = pc[d].made - index_bytes(nbd) - (flags ? align4(pay) : pay);
+        const u8* from = pc[d].out;
+        const u64 lo = pc[d].blk_lo;
+        pool.emplace_back([=] {
+            for(u64 b = 0; b <= nbd; ++b) {  // the last entry of a piece is the first of the next: the same value
+                const u64 o = rd64(index + 8 * b) + base;
+                memcpy(dst + B2RC_HEADER_BYTES + 8 * (lo + b), &o, 8);
+            }
+            b2rc_host_copy(dst + idx + base, from + index_bytes(nbd), pay);
+            if(tab) {
+                memcpy(dst + tab_at, from + index_bytes(nbd) + align4(pay), (size_t)tab);
+            }
+        });
+        base += pay;
+        tab_at += tab;
+    }
+    for(auto& th : pool) {
+        th.join();
+    }
+    return B2RC_OK;
+}
+
+static int multi_decode(b2rc_ctx* ctx, const u8* src, u64 n, u8* dst, u64 dst_cap, u64* out_n)
+{
+    int mode;
+    u32 block;
+    u64 total, nb;
+    int rc = b2rc_check(src, n, &total);  // header and the whole index, before anything is sized by them
+    if(rc != B2RC_OK || (rc = b2rc_peek(src, n, &mode, &block, nullptr, &nb)) != B2RC_OK) {
+        return rc;
+    }
+    if(out_n) {
+        *out_n = total;
+    }
+    if(dst_cap < total || (total && !dst)) {
+        return B2RC_E_DST_SMALL;
+    }
+    const int N = ctx->ndev;
+    const u64 idx = index_bytes(nb);
+    u32 flags;
+    memcpy(&flags, src + 12, 4);
+    const u32 seg = flags ? (flags >> 8) * 64u : 0u;
+    const u64 rec_bytes = seg ? 4ull * rec_words(mode) * b2rc_restart_records(block, seg) : 0ull;  // per block
+    const u64 pay_end = rd64(src + B2RC_HEADER_BYTES + 8 * nb);
+    std::vector<int> rcs((size_t)N, B2RC_OK);
+    std::vector<std::thread> pool;
+    for(int d = 0; d < N; ++d) {
+        pool.emplace_back([&, d] {
+            // a container of this device's blocks alone, in its pinned staging: header, index from zero, payloads, points
+            b2rc_ctx* c = ctx->sub[d];
+            const u64 lo = nb * (u64)d / (u64)N, hi = nb * (u64)(d + 1) / (u64)N, nbd = hi - lo;
+            const u64 p0 = rd64(src + B2RC_HEADER_BYTES + 8 * lo), p1 = rd64(src + B2RC_HEADER_BYTES + 8 * hi);
+            const u64 byte_lo = lo * block, byte_hi = hi * (u64)block < total ? hi * (u64)block : total;
+            const u64 need = index_bytes(nbd) + align4(p1 - p0) + rec_bytes * nbd;
+            DeviceGuard g(c->device);
+            if((rcs[d] = grow_host(c, c->h_in, c->h_in_cap, (size_t)need + 16)) != B2RC_OK) {
+                return;
+            }
+            u8* sub = c->h_in;
+            const u64 tot_d = byte_hi - byte_lo;
+            const u32 h[8] = {0x43523242u, 1u | ((u32)mode << 16), block, flags, (u32)tot_d, (u32)(tot_d >> 32), (u32)nbd, (u32)(nbd >> 32)};
+            memcpy(sub, h, sizeof h);
+            for(u64 b = 0; b <= nbd; ++b) {
+                const u64 o = rd64(src + B2RC_HEADER_BYTES + 8 * (lo + b)) - p0;
+                memcpy(sub + B2RC_HEADER_BYTES + 8 * b, &o, 8);
+            }
+            b2rc_host_copy(sub + index_bytes(nbd), src + idx + p0, p1 - p0);
+            if(seg) {
+                memset(sub + index_bytes(nbd) + (p1 - p0), 0, (size_t)(align4(p1 - p0) - (p1 - p0)));
+                memcpy(sub + index_bytes(nbd) + align4(p1 - p0), src + idx + align4(pay_end) + rec_bytes * lo, (size_t)(rec_bytes * nbd));
+            }
+            u64 got = 0;
+            rcs[d] = b2rc_decode(c, sub, index_bytes(nbd) + (seg ? align4(p1 - p0) + rec_bytes * nbd : p1 - p0), dst + byte_lo,
+                                 tot_d, &got);
+        });
+    }
+    for(auto& th : pool) {
+        th.join();
+    }
+    for(int d = 0; d < N; ++d) {
+        if(rcs[d] != B2RC_OK) {
+            snprintf(ctx->last_err, sizeof ctx->last_err, "device %d: %.200s", ctx->sub[d]->device, ctx->sub[d]->last_err);
+            return rcs[d];
+        }
+    }
+    return B2RC_OK;
 }
 
 // ------------------------------------------------------- host-side validation --

@@ -23,41 +23,46 @@
 namespace b2rc
 {
 // ------------------------------------------------------------------ leafless tree --
+// Layout: the two CHILDREN of node j share one 32-bit word, [j][lane] (bank == lane: no conflicts, the
+// u16 [node][lane] layout of the full tree has two lanes per bank word); node 2j in the low half, 2j+1
+// in the high half, so the root (node 1) is the high half of word 0.  Arriving at a node the walk
+// holds its count and the word with both children; one level is: multiply, compare, the bookkeeping
+// of the side taken, one 16-bit store (the node), one 32-bit load (the children of the child).
 struct Leafless {
-    static constexpr u32 S = 64u;  // bytes between consecutive nodes of one lane (u16 [256][32])
-    static __device__ __forceinline__ u32 ld(u32 a) { return lds16v(a); }
-    static __device__ __forceinline__ void st(u32 a, u32 v) { sts16v(a, v); }
+    static constexpr u32 S = 128u;  // bytes between consecutive words of one lane (u32 [128][32])
+    static __device__ __forceinline__ u32 node_addr(u32 base, u32 id) { return base + (id >> 1) * S + (id & 1u) * 2u; }
 
-    // One level of the walk, L >= 1.  `rem` = low minus everything known to lie below the symbol (times
-    // t); `aid` = address of the node, `v` its count, `cl` / `cr` the counts of its children, `sub` how
-    // many symbols so far lie in the subtree of this node.  Grandchildren are read two levels ahead.
+    // `rem` = low minus everything known to lie below the symbol (times t); `v` the node's count, `kids`
+    // the word with the counts of its two children, `ka` that word's address, `na` the node's own;
+    // `sub` how many symbols so far lie in this node's subtree.  The words with the GRANDchildren are
+    // requested here, two levels ahead of their use: no shared-memory latency is left on the chain of
+    // the walk, which is per level multiply-add, compare, select.
     template <int L>
-    static __device__ __forceinline__ void level(u32 base, u32 t, u32& rem, u32& aid, u32& v, u32& cl, u32& cr, u32& sub)
+    static __device__ __forceinline__ void level(u32 base, u32 t, u32& rem, u32& v, u32& kids, u32& na, u32& ka, u32& sub)
     {
-        u32 g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+        u32 ga, gl = 0, gr = 0;  // ga = base + 128 * (2 id): the children of the left child; the right child's follow
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(ga) : "r"(ka), "r"(0u - base));
         if(L >= 2) {
-            u32 ga;  // base + 4*id*S = 4*aid - 3*base
-            asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(ga) : "r"(aid), "r"(0u - 3u * base));
-            g0 = ld(ga);
-            g1 = ld(ga + S);
-            g2 = ld(ga + 2u * S);
-            g3 = ld(ga + 3u * S);
+            gl = lds32v(ga);
+            gr = lds32v(ga + S);
         }
-        u32 ca;  // address of the left child: base + 2*id*S = 2*aid - base
-        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(ca) : "r"(aid), "r"(0u - base));
-        const u32 prod = (v + (1u << L)) * t;  // left subtree: counts + the implicit one per symbol
-        u32 anext, vnext, nl, nr;
-        asm("{ .reg .pred p;\n\tsetp.le.u32 p, %7, %0;\n\t@p sub.u32 %0, %0, %7;\n\t@p sub.u32 %2, %2, %1;\n\t"
-            "@!p mov.u32 %2, %1;\n\t@!p add.u32 %1, %1, 1;\n\t"
-            "selp.u32 %3, %8, %9, p;\n\tselp.u32 %4, %10, %11, p;\n\t"
-            "selp.u32 %5, %12, %13, p;\n\tselp.u32 %6, %14, %15, p; }"
-            : "+r"(rem), "+r"(v), "+r"(sub), "=r"(anext), "=r"(vnext), "=r"(nl), "=r"(nr)
-            : "r"(prod), "r"(ca + S), "r"(ca), "r"(cr), "r"(cl), "r"(g2), "r"(g0), "r"(g3), "r"(g1));
-        st(aid, v);  // incremented when the symbol went left, unchanged otherwise
-        aid = anext;
+        const u32 prod = v * t + (t << L);  // left subtree: counts + the implicit one per symbol, times t
+        u32 vnext, knext, nan, kan;
+        // outputs that are written before the last input is read are early-clobber: they must not share a register
+        asm("{ .reg .pred p;\n\t.reg .u32 hi, lo;\n\t"
+            "setp.le.u32 p, %7, %0;\n\t"
+            "@p sub.u32 %0, %0, %7;\n\t@p sub.u32 %2, %2, %1;\n\t@!p mov.u32 %2, %1;\n\t@!p add.u32 %1, %1, 1;\n\t"
+            "shr.u32 hi, %8, 16;\n\tand.b32 lo, %8, 0xFFFF;\n\tselp.u32 %3, hi, lo, p;\n\t"
+            "selp.u32 %4, %12, %11, p;\n\t"
+            "selp.u32 %5, 2, 0, p;\n\tadd.u32 %5, %5, %9;\n\t"
+            "selp.u32 %6, 128, 0, p;\n\tadd.u32 %6, %6, %10; }"
+            : "+r"(rem), "+r"(v), "+r"(sub), "=&r"(vnext), "=&r"(knext), "=&r"(nan), "=&r"(kan)
+            : "r"(prod), "r"(kids), "r"(ka), "r"(ga), "r"(gl), "r"(gr));
+        sts16v(na, v);  // incremented when the symbol went left, unchanged otherwise
+        na = nan;
+        ka = kan;
         v = vnext;
-        cl = nl;
-        cr = nr;
+        kids = knext;
     }
 
     // AdaptiveFrequencyTable::find (cpprcoder.h:1221-1241) in the product domain + update (:1134-1177,
@@ -65,52 +70,53 @@ struct Leafless {
     // `rem` comes back as low - cum*t, freq as the symbol's frequency.
     static __device__ __forceinline__ u32 decode(u32 base, u32 t, u32 seen, u32& rem, u32& freq)
     {
-        u32 aid = base + S;  // node 1, the root
-        u32 v = ld(aid), cl = ld(base + 2u * S), cr = ld(base + 3u * S), sub = seen;
-        level<7>(base, t, rem, aid, v, cl, cr, sub);
-        level<6>(base, t, rem, aid, v, cl, cr, sub);
-        level<5>(base, t, rem, aid, v, cl, cr, sub);
-        level<4>(base, t, rem, aid, v, cl, cr, sub);
-        level<3>(base, t, rem, aid, v, cl, cr, sub);
-        level<2>(base, t, rem, aid, v, cl, cr, sub);
-        level<1>(base, t, rem, aid, v, cl, cr, sub);
-        // the last level: the node's two children are symbols
+        u32 na = base + 2u, ka = base + S;  // node 1, the root, and the word of its children (nodes 2, 3)
+        u32 v = lds16v(na), kids = lds32v(ka), sub = seen;
+        level<7>(base, t, rem, v, kids, na, ka, sub);
+        level<6>(base, t, rem, v, kids, na, ka, sub);
+        level<5>(base, t, rem, v, kids, na, ka, sub);
+        level<4>(base, t, rem, v, kids, na, ka, sub);
+        level<3>(base, t, rem, v, kids, na, ka, sub);
+        level<2>(base, t, rem, v, kids, na, ka, sub);
+        level<1>(base, t, rem, v, kids, na, ka, sub);
+        // the last level: the node's two children are symbols; ka = base + 128 * (its number)
         const u32 prod = (v + 1u) * t;
         u32 bit;
         asm("{ .reg .pred p;\n\tsetp.le.u32 p, %4, %0;\n\t@p sub.u32 %0, %0, %4;\n\t@p sub.u32 %2, %2, %1;\n\t"
             "@!p mov.u32 %2, %1;\n\t@!p add.u32 %1, %1, 1;\n\tselp.u32 %3, 1, 0, p; }"
             : "+r"(rem), "+r"(v), "+r"(sub), "=r"(bit)
             : "r"(prod));
-        st(aid, v);
+        sts16v(na, v);
         freq = sub + 1u;
-        return ((2u * ((aid - base) / S)) | bit) & 255u;
+        return (((ka - base) >> 6) | bit) & 255u;
     }
 
     // The lane's tree from 256 symbol counts (two per word at `leaves`; null: an empty model).
     static __device__ __forceinline__ void build(u32 base, const u32* leaves)
     {
         if(!leaves) {
-            for(u32 id = 0; id < 256u; ++id) {
-                st(base + id * S, 0u);
+            for(u32 j = 0; j < 128u; ++j) {
+                sts32v(base + j * S, 0u);
             }
             return;
         }
         // totals bottom up, in place ...
         for(u32 id = 255u; id >= 128u; --id) {
             const u32 pair = __ldg(leaves + (id - 128u));
-            st(base + id * S, (pair & 0xFFFFu) + (pair >> 16));
+            sts16v(node_addr(base, id), (pair & 0xFFFFu) + (pair >> 16));
         }
         for(u32 id = 127u; id >= 1u; --id) {
-            st(base + id * S, ld(base + 2u * id * S) + ld(base + (2u * id + 1u) * S));
+            const u32 kids = lds32v(base + id * S);  // nodes 2 id and 2 id + 1
+            sts16v(node_addr(base, id), (kids & 0xFFFFu) + (kids >> 16));
         }
         // ... then every node takes its LEFT child's total, parents before their children
         for(u32 id = 1u; id < 128u; ++id) {
-            st(base + id * S, ld(base + 2u * id * S));
+            sts16v(node_addr(base, id), lds32v(base + id * S) & 0xFFFFu);
         }
         for(u32 id = 128u; id < 256u; ++id) {
-            st(base + id * S, __ldg(leaves + (id - 128u)) & 0xFFFFu);
+            sts16v(node_addr(base, id), __ldg(leaves + (id - 128u)) & 0xFFFFu);
         }
-        st(base, 0u);
+        sts16v(base, 0u);
     }
 };
 
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(32) k_dec_adaptive_seg(DecArgs a)
             skip = (skip + m) & 3u;
         }
     }
-    const u32 tbase = sbase + lane * 2u;
+    const u32 tbase = sbase + lane * 4u;
     Leafless::build(tbase, mine_ok ? leaves : nullptr);
     if(mine_ok && leaves) {
         // the counts of a point must add up to the symbols in front of it, or the walk's bookkeeping

@@ -748,6 +748,9 @@ __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, 
                     TreeOps<W>::encode(tab.base, sym, cum, freq);
                 }
                 const u32 t = rc_div(st.range, d0 + j, magic);
+                // the funnel-shift form of the step: this kernel runs one warp per scheduler and is bound by
+                // the latency of its chain; the multiplier form (fewer instructions, longer latencies) was
+                // measured here and lost 7 % (profiles/r2_ncu_notes.md)
                 rc_enc_step<3>(st, cum, freq, t, cuts[k], active);
             }
             rc_enc_commit(st, cuts, sink);

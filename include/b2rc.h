@@ -52,9 +52,12 @@ extern "C" {
 #define B2RC_DEFAULT_RESTART_SYMS 8192u /* restart points (static coder, byte rANS), see b2rc_k_encode_blocks_r */
 #define B2RC_MIN_RESTART_SYMS 1024u     /* shortest segment a context accepts (env B2RC_RESTART_SYMS; 0 = none) */
 /* The adaptive coder's restart points carry the model as well (256 u16 symbol counts): 524 bytes each.
- * Default every 16384 symbols: 3 points = 1572 B per 64 KiB block (+2.4 % of the input size, counted in
- * every ratio the bench prints); env B2RC_ADAPTIVE_RESTART_SYMS, 0 = none (the reference's stream size). */
-#define B2RC_DEFAULT_ADAPTIVE_RESTART_SYMS 16384u
+ * Default every 21888 symbols: a 64 KiB block is three chains for the decoder and carries two points,
+ * 1048 B (+1.6 % of the input size, counted in every ratio the bench prints).  Three, because the
+ * decoder keeps 11 warps of 32 blocks per SM (16 KiB of model each): 1628 on a B200, and a 1 GiB stream
+ * is 512 warps per segment -- four segments would need a second, mostly empty, wave (measured: 10.4 ms
+ * against 6.9).  env B2RC_ADAPTIVE_RESTART_SYMS, 0 = none (the reference's stream size). */
+#define B2RC_DEFAULT_ADAPTIVE_RESTART_SYMS 21888u
 #define B2RC_MIN_ADAPTIVE_RESTART_SYMS 4096u
 #define B2RC_ADAPTIVE_RESTART_WORDS 131u /* u32 per point: bytes shifted, low, range, then 256 x u16 counts */
 
@@ -77,6 +80,16 @@ typedef struct b2rc_ctx b2rc_ctx;
  * per-block sizes, frequency tables) and a stream of its own for the host-pointer calls. */
 int b2rc_ctx_create(int device, b2rc_ctx** out);
 void b2rc_ctx_destroy(b2rc_ctx* ctx);
+/* One context over several devices of ONE process ("multi-GPU = single process, one
+ * stream per device"): the host-pointer calls -- b2rc_encode, b2rc_decode and the *_staged pair, i.e.
+ * everything the C++ drop-in classes use -- shard the blocks by contiguous range over the devices
+ * (SURVEY.md 8e), one host thread per device.  The payload sizes meet on the host, so this path
+ * needs no collective at all; the container is byte for byte the one a single device writes.
+ * The device-pointer calls and the kernel doors of such a context run on devices[0].
+ * A device may be listed more than once (two streams of work on one GPU; also how the path is
+ * tested on a one-GPU box).  1 <= ndev <= 16. */
+int b2rc_ctx_create_multi(const int* devices, int ndev, b2rc_ctx** out);
+int b2rc_ctx_devices(const b2rc_ctx* ctx);
 const char* b2rc_strerror(int code);
 /* Last CUDA error text seen by this context ("" if none). */
 const char* b2rc_last_cuda_error(const b2rc_ctx* ctx);

@@ -128,7 +128,12 @@ long sim_encode(int mode, const u8* src, u32 n, u8* dst, size_t cap, int force_e
     } else {
         ArrTab tab;
         memset(tab.v, 0, sizeof tab.v);
-        rc_enc_init(e, RC_ADAPT_RANGE0);
+        RcEnc2 e2;  // the multiplier form of the step, as k_enc_adaptive runs it
+        e2.x = 0;
+        e2.oc = 1u << 8;
+        e2.range = RC_ADAPT_RANGE0;
+        e2.pend = 0;
+        e2.nff = 0;
         for(u32 i = 0; i < n; i += 4) {
             RcCut cuts[4];
             for(u32 k = 0; k < 4; ++k) {
@@ -137,12 +142,13 @@ long sim_encode(int mode, const u8* src, u32 n, u8* dst, size_t cap, int force_e
                 if(active) {
                     rc_model_encode(tab, src[i + k], cum, freq);
                     const u32 d = 256u + i + k;
-                    t = rc_div(e.range, d, rc_magic(d));
+                    t = rc_div(e2.range, d, rc_magic(d));
                 }
-                rc_enc_step<3>(e, cum, freq, t, cuts[k], active);
+                rc_enc2_step<3>(e2, cum, freq, t, cuts[k], active);
             }
-            rc_enc_commit(e, cuts, sink);
+            rc_enc2_commit(e2, cuts, sink);
         }
+        e = rc_enc2_view(e2);
         const u32 nt = rc_enc_finish(e, sink, tail);
         out.insert(out.end(), tail, tail + nt);
     }

@@ -62,7 +62,9 @@ def test_containers_with_and_without_points_are_interchangeable(oracle):
     try:
         plain, pointed = a.encode(ADAPTIVE, data, 65536), b.encode(ADAPTIVE, data, 65536)
         assert payloads(plain) == payloads(pointed)
-        assert pointed.size - plain.size == 4 * 131 * 3 * 34 + (-plain.size) % 4   # three points a block, 524 B each
+        nrec = container.restart_records(65536, container.parse(pointed).seg_syms)
+        assert nrec == 2                                                            # the default: three chains per block
+        assert pointed.size - plain.size == 4 * 131 * nrec * 34 + (-plain.size) % 4   # 524 B a point
         for c in (a, b):
             assert c.decode(plain).tobytes() == data.tobytes()
             assert c.decode(pointed).tobytes() == data.tobytes()
@@ -80,13 +82,14 @@ def test_damaged_points_are_detected(oracle):
         info = container.parse(enc)
         table_at = info.payload_base + ((int(info.offsets[-1]) + 3) & ~3)
         rng = np.random.default_rng(78)
+        nrec = info.restart.shape[1]
         for trial in range(40):
             bad = enc.copy()
             b = int(rng.integers(0, info.nblocks - 1))
-            j = int(rng.integers(0, 3))
+            j = int(rng.integers(0, nrec))
             w = trial % 4                                      # 0: bytes shifted, 1: low, 2: range, 3: a count
             word_ix = w if w < 3 else 3 + int(rng.integers(0, 128))
-            at = table_at + 4 * ((b * 3 + j) * 131 + word_ix)
+            at = table_at + 4 * ((b * nrec + j) * 131 + word_ix)
             word = int(np.frombuffer(bad[at:at + 4].tobytes(), dtype="<u4")[0])
             if w == 0:
                 word = (word + int(rng.choice([-3, -1, 1, 2, 300]))) & 0xFFFFFFFF
@@ -101,7 +104,7 @@ def test_damaged_points_are_detected(oracle):
         # counts moved between two symbols (the sum still fits the position): the chain goes astray and
         # does not end on the next point
         bad = enc.copy()
-        at = table_at + 4 * ((2 * 3 + 1) * 131 + 3)
+        at = table_at + 4 * ((2 * nrec + 1) * 131 + 3)
         pair = np.frombuffer(bad[at:at + 4].tobytes(), dtype="<u2").copy()
         if pair[0] > 0:
             pair[0] -= 1
