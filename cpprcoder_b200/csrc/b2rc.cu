@@ -30,6 +30,7 @@ using namespace b2rc;
 struct b2rc_ctx {
     int device;
     int ndev;                          // > 1: the host-pointer calls shard over sub[0 .. ndev)
+    int in_multi;                      // set while a sharded call runs: sub[0] is this context, its share is a plain call
     b2rc_ctx* sub[B2RC_MAX_DEVICES];   // sub[0] is this context itself
     cudaStream_t stream;
     // device scratch, grown on demand
@@ -1342,8 +1343,11 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     if(!ctx || !dst || (n && !src) || !mode_ok(mode) || !block_ok(block_size)) {
         return B2RC_E_ARG;
     }
-    if(ctx->ndev > 1 && b2rc_nblocks(n, block_size) >= 2ull * (u64)ctx->ndev) {
-        return multi_encode(ctx, mode, block_size, src, n, dst, dst_cap, out_n);
+    if(ctx->ndev > 1 && !ctx->in_multi && b2rc_nblocks(n, block_size) >= 2ull * (u64)ctx->ndev) {
+        ctx->in_multi = 1;
+        const int rc = multi_encode(ctx, mode, block_size, src, n, dst, dst_cap, out_n);
+        ctx->in_multi = 0;
+        return rc;
     }
     DeviceGuard g(ctx->device);
     const u64 bound = b2rc_bound(mode, n, block_size);
@@ -1495,8 +1499,11 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     if(rc != B2RC_OK) {
         return rc;
     }
-    if(ctx->ndev > 1 && nb >= 2ull * (u64)ctx->ndev) {
-        return multi_decode(ctx, src, n, dst, dst_cap, out_n);
+    if(ctx->ndev > 1 && !ctx->in_multi && nb >= 2ull * (u64)ctx->ndev) {
+        ctx->in_multi = 1;
+        rc = multi_decode(ctx, src, n, dst, dst_cap, out_n);
+        ctx->in_multi = 0;
+        return rc;
     }
     if(out_n) {
         *out_n = total;

@@ -80,7 +80,10 @@ __device__ __forceinline__ void enc_range_tiles(const SegArgs& a, u32 tiles, u32
             if(tix * TILE < n_b) {
                 const u32 j = tix / seg_tiles;
                 rec[2u * j] = bits >> 3;
-                rec[2u * j + 1u] = POW2 ? (t << shift) : range;  // any range with the same range / total serves
+                // any range with the same range / total serves a decoder; ONE form is written whatever path the
+                // warp took (the path depends on which blocks share a warp, which a multi-device split changes):
+                // power-of-two total (shift != 0, or total 1): the quotient shifted back; else the range itself
+                rec[2u * j + 1u] = POW2 ? (t << shift) : ((range >> shift) << shift);
             }
         }
         const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
@@ -578,9 +581,10 @@ __global__ void __launch_bounds__(SEAM_THREADS) k_enc_seams(SegArgs a)
             [&](u32 i, u32 shifted, u32 lo2, u32 range) {
                 if(rrow && i != 0u && i % a.seg_syms == 0u) {
                     u32* r = rrow + (i / a.seg_syms - 1u) * 3u;
+                    const u32 sh2 = (run & (run - 1u)) == 0u ? 31u - rc_clz(run) : 0u;  // as k_enc_ranges writes it
                     r[0] = shifted;
                     r[1] = lo2;
-                    r[2] = range;
+                    r[2] = (range >> sh2) << sh2;
                 }
             });
         if(over || at != cap) {

@@ -263,7 +263,7 @@ __device__ __forceinline__ void enc_static_tiles(const EncArgs& a, u32 tiles, co
                 const u32 words = (u32)(sink.wcount + 1) + st.nff;  // words cut off the shift register so far
                 rec[0] = 4u * words + (u32)st.ocnt / 8u - 1u;       // bytes shifted out of low, the dummy byte aside
                 rec[1] = st.low;
-                rec[2] = POW2 ? (tcur << shift) : st.range;         // any range with the same range / total serves
+                rec[2] = POW2 ? (tcur << shift) : ((st.range >> shift) << shift);  // one form whatever the warp's path (b2rc_encseg.cuh)
             }
         }
         const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(32) k_enc_static(EncArgs a)
                     u32* rec = a.restart + (b * nrec + i / a.seg_syms - 1u) * 3u;
                     rec[0] = shifted;
                     rec[1] = low;
-                    rec[2] = range;
+                    rec[2] = (range >> shift) << shift;
                 }
             });
         if(over) {
