@@ -39,6 +39,7 @@ SIGNATURES = {
     "b2rc_decode": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64)]),
     "b2rc_peek": (C.c_int, [_P, _U64, C.POINTER(C.c_int), C.POINTER(_U32), C.POINTER(_U64), C.POINTER(_U64)]),
     "b2rc_check": (C.c_int, [_P, _U64, C.POINTER(_U64)]),
+    "b2rc_container_bytes": (C.c_int, [_P, _U64, C.POINTER(_U64)]),
     "b2rc_encode_staged": (C.c_int, [_P, C.c_int, _U32, _P, _U64, C.POINTER(_P), C.POINTER(_U64)]),
     "b2rc_decode_staged": (C.c_int, [_P, _P, _U64, C.POINTER(_P), C.POINTER(_U64)]),
     "b2rc_host_alloc": (C.c_int, [_U64, C.POINTER(_P)]),

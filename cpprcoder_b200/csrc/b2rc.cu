@@ -1799,6 +1799,43 @@ static int multi_decode(b2rc_ctx* ctx, const u8* src, u64 n, u8* dst, u64 dst_ca
     return B2RC_OK;
 }
 
+int b2rc_container_bytes(const uint8_t* prefix, uint64_t have, uint64_t* need)
+{
+    if(!prefix || !need) {
+        return B2RC_E_ARG;
+    }
+    if(have < B2RC_HEADER_BYTES) {
+        *need = B2RC_HEADER_BYTES + 8;
+        return B2RC_OK;
+    }
+    u32 h[8];
+    memcpy(h, prefix, sizeof h);
+    const u32 md = h[1] >> 16;
+    if(h[0] != 0x43523242u || (h[1] & 0xFFFFu) != 1u || !mode_ok((int)md) || !block_ok(h[2])) {
+        return B2RC_E_CORRUPT;
+    }
+    const u64 nb = (u64)h[6] | ((u64)h[7] << 32);
+    if(nb > (1ull << 40)) {
+        return B2RC_E_CORRUPT;
+    }
+    const u64 idx = index_bytes(nb);
+    if(have < idx) {
+        *need = idx;
+        return B2RC_OK;
+    }
+    const u64 last = rd64(prefix + idx - 8);
+    u64 total = idx + last;
+    if(h[3] != 0u) {
+        const u32 seg = (h[3] >> 8) * 64u;
+        if((h[3] & 0xFFu) != 1u || !has_restart((int)md) || !seg_ok(h[2], seg)) {
+            return B2RC_E_CORRUPT;
+        }
+        total = idx + align4(last) + nb * 4ull * rec_words((int)md) * b2rc_restart_records(h[2], seg);
+    }
+    *need = total;
+    return B2RC_OK;
+}
+
 // ------------------------------------------------------- host-side validation --
 int b2rc_check(const uint8_t* src, uint64_t n, uint64_t* total_out)
 {

@@ -597,26 +597,12 @@ private:
     AdaptiveRangeDecoder(const AdaptiveRangeDecoder&) = delete;
     AdaptiveRangeDecoder& operator=(const AdaptiveRangeDecoder&) = delete;
 
-    // Total container length once enough of it is known; the smallest prefix that tells
-    // more when it is not; 0 for garbage.
+    // Total container length once enough of it is known (restart table included); the smallest prefix
+    // that tells more when it is not; 0 for garbage.
     static u64 containerBytes(const u8* bytes, u64 have)
     {
-        if(have < B2RC_HEADER_BYTES) {
-            return B2RC_HEADER_BYTES + 8;
-        }
-        u32 h[8];
-        ::memcpy(h, bytes, sizeof h);
-        if(h[0] != 0x43523242U || (h[1] & 0xFFFFU) != 1U) {
-            return 0;
-        }
-        const u64 nblocks = static_cast<u64>(h[6]) | (static_cast<u64>(h[7]) << 32);
-        const u64 index = B2RC_HEADER_BYTES + 8ULL * (nblocks + 1);
-        if(have < index) {
-            return index;
-        }
-        u64 last;
-        ::memcpy(&last, bytes + index - 8, 8);
-        return index + last;
+        u64 need = 0;
+        return B2RC_OK == b2rc_container_bytes(bytes, have, &need) ? need : 0;
     }
 
     T* stream_;

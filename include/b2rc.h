@@ -113,6 +113,10 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
 int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n);
 /* Parses a container header held in host memory. */
 int b2rc_peek(const uint8_t* src, uint64_t n, int* mode, uint32_t* block_size, uint64_t* total, uint64_t* nblocks);
+/* How long is the container that starts at `prefix`?  *need = its total length once `have` bytes of it
+ * tell (header, index, restart table and all); otherwise the shortest prefix that tells more.
+ * B2RC_E_CORRUPT for something that is not a container.  (Streaming callers: AdaptiveRangeDecoder.) */
+int b2rc_container_bytes(const uint8_t* prefix, uint64_t have, uint64_t* need);
 /* b2rc_peek + the whole index, on the host, before anything is allocated for the output: offsets
  * monotone and inside the container, every payload at least as long as its mode's header, the
  * restart table (if any) inside the container.  *total = bytes b2rc_decode will write.  A container
