@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <thread>
 #include <vector>
@@ -85,6 +86,8 @@ struct b2rc_ctx {
     } * h_res;  // pinned
     u32* blk_rounds;  // block sort: doubling rounds per block of the last forward call
     size_t blk_rounds_cap;
+    u32* blk_tie_list;  // block sort: [0] how many blocks of the call have a period, [1 ..] which
+    size_t blk_tie_cap;
     u8* blk_ties;     // block sort: scratch of the tie replay (block list, ranks, range queues)
     size_t blk_ties_cap;
     u64 blk_last_blocks;
@@ -573,6 +576,7 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     cudaFree(ctx->stage_out);
     cudaFree(ctx->d_err);
     cudaFree(ctx->blk_rounds);
+    cudaFree(ctx->blk_tie_list);
     cudaFree(ctx->blk_ties);
     cudaFree(ctx->d_total);
     if(ctx->h_res) {
@@ -1995,7 +1999,8 @@ static int blk_forward_launch(b2rc_ctx* ctx, const u8* d_src, u8* d_dst, u64 b0,
         const u64 now = nb - done < 0x7FFFFFFFull ? nb - done : 0x7FFFFFFFull;
         KernelTimer kt(ctx, B2RC_K_BLK_FORWARD, st);
         k_blk_fwd<<<(unsigned)now, BLK_THREADS, BLK_FWD_SMEM, st>>>(d_src + (b0 + done) * BLK_N, d_dst + (b0 + done) * BLK_CODED,
-                                                                    ctx->blk_rounds + b0 + done, nullptr, nullptr);
+                                                                    ctx->blk_rounds + b0 + done, nullptr, nullptr,
+                                                                    ctx->blk_tie_list, (u32)(b0 + done));
         const int rc = launch_check(ctx, "k_blk_fwd");
         if(rc != B2RC_OK) {
             return rc;
@@ -2005,27 +2010,26 @@ static int blk_forward_launch(b2rc_ctx* ctx, const u8* d_src, u8* d_dst, u64 b0,
     return B2RC_OK;
 }
 
-// Blocks with a period (bit 31 of their rounds word, not bit 30): the row number B1 wrote is the canonical
-// one; the reference's depends on the swaps of its quicksort.  k_blk_ties replays them (b2rc_blk.cuh, B3).
-// The stream must have drained: the rounds words are read here.  `fixed` (optional) receives the blocks
-// whose row number was rewritten.
+// Blocks with a period: the row number B1 wrote is the canonical one; the reference's depends on the swaps of
+// its quicksort.  k_blk_ties replays them (b2rc_blk.cuh, B3).  B1 appended such blocks to a device list through
+// an atomic counter: the host reads the counter alone (one word, the stream drains for it) and does nothing more
+// when it is zero -- no copy of per-block words, no host work proportional to the number of blocks.
+// `fixed` (optional) receives the blocks whose row number was rewritten.
 static int blk_fix_ties(b2rc_ctx* ctx, const u8* d_src, u8* d_dst, u64 nb, cudaStream_t st, std::vector<u64>* fixed)
 {
     if(nb == 0) {
         return B2RC_OK;
     }
-    std::vector<u32> flags((size_t)nb);
-    CK(cudaMemcpyAsync(flags.data(), ctx->blk_rounds, (size_t)(nb * 4), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ctx->h_res->pad, ctx->blk_tie_list, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    std::vector<u32> list;
-    for(u64 b = 0; b < nb; ++b) {
-        if((flags[(size_t)b] >> 30) == 2u) {
-            list.push_back((u32)b);
-        }
-    }
-    if(list.empty()) {
+    const u32 count = (u32)ctx->h_res->pad;
+    if(count == 0) {
         return B2RC_OK;
     }
+    std::vector<u32> list((size_t)count);
+    CK(cudaMemcpyAsync(list.data(), ctx->blk_tie_list + 1, (size_t)count * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::sort(list.begin(), list.end());  // the counter hands places out in arrival order
     const size_t batch = list.size() < 592 ? list.size() : 592;  // four waves of one CTA per SM; 320 KiB of scratch per block
     const size_t rk_bytes = (size_t)BLK_N * 2, q_bytes = (size_t)2 * BLK_TIES_QUEUE * sizeof(TieRange);
     int rc;
@@ -2088,10 +2092,12 @@ int b2rc_blk_encode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc;
-    if((rc = grow(ctx, ctx->blk_rounds, ctx->blk_rounds_cap, (size_t)(nb * 4 + 16))) != B2RC_OK) {
+    if((rc = grow(ctx, ctx->blk_rounds, ctx->blk_rounds_cap, (size_t)(nb * 4 + 16))) != B2RC_OK ||
+       (rc = grow(ctx, ctx->blk_tie_list, ctx->blk_tie_cap, (size_t)(nb * 4 + 16))) != B2RC_OK) {
         return rc;
     }
     ctx->blk_last_blocks = nb;
+    CK(cudaMemsetAsync(ctx->blk_tie_list, 0, 4, st));
     if(nb && (rc = blk_forward_launch(ctx, d_src, d_dst, 0, nb, st)) != B2RC_OK) {
         return rc;
     }
@@ -2150,13 +2156,17 @@ static int blk_host(b2rc_ctx* ctx, bool forward, const uint8_t* src, uint64_t n,
     int rc;
     if((rc = grow(ctx, ctx->stage_in, ctx->stage_in_cap, (size_t)(n + 16))) != B2RC_OK ||
        (rc = grow(ctx, ctx->stage_out, ctx->stage_out_cap, (size_t)(need + 16))) != B2RC_OK ||
-       (forward && (rc = grow(ctx, ctx->blk_rounds, ctx->blk_rounds_cap, (size_t)(nb * 4 + 16))) != B2RC_OK)) {
+       (forward && (rc = grow(ctx, ctx->blk_rounds, ctx->blk_rounds_cap, (size_t)(nb * 4 + 16))) != B2RC_OK) ||
+       (forward && (rc = grow(ctx, ctx->blk_tie_list, ctx->blk_tie_cap, (size_t)(nb * 4 + 16))) != B2RC_OK)) {
         return rc;
     }
     if(forward) {
         ctx->blk_last_blocks = nb;
     }
     cudaStream_t s0 = ctx->pipe[0];
+    if(forward) {
+        CK(cudaMemsetAsync(ctx->blk_tie_list, 0, 4, s0));  // ordered before every chunk by index_ready
+    }
     CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), s0));
     CK(cudaEventRecord(ctx->index_ready, s0));
     // chunk boundaries at even block numbers keep every chunk 4-byte aligned on the coded side

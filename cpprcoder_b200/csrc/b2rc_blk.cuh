@@ -609,8 +609,12 @@ __device__ __forceinline__ u32 blk_place_short(u32 n, const u16* list, u16* sa, 
 // bit 30 = all rotations are equal (one repeated byte): row 0, which is what the reference reports.
 // list / rk_out (both optional, used together by the tie replay B3): CTA c sorts block list[c] and leaves the
 // final rank of every rotation in rk_out[c][32 768] instead of touching dst.
+// `ties` (optional): ties[0] counts the blocks of this call that have a period (and are not one repeated
+// byte), ties[1 ..] lists them as tie_base + block number, in no particular order -- the host reads the
+// counter alone and, only when it is not zero, the list (blocks are numbered in 32 bits: 128 TiB per call).
 __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_fwd(const u8* __restrict__ src, u8* __restrict__ dst, u32* __restrict__ rounds,
-                                                             const u32* __restrict__ list, u16* __restrict__ rk_out)
+                                                             const u32* __restrict__ list, u16* __restrict__ rk_out,
+                                                             u32* __restrict__ ties = nullptr, u32 tie_base = 0)
 {
     extern __shared__ __align__(16) u8 blk_sm[];
     u16* sa = reinterpret_cast<u16*>(blk_sm + BF_SA);
@@ -704,6 +708,9 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) k_blk_fwd(const u8* __restrict
         *reinterpret_cast<u16*>(o + BLK_N) = rk[0];
         if(rounds) {
             rounds[blk] = nrounds | (distinct < BLK_N ? 0x80000000u : 0u) | (distinct == 1u ? 0x40000000u : 0u);
+        }
+        if(ties && distinct < BLK_N && distinct != 1u) {
+            ties[1u + atomicAdd(ties, 1u)] = tie_base + (u32)blk;
         }
     }
 }

@@ -94,14 +94,17 @@ def test_restart_helpers_and_flags(lib):
     nb = 16
     plain = 32 + 8 * (nb + 1) + nb * lib.b2rc_slot_bytes(65536)
     assert lib.b2rc_bound(0, nb * 65536, 65536) >= plain + 3 + nb * 63 * 12
-    assert lib.b2rc_bound(1, nb * 65536, 65536) == plain  # the adaptive coder has no restart points
-    # peek accepts the flag for the static coder only, with a legal segment length
+    # the adaptive coder's points carry the model: 131 words each, at most every 4096 symbols
+    assert lib.b2rc_bound(1, nb * 65536, 65536) >= plain + 3 + nb * 15 * 524
+    assert lib.b2rc_bound(3, nb * 65536, 65536) == 32 + 8 * (nb + 1) + nb * lib.b2rc_slot_bytes_for(3, 65536)  # rANS word: none
+    # peek accepts the flag for the coders that have restart points, with a legal segment length
     def peek(header):
         raw = bytes(header) + bytes(8 * 17)
         buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
         return lib.b2rc_peek(buf, len(raw), None, None, None, None)
     assert peek(container.pack_header(0, 65536, nb * 65536, nb, 8192)) == 0
-    assert peek(container.pack_header(1, 65536, nb * 65536, nb, 8192)) == -3
+    assert peek(container.pack_header(1, 65536, nb * 65536, nb, 8192)) == 0
+    assert peek(container.pack_header(3, 65536, nb * 65536, nb, 8192)) == -3
     bad = bytearray(container.pack_header(0, 65536, nb * 65536, nb, 8192))
     bad[12] = 3                                   # unknown flag bit
     assert peek(bad) == -3
