@@ -283,13 +283,32 @@ struct detail_access {
 namespace detail
 {
 // One b2rc context per host thread, created on first use (device 0 unless
-// CPPRCODER_B200_DEVICE is set).  Null when there is no CUDA device.
+// CPPRCODER_B200_DEVICE or CPPRCODER_B200_DEVICES is set).  Null when there is no CUDA device.
 inline b2rc_ctx* context()
 {
     struct Holder {
         b2rc_ctx* ctx;
         Holder() : ctx(CPPRCODER_NULL)
         {
+            // CPPRCODER_B200_DEVICES=0,1,2,3: one context over several devices (b2rc_ctx_create_multi);
+            // the host-pointer calls these classes make then shard the blocks over them
+            if(const char* list = ::getenv("CPPRCODER_B200_DEVICES")) {
+                int devs[16];
+                int n = 0;
+                for(const char* p = list; *p && n < 16;) {
+                    devs[n++] = ::atoi(p);
+                    while(*p && *p != ',') {
+                        ++p;
+                    }
+                    if(*p == ',') {
+                        ++p;
+                    }
+                }
+                if(0 < n) {
+                    b2rc_ctx_create_multi(devs, n, &ctx);
+                    return;
+                }
+            }
             const char* dev = ::getenv("CPPRCODER_B200_DEVICE");
             b2rc_ctx_create(dev ? ::atoi(dev) : 0, &ctx);
         }
