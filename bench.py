@@ -338,6 +338,7 @@ class Leg:
             if ev:
                 ev[1].record()
             rcdist.decode_shard(dec_ctx or ctx, self.shard, self.dec)
+            self.shard.offsets  # the collective was started before the decode; its result is part of the step
         if ev:
             ev[2].record()
 

@@ -26,23 +26,45 @@ def shard_of(n_total: int, block: int, rank: int, world: int):
     return blk_lo * block, min(blk_hi * block, n_total), blk_lo, blk_hi
 
 
-def allgather_sizes(local_sizes: torch.Tensor, n_total: int, block: int, group=None) -> torch.Tensor:
-    """All ranks' per-block payload sizes, in block order (int64, length nblocks).
+class _Gather:
+    """An all-gather of payload sizes in flight; result() waits for it and puts the rows in block order."""
 
-    `local_sizes` holds this rank's blocks (int32, on the device NCCL runs on, or on CPU for gloo).
-    Shards differ by at most one block, so every rank pads to the same length before the collective."""
+    def __init__(self, work, gathered, counts, width):
+        self.work, self.gathered, self.counts, self.width = work, gathered, counts, width
+
+    def result(self) -> torch.Tensor:
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        if self.width == 0:
+            return self.gathered
+        rows = self.gathered.view(len(self.counts), self.width)
+        return torch.cat([rows[r, :c] for r, c in enumerate(self.counts)]).to(torch.int64)
+
+
+def allgather_sizes_async(local_sizes: torch.Tensor, n_total: int, block: int, group=None) -> _Gather:
+    """Starts the path's one collective -- every rank's per-block payload sizes (4 bytes per block) -- and
+    returns at once; nothing on the data path waits for it (decoding a rank's own blocks needs only its own
+    index), so it overlaps the decode that follows."""
     world = dist.get_world_size(group)
     nb = container.nblocks_of(n_total, block)
     counts = [container.shard_range(nb, r, world)[1] - container.shard_range(nb, r, world)[0] for r in range(world)]
     width = max(counts) if counts else 0
     if width == 0:
-        return torch.zeros(0, dtype=torch.int64, device=local_sizes.device)
+        return _Gather(None, torch.zeros(0, dtype=torch.int64, device=local_sizes.device), counts, 0)
     mine = torch.zeros(width, dtype=torch.int32, device=local_sizes.device)
     mine[:local_sizes.numel()] = local_sizes.to(torch.int32)
     gathered = torch.empty(world * width, dtype=torch.int32, device=local_sizes.device)
-    dist.all_gather_into_tensor(gathered, mine, group=group)
-    rows = gathered.view(world, width)
-    return torch.cat([rows[r, :counts[r]] for r in range(world)]).to(torch.int64)
+    work = dist.all_gather_into_tensor(gathered, mine, group=group, async_op=True)
+    return _Gather(work, gathered, counts, width)
+
+
+def allgather_sizes(local_sizes: torch.Tensor, n_total: int, block: int, group=None) -> torch.Tensor:
+    """All ranks' per-block payload sizes, in block order (int64, length nblocks).
+
+    `local_sizes` holds this rank's blocks (int32, on the device NCCL runs on, or on CPU for gloo).
+    Shards differ by at most one block, so every rank pads to the same length before the collective."""
+    return allgather_sizes_async(local_sizes, n_total, block, group).result()
 
 
 def global_offsets(all_sizes: torch.Tensor) -> torch.Tensor:
@@ -64,7 +86,15 @@ class Shard:
     blk_hi: int
     container: torch.Tensor      # this rank's blocks as a B2RC container of their own (device), b2rc_encode_device's output
     used: int                    # its length
-    offsets: torch.Tensor        # int64, global index, replicated on every rank
+    gather: _Gather              # the all-gather of payload sizes, possibly still in flight
+    _offsets: torch.Tensor | None = None
+
+    @property
+    def offsets(self) -> torch.Tensor:
+        """int64, the global index, replicated on every rank (waits for the collective the first time)."""
+        if self._offsets is None:
+            self._offsets = global_offsets(self.gather.result())
+        return self._offsets
 
     @property
     def nblocks(self) -> int:
@@ -77,7 +107,7 @@ class Shard:
 
     @property
     def payload_bytes(self) -> int:
-        return int((self.offsets[self.blk_hi] - self.offsets[self.blk_lo]).item())
+        return int(self.local_offsets[-1].item())
 
     @property
     def payload(self) -> torch.Tensor:
@@ -102,8 +132,8 @@ def encode_shard(ctx, mode: int, src_shard: torch.Tensor, n_total: int, block: i
     enc, used = ctx.encode_device(mode, src_shard, dst, block)   # raises B2rcError on any device-side error bit
     local = enc[container.HEADER:container.HEADER + 8 * (nb + 1)].view(torch.int64)
     sizes = (local[1:] - local[:-1]).to(torch.int32)
-    all_sizes = allgather_sizes(sizes, n_total, block, group)  # the one collective
-    return Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, enc, used, global_offsets(all_sizes))
+    gather = allgather_sizes_async(sizes, n_total, block, group)  # the one collective; Shard.offsets waits for it
+    return Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, enc, used, gather)
 
 
 def decode_shard(ctx, shard: Shard, dst_shard: torch.Tensor) -> int:
