@@ -66,6 +66,9 @@ SIGNATURES = {
     "b2rc_blk_encode": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64)]),
     "b2rc_blk_decode": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64)]),
     "b2rc_blk_rounds": (C.c_int, [_P, _P, _U64, C.POINTER(_U64)]),
+    "b2rc_blkrc_bound": (_U64, [C.c_int, _U64, _U32]),
+    "b2rc_blkrc_encode_device": (C.c_int, [_P, C.c_int, _U32, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
+    "b2rc_blkrc_decode_device": (C.c_int, [_P, _P, _U64, _P, _U64, C.POINTER(_U64), _P]),
     "b2rc_build_arch": (C.c_char_p, []),
 }
 

@@ -234,6 +234,23 @@ class Context:
                                                     _stream()), "b2rc_blk_decode_device")
         return dst[:int(out_n.value)]
 
+    def blkrc_encode_device(self, mode: int, src: torch.Tensor, dst: torch.Tensor | None = None,
+                            block: int = DEFAULT_BLOCK) -> tuple[torch.Tensor, int]:
+        """Block sort, then the coder, one call on the device (the reference's run_zlib_blk shape, test/main.cpp:944-1002)."""
+        n = src.numel()
+        if dst is None:
+            dst = torch.empty(int(self.lib.b2rc_blkrc_bound(mode, n, block)), dtype=torch.uint8, device=src.device)
+        out_n = C.c_uint64(0)
+        self._check(self.lib.b2rc_blkrc_encode_device(self.h, mode, block, _ptr(src), n, _ptr(dst), dst.numel(), C.byref(out_n),
+                                                      _stream()), "b2rc_blkrc_encode_device")
+        return dst, int(out_n.value)
+
+    def blkrc_decode_device(self, src: torch.Tensor, n_src: int, dst: torch.Tensor) -> int:
+        out_n = C.c_uint64(0)
+        self._check(self.lib.b2rc_blkrc_decode_device(self.h, _ptr(src), n_src, _ptr(dst), dst.numel(), C.byref(out_n), _stream()),
+                    "b2rc_blkrc_decode_device")
+        return int(out_n.value)
+
     def _blk_host(self, fn, what: str, src, need: int, dst):
         src = np.ascontiguousarray(np.frombuffer(src, dtype=np.uint8) if isinstance(src, (bytes, bytearray)) else src,
                                    dtype=np.uint8)

@@ -88,6 +88,8 @@ struct b2rc_ctx {
     size_t blk_rounds_cap;
     u32* blk_tie_list;  // block sort: [0] how many blocks of the call have a period, [1 ..] which
     size_t blk_tie_cap;
+    u8* blk_tmp;        // block sort in front of a coder (b2rc_blkrc_*): the transformed stream between the two
+    size_t blk_tmp_cap;
     u8* blk_ties;     // block sort: scratch of the tie replay (block list, ranks, range queues)
     size_t blk_ties_cap;
     u64 blk_last_blocks;
@@ -577,6 +579,7 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx)
     cudaFree(ctx->d_err);
     cudaFree(ctx->blk_rounds);
     cudaFree(ctx->blk_tie_list);
+    cudaFree(ctx->blk_tmp);
     cudaFree(ctx->blk_ties);
     cudaFree(ctx->d_total);
     if(ctx->h_res) {
@@ -2134,6 +2137,98 @@ int b2rc_blk_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return map_kernel_err(ctx->h_res->err);
+}
+
+// ---- block sort, then a coder, one call (include/b2rc.h)
+uint64_t b2rc_blkrc_bound(int mode, uint64_t n, uint32_t block_size)
+{
+    const u64 inner = b2rc_bound(mode, b2rc_blk_encode_bound(n), block_size);
+    return inner ? 16u + inner : 0u;
+}
+
+int b2rc_blkrc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
+                             uint8_t* d_dst, uint64_t dst_cap, uint64_t* out_n, void* cuda_stream)
+{
+    if(!ctx || !d_dst || (n && !d_src) || !mode_ok(mode) || !block_ok(block_size) || !aligned16(d_src) || !aligned16(d_dst)) {
+        return B2RC_E_ARG;
+    }
+    if(out_n) {
+        *out_n = b2rc_blkrc_bound(mode, n, block_size);
+    }
+    if(dst_cap < 16u + index_bytes(0)) {
+        return B2RC_E_DST_SMALL;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const u64 nt = b2rc_blk_encode_bound(n);
+    int rc;
+    if((rc = grow(ctx, ctx->blk_tmp, ctx->blk_tmp_cap, (size_t)nt + 16)) != B2RC_OK) {
+        return rc;
+    }
+    u64 made = 0;
+    if((rc = b2rc_blk_encode_device(ctx, d_src, n, ctx->blk_tmp, nt, &made, st)) != B2RC_OK || made != nt) {
+        return rc != B2RC_OK ? rc : B2RC_E_INTERNAL;
+    }
+    u64 inner = 0;
+    rc = b2rc_encode_device(ctx, mode, block_size, ctx->blk_tmp, nt, d_dst + 16, dst_cap - 16, &inner, st);
+    if(out_n) {
+        *out_n = 16u + inner;
+    }
+    if(rc != B2RC_OK) {
+        return rc;
+    }
+    u32* h = reinterpret_cast<u32*>(ctx->h_res->header);  // pinned
+    h[0] = 0x53423242u;  // 'B','2','B','S'
+    h[1] = 0;
+    h[2] = (u32)n;
+    h[3] = (u32)(n >> 32);
+    CK(cudaMemcpyAsync(d_dst, h, 16, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return B2RC_OK;
+}
+
+int b2rc_blkrc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t dst_cap,
+                             uint64_t* out_n, void* cuda_stream)
+{
+    if(!ctx || !d_src || !aligned16(d_src) || !aligned16(d_dst)) {
+        return B2RC_E_ARG;
+    }
+    if(n < 16u + B2RC_HEADER_BYTES + 8) {
+        return B2RC_E_CORRUPT;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaMemcpyAsync(ctx->h_res->header, d_src, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    u32 h[4];
+    memcpy(h, ctx->h_res->header, 16);
+    const u64 orig = (u64)h[2] | ((u64)h[3] << 32);
+    if(h[0] != 0x53423242u || h[1] != 0u || orig > (1ull << 46)) {
+        return B2RC_E_CORRUPT;
+    }
+    if(out_n) {
+        *out_n = orig;
+    }
+    if(dst_cap < orig || (orig && !d_dst)) {
+        return B2RC_E_DST_SMALL;
+    }
+    const u64 nt = b2rc_blk_encode_bound(orig);
+    int rc;
+    if((rc = grow(ctx, ctx->blk_tmp, ctx->blk_tmp_cap, (size_t)nt + 16)) != B2RC_OK) {
+        return rc;
+    }
+    u64 got = 0;
+    if((rc = b2rc_decode_device(ctx, d_src + 16, n - 16, ctx->blk_tmp, nt, &got, st)) != B2RC_OK) {
+        return rc == B2RC_E_DST_SMALL ? B2RC_E_CORRUPT : rc;  // the container disagrees with the size in front of it
+    }
+    if(got != nt) {
+        return B2RC_E_CORRUPT;
+    }
+    u64 back = 0;
+    if((rc = b2rc_blk_decode_device(ctx, ctx->blk_tmp, nt, d_dst, dst_cap, &back, st)) != B2RC_OK) {
+        return rc;
+    }
+    return back == orig ? B2RC_OK : B2RC_E_CORRUPT;
 }
 
 // Host pointers: chunks of whole blocks, each on a stream of its own (copy in, kernel, copy out), so the

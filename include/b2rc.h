@@ -240,6 +240,17 @@ int b2rc_blk_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint
                            uint64_t* out_n, void* cuda_stream);
 int b2rc_blk_encode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n);
 int b2rc_blk_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* out_n);
+/* Block sort in front of a coder in ONE call, everything on the device -- the shape of the reference's
+ * run_zlib_blk / run_zstd_blk pipelines (test/main.cpp:944-1110: BlkSort::encode, then a compressor over its
+ * output) with this library's coders where zlib / zstd stand.  Output = 16 bytes {'B','2','B','S', u32 0,
+ * u64 original size} and behind them the B2RC container of BlkSort::encode's output (b2rc_encode_device, `mode`
+ * and `block_size` as there); b2rc_blkrc_decode_device undoes both.  d_src / d_dst 16-byte aligned; the calls
+ * return after the stream has drained. */
+uint64_t b2rc_blkrc_bound(int mode, uint64_t n, uint32_t block_size);
+int b2rc_blkrc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* d_src, uint64_t n,
+                             uint8_t* d_dst, uint64_t dst_cap, uint64_t* out_n, void* cuda_stream);
+int b2rc_blkrc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t dst_cap,
+                             uint64_t* out_n, void* cuda_stream);
 /* Doubling rounds the forward kernel took per block in the last b2rc_blk_encode_device call of
  * this context (bit 31: the block has a period; bit 30: one repeated byte; bits 8..15: how many of the rounds were short ones); copies min(cap, blocks) words to host memory.
  * Measurement / tests only. */

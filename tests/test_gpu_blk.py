@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from _cases import blk_cases, blk_fuzz_stream, blk_periodic_cases
-from _oracle import BLK_BLOCK, BLK_CODED, BlkSort, Oracle, blk_decoded_size, blk_encode_bound, fnv1a64
+from _oracle import BLK_BLOCK, BLK_CODED, BlkSort, Oracle, blk_decoded_size, blk_encode_bound, canterbury, fnv1a64
+from cpprcoder_b200 import synth
 
 pytestmark = pytest.mark.gpu
 GOLDEN = {c["label"]: c for c in json.loads((Path(__file__).resolve().parent / "golden" / "golden_blk.json").read_text())["cases"]}
@@ -135,3 +136,37 @@ def test_large_stream_by_properties(ctx, oracle):
         assert np.array_equal(host[b * BLK_CODED:(b + 1) * BLK_CODED], want), b
     cols = coded.view(-1, BLK_CODED)[:, :BLK_BLOCK]
     assert torch.equal(torch.sort(cols[:64], dim=1).values, torch.sort(src.view(-1, BLK_BLOCK)[:64], dim=1).values)
+
+
+def test_block_sort_then_coder_in_one_device_call(ctx):
+    """b2rc_blkrc_*: BlkSort::encode and a coder over its output in one C-ABI call, nothing visiting the host
+    in between (run_zlib_blk's shape, test/main.cpp:944-1002).  Equal to the two calls made one after the other,
+    and its payloads are what the reference's coder makes of the reference's block-sort output."""
+    import torch
+    from _oracle import ADAPTIVE, STATIC, BlkSort, Oracle
+    from cpprcoder_b200 import container
+    from cpprcoder_b200._lib import B2rcError, E_CORRUPT
+    o = Oracle.get()
+    data = np.concatenate([np.frombuffer(canterbury("lcet10.txt"), dtype=np.uint8), np.tile(np.arange(16, dtype=np.uint8), 4096),
+                           synth.mixed(5 * 32768 + 999)])
+    src = torch.from_numpy(data).cuda()
+    sorted_ref = BlkSort(o).encode(data, threads=4)
+    for mode in (STATIC, ADAPTIVE):
+        enc, used = ctx.blkrc_encode_device(mode, src)
+        host = enc[:used].cpu().numpy()
+        assert host[:4].tobytes() == b"B2BS" and int(np.frombuffer(host[8:16].tobytes(), dtype="<u8")[0]) == data.size
+        inner = host[16:]
+        two_calls, used2 = ctx.encode_device(mode, ctx.blk_encode_device(src))
+        assert two_calls[:used2].cpu().numpy().tobytes() == inner.tobytes()
+        info = container.parse(inner)
+        assert info.total == sorted_ref.size
+        want = o.encode_blocks(mode, sorted_ref, 65536, threads=4)
+        assert [bytes(info.payload(inner, b)) for b in range(info.nblocks)] == want
+        dst = torch.empty(data.size, dtype=torch.uint8, device="cuda")
+        assert ctx.blkrc_decode_device(enc, used, dst) == data.size
+        assert dst.cpu().numpy().tobytes() == data.tobytes()
+        bad = enc.clone()
+        bad[8] ^= 1  # the size in front no longer fits the container behind it
+        with pytest.raises(B2rcError) as e:
+            ctx.blkrc_decode_device(bad, used, dst)
+        assert e.value.code == E_CORRUPT
