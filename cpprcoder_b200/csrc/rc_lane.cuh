@@ -669,46 +669,44 @@ RC_HD void rc_static_find(const Tab& tab, const u32 (&k1)[8], u32 t, u32 low, u3
     freq = nxt - cum;
 }
 
-// 0xFFFFFFFF when k * t <= low, 0 when it is above: the high half of k * t + (2^64 - 1 - low), ONE
-// multiply-add on the multiplier pipe where rc_count_gt takes a multiply and two adds on the integer pipe.
-// `nlow64` = 0xFFFFFFFF : ~low.
-RC_HD u32 rc_not_above(u32 k, u32 t, u64 nlow64)
-{
-#if defined(__CUDA_ARCH__)
-    u64 p;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(k), "r"(t), "l"(nlow64));
-    return (u32)(p >> 32);
-#else
-    return (u32)(((u64)k * t + nlow64) >> 32);
-#endif
-}
-
-// The same search in four levels of four (4 x 4 x 4 x 4): 12 compares and three table round trips
-// instead of 17 and two.  For the segmented decoder, whose warps share schedulers and are bound by
-// the integer pipe (ALU 68 % busy, issue 70 %, profiles/r2_ncu_notes.md), not by the latency of one
-// chain: every compare is one wide multiply-add (rc_not_above), a level is three of them, one
-// three-input add and the address of the next level; the last level reads cum and the next cum of
-// the symbol it found instead of selecting them.  k0[j] = cum[64 j], j = 1..3.
+// The same search in four levels of four (4 x 4 x 4 x 4): 12 compares and three table round
+// trips instead of 17 and two.  Fewer instructions, a longer chain: for the segmented decoder,
+// whose warps share schedulers and are bound by issue slots, not by the latency of one chain.
+// k0[j] = cum[64 j], j = 1..3.
+// (Round 2 tried the compares as wide multiply-adds -- the high half of k * t + (2^64 - 1 - low) is
+// all ones exactly when k * t <= low: one instruction on the multiplier pipe instead of a multiply
+// and two adds on the integer pipe, which ncu shows 68 % busy in k_dec_static_seg.  95 -> 80
+// instructions per symbol and 3.97 -> 4.9 ms: IMAD.WIDE with a 64-bit addend is far slower than
+// its count suggests.  profiles/r2_ncu_notes.md.)
 template <class Tab>
 RC_HD void rc_static_find4(const Tab& tab, const u32 (&k0)[4], u32 t, u32 low, u32& sym, u32& cum, u32& freq)
 {
     constexpr u32 U = Tab::UNIT;
-    const u64 nlow64 = 0xFFFFFFFF00000000ull | (u32)~low;
-    // every term is 0 or -1: minus their sum is the number of boundaries at or below low
-    u32 n = 0u - (rc_not_above(k0[1], t, nlow64) + rc_not_above(k0[2], t, nlow64) + rc_not_above(k0[3], t, nlow64));
-    const u32 p1 = n * (64u * U);
+    const u32 nlow = ~low;
+    u32 a = 0;  // boundaries ABOVE low
+    rc_count_gt(a, k0[1] * t, nlow);
+    rc_count_gt(a, k0[2] * t, nlow);
+    rc_count_gt(a, k0[3] * t, nlow);
+    const u32 p1 = (3u - a) * (64u * U);
     const u32 e1 = tab.at(p1 + 16u * U), e2 = tab.at(p1 + 32u * U), e3 = tab.at(p1 + 48u * U);
-    n = 0u - (rc_not_above(e1, t, nlow64) + rc_not_above(e2, t, nlow64) + rc_not_above(e3, t, nlow64));
-    const u32 p2 = p1 + n * (16u * U);
+    a = 0;
+    rc_count_gt(a, e1 * t, nlow);
+    rc_count_gt(a, e2 * t, nlow);
+    rc_count_gt(a, e3 * t, nlow);
+    const u32 p2 = p1 + (3u - a) * (16u * U);
     const u32 g1 = tab.at(p2 + 4u * U), g2 = tab.at(p2 + 8u * U), g3 = tab.at(p2 + 12u * U);
-    n = 0u - (rc_not_above(g1, t, nlow64) + rc_not_above(g2, t, nlow64) + rc_not_above(g3, t, nlow64));
-    const u32 p3 = p2 + n * (4u * U);
-    const u32 f1 = tab.at(p3 + U), f2 = tab.at(p3 + 2 * U), f3 = tab.at(p3 + 3 * U);
-    n = 0u - (rc_not_above(f1, t, nlow64) + rc_not_above(f2, t, nlow64) + rc_not_above(f3, t, nlow64));
-    const u32 p4 = p3 + n * U;  // the symbol's own entry
-    sym = p4 / U;
-    cum = tab.at(p4);
-    freq = tab.at(p4 + U) - cum;
+    a = 0;
+    rc_count_gt(a, g1 * t, nlow);
+    rc_count_gt(a, g2 * t, nlow);
+    rc_count_gt(a, g3 * t, nlow);
+    const u32 p3 = p2 + (3u - a) * (4u * U);
+    const u32 f0 = tab.at(p3), f1 = tab.at(p3 + U), f2 = tab.at(p3 + 2 * U), f3 = tab.at(p3 + 3 * U),
+              f4 = tab.at(p3 + 4 * U);
+    const bool q1 = f1 * t <= low, q2 = f2 * t <= low, q3 = f3 * t <= low;  // monotone: q1 >= q2 >= q3
+    sym = p3 / U + (q1 ? 1u : 0u) + (q2 ? 1u : 0u) + (q3 ? 1u : 0u);
+    cum = q3 ? f3 : (q2 ? f2 : (q1 ? f1 : f0));
+    const u32 nxt = q3 ? f4 : (q2 ? f3 : (q1 ? f2 : f1));
+    freq = nxt - cum;
 }
 
 // -------------------------------------------------------------------- decoder --
