@@ -289,8 +289,25 @@ constexpr u32 enc_seg_smem(bool wide, u32 warps)
     return (wide ? ENC_STATIC_TAB_WIDE : ENC_STATIC_TAB_NARROW) + 128u + warps * 2u * TILE_BYTES;  // tables, totals, tiles
 }
 
+// Which form of the encoder step the segment kernel runs (rc_lane.cuh).  Measured on 1 GiB zipf, P = 2048:
+// funnel-shift form as k_enc_static has it 2.07 ms (integer pipe 84 % busy); multiplier form (RcEnc2) 2.03 ms
+// (integer pipe 45 %, but IMAD.WIDE is dear); funnel-shift form with the byte loads, the one-compare test for
+// all-ones words and the edge path that the multiplier version brought 1.88 ms: the default.
+#if defined(B2RC_SEG_MULTIPLIER)
+typedef RcEnc2 SegEnc;
+#else
+typedef RcEnc SegEnc;
+#endif
+#if defined(B2RC_SEG_NO_FLO)
+constexpr bool SEG_FLO = false;
+#else
+constexpr bool SEG_FLO = true;  // the renormalisation shift from the highest set bit (rc_norm_shift_flo)
+#endif
+__device__ __forceinline__ u32 seg_low(const RcEnc& e) { return e.low; }
+__device__ __forceinline__ u32 seg_low(const RcEnc2& e) { return (u32)e.x; }
+
 template <bool WIDE, bool POW2, bool RAGGED>
-__device__ __forceinline__ void enc_seg_tiles(const SegArgs& a, u32 tiles, const StaticTab<WIDE>& tab, RcEnc2& st,
+__device__ __forceinline__ void enc_seg_tiles(const SegArgs& a, u32 tiles, const StaticTab<WIDE>& tab, SegEnc& st,
                                               RcSegSink& sink, u64 b0, u32 n_eff, u32 tix0, u32 tix1, u32 total,
                                               u32 magic, u32 shift, u32 lane)
 {
@@ -325,6 +342,16 @@ __device__ __forceinline__ void enc_seg_tiles(const SegArgs& a, u32 tiles, const
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
                 const bool active = !RAGGED || tix * TILE + at + k < n_eff;
+#if !defined(B2RC_SEG_MULTIPLIER)
+                if(POW2) {
+                    rc_enc_step_pow2<WIDE ? 3 : 2, SEG_FLO>(st, tcur, shift, cum[k], freq[k], cuts[k], active);
+                } else {
+                    const u32 t = rc_div(st.range, total, magic);
+                    rc_enc_step<WIDE ? 3 : 2, SEG_FLO>(st, cum[k], freq[k], t, cuts[k], active);
+                }
+            }
+            rc_enc_commit_edge(st, cuts, sink);
+#else
                 if(POW2) {
                     rc_enc2_step_pow2<WIDE ? 3 : 2>(st, tcur, shift, cum[k], freq[k], cuts[k], active);
                 } else {
@@ -333,6 +360,7 @@ __device__ __forceinline__ void enc_seg_tiles(const SegArgs& a, u32 tiles, const
                 }
             }
             rc_enc2_commit(st, cuts, sink);
+#endif
 #pragma unroll
             for(int k = 0; k < 4; ++k) {
                 cum[k] = ncum[k];
@@ -472,7 +500,7 @@ __global__ void __launch_bounds__(32 * ENC_SEG_WARPS) k_enc_seg(SegArgs a)
     }
     const bool last = seg + 1u == nseg_b;
     const u32 own = (last ? S1 + 5u : S1 + 1u) - (S0 + 1u);
-    RcEnc2 st;  // the multiplier form of the step: this kernel is bound by the integer pipe (rc_lane.cuh)
+    SegEnc st;
     RcSegSink sink;
     rc_seg_begin(st, sink, a.payload + off + RC_STATIC_HDR + S0 + 1u, mine ? own : 0u, range0);
     const u32 total = has ? tots[lane] : 0u;
@@ -502,7 +530,7 @@ __global__ void __launch_bounds__(32 * ENC_SEG_WARPS) k_enc_seg(SegArgs a)
         if(!rc_seg_end(st, sink, last)) {
             atomicOr(a.err, ERR_INTERNAL);
         }
-        a.lows[b * (u64)a.nseg + seg] = (u32)st.x;
+        a.lows[b * (u64)a.nseg + seg] = seg_low(st);
     }
 }
 

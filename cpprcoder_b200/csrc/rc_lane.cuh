@@ -215,16 +215,32 @@ RC_HD u32 rc_norm_shift(u32 r)
     return sh;
 }
 
+// The same shift from the position of the highest set bit: one instruction on the conversion pipe and
+// one on the integer pipe instead of four (six) on the integer pipe, at a longer latency -- for kernels
+// that run many warps per scheduler and are bound by the integer pipe (k_enc_seg), not for the
+// one-warp-per-scheduler kernels, whose chain it would lengthen.  r >= 1.
+RC_HD u32 rc_norm_shift_flo(u32 r)
+{
+#if defined(__CUDA_ARCH__)
+    u32 top;
+    asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(r));
+    return ~top & 24u;
+#else
+    return rc_clz(r) & 24u;
+#endif
+}
+
 // One symbol, branch free: cum/freq from the model, t = range / total already divided.
 // Leaves at most one cut word in `c`; rc_enc_commit() takes care of it later, off the chain.
-template <int MAXSH>
+// FLO: the shift by rc_norm_shift_flo.
+template <int MAXSH, bool FLO = false>
 RC_HD void rc_enc_step(RcEnc& e, u32 cum, u32 freq, u32 t, RcCut& c, bool active = true)
 {
     u32 sh = 0;
     if(active) {
         rc_add96(e.low, e.o_lo, e.o_hi, cum * t);
         e.range = freq * t;
-        sh = rc_norm_shift<MAXSH>(e.range);
+        sh = FLO ? rc_norm_shift_flo(e.range) : rc_norm_shift<MAXSH>(e.range);
         e.range <<= sh;
     }
     e.o_hi = rc_funnel_l(e.o_lo, e.o_hi, sh);
@@ -246,14 +262,14 @@ RC_HD void rc_enc_step(RcEnc& e, u32 cum, u32 freq, u32 t, RcCut& c, bool active
 // the chain is IMAD -> compare -> select -> shift -> shift; a lone warp issues roughly one
 // instruction every two cycles, so the instruction count, not the last few cycles of chain,
 // decides (profiles/r1_ncu_notes.md).  `e.range` is not maintained on this path.
-template <int MAXSH>
+template <int MAXSH, bool FLO = false>
 RC_HD void rc_enc_step_pow2(RcEnc& e, u32& t, u32 shift, u32 cum, u32 freq, RcCut& c, bool active = true)
 {
     u32 sh = 0;
     if(active) {
         rc_add96(e.low, e.o_lo, e.o_hi, cum * t);
         const u32 r = freq * t;
-        sh = rc_norm_shift<MAXSH>(r);
+        sh = FLO ? rc_norm_shift_flo(r) : rc_norm_shift<MAXSH>(r);
         t = (r << sh) >> shift;  // two shifts on the chain instead of three candidates and two selects: fewer instructions
     }
     e.o_hi = rc_funnel_l(e.o_lo, e.o_hi, sh);
@@ -481,6 +497,58 @@ RC_HD void rc_enc2_commit(RcEnc2& e, const RcCut (&c)[4], Sink& s)
             }
         }
         // no all-ones word anywhere near: the straight-line commit through the checked sink
+        typename Sink::Checked ts(s);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int k = 0; k < 4; ++k) {
+            if(c[k].on) {
+                ts.push(e.pend + c[k].ovf);
+                e.pend = c[k].word;
+            }
+        }
+        ts.settle(s);
+        return;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int k = 0; k < 4; ++k) {
+        if(c[k].on) {
+            s.push(e.pend + c[k].ovf);
+            e.pend = c[k].word;
+        }
+    }
+}
+
+// The same commit for cuts made by rc_enc_step / rc_enc_step_pow2 (the funnel-shift form), whose
+// c.word is arbitrary when nothing was cut: masked first.
+template <class Enc, class Sink>
+RC_HD void rc_enc_commit_edge(Enc& e, const RcCut (&c)[4], Sink& s)
+{
+    const u32 w0 = c[0].on ? c[0].word : 0u, w1 = c[1].on ? c[1].word : 0u, w2 = c[2].on ? c[2].word : 0u,
+              w3 = c[3].on ? c[3].word : 0u;
+    u32 top = w0 > w1 ? w0 : w1;
+    top = top > w2 ? top : w2;
+    top = top > w3 ? top : w3;
+    const bool rare = e.nff != 0u || top == 0xFFFFFFFFu;
+    const bool edge = s.tight(4);
+    if(RC_WARP_ANY(rare || edge)) {
+        if(RC_WARP_ANY(rare)) {
+            if(rare) {
+                Enc te = e;
+                typename Sink::Checked ts(s);
+                for(int k = 0; k < 4; ++k) {
+                    if(c[k].on) {
+                        rc_enc_word_slow(te, c[k].word, c[k].ovf, ts);
+                    }
+                }
+                e.pend = te.pend;
+                e.nff = te.nff;
+                ts.settle(s);
+                return;
+            }
+        }
         typename Sink::Checked ts(s);
 #if defined(__CUDA_ARCH__)
 #pragma unroll

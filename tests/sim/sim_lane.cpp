@@ -307,7 +307,7 @@ long sim_encode_segmented(const u8* src, u32 n, u8* dst, size_t cap, u32 lead, u
     for(u32 j = nseg; j-- > 0;) {
         const bool last = j + 1 == nseg;
         const u32 own = (last ? S[nseg] + 5u : S[j + 1] + 1u) - (S[j] + 1u);
-        RcEnc2 e;  // the multiplier form of the step, as k_enc_seg runs it
+        RcEnc2 e;  // the multiplier form of the step (k_enc_seg with B2RC_SEG_MULTIPLIER; the default funnel form is sim_encode's)
         RcSegSink sink;
         rc_seg_begin(e, sink, coded + S[j] + 1u, own, R[j]);
         u32 t = pow2 ? (e.range >> shT) : 0;
