@@ -78,6 +78,7 @@ struct b2rc_ctx {
     size_t seg_lows_cap;
     u32 enc_seg_syms;  // symbols per segment of the static encoder; env B2RC_ENC_SEG_SYMS (0: one chain per block, k_enc_static)
     u32 force_exact;   // env B2RC_FORCE_EXACT=1 (tests): every static block takes the reference-shaped path
+    u32 adaptive_two_warps;  // env B2RC_ADAPTIVE_TWO_WARPS=1: k_enc_adaptive2 (model and coder on a warp each; slower, b2rc_adaptseg.cuh)
     struct Result {
         int err;
         int pad;
@@ -237,6 +238,7 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
     CK(cudaFuncSetAttribute(k_dec_adaptive_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_ADAPT_SEG_SMEM));
+    CK(cudaFuncSetAttribute(k_enc_adaptive2, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_AD2_SMEM));
     CK(cudaFuncSetAttribute(k_dec_static_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(true)));
     CK(cudaFuncSetAttribute(k_dec_static_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(false)));
     CK(cudaFuncSetAttribute(k_enc_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(false, ENC_SEG_WARPS)));
@@ -451,6 +453,9 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
     }
     if(const char* e = getenv("B2RC_FORCE_EXACT")) {
         ctx->force_exact = atol(e) ? 1u : 0u;
+    }
+    if(const char* e = getenv("B2RC_ADAPTIVE_TWO_WARPS")) {
+        ctx->adaptive_two_warps = atol(e) ? 1u : 0u;
     }
     ctx->seg_syms_adaptive = B2RC_DEFAULT_ADAPTIVE_RESTART_SYMS;
     if(const char* e = getenv("B2RC_ADAPTIVE_RESTART_SYMS")) {
@@ -875,6 +880,8 @@ int b2rc_k_encode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
     } else {
         if(wide) {
             k_enc_adaptive<u32><<<grid, 32, smem_enc_adaptive(true), st>>>(a);
+        } else if(ctx->adaptive_two_warps) {
+            k_enc_adaptive2<<<grid, 64, ENC_AD2_SMEM, st>>>(a);  // model and coder on a warp each: measured slower, kept for the record
         } else {
             k_enc_adaptive<u16><<<grid, 32, smem_enc_adaptive(false), st>>>(a);
         }

@@ -22,6 +22,166 @@
 
 namespace b2rc
 {
+// =================================================== K2a, two warps per 32 blocks ==
+// k_enc_adaptive runs one warp per scheduler and is bound by the length of what that warp does per
+// symbol: 115 instructions at 2.2 cycles each, of which 65 are the model (nine table reads, nine
+// writes, the bookkeeping of eight tree levels) and 50 the coder (the exact division by 256 + i, the
+// step, the commit).  The model does not depend on the coder at all, so the two halves go to two
+// warps of one CTA: warp 0 walks the tree for tile k + 1 and leaves (cum - symbol, freq - 1), 16 bits
+// each, in shared memory while warp 1 codes tile k from what warp 0 left a barrier ago.  Same tables,
+// same arithmetic, same bytes; the time per symbol is the longer half instead of the sum.
+// Blocks of at most 65536 bytes (the pairs are 16 + 16 bits); longer blocks keep k_enc_adaptive<u32>.
+// MEASURED (1 GiB mixed stream): 9.2 ms against 7.9 ms for k_enc_adaptive -- SLOWER.  The model half is
+// not 65 instructions' worth of time but a read-modify-write chain through shared memory (every symbol
+// reads the nodes the previous symbol wrote, the root always): about 250 cycles per symbol on its own,
+// as long as the whole one-warp loop, plus a barrier per tile.  Kept behind B2RC_ADAPTIVE_TWO_WARPS=1
+// (same bytes, tests/test_gpu_adaptseg.py::test_two_warp_encoder_writes_the_same_container).
+constexpr u32 ENC_AD2_TAB = 512u * 32u * 2u;
+constexpr u32 ENC_AD2_SRC = 3u * TILE_BYTES;        // three input tiles: being staged / modelled / coded
+constexpr u32 ENC_AD2_PAIRS = 2u * TILE * 128u;     // two tiles of [symbol][lane] u32
+constexpr u32 ENC_AD2_SMEM = ENC_AD2_TAB + ENC_AD2_SRC + ENC_AD2_PAIRS;
+
+__global__ void __launch_bounds__(64) k_enc_adaptive2(EncArgs a)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    const u32 sbase = smem_addr(smem);
+    const u32 src_a = sbase + ENC_AD2_TAB;
+    const u32 pairs_a = src_a + ENC_AD2_SRC;
+    const u32 warp = threadIdx.x >> 5, lane = lane_id();
+    const u64 b0 = (u64)blockIdx.x * 32u;
+    const u64 b = b0 + lane;
+    const bool has = b < a.nblocks;
+    u32 n_b = 0;
+    if(has) {
+        const u64 lo = b * (u64)a.block;
+        n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
+    }
+    u8* slot = a.slots + b * a.slot_stride;
+    const u32 n_max = __reduce_max_sync(FULL, n_b);
+    const u32 ntiles = (n_max + TILE - 1) / TILE;
+    const u32 nrec = a.restart ? (a.block + a.seg_syms - 1u) / a.seg_syms - 1u : 0u;
+    const u32 seg_tiles = a.restart ? a.seg_syms / TILE : 0xFFFFFFFFu;
+
+    {  // initialize(): all counts zero (the ones are implicit), cpprcoder.h:1094-1132
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for(u32 i = threadIdx.x; i < ENC_AD2_TAB / 16u; i += 64u) {
+            z[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    LaneTab<u16> tab{sbase + lane * 2u};
+    if(warp == 0) {
+        stage_tile(src_a, a.src, a.n, b0, a.block, 0, lane);
+        cp_async_commit();
+        if(ntiles > 1) {
+            stage_tile(src_a + TILE_BYTES, a.src, a.n, b0, a.block, TILE, lane);
+        }
+        cp_async_commit();
+    } else if(has) {
+        *reinterpret_cast<u32*>(slot) = n_b;  // cpprcoder.h:689-694
+    }
+    __syncthreads();
+
+    // ---- warp 0: the model of one tile -> pairs
+    auto model_tile = [&](u32 k) {
+        if(nrec && k != 0u && k % seg_tiles == 0u && k * TILE < n_b) {
+            // a segment starts with this tile: the model as it stands, for the restart point (the coder adds its three words)
+            u32* rec = a.restart + ((b0 + lane) * nrec + k / seg_tiles - 1u) * (u64)ADAPT_REC_WORDS;
+#pragma unroll 4
+            for(u32 s = 0; s < 256u; s += 2u) {
+                rec[3u + s / 2u] = tab.ld(256u + s) | (tab.ld(257u + s) << 16);
+            }
+        }
+        const u32 row = src_a + (k % 3u) * TILE_BYTES + lane * ROW;
+        const u32 out = pairs_a + (k & 1u) * (TILE * 128u) + lane * 4u;
+#pragma unroll 1
+        for(int wi = 0; wi < TILE / 4; ++wi) {
+            const u32 word = lds32(row + 4u * (u32)wi);
+#pragma unroll
+            for(int q = 0; q < 4; ++q) {
+                const u32 j = (u32)(wi * 4 + q);
+                if(k * TILE + j < n_b) {
+                    const u32 sym = (word >> (8 * q)) & 0xFFu;
+                    u32 cum, freq;
+                    TreeOps<u16>::encode(tab.base, sym, cum, freq);
+                    sts32v(out + j * 128u, (cum - sym) | ((freq - 1u) << 16));  // both fit 16 bits: at most 65535 symbols so far
+                }
+            }
+        }
+    };
+
+    RcEnc st;
+    rc_enc_init(st, RC_ADAPT_RANGE0);
+    SlotSink sink;
+    sink.out = reinterpret_cast<u32*>(slot + RC_ADAPT_HDR);
+    sink.wcount = -1;
+    sink.cap_words = has ? (u32)((a.slot_stride - RC_ADAPT_HDR) / 4u) : 0u;
+    sink.err = a.err;
+
+    // ---- warp 1: the coder of one tile <- pairs
+    auto code_tile = [&](u32 k) {
+        if(nrec && k != 0u && k % seg_tiles == 0u && k * TILE < n_b) {
+            u32* rec = a.restart + ((b0 + lane) * nrec + k / seg_tiles - 1u) * (u64)ADAPT_REC_WORDS;
+            const u32 words = (u32)(sink.wcount + 1) + st.nff;  // words cut off the shift register so far
+            rec[0] = 4u * words + (u32)st.ocnt / 8u - 1u;       // bytes shifted out of low, the dummy byte aside
+            rec[1] = st.low;
+            rec[2] = st.range;
+        }
+        const u32 d0 = 256u + k * TILE;
+        const u32 mg0 = rc_magic(d0 + lane);
+        const u32 mg1 = rc_magic(d0 + 32u + lane);
+        const u32 row = src_a + (k % 3u) * TILE_BYTES + lane * ROW;
+        const u32 in = pairs_a + (k & 1u) * (TILE * 128u) + lane * 4u;
+#pragma unroll 1
+        for(int wi = 0; wi < TILE / 4; ++wi) {
+            const u32 word = lds32(row + 4u * (u32)wi);
+            const u32 mg = wi < 8 ? mg0 : mg1;
+            RcCut cuts[4];
+#pragma unroll
+            for(int q = 0; q < 4; ++q) {
+                const int j = wi * 4 + q;
+                const u32 magic = __shfl_sync(FULL, mg, j & 31);
+                const bool active = k * TILE + (u32)j < n_b;
+                u32 cum = 0, freq = 1;
+                if(active) {
+                    const u32 p = lds32v(in + (u32)j * 128u);
+                    cum = (p & 0xFFFFu) + ((word >> (8 * q)) & 0xFFu);
+                    freq = (p >> 16) + 1u;
+                }
+                const u32 t = rc_div(st.range, d0 + (u32)j, magic);
+                rc_enc_step<3>(st, cum, freq, t, cuts[q], active);
+            }
+            rc_enc_commit(st, cuts, sink);
+        }
+    };
+
+    if(warp == 0) {
+        cp_async_wait<1>();  // tile 0 has arrived
+        __syncwarp();
+        model_tile(0);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for(u32 k = 0; k < ntiles; ++k) {
+        if(warp == 0) {
+            if(k + 2 < ntiles) {
+                stage_tile(src_a + ((k + 2) % 3u) * TILE_BYTES, a.src, a.n, b0, a.block, (k + 2) * TILE, lane);
+            }
+            cp_async_commit();
+            if(k + 1 < ntiles) {
+                cp_async_wait<1>();  // everything but the newest group: tile k + 1 is there
+                __syncwarp();
+                model_tile(k + 1);
+            }
+        } else {
+            code_tile(k);
+        }
+        __syncthreads();
+    }
+    if(warp == 1) {
+        finish_block(st, sink, has, RC_ADAPT_HDR, n_b, slot, a.sizes + b);
+    }
+}
+
 // ------------------------------------------------------------------ leafless tree --
 // Layout: the two CHILDREN of node j share one 32-bit word, [j][lane] (bank == lane: no conflicts, the
 // u16 [node][lane] layout of the full tree has two lanes per bank word); node 2j in the low half, 2j+1

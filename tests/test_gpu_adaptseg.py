@@ -116,3 +116,18 @@ def test_damaged_points_are_detected(oracle):
         assert ctx.decode(enc).tobytes() == data.tobytes()
     finally:
         ctx.close()
+
+
+def test_two_warp_encoder_writes_the_same_container(oracle):
+    """k_enc_adaptive2 (model and coder on a warp each, B2RC_ADAPTIVE_TWO_WARPS=1): measured slower than the
+    one-warp kernel and not the default, but it must write the same bytes, restart points included."""
+    data = np.concatenate([crafted_stream(37, 65536, seed=13, ragged=4321), synth.mixed(9 * 65536 + 5)])
+    a, b = make_ctx(), make_ctx(B2RC_ADAPTIVE_TWO_WARPS=1)
+    try:
+        one, two = a.encode(ADAPTIVE, data, 65536), b.encode(ADAPTIVE, data, 65536)
+        assert one.tobytes() == two.tobytes()
+        assert payloads(two) == oracle.encode_blocks(ADAPTIVE, data, 65536, threads=4)
+        assert b.decode(two).tobytes() == data.tobytes()
+    finally:
+        a.close()
+        b.close()
