@@ -64,9 +64,13 @@ __device__ __forceinline__ void enc_range_tiles(const SegArgs& a, u32 tiles, u32
     u32 range = RC_STATIC_RANGE0;
     u32 t = POW2 ? (range >> shift) : 0u;
     u32 bits = 0;
+    u32 ntotal = 0u - total;
+    asm volatile("" : "+r"(ntotal));  // opaque: see rc_range_step_div
     const u32 ntiles = (n_max + TILE - 1) / TILE;
     const u32 seg_tiles = a.P / TILE;
     u32 next_mark = 0;
+    // (a deeper ring of input tiles was tried for 1 MiB blocks, whose rows lie 1 MiB apart: no change -- the
+    // chain, not the staging, is what the lone warp waits for)
 #pragma unroll 1
     for(u32 tix = 0; tix < ntiles; ++tix) {
         if(tix + 1 < ntiles) {
@@ -79,11 +83,13 @@ __device__ __forceinline__ void enc_range_tiles(const SegArgs& a, u32 tiles, u32
             next_mark += seg_tiles;
             if(tix * TILE < n_b) {
                 const u32 j = tix / seg_tiles;
-                rec[2u * j] = bits >> 3;
+                // the general chain carries the range before its renormalisation (rc_range_step_div)
+                const u32 shn = POW2 ? 0u : rc_norm_shift_flo(range);
+                rec[2u * j] = (bits + shn) >> 3;
                 // any range with the same range / total serves a decoder; ONE form is written whatever path the
                 // warp took (the path depends on which blocks share a warp, which a multi-device split changes):
                 // power-of-two total (shift != 0, or total 1): the quotient shifted back; else the range itself
-                rec[2u * j + 1u] = POW2 ? (t << shift) : ((range >> shift) << shift);
+                rec[2u * j + 1u] = POW2 ? (t << shift) : (((range << shn) >> shift) << shift);
             }
         }
         const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;
@@ -108,7 +114,7 @@ __device__ __forceinline__ void enc_range_tiles(const SegArgs& a, u32 tiles, u32
                     if(POW2) {
                         bits += rc_range_step_pow2<MAXSH>(t, shift, f[k]);
                     } else {
-                        bits += rc_range_step<MAXSH>(range, f[k], rc_div(range, total, magic));
+                        rc_range_step_div(range, bits, f[k], total, ntotal, magic);
                     }
                 }
             }
@@ -121,7 +127,7 @@ __device__ __forceinline__ void enc_range_tiles(const SegArgs& a, u32 tiles, u32
     }
     if(n_b) {
         const u32 nseg_b = (n_b + a.P - 1u) / a.P;
-        rec[2u * nseg_b] = bits >> 3;
+        rec[2u * nseg_b] = (bits + (POW2 ? 0u : rc_norm_shift_flo(range))) >> 3;
         rec[2u * nseg_b + 1u] = 0u;
     }
 }

@@ -230,6 +230,23 @@ RC_HD u32 rc_norm_shift_flo(u32 r)
 #endif
 }
 
+// And as three compares in parallel and a TREE of selects, two deep (the plain form above compiles to a
+// chain of three): the shortest way from r to its shift, for a lone warp whose chain runs through it.
+RC_HD u32 rc_norm_shift_tree(u32 r)
+{
+#if defined(__CUDA_ARCH__)
+    u32 sh;
+    asm("{ .reg .pred p8, p16, p24;\n\t.reg .u32 a, b;\n\t"
+        "setp.lt.u32 p24, %1, 0x1000000;\n\tsetp.lt.u32 p16, %1, 0x10000;\n\tsetp.lt.u32 p8, %1, 0x100;\n\t"
+        "selp.u32 a, 8, 0, p24;\n\tselp.u32 b, 24, 16, p8;\n\tselp.u32 %0, b, a, p16; }"
+        : "=r"(sh)
+        : "r"(r));
+    return sh;
+#else
+    return rc_clz(r) & 24u;
+#endif
+}
+
 // One symbol, branch free: cum/freq from the model, t = range / total already divided.
 // Leaves at most one cut word in `c`; rc_enc_commit() takes care of it later, off the chain.
 // FLO: the shift by rc_norm_shift_flo.
@@ -1028,6 +1045,29 @@ RC_HD u32 rc_range_step_pow2(u32& t, u32 shift, u32 freq)
     const u32 sh = rc_norm_shift<MAXSH>(r);
     t = (r << sh) >> shift;
     return sh;
+}
+
+// The same chain for a total that is not a power of two, with the renormalisation taken OFF the
+// dependent chain.  The link is  range' = freq * (range / total)  shifted left by whole bytes until it
+// is at least 2^24; done in that order it reads  multiply -> three compares -> three selects -> shift ->
+// multiply-high -> multiply -> compare -> select  (65 cycles per link for a lone warp).  Here the chain
+// carries x = freq * t BEFORE the shift: (x << sh) * magic = (x * magic) << sh as 64-bit integers
+// (x << sh < 2^32), so the estimate of the quotient is the high word of the wide product funnel-shifted
+// by sh, and sh (from the highest set bit of x) is worked out while the multiplier runs.  Same
+// arithmetic as rc_div, same results.  `bits` counts the shifts of the symbols BEFORE the newest one:
+// a reader of the chain's state adds rc_norm_shift_flo(x) and takes x << that as the range.
+// `ntotal` = 0 - total, handed in by the caller (as a value the compiler cannot see through, or it
+// negates the quotient on the chain instead).
+RC_HD void rc_range_step_div(u32& x, u32& bits, u32 freq, u32 total, u32 ntotal, u32 magic)
+{
+    const u32 sh = rc_norm_shift_tree(x);  // FLO here: 59 cycles per link instead of 65; it is a slow instruction
+    u32 p_lo, p_hi;
+    rc_mul_wide(x, magic, p_lo, p_hi);
+    const u32 q = rc_funnel_l(p_lo, p_hi, sh);  // = umulhi(x << sh, magic), at most one below the quotient
+    const u32 rem = (x << sh) + q * ntotal;
+    const u32 x0 = q * freq;
+    x = rem >= total ? x0 + freq : x0;
+    bits += sh;
 }
 
 // Sink of one segment: aligned 4-byte words of the destination, which the segment shares with its

@@ -270,22 +270,30 @@ long sim_encode_segmented(const u8* src, u32 n, u8* dst, size_t cap, u32 lead, u
     {
         u32 range = RC_STATIC_RANGE0, t = pow2 ? (range >> shT) : 0, bits = 0;
         for(u32 i = 0; i < n; ++i) {
+            // the general chain carries the range before its renormalisation (rc_range_step_div)
+            const u32 shn = pow2 ? 0u : rc_norm_shift_flo(range);
             if(i % P == 0) {
-                S[i / P] = bits / 8;
-                R[i / P] = pow2 ? (t << shT) : range;
+                S[i / P] = (bits + shn) / 8;
+                R[i / P] = pow2 ? (t << shT) : (range << shn);
             }
             const u32 f = cum[src[i] + 1] - cum[src[i]];
             if(pow2) {
                 bits += rc_range_step_pow2<2>(t, shT, f);
             } else {
-                bits += rc_range_step<3>(range, f, rc_div(range, total, magic));
+                // ... and must agree with the plain form of the link at every symbol
+                u32 plain = range << shn;
+                const u32 plain_sh = rc_range_step<3>(plain, f, rc_div(plain, total, magic));
+                rc_range_step_div(range, bits, f, total, 0u - total, magic);
+                if(range << rc_norm_shift_flo(range) != plain || rc_norm_shift_flo(range) != plain_sh) {
+                    return -2;
+                }
             }
         }
         if(n == 0) {
             S[0] = 0;
             R[0] = RC_STATIC_RANGE0;
         }
-        S[nseg] = bits / 8;
+        S[nseg] = (bits + ((pow2 || n == 0) ? 0u : rc_norm_shift_flo(range))) / 8;
     }
     const size_t size = RC_STATIC_HDR + 5u + S[nseg];
     if(lead + size > cap) {
