@@ -332,13 +332,18 @@ class Leg:
                 ev[1].record()
             (dec_ctx or ctx).decode_device(self.enc, self.used, self.dec)
         else:
-            # one b2rc_encode_device call per rank + the all-gather of payload sizes (NCCL)
-            self.shard = rcdist.encode_shard(ctx, mode, self.src, self.n_total, self.block, dst=self.enc)
+            # one b2rc_encode_device call per rank + the all-gather of payload sizes (NCCL).  A rank decodes its
+            # own blocks from its own index, so the decode is launched first and the collective behind it
+            # (B2RC_BENCH_GATHER=overlap: the collective first, running beside the decode -- measured slower:
+            # its kernel sits on SMs the decoder's single wave needs)
+            overlap = os.environ.get("B2RC_BENCH_GATHER", "after") == "overlap"
+            self.shard = rcdist.encode_shard(ctx, mode, self.src, self.n_total, self.block, dst=self.enc,
+                                             defer_gather=not overlap)
             self.used = self.shard.used
             if ev:
                 ev[1].record()
             rcdist.decode_shard(dec_ctx or ctx, self.shard, self.dec)
-            self.shard.offsets  # the collective was started before the decode; its result is part of the step
+            self.shard.offsets  # the global index is part of the step: the collective has to have finished
         if ev:
             ev[2].record()
 

@@ -1562,6 +1562,14 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_hist(const u8* src, u64 n, 
     }
 }
 
+// (Tried and taken out: LANE-private bins, u32 [bin][lane], 32 KiB per warp, seven warps per SM, the 32 partial
+// counts summed once per block -- no two lanes ever in one bank.  0.595 ms against 0.338 ms for 1 GiB.  The
+// shared-memory atomic here is ATOMS.POPC.INC: lanes with the SAME address are merged by the hardware and cost
+// nothing; what costs is the number of DISTINCT addresses per instruction, and private bins make that 32
+// every time.  With shared bins a zipf stream has ~20 distinct bytes per instruction, which fall into the 32
+// banks like balls into bins: 2.45 wavefronts per instruction, the shared-memory pipe 96 % busy -- that, not
+// HBM, is this kernel's roofline: 0.49 of the measured copy bandwidth.)
+
 // K1 for blocks above 65536 bytes, where RangeEncoder::count is order dependent: whenever the
 // symbol about to be counted already stands at 0xFFFF, EVERY non-zero count becomes
 // (x >> 1) | 1 first (cpprcoder.h:549-555).  One warp per block walks it in segments: the

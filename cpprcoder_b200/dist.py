@@ -36,10 +36,10 @@ class _Gather:
         if self.work is not None:
             self.work.wait()
             self.work = None
-        if self.width == 0:
-            return self.gathered
+        if self.width == 0 or all(c == self.width for c in self.counts):
+            return self.gathered  # equal shares: the rows are the block order already (no kernel launched here)
         rows = self.gathered.view(len(self.counts), self.width)
-        return torch.cat([rows[r, :c] for r, c in enumerate(self.counts)]).to(torch.int64)
+        return torch.cat([rows[r, :c] for r, c in enumerate(self.counts)])
 
 
 def allgather_sizes_async(local_sizes: torch.Tensor, n_total: int, block: int, group=None) -> _Gather:
@@ -52,15 +52,18 @@ def allgather_sizes_async(local_sizes: torch.Tensor, n_total: int, block: int, g
     width = max(counts) if counts else 0
     if width == 0:
         return _Gather(None, torch.zeros(0, dtype=torch.int64, device=local_sizes.device), counts, 0)
-    mine = torch.zeros(width, dtype=torch.int32, device=local_sizes.device)
-    mine[:local_sizes.numel()] = local_sizes.to(torch.int32)
+    if local_sizes.numel() == width:
+        mine = local_sizes.to(torch.int32).contiguous()
+    else:
+        mine = torch.zeros(width, dtype=torch.int32, device=local_sizes.device)
+        mine[:local_sizes.numel()] = local_sizes.to(torch.int32)
     gathered = torch.empty(world * width, dtype=torch.int32, device=local_sizes.device)
     work = dist.all_gather_into_tensor(gathered, mine, group=group, async_op=True)
     return _Gather(work, gathered, counts, width)
 
 
 def allgather_sizes(local_sizes: torch.Tensor, n_total: int, block: int, group=None) -> torch.Tensor:
-    """All ranks' per-block payload sizes, in block order (int64, length nblocks).
+    """All ranks' per-block payload sizes, in block order (int32, length nblocks).
 
     `local_sizes` holds this rank's blocks (int32, on the device NCCL runs on, or on CPU for gloo).
     Shards differ by at most one block, so every rank pads to the same length before the collective."""
@@ -71,7 +74,7 @@ def global_offsets(all_sizes: torch.Tensor) -> torch.Tensor:
     """offsets[nblocks+1] (int64) of the stitched container from the gathered sizes."""
     off = torch.zeros(all_sizes.numel() + 1, dtype=torch.int64, device=all_sizes.device)
     if all_sizes.numel():
-        off[1:] = torch.cumsum(all_sizes, 0)
+        torch.cumsum(all_sizes, 0, dtype=torch.int64, out=off[1:])
     return off
 
 
@@ -86,13 +89,24 @@ class Shard:
     blk_hi: int
     container: torch.Tensor      # this rank's blocks as a B2RC container of their own (device), b2rc_encode_device's output
     used: int                    # its length
-    gather: _Gather              # the all-gather of payload sizes, possibly still in flight
+    gather: _Gather | None       # the all-gather of payload sizes, possibly still in flight (None: not started yet)
+    group: object = None
     _offsets: torch.Tensor | None = None
+
+    def start_gather(self) -> None:
+        """Starts the collective if encode_shard was told to leave it (defer_gather): a caller that decodes its
+        own blocks right away launches the decode FIRST and the exchange behind it, so the collective's
+        kernel takes no SM away from the decoder (which fills the GPU in exactly one wave) and the host's
+        launch work hides behind the decode."""
+        if self.gather is None:
+            local = self.local_offsets
+            self.gather = allgather_sizes_async((local[1:] - local[:-1]).to(torch.int32), self.n_total, self.block, self.group)
 
     @property
     def offsets(self) -> torch.Tensor:
         """int64, the global index, replicated on every rank (waits for the collective the first time)."""
         if self._offsets is None:
+            self.start_gather()
             self._offsets = global_offsets(self.gather.result())
         return self._offsets
 
@@ -121,19 +135,20 @@ class Shard:
 
 
 def encode_shard(ctx, mode: int, src_shard: torch.Tensor, n_total: int, block: int, group=None,
-                 dst: torch.Tensor | None = None) -> Shard:
+                 dst: torch.Tensor | None = None, defer_gather: bool = False) -> Shard:
     """Code this rank's blocks on its GPU -- ONE b2rc_encode_device call, the same one a single GPU makes for
     a whole stream -- and all-gather the payload sizes (4 bytes per block), the path's only exchange.
-    A rank without blocks (world > nblocks) still enters the collective."""
+    A rank without blocks (world > nblocks) still enters the collective.  defer_gather: the collective starts
+    at Shard.start_gather() / the first use of Shard.offsets instead (EVERY rank must get there)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi, blk_lo, blk_hi = shard_of(n_total, block, rank, world)
     assert src_shard.numel() == hi - lo, "src_shard must hold exactly this rank's byte range"
     nb = blk_hi - blk_lo
     enc, used = ctx.encode_device(mode, src_shard, dst, block)   # raises B2rcError on any device-side error bit
-    local = enc[container.HEADER:container.HEADER + 8 * (nb + 1)].view(torch.int64)
-    sizes = (local[1:] - local[:-1]).to(torch.int32)
-    gather = allgather_sizes_async(sizes, n_total, block, group)  # the one collective; Shard.offsets waits for it
-    return Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, enc, used, gather)
+    shard = Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, enc, used, None, group)
+    if not defer_gather:
+        shard.start_gather()  # the one collective; Shard.offsets waits for it
+    return shard
 
 
 def decode_shard(ctx, shard: Shard, dst_shard: torch.Tensor) -> int:
