@@ -29,6 +29,8 @@ SIGNATURES = {
     "b2rc_ctx_destroy": (None, [_P]),
     "b2rc_ctx_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
     "b2rc_ctx_devices": (C.c_int, [_P]),
+    "b2rc_restart_for": (_U32, [_P, C.c_int, _U32, _U64]),
+    "b2rc_ctx_force_restart": (C.c_int, [_P, _U32]),
     "b2rc_strerror": (C.c_char_p, [C.c_int]),
     "b2rc_last_cuda_error": (C.c_char_p, [_P]),
     "b2rc_bound": (_U64, [C.c_int, _U64, _U32]),

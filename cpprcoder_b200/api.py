@@ -93,6 +93,14 @@ class Context:
         """Coders this build carries kernels for, in container mode numbers."""
         return (MODE_STATIC, MODE_ADAPTIVE, MODE_RANS_BYTE, MODE_RANS_WORD)
 
+    def restart_for(self, mode: int, block: int, nblocks: int) -> int:
+        """Spacing of the restart points this context writes a stream of `nblocks` blocks with (0: none)."""
+        return int(self.lib.b2rc_restart_for(self.h, mode, block, nblocks))
+
+    def force_restart(self, seg_syms: int):
+        """One spacing for every stream from now on (0: automatic again) -- for containers that get stitched."""
+        self._check(self.lib.b2rc_ctx_force_restart(self.h, seg_syms), "b2rc_ctx_force_restart")
+
     def profile(self, enable: bool = True):
         self._check(self.lib.b2rc_profile(self.h, 1 if enable else 0), "b2rc_profile")
 

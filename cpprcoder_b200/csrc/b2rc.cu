@@ -64,6 +64,8 @@ struct b2rc_ctx {
     u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
     u64 max_phases;  // <= B2RC_PHASES; env B2RC_PHASES overrides (1 switches the phased decode off)
     u32 seg_syms;    // restart points of the static coder every so many symbols; env B2RC_RESTART_SYMS (0: none)
+    u32 seg_auto;    // no env setting: streams of few blocks get more points per block (seg_for)
+    u32 seg_force;   // b2rc_ctx_force_restart: this spacing whatever the stream (0: not forced)
     u32 seg_syms_adaptive;  // the same for the adaptive coder (524 B per point); env B2RC_ADAPTIVE_RESTART_SYMS (0: none)
     u32* restart;    // device scratch: the table while a container is being written / read
     size_t restart_cap;
@@ -181,12 +183,34 @@ u32 rec_words(int mode)
 {
     return mode == B2RC_MODE_ADAPTIVE ? 3u + 128u : 3u;
 }
-u32 seg_for(const b2rc_ctx* ctx, int mode, u32 block_size)
+// The decoder runs one warp per 32 blocks and segment; it wants about as many warps as the 1 GiB / 64 KiB case
+// gives it at the default spacing (512 x 8, seven CTAs of four on every SM).  A stream with fewer blocks gets its
+// points closer together, down to B2RC_MIN_RESTART_SYMS: 128 MiB decode in 0.64 instead of 1.42 ms, 16 MiB in
+// 0.27 instead of 1.39 ms (tools/dec_perf.py) for at most +1.3 % size.  12 bytes per point.
+constexpr u64 SEG_AUTO_WARPS = 4096;
+u32 seg_for(const b2rc_ctx* ctx, int mode, u32 block_size, u64 nblocks)
 {
     if(mode == B2RC_MODE_ADAPTIVE) {  // the points hold u16 counts: blocks of at most 65536 bytes
         return (block_size <= 65536u && seg_ok(block_size, ctx->seg_syms_adaptive)) ? ctx->seg_syms_adaptive : 0u;
     }
-    return (has_restart(mode) && seg_ok(block_size, ctx->seg_syms)) ? ctx->seg_syms : 0u;
+    if(!has_restart(mode)) {
+        return 0u;
+    }
+    if(ctx->seg_force) {
+        return seg_ok(block_size, ctx->seg_force) ? ctx->seg_force : 0u;
+    }
+    if(!seg_ok(block_size, ctx->seg_syms)) {
+        return 0u;
+    }
+    u32 seg = ctx->seg_syms;
+    if(ctx->seg_auto) {
+        const u64 groups = (nblocks + 31u) / 32u;
+        while(seg / 2u >= B2RC_MIN_RESTART_SYMS && (seg / 2u) % 64u == 0u &&
+              groups * ((block_size + seg - 1u) / seg) < SEG_AUTO_WARPS) {
+            seg /= 2u;
+        }
+    }
+    return seg;
 }
 bool aligned16(const void* p)
 {
@@ -438,10 +462,12 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
     }
     ctx->max_phases = 4;  // measured on B200: 4 and 8 launches per chunk time the same
     ctx->seg_syms = B2RC_DEFAULT_RESTART_SYMS;
+    ctx->seg_auto = 1;
     if(const char* e = getenv("B2RC_RESTART_SYMS")) {
         const long v = atol(e);
         if(v == 0 || (v >= (long)B2RC_MIN_RESTART_SYMS && v <= (1 << 22) && v % 64 == 0)) {
             ctx->seg_syms = (u32)v;
+            ctx->seg_auto = 0;  // an explicit spacing is kept for every stream
         }
     }
     ctx->enc_seg_syms = 2048;
@@ -554,6 +580,25 @@ int b2rc_ctx_create_multi(const int* devices, int ndev, b2rc_ctx** out)
         head->ndev = d + 1;
     }
     *out = head;
+    return B2RC_OK;
+}
+
+uint32_t b2rc_restart_for(const b2rc_ctx* ctx, int mode, uint32_t block_size, uint64_t nblocks)
+{
+    return (ctx && mode_ok(mode) && block_ok(block_size)) ? seg_for(ctx, mode, block_size, nblocks) : 0u;
+}
+
+int b2rc_ctx_force_restart(b2rc_ctx* ctx, uint32_t seg_syms)
+{
+    if(!ctx || (seg_syms && (seg_syms < B2RC_MIN_RESTART_SYMS || seg_syms > (1u << 22) || seg_syms % 64u))) {
+        return B2RC_E_ARG;
+    }
+    ctx->seg_force = seg_syms;
+    for(int d = 0; d < ctx->ndev && ctx->ndev > 1; ++d) {
+        if(ctx->sub[d] && ctx->sub[d] != ctx) {
+            ctx->sub[d]->seg_force = seg_syms;
+        }
+    }
     return B2RC_OK;
 }
 
@@ -1185,7 +1230,7 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const u64 stride = b2rc_slot_bytes_for(mode, block_size);
-    const u32 seg = nb ? seg_for(ctx, mode, block_size) : 0u;
+    const u32 seg = nb ? seg_for(ctx, mode, block_size, nb) : 0u;
     // static coder: many chains per block, coded straight into the container (b2rc_encseg.cuh)
     const u32 P = (mode == B2RC_MODE_STATIC && nb) ? enc_seg_plan(ctx, block_size, seg) : 0u;
     int rc;
@@ -1376,7 +1421,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     }
     const u64 stride = b2rc_slot_bytes_for(mode, block_size);
     const bool need_hist = mode == B2RC_MODE_STATIC;
-    const u32 seg = nb ? seg_for(ctx, mode, block_size) : 0u;
+    const u32 seg = nb ? seg_for(ctx, mode, block_size, nb) : 0u;
     const u32 nrec = seg ? b2rc_restart_records(block_size, seg) : 0u;
     const u32 P = (mode == B2RC_MODE_STATIC && nb) ? enc_seg_plan(ctx, block_size, seg) : 0u;  // b2rc_encseg.cuh
     int rc;
@@ -1682,6 +1727,8 @@ static int multi_encode(b2rc_ctx* ctx, int mode, u32 block_size, const u8* src, 
     if(dst_cap < idx) {
         return B2RC_E_DST_SMALL;
     }
+    // the spacing of the restart points follows the share of ONE device (each decodes its share on its own)
+    const u32 seg_each = ctx->seg_force ? ctx->seg_force : seg_for(ctx, mode, block_size, (nb + (u64)N - 1) / (u64)N);
     std::vector<Piece> pc((size_t)N);
     std::vector<std::thread> pool;
     for(int d = 0; d < N; ++d) {
@@ -1690,7 +1737,10 @@ static int multi_encode(b2rc_ctx* ctx, int mode, u32 block_size, const u8* src, 
         pool.emplace_back([&, d] {
             const u64 lo = pc[d].blk_lo * block_size;
             const u64 hi = pc[d].blk_hi * (u64)block_size < n ? pc[d].blk_hi * (u64)block_size : n;
+            const u32 keep = ctx->sub[d]->seg_force;  // sub[0] is the head itself
+            ctx->sub[d]->seg_force = seg_each;        // every piece with the same spacing: the pieces are stitched
             pc[d].rc = b2rc_encode_staged(ctx->sub[d], mode, block_size, src + lo, hi - lo, &pc[d].out, &pc[d].made);
+            ctx->sub[d]->seg_force = keep;
         });
     }
     for(auto& th : pool) {

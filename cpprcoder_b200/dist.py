@@ -143,8 +143,17 @@ def encode_shard(ctx, mode: int, src_shard: torch.Tensor, n_total: int, block: i
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi, blk_lo, blk_hi = shard_of(n_total, block, rank, world)
     assert src_shard.numel() == hi - lo, "src_shard must hold exactly this rank's byte range"
-    nb = blk_hi - blk_lo
-    enc, used = ctx.encode_device(mode, src_shard, dst, block)   # raises B2rcError on any device-side error bit
+    # every rank writes its restart points at the spacing a share of ceil(nblocks / world) blocks gets: the shards
+    # may be stitched into one container (one spacing), and each is decoded by a GPU of its own
+    force = getattr(ctx, "force_restart", None)
+    if force is not None:
+        nb_all = container.nblocks_of(n_total, block)
+        force(ctx.restart_for(mode, block, -(-nb_all // world)))
+    try:
+        enc, used = ctx.encode_device(mode, src_shard, dst, block)   # raises B2rcError on any device-side error bit
+    finally:
+        if force is not None:
+            force(0)
     shard = Shard(rank, world, mode, block, n_total, blk_lo, blk_hi, enc, used, None, group)
     if not defer_gather:
         shard.start_gather()  # the one collective; Shard.offsets waits for it

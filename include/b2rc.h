@@ -90,6 +90,14 @@ void b2rc_ctx_destroy(b2rc_ctx* ctx);
  * tested on a one-GPU box).  1 <= ndev <= 16. */
 int b2rc_ctx_create_multi(const int* devices, int ndev, b2rc_ctx** out);
 int b2rc_ctx_devices(const b2rc_ctx* ctx);
+/* Restart points are written every B2RC_DEFAULT_RESTART_SYMS symbols for a stream that
+ * fills the GPU; a stream of fewer blocks gets them closer together (down to B2RC_MIN_RESTART_SYMS), so that its
+ * decoder still has a warp per scheduler slot.  b2rc_restart_for: the spacing this context would write a stream of
+ * `nblocks` blocks with (0: no restart table).  b2rc_ctx_force_restart: one spacing for every stream from now on
+ * (a multiple of 64, B2RC_MIN_RESTART_SYMS ..; 0 = automatic again) -- what a caller that stitches containers of
+ * several contexts sets (cpprcoder_b200/dist.py); env B2RC_RESTART_SYMS does the same at context creation. */
+uint32_t b2rc_restart_for(const b2rc_ctx* ctx, int mode, uint32_t block_size, uint64_t nblocks);
+int b2rc_ctx_force_restart(b2rc_ctx* ctx, uint32_t seg_syms);
 const char* b2rc_strerror(int code);
 /* Last CUDA error text seen by this context ("" if none). */
 const char* b2rc_last_cuda_error(const b2rc_ctx* ctx);

@@ -55,6 +55,11 @@ def test_segments_give_the_reference_payloads(oracle, one_chain, P, block, nbloc
     data = crafted_stream(nblocks, block, seed=7 * block + P, ragged=ragged)
     want = oracle.encode_blocks(STATIC, data, block, threads=4)
     ctx = make_ctx(B2RC_ENC_SEG_SYMS=P)
+    # the encoder's segments are never longer than the spacing of the restart points, which for these few blocks
+    # would be 1024 (b2rc_restart_for): the long segments are tested at the spacing a full GPU gets
+    spacing = 8192 if P >= 2048 else 0
+    ctx.force_restart(spacing)
+    one_chain.force_restart(spacing)
     try:
         host = ctx.encode(STATIC, data, block)                       # chunked host pipeline
         assert payloads(host) == want
@@ -65,6 +70,7 @@ def test_segments_give_the_reference_payloads(oracle, one_chain, P, block, nbloc
         assert one_chain.encode(STATIC, data, block).tobytes() == host.tobytes()
         assert ctx.decode(host).tobytes() == data.tobytes()
     finally:
+        one_chain.force_restart(0)
         ctx.close()
 
 
@@ -165,6 +171,7 @@ def test_damaged_restart_records_are_detected(oracle):
     data = np.concatenate([synth.zipf(20 * 65536), synth.mixed(12 * 65536 + 3000)])
     ctx = make_ctx()
     try:
+        ctx.force_restart(8192)  # seven records per block, as a stream that fills the GPU gets them
         enc = ctx.encode(STATIC, data, 65536)
         info = container.parse(enc)
         assert info.restart is not None and info.restart.shape[1] == 7

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from _cases import crafted, crafted_stream
-from _oracle import ADAPTIVE, CANTERBURY, STATIC, Oracle, canterbury, fnv1a64, offsets_of
+from _oracle import ADAPTIVE, CANTERBURY, RANS_BYTE, RANS_WORD, STATIC, Oracle, canterbury, fnv1a64, offsets_of
 from cpprcoder_b200 import container, synth
 
 pytestmark = pytest.mark.gpu
@@ -325,29 +325,41 @@ def _sim_lib(built):
     return lib
 
 
+@pytest.fixture
+def spacing(ctx, request):
+    """Restart points every `param` symbols (0: the context's own rule, which packs them closer for the few
+    blocks of a test stream: b2rc_restart_for)."""
+    ctx.force_restart(request.param)
+    yield request.param
+    ctx.force_restart(0)
+
+
+@pytest.mark.parametrize("spacing", [8192, 0], indirect=True)
 @pytest.mark.parametrize("gen,block,extra", [("zipf", 65536, 0), ("kennedy", 65536, 4097), ("mixed", 16384, 77),
                                              ("kennedy", 262144, 100000)])
-def test_static_container_carries_restart_points(ctx, oracle, built, gen, block, extra):
-    """The static coder's containers end in a table of restart points (one per 8192 symbols): the
-    payloads are still the reference's, the records are what the lane code computes on the CPU, and
-    the decoder -- which now runs a chain per segment -- gives the input back."""
+def test_static_container_carries_restart_points(ctx, oracle, built, gen, block, extra, spacing):
+    """The static coder's containers end in a table of restart points (one per 8192 symbols, closer together
+    for a stream of few blocks): the payloads are still the reference's, the records are what the lane code
+    computes on the CPU, and the decoder -- which now runs a chain per segment -- gives the input back."""
     n = 20 * block + extra
     data = synth.GENERATORS[gen](n)
     enc = ctx.encode(STATIC, data, block)
     info = container.parse(enc)
-    assert info.seg_syms == 8192 and info.restart.shape == (info.nblocks, block // 8192 - 1, 3)
+    seg = spacing or ctx.restart_for(STATIC, block, info.nblocks)
+    assert spacing or seg == 1024                       # 21 blocks are far from filling the GPU
+    assert info.seg_syms == seg and info.restart.shape == (info.nblocks, block // seg - 1, 3)
     want = oracle.encode_blocks(STATIC, data, block, threads=4)
     assert_blocks_equal([bytes(info.payload(enc, b)) for b in range(info.nblocks)], want, f"{gen}/{block}")
     assert ctx.decode(enc).tobytes() == data.tobytes()
     if block <= 65536:
         sim = _sim_lib(built)
-        nseg = block // 8192
+        nseg = block // seg
         for b in (0, info.nblocks // 2, info.nblocks - 1):
             blk = np.ascontiguousarray(data[b * block:(b + 1) * block])
             out = np.empty(2 * blk.size + 4096, np.uint8)
             rec = np.zeros(3 * (nseg - 1), np.uint32)
             r = sim.sim_encode_restart(blk.ctypes.data_as(C.c_void_p), blk.size, out.ctypes.data_as(C.c_void_p), out.size,
-                                       8192, nseg, rec.ctypes.data_as(C.c_void_p))
+                                       seg, nseg, rec.ctypes.data_as(C.c_void_p))
             assert r > 0
             got, ref = info.restart[b].reshape(-1, 3), rec.reshape(-1, 3)
             reached = ref[:, 0] != 0xFFFFFFFF
@@ -364,6 +376,31 @@ def test_static_container_carries_restart_points(ctx, oracle, built, gen, block,
     plain = container.build(STATIC, block, n, want)
     assert container.parse(plain).restart is None
     assert ctx.decode(plain).tobytes() == data.tobytes()
+
+
+def test_restart_spacing_follows_the_number_of_blocks(ctx):
+    """b2rc_restart_for: 8192 symbols for a stream that fills the GPU at that spacing (1 GiB of 64 KiB blocks),
+    halved until ceil(nblocks / 32) x segments reaches 4096 warps, not below 1024; a forced spacing wins."""
+    assert ctx.restart_for(STATIC, 65536, 16384) == 8192
+    assert ctx.restart_for(STATIC, 65536, 8192) == 4096
+    assert ctx.restart_for(STATIC, 65536, 4096) == 2048
+    assert ctx.restart_for(STATIC, 65536, 2048) == 1024
+    assert ctx.restart_for(STATIC, 65536, 1) == 1024
+    assert ctx.restart_for(STATIC, 1 << 20, 1024) == 8192       # 1 GiB of 1 MiB blocks: 32 x 128 warps
+    assert ctx.restart_for(STATIC, 1 << 20, 64) == 1024
+    assert ctx.restart_for(RANS_BYTE, 65536, 2048) == 1024
+    assert ctx.restart_for(STATIC, 4096, 1 << 18) == 0           # blocks no longer than the spacing: no table
+    assert ctx.restart_for(ADAPTIVE, 65536, 5) == 21888          # the adaptive coder's points carry the model: fixed
+    assert ctx.restart_for(RANS_WORD, 65536, 5) == 0
+    ctx.force_restart(4096)
+    try:
+        assert ctx.restart_for(STATIC, 65536, 5) == 4096 and ctx.restart_for(STATIC, 65536, 1 << 20) == 4096
+        assert ctx.restart_for(ADAPTIVE, 65536, 5) == 21888
+    finally:
+        ctx.force_restart(0)
+    from cpprcoder_b200._lib import B2rcError
+    with pytest.raises(B2rcError):
+        ctx.force_restart(100)
 
 
 def test_restart_points_can_be_switched_off(built, oracle, monkeypatch):

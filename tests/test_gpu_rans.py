@@ -282,7 +282,11 @@ def test_byte_rans_container_carries_restart_points(ctx, oracle, gen, block, ext
     from cpprcoder_b200 import container
     n = 12 * block + extra
     data = synth.GENERATORS[gen](n)
-    enc = ctx.encode(RANS_BYTE, data, block)
+    ctx.force_restart(8192)  # (12 blocks on their own would get the points every 1024 symbols: b2rc_restart_for)
+    try:
+        enc = ctx.encode(RANS_BYTE, data, block)
+    finally:
+        ctx.force_restart(0)
     info = container.parse(enc)
     assert info.seg_syms == 8192 and info.restart.shape == (info.nblocks, block // 8192 - 1, 3)
     want = oracle.encode_blocks(RANS_BYTE, data, block, threads=4)
@@ -301,7 +305,11 @@ def test_byte_rans_container_carries_restart_points(ctx, oracle, gen, block, ext
             nxt = int(recs[k + 1][1]) if k + 1 < recs.shape[0] and 8192 * (k + 2) < blk.size else 1 << 23
             assert x_end == nxt
     assert ctx.decode(enc).tobytes() == data.tobytes()
-    d_enc, used = ctx.encode_device(RANS_BYTE, torch.from_numpy(data).cuda(), block=block)
+    ctx.force_restart(8192)
+    try:
+        d_enc, used = ctx.encode_device(RANS_BYTE, torch.from_numpy(data).cuda(), block=block)
+    finally:
+        ctx.force_restart(0)
     assert used == enc.size and d_enc[:used].cpu().numpy().tobytes() == enc.tobytes()
     d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
     assert ctx.decode_device(d_enc, used, d_out) == n and d_out.cpu().numpy().tobytes() == data.tobytes()
