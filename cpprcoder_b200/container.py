@@ -14,6 +14,7 @@ MAGIC = 0x43523242  # 'B','2','R','C'
 HEADER = 32
 MIN_BLOCK, MAX_BLOCK = 64, 1 << 23
 ADAPTIVE_RESTART_WORDS = 131  # u32 per restart point of the adaptive coder: bytes shifted, low, range, 256 x u16 counts
+ADAPTIVE_RESTART_WORDS_WIDE = 259  # ... for blocks above 65536 bytes: 256 x u32 counts
 
 
 def nblocks_of(n: int, block: int) -> int:
@@ -72,7 +73,7 @@ def parse(buf) -> Info:
     restart = None
     if flags:
         at = base + ((int(offsets[-1]) + 3) & ~3)
-        per = ADAPTIVE_RESTART_WORDS if mode == 1 else 3
+        per = 3 if mode != 1 else (ADAPTIVE_RESTART_WORDS if block <= 65536 else ADAPTIVE_RESTART_WORDS_WIDE)
         words = nblocks * restart_records(block, seg_syms) * per
         if at + 4 * words > buf.size:
             raise ValueError("restart table does not fit")

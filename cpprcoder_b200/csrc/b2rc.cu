@@ -67,6 +67,7 @@ struct b2rc_ctx {
     u32 seg_auto;    // no env setting: streams of few blocks get more points per block (seg_for)
     u32 seg_force;   // b2rc_ctx_force_restart: this spacing whatever the stream (0: not forced)
     u32 seg_syms_adaptive;  // the same for the adaptive coder (524 B per point); env B2RC_ADAPTIVE_RESTART_SYMS (0: none)
+    u32 seg_syms_adaptive_wide;  // ... for blocks above 65536 bytes (1036 B per point); env B2RC_ADAPTIVE_RESTART_SYMS_WIDE
     u32* restart;    // device scratch: the table while a container is being written / read
     size_t restart_cap;
     // segmented static encode (b2rc_encseg.cuh): the range pass's records and the segments' final lows
@@ -178,10 +179,11 @@ bool has_restart(int mode)
     // counts in every point, the adaptive range coder
     return mode == B2RC_MODE_STATIC || mode == B2RC_MODE_RANS_BYTE || mode == B2RC_MODE_ADAPTIVE;
 }
-// u32 words per restart point: {bytes shifted, low, range}; the adaptive coder adds its 256 u16 symbol counts
-u32 rec_words(int mode)
+// u32 words per restart point: {bytes shifted, low, range}; the adaptive coder adds its 256 symbol counts
+// (u16, two per word; u32 for blocks above 65536 bytes)
+u32 rec_words(int mode, u32 block_size)
 {
-    return mode == B2RC_MODE_ADAPTIVE ? 3u + 128u : 3u;
+    return mode != B2RC_MODE_ADAPTIVE ? 3u : (block_size <= 65536u ? ADAPT_REC_WORDS : ADAPT_REC_WORDS_WIDE);
 }
 // The decoder runs one warp per 32 blocks and segment; it wants about as many warps as the 1 GiB / 64 KiB case
 // gives it at the default spacing (512 x 8, seven CTAs of four on every SM).  A stream with fewer blocks gets its
@@ -190,8 +192,9 @@ u32 rec_words(int mode)
 constexpr u64 SEG_AUTO_WARPS = 4096;
 u32 seg_for(const b2rc_ctx* ctx, int mode, u32 block_size, u64 nblocks)
 {
-    if(mode == B2RC_MODE_ADAPTIVE) {  // the points hold u16 counts: blocks of at most 65536 bytes
-        return (block_size <= 65536u && seg_ok(block_size, ctx->seg_syms_adaptive)) ? ctx->seg_syms_adaptive : 0u;
+    if(mode == B2RC_MODE_ADAPTIVE) {  // the points carry the model: one spacing per tree width, no halving
+        const u32 seg = block_size <= 65536u ? ctx->seg_syms_adaptive : ctx->seg_syms_adaptive_wide;
+        return seg_ok(block_size, seg) ? seg : 0u;
     }
     if(!has_restart(mode)) {
         return 0u;
@@ -261,7 +264,8 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_dec_adaptive<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dec_adaptive(true)));
     CK(cudaFuncSetAttribute(k_ans_enc_byte, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_ENC_BYTE_SMEM));
-    CK(cudaFuncSetAttribute(k_dec_adaptive_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_ADAPT_SEG_SMEM));
+    CK(cudaFuncSetAttribute(k_dec_adaptive_seg<Leafless>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_ADAPT_SEG_SMEM));
+    CK(cudaFuncSetAttribute(k_dec_adaptive_seg<LeaflessW>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_ADAPT_SEG_SMEM_WIDE));
     CK(cudaFuncSetAttribute(k_enc_adaptive2, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_AD2_SMEM));
     CK(cudaFuncSetAttribute(k_dec_static_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(true)));
     CK(cudaFuncSetAttribute(k_dec_static_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(false)));
@@ -412,7 +416,7 @@ uint64_t b2rc_bound(int mode, uint64_t n, uint32_t block_size)
     const u64 last = n - (nb - 1) * block_size;
     // room for a restart table at the shortest segment length a context can be set to
     const u64 table = !has_restart(mode) ? 0ull
-                      : 4ull + nb * 4ull * rec_words(mode) *
+                      : 4ull + nb * 4ull * rec_words(mode, block_size) *
                                    b2rc_restart_records(block_size, mode == B2RC_MODE_ADAPTIVE ? B2RC_MIN_ADAPTIVE_RESTART_SYMS
                                                                                               : B2RC_MIN_RESTART_SYMS);
     return index_bytes(nb) + (nb - 1) * b2rc_slot_bytes_for(mode, block_size) + b2rc_slot_bytes_for(mode, (u32)last) +
@@ -488,6 +492,13 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         const long v = atol(e);
         if(v == 0 || (v >= (long)B2RC_MIN_ADAPTIVE_RESTART_SYMS && v <= (1 << 22) && v % 64 == 0)) {
             ctx->seg_syms_adaptive = (u32)v;
+        }
+    }
+    ctx->seg_syms_adaptive_wide = B2RC_DEFAULT_ADAPTIVE_RESTART_SYMS_WIDE;
+    if(const char* e = getenv("B2RC_ADAPTIVE_RESTART_SYMS_WIDE")) {
+        const long v = atol(e);
+        if(v == 0 || (v >= (long)B2RC_MIN_ADAPTIVE_RESTART_SYMS && v <= (1 << 22) && v % 64 == 0)) {
+            ctx->seg_syms_adaptive_wide = (u32)v;
         }
     }
     if(const char* e = getenv("B2RC_PHASES")) {
@@ -912,7 +923,7 @@ int b2rc_k_encode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
     a.seg_syms = d_restart ? seg_syms : 0u;
     if(d_restart) {
         // 0xFF: "no such point" for blocks shorter than the segment start
-        CK(cudaMemsetAsync(d_restart, 0xFF, (size_t)(nb * b2rc_restart_records(block_size, seg_syms) * 4u * rec_words(mode)), st));
+        CK(cudaMemsetAsync(d_restart, 0xFF, (size_t)(nb * b2rc_restart_records(block_size, seg_syms) * 4u * rec_words(mode, block_size)), st));
     }
     const unsigned grid = (unsigned)((nb + 31) / 32);
     KernelTimer kt(ctx, B2RC_K_ENCODE, st);
@@ -1036,11 +1047,12 @@ int b2rc_k_decode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
     const u32 nseg = b2rc_restart_records(block_size, seg_syms) + 1u;
     KernelTimer kt(ctx, B2RC_K_DECODE, st);
     if(mode == B2RC_MODE_ADAPTIVE) {
-        if(block_size > 65536u) {
-            return B2RC_E_ARG;
-        }
         const dim3 agrid((unsigned)((nblocks + 31) / 32), nseg);
-        k_dec_adaptive_seg<<<agrid, 32, DEC_ADAPT_SEG_SMEM, st>>>(a);
+        if(block_size <= 65536u) {
+            k_dec_adaptive_seg<Leafless><<<agrid, 32, DEC_ADAPT_SEG_SMEM, st>>>(a);
+        } else {
+            k_dec_adaptive_seg<LeaflessW><<<agrid, 32, DEC_ADAPT_SEG_SMEM_WIDE, st>>>(a);
+        }
         return launch_check(ctx, "k_dec_adaptive_seg");
     }
     if(mode == B2RC_MODE_RANS_BYTE) {
@@ -1243,7 +1255,7 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
     if(need_hist && (rc = grow(ctx, ctx->freq16, ctx->freq_cap, (size_t)(nb * 512 + 16))) != B2RC_OK) {
         return rc;
     }
-    const u64 table_words = seg ? nb * (u64)rec_words(mode) * b2rc_restart_records(block_size, seg) : 0ull;
+    const u64 table_words = seg ? nb * (u64)rec_words(mode, block_size) * b2rc_restart_records(block_size, seg) : 0ull;
     if(seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(table_words * 4 + 16))) != B2RC_OK) {
         return rc;
     }
@@ -1338,7 +1350,7 @@ int b2rc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t*
         CK(cudaMemcpyAsync(&ctx->h_res->total, d_src + B2RC_HEADER_BYTES + 8 * nb, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const u64 pay = ctx->h_res->total;
-        const u64 bytes = nb * 4ull * rec_words(mode) * b2rc_restart_records(block, seg);
+        const u64 bytes = nb * 4ull * rec_words(mode, block) * b2rc_restart_records(block, seg);
         if(pay > n - idx || align4(pay) + bytes > n - idx) {
             return B2RC_E_CORRUPT;
         }
@@ -1425,7 +1437,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     const u32 nrec = seg ? b2rc_restart_records(block_size, seg) : 0u;
     const u32 P = (mode == B2RC_MODE_STATIC && nb) ? enc_seg_plan(ctx, block_size, seg) : 0u;  // b2rc_encseg.cuh
     int rc;
-    const u64 rw = rec_words(mode);
+    const u64 rw = rec_words(mode, block_size);
     if(seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(nb * nrec * 4ull * rw + 16))) != B2RC_OK) {
         return rc;
     }
@@ -1586,7 +1598,7 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     memcpy(&flags, src + 12, 4);
     const u32 seg = flags ? (flags >> 8) * 64u : 0u;
     const u32 nrec = seg ? b2rc_restart_records(block, seg) : 0u;
-    const u64 rw = rec_words(mode);
+    const u64 rw = rec_words(mode, block);
     const u64 table_bytes = (u64)nb * nrec * 4ull * rw;
     if(seg && (align4(prev) + table_bytes > payload_len)) {
         return B2RC_E_CORRUPT;
@@ -1817,7 +1829,7 @@ static int multi_decode(b2rc_ctx* ctx, const u8* src, u64 n, u8* dst, u64 dst_ca
     u32 flags;
     memcpy(&flags, src + 12, 4);
     const u32 seg = flags ? (flags >> 8) * 64u : 0u;
-    const u64 rec_bytes = seg ? 4ull * rec_words(mode) * b2rc_restart_records(block, seg) : 0ull;  // per block
+    const u64 rec_bytes = seg ? 4ull * rec_words(mode, block) * b2rc_restart_records(block, seg) : 0ull;  // per block
     const u64 pay_end = rd64(src + B2RC_HEADER_BYTES + 8 * nb);
     std::vector<int> rcs((size_t)N, B2RC_OK);
     std::vector<std::thread> pool;
@@ -1894,7 +1906,7 @@ int b2rc_container_bytes(const uint8_t* prefix, uint64_t have, uint64_t* need)
         if((h[3] & 0xFFu) != 1u || !has_restart((int)md) || !seg_ok(h[2], seg)) {
             return B2RC_E_CORRUPT;
         }
-        total = idx + align4(last) + nb * 4ull * rec_words((int)md) * b2rc_restart_records(h[2], seg);
+        total = idx + align4(last) + nb * 4ull * rec_words((int)md, h[2]) * b2rc_restart_records(h[2], seg);
     }
     *need = total;
     return B2RC_OK;
@@ -1926,7 +1938,7 @@ int b2rc_check(const uint8_t* src, uint64_t n, uint64_t* total_out)
     memcpy(&flags, src + 12, 4);
     if(flags) {
         const u32 seg = (flags >> 8) * 64u;
-        if(align4(prev) + (u64)nb * b2rc_restart_records(block, seg) * 4ull * rec_words(mode) > payload_len) {
+        if(align4(prev) + (u64)nb * b2rc_restart_records(block, seg) * 4ull * rec_words(mode, block) > payload_len) {
             return B2RC_E_CORRUPT;
         }
     }

@@ -190,6 +190,18 @@ __global__ void __launch_bounds__(64) k_enc_adaptive2(EncArgs a)
 // of the side taken, one 16-bit store (the node), one 32-bit load (the children of the child).
 struct Leafless {
     static constexpr u32 S = 128u;  // bytes between consecutive words of one lane (u32 [128][32])
+    static constexpr u32 LANE = 4u;
+    static constexpr u32 BYTES = 256u * 32u * 2u;
+    static constexpr u32 REC = ADAPT_REC_WORDS;
+    static __device__ __forceinline__ u32 total(const u32* leaves)
+    {
+        u32 sum = 0;
+        for(u32 k = 0; k < 128u; ++k) {
+            const u32 pair = __ldg(leaves + k);
+            sum += (pair & 0xFFFFu) + (pair >> 16);
+        }
+        return sum;
+    }
     static __device__ __forceinline__ u32 node_addr(u32 base, u32 id) { return base + (id >> 1) * S + (id & 1u) * 2u; }
 
     // `rem` = low minus everything known to lie below the symbol (times t); `v` the node's count, `kids`
@@ -280,9 +292,106 @@ struct Leafless {
     }
 };
 
-constexpr u32 DEC_ADAPT_SEG_SMEM = 256u * 32u * 2u + TILE_BYTES + INQ_BYTES;
+// The same tree with 32-bit counts, for blocks above 65536 bytes: the two children of node j are the two words
+// of an 8-byte pair, [j][lane] (one 64-bit load; the two half-warps take a wavefront each, no conflicts).
+// 32 KiB per warp, six warps per SM.  Written plainly: the narrow tree is the hot one.
+struct LeaflessW {
+    static constexpr u32 S = 256u;  // bytes between consecutive pairs of one lane (u32 [128][32][2])
+    static constexpr u32 LANE = 8u;
+    static constexpr u32 BYTES = 128u * 32u * 8u;
+    static constexpr u32 REC = ADAPT_REC_WORDS_WIDE;
+    static __device__ __forceinline__ u32 node_addr(u32 base, u32 id) { return base + (id >> 1) * S + (id & 1u) * 4u; }
+    static __device__ __forceinline__ void ld2(u32 a, u32& lo, u32& hi)
+    {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
+    }
 
-template <class Src>
+    template <int L>
+    static __device__ __forceinline__ void level(u32 base, u32 t, u32& rem, u32& v, u32& k_lo, u32& k_hi, u32& na,
+                                                 u32& ka, u32& sub)
+    {
+        const u32 ga = 2u * ka - base;  // pair 2 id: the children of the left child; the right child's follow
+        u32 gl_lo = 0, gl_hi = 0, gr_lo = 0, gr_hi = 0;
+        if(L >= 2) {
+            ld2(ga, gl_lo, gl_hi);
+            ld2(ga + S, gr_lo, gr_hi);
+        }
+        const u32 prod = v * t + (t << L);  // left subtree: counts + the implicit one per symbol, times t
+        const bool right = prod <= rem;
+        rem -= right ? prod : 0u;
+        sub = right ? sub - v : v;
+        v += right ? 0u : 1u;
+        sts32v(na, v);  // incremented when the symbol went left, unchanged otherwise
+        v = right ? k_hi : k_lo;
+        na = ka + (right ? 4u : 0u);
+        ka = ga + (right ? S : 0u);
+        k_lo = right ? gr_lo : gl_lo;
+        k_hi = right ? gr_hi : gl_hi;
+    }
+
+    static __device__ __forceinline__ u32 decode(u32 base, u32 t, u32 seen, u32& rem, u32& freq)
+    {
+        u32 na = base + 4u, ka = base + S;  // node 1, the root, and the pair of its children (nodes 2, 3)
+        u32 v = lds32v(na), k_lo, k_hi, sub = seen;
+        ld2(ka, k_lo, k_hi);
+        level<7>(base, t, rem, v, k_lo, k_hi, na, ka, sub);
+        level<6>(base, t, rem, v, k_lo, k_hi, na, ka, sub);
+        level<5>(base, t, rem, v, k_lo, k_hi, na, ka, sub);
+        level<4>(base, t, rem, v, k_lo, k_hi, na, ka, sub);
+        level<3>(base, t, rem, v, k_lo, k_hi, na, ka, sub);
+        level<2>(base, t, rem, v, k_lo, k_hi, na, ka, sub);
+        level<1>(base, t, rem, v, k_lo, k_hi, na, ka, sub);
+        // the last level: the node's two children are symbols; ka = base + 256 * (its number)
+        const u32 prod = (v + 1u) * t;
+        const bool right = prod <= rem;
+        rem -= right ? prod : 0u;
+        sub = right ? sub - v : v;
+        v += right ? 0u : 1u;
+        sts32v(na, v);
+        freq = sub + 1u;
+        return (((ka - base) >> 7) | (right ? 1u : 0u)) & 255u;
+    }
+
+    // The lane's tree from 256 symbol counts (one per word at `leaves`; null: an empty model).
+    static __device__ __forceinline__ void build(u32 base, const u32* leaves)
+    {
+        if(!leaves) {
+            for(u32 j = 0; j < 256u; ++j) {
+                sts32v(base + (j >> 1) * S + (j & 1u) * 4u, 0u);
+            }
+            return;
+        }
+        // totals bottom up, in place ...
+        for(u32 id = 255u; id >= 128u; --id) {
+            sts32v(node_addr(base, id), __ldg(leaves + 2u * (id - 128u)) + __ldg(leaves + 2u * (id - 128u) + 1u));
+        }
+        for(u32 id = 127u; id >= 1u; --id) {
+            sts32v(node_addr(base, id), lds32v(node_addr(base, 2u * id)) + lds32v(node_addr(base, 2u * id + 1u)));
+        }
+        // ... then every node takes its LEFT child's total, parents before their children
+        for(u32 id = 1u; id < 128u; ++id) {
+            sts32v(node_addr(base, id), lds32v(node_addr(base, 2u * id)));
+        }
+        for(u32 id = 128u; id < 256u; ++id) {
+            sts32v(node_addr(base, id), __ldg(leaves + 2u * (id - 128u)));
+        }
+        sts32v(base, 0u);
+    }
+    // sum of the counts of a point (must equal its position in the block)
+    static __device__ __forceinline__ u32 total(const u32* leaves)
+    {
+        u32 sum = 0;
+        for(u32 k = 0; k < 256u; ++k) {
+            sum += __ldg(leaves + k);
+        }
+        return sum;
+    }
+};
+
+constexpr u32 DEC_ADAPT_SEG_SMEM = 256u * 32u * 2u + TILE_BYTES + INQ_BYTES;
+constexpr u32 DEC_ADAPT_SEG_SMEM_WIDE = LeaflessW::BYTES + TILE_BYTES + INQ_BYTES;
+
+template <class Tree, class Src>
 __device__ __forceinline__ void dec_adaptive_seg_tile(u32 tbase, RcDec& d, Src& src, u32 otile_a, u32 tile_off, u32 n_b,
                                                       u32 lane)
 {
@@ -300,7 +409,7 @@ __device__ __forceinline__ void dec_adaptive_seg_tile(u32 tbase, RcDec& d, Src& 
             if(tile_off + j < n_b) {
                 const u32 t = rc_div(d.range, d0 + j, magic);
                 u32 freq;
-                const u32 sym = Leafless::decode(tbase, t, tile_off + j, d.low, freq);  // d.low -= cum * t on the way
+                const u32 sym = Tree::decode(tbase, t, tile_off + j, d.low, freq);  // d.low -= cum * t on the way
                 rc_dec_advance(d, 0u, freq, t, src);
                 word |= sym << (8 * k);
             }
@@ -309,11 +418,13 @@ __device__ __forceinline__ void dec_adaptive_seg_tile(u32 tbase, RcDec& d, Src& 
     }
 }
 
-// grid = (ceil(nblocks / 32), segments per block); one warp per CTA.  Blocks of at most 65536 bytes.
+// grid = (ceil(nblocks / 32), segments per block); one warp per CTA.  Tree = Leafless for blocks of at most
+// 65536 bytes (16-bit counts), LeaflessW above.
+template <class Tree>
 __global__ void __launch_bounds__(32) k_dec_adaptive_seg(DecArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
-    constexpr u32 TAB_BYTES = 256u * 32u * 2u;
+    constexpr u32 TAB_BYTES = Tree::BYTES;
     const u32 sbase = smem_addr(smem);
     u8* otile = smem + TAB_BYTES;
     const u32 otile_a = sbase + TAB_BYTES;
@@ -357,7 +468,7 @@ __global__ void __launch_bounds__(32) k_dec_adaptive_seg(DecArgs a)
     u32 skip = skip0, word0 = 0, range0 = RC_ADAPT_RANGE0, enc_low = 0;
     const u32* leaves = nullptr;
     if(seg != 0u && mine_ok) {
-        const u32* rec = a.restart + (b * nrec + seg - 1u) * (u64)ADAPT_REC_WORDS;
+        const u32* rec = a.restart + (b * nrec + seg - 1u) * (u64)Tree::REC;
         const u32 m = rec[0];
         enc_low = rec[1];
         range0 = rec[2];
@@ -371,17 +482,12 @@ __global__ void __launch_bounds__(32) k_dec_adaptive_seg(DecArgs a)
             skip = (skip + m) & 3u;
         }
     }
-    const u32 tbase = sbase + lane * 4u;
-    Leafless::build(tbase, mine_ok ? leaves : nullptr);
+    const u32 tbase = sbase + lane * Tree::LANE;
+    Tree::build(tbase, mine_ok ? leaves : nullptr);
     if(mine_ok && leaves) {
         // the counts of a point must add up to the symbols in front of it, or the walk's bookkeeping
         // (and with it every frequency) would be off: the root's total is checked against the position
-        u32 total = 0;
-        for(u32 k = 0; k < 128u; ++k) {
-            const u32 pair = __ldg(leaves + k);
-            total += (pair & 0xFFFFu) + (pair >> 16);
-        }
-        if(total != seg_lo) {
+        if(Tree::total(leaves) != seg_lo) {
             mine_ok = false;
             atomicOr(a.err, ERR_CORRUPT);
         }
@@ -410,9 +516,9 @@ __global__ void __launch_bounds__(32) k_dec_adaptive_seg(DecArgs a)
     for(u32 tix = tix0; tix < tix1; ++tix) {
         if(__all_sync(FULL, src.tile_is_inside())) {
             WordSrcInside in{src};
-            dec_adaptive_seg_tile(tbase, d, in, otile_a, tix * TILE, n_eff, lane);
+            dec_adaptive_seg_tile<Tree>(tbase, d, in, otile_a, tix * TILE, n_eff, lane);
         } else {
-            dec_adaptive_seg_tile(tbase, d, src, otile_a, tix * TILE, n_eff, lane);
+            dec_adaptive_seg_tile<Tree>(tbase, d, src, otile_a, tix * TILE, n_eff, lane);
         }
         __syncwarp();
         // only this segment's columns of the tile are this warp's to store
@@ -425,7 +531,7 @@ __global__ void __launch_bounds__(32) k_dec_adaptive_seg(DecArgs a)
         const u32 used = 4u * src.rd - skip0 - (u32)d.wbits / 8u;
         bool good;
         if(seg_hi < n_b) {
-            const u32* rec = a.restart + (b * nrec + seg) * (u64)ADAPT_REC_WORDS;
+            const u32* rec = a.restart + (b * nrec + seg) * (u64)Tree::REC;
             const u32 m = rec[0];
             good = m != 0xFFFFFFFFu && (u64)m + RC_ADAPT_HDR + 5u <= len && used == m + 5u;
             if(good) {

@@ -693,9 +693,12 @@ struct TreeOps {
 };
 
 constexpr u32 ADAPT_REC_WORDS = 3u + 128u;  // B2RC_ADAPTIVE_RESTART_WORDS: a restart point of the adaptive coder
+constexpr u32 ADAPT_REC_WORDS_WIDE = 3u + 256u;  // ... for blocks above 65536 bytes: the counts take 32 bits
+template <class W>
+constexpr u32 adapt_rec_words() { return sizeof(W) == 2 ? ADAPT_REC_WORDS : ADAPT_REC_WORDS_WIDE; }
 
 // Called by k_enc_adaptive at the tile that starts segment j >= 1 of the lane's block: the point's three
-// words, then the model's 256 leaf counts (entries 256..511 of the lane's tree), two per word.
+// words, then the model's 256 leaf counts (entries 256..511 of the lane's tree), two per word (u16) or one.
 template <class W>
 __device__ __forceinline__ void adaptive_mark(u32* rec, const RcEnc& st, s32 wcount, const LaneTab<W>& tab)
 {
@@ -703,9 +706,16 @@ __device__ __forceinline__ void adaptive_mark(u32* rec, const RcEnc& st, s32 wco
     rec[0] = 4u * words + (u32)st.ocnt / 8u - 1u;       // bytes shifted out of low, the dummy byte aside
     rec[1] = st.low;
     rec[2] = st.range;
+    if(sizeof(W) == 2) {
 #pragma unroll 4
-    for(u32 s = 0; s < 256u; s += 2u) {
-        rec[3u + s / 2u] = tab.ld(256u + s) | (tab.ld(257u + s) << 16);
+        for(u32 s = 0; s < 256u; s += 2u) {
+            rec[3u + s / 2u] = tab.ld(256u + s) | (tab.ld(257u + s) << 16);
+        }
+    } else {
+#pragma unroll 4
+        for(u32 s = 0; s < 256u; ++s) {
+            rec[3u + s] = tab.ld(256u + s);
+        }
     }
 }
 
@@ -728,7 +738,7 @@ __device__ __forceinline__ void enc_adaptive_tiles(const EncArgs& a, u32 tiles, 
         if(a.restart && tix != 0u && (tix * TILE) % a.seg_syms == 0u && tix * TILE < n_b) {
             // a segment starts here: what a decoder needs to start here too, the model included (b2rc_adaptseg.cuh)
             const u32 nrec = (a.block + a.seg_syms - 1u) / a.seg_syms - 1u;
-            adaptive_mark(a.restart + ((b0 + lane) * nrec + tix * TILE / a.seg_syms - 1u) * (u64)ADAPT_REC_WORDS, st,
+            adaptive_mark(a.restart + ((b0 + lane) * nrec + tix * TILE / a.seg_syms - 1u) * (u64)adapt_rec_words<W>(), st,
                           sink.wcount, tab);
         }
         const u32 row = tiles + (tix & 1u) * TILE_BYTES + lane * ROW;

@@ -60,6 +60,11 @@ extern "C" {
 #define B2RC_DEFAULT_ADAPTIVE_RESTART_SYMS 21888u
 #define B2RC_MIN_ADAPTIVE_RESTART_SYMS 4096u
 #define B2RC_ADAPTIVE_RESTART_WORDS 131u /* u32 per point: bytes shifted, low, range, then 256 x u16 counts */
+/* Blocks above 65536 bytes: the counts take 32 bits (259 words = 1036 bytes a point) and the decoder's tree 32 KiB
+ * per warp, six warps per SM = 888 on a B200.  Default every 43712 symbols: 1 GiB in blocks of 128 KiB .. 1 MiB is
+ * then 768 warps, one wave (+2.4 % size).  env B2RC_ADAPTIVE_RESTART_SYMS_WIDE, 0 = none. */
+#define B2RC_DEFAULT_ADAPTIVE_RESTART_SYMS_WIDE 43712u
+#define B2RC_ADAPTIVE_RESTART_WORDS_WIDE 259u
 
 /* Status codes.  0 = the reference's `true` / Status_Success (cpprcoder.h:112-117);
  * negatives map to `false` / Status_Error in the C++ header. */

@@ -131,3 +131,62 @@ def test_two_warp_encoder_writes_the_same_container(oracle):
     finally:
         a.close()
         b.close()
+
+
+@pytest.mark.parametrize("block,seg", [(131072, None), (262144, 43712), (1 << 20, 8192), (131072, 0)])
+def test_wide_blocks_carry_points_with_32_bit_counts(oracle, block, seg):
+    """Blocks above 65536 bytes: a symbol's count no longer fits 16 bits, the points hold 256 u32 counts (259 words)
+    and the decoder walks a tree of 32-bit nodes (LeaflessW).  Same contract: the reference's payloads, the model of
+    every point = the counts of the symbols in front of it, several chains per block, damage is detected."""
+    import torch
+    from cpprcoder_b200._lib import B2rcError, E_CORRUPT
+    ctx = make_ctx(**({} if seg is None else {"B2RC_ADAPTIVE_RESTART_SYMS_WIDE": seg}))
+    want_seg = 43712 if seg is None else seg
+    try:
+        # one block of a single symbol (its count passes 65535 inside the block), text-like and mixed blocks, a ragged end
+        data = np.concatenate([synth.kennedy(2 * block), np.full(block, 0x41, np.uint8), synth.mixed(2 * block + 70001)])
+        enc = ctx.encode(ADAPTIVE, data, block)
+        info = container.parse(enc)
+        assert payloads(enc) == oracle.encode_blocks(ADAPTIVE, data, block, threads=4)
+        if not want_seg:
+            assert info.restart is None
+        else:
+            assert info.seg_syms == want_seg and info.restart.shape == (info.nblocks, -(-block // want_seg) - 1, 259)
+            for b in range(info.nblocks):
+                blk = data[b * block:(b + 1) * block]
+                for j in range(info.restart.shape[1]):
+                    at = (j + 1) * want_seg
+                    rec = info.restart[b, j]
+                    if at >= blk.size:
+                        assert rec[0] == 0xFFFFFFFF
+                        continue
+                    assert np.array_equal(rec[3:], np.bincount(blk[:at], minlength=256).astype(np.uint32)), (b, j)
+            assert int(info.restart[2, -1, 3 + 0x41]) > 65535
+        assert ctx.decode(enc).tobytes() == data.tobytes()
+        src = torch.from_numpy(data).cuda()
+        e2, used = ctx.encode_device(ADAPTIVE, src, block=block)
+        assert e2[:used].cpu().numpy().tobytes() == enc.tobytes()
+        dst = torch.empty(data.size, dtype=torch.uint8, device="cuda")
+        assert ctx.decode_device(e2, used, dst) == data.size and dst.cpu().numpy().tobytes() == data.tobytes()
+        # a container without points (what the reference-shaped path writes) decodes with either context
+        plain = container.build(ADAPTIVE, block, data.size, payloads(enc))
+        assert ctx.decode(plain).tobytes() == data.tobytes()
+        if want_seg:
+            table_at = info.payload_base + ((int(info.offsets[-1]) + 3) & ~3)
+            nrec = info.restart.shape[1]
+            rng = np.random.default_rng(block + want_seg)
+            for trial in range(12):
+                bad = enc.copy()
+                b = int(rng.integers(0, 2))                       # full blocks: every point is live
+                j = int(rng.integers(0, nrec))
+                w = trial % 4                                      # 0: bytes shifted, 1: low, 2: range, 3: a count
+                word_ix = w if w < 3 else 3 + int(rng.integers(0, 256))
+                at = table_at + 4 * ((b * nrec + j) * 259 + word_ix)
+                word = int(np.frombuffer(bad[at:at + 4].tobytes(), dtype="<u4")[0])
+                word = (word + 1) & 0xFFFFFFFF if w in (0, 3) else word ^ (1 << int(rng.integers(0, 32)))
+                bad[at:at + 4] = np.frombuffer(np.uint32(word).tobytes(), dtype=np.uint8)
+                with pytest.raises(B2rcError) as e:
+                    ctx.decode(bad)
+                assert e.value.code == E_CORRUPT, (trial, b, j, w)
+    finally:
+        ctx.close()
