@@ -92,8 +92,11 @@ def config_of(args, world):
         "global_bytes": nbytes * world,
         "parallelism": f"blocks sharded by contiguous range over {world} GPU(s)",
         "l2": "inputs (1 GiB per GPU) are larger than the 126 MB L2; no explicit flush",
-        "restart_points": ("every 8192 symbols (static coder: 84 B per 64 KiB block behind the payloads, counted in "
-                           "compressed_ratio; the payloads are the reference's)") if mode == 0 else "none",
+        "restart_points": ("every 8192 symbols for a stream that fills the GPU at that spacing, as 1 GiB per GPU does "
+                           "(static coder: 84 B per 64 KiB block behind the payloads, counted in compressed_ratio; the "
+                           "payloads are the reference's); closer together for fewer blocks (b2rc_restart_for)") if mode == 0
+                          else ("adaptive coder: every 21888 symbols, 524 B a point with the model's counts, counted in "
+                                "compressed_ratio" if mode == 1 else "none"),
     }, gen, nbytes, mode, block
 
 
@@ -582,6 +585,8 @@ def run_ours(args):
                   "encode_GBps": s["encode_GBps"], "decode_GBps": s["decode_GBps"], "parity_blocks_checked_this_rank": sp,
                   "speedup_over_one_gpu_share": s["value"] / (main["value"] / world),
                   "efficiency": s["value"] / main["value"],
+                  "compressed_ratio": s["compressed_ratio"],
+                  "restart_syms": ctx.restart_for(mode, block, -(-(nbytes // block) // world)) if mode <= 3 else 0,
                   "note": "same stream as 1 GPU codes alone, blocks sharded over the ranks; efficiency = strong value / "
                           "weak value of this run (= N x the per-GPU rate on a full 1 GiB shard)"}
         del sleg
