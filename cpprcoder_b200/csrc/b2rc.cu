@@ -64,6 +64,7 @@ struct b2rc_ctx {
     u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
     u64 max_phases;  // <= B2RC_PHASES; env B2RC_PHASES overrides (1 switches the phased decode off)
     u32 seg_syms;    // restart points of the static coder every so many symbols; env B2RC_RESTART_SYMS (0: none)
+    u32 ranges_warps;  // env B2RC_RANGES_WARPS: 1 = k_enc_ranges for 64 KiB blocks too, 2 / 3 = k_enc_ranges2, unset = by size
     u32 seg_auto;    // no env setting: streams of few blocks get more points per block (seg_for)
     u32 seg_force;   // b2rc_ctx_force_restart: this spacing whatever the stream (0: not forced)
     u32 seg_syms_adaptive;  // the same for the adaptive coder (524 B per point); env B2RC_ADAPTIVE_RESTART_SYMS (0: none)
@@ -272,6 +273,8 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_enc_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(false, ENC_SEG_WARPS)));
     CK(cudaFuncSetAttribute(k_enc_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(true, ENC_SEG_WARPS)));
     CK(cudaFuncSetAttribute(k_ans_dec_byte_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_DEC_BYTE_SEG_SMEM));
+    CK(cudaFuncSetAttribute(k_enc_ranges2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_RANGES2_SMEM));
+    CK(cudaFuncSetAttribute(k_enc_ranges2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_RANGES2_SMEM));
     CK(cudaFuncSetAttribute(k_blk_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_FWD_SMEM));
     CK(cudaFuncSetAttribute(k_blk_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_INV_SMEM));
     CK(cudaFuncSetAttribute(k_blk_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_TIES_SMEM));
@@ -483,6 +486,11 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
     }
     if(const char* e = getenv("B2RC_FORCE_EXACT")) {
         ctx->force_exact = atol(e) ? 1u : 0u;
+    }
+    ctx->ranges_warps = 0;  // by the size of the call (static_ranges_launch)
+    if(const char* e = getenv("B2RC_RANGES_WARPS")) {
+        const long v = atol(e);
+        ctx->ranges_warps = (v >= 1 && v <= 3) ? (u32)v : 0u;
     }
     if(const char* e = getenv("B2RC_ADAPTIVE_TWO_WARPS")) {
         ctx->adaptive_two_warps = atol(e) ? 1u : 0u;
@@ -1188,12 +1196,20 @@ static SegArgs seg_args(b2rc_ctx* ctx, u32 block, u32 P, const u8* d_src, u64 n,
 }
 
 // K2r: sizes of all payloads (and where every segment starts), before a byte is coded
-static int static_ranges_launch(b2rc_ctx* ctx, const SegArgs& a, cudaStream_t st)
+// `call_blocks`: blocks of the whole call (the chunks of the host pipeline run side by side).  A stream that leaves
+// most of the GPU idle -- at most one CTA per SM -- takes the three-warp kernel for 64 KiB blocks: 0.75 instead of
+// 1.06 ms; with more CTAs than SMs the extra warps get in each other's way (1 GiB: 2.1 against 1.08 ms).
+static int static_ranges_launch(b2rc_ctx* ctx, const SegArgs& a, u64 call_blocks, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((a.nblocks + 31) / 32);
+    const u32 warps = ctx->ranges_warps ? ctx->ranges_warps : ((call_blocks + 31) / 32 <= 148u ? 3u : 1u);
     KernelTimer kt(ctx, B2RC_K_RANGES, st);
     if(a.block > 65536u) {
         k_enc_ranges<true><<<grid, 32, ENC_RANGES_SMEM, st>>>(a);
+    } else if(a.block == 65536u && warps == 3) {  // total 65536 happens for these only (b2rc_encseg.cuh)
+        k_enc_ranges2<3><<<grid, 96, ENC_RANGES2_SMEM, st>>>(a);
+    } else if(a.block == 65536u && warps == 2) {
+        k_enc_ranges2<2><<<grid, 64, ENC_RANGES2_SMEM, st>>>(a);
     } else {
         k_enc_ranges<false><<<grid, 32, ENC_RANGES_SMEM, st>>>(a);
     }
@@ -1265,7 +1281,7 @@ int b2rc_encode_device(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8
         const SegArgs a = seg_args(ctx, block_size, P, d_src, n, ctx->freq16, 0, ctx->sizes, d_offsets, d_dst + idx,
                                    dst_cap - idx, seg ? ctx->restart : nullptr, seg);
         if((rc = b2rc_k_histogram(ctx, d_src, n, block_size, ctx->freq16, st)) != B2RC_OK ||
-           (rc = static_ranges_launch(ctx, a, st)) != B2RC_OK ||
+           (rc = static_ranges_launch(ctx, a, nb, st)) != B2RC_OK ||
            (rc = scan_launch(ctx, ctx->sizes, nb, d_offsets, ctx->d_total, d_dst, (u32)mode, block_size, n, st, nullptr,
                              flags_of(seg))) != B2RC_OK ||
            (rc = static_segments_launch(ctx, a, st)) != B2RC_OK) {
@@ -1483,7 +1499,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         if(P) {  // sizes first (the range pass), the payloads then go straight to their final place
             sa = seg_args(ctx, block_size, P, ctx->stage_in + byte0, bytes, freq, b0, ctx->sizes + b0, d_offsets + b0,
                           d_payload, bound - idx, seg ? ctx->restart + b0 * nrec * rw : nullptr, seg);
-            if((rc = static_ranges_launch(ctx, sa, st)) != B2RC_OK) {
+            if((rc = static_ranges_launch(ctx, sa, nb, st)) != B2RC_OK) {
                 return rc;
             }
         } else if((rc = b2rc_k_encode_blocks_r(ctx, mode, block_size, ctx->stage_in + byte0, bytes, freq,

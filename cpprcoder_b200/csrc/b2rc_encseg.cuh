@@ -218,54 +218,68 @@ __device__ __forceinline__ void enc_range_tiles16(const SegArgs& a, u32 tiles, u
     }
 }
 
-template <bool WIDE>
-__global__ void __launch_bounds__(32) k_enc_ranges(SegArgs a)
-{
-    extern __shared__ __align__(16) u8 smem[];
-    const u32 sbase = smem_addr(smem);
-    const u32 tiles = sbase + 256u * 32u * 2u;
-    const u32 lane = lane_id();
-    const u64 b0 = (u64)blockIdx.x * 32u;
-    const u64 b = b0 + lane;
-    const bool has = b < a.nblocks;
-    const u32 n_b = has ? seg_block_len(a, b) : 0u;
+// What a warp of the range pass knows about its 32 blocks once the frequencies are in shared memory.
+struct RangesWarp {
+    u32 lane, n_b, n_max, total, ftab;
+    u64 b0, b;
+    bool has, ragged;
+    u32* rec;
+};
 
-    stage_tile(tiles, a.src, a.n, b0, a.block, 0, lane);
+// Stages input tile 0 (committed, not waited for) and builds the 32 blocks' frequency table, u16 [256][32].
+__device__ __forceinline__ void ranges_prepare(const SegArgs& a, u8* smem, u32 sbase, u32 tiles, RangesWarp& w)
+{
+    w.lane = lane_id();
+    w.b0 = (u64)blockIdx.x * 32u;
+    w.b = w.b0 + w.lane;
+    w.has = w.b < a.nblocks;
+    w.n_b = w.has ? seg_block_len(a, w.b) : 0u;
+    stage_tile(tiles, a.src, a.n, w.b0, a.block, 0, w.lane);
     cp_async_commit();
     u16* frq16 = reinterpret_cast<u16*>(smem);
     u32 total = 0;
 #pragma unroll 1
     for(u32 r = 0; r < 32; ++r) {
-        if(b0 + r >= a.nblocks) {
+        if(w.b0 + r >= a.nblocks) {
             break;
         }
         // lane j holds the frequencies of symbols 8j .. 8j+7 of block b0+r
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.freq16 + (b0 + r) * 256u) + lane);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.freq16 + (w.b0 + r) * 256u) + w.lane);
         const u32 f[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
                           v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
         u32 sum = 0;
 #pragma unroll
         for(int k = 0; k < 8; ++k) {
             sum += f[k];
-            frq16[(8u * lane + k) * 32u + r] = (u16)f[k];
+            frq16[(8u * w.lane + k) * 32u + r] = (u16)f[k];
         }
         sum = __reduce_add_sync(FULL, sum);
-        if(lane == r) {
+        if(w.lane == r) {
             total = sum;
         }
     }
     __syncwarp();
+    w.total = total;
+    w.n_max = __reduce_max_sync(FULL, w.n_b);
+    w.ragged = __any_sync(FULL, w.n_b != w.n_max);
+    w.rec = a.recs + (w.has ? w.b : w.b0) * (u64)(a.nseg + 1u) * 2u;
+    w.ftab = sbase + w.lane * 2u;
+}
 
+// The pass with ONE warp per 32 blocks (every path), sizes included.
+template <bool WIDE>
+__device__ __forceinline__ void ranges_one_warp(const SegArgs& a, u32 tiles, const RangesWarp& w)
+{
+    const u32 total = w.total, lane = w.lane, n_b = w.n_b, n_max = w.n_max, ftab = w.ftab;
+    const u64 b0 = w.b0;
+    u32* rec = w.rec;
     const u32 magic = rc_magic(total);
     const bool is_pow2 = total != 0 && (total & (total - 1u)) == 0;
     const u32 shift = is_pow2 ? 31u - rc_clz(total) : 0u;
-    const u32 n_max = __reduce_max_sync(FULL, n_b);
-    const bool all_pow2 = __all_sync(FULL, is_pow2 || !has);
-    const bool ragged = __any_sync(FULL, n_b != n_max);
-    u32* rec = a.recs + (has ? b : b0) * (u64)(a.nseg + 1u) * 2u;
-    const u32 ftab = sbase + lane * 2u;
+    const bool all_pow2 = __all_sync(FULL, is_pow2 || !w.has);
+    const bool ragged = w.ragged;
     constexpr int MAXSH = WIDE ? 3 : 2;
-    const bool all16 = !WIDE && __all_sync(FULL, total == 65536u || !has);
+    const bool all16 = !WIDE && __all_sync(FULL, total == 65536u || !w.has);
     if(all16 && !ragged) {
         enc_range_tiles16<false>(a, tiles, ftab, b0, n_b, n_max, lane, rec);
     } else if(all16) {
@@ -279,9 +293,289 @@ __global__ void __launch_bounds__(32) k_enc_ranges(SegArgs a)
     } else {
         enc_range_tiles<3, false, true>(a, tiles, ftab, b0, n_b, n_max, total, magic, shift, lane, rec);
     }
-    if(has) {
+    if(w.has) {
         const u32 nseg_b = (n_b + a.P - 1u) / a.P;
-        a.sizes[b] = RC_STATIC_HDR + 5u + rec[2u * nseg_b];  // cpprcoder.h:386-395 header, buffer_, shifted bytes, low
+        a.sizes[w.b] = RC_STATIC_HDR + 5u + rec[2u * nseg_b];  // cpprcoder.h:386-395 header, buffer_, shifted bytes, low
+    }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(32) k_enc_ranges(SegArgs a)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    const u32 sbase = smem_addr(smem);
+    const u32 tiles = sbase + 256u * 32u * 2u;
+    RangesWarp w;
+    ranges_prepare(a, smem, sbase, tiles, w);
+    ranges_one_warp<WIDE>(a, tiles, w);
+}
+
+// --------------------------------------- K2r for 64 KiB blocks, two or three warps per 32 blocks --
+// A lone warp issues an instruction every other cycle at best (2.0 - 2.3 cycles each in every capture of this
+// round), so k_enc_ranges's 16 instructions per symbol cost 32 cycles although the chain for total == 65536 is
+// only multiply-add, minimum, add.  Most of the 16 do not depend on the chain: the symbol's byte, its table
+// address, its frequency, and the count of the bytes shifted out (multiply, highest set bit, mask, add).  Here
+// other warps of the CTA do that work:
+//   chain warp    per symbol: load {freq, 256 freq - 256}, two adds, three multiply-adds, two shifts, minimum,
+//                 store r - 256 -- ten instructions, immediate addresses, a chain three deep (ranges2_chain)
+//   freqs warp    turns input tile k + 1 into the tile of {freq, addend} pairs the chain warp reads next
+//   shifts warp   counts what tile k - 1 shifted out from the products the chain warp left, writes the byte
+//                 counts and the sizes, fetches the input tiles (cp.async) three tiles ahead
+// (k_enc_ranges2<2>: one helper warp does both helper jobs).  One CTA barrier per tile of 64 symbols.  Same
+// arithmetic, same records (tests/test_gpu_encseg.py runs every case with 1, 2 and 3 warps).
+// MEASURED, 1 GiB Zipf / 128 MiB: one warp 1.08 / 1.06 ms; two warps 2.9 / 1.37 (the helper is the longer half);
+// three warps 2.1 / 0.75 ms (22 cycles per link).  With more CTAs than SMs the extra warps share schedulers with
+// other chains and everything slows down; with at most one CTA per SM (4736 blocks, 296 MiB) three warps win,
+// and that is when they run (static_ranges_launch; env B2RC_RANGES_WARPS = 1, 2, 3 forces one form).
+// A warp whose blocks do not all have total 65536 (a block of one repeated byte: 0x8000) falls back to the
+// one-warp paths; the other warps leave.
+constexpr u32 ENC_RANGES2_F = TILE * 256u;  // one tile of {freq, 256 * freq - 256}, 2 x u32 [symbol][lane]
+constexpr u32 ENC_RANGES2_T = TILE * 128u;  // one tile of products, u32 [symbol][lane]
+constexpr u32 ENC_RANGES2_SRC = 4u;         // input tiles in the second warp's ring: three tiles of lead on DRAM
+constexpr u32 ENC_RANGES2_SMEM =
+    256u * 32u * 2u + ENC_RANGES2_SRC * TILE_BYTES + 2u * ENC_RANGES2_F + 2u * ENC_RANGES2_T + 16u;
+constexpr u32 RANGES2_IDLE = 0x7FFFFFFFu;   // "no symbol here": + 256 has its top bit set, shift 0
+
+// The chain carries m = t - 256.  With r = freq * t = freq * m + 256 * freq the three candidates of range_step16
+// are multiply-adds whose addends (256 * freq - K) do not depend on the chain, and their minimum IS the next m:
+// the link is multiply-add, shift, minimum -- three deep, no add.
+template <bool RAGGED>
+__device__ __forceinline__ void ranges2_chain(const SegArgs& a, u32 fbuf, u32 tbuf, const RangesWarp& w)
+{
+    u32 m = (RC_STATIC_RANGE0 >> 16) - 256u;
+    const u32 ntiles = (w.n_max + TILE - 1) / TILE;
+    const u32 seg_tiles = a.P / TILE;
+    u32 next_mark = 0;
+    __syncthreads();  // the first tile of frequencies is there
+#pragma unroll 1
+    for(u32 tix = 0; tix < ntiles; ++tix) {
+        if(tix == next_mark) {  // a segment starts here; another warp writes the byte count beside it
+            next_mark += seg_tiles;
+            if(tix * TILE < w.n_b) {
+                w.rec[2u * (tix / seg_tiles) + 1u] = (m + 256u) << 16;  // any range with the same range >> 16 serves
+            }
+        }
+        const u32 F = fbuf + (tix & 1u) * ENC_RANGES2_F + w.lane * 8u;
+        const u32 T = tbuf + (tix & 1u) * ENC_RANGES2_T + w.lane * 4u;
+        u32 f[8], c[8];
+#pragma unroll
+        for(int k = 0; k < 8; ++k) {
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(f[k]), "=r"(c[k]) : "r"(F + (u32)k * 256u));
+        }
+#pragma unroll
+        for(u32 at = 0; at < (u32)TILE; at += 8u) {
+            u32 nf[8], nc[8];
+#pragma unroll
+            for(int k = 0; k < 8; ++k) {
+                nf[k] = nc[k] = 0u;
+                if(at + 8u < (u32)TILE) {
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                                 : "=r"(nf[k]), "=r"(nc[k])
+                                 : "r"(F + (at + 8u + (u32)k) * 256u));
+                }
+            }
+#pragma unroll
+            for(int k = 0; k < 8; ++k) {
+                u32 r1, r2, r3 = RANGES2_IDLE;
+                if(!RAGGED || tix * TILE + at + (u32)k < w.n_b) {
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r1) : "r"(f[k]), "r"(m), "r"(c[k] - 0x00FFFF00u));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r2) : "r"(f[k]), "r"(m), "r"(c[k] - 0x0000FF00u));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r3) : "r"(f[k]), "r"(m), "r"(c[k]));
+                    m = min(min(r1 >> 16, r2 >> 8), r3);
+                }
+                sts32v(T + (at + (u32)k) * 128u, r3);
+            }
+#pragma unroll
+            for(int k = 0; k < 8; ++k) {
+                f[k] = nf[k];
+                c[k] = nc[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// bytes * 8 the coder shifts out for one tile of products
+__device__ __forceinline__ u32 ranges2_shifts(u32 T)
+{
+#if defined(B2RC_RANGES2_NO_SHIFTS)  // timing experiment only: wrong sizes
+    return lds32v(T) & 8u;
+#else
+    u32 bits = 0;
+#pragma unroll 1
+    for(u32 j0 = 0; j0 < (u32)TILE; j0 += 16u) {
+        u32 r[16];
+#pragma unroll
+        for(int k = 0; k < 16; ++k) {
+            r[k] = lds32v(T + (j0 + (u32)k) * 128u);
+        }
+#pragma unroll
+        for(int k = 0; k < 16; ++k) {
+            u32 top;
+            asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(r[k] + 256u));
+            bits += ~top & 24u;
+        }
+    }
+    return bits;
+#endif
+}
+
+// one input tile -> one tile of frequencies.  Thirty-two at a time: the loads of a batch go out together (volatile
+// accesses keep their order, and a store behind every load would wait for two shared-memory round trips)
+__device__ __forceinline__ void ranges2_freqs(u32 tile_row, u32 ftab, u32 F)
+{
+#pragma unroll 1
+    for(u32 j0 = 0; j0 < (u32)TILE; j0 += 32u) {
+        u32 sym[32], f[32];
+#pragma unroll
+        for(int k = 0; k < 32; ++k) {
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sym[k]) : "r"(tile_row + j0 + (u32)k));
+        }
+#pragma unroll
+        for(int k = 0; k < 32; ++k) {
+            f[k] = lds16(ftab + sym[k] * 64u);
+        }
+#pragma unroll
+        for(int k = 0; k < 32; ++k) {
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(F + (j0 + (u32)k) * 256u), "r"(f[k]), "r"(f[k] * 256u - 256u));
+        }
+    }
+}
+
+// FREQS: this warp turns input tiles into frequency tiles; SHIFTS: it counts what the chain warp's tiles shift out
+// and writes the byte counts and the sizes.  One helper warp does both (k_enc_ranges2<2>), or one each (<3>).
+template <bool FREQS, bool SHIFTS>
+__device__ __forceinline__ void ranges2_helper(const SegArgs& a, u32 tiles, u32 fbuf, u32 tbuf, const RangesWarp& w)
+{
+    // With two helper warps the one that counts the shifts has time to spare: it also fetches the input tiles
+    // (cp.async) and waits for them, so that the warp that converts them never waits for DRAM: a tile is
+    // confirmed one barrier before it is converted.
+    constexpr bool STAGES = SHIFTS;
+    constexpr bool LEAD = FREQS && SHIFTS ? 0 : 1;  // barriers between "tile has arrived" and its conversion
+    const u32 lane = w.lane;
+    const u32 ntiles = (w.n_max + TILE - 1) / TILE;
+    const u32 seg_tiles = a.P / TILE;
+    u32 next_mark = 0, bits = 0;
+    constexpr u32 R = ENC_RANGES2_SRC;
+    if(STAGES) {
+        // tile 0 was staged by the chain warp and is complete (the barrier in the kernel); tiles 1 .. R - 1 go out now
+        for(u32 k = 1; k < R; ++k) {
+            if(k < ntiles) {
+                stage_tile(tiles + k * TILE_BYTES, a.src, a.n, w.b0, a.block, k * TILE, lane);
+            }
+            cp_async_commit();
+        }
+        if(LEAD) {
+            cp_async_wait<R - 2>();  // tile 1, for the other helper's first trip
+            __syncwarp();
+        }
+    }
+    if(FREQS) {
+        ranges2_freqs(tiles + lane * ROW, w.ftab, fbuf + lane * 8u);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for(u32 tix = 0; tix < ntiles; ++tix) {
+        if(STAGES && !LEAD && tix + 1 < ntiles) {
+            cp_async_wait<R - 2>();  // all but the newest R - 2 groups: tile tix + 1 has arrived
+            __syncwarp();
+        }
+        if(FREQS && tix + 1 < ntiles) {  // frequencies of the tile the chain warp walks next
+            ranges2_freqs(tiles + ((tix + 1) % R) * TILE_BYTES + lane * ROW, w.ftab,
+                          fbuf + ((tix + 1) & 1u) * ENC_RANGES2_F + lane * 8u);
+            __syncwarp();
+        }
+        if(STAGES) {
+            // tile tix + R - LEAD goes into the buffer of tile tix - LEAD, which was converted an iteration ago
+            if(tix + 1u > (u32)LEAD && tix + R - LEAD < ntiles) {
+                stage_tile(tiles + ((tix - LEAD) % R) * TILE_BYTES, a.src, a.n, w.b0, a.block, (tix + R - LEAD) * TILE, lane);
+            }
+            cp_async_commit();
+            if(LEAD && tix + 2 < ntiles) {
+                cp_async_wait<R - 3>();  // tile tix + 2 has arrived: the other helper converts it after the barrier
+                __syncwarp();
+            }
+        }
+        if(SHIFTS) {
+            if(tix >= 1) {  // what the tile the chain warp just left shifted out
+                bits += ranges2_shifts(tbuf + ((tix - 1) & 1u) * ENC_RANGES2_T + lane * 4u);
+            }
+            if(tix == next_mark) {
+                next_mark += seg_tiles;
+                if(tix * TILE < w.n_b) {
+                    w.rec[2u * (tix / seg_tiles)] = bits >> 3;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if(SHIFTS) {
+        if(ntiles) {
+            bits += ranges2_shifts(tbuf + ((ntiles - 1) & 1u) * ENC_RANGES2_T + lane * 4u);
+        }
+        if(w.n_b) {
+            const u32 nseg_b = (w.n_b + a.P - 1u) / a.P;
+            w.rec[2u * nseg_b] = bits >> 3;
+            w.rec[2u * nseg_b + 1u] = 0u;
+            a.sizes[w.b] = RC_STATIC_HDR + 5u + (bits >> 3);  // cpprcoder.h:386-395 header, buffer_, shifted bytes, low
+        }
+    }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_enc_ranges2(SegArgs a)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    const u32 sbase = smem_addr(smem);
+    const u32 tiles = sbase + 256u * 32u * 2u;
+    const u32 fbuf = tiles + ENC_RANGES2_SRC * TILE_BYTES;
+    const u32 tbuf = fbuf + 2u * ENC_RANGES2_F;
+    volatile u32* flag = reinterpret_cast<volatile u32*>(smem + 256u * 32u * 2u + ENC_RANGES2_SRC * TILE_BYTES +
+                                                         2u * ENC_RANGES2_F + 2u * ENC_RANGES2_T);
+    const u32 warp = threadIdx.x >> 5;
+    RangesWarp w;
+    if(warp == 0) {
+        ranges_prepare(a, smem, sbase, tiles, w);
+        const bool all16 = __all_sync(FULL, w.total == 65536u || !w.has);
+        cp_async_wait<0>();  // tile 0: the other warp reads it first
+        if(w.lane == 0) {
+            flag[0] = all16 ? 1u : 0u;
+            flag[1] = w.n_max;
+            flag[2] = w.ragged ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    const bool two = flag[0] != 0u;
+    if(!two) {
+        if(warp == 0) {
+            ranges_one_warp<false>(a, tiles, w);
+        }
+        return;
+    }
+    if(warp == 0) {
+        if(w.ragged) {
+            ranges2_chain<true>(a, fbuf, tbuf, w);
+        } else {
+            ranges2_chain<false>(a, fbuf, tbuf, w);
+        }
+    } else {
+        w.lane = lane_id();
+        w.b0 = (u64)blockIdx.x * 32u;
+        w.b = w.b0 + w.lane;
+        w.has = w.b < a.nblocks;
+        w.n_b = w.has ? seg_block_len(a, w.b) : 0u;
+        w.n_max = flag[1];
+        w.ragged = flag[2] != 0u;
+        w.total = 0;
+        w.rec = a.recs + (w.has ? w.b : w.b0) * (u64)(a.nseg + 1u) * 2u;
+        w.ftab = sbase + w.lane * 2u;
+        if(WARPS == 2) {
+            ranges2_helper<true, true>(a, tiles, fbuf, tbuf, w);
+        } else if(warp == 1) {
+            ranges2_helper<true, false>(a, tiles, fbuf, tbuf, w);
+        } else {
+            ranges2_helper<false, true>(a, tiles, fbuf, tbuf, w);
+        }
     }
 }
 

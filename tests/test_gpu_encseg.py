@@ -74,6 +74,33 @@ def test_segments_give_the_reference_payloads(oracle, one_chain, P, block, nbloc
         ctx.close()
 
 
+def test_range_pass_with_one_two_three_warps_writes_the_same_container(oracle):
+    """k_enc_ranges (one warp per 32 blocks) and k_enc_ranges2<2>, <3> (a chain warp and one or two helper warps,
+    the form small streams of 64 KiB blocks take): same containers byte for byte, payloads the reference's.  The
+    streams hold blocks of one repeated byte (total 0x8000: that CTA falls back to the one-warp path), a ragged
+    last block, a last warp with missing lanes, and restart spacings from 1024 to 8192."""
+    import torch
+    streams = [crafted_stream(37, 65536, seed=91, ragged=4321), synth.zipf(70 * 65536), synth.mixed(64 * 65536),
+               synth.kennedy(33 * 65536 + 1), np.concatenate([synth.zipf(3 * 65536), np.zeros(65536, np.uint8)] * 9)]
+    ctxs = {w: make_ctx(B2RC_RANGES_WARPS=w) for w in (1, 2, 3)}
+    try:
+        for k, data in enumerate(streams):
+            want = oracle.encode_blocks(STATIC, data, 65536, threads=4)
+            for spacing in (0, 8192):
+                got = {}
+                for w, ctx in ctxs.items():
+                    ctx.force_restart(spacing)
+                    enc, used = ctx.encode_device(STATIC, torch.from_numpy(data).cuda(), block=65536)
+                    got[w] = enc[:used].cpu().numpy()
+                    assert payloads(got[w]) == want, (k, spacing, w)
+                    assert ctx.encode(STATIC, data, 65536).tobytes() == got[w].tobytes(), (k, spacing, w)
+                assert got[1].tobytes() == got[2].tobytes() == got[3].tobytes(), (k, spacing)
+                assert ctxs[3].decode(got[3]).tobytes() == data.tobytes()
+    finally:
+        for ctx in ctxs.values():
+            ctx.close()
+
+
 def test_every_alignment_of_the_payloads(oracle):
     """Payload offsets take every residue mod 4 (sizes are data dependent); a canary behind the
     container stays intact and the bound is respected."""
