@@ -92,8 +92,8 @@ def config_of(args, world):
         "global_bytes": nbytes * world,
         "parallelism": f"blocks sharded by contiguous range over {world} GPU(s)",
         "l2": "inputs (1 GiB per GPU) are larger than the 126 MB L2; no explicit flush",
-        "restart_points": ("every 8192 symbols for a stream that fills the GPU at that spacing, as 1 GiB per GPU does "
-                           "(static coder: 84 B per 64 KiB block behind the payloads, counted in compressed_ratio; the "
+        "restart_points": ("every 4096 symbols for a stream that fills the GPU at that spacing, as 1 GiB per GPU does "
+                           "(static coder: 180 B per 64 KiB block behind the payloads, counted in compressed_ratio; the "
                            "payloads are the reference's); closer together for fewer blocks (b2rc_restart_for)") if mode == 0
                           else ("adaptive coder: every 21888 symbols, 524 B a point with the model's counts, counted in "
                                 "compressed_ratio" if mode == 1 else "none"),

@@ -63,7 +63,9 @@ struct b2rc_ctx {
     u64* h_ends;  // pinned
     u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
     u64 max_phases;  // <= B2RC_PHASES; env B2RC_PHASES overrides (1 switches the phased decode off)
-    u32 seg_syms;    // restart points of the static coder every so many symbols; env B2RC_RESTART_SYMS (0: none)
+    u32 seg_syms;    // restart points of the byte rANS coder every so many symbols; env B2RC_RESTART_SYMS (0: none)
+    u32 seg_syms_static;  // ... of the static range coder (the same env sets both)
+    u32 dec_seg_warps;  // env B2RC_DEC_SEG_WARPS: warps (= segments) per CTA of k_dec_static_seg, 1 .. 12 (tuning)
     u32 ranges_warps;  // env B2RC_RANGES_WARPS: 1 = k_enc_ranges for 64 KiB blocks too, 2 / 3 = k_enc_ranges2, unset = by size
     u32 seg_auto;    // no env setting: streams of few blocks get more points per block (seg_for)
     u32 seg_force;   // b2rc_ctx_force_restart: this spacing whatever the stream (0: not forced)
@@ -203,10 +205,10 @@ u32 seg_for(const b2rc_ctx* ctx, int mode, u32 block_size, u64 nblocks)
     if(ctx->seg_force) {
         return seg_ok(block_size, ctx->seg_force) ? ctx->seg_force : 0u;
     }
-    if(!seg_ok(block_size, ctx->seg_syms)) {
+    u32 seg = mode == B2RC_MODE_STATIC ? ctx->seg_syms_static : ctx->seg_syms;
+    if(!seg_ok(block_size, seg)) {
         return 0u;
     }
-    u32 seg = ctx->seg_syms;
     if(ctx->seg_auto) {
         const u64 groups = (nblocks + 31u) / 32u;
         while(seg / 2u >= B2RC_MIN_RESTART_SYMS && (seg / 2u) % 64u == 0u &&
@@ -268,8 +270,8 @@ int set_smem_limits(b2rc_ctx* ctx)
     CK(cudaFuncSetAttribute(k_dec_adaptive_seg<Leafless>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_ADAPT_SEG_SMEM));
     CK(cudaFuncSetAttribute(k_dec_adaptive_seg<LeaflessW>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_ADAPT_SEG_SMEM_WIDE));
     CK(cudaFuncSetAttribute(k_enc_adaptive2, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_AD2_SMEM));
-    CK(cudaFuncSetAttribute(k_dec_static_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(true)));
-    CK(cudaFuncSetAttribute(k_dec_static_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(false)));
+    CK(cudaFuncSetAttribute(k_dec_static_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(true, SEG_WARPS_MAX)));
+    CK(cudaFuncSetAttribute(k_dec_static_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_seg_smem(false, SEG_WARPS_MAX)));
     CK(cudaFuncSetAttribute(k_enc_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(false, ENC_SEG_WARPS)));
     CK(cudaFuncSetAttribute(k_enc_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_seg_smem(true, ENC_SEG_WARPS)));
     CK(cudaFuncSetAttribute(k_ans_dec_byte_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, ANS_DEC_BYTE_SEG_SMEM));
@@ -469,11 +471,13 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
     }
     ctx->max_phases = 4;  // measured on B200: 4 and 8 launches per chunk time the same
     ctx->seg_syms = B2RC_DEFAULT_RESTART_SYMS;
+    ctx->seg_syms_static = B2RC_DEFAULT_STATIC_RESTART_SYMS;
     ctx->seg_auto = 1;
     if(const char* e = getenv("B2RC_RESTART_SYMS")) {
         const long v = atol(e);
         if(v == 0 || (v >= (long)B2RC_MIN_RESTART_SYMS && v <= (1 << 22) && v % 64 == 0)) {
             ctx->seg_syms = (u32)v;
+            ctx->seg_syms_static = (u32)v;
             ctx->seg_auto = 0;  // an explicit spacing is kept for every stream
         }
     }
@@ -486,6 +490,10 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
     }
     if(const char* e = getenv("B2RC_FORCE_EXACT")) {
         ctx->force_exact = atol(e) ? 1u : 0u;
+    }
+    if(const char* e = getenv("B2RC_DEC_SEG_WARPS")) {
+        const long v = atol(e);
+        ctx->dec_seg_warps = (v >= 1 && v <= (long)SEG_WARPS_MAX) ? (u32)v : 0u;
     }
     ctx->ranges_warps = 0;  // by the size of the call (static_ranges_launch)
     if(const char* e = getenv("B2RC_RANGES_WARPS")) {
@@ -1068,11 +1076,15 @@ int b2rc_k_decode_blocks_r(b2rc_ctx* ctx, int mode, uint32_t block_size, const u
         k_ans_dec_byte_seg<<<agrid, 32 * ANS_SEG_WARPS, ANS_DEC_BYTE_SEG_SMEM, st>>>(a);
         return launch_check(ctx, "k_ans_dec_byte_seg");
     }
-    const dim3 grid((unsigned)((nblocks + 31) / 32), (nseg + SEG_WARPS - 1u) / SEG_WARPS);
+    // sixteen or more segments per block: CTAs of eight warps (one table per eight chains, 32 warps per SM instead
+    // of 28); the eight segments of the older spacing stay two CTAs of four (eight in one leave some SMs with 24
+    // warps and others with 32: 4.40 against 4.04 ms)
+    const u32 warps = ctx->dec_seg_warps ? ctx->dec_seg_warps : (nseg >= 16u ? 8u : (nseg < SEG_WARPS ? nseg : SEG_WARPS));
+    const dim3 grid((unsigned)((nblocks + 31) / 32), (nseg + warps - 1u) / warps);
     if(block_size <= 65536u) {
-        k_dec_static_seg<true><<<grid, 32 * SEG_WARPS, dec_seg_smem(true), st>>>(a);
+        k_dec_static_seg<true><<<grid, 32 * warps, dec_seg_smem(true, warps), st>>>(a);
     } else {
-        k_dec_static_seg<false><<<grid, 32 * SEG_WARPS, dec_seg_smem(false), st>>>(a);
+        k_dec_static_seg<false><<<grid, 32 * warps, dec_seg_smem(false, warps), st>>>(a);
     }
     return launch_check(ctx, "k_dec_static_seg");
 }

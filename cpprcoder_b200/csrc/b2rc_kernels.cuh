@@ -1198,19 +1198,20 @@ __global__ void __launch_bounds__(32) k_dec_static(DecArgs a)
 // Mapping: a CTA of SEG_WARPS warps takes 32 blocks; lane = block as everywhere, WARP = segment,
 // so the cumulative tables of the 32 blocks are built once and shared by the CTA with the usual
 // bank == lane layout.  blockIdx.y walks groups of SEG_WARPS segments for long blocks.
-constexpr u32 SEG_WARPS = 4;
+constexpr u32 SEG_WARPS = 4;       // the default CTA; the launch may take any count up to SEG_WARPS_MAX (blockDim.x / 32)
+constexpr u32 SEG_WARPS_MAX = 12;
 // NARROW: blocks <= 65536 bytes, u16 table (CumTab16); else the u32 table of k_dec_static.
 constexpr u32 dec_seg_tab(bool narrow)
 {
     return 257u * 32u * (narrow ? 2u : 4u);
 }
-constexpr u32 dec_seg_smem(bool narrow)
+constexpr u32 dec_seg_smem(bool narrow, u32 warps = SEG_WARPS)
 {
-    return dec_seg_tab(narrow) + 3u * 128u + SEG_WARPS * (TILE_BYTES + INQ_BYTES);
+    return dec_seg_tab(narrow) + 3u * 128u + warps * (TILE_BYTES + INQ_BYTES);
 }
 
 template <bool NARROW>
-__global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
+__global__ void __launch_bounds__(32 * SEG_WARPS_MAX, 3) k_dec_static_seg(DecArgs a)
 {
     extern __shared__ __align__(16) u8 smem[];
     constexpr u32 DEC_SEG_TAB = dec_seg_tab(NARROW);
@@ -1234,7 +1235,7 @@ __global__ void __launch_bounds__(32 * SEG_WARPS) k_dec_static_seg(DecArgs a)
         n_b = (u32)((a.n - lo < a.block) ? (a.n - lo) : a.block);
     }
     const u32 nseg = (a.block + a.seg_syms - 1u) / a.seg_syms;
-    const u32 seg = blockIdx.y * SEG_WARPS + warp;
+    const u32 seg = blockIdx.y * (blockDim.x >> 5) + warp;
 
     // where this lane's payload is; every warp needs that, warp 0 also reports a bad one
     const u8* pay = a.payload;

@@ -338,7 +338,7 @@ def spacing(ctx, request):
 @pytest.mark.parametrize("gen,block,extra", [("zipf", 65536, 0), ("kennedy", 65536, 4097), ("mixed", 16384, 77),
                                              ("kennedy", 262144, 100000)])
 def test_static_container_carries_restart_points(ctx, oracle, built, gen, block, extra, spacing):
-    """The static coder's containers end in a table of restart points (one per 8192 symbols, closer together
+    """The static coder's containers end in a table of restart points (one per 4096 symbols, closer together
     for a stream of few blocks): the payloads are still the reference's, the records are what the lane code
     computes on the CPU, and the decoder -- which now runs a chain per segment -- gives the input back."""
     n = 20 * block + extra
@@ -379,17 +379,20 @@ def test_static_container_carries_restart_points(ctx, oracle, built, gen, block,
 
 
 def test_restart_spacing_follows_the_number_of_blocks(ctx):
-    """b2rc_restart_for: 8192 symbols for a stream that fills the GPU at that spacing (1 GiB of 64 KiB blocks),
-    halved until ceil(nblocks / 32) x segments reaches 4096 warps, not below 1024; a forced spacing wins."""
-    assert ctx.restart_for(STATIC, 65536, 16384) == 8192
+    """b2rc_restart_for: the coder's default spacing (static 4096, byte rANS 8192 symbols) for a stream that gives
+    the decoder 4096 warps at that spacing, else halved until ceil(nblocks / 32) x segments reaches 4096 warps, not
+    below 1024; a forced spacing wins."""
+    assert ctx.restart_for(STATIC, 65536, 16384) == 4096          # the static coder's default: sixteen chains per block
     assert ctx.restart_for(STATIC, 65536, 8192) == 4096
     assert ctx.restart_for(STATIC, 65536, 4096) == 2048
     assert ctx.restart_for(STATIC, 65536, 2048) == 1024
     assert ctx.restart_for(STATIC, 65536, 1) == 1024
-    assert ctx.restart_for(STATIC, 1 << 20, 1024) == 8192       # 1 GiB of 1 MiB blocks: 32 x 128 warps
+    assert ctx.restart_for(STATIC, 1 << 20, 1024) == 4096         # 1 GiB of 1 MiB blocks: 32 x 256 warps
     assert ctx.restart_for(STATIC, 1 << 20, 64) == 1024
+    assert ctx.restart_for(RANS_BYTE, 65536, 16384) == 8192       # the byte rANS coder's default
     assert ctx.restart_for(RANS_BYTE, 65536, 2048) == 1024
-    assert ctx.restart_for(STATIC, 4096, 1 << 18) == 0           # blocks no longer than the spacing: no table
+    assert ctx.restart_for(STATIC, 4096, 1 << 18) == 0            # blocks no longer than the spacing: no table
+    assert ctx.restart_for(STATIC, 8192, 1 << 17) == 4096
     assert ctx.restart_for(ADAPTIVE, 65536, 5) == 21888          # the adaptive coder's points carry the model: fixed
     assert ctx.restart_for(RANS_WORD, 65536, 5) == 0
     ctx.force_restart(4096)
