@@ -62,6 +62,7 @@ struct b2rc_ctx {
     u64* d_ends;  // B2RC_PIPE_CHUNKS + 1
     u64* h_ends;  // pinned
     u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
+    u32 ramp_chunks; // shorter chunks at both ends of the host pipeline (plan_chunks); env B2RC_PIPE_RAMP=0: equal chunks
     u64 max_phases;  // <= B2RC_PHASES; env B2RC_PHASES overrides (1 switches the phased decode off)
     u32 seg_syms;    // restart points of the byte rANS coder every so many symbols; env B2RC_RESTART_SYMS (0: none)
     u32 seg_syms_static;  // ... of the static range coder (the same env sets both)
@@ -462,6 +463,10 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         if(conn < B2RC_PIPE_CHUNKS + 2) {
             ctx->max_chunks = conn > 4 ? (u64)(conn - 2) : 2;
         }
+    }
+    ctx->ramp_chunks = 1;
+    if(const char* e = getenv("B2RC_PIPE_RAMP")) {
+        ctx->ramp_chunks = atol(e) ? 1u : 0u;
     }
     if(const char* e = getenv("B2RC_PIPE_CHUNKS")) {
         const long v = atol(e);
@@ -1407,10 +1412,15 @@ int b2rc_decode_device(b2rc_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t*
 namespace
 {
 struct Chunks {
-    u64 nb, per, count;
-    u64 lo(u64 c) const { return c * per < nb ? c * per : nb; }
-    u64 hi(u64 c) const { return (c + 1) * per < nb ? (c + 1) * per : nb; }
+    u64 nb, count;
+    u64 bnd[B2RC_PIPE_CHUNKS + 1];  // chunk c = blocks [bnd[c], bnd[c + 1])
+    u64 lo(u64 c) const { return bnd[c]; }
+    u64 hi(u64 c) const { return bnd[c + 1]; }
 };
+// The pipeline's time is the longer direction's copies plus what cannot overlap them: the first chunk's way in and
+// its kernels (decode: the copies home are the longer direction) and the last chunk's way home (encode: the
+// copies in are).  So the chunks at both ends are shorter, growing by about 1.4 a step -- the next chunk in has to
+// be there when the previous one has gone home, or the wire idles.
 Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block)
 {
     Chunks ch;
@@ -1422,13 +1432,30 @@ Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block)
     if(count < 1) {
         count = 1;
     }
-    u64 per = (ch.nb + count - 1) / count;
-    per = (per + 31) & ~31ull;  // whole warps of blocks
-    if(per == 0) {
-        per = 32;
+    const u64 units = (ch.nb + 31) / 32;  // whole warps of blocks
+    if(count > units) {
+        count = units;
     }
-    ch.per = per;
-    ch.count = ch.nb ? (ch.nb + per - 1) / per : 0;
+    static const u32 ramp[3] = {35, 50, 70};  // per cent of a middle chunk
+    u32 w[B2RC_PIPE_CHUNKS];
+    u64 wsum = 0;
+    for(u64 c = 0; c < count; ++c) {
+        const u64 edge = c < count - 1 - c ? c : count - 1 - c;
+        w[c] = (count >= 8 && edge < 3 && ctx->ramp_chunks) ? ramp[edge] : 100u;
+        wsum += w[c];
+    }
+    u64 acc = 0, at = 0;
+    ch.bnd[0] = 0;
+    ch.count = 0;
+    for(u64 c = 0; c < count; ++c) {
+        acc += w[c];
+        u64 end = c + 1 == count ? units : (units * acc + wsum / 2) / wsum;
+        if(end <= at) {
+            continue;  // rounding left nothing for this one
+        }
+        at = end;
+        ch.bnd[++ch.count] = at * 32 < ch.nb ? at * 32 : ch.nb;
+    }
     return ch;
 }
 }  // namespace
