@@ -1538,7 +1538,9 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         if(P) {  // sizes first (the range pass), the payloads then go straight to their final place
             sa = seg_args(ctx, block_size, P, ctx->stage_in + byte0, bytes, freq, b0, ctx->sizes + b0, d_offsets + b0,
                           d_payload, bound - idx, seg ? ctx->restart + b0 * nrec * rw : nullptr, seg);
-            if((rc = static_ranges_launch(ctx, sa, nb, st)) != B2RC_OK) {
+            // the chunks arrive as fast as the wire brings them: one or two are being coded at any time, the GPU is
+            // mostly idle, and the range pass may take its helper warps (its latency is the pipeline's drain)
+            if((rc = static_ranges_launch(ctx, sa, 2 * (b1 - b0), st)) != B2RC_OK) {
                 return rc;
             }
         } else if((rc = b2rc_k_encode_blocks_r(ctx, mode, block_size, ctx->stage_in + byte0, bytes, freq,
