@@ -10,6 +10,7 @@
 #include <cstring>
 #include <algorithm>
 #include <new>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -1421,6 +1422,9 @@ struct Chunks {
 // its kernels (decode: the copies home are the longer direction) and the last chunk's way home (encode: the
 // copies in are).  So the chunks at both ends are shorter, growing by about 1.4 a step -- the next chunk in has to
 // be there when the previous one has gone home, or the wire idles.
+// (Cutting b2rc_encode's input into 32 chunks instead of 16 was tried -- copies alone in the pipeline's shape get
+// faster with more chunks one way (1 GiB in, 0.79 GiB home: 23.5 / 22.5 / 21.8 ms for 16 / 32 / 64) and slower the
+// other (23.8 / 24.1 / 24.8), tools/e2e_phases.py -- and changed nothing once the kernels sit between the copies.)
 Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block)
 {
     Chunks ch;
@@ -1458,6 +1462,72 @@ Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block)
     }
     return ch;
 }
+}  // namespace
+
+// B2RC_TRACE=1: a timeline of one b2rc_encode / b2rc_decode on stderr (device times by events against the call's
+// first event, host times by the steady clock) -- tuning aid for the pipeline, off the product path otherwise.
+namespace
+{
+struct PipeTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr, a[B2RC_PIPE_CHUNKS] = {}, b[B2RC_PIPE_CHUNKS] = {}, c[B2RC_PIPE_CHUNKS] = {};
+    std::chrono::steady_clock::time_point h0;
+    double host[B2RC_PIPE_CHUNKS + 3] = {};
+    explicit PipeTrace(cudaStream_t s0)
+    {
+        const char* e = getenv("B2RC_TRACE");
+        on = e && atol(e) != 0;
+        if(on) {
+            cudaEventCreate(&t0);
+            for(int k = 0; k < B2RC_PIPE_CHUNKS; ++k) {
+                cudaEventCreate(&a[k]);
+                cudaEventCreate(&b[k]);
+                cudaEventCreate(&c[k]);
+            }
+            h0 = std::chrono::steady_clock::now();
+            cudaEventRecord(t0, s0);
+        }
+    }
+    void rec(cudaEvent_t* ev, u64 k, cudaStream_t st)
+    {
+        if(on) {
+            cudaEventRecord(ev[k], st);
+        }
+    }
+    void mark(u64 k)
+    {
+        if(on) {
+            host[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+        }
+    }
+    void print(const char* what, u64 count, const char* la, const char* lb, const char* lc)
+    {
+        if(!on) {
+            return;
+        }
+        fprintf(stderr, "[b2rc trace] %s: enqueued at %.3f ms (host), done at %.3f ms (host)\n", what, host[B2RC_PIPE_CHUNKS],
+                host[B2RC_PIPE_CHUNKS + 1]);
+        for(u64 k = 0; k < count; ++k) {
+            float x = -1, y = -1, z = -1;
+            cudaEventElapsedTime(&x, t0, a[k]);
+            cudaEventElapsedTime(&y, t0, b[k]);
+            cudaEventElapsedTime(&z, t0, c[k]);
+            fprintf(stderr, "[b2rc trace]   chunk %2llu: %s %.3f  %s %.3f  %s %.3f  host saw it at %.3f\n", (unsigned long long)k,
+                    la, x, lb, y, lc, z, host[k]);
+        }
+    }
+    ~PipeTrace()
+    {
+        if(on) {
+            cudaEventDestroy(t0);
+            for(int k = 0; k < B2RC_PIPE_CHUNKS; ++k) {
+                cudaEventDestroy(a[k]);
+                cudaEventDestroy(b[k]);
+                cudaEventDestroy(c[k]);
+            }
+        }
+    }
+};
 }  // namespace
 
 static int multi_encode(b2rc_ctx* ctx, int mode, u32 block_size, const u8* src, u64 n, u8* dst, u64 dst_cap, u64* out_n);
@@ -1517,6 +1587,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         CK(cudaMemsetAsync(d_offsets, 0, 8, s0));
     }
     CK(cudaEventRecord(ctx->index_ready, s0));
+    PipeTrace tr(s0);
     // enqueue every chunk
     for(u64 c = 0; c < ch.count; ++c) {
         cudaStream_t st = ctx->pipe[c % B2RC_PIPE_STREAMS];
@@ -1530,6 +1601,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
             b2rc_host_copy(ctx->h_in + byte0, src + byte0, bytes);  // chunk c-1 is on the wire meanwhile
         }
         CK(cudaMemcpyAsync(ctx->stage_in + byte0, (stage_src ? ctx->h_in : src) + byte0, bytes, cudaMemcpyHostToDevice, st));
+        tr.rec(tr.a, c, st);
         u16* freq = need_hist ? ctx->freq16 + b0 * 256 : nullptr;
         if(need_hist && (rc = b2rc_k_histogram(ctx, ctx->stage_in + byte0, bytes, block_size, freq, st)) != B2RC_OK) {
             return rc;
@@ -1566,14 +1638,17 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         if(rc != B2RC_OK) {
             return rc;
         }
+        tr.rec(tr.b, c, st);
         CK(cudaMemcpyAsync(ctx->h_ends + c + 1, ctx->d_ends + c + 1, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ctx->chunk_done[c], st));
     }
+    tr.mark(B2RC_PIPE_CHUNKS);
     // drain: as each chunk's size becomes known, send its payload home on the chunk's own stream
     ctx->h_ends[0] = 0;
     int result = B2RC_OK;
     for(u64 c = 0; c < ch.count; ++c) {
         CK(cudaEventSynchronize(ctx->chunk_done[c]));
+        tr.mark(c);
         const u64 lo = ctx->h_ends[c], hi = ctx->h_ends[c + 1];
         if(idx + hi > dst_cap) {
             result = B2RC_E_DST_SMALL;
@@ -1583,6 +1658,7 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
             // on the context's own stream: the chunk's stream still has later chunks queued
             CK(cudaMemcpyAsync(dst + idx + lo, d_payload + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->stream));
         }
+        tr.rec(tr.c, c, ctx->stream);
     }
     const u64 total = ch.count ? ctx->h_ends[ch.count] : 0;
     const u64 table_bytes = (u64)nb * nrec * 4ull * rw;
@@ -1611,6 +1687,8 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
         CK(cudaStreamSynchronize(ctx->pipe[k]));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    tr.mark(B2RC_PIPE_CHUNKS + 1);
+    tr.print("b2rc_encode", ch.count, "in", "coded", "home");
     const int kerr = map_kernel_err(ctx->h_res->err);
     return kerr != B2RC_OK ? kerr : result;
 }
@@ -1695,6 +1773,7 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
         CK(cudaMemcpyAsync(ctx->restart, src + idx + align4(prev), table_bytes, cudaMemcpyHostToDevice, s0));
     }
     CK(cudaEventRecord(ctx->index_ready, s0));
+    PipeTrace tr(s0);
     for(u64 c = 0; c < ch.count; ++c) {
         cudaStream_t st = ctx->pipe[c % B2RC_PIPE_STREAMS];
         const u64 b0 = ch.lo(c), b1 = ch.hi(c);
@@ -1713,13 +1792,16 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
             CK(cudaMemcpyAsync(ctx->stage_in + idx + p0, (stage_src ? ctx->h_in : src) + idx + p0, p1 - p0,
                                cudaMemcpyHostToDevice, st));
         }
+        tr.rec(tr.a, c, st);
         if(phases <= 1) {
             if((rc = b2rc_k_decode_blocks_r(ctx, mode, block, ctx->stage_in + idx, payload_len, d_offsets + b0, b1 - b0,
                                             ctx->stage_out + byte0, bytes, seg ? ctx->restart + b0 * nrec * rw : nullptr,
                                             seg, ctx->d_err, st)) != B2RC_OK) {
                 return rc;
             }
+            tr.rec(tr.b, c, st);
             CK(cudaMemcpyAsync(dst + byte0, ctx->stage_out + byte0, bytes, cudaMemcpyDeviceToHost, st));
+            tr.rec(tr.c, c, st);
             continue;
         }
         // Phased: a launch decodes the next `per` symbols of every block of the chunk, and that
@@ -1761,6 +1843,10 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
     }
     CK(cudaMemcpyAsync(&ctx->h_res->err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, s0));
     CK(cudaStreamSynchronize(s0));
+    tr.mark(B2RC_PIPE_CHUNKS + 1);
+    if(phases <= 1) {
+        tr.print("b2rc_decode", ch.count, "in", "decoded", "home");
+    }
     return map_kernel_err(ctx->h_res->err);
 }
 
