@@ -6,6 +6,7 @@
 #include "../../cpprcoder_b200/csrc/ans_lane.cuh"
 
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 namespace
@@ -591,6 +592,28 @@ long sim_ans_byte_decode(const u8* stream, size_t stream_len, u32 lead, u8* dst,
         }
     }
     return (long)want;
+}
+
+// The range chain for total == 65536 as the range-pass kernels compute it (b2rc_encseg.cuh), for one frequency and
+// EVERY t in [2^8, 2^16), against the plain form of the link (rc_range_step_pow2): the next t as the minimum of three
+// wrapped candidates (range_step16), the same with the chain carrying t - 256 and the addends 256 f - K prepared
+// beside it (ranges2_chain), and the shift read off r - 256 afterwards (ranges2_shifts).  Returns the mismatches.
+u64 sim_check_range16(u32 f)
+{
+    u64 bad = 0;
+    for(u32 t = 256u; t < 65536u; ++t) {
+        u32 want = t;
+        const u32 want_sh = rc_range_step_pow2<2>(want, 16u, f);
+        const u32 r = f * t;
+        const u32 a = (r - 0x01000000u) >> 16, b = (r - 0x00010000u) >> 8, c = r - 0x00000100u;
+        const u32 t1 = std::min(std::min(a, b), c) + 256u;
+        const u32 m = t - 256u, c3 = f * 256u - 256u;
+        const u32 r1 = f * m + (c3 - 0x00FFFF00u), r2 = f * m + (c3 - 0x0000FF00u), r3 = f * m + c3;
+        const u32 m1 = std::min(std::min(r1 >> 16, r2 >> 8), r3);
+        const u32 sh2 = rc_clz(r3 + 256u) & 24u;
+        bad += (t1 != want ? 1u : 0u) + (m1 + 256u != want ? 1u : 0u) + (sh2 != want_sh ? 1u : 0u) + (r3 != c ? 1u : 0u);
+    }
+    return bad;
 }
 
 // exhaustive-ish check of the magic division; returns the number of mismatches

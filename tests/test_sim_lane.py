@@ -52,6 +52,16 @@ def test_magic_division_is_exact(sim):
     assert bad == 0
 
 
+def test_range_chain_for_total_65536_is_exact(sim):
+    """The three-candidate minimum of the range-pass kernels (k_enc_ranges, k_enc_ranges2): every t in [2^8, 2^16)
+    for some 310 frequencies (the edges and random ones) -- 20 million links, all equal to the plain form."""
+    sim.sim_check_range16.restype = C.c_uint64
+    sim.sim_check_range16.argtypes = [C.c_uint32]
+    rng = np.random.default_rng(16)
+    fs = sorted({1, 2, 3, 255, 256, 257, 4095, 4096, 32767, 32768, 65534, 65535} | set(int(x) for x in rng.integers(1, 65536, 300)))
+    assert sum(sim.sim_check_range16(f) for f in fs) == 0
+
+
 def test_lane_coder_matches_oracle_on_crafted_blocks(sim):
     o = Oracle.get()
     rng = np.random.default_rng(7)
