@@ -63,6 +63,7 @@ struct b2rc_ctx {
     u64* d_ends;  // B2RC_PIPE_CHUNKS + 1
     u64* h_ends;  // pinned
     u64 max_chunks;  // <= B2RC_PIPE_CHUNKS; env B2RC_PIPE_CHUNKS overrides (tuning)
+    u64 min_chunk;   // bytes of input per chunk, at least (B2RC_PIPE_MIN_CHUNK; env B2RC_PIPE_MIN_CHUNK: tests cut small streams)
     u32 ramp_chunks; // shorter chunks at both ends of the host pipeline (plan_chunks); env B2RC_PIPE_RAMP=0: equal chunks
     u64 max_phases;  // <= B2RC_PHASES; env B2RC_PHASES overrides (1 switches the phased decode off)
     u32 seg_syms;    // restart points of the byte rANS coder every so many symbols; env B2RC_RESTART_SYMS (0: none)
@@ -463,6 +464,13 @@ int b2rc_ctx_create(int device, b2rc_ctx** out)
         }
         if(conn < B2RC_PIPE_CHUNKS + 2) {
             ctx->max_chunks = conn > 4 ? (u64)(conn - 2) : 2;
+        }
+    }
+    ctx->min_chunk = B2RC_PIPE_MIN_CHUNK;
+    if(const char* e = getenv("B2RC_PIPE_MIN_CHUNK")) {
+        const long long v = atoll(e);
+        if(v >= 65536) {
+            ctx->min_chunk = (u64)v;
         }
     }
     ctx->ramp_chunks = 1;
@@ -1429,7 +1437,7 @@ Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block)
 {
     Chunks ch;
     ch.nb = b2rc_nblocks(n, block);
-    u64 count = n / B2RC_PIPE_MIN_CHUNK;
+    u64 count = n / ctx->min_chunk;
     if(count > ctx->max_chunks) {
         count = ctx->max_chunks;
     }

@@ -101,6 +101,31 @@ def test_range_pass_with_one_two_three_warps_writes_the_same_container(oracle):
             ctx.close()
 
 
+@pytest.mark.parametrize("mode_name", ["static", "adaptive", "rans", "rans-word"])
+def test_host_pipeline_with_many_uneven_chunks(oracle, mode_name):
+    """b2rc_encode / b2rc_decode cut a stream into up to 16 chunks, shorter at both ends (plan_chunks).  With the
+    smallest chunk size a test may ask for, a 40 MiB stream goes through the same plan a 1 GiB stream gets: the
+    container must be the device call's, byte for byte, with equal chunks, with uneven ones and with one chunk."""
+    import torch
+    mode = {"static": 0, "adaptive": 1, "rans": 2, "rans-word": 3}[mode_name]
+    data = np.concatenate([synth.zipf(23 * (1 << 20) + 4321), synth.mixed(17 * (1 << 20))])
+    plans = {"uneven": dict(B2RC_PIPE_MIN_CHUNK=1 << 20), "equal": dict(B2RC_PIPE_MIN_CHUNK=1 << 20, B2RC_PIPE_RAMP=0),
+             "seven": dict(B2RC_PIPE_MIN_CHUNK=1 << 20, B2RC_PIPE_CHUNKS=7), "one": {}}
+    ctxs = {k: make_ctx(**v) for k, v in plans.items()}
+    try:
+        for block in (65536, 4096):
+            ref, used = ctxs["one"].encode_device(mode, torch.from_numpy(data).cuda(), block=block)
+            ref = ref[:used].cpu().numpy()
+            for name, ctx in ctxs.items():
+                ctx.force_restart(ctxs["one"].restart_for(mode, block, container.nblocks_of(data.size, block)))
+                enc = ctx.encode(mode, data, block)
+                assert enc.tobytes() == ref.tobytes(), (name, block)
+                assert ctx.decode(enc).tobytes() == data.tobytes(), (name, block)
+    finally:
+        for ctx in ctxs.values():
+            ctx.close()
+
+
 def test_every_alignment_of_the_payloads(oracle):
     """Payload offsets take every residue mod 4 (sizes are data dependent); a canary behind the
     container stays intact and the bound is respected."""
