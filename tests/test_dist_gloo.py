@@ -49,7 +49,11 @@ def _worker(rank, world, port, n_total, block, mode, out_dir):
         data = synth.kennedy(n_total)
         lo, hi, blk_lo, blk_hi = rcdist.shard_of(n_total, block, rank, world)
         ctx = OracleCtx()
-        shard = rcdist.encode_shard(ctx, mode, torch.from_numpy(data[lo:hi].copy()), n_total, block)
+        # odd ranks leave the collective for later (what bench.py does: the decode of a rank's own blocks is launched
+        # first); it starts at the first use of the index, and every rank gets there
+        shard = rcdist.encode_shard(ctx, mode, torch.from_numpy(data[lo:hi].copy()), n_total, block,
+                                    defer_gather=bool(rank & 1))
+        assert (shard.gather is None) == bool(rank & 1)
         assert shard.nblocks == blk_hi - blk_lo
         # every rank must now hold the same, complete index
         gathered = [None] * world
