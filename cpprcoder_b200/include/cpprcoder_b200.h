@@ -33,6 +33,9 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include "../../include/b2rc.h"
 
@@ -97,6 +100,28 @@ private:
 // Growable memory buffer with the reference's conventions (cpprcoder.h:185-247, :964-1077):
 // capacity rounded up to 16, write() grows (x2 below 16 KiB, +16 KiB above), writeByte()
 // never grows, reserve() discards, size() is both cursors.
+namespace detail
+{
+// malloc for a stream's buffer.  A buffer of many megabytes is fresh memory from the kernel, and the first write to
+// every 4 KiB page of it is a page fault (a quarter of a million of them for a 1 GiB stream): ask for huge pages where
+// the system hands them out on request (transparent huge pages in "madvise" mode; nothing happens elsewhere).
+inline u8* big_malloc(size_t bytes)
+{
+    u8* p = static_cast<u8*>(::malloc(bytes));
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    const size_t huge = size_t(2) << 20;
+    if(p && bytes >= 4 * huge) {
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(p) + huge - 1) & ~(uintptr_t)(huge - 1);
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(p) + bytes) & ~(uintptr_t)(huge - 1);
+        if(hi > lo) {
+            ::madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
+        }
+    }
+#endif
+    return p;
+}
+}  // namespace detail
+
 class MemoryStream : public IStream<MemoryStream>
 {
 public:
@@ -104,7 +129,7 @@ public:
     explicit MemoryStream(s32 capacity) : capacity_(capacity), size_(0)
     {
         capacity_ = (capacity_ <= 0) ? 16 : static_cast<s32>((static_cast<u32>(capacity_) + 15U) & ~15U);
-        buffer_ = static_cast<u8*>(::malloc(static_cast<size_t>(capacity_)));
+        buffer_ = detail::big_malloc(static_cast<size_t>(capacity_));
     }
     ~MemoryStream() { ::free(buffer_); }
 
@@ -130,7 +155,7 @@ public:
         }
         ::free(buffer_);
         capacity_ = capacity;
-        buffer_ = static_cast<u8*>(::malloc(static_cast<size_t>(capacity_)));
+        buffer_ = detail::big_malloc(static_cast<size_t>(capacity_));
     }
     void resize(s32 size)
     {
@@ -197,7 +222,7 @@ private:
             }
         } while(capacity < size);
         capacity = static_cast<s32>((static_cast<u32>(capacity) + 15U) & ~15U);
-        u8* grown = static_cast<u8*>(::malloc(static_cast<size_t>(capacity)));
+        u8* grown = detail::big_malloc(static_cast<size_t>(capacity));
         if(CPPRCODER_NULL == grown) {
             return false;
         }
