@@ -1433,13 +1433,17 @@ struct Chunks {
 // (Cutting b2rc_encode's input into 32 chunks instead of 16 was tried -- copies alone in the pipeline's shape get
 // faster with more chunks one way (1 GiB in, 0.79 GiB home: 23.5 / 22.5 / 21.8 ms for 16 / 32 / 64) and slower the
 // other (23.8 / 24.1 / 24.8), tools/e2e_phases.py -- and changed nothing once the kernels sit between the copies.)
-Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block)
+// `coarse`: a pageable source is moved into pinned staging chunk by chunk by the host's threads (b2rc_host_copy), and
+// that copy is the call's bottleneck: six long chunks keep every thread busy on each (1 GiB through MemoryStream,
+// tools/e2e_cpp: 64 + 63 ms with six chunks, 86 + 78 ms with sixteen).
+Chunks plan_chunks(const b2rc_ctx* ctx, u64 n, u32 block, bool coarse = false)
 {
     Chunks ch;
     ch.nb = b2rc_nblocks(n, block);
     u64 count = n / ctx->min_chunk;
-    if(count > ctx->max_chunks) {
-        count = ctx->max_chunks;
+    const u64 most = (coarse && ctx->max_chunks > 6) ? 6 : ctx->max_chunks;
+    if(count > most) {
+        count = most;
     }
     if(count < 1) {
         count = 1;
@@ -1555,7 +1559,8 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     }
     DeviceGuard g(ctx->device);
     const u64 bound = b2rc_bound(mode, n, block_size);
-    const Chunks ch = plan_chunks(ctx, n, block_size);
+    const bool stage_src = n >= (16ull << 20) && is_pageable(src);
+    const Chunks ch = plan_chunks(ctx, n, block_size, stage_src);
     const u64 nb = ch.nb;
     const u64 idx = index_bytes(nb);
     if(out_n) {
@@ -1585,7 +1590,6 @@ int b2rc_encode(b2rc_ctx* ctx, int mode, uint32_t block_size, const uint8_t* src
     u8* d_payload = ctx->stage_out + idx;
     u64* d_offsets = reinterpret_cast<u64*>(ctx->stage_out + B2RC_HEADER_BYTES);
     cudaStream_t s0 = ctx->pipe[0];
-    const bool stage_src = n >= (16ull << 20) && is_pageable(src);
     if(stage_src && (rc = grow_host(ctx, ctx->h_in, ctx->h_in_cap, (size_t)n + 16)) != B2RC_OK) {
         return rc;
     }
@@ -1752,8 +1756,8 @@ int b2rc_decode(b2rc_ctx* ctx, const uint8_t* src, uint64_t n, uint8_t* dst, uin
        (seg && (rc = grow(ctx, ctx->restart, ctx->restart_cap, (size_t)(table_bytes + 16))) != B2RC_OK)) {
         return rc;
     }
-    const Chunks ch = plan_chunks(ctx, total, block);
     const bool stage_src = n >= (16ull << 20) && is_pageable(src);
+    const Chunks ch = plan_chunks(ctx, total, block, stage_src);
     if(stage_src && (rc = grow_host(ctx, ctx->h_in, ctx->h_in_cap, (size_t)n + 16)) != B2RC_OK) {
         return rc;
     }
