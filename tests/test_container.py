@@ -58,3 +58,24 @@ def test_restart_table_framing():
     bad[6] = 1                                         # adaptive mode with a restart table
     with pytest.raises(ValueError):
         container.parse(bad)
+
+
+def test_adaptive_restart_points_carry_the_model():
+    # the adaptive coder's points: 3 words + 256 counts -- u16 pairs (131 words) for blocks of at most 65536 bytes,
+    # u32 (259 words) above
+    for block, seg, per in ((65536, 21888, 131), (131072, 43712, 259), (1 << 20, 43712, 259)):
+        nb = 2
+        total = block + 17
+        nrec = container.restart_records(block, seg)
+        assert nrec == -(-block // seg) - 1
+        pays = [b"abcde", b"fg"]
+        plain = container.build(1, block, total, pays)
+        body = plain[32 + 8 * (nb + 1):].tobytes()
+        table = np.arange(nb * nrec * per, dtype=np.uint32)
+        buf = np.frombuffer(container.pack_header(1, block, total, nb, seg) + plain[32:32 + 8 * (nb + 1)].tobytes() + body
+                            + bytes(-len(body) % 4) + table.tobytes(), dtype=np.uint8)
+        info = container.parse(buf)
+        assert info.seg_syms == seg and info.restart.shape == (nb, nrec, per)
+        assert (info.restart.reshape(-1) == table).all()
+        with pytest.raises(ValueError):
+            container.parse(buf[:-4])
